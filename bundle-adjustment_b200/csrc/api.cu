@@ -1,0 +1,967 @@
+// api.cu -- C ABI (include/jaicov_b200.h) and the device-resident adjustment loop.
+//
+// Restates the control flow of BundleAdjustment.estimateModel() (BundleAdjustment.java:203-387) around the CUDA
+// stages; the Java host keeps the integer bookkeeping (prepareUnknownParameters :667-782, detectRankDefect
+// :836-1042) and hands over flat arrays.  No CPU compute path exists here: without a usable sm_100 device every
+// computing entry point fails with JAICOV_NOT_INITIALISED.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "dense_driver.hpp"
+
+namespace jaicov {
+
+long long g_launch_count = 0;
+
+// dense_kernels.cu
+void launch_gemm(const GemmDesc &g, cudaStream_t s);
+void launch_potrf_diag(double *A, int64_t ld, double *dinv, int row0, int *info, cudaStream_t s);
+void launch_copy2d(double *dst, int64_t ldd, const double *src, int64_t lds, int64_t rows, int64_t cols, cudaStream_t s);
+// stage_kernels.cu
+void launch_precond_diag(const double *M, int64_t ld, int u, int64_t np, double *V, cudaStream_t s);
+void launch_datum_rows(const double *xyz, const int32_t *pt_col, const int32_t *datum_pts, int nDatum, int free_mask, int d,
+                       int64_t np, double *Bt, cudaStream_t s);
+void launch_scale_system(double *M, int64_t ld, int u, const double *V, const double *Bt, int d, int64_t np, cudaStream_t s);
+void launch_build_rhs(double *Rt, double *Btv, int64_t np, int u, const double *V, const double *rhs, const double *Bt, int d,
+                      int simulation, cudaStream_t s);
+void launch_datum_solve(const double *Xt, const double *Btv, int d, int64_t np, int u, const double *V, double *dxref, double *H,
+                        double *Tq, double *small, cudaStream_t s);
+void launch_qxx_epilogue(double *M, int64_t ld, int u, const double *V, const double *H, const double *G, int d, int64_t np,
+                         cudaStream_t s);
+void launch_update(double *val, const int32_t *col, int64_t n, const double *dxref, int apply, unsigned long long *out,
+                   cudaStream_t s);
+void launch_pack_columns(const double *lower, int64_t ld, const double *border, int64_t np, const double *q11, int d, int64_t c0,
+                         int64_t c1, double *out, cudaStream_t s);
+void launch_get_block(const double *lower, int64_t ld, const double *border, int64_t np, const double *q11, int d, int r0, int r1,
+                      int c0, int c1, double *out, cudaStream_t s);
+void launch_group_w(int r, const double *const *tptr, const double *obs, double *w, cudaStream_t s);
+void launch_group_stack(int r, const int32_t *col, const double *var, const double *Pw, int64_t ldp, double sigma2, const double *w,
+                        int d, int64_t ld, double *M, double *rhs, cudaStream_t s);
+void launch_group_omega(int r, const int32_t *col, const double *var, const double *Pw, int64_t ldp, double sigma2, const double *w,
+                        const double *dxref, double *out, cudaStream_t s);
+void launch_unpack_scaled(const double *ap, int r, double scale, double *M, int64_t ld, int64_t np, cudaStream_t s);
+void launch_symmetrize(double *M, int64_t ld, int r, cudaStream_t s);
+
+struct CudaBackend {
+    cudaStream_t stream;
+    int *info;
+    void gemm(const GemmDesc &g) { launch_gemm(g, stream); }
+    void potrf_diag(double *a, int64_t ld, double *dinv, int row0) { launch_potrf_diag(a, ld, dinv, row0, info, stream); }
+    void copy2d(double *dst, int64_t ldd, const double *src, int64_t lds, int64_t rows, int64_t cols) {
+        launch_copy2d(dst, ldd, src, lds, rows, cols, stream);
+    }
+};
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) JCHECK(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void upload(const std::vector<T> &h) {
+        alloc(h.size());
+        if (!h.empty()) JCHECK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+};
+
+struct Group {
+    int r = 0;
+    std::vector<int32_t> kind, index, comp;
+    std::vector<double> obs, var, sigma;   // sigma: packed upper dispersion (may be empty)
+    DevBuf<const double *> tptr;
+    DevBuf<int32_t> col;
+    DevBuf<double> d_obs, d_var, w, Pw;
+    int64_t ldp = 0;
+};
+
+static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+}  // namespace jaicov
+
+using namespace jaicov;
+
+struct jaicov_handle {
+    jaicov_options opt{};
+    std::string err;
+    // host copies of the flattened object graph
+    std::vector<double> io_val, r0, coef_val, eo_val, xy, var, rho, xyz, bar_len, bar_var;
+    std::vector<int32_t> io_col, coef_ptr, coef_type, coef_order, coef_col, cam_of_img, eo_col, obj_idx, pt_col, bar_a, bar_b;
+    std::vector<int64_t> pt_ptr;
+    std::vector<uint8_t> is_datum;
+    std::vector<Group> groups;
+    int free_flags[7] = {0, 0, 0, 0, 0, 0, 0};
+    int n_unknowns = -1, n_observations = 0;
+    bool has_datum_call = false;
+    // device
+    DevProblem P;
+    AssemblyScratch S;
+    DevBuf<double> d_io_val, d_r0, d_coef_val, d_zern_c, d_eo_val, d_pose, d_xy, d_var, d_rho, d_xyz, d_bar_len, d_bar_var;
+    DevBuf<int32_t> d_io_col, d_coef_ptr, d_coef_type, d_coef_order, d_coef_col, d_zern_m, d_zern_ptr, d_zern_p, d_cam_kbase,
+        d_campos_col, d_cam_of_img, d_eo_col, d_obj_idx, d_img_of_obs, d_pt_col, d_bar_a, d_bar_b, d_img_work_ptr, d_datum_pts;
+    DevBuf<int64_t> d_pt_ptr, d_pt_obs_ptr, d_pt_obs;
+    DevBuf<WorkItem> d_work;
+    DevBuf<double> d_img_partial, d_cam_partial, d_pt_partial, d_omega_partial;
+    DevBuf<double> M, W, Dinv, rhs, V, Bt, Btv, Rt, H, Tq, small, dxref, omega_parts;
+    DevBuf<int> info;
+    DevBuf<unsigned long long> upd;
+    int nDatumPts = 0, free_mask = 0;
+    bool prepared = false, have_qxx = false, have_neq = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    jaicov_stats stats{};
+    double centroid[3] = {0, 0, 0};
+};
+
+namespace {
+
+int fail(jaicov_handle *h, int code, const std::string &msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+int usable_devices() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; i++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ok++;
+    }
+    return ok;
+}
+
+#define API_GUARD_BEGIN try {
+#define API_GUARD_END(h)                                                                                      \
+    }                                                                                                         \
+    catch (const CudaError &e) {                                                                              \
+        char buf[512];                                                                                        \
+        snprintf(buf, sizeof buf, "CUDA error %d (%s) in %s at %s:%d", (int)e.code, cudaGetErrorString(e.code), e.what, e.file, e.line); \
+        cudaGetLastError();                                                                                   \
+        return fail(h, e.code == cudaErrorMemoryAllocation ? JAICOV_OUT_OF_MEMORY : JAICOV_NOT_INITIALISED, buf); \
+    }                                                                                                         \
+    catch (const std::bad_alloc &) { return fail(h, JAICOV_OUT_OF_MEMORY, "host allocation failed"); }        \
+    catch (const std::exception &e) { return fail(h, JAICOV_ILLEGAL_ARGUMENT, e.what()); }
+
+bool active(int32_t c) { return c >= 0 && c != JAICOV_COL_FIXED; }
+
+// MathExtension.binomial, MathExtension.java:53-64
+long long binomial(int n, int k) {
+    if (k < 0 || k > n) return 0;
+    if (k > n - k) k = n - k;
+    long long r = 1;
+    for (int i = 1; i <= k; i++) r = r * (n - k + i) / i;
+    return r;
+}
+
+// Zernike radial terms of coefficient index j (ZernikeCoefficient.ZernikePolynomial, parameter/ZernikeCoefficient.java:40-56)
+void zernike_terms(int order, int &m, std::vector<int32_t> &p, std::vector<double> &c) {
+    const int n = (int)std::ceil((-3 + std::sqrt((double)(9 + 8 * order))) / 2);
+    m = 2 * order - n * (n + 2);
+    const int halfnm = (n - std::abs(m)) / 2;
+    const double length = std::sqrt((double)((1 + ((m != 0) ? 1 : 0)) * (n + 1)) / 3.14159265358979323846);
+    for (int k = 0; k <= halfnm; k++) {
+        p.push_back(n - 2 * k);
+        c.push_back(length * (double)(((k % 2 == 0) ? 1 : -1) * binomial(n - k, k) * binomial(n - 2 * k, halfnm - k)));
+    }
+}
+
+void prepare(jaicov_handle *h) {
+    if (h->prepared) return;
+    if (usable_devices() == 0) throw CudaError{cudaErrorNoDevice, "no sm_100 device: jaicov_b200 has no CPU path", __FILE__, __LINE__};
+    JCHECK(cudaSetDevice(h->opt.device));
+    if (!h->stream) {
+        JCHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        for (auto &e : h->ev) JCHECK(cudaEventCreate(&e));
+    }
+    if (!h->has_datum_call || h->n_unknowns < 0) throw std::runtime_error("jaicov_set_datum has not been called");
+    DevProblem &P = h->P;
+    P = DevProblem();
+    int d = 0, mask = 0;
+    for (int i = 0; i < 7; i++) if (h->free_flags[i]) { d++; mask |= 1 << i; }
+    h->free_mask = mask;
+    P.d = d;
+    P.u = h->n_unknowns;
+    P.np = round_up(std::max(P.u, 1), kBlk);
+    P.sigma2 = h->opt.sigma2apriori > 0 ? h->opt.sigma2apriori : 1.0;   // BA:221
+    // ---- cameras -----------------------------------------------------------------------------------------------
+    P.nCam = (int)h->r0.size();
+    P.nCoef = (int)h->coef_val.size();
+    if (h->coef_ptr.empty()) h->coef_ptr.assign(1, 0);
+    std::vector<int32_t> zm(P.nCoef, 0), zptr(P.nCoef + 1, 0), zp;
+    std::vector<double> zc;
+    int maxcoef = 0;
+    for (int k = 0; k < P.nCoef; k++) {
+        zptr[k] = (int32_t)zp.size();
+        const int t = h->coef_type[k];
+        if (t == JAICOV_PT_ZERNIKE_X || t == JAICOV_PT_ZERNIKE_Y || t == JAICOV_PT_ZERNIKE_Z) {
+            int m;
+            zernike_terms(h->coef_order[k], m, zp, zc);
+            zm[k] = m;
+        }
+    }
+    zptr[P.nCoef] = (int32_t)zp.size();
+    if (zp.empty()) { zp.push_back(0); zc.push_back(0.0); }
+    std::vector<int32_t> kbase(P.nCam + 1, 0), campos;
+    for (int c = 0; c < P.nCam; c++) {
+        const int nc = h->coef_ptr[c + 1] - h->coef_ptr[c];
+        if (nc > kMaxCoef) throw std::runtime_error("more than 64 distortion coefficients per camera are not supported");
+        maxcoef = std::max(maxcoef, nc);
+        kbase[c + 1] = kbase[c] + 3 + nc;
+        for (int i = 0; i < 3; i++) campos.push_back(h->io_col[3 * c + i]);
+        for (int k = h->coef_ptr[c]; k < h->coef_ptr[c + 1]; k++) campos.push_back(h->coef_col[k]);
+    }
+    P.kRaw = kbase[P.nCam];
+    h->S = AssemblyScratch();
+    h->S.ntImg = (9 + maxcoef + 1 + 7) / 8;
+    h->S.ntPt = (3 + P.kRaw + 1 + 7) / 8;
+    h->S.kcMax = 3 + maxcoef;
+    if (h->S.ntPt > 8) throw std::runtime_error("too many camera parameters in total (by-point Gram limited to 64 columns)");
+    // ---- images / observations -----------------------------------------------------------------------------------
+    P.nImg = (int)h->cam_of_img.size();
+    P.m = (int64_t)h->obj_idx.size();
+    if (h->pt_ptr.empty()) h->pt_ptr.assign(1, 0);
+    if (h->pt_ptr.back() != P.m) throw std::runtime_error("pt_ptr does not cover the image points");
+    P.nPt = (int)(h->xyz.size() / 3);
+    std::vector<int32_t> img_of_obs(P.m);
+    std::vector<WorkItem> work;
+    std::vector<int32_t> img_work_ptr(P.nImg + 1, 0);
+    const int64_t chunk = 1024;
+    for (int i = 0; i < P.nImg; i++) {
+        img_work_ptr[i] = (int32_t)work.size();
+        for (int64_t j = h->pt_ptr[i]; j < h->pt_ptr[i + 1]; j++) img_of_obs[j] = i;
+        for (int64_t b = h->pt_ptr[i]; b < h->pt_ptr[i + 1]; b += chunk)
+            work.push_back(WorkItem{i, 0, b, std::min(b + chunk, h->pt_ptr[i + 1])});
+    }
+    img_work_ptr[P.nImg] = (int32_t)work.size();
+    std::vector<int64_t> pt_obs_ptr(P.nPt + 1, 0), pt_obs(P.m);
+    for (int64_t j = 0; j < P.m; j++) {
+        if (h->obj_idx[j] < 0 || h->obj_idx[j] >= P.nPt) throw std::runtime_error("object point index out of range");
+        pt_obs_ptr[h->obj_idx[j] + 1]++;
+    }
+    for (int p = 0; p < P.nPt; p++) pt_obs_ptr[p + 1] += pt_obs_ptr[p];
+    {
+        std::vector<int64_t> cur(pt_obs_ptr.begin(), pt_obs_ptr.end() - 1);
+        for (int64_t j = 0; j < P.m; j++) pt_obs[cur[h->obj_idx[j]]++] = j;
+    }
+    // ---- validate columns ----------------------------------------------------------------------------------------
+    auto check_cols = [&](const std::vector<int32_t> &c) {
+        for (int32_t x : c)
+            if (active(x) && (x < d || x >= P.u + d)) throw std::runtime_error("column index outside [d, u+d)");
+    };
+    check_cols(h->io_col); check_cols(h->coef_col); check_cols(h->eo_col); check_cols(h->pt_col);
+    // datum points: isDatum and no fixed component (BA:501-513)
+    std::vector<int32_t> datum_pts;
+    for (int p = 0; p < P.nPt; p++) {
+        if (!h->is_datum.empty() && !h->is_datum[p]) continue;
+        if (h->is_datum.empty()) continue;
+        const int32_t *c = &h->pt_col[3 * (size_t)p];
+        if (c[0] == JAICOV_COL_FIXED || c[1] == JAICOV_COL_FIXED || c[2] == JAICOV_COL_FIXED) continue;
+        if (!active(c[0]) || !active(c[1]) || !active(c[2])) continue;
+        datum_pts.push_back(p);
+    }
+    h->nDatumPts = (int)datum_pts.size();
+    if (d > 0 && h->nDatumPts < 3) throw std::runtime_error("not enough object points to realise the frame datum (BA:515-516)");
+    // ---- upload --------------------------------------------------------------------------------------------------
+    h->d_io_val.upload(h->io_val); h->d_io_col.upload(h->io_col); h->d_r0.upload(h->r0);
+    h->d_coef_ptr.upload(h->coef_ptr); h->d_coef_type.upload(h->coef_type); h->d_coef_order.upload(h->coef_order);
+    h->d_coef_val.upload(h->coef_val); h->d_coef_col.upload(h->coef_col);
+    h->d_zern_m.upload(zm); h->d_zern_ptr.upload(zptr); h->d_zern_p.upload(zp); h->d_zern_c.upload(zc);
+    h->d_cam_kbase.upload(kbase); h->d_campos_col.upload(campos);
+    h->d_cam_of_img.upload(h->cam_of_img); h->d_eo_val.upload(h->eo_val); h->d_eo_col.upload(h->eo_col);
+    h->d_pt_ptr.upload(h->pt_ptr); h->d_pose.alloc((size_t)std::max(P.nImg, 1) * 16);
+    h->d_obj_idx.upload(h->obj_idx); h->d_xy.upload(h->xy); h->d_var.upload(h->var); h->d_rho.upload(h->rho);
+    h->d_img_of_obs.upload(img_of_obs); h->d_pt_obs_ptr.upload(pt_obs_ptr); h->d_pt_obs.upload(pt_obs);
+    h->d_xyz.upload(h->xyz); h->d_pt_col.upload(h->pt_col);
+    h->d_bar_a.upload(h->bar_a); h->d_bar_b.upload(h->bar_b); h->d_bar_len.upload(h->bar_len); h->d_bar_var.upload(h->bar_var);
+    h->d_work.upload(work); h->d_img_work_ptr.upload(img_work_ptr); h->d_datum_pts.upload(datum_pts);
+    P.io_val = h->d_io_val.p; P.io_col = h->d_io_col.p; P.r0 = h->d_r0.p; P.coef_ptr = h->d_coef_ptr.p;
+    P.coef_type = h->d_coef_type.p; P.coef_order = h->d_coef_order.p; P.coef_col = h->d_coef_col.p; P.coef_val = h->d_coef_val.p;
+    P.zern_m = h->d_zern_m.p; P.zern_ptr = h->d_zern_ptr.p; P.zern_p = h->d_zern_p.p; P.zern_c = h->d_zern_c.p;
+    P.cam_kbase = h->d_cam_kbase.p; P.campos_col = h->d_campos_col.p;
+    P.cam_of_img = h->d_cam_of_img.p; P.eo_val = h->d_eo_val.p; P.eo_col = h->d_eo_col.p; P.pt_ptr = h->d_pt_ptr.p;
+    P.pose = h->d_pose.p; P.obj_idx = h->d_obj_idx.p; P.xy = h->d_xy.p; P.var = h->d_var.p; P.rho = h->d_rho.p;
+    P.img_of_obs = h->d_img_of_obs.p; P.pt_obs_ptr = h->d_pt_obs_ptr.p; P.pt_obs = h->d_pt_obs.p;
+    P.xyz = h->d_xyz.p; P.pt_col = h->d_pt_col.p;
+    P.nBar = (int)h->bar_a.size();
+    P.bar_a = h->d_bar_a.p; P.bar_b = h->d_bar_b.p; P.bar_len = h->d_bar_len.p; P.bar_var = h->d_bar_var.p;
+    AssemblyScratch &S = h->S;
+    S.nWork = (int)work.size();
+    S.work = h->d_work.p; S.img_work_ptr = h->d_img_work_ptr.p;
+    const int NCi = 8 * S.ntImg, NCp = 8 * S.ntPt;
+    h->d_img_partial.alloc((size_t)std::max(S.nWork, 1) * NCi * NCi);
+    h->d_cam_partial.alloc((size_t)std::max(P.nImg, 1) * S.kcMax * (S.kcMax + 1));
+    h->d_pt_partial.alloc((size_t)std::max(P.nPt, 1) * 3 * NCp);
+    S.omegaBlocks = (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (P.m + 255) / 256));
+    h->d_omega_partial.alloc(S.omegaBlocks + 2);
+    S.img_partial = h->d_img_partial.p; S.cam_partial = h->d_cam_partial.p; S.pt_partial = h->d_pt_partial.p;
+    S.omega_partial = h->d_omega_partial.p;
+    // ---- system buffers ------------------------------------------------------------------------------------------
+    const size_t np = (size_t)P.np;
+    h->M.alloc(np * np);
+    if (h->opt.invert_mode == JAICOV_INVERT_FULL) h->W.alloc(np * np);
+    h->Dinv.alloc(np * kBlk);
+    h->rhs.alloc(np); h->V.alloc(np);
+    h->Bt.alloc(8 * np); h->Btv.alloc(8 * np); h->H.alloc(8 * np); h->Tq.alloc(8 * np);
+    h->Rt.alloc((size_t)kRhsRows * np);
+    h->small.alloc(128); h->dxref.alloc(np + 8); h->omega_parts.alloc(4 + h->groups.size());
+    h->info.alloc(1); h->upd.alloc(2);
+    JCHECK(cudaMemset(h->dxref.p, 0, (np + 8) * sizeof(double)));
+    // ---- directly observed groups ----------------------------------------------------------------------------------
+    int gi = 0;
+    for (Group &g : h->groups) {
+        std::vector<const double *> tp(g.r);
+        std::vector<int32_t> col(g.r);
+        for (int i = 0; i < g.r; i++) {
+            const int k = g.kind[i], ix = g.index[i], cp = g.comp[i];
+            if (k == 0) { tp[i] = P.xyz + 3 * (size_t)ix + cp; col[i] = h->pt_col.at(3 * (size_t)ix + cp); }
+            else if (k == 1) { tp[i] = P.io_val + 3 * (size_t)ix + cp; col[i] = h->io_col.at(3 * (size_t)ix + cp); }
+            else if (k == 2) { tp[i] = P.coef_val + ix; col[i] = h->coef_col.at(ix); }
+            else if (k == 3) { tp[i] = P.eo_val + 6 * (size_t)ix + cp; col[i] = h->eo_col.at(6 * (size_t)ix + cp); }
+            else throw std::runtime_error("unknown target kind in observed group");
+        }
+        g.tptr.upload(tp); g.col.upload(col); g.d_obs.upload(g.obs); g.w.alloc(g.r);
+        if (g.sigma.empty()) {
+            g.d_var.upload(g.var);
+        } else {
+            // P = (Sigma / sigma0^2)^-1 (DOPG:80-90) with the same blocked Cholesky + inverse as the main system
+            const int64_t rp = round_up(g.r, kBlk);
+            DevBuf<double> ap, Wg, Dg;
+            ap.upload(g.sigma);
+            g.Pw.alloc((size_t)rp * rp);
+            Wg.alloc((size_t)rp * rp);
+            Dg.alloc((size_t)rp * kBlk);
+            g.ldp = rp;
+            launch_unpack_scaled(ap.p, g.r, 1.0 / P.sigma2, g.Pw.p, rp, rp, h->stream);
+            JCHECK(cudaMemsetAsync(h->info.p, 0, sizeof(int), h->stream));
+            CudaBackend be{h->stream, h->info.p};
+            DenseSchedule<CudaBackend> ds{be, g.Pw.p, rp, rp, Dg.p};
+            ds.potrf();
+            ds.invert_from_factor(Wg.p);
+            launch_symmetrize(g.Pw.p, rp, g.r, h->stream);
+            int info = 0;
+            JCHECK(cudaMemcpyAsync(&info, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            JCHECK(cudaStreamSynchronize(h->stream));
+            if (info != 0) throw std::runtime_error("dispersion matrix of a directly observed group is not positive definite");
+        }
+        gi++;
+    }
+    (void)gi;
+    h->prepared = true;
+    h->have_qxx = false;
+    h->have_neq = false;
+}
+
+// stages 1-2 of one pass: N, n of the current values in M (lower) / rhs, datum rows in Bt
+void assemble(jaicov_handle *h) {
+    const DevProblem &P = h->P;
+    cudaStream_t s = h->stream;
+    const size_t np = (size_t)P.np;
+    JCHECK(cudaMemsetAsync(h->M.p, 0, np * np * sizeof(double), s));
+    JCHECK(cudaMemsetAsync(h->rhs.p, 0, np * sizeof(double), s));
+    JCHECK(cudaMemsetAsync(h->Bt.p, 0, 8 * np * sizeof(double), s));
+    launch_pose(P, s);
+    launch_assemble(P, h->S, h->M.p, h->rhs.p, s);
+    launch_scale_bars(P, h->M.p, h->rhs.p, s);
+    for (Group &g : h->groups) {
+        launch_group_w(g.r, g.tptr.p, g.d_obs.p, g.w.p, s);
+        launch_group_stack(g.r, g.col.p, g.d_var.p, g.Pw.p, g.ldp, P.sigma2, g.w.p, P.d, P.np, h->M.p, h->rhs.p, s);
+    }
+    if (P.d > 0) launch_datum_rows(P.xyz, P.pt_col, h->d_datum_pts.p, h->nDatumPts, h->free_mask, P.d, P.np, h->Bt.p, s);
+    JCHECK(cudaGetLastError());
+    h->have_neq = true;
+    h->have_qxx = false;
+}
+
+struct PassResult {
+    int info = 0;
+    double max_abs_dx = 0.0;
+    bool bad = false;
+    double omega = 0.0;
+};
+
+PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
+    const DevProblem &P = h->P;
+    cudaStream_t s = h->stream;
+    const size_t np = (size_t)P.np;
+    const bool invert = final_pass && h->opt.invert_mode == JAICOV_INVERT_FULL;
+    JCHECK(cudaEventRecord(h->ev[0], s));
+    assemble(h);
+    // preconditioner and SPD reformulation (K4)
+    launch_precond_diag(h->M.p, P.np, P.u, P.np, h->V.p, s);
+    launch_scale_system(h->M.p, P.np, P.u, h->V.p, h->Bt.p, P.d, P.np, s);
+    JCHECK(cudaMemsetAsync(h->Rt.p, 0, (size_t)kRhsRows * np * sizeof(double), s));
+    launch_build_rhs(h->Rt.p, h->Btv.p, P.np, P.u, h->V.p, h->rhs.p, h->Bt.p, P.d, h->opt.estimation_type == JAICOV_SIMULATION, s);
+    h->have_neq = false;
+    JCHECK(cudaEventRecord(h->ev[1], s));
+    // factor (K5)
+    JCHECK(cudaMemsetAsync(h->info.p, 0, sizeof(int), s));
+    CudaBackend be{s, h->info.p};
+    DenseSchedule<CudaBackend> ds{be, h->M.p, P.np, P.np, h->Dinv.p};
+    ds.potrf();
+    JCHECK(cudaEventRecord(h->ev[2], s));
+    // solve for n and the datum rows, datum correction, dx (K5/K9)
+    ds.solve_rows(h->Rt.p, P.np, 1);
+    launch_datum_solve(h->Rt.p, h->Btv.p, P.d, P.np, P.u, h->V.p, h->dxref.p, h->H.p, h->Tq.p, h->small.p, s);
+    JCHECK(cudaEventRecord(h->ev[3], s));
+    // inverse (K6/K7)
+    if (invert) {
+        ds.invert_from_factor(h->W.p);
+        launch_qxx_epilogue(h->M.p, P.np, P.u, h->V.p, h->H.p, h->Rt.p + np, P.d, P.np, s);
+    }
+    JCHECK(cudaEventRecord(h->ev[4], s));
+    // Omega at the pre-update point (K8), BA:429-430
+    const bool want_omega = final_pass && h->opt.estimation_type != JAICOV_SIMULATION;
+    if (want_omega) {
+        launch_omega(P, h->S, h->dxref.p, h->omega_parts.p, s);
+        if (P.nBar) launch_omega_bars(P, h->dxref.p, h->omega_parts.p + 1, s);
+        int gi = 0;
+        for (Group &g : h->groups) {
+            launch_group_omega(g.r, g.col.p, g.d_var.p, g.Pw.p, g.ldp, P.sigma2, g.w.p, h->dxref.p, h->omega_parts.p + 2 + gi, s);
+            gi++;
+        }
+    }
+    JCHECK(cudaEventRecord(h->ev[5], s));
+    // update + max|dx| (K9), BA:450-462
+    JCHECK(cudaMemsetAsync(h->upd.p, 0, 2 * sizeof(unsigned long long), s));
+    launch_update(P.xyz, P.pt_col, 3 * (int64_t)P.nPt, h->dxref.p, apply_update, h->upd.p, s);
+    launch_update(P.io_val, P.io_col, 3 * (int64_t)P.nCam, h->dxref.p, apply_update, h->upd.p, s);
+    launch_update(P.coef_val, P.coef_col, P.nCoef, h->dxref.p, apply_update, h->upd.p, s);
+    launch_update(P.eo_val, P.eo_col, 6 * (int64_t)P.nImg, h->dxref.p, apply_update, h->upd.p, s);
+    JCHECK(cudaEventRecord(h->ev[6], s));
+    JCHECK(cudaGetLastError());
+    // the one host read per pass: status word, max|dx|, Omega
+    PassResult r;
+    unsigned long long upd[2];
+    std::vector<double> om(2 + h->groups.size(), 0.0);
+    double small99 = 0.0;
+    JCHECK(cudaMemcpyAsync(&r.info, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    JCHECK(cudaMemcpyAsync(upd, h->upd.p, sizeof upd, cudaMemcpyDeviceToHost, s));
+    if (want_omega) JCHECK(cudaMemcpyAsync(om.data(), h->omega_parts.p, om.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (P.d > 0) JCHECK(cudaMemcpyAsync(&small99, h->small.p + 98, sizeof(double), cudaMemcpyDeviceToHost, s));
+    JCHECK(cudaStreamSynchronize(s));
+    if (small99 != 0.0 && r.info == 0) r.info = -1;
+    memcpy(&r.max_abs_dx, &upd[0], sizeof(double));
+    r.bad = upd[1] != 0;
+    if (want_omega) {
+        r.omega = om[0];
+        if (P.nBar) r.omega += om[1];
+        for (size_t g = 0; g < h->groups.size(); g++) r.omega += om[2 + g];
+    }
+    float ms[6];
+    for (int i = 0; i < 6; i++) cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]);
+    h->stats.ms_assembly = ms[0]; h->stats.ms_factor = ms[1]; h->stats.ms_solve = ms[2]; h->stats.ms_inverse = ms[3];
+    h->stats.ms_omega = ms[4];
+    float tot;
+    cudaEventElapsedTime(&tot, h->ev[0], h->ev[6]);
+    h->stats.ms_total = tot;
+    h->have_qxx = invert && r.info == 0;
+    return r;
+}
+
+void download_values(jaicov_handle *h) {
+    const DevProblem &P = h->P;
+    auto dl = [&](std::vector<double> &v, const double *p) {
+        if (!v.empty()) JCHECK(cudaMemcpy(v.data(), p, v.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    };
+    dl(h->xyz, P.xyz); dl(h->io_val, P.io_val); dl(h->coef_val, P.coef_val); dl(h->eo_val, P.eo_val);
+}
+
+void upload_values(jaicov_handle *h) {
+    const DevProblem &P = h->P;
+    auto ul = [&](const std::vector<double> &v, double *p) {
+        if (!v.empty()) JCHECK(cudaMemcpy(p, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice));
+    };
+    ul(h->xyz, P.xyz); ul(h->io_val, P.io_val); ul(h->coef_val, P.coef_val); ul(h->eo_val, P.eo_val);
+    for (Group &g : h->groups)
+        if (g.r) JCHECK(cudaMemcpy(g.d_obs.p, g.obs.data(), g.r * sizeof(double), cudaMemcpyHostToDevice));
+}
+
+// centroidCoordinates (BA:115-201) on the host copies; sign = -1 before the loop, +1 after
+bool centroid_shift(jaicov_handle *h, bool invert) {
+    const size_t nPt = h->xyz.size() / 3, nImg = h->eo_val.size() / 6;
+    if (!invert) {
+        double s[3] = {0, 0, 0};
+        long cnt[3] = {0, 0, 0};
+        for (size_t p = 0; p < nPt; p++)
+            for (int c = 0; c < 3; c++)
+                if (active(h->pt_col[3 * p + c])) { s[c] += h->xyz[3 * p + c]; cnt[c]++; }
+        for (size_t i = 0; i < nImg; i++)
+            for (int c = 0; c < 3; c++)
+                if (active(h->eo_col[6 * i + c])) { s[c] += h->eo_val[6 * i + c]; cnt[c]++; }
+        if (!(cnt[0] == cnt[1] && cnt[0] == cnt[2] && cnt[0] > 0)) return false;
+        for (int c = 0; c < 3; c++) h->centroid[c] = s[c] / (double)cnt[c];
+    }
+    const double sign = invert ? 1.0 : -1.0;
+    for (size_t p = 0; p < nPt; p++)
+        for (int c = 0; c < 3; c++)
+            if (active(h->pt_col[3 * p + c])) h->xyz[3 * p + c] += sign * h->centroid[c];
+    for (size_t i = 0; i < nImg; i++)
+        for (int c = 0; c < 3; c++)
+            if (active(h->eo_col[6 * i + c])) h->eo_val[6 * i + c] += sign * h->centroid[c];
+    for (Group &g : h->groups)
+        for (int i = 0; i < g.r; i++) {
+            if (g.kind[i] == 0) g.obs[i] += sign * h->centroid[g.comp[i]];
+            else if (g.kind[i] == 3 && g.comp[i] < 3) g.obs[i] += sign * h->centroid[g.comp[i]];
+        }
+    return true;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+int32_t jaicov_default_options(jaicov_options *opt) {
+    if (!opt) return JAICOV_ILLEGAL_ARGUMENT;
+    opt->invert_mode = JAICOV_INVERT_FULL;
+    opt->estimation_type = JAICOV_L2NORM;
+    opt->max_iterations = 5000;
+    opt->use_centroid = 1;
+    opt->apply_aposteriori = 1;
+    opt->device = 0;
+    opt->sigma2apriori = 1.0;
+    opt->damping_value = 0.0;
+    return JAICOV_OK;
+}
+
+int32_t jaicov_device_count(void) { return usable_devices(); }
+
+int64_t jaicov_launch_count(void) { return (int64_t)g_launch_count; }
+
+int32_t jaicov_create(const jaicov_options *opt, jaicov_handle **out) {
+    if (!opt || !out) return JAICOV_ILLEGAL_ARGUMENT;
+    *out = nullptr;
+    if (opt->damping_value != 0.0) return JAICOV_ILLEGAL_ARGUMENT;
+    if (opt->invert_mode != JAICOV_INVERT_NONE && opt->invert_mode != JAICOV_INVERT_FULL) return JAICOV_ILLEGAL_ARGUMENT;
+    if (opt->estimation_type != JAICOV_L2NORM && opt->estimation_type != JAICOV_SIMULATION) return JAICOV_ILLEGAL_ARGUMENT;
+    jaicov_handle *h = new (std::nothrow) jaicov_handle();
+    if (!h) return JAICOV_OUT_OF_MEMORY;
+    h->opt = *opt;
+    *out = h;
+    return JAICOV_OK;
+}
+
+void jaicov_destroy(jaicov_handle *h) {
+    if (!h) return;
+    if (h->stream) {
+        cudaSetDevice(h->opt.device);
+        cudaStreamSynchronize(h->stream);
+        for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+        cudaStreamDestroy(h->stream);
+    }
+    delete h;
+}
+
+const char *jaicov_last_error(const jaicov_handle *h) { return h ? h->err.c_str() : "null handle"; }
+
+int32_t jaicov_set_cameras(jaicov_handle *h, int32_t n_cam, const double *io_val, const int32_t *io_col, const double *r0,
+                           const int32_t *coef_ptr, const int32_t *coef_type, const int32_t *coef_order, const double *coef_val,
+                           const int32_t *coef_col) {
+    if (!h || n_cam < 0) return JAICOV_ILLEGAL_ARGUMENT;
+    API_GUARD_BEGIN
+    h->io_val.assign(io_val, io_val + 3 * (size_t)n_cam);
+    h->io_col.assign(io_col, io_col + 3 * (size_t)n_cam);
+    h->r0.assign(r0, r0 + n_cam);
+    h->coef_ptr.assign(coef_ptr, coef_ptr + n_cam + 1);
+    const size_t nc = (size_t)h->coef_ptr[n_cam];
+    h->coef_type.assign(coef_type, coef_type + nc);
+    h->coef_order.assign(coef_order, coef_order + nc);
+    h->coef_val.assign(coef_val, coef_val + nc);
+    h->coef_col.assign(coef_col, coef_col + nc);
+    h->prepared = false;
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+int32_t jaicov_set_images(jaicov_handle *h, int32_t n_img, const int32_t *cam_of_img, const double *eo_val, const int32_t *eo_col,
+                          const int64_t *pt_ptr) {
+    if (!h || n_img < 0) return JAICOV_ILLEGAL_ARGUMENT;
+    API_GUARD_BEGIN
+    h->cam_of_img.assign(cam_of_img, cam_of_img + n_img);
+    h->eo_val.assign(eo_val, eo_val + 6 * (size_t)n_img);
+    h->eo_col.assign(eo_col, eo_col + 6 * (size_t)n_img);
+    h->pt_ptr.assign(pt_ptr, pt_ptr + n_img + 1);
+    h->prepared = false;
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+int32_t jaicov_set_image_points(jaicov_handle *h, int64_t m, const int32_t *obj_idx, const double *xy, const double *var,
+                                const double *rho) {
+    if (!h || m < 0) return JAICOV_ILLEGAL_ARGUMENT;
+    API_GUARD_BEGIN
+    h->obj_idx.assign(obj_idx, obj_idx + m);
+    h->xy.assign(xy, xy + 2 * m);
+    h->var.assign(var, var + 2 * m);
+    if (rho) h->rho.assign(rho, rho + m); else h->rho.assign(m, 0.0);
+    h->prepared = false;
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+int32_t jaicov_set_object_points(jaicov_handle *h, int32_t n_pt, const double *xyz, const int32_t *col, const uint8_t *is_datum) {
+    if (!h || n_pt < 0) return JAICOV_ILLEGAL_ARGUMENT;
+    API_GUARD_BEGIN
+    h->xyz.assign(xyz, xyz + 3 * (size_t)n_pt);
+    h->pt_col.assign(col, col + 3 * (size_t)n_pt);
+    if (is_datum) h->is_datum.assign(is_datum, is_datum + n_pt); else h->is_datum.assign(n_pt, 0);
+    h->prepared = false;
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+int32_t jaicov_set_scale_bars(jaicov_handle *h, int32_t n_bar, const int32_t *a, const int32_t *b, const double *length,
+                              const double *var) {
+    if (!h || n_bar < 0) return JAICOV_ILLEGAL_ARGUMENT;
+    API_GUARD_BEGIN
+    h->bar_a.assign(a, a + n_bar); h->bar_b.assign(b, b + n_bar);
+    h->bar_len.assign(length, length + n_bar); h->bar_var.assign(var, var + n_bar);
+    h->prepared = false;
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+int32_t jaicov_add_observed_group(jaicov_handle *h, int32_t r, const int32_t *target_kind, const int32_t *target_index,
+                                  const int32_t *target_comp, const double *obs, const double *var, const double *sigma_packed_upper) {
+    if (!h || r <= 0 || (!var && !sigma_packed_upper)) return JAICOV_ILLEGAL_ARGUMENT;
+    API_GUARD_BEGIN
+    h->groups.emplace_back();
+    Group &g = h->groups.back();
+    g.r = r;
+    g.kind.assign(target_kind, target_kind + r);
+    g.index.assign(target_index, target_index + r);
+    g.comp.assign(target_comp, target_comp + r);
+    g.obs.assign(obs, obs + r);
+    if (sigma_packed_upper) g.sigma.assign(sigma_packed_upper, sigma_packed_upper + (size_t)r * (r + 1) / 2);
+    else g.var.assign(var, var + r);
+    h->prepared = false;
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+int32_t jaicov_set_datum(jaicov_handle *h, const int32_t free_flags[7], int32_t n_unknowns, int32_t n_observations) {
+    if (!h || !free_flags || n_unknowns < 0) return JAICOV_ILLEGAL_ARGUMENT;
+    for (int i = 0; i < 7; i++) h->free_flags[i] = free_flags[i] != 0;
+    h->n_unknowns = n_unknowns;
+    h->n_observations = n_observations;
+    h->has_datum_call = true;
+    h->prepared = false;
+    return JAICOV_OK;
+}
+
+int32_t jaicov_iterate(jaicov_handle *h, int32_t final_pass, int32_t apply_update) {
+    if (!h) return JAICOV_ILLEGAL_ARGUMENT;
+    API_GUARD_BEGIN
+    prepare(h);
+    JCHECK(cudaSetDevice(h->opt.device));
+    PassResult r = run_pass(h, final_pass != 0, apply_update != 0);
+    h->stats.max_abs_dx = r.max_abs_dx;
+    if (final_pass) h->stats.omega = r.omega;
+    h->stats.iterations++;
+    if (r.info != 0 || r.bad) { h->stats.status = JAICOV_SINGULAR_MATRIX; return JAICOV_SINGULAR_MATRIX; }
+    h->stats.status = JAICOV_OK;
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+int32_t jaicov_estimate(jaicov_handle *h, jaicov_progress_cb cb, void *user, volatile int32_t *interrupt_flag) {
+    if (!h) return JAICOV_ILLEGAL_ARGUMENT;
+    API_GUARD_BEGIN
+    const double SQRT_EPS = std::sqrt(kEps);                 // BA:77
+    auto fire = [&](int st, double a, double b) { if (cb) cb(user, st, a, b); };
+    fire(JAICOV_STATE_BUSY, 0, 1);
+    const int maxIter = h->opt.max_iterations;
+    int runs = maxIter - 1;                                  // BA:213
+    bool isEstimated = false, complete = false, isConverge = true;
+    if (maxIter == 0) complete = isEstimated = true;         // BA:216-219
+    h->prepared = false;                                     // (re)upload the caller's values
+    if (h->opt.use_centroid && !centroid_shift(h, false))
+        return fail(h, JAICOV_ILLEGAL_ARGUMENT, "numbers of coordinate components are un-equal or zero (BA:151)");
+    prepare(h);
+    JCHECK(cudaSetDevice(h->opt.device));
+    upload_values(h);
+    h->stats = jaicov_stats();
+    int status = JAICOV_OK;
+    do {
+        h->stats.iteration_step = maxIter - runs;            // BA:230
+        fire(JAICOV_STATE_ITERATE, maxIter, h->stats.iteration_step);
+        if (interrupt_flag && *interrupt_flag) { *interrupt_flag = 0; status = JAICOV_INTERRUPT; break; }   // BA:240-245
+        complete = isEstimated;                              // BA:250
+        if (complete && h->opt.invert_mode != JAICOV_INVERT_NONE) fire(JAICOV_STATE_INVERT_NORMAL_EQUATION_MATRIX, 0, 1);
+        PassResult r = run_pass(h, complete, true);
+        h->stats.iterations++;
+        if (r.info != 0) { status = JAICOV_SINGULAR_MATRIX; break; }                                        // BA:304-309
+        if (complete) { fire(JAICOV_STATE_ESTIMATE_STOCHASTIC_PARAMETERS, 0, 1); h->stats.omega = r.omega; }
+        h->stats.max_abs_dx = r.max_abs_dx;
+        if (interrupt_flag && *interrupt_flag) { *interrupt_flag = 0; status = JAICOV_INTERRUPT; break; }   // BA:320-325
+        if (r.bad || std::isnan(r.max_abs_dx) || std::isinf(r.max_abs_dx)) { status = JAICOV_SINGULAR_MATRIX; break; }  // BA:327-330
+        else if (r.max_abs_dx <= SQRT_EPS && runs > 0) {     // BA:332-337
+            isEstimated = true;
+            fire(JAICOV_STATE_CONVERGENCE, SQRT_EPS, r.max_abs_dx);
+        } else if (runs-- <= 1) {                            // BA:338-345
+            if (complete) isConverge = false;
+            isEstimated = true;
+        } else {
+            fire(JAICOV_STATE_CONVERGENCE, SQRT_EPS, r.max_abs_dx);
+        }
+    } while (!complete);
+    download_values(h);
+    if (status == JAICOV_OK) {
+        if (h->opt.use_centroid) centroid_shift(h, true);    // BA:357-358
+        status = isConverge ? JAICOV_ERROR_FREE_ESTIMATION : JAICOV_NO_CONVERGENCE;   // BA:377-384
+    }
+    h->prepared = false;   // device values are centred; a later call starts from the host copies
+    h->stats.status = status;
+    return status;
+    API_GUARD_END(h)
+}
+
+int32_t jaicov_get_stats(jaicov_handle *h, jaicov_stats *out) {
+    if (!h || !out) return JAICOV_ILLEGAL_ARGUMENT;
+    int d = 0;
+    for (int i = 0; i < 7; i++) d += h->free_flags[i];
+    h->stats.n_unknowns = h->n_unknowns;
+    h->stats.n_datum = d;
+    h->stats.n_observations = h->n_observations;
+    h->stats.dof = h->n_observations - h->n_unknowns + d;      // BA:1080-1082
+    const double s2 = h->opt.sigma2apriori > 0 ? h->opt.sigma2apriori : 1.0;
+    h->stats.sigma2apriori = s2;
+    // getVarianceFactorAposteriori, BA:1090-1093
+    h->stats.sigma2aposteriori = (h->stats.dof > 0 && h->stats.omega > 0 && h->opt.estimation_type != JAICOV_SIMULATION &&
+                                  h->opt.apply_aposteriori)
+                                     ? std::fabs(h->stats.omega / (double)h->stats.dof)
+                                     : s2;
+    *out = h->stats;
+    return JAICOV_OK;
+}
+
+int32_t jaicov_get_values(jaicov_handle *h, double *xyz, double *io_val, double *coef_val, double *eo_val) {
+    if (!h) return JAICOV_ILLEGAL_ARGUMENT;
+    API_GUARD_BEGIN
+    if (h->prepared) { JCHECK(cudaSetDevice(h->opt.device)); download_values(h); }
+    if (xyz && !h->xyz.empty()) memcpy(xyz, h->xyz.data(), h->xyz.size() * sizeof(double));
+    if (io_val && !h->io_val.empty()) memcpy(io_val, h->io_val.data(), h->io_val.size() * sizeof(double));
+    if (coef_val && !h->coef_val.empty()) memcpy(coef_val, h->coef_val.data(), h->coef_val.size() * sizeof(double));
+    if (eo_val && !h->eo_val.empty()) memcpy(eo_val, h->eo_val.data(), h->eo_val.size() * sizeof(double));
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+int32_t jaicov_get_dx(jaicov_handle *h, double *dx) {
+    if (!h || !dx || !h->dxref.p) return JAICOV_ILLEGAL_ARGUMENT;
+    API_GUARD_BEGIN
+    JCHECK(cudaSetDevice(h->opt.device));
+    JCHECK(cudaMemcpy(dx, h->dxref.p, (size_t)(h->P.u + h->P.d) * sizeof(double), cudaMemcpyDeviceToHost));
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+static int32_t pack_to_host(jaicov_handle *h, const double *border, const double *q11, double *dst) {
+    const DevProblem &P = h->P;
+    const int64_t n = (int64_t)P.u + P.d;
+    const int64_t budget = (int64_t)1 << 25;   // doubles per staging chunk (256 MiB)
+    DevBuf<double> stage[2];
+    int64_t c0 = 0;
+    int which = 0;
+    cudaStream_t s = h->stream;
+    stage[0].alloc((size_t)std::min<int64_t>(budget + n, n * (n + 1) / 2 + 1));
+    stage[1].alloc(stage[0].n);
+    while (c0 < n) {
+        int64_t c1 = c0;
+        int64_t cnt = 0;
+        while (c1 < n && (cnt == 0 || cnt + c1 + 1 <= (int64_t)stage[0].n)) { cnt += c1 + 1; c1++; }
+        launch_pack_columns(h->M.p, P.np, border, P.np, q11, P.d, c0, c1, stage[which].p, s);
+        JCHECK(cudaMemcpyAsync(dst + c0 * (c0 + 1) / 2, stage[which].p, cnt * sizeof(double), cudaMemcpyDeviceToHost, s));
+        which ^= 1;
+        c0 = c1;
+        if (which == 0) JCHECK(cudaStreamSynchronize(s));   // both staging buffers in flight at most
+    }
+    JCHECK(cudaStreamSynchronize(s));
+    return JAICOV_OK;
+}
+
+int32_t jaicov_get_qxx_packed(jaicov_handle *h, double *dst) {
+    if (!h || !dst) return JAICOV_ILLEGAL_ARGUMENT;
+    if (!h->have_qxx) return fail(h, JAICOV_NOT_INITIALISED, "no cofactor matrix: run a final pass with invert_mode FULL");
+    API_GUARD_BEGIN
+    JCHECK(cudaSetDevice(h->opt.device));
+    return pack_to_host(h, h->Tq.p, h->small.p + 49, dst);
+    API_GUARD_END(h)
+}
+
+int32_t jaicov_get_qxx_block(jaicov_handle *h, int32_t r0, int32_t r1, int32_t c0, int32_t c1, double *dst, int64_t ld) {
+    if (!h || !dst) return JAICOV_ILLEGAL_ARGUMENT;
+    if (!h->have_qxx) return fail(h, JAICOV_NOT_INITIALISED, "no cofactor matrix: run a final pass with invert_mode FULL");
+    const int n = h->P.u + h->P.d;
+    if (r0 < 0 || c0 < 0 || r1 > n || c1 > n || r1 < r0 || c1 < c0 || ld < c1 - c0) return JAICOV_ILLEGAL_ARGUMENT;
+    API_GUARD_BEGIN
+    JCHECK(cudaSetDevice(h->opt.device));
+    DevBuf<double> tmp;
+    const int64_t rows_per = std::max<int64_t>(1, ((int64_t)1 << 25) / std::max(1, c1 - c0));
+    tmp.alloc((size_t)std::min<int64_t>(rows_per, std::max(1, r1 - r0)) * std::max(1, c1 - c0));
+    for (int64_t r = r0; r < r1; r += rows_per) {
+        const int rr1 = (int)std::min<int64_t>(r1, r + rows_per);
+        launch_get_block(h->M.p, h->P.np, h->Tq.p, h->P.np, h->small.p + 49, h->P.d, (int)r, rr1, c0, c1, tmp.p, h->stream);
+        JCHECK(cudaMemcpy2DAsync(dst + (r - r0) * ld, ld * sizeof(double), tmp.p, (size_t)(c1 - c0) * sizeof(double),
+                                 (size_t)(c1 - c0) * sizeof(double), rr1 - r, cudaMemcpyDeviceToHost, h->stream));
+        JCHECK(cudaStreamSynchronize(h->stream));
+    }
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+int32_t jaicov_get_qxx_diag(jaicov_handle *h, double *dst) {
+    if (!h || !dst) return JAICOV_ILLEGAL_ARGUMENT;
+    if (!h->have_qxx) return fail(h, JAICOV_NOT_INITIALISED, "no cofactor matrix: run a final pass with invert_mode FULL");
+    API_GUARD_BEGIN
+    JCHECK(cudaSetDevice(h->opt.device));
+    const DevProblem &P = h->P;
+    std::vector<double> small(128);
+    JCHECK(cudaMemcpy(small.data(), h->small.p, 128 * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int a = 0; a < P.d; a++) dst[a] = small[49 + a * kMaxDatum + a];
+    if (P.u)
+        JCHECK(cudaMemcpy2D(dst + P.d, sizeof(double), h->M.p, (size_t)(P.np + 1) * sizeof(double), sizeof(double), P.u,
+                            cudaMemcpyDeviceToHost));
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+int32_t jaicov_eval_residual_jacobian(jaicov_handle *h, int32_t ns_max, double *a, double *w, double *p) {
+    if (!h || !a || !w || !p) return JAICOV_ILLEGAL_ARGUMENT;
+    API_GUARD_BEGIN
+    prepare(h);
+    JCHECK(cudaSetDevice(h->opt.device));
+    const DevProblem &P = h->P;
+    int maxcoef = 0;
+    for (int c = 0; c < P.nCam; c++) maxcoef = std::max(maxcoef, h->coef_ptr[c + 1] - h->coef_ptr[c]);
+    if (ns_max < 12 + maxcoef) return fail(h, JAICOV_ILLEGAL_ARGUMENT, "ns_max too small");
+    DevBuf<double> da, dw, dp;
+    da.alloc((size_t)P.m * 2 * ns_max); dw.alloc((size_t)P.m * 2); dp.alloc((size_t)P.m * 3);
+    launch_pose(P, h->stream);
+    launch_eval_k1(P, ns_max, da.p, dw.p, dp.p, h->stream);
+    JCHECK(cudaGetLastError());
+    JCHECK(cudaStreamSynchronize(h->stream));
+    if (P.m) {
+        JCHECK(cudaMemcpy(a, da.p, da.n * sizeof(double), cudaMemcpyDeviceToHost));
+        JCHECK(cudaMemcpy(w, dw.p, dw.n * sizeof(double), cudaMemcpyDeviceToHost));
+        JCHECK(cudaMemcpy(p, dp.p, dp.n * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+int32_t jaicov_get_normal_equations(jaicov_handle *h, double *n_packed, double *rhs) {
+    if (!h) return JAICOV_ILLEGAL_ARGUMENT;
+    API_GUARD_BEGIN
+    prepare(h);
+    JCHECK(cudaSetDevice(h->opt.device));
+    assemble(h);
+    JCHECK(cudaStreamSynchronize(h->stream));
+    const DevProblem &P = h->P;
+    if (n_packed) pack_to_host(h, h->Bt.p, nullptr, n_packed);
+    if (rhs) {
+        for (int a = 0; a < P.d; a++) rhs[a] = 0.0;
+        if (P.u) JCHECK(cudaMemcpy(rhs + P.d, h->rhs.p, (size_t)P.u * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+int32_t jaicov_omega(jaicov_handle *h, const double *dx, double *omega) {
+    if (!h || !dx || !omega) return JAICOV_ILLEGAL_ARGUMENT;
+    API_GUARD_BEGIN
+    prepare(h);
+    JCHECK(cudaSetDevice(h->opt.device));
+    const DevProblem &P = h->P;
+    cudaStream_t s = h->stream;
+    JCHECK(cudaMemcpy(h->dxref.p, dx, (size_t)(P.u + P.d) * sizeof(double), cudaMemcpyHostToDevice));
+    launch_pose(P, s);
+    launch_omega(P, h->S, h->dxref.p, h->omega_parts.p, s);
+    JCHECK(cudaMemsetAsync(h->omega_parts.p + 1, 0, sizeof(double), s));
+    if (P.nBar) launch_omega_bars(P, h->dxref.p, h->omega_parts.p + 1, s);
+    int gi = 0;
+    for (Group &g : h->groups) {
+        launch_group_w(g.r, g.tptr.p, g.d_obs.p, g.w.p, s);
+        launch_group_omega(g.r, g.col.p, g.d_var.p, g.Pw.p, g.ldp, P.sigma2, g.w.p, h->dxref.p, h->omega_parts.p + 2 + gi, s);
+        gi++;
+    }
+    JCHECK(cudaGetLastError());
+    std::vector<double> om(2 + h->groups.size());
+    JCHECK(cudaMemcpyAsync(om.data(), h->omega_parts.p, om.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    JCHECK(cudaStreamSynchronize(s));
+    double t = 0.0;
+    for (double v : om) t += v;
+    *omega = t;
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+int32_t jaicov_spd_solve_invert(int32_t device, int64_t n, double *a, int32_t nrhs, double *b, int32_t invert, double *ms_factor,
+                                double *ms_inverse) {
+    if (n <= 0 || !a || nrhs < 0 || nrhs > kRhsRows || (nrhs > 0 && !b)) return JAICOV_ILLEGAL_ARGUMENT;
+    jaicov_handle *h = nullptr;
+    API_GUARD_BEGIN
+    if (usable_devices() == 0) return JAICOV_NOT_INITIALISED;
+    JCHECK(cudaSetDevice(device));
+    const int64_t np = round_up(n, kBlk);
+    DevBuf<double> M, W, Dinv, Rt;
+    DevBuf<int> info;
+    M.alloc((size_t)np * np); Dinv.alloc((size_t)np * kBlk); Rt.alloc((size_t)kRhsRows * np); info.alloc(1);
+    if (invert) W.alloc((size_t)np * np);
+    cudaStream_t s;
+    JCHECK(cudaStreamCreate(&s));
+    cudaEvent_t e0, e1, e2, e3;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
+    JCHECK(cudaMemsetAsync(M.p, 0, (size_t)np * np * sizeof(double), s));
+    JCHECK(cudaMemcpy2DAsync(M.p, np * sizeof(double), a, n * sizeof(double), n * sizeof(double), n, cudaMemcpyHostToDevice, s));
+    if (np > n) {   // identity padding
+        std::vector<double> ones(np - n, 1.0);
+        JCHECK(cudaMemcpy2DAsync(M.p + n * np + n, (np + 1) * sizeof(double), ones.data(), sizeof(double), sizeof(double), np - n,
+                                 cudaMemcpyHostToDevice, s));
+        JCHECK(cudaStreamSynchronize(s));
+    }
+    JCHECK(cudaMemsetAsync(Rt.p, 0, (size_t)kRhsRows * np * sizeof(double), s));
+    if (nrhs) JCHECK(cudaMemcpy2DAsync(Rt.p, np * sizeof(double), b, n * sizeof(double), n * sizeof(double), nrhs, cudaMemcpyHostToDevice, s));
+    JCHECK(cudaMemsetAsync(info.p, 0, sizeof(int), s));
+    CudaBackend be{s, info.p};
+    DenseSchedule<CudaBackend> ds{be, M.p, np, np, Dinv.p};
+    cudaEventRecord(e0, s);
+    ds.potrf();
+    cudaEventRecord(e1, s);
+    if (nrhs) ds.solve_rows(Rt.p, np, 1);
+    cudaEventRecord(e2, s);
+    if (invert) { ds.invert_from_factor(W.p); launch_symmetrize(M.p, np, (int)n, s); }
+    cudaEventRecord(e3, s);
+    JCHECK(cudaGetLastError());
+    int hinfo = 0;
+    JCHECK(cudaMemcpyAsync(&hinfo, info.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (invert) JCHECK(cudaMemcpy2DAsync(a, n * sizeof(double), M.p, np * sizeof(double), n * sizeof(double), n, cudaMemcpyDeviceToHost, s));
+    if (nrhs) JCHECK(cudaMemcpy2DAsync(b, n * sizeof(double), Rt.p, np * sizeof(double), n * sizeof(double), nrhs, cudaMemcpyDeviceToHost, s));
+    JCHECK(cudaStreamSynchronize(s));
+    float f1 = 0, f2 = 0;
+    cudaEventElapsedTime(&f1, e0, e1);
+    cudaEventElapsedTime(&f2, e2, e3);
+    if (ms_factor) *ms_factor = f1;
+    if (ms_inverse) *ms_inverse = f2;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+    cudaStreamDestroy(s);
+    return hinfo != 0 ? JAICOV_SINGULAR_MATRIX : JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+}  // extern "C"

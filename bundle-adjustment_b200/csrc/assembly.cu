@@ -1,0 +1,607 @@
+// assembly.cu -- K1/K2/K8 of SURVEY.md section 2.1: residual + Jacobian evaluation, normal-equation assembly
+// N = A'PA, n = A'Pw and Omega = v'Pv, for sm_100a.
+//
+// Reference semantics: PartialDerivativeFactory.getPartialDerivativeImageCoordinate (PDF:285-445) followed by
+// stackNormalEquationSystem (PDF:475-505) for every image point, getPartialDerivativeScaleBar (PDF:210-283),
+// BundleAdjustment.getOmega (BA:472-491).
+//
+// B200 design (nothing here mirrors the Java control flow):
+//  * one thread per image observation evaluates the model (model.cuh) with the camera staged in shared memory;
+//  * a warp's 32 observations are staged as 64 weighted rows R*[A_cam | w] (P = R'R) in a shared-memory tile and
+//    contracted with FP64 tensor-core tiles (mma.sync m8n8k4.f64 -> SASS DMMA): the per-image camera block
+//    [EO | IO | coefficients | w]' P [EO | IO | coefficients | w] is a 64 x NC Gram per warp batch;
+//  * ownership instead of atomics: the EO x point 6x3 block of an observation has exactly one producer and is
+//    stored straight into N; image-level sums go through per-work-item partials that are reduced in a fixed order
+//    (bitwise reproducible); point-level sums (point x point, point x IO, n_point) are produced by a second sweep
+//    with one warp per object point over that point's observations (CSC), again as DMMA tiles;
+//  * the packed per-point / per-camera partial buffers are exactly what an image-sharded multi-GPU run all-reduces.
+#include "common.h"
+#include "model.cuh"
+
+namespace jaicov {
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ bool col_active(int32_t c) { return c >= 0 && c != JAICOV_COL_FIXED; }
+
+// element (r,c) of the symmetric system stored as lower triangle, row-major, internal indices (col - d)
+__device__ __forceinline__ int64_t lower_idx(int64_t a, int64_t b, int64_t ld) {
+    return a >= b ? a * ld + b : b * ld + a;
+}
+
+struct CamSmem {
+    double io[3];
+    double r0;
+    double val[kMaxCoef];
+    int32_t type[kMaxCoef], order[kMaxCoef], zm[kMaxCoef], zptr[kMaxCoef + 1];
+    int32_t ncoef;
+};
+
+__device__ __forceinline__ void load_camera(const DevProblem &P, int cam, CamSmem &s, int tid, int nthreads) {
+    const int c0 = P.coef_ptr[cam], c1 = P.coef_ptr[cam + 1];
+    if (tid < 3) s.io[tid] = P.io_val[3 * cam + tid];
+    if (tid == 3) { s.r0 = P.r0[cam]; s.ncoef = c1 - c0; }
+    for (int k = tid; k < c1 - c0; k += nthreads) {
+        s.val[k] = P.coef_val[c0 + k];
+        s.type[k] = P.coef_type[c0 + k];
+        s.order[k] = P.coef_order[c0 + k];
+        s.zm[k] = P.zern_m[c0 + k];
+    }
+    for (int k = tid; k <= c1 - c0; k += nthreads) s.zptr[k] = P.zern_ptr[c0 + k];
+}
+
+__device__ __forceinline__ CamView view_of(const DevProblem &P, const CamSmem &s) {
+    CamView v;
+    v.io = s.io; v.r0 = s.r0; v.ncoef = s.ncoef; v.type = s.type; v.order = s.order; v.val = s.val;
+    v.zern_m = s.zm; v.zern_ptr = s.zptr; v.zern_p = P.zern_p; v.zern_c = P.zern_c;
+    return v;
+}
+
+__device__ __forceinline__ CamView view_global(const DevProblem &P, int cam) {
+    const int c0 = P.coef_ptr[cam];
+    CamView v;
+    v.io = P.io_val + 3 * cam; v.r0 = P.r0[cam]; v.ncoef = P.coef_ptr[cam + 1] - c0;
+    v.type = P.coef_type + c0; v.order = P.coef_order + c0; v.val = P.coef_val + c0;
+    v.zern_m = P.zern_m + c0; v.zern_ptr = P.zern_ptr + c0; v.zern_p = P.zern_p; v.zern_c = P.zern_c;
+    return v;
+}
+
+__device__ __forceinline__ ImgPose load_pose(const double *pose, int img) {
+    const double *p = pose + (int64_t)img * kPoseStride;
+    ImgPose q;
+    q.r11 = p[0]; q.r12 = p[1]; q.r13 = p[2]; q.r21 = p[3]; q.r22 = p[4]; q.r23 = p[5];
+    q.r31 = p[6]; q.r32 = p[7]; q.r33 = p[8]; q.sinK = p[9]; q.cosK = p[10]; q.X0 = p[11]; q.Y0 = p[12]; q.Z0 = p[13];
+    return q;
+}
+
+// ---- pose table ---------------------------------------------------------------------------------------------------
+__global__ void k_pose(DevProblem P) {
+    int img = blockIdx.x * blockDim.x + threadIdx.x;
+    if (img >= P.nImg) return;
+    ImgPose q = make_pose(P.eo_val + 6 * (int64_t)img);
+    double *p = P.pose + (int64_t)img * kPoseStride;
+    p[0] = q.r11; p[1] = q.r12; p[2] = q.r13; p[3] = q.r21; p[4] = q.r22; p[5] = q.r23;
+    p[6] = q.r31; p[7] = q.r32; p[8] = q.r33; p[9] = q.sinK; p[10] = q.cosK; p[11] = q.X0; p[12] = q.Y0; p[13] = q.Z0;
+    p[14] = 0.0; p[15] = 0.0;
+}
+
+void launch_pose(const DevProblem &P, cudaStream_t s) {
+    if (P.nImg == 0) return;
+    g_launch_count++;
+    k_pose<<<(P.nImg + 127) / 128, 128, 0, s>>>(P);
+}
+
+// ---- K1 materialised (parity / profiling) ---------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_eval_k1(DevProblem P, int ns_max, double *__restrict__ a, double *__restrict__ w,
+                                                  double *__restrict__ p) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.m) return;
+    const int img = P.img_of_obs[j];
+    const int cam = P.cam_of_img[img];
+    const int pt = P.obj_idx[j];
+    const ImgPose q = load_pose(P.pose, img);
+    const CamView cv = view_global(P, cam);
+    double *a0 = a + j * 2 * (int64_t)ns_max, *a1 = a0 + ns_max;
+    const int32_t *ccol = P.coef_col + P.coef_ptr[cam];
+    BaseRows r;
+    eval_observation(q, cv, P.xyz[3 * (int64_t)pt], P.xyz[3 * (int64_t)pt + 1], P.xyz[3 * (int64_t)pt + 2], P.xy[2 * j],
+                     P.xy[2 * j + 1], r, [&](int k, double v0, double v1) {
+                         const bool act = col_active(ccol[k]);
+                         a0[12 + k] = act ? v0 : 0.0;
+                         a1[12 + k] = act ? v1 : 0.0;
+                     });
+    for (int s = 12 + cv.ncoef; s < ns_max; s++) { a0[s] = 0.0; a1[s] = 0.0; }
+    const int32_t *pc = P.pt_col + 3 * (int64_t)pt, *ic = P.io_col + 3 * cam, *ec = P.eo_col + 6 * (int64_t)img;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const bool ap = col_active(pc[i]), ae = col_active(ec[i]), ar = col_active(ec[3 + i]);
+        a0[i] = ap ? r.ax[i] : 0.0;  a1[i] = ap ? r.ay[i] : 0.0;
+        a0[6 + i] = ae ? -r.ax[i] : 0.0;  a1[6 + i] = ae ? -r.ay[i] : 0.0;
+        a0[9 + i] = ar ? r.ax[4 + i] : 0.0;  a1[9 + i] = ar ? r.ay[4 + i] : 0.0;
+    }
+    a0[3] = col_active(ic[0]) ? 1.0 : 0.0;  a1[3] = 0.0;
+    a0[4] = 0.0;  a1[4] = col_active(ic[1]) ? 1.0 : 0.0;
+    a0[5] = col_active(ic[2]) ? r.ax[3] : 0.0;  a1[5] = col_active(ic[2]) ? r.ay[3] : 0.0;
+    w[2 * j] = r.w0;  w[2 * j + 1] = r.w1;
+    double p00, p01, p11;
+    point_weight(P.sigma2, P.var[2 * j], P.var[2 * j + 1], P.rho[j], p00, p01, p11);
+    p[3 * j] = p00;  p[3 * j + 1] = p01;  p[3 * j + 2] = p11;
+}
+
+void launch_eval_k1(const DevProblem &P, int ns_max, double *a, double *w, double *p, cudaStream_t s) {
+    if (P.m == 0) return;
+    g_launch_count++;
+    k_eval_k1<<<(unsigned)((P.m + 127) / 128), 128, 0, s>>>(P, ns_max, a, w, p);
+}
+
+// ---- by-image sweep ---------------------------------------------------------------------------------------------
+// tile columns: 0..5 EO (X0,Y0,Z0,omega,phi,kappa), 6..8 IO (x0,y0,c), 9..9+ncoef-1 coefficients, 9+ncoef = w.
+constexpr int kImgWarps = 4;
+
+template <int NT>
+__global__ void __launch_bounds__(kImgWarps * 32) k_by_image(DevProblem P, const WorkItem *__restrict__ work,
+                                                             double *__restrict__ partial, double *__restrict__ M) {
+    constexpr int LDT = 68;  // tile is stored column-major [NC][68]: == 4 (mod 16) -> conflict-free fragment reads,
+                             // and lanes write consecutive rows of one column -> conflict-free stores
+    constexpr int NC = 8 * NT;
+    extern __shared__ double smem[];
+    __shared__ CamSmem cs;
+    __shared__ int32_t s_eocol[6];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const WorkItem wi = work[blockIdx.x];
+    const int img = wi.img, cam = P.cam_of_img[img];
+    load_camera(P, cam, cs, tid, blockDim.x);
+    if (tid < 6) s_eocol[tid] = P.eo_col[6 * (int64_t)img + tid];
+    double *tile = smem + (size_t)warp * NC * LDT;
+    for (int i = lane; i < NC * LDT; i += 32) tile[i] = 0.0;
+    __syncthreads();
+    const CamView cv = view_of(P, cs);
+    const ImgPose q = load_pose(P.pose, img);
+    const int wcol = 9 + cs.ncoef;
+    const int64_t ld = P.np;
+    const int d = P.d;
+
+    double acc[NT][NT][2];
+#pragma unroll
+    for (int i = 0; i < NT; i++)
+#pragma unroll
+        for (int j = 0; j < NT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // lane l owns tile rows l and l+32; element (row, col) lives at tile[col * LDT + row]
+#define ROW0(c) tile[(c) * LDT + lane]
+#define ROW1(c) tile[(c) * LDT + lane + 32]
+    for (int64_t base = wi.begin + warp * 32; base < wi.end; base += kImgWarps * 32) {
+        const int64_t j = base + lane;
+        if (j < wi.end) {
+            const int pt = P.obj_idx[j];
+            double p00, p01, p11;
+            point_weight(P.sigma2, P.var[2 * j], P.var[2 * j + 1], P.rho[j], p00, p01, p11);
+            // P = R'R, R = [r00 r01; 0 r11]
+            const double r00 = sqrt(p00), r01 = p01 / r00, r11 = sqrt(p11 - r01 * r01);
+            BaseRows r;
+            eval_observation(q, cv, P.xyz[3 * (int64_t)pt], P.xyz[3 * (int64_t)pt + 1], P.xyz[3 * (int64_t)pt + 2],
+                             P.xy[2 * j], P.xy[2 * j + 1], r, [&](int k, double v0, double v1) {
+                                 ROW0(9 + k) = r00 * v0 + r01 * v1;
+                                 ROW1(9 + k) = r11 * v1;
+                             });
+            // weighted base rows
+            double tpx[3], tpy[3], tex[6], tey[6];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                tpx[i] = r00 * r.ax[i] + r01 * r.ay[i];
+                tpy[i] = r11 * r.ay[i];
+                tex[i] = -tpx[i];  tey[i] = -tpy[i];                         // X0,Y0,Z0 = -(X,Y,Z)
+                tex[3 + i] = r00 * r.ax[4 + i] + r01 * r.ay[4 + i];          // omega,phi,kappa
+                tey[3 + i] = r11 * r.ay[4 + i];
+            }
+#pragma unroll
+            for (int e = 0; e < 6; e++) { ROW0(e) = tex[e]; ROW1(e) = tey[e]; }
+            ROW0(6) = r00;  ROW1(6) = 0.0;                                   // x0: (1,0)
+            ROW0(7) = r01;  ROW1(7) = r11;                                   // y0: (0,1)
+            ROW0(8) = r00 * r.ax[3] + r01 * r.ay[3];  ROW1(8) = r11 * r.ay[3];  // c
+            ROW0(wcol) = r00 * r.w0 + r01 * r.w1;  ROW1(wcol) = r11 * r.w1;
+            // EO x point block: single producer -> plain stores
+            const int32_t *pc = P.pt_col + 3 * (int64_t)pt;
+#pragma unroll
+            for (int e = 0; e < 6; e++) {
+                const int32_t ce = s_eocol[e];
+                if (!col_active(ce)) continue;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const int32_t cp = pc[c];
+                    if (!col_active(cp)) continue;
+                    M[lower_idx(ce - d, cp - d, ld)] = tex[e] * tpx[c] + tey[e] * tpy[c];
+                }
+            }
+        } else {
+            for (int i = 0; i <= wcol; i++) { ROW0(i) = 0.0; ROW1(i) = 0.0; }
+        }
+        __syncwarp();
+        // Gram of the 64 x NC tile on FP64 tensor cores
+#pragma unroll 4
+        for (int ks = 0; ks < 16; ks++) {
+            double f[NT];
+            const double *src = tile + (lane >> 2) * LDT + 4 * ks + (lane & 3);
+#pragma unroll
+            for (int b = 0; b < NT; b++) f[b] = src[8 * b * LDT];
+#pragma unroll
+            for (int i = 0; i < NT; i++)
+#pragma unroll
+                for (int jb = 0; jb < NT; jb++) dmma884(acc[i][jb][0], acc[i][jb][1], f[i], f[jb]);
+        }
+        __syncwarp();
+    }
+    // cross-warp reduction in warp order (deterministic)
+    __syncthreads();
+#undef ROW0
+#undef ROW1
+    double *red = smem + (size_t)warp * NC * LDT;  // each warp reuses its own tile: NC*NC <= NC*LDT
+#pragma unroll
+    for (int i = 0; i < NT; i++)
+#pragma unroll
+        for (int jb = 0; jb < NT; jb++) {
+            const int rr = 8 * i + (lane >> 2), cc = 8 * jb + 2 * (lane & 3);
+            red[rr * NC + cc] = acc[i][jb][0];
+            red[rr * NC + cc + 1] = acc[i][jb][1];
+        }
+    __syncthreads();
+    double *out = partial + (size_t)blockIdx.x * NC * NC;
+    for (int i = tid; i < NC * NC; i += blockDim.x) {
+        double s = 0.0;
+#pragma unroll
+        for (int wp = 0; wp < kImgWarps; wp++) s += smem[(size_t)wp * NC * LDT + i];
+        out[i] = s;
+    }
+}
+
+// per image: sum work-item partials (fixed order), scatter EO blocks, hand the camera block to cam_partial
+__global__ void __launch_bounds__(256) k_image_finalize(DevProblem P, AssemblyScratch S, double *__restrict__ M,
+                                                         double *__restrict__ rhs) {
+    extern __shared__ double G[];  // NC*NC
+    const int img = blockIdx.x, tid = threadIdx.x;
+    const int NC = 8 * S.ntImg;
+    const int w0 = S.img_work_ptr[img], w1 = S.img_work_ptr[img + 1];
+    for (int i = tid; i < NC * NC; i += blockDim.x) {
+        double s = 0.0;
+        for (int w = w0; w < w1; w++) s += S.img_partial[(size_t)w * NC * NC + i];
+        G[i] = s;
+    }
+    __syncthreads();
+    const int cam = P.cam_of_img[img];
+    const int ncoef = P.coef_ptr[cam + 1] - P.coef_ptr[cam];
+    const int kc = 3 + ncoef, wcol = 9 + ncoef;
+    const int32_t *ec = P.eo_col + 6 * (int64_t)img;
+    const int32_t *cc = P.campos_col + P.cam_kbase[cam];
+    const int64_t ld = P.np;
+    const int d = P.d;
+    // EO x EO (lower incl. diagonal), EO x camera parameters, rhs of EO
+    for (int i = tid; i < 6 * (6 + kc + 1); i += blockDim.x) {
+        const int e = i / (6 + kc + 1), c = i % (6 + kc + 1);
+        const int32_t ce = ec[e];
+        if (!col_active(ce)) continue;
+        if (c < 6) {
+            if (c > e) continue;
+            const int32_t c2 = ec[c];
+            if (!col_active(c2)) continue;
+            M[lower_idx(ce - d, c2 - d, ld)] += G[e * NC + c];
+        } else if (c < 6 + kc) {
+            const int32_t c2 = cc[c - 6];
+            if (!col_active(c2)) continue;
+            M[lower_idx(ce - d, c2 - d, ld)] += G[e * NC + c];
+        } else {
+            rhs[ce - d] += G[e * NC + wcol];
+        }
+    }
+    // camera block (kc x kc) and its rhs column -> cam_partial[img][kcMax][kcMax+1]
+    double *cp = S.cam_partial + (size_t)img * S.kcMax * (S.kcMax + 1);
+    for (int i = tid; i < kc * (kc + 1); i += blockDim.x) {
+        const int a = i / (kc + 1), b = i % (kc + 1);
+        cp[a * (S.kcMax + 1) + b] = (b < kc) ? G[(6 + a) * NC + 6 + b] : G[(6 + a) * NC + wcol];
+    }
+}
+
+// per camera: sum the camera blocks of its images in image order, scatter into N / n
+__global__ void __launch_bounds__(256) k_camera_finalize(DevProblem P, AssemblyScratch S, double *__restrict__ M,
+                                                          double *__restrict__ rhs) {
+    const int cam = blockIdx.x, tid = threadIdx.x;
+    const int kc = 3 + P.coef_ptr[cam + 1] - P.coef_ptr[cam];
+    const int32_t *cc = P.campos_col + P.cam_kbase[cam];
+    const int64_t ld = P.np;
+    const int d = P.d;
+    for (int i = tid; i < kc * (kc + 1); i += blockDim.x) {
+        const int a = i / (kc + 1), b = i % (kc + 1);
+        if (b < kc && b > a) continue;
+        const int32_t ca = cc[a];
+        if (!col_active(ca)) continue;
+        if (b < kc && !col_active(cc[b])) continue;
+        double s = 0.0;
+        for (int img = 0; img < P.nImg; img++)
+            if (P.cam_of_img[img] == cam) s += S.cam_partial[(size_t)img * S.kcMax * (S.kcMax + 1) + a * (S.kcMax + 1) + b];
+        if (b < kc) M[lower_idx(ca - d, cc[b] - d, ld)] += s;
+        else rhs[ca - d] += s;
+    }
+}
+
+// ---- by-point sweep -----------------------------------------------------------------------------------------------
+// tile columns: 0..2 point X,Y,Z; 3..3+kRaw-1 raw camera parameters of ALL cameras (x0,y0,c,coefs per camera);
+// 3+kRaw = w.  One warp per object point; output rows 0..2 of the skinny Gram: [PP | P x camera | n_P].
+constexpr int kPtWarps = 4;
+
+template <int NT>
+__global__ void __launch_bounds__(kPtWarps * 32) k_by_point(DevProblem P, double *__restrict__ pt_partial) {
+    constexpr int LDT = 68;
+    constexpr int NC = 8 * NT;
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pt = blockIdx.x * kPtWarps + warp;
+    if (pt >= P.nPt) return;  // warp-uniform
+    double *tile = smem + (size_t)warp * NC * LDT;
+#define ROW0(c) tile[(c) * LDT + lane]
+#define ROW1(c) tile[(c) * LDT + lane + 32]
+    const int wcol = 3 + P.kRaw;
+    const double X = P.xyz[3 * (int64_t)pt], Y = P.xyz[3 * (int64_t)pt + 1], Z = P.xyz[3 * (int64_t)pt + 2];
+    double acc[NT][2];
+#pragma unroll
+    for (int i = 0; i < NT; i++) acc[i][0] = acc[i][1] = 0.0;
+    const int64_t o0 = P.pt_obs_ptr[pt], o1 = P.pt_obs_ptr[pt + 1];
+    for (int64_t base = o0; base < o1; base += 32) {
+        for (int i = 0; i < NC; i++) { ROW0(i) = 0.0; ROW1(i) = 0.0; }
+        const int64_t oi = base + lane;
+        if (oi < o1) {
+            const int64_t j = P.pt_obs[oi];
+            const int img = P.img_of_obs[j], cam = P.cam_of_img[img];
+            const ImgPose q = load_pose(P.pose, img);
+            const CamView cv = view_global(P, cam);
+            const int kb = 3 + P.cam_kbase[cam];
+            double p00, p01, p11;
+            point_weight(P.sigma2, P.var[2 * j], P.var[2 * j + 1], P.rho[j], p00, p01, p11);
+            const double r00 = sqrt(p00), r01 = p01 / r00, r11 = sqrt(p11 - r01 * r01);
+            BaseRows r;
+            eval_observation(q, cv, X, Y, Z, P.xy[2 * j], P.xy[2 * j + 1], r, [&](int k, double v0, double v1) {
+                ROW0(kb + 3 + k) = r00 * v0 + r01 * v1;
+                ROW1(kb + 3 + k) = r11 * v1;
+            });
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                ROW0(i) = r00 * r.ax[i] + r01 * r.ay[i];
+                ROW1(i) = r11 * r.ay[i];
+            }
+            ROW0(kb) = r00;  ROW1(kb) = 0.0;
+            ROW0(kb + 1) = r01;  ROW1(kb + 1) = r11;
+            ROW0(kb + 2) = r00 * r.ax[3] + r01 * r.ay[3];  ROW1(kb + 2) = r11 * r.ay[3];
+            ROW0(wcol) = r00 * r.w0 + r01 * r.w1;  ROW1(wcol) = r11 * r.w1;
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (int ks = 0; ks < 16; ks++) {
+            const double *src = tile + (lane >> 2) * LDT + 4 * ks + (lane & 3);
+            const double fa = src[0];
+#pragma unroll
+            for (int b = 0; b < NT; b++) dmma884(acc[b][0], acc[b][1], fa, src[8 * b * LDT]);
+        }
+        __syncwarp();
+    }
+#undef ROW0
+#undef ROW1
+    if ((lane >> 2) < 3) {
+        double *out = pt_partial + ((size_t)pt * 3 + (lane >> 2)) * NC;
+#pragma unroll
+        for (int b = 0; b < NT; b++) {
+            out[8 * b + 2 * (lane & 3)] = acc[b][0];
+            out[8 * b + 2 * (lane & 3) + 1] = acc[b][1];
+        }
+    }
+}
+
+// scatter the per-point partials into N / n (single owner per entry)
+__global__ void __launch_bounds__(256) k_point_scatter(DevProblem P, AssemblyScratch S, double *__restrict__ M,
+                                                        double *__restrict__ rhs) {
+    const int NC = 8 * S.ntPt;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)P.nPt * 3 * NC) return;
+    const int pt = (int)(i / (3 * NC));
+    const int c = (int)((i / NC) % 3), j = (int)(i % NC);
+    if (P.pt_obs_ptr[pt + 1] == P.pt_obs_ptr[pt]) return;  // no image observation
+    const int32_t cp = P.pt_col[3 * (int64_t)pt + c];
+    if (!col_active(cp)) return;
+    const double v = S.pt_partial[i];
+    const int64_t ld = P.np;
+    const int d = P.d;
+    if (j < 3) {
+        if (j > c) return;
+        const int32_t c2 = P.pt_col[3 * (int64_t)pt + j];
+        if (!col_active(c2)) return;
+        M[lower_idx(cp - d, c2 - d, ld)] += v;
+    } else if (j < 3 + P.kRaw) {
+        const int32_t c2 = P.campos_col[j - 3];
+        if (!col_active(c2)) return;
+        M[lower_idx(cp - d, c2 - d, ld)] += v;
+    } else if (j == 3 + P.kRaw) {
+        rhs[cp - d] += v;
+    }
+}
+
+template <int NT>
+static void run_by_image(const DevProblem &P, const AssemblyScratch &S, double *M, cudaStream_t s) {
+    const size_t smem = (size_t)kImgWarps * 8 * NT * 68 * sizeof(double);
+    static bool attr = false;
+    if (!attr) {
+        JCHECK(cudaFuncSetAttribute(k_by_image<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    g_launch_count++;
+    k_by_image<NT><<<S.nWork, kImgWarps * 32, smem, s>>>(P, S.work, S.img_partial, M);
+}
+
+template <int NT>
+static void run_by_point(const DevProblem &P, const AssemblyScratch &S, cudaStream_t s) {
+    const size_t smem = (size_t)kPtWarps * 8 * NT * 68 * sizeof(double);
+    static bool attr = false;
+    if (!attr) {
+        JCHECK(cudaFuncSetAttribute(k_by_point<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    g_launch_count++;
+    k_by_point<NT><<<(P.nPt + kPtWarps - 1) / kPtWarps, kPtWarps * 32, smem, s>>>(P, S.pt_partial);
+}
+
+#define JAICOV_DISPATCH_NT(nt, CALL)                 \
+    switch (nt) {                                    \
+        case 1: CALL(1); break;                      \
+        case 2: CALL(2); break;                      \
+        case 3: CALL(3); break;                      \
+        case 4: CALL(4); break;                      \
+        case 5: CALL(5); break;                      \
+        case 6: CALL(6); break;                      \
+        case 7: CALL(7); break;                      \
+        case 8: CALL(8); break;                      \
+        default: throw CudaError{cudaErrorInvalidValue, "too many camera parameters for one Gram tile row", __FILE__, __LINE__}; \
+    }
+
+// image points: N (lower, row-major, ld = np) and n.  M and rhs must be zero on entry.
+void launch_assemble(const DevProblem &P, const AssemblyScratch &S, double *M, double *rhs, cudaStream_t s) {
+    if (P.m == 0) return;
+#define CALL_IMG(NT) run_by_image<NT>(P, S, M, s)
+    JAICOV_DISPATCH_NT(S.ntImg, CALL_IMG)
+#undef CALL_IMG
+    const int NC = 8 * S.ntImg;
+    g_launch_count++;
+    k_image_finalize<<<P.nImg, 256, NC * NC * sizeof(double), s>>>(P, S, M, rhs);
+    g_launch_count++;
+    k_camera_finalize<<<P.nCam, 256, 0, s>>>(P, S, M, rhs);
+#define CALL_PT(NT) run_by_point<NT>(P, S, s)
+    JAICOV_DISPATCH_NT(S.ntPt, CALL_PT)
+#undef CALL_PT
+    const int64_t tot = (int64_t)P.nPt * 3 * 8 * S.ntPt;
+    g_launch_count++;
+    k_point_scatter<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(P, S, M, rhs);
+}
+
+// ---- scale bars (PDF:210-283): a handful of observations, one thread, reference order ------------------------
+__global__ void k_scale_bars(DevProblem P, double *__restrict__ M, double *__restrict__ rhs) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const int64_t ld = P.np;
+    const int d = P.d;
+    for (int b = 0; b < P.nBar; b++) {
+        const double *A = P.xyz + 3 * (int64_t)P.bar_a[b], *B = P.xyz + 3 * (int64_t)P.bar_b[b];
+        const double dX = B[0] - A[0], dY = B[1] - A[1], dZ = B[2] - A[2];
+        const double len = sqrt(dX * dX + dY * dY + dZ * dZ);
+        const double a[6] = {-dX / len, -dY / len, -dZ / len, dX / len, dY / len, dZ / len};
+        int32_t col[6];
+        for (int i = 0; i < 3; i++) { col[i] = P.pt_col[3 * (int64_t)P.bar_a[b] + i]; col[3 + i] = P.pt_col[3 * (int64_t)P.bar_b[b] + i]; }
+        const double Pw = P.sigma2 / P.bar_var[b];
+        const double w = P.bar_len[b] - len;
+        for (int i = 0; i < 6; i++) {
+            if (!col_active(col[i])) continue;
+            rhs[col[i] - d] += a[i] * Pw * w;
+            for (int j = 0; j <= i; j++) {
+                if (!col_active(col[j])) continue;
+                M[lower_idx(col[i] - d, col[j] - d, ld)] += a[i] * Pw * a[j];
+            }
+        }
+    }
+}
+
+void launch_scale_bars(const DevProblem &P, double *M, double *rhs, cudaStream_t s) {
+    if (P.nBar == 0) return;
+    g_launch_count++;
+    k_scale_bars<<<1, 32, 0, s>>>(P, M, rhs);
+}
+
+__global__ void k_omega_bars(DevProblem P, const double *__restrict__ dxref, double *__restrict__ out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double om = 0.0;
+    for (int b = 0; b < P.nBar; b++) {
+        const double *A = P.xyz + 3 * (int64_t)P.bar_a[b], *B = P.xyz + 3 * (int64_t)P.bar_b[b];
+        const double dX = B[0] - A[0], dY = B[1] - A[1], dZ = B[2] - A[2];
+        const double len = sqrt(dX * dX + dY * dY + dZ * dZ);
+        const double a[6] = {-dX / len, -dY / len, -dZ / len, dX / len, dY / len, dZ / len};
+        double v = P.bar_len[b] - len;
+        for (int i = 0; i < 3; i++) {
+            const int32_t ca = P.pt_col[3 * (int64_t)P.bar_a[b] + i], cb = P.pt_col[3 * (int64_t)P.bar_b[b] + i];
+            if (col_active(ca)) v -= a[i] * dxref[ca];
+            if (col_active(cb)) v -= a[3 + i] * dxref[cb];
+        }
+        om += v * v * (P.sigma2 / P.bar_var[b]);
+    }
+    out[0] = om;
+}
+
+void launch_omega_bars(const DevProblem &P, const double *dxref, double *omega_out, cudaStream_t s) {
+    g_launch_count++;
+    k_omega_bars<<<1, 32, 0, s>>>(P, dxref, omega_out);
+}
+
+// ---- K8: Omega = sum v'Pv, v = w - A dx (BA:472-491); warp-shuffle + block reduction, two deterministic stages ----
+constexpr int kOmegaThreads = 256;
+
+__global__ void __launch_bounds__(kOmegaThreads) k_omega(DevProblem P, const double *__restrict__ dxref,
+                                                         double *__restrict__ partial) {
+    __shared__ double s_red[kOmegaThreads / 32];
+    double local = 0.0;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < P.m; j += (int64_t)gridDim.x * blockDim.x) {
+        const int img = P.img_of_obs[j], cam = P.cam_of_img[img], pt = P.obj_idx[j];
+        const ImgPose q = load_pose(P.pose, img);
+        const CamView cv = view_global(P, cam);
+        const int32_t *ccol = P.coef_col + P.coef_ptr[cam];
+        double s0 = 0.0, s1 = 0.0;  // (A dx) rows
+        BaseRows r;
+        eval_observation(q, cv, P.xyz[3 * (int64_t)pt], P.xyz[3 * (int64_t)pt + 1], P.xyz[3 * (int64_t)pt + 2],
+                         P.xy[2 * j], P.xy[2 * j + 1], r, [&](int k, double v0, double v1) {
+                             const int32_t c = ccol[k];
+                             if (col_active(c)) { const double dx = dxref[c]; s0 += v0 * dx; s1 += v1 * dx; }
+                         });
+        const int32_t *pc = P.pt_col + 3 * (int64_t)pt, *ic = P.io_col + 3 * cam, *ec = P.eo_col + 6 * (int64_t)img;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            double dd = 0.0;
+            if (col_active(pc[i])) dd += dxref[pc[i]];
+            if (col_active(ec[i])) dd -= dxref[ec[i]];
+            s0 += r.ax[i] * dd;  s1 += r.ay[i] * dd;
+            if (col_active(ec[3 + i])) { const double dx = dxref[ec[3 + i]]; s0 += r.ax[4 + i] * dx; s1 += r.ay[4 + i] * dx; }
+        }
+        if (col_active(ic[0])) s0 += dxref[ic[0]];
+        if (col_active(ic[1])) s1 += dxref[ic[1]];
+        if (col_active(ic[2])) { const double dx = dxref[ic[2]]; s0 += r.ax[3] * dx; s1 += r.ay[3] * dx; }
+        const double v0 = r.w0 - s0, v1 = r.w1 - s1;
+        double p00, p01, p11;
+        point_weight(P.sigma2, P.var[2 * j], P.var[2 * j + 1], P.rho[j], p00, p01, p11);
+        local += v0 * (p00 * v0 + p01 * v1) + v1 * (p01 * v0 + p11 * v1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < kOmegaThreads / 32; i++) s += s_red[i];
+        partial[blockIdx.x] = s;
+    }
+}
+
+__global__ void k_omega_final(const double *__restrict__ partial, int n, double *__restrict__ out) {
+    // one warp, fixed order
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 32) s += partial[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+// omega_out[0] = image points part
+void launch_omega(const DevProblem &P, const AssemblyScratch &S, const double *dxref, double *omega_out, cudaStream_t s) {
+    if (P.m == 0) {
+        cudaMemsetAsync(omega_out, 0, sizeof(double), s);
+        return;
+    }
+    g_launch_count++;
+    k_omega<<<S.omegaBlocks, kOmegaThreads, 0, s>>>(P, dxref, S.omega_partial);
+    g_launch_count++;
+    k_omega_final<<<1, 32, 0, s>>>(S.omega_partial, S.omegaBlocks, omega_out);
+}
+
+}  // namespace jaicov

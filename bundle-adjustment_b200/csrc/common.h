@@ -1,0 +1,109 @@
+// common.h -- shared declarations of the jaicov_b200 CUDA library (host side).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/jaicov_b200.h"
+
+namespace jaicov {
+
+constexpr int kBlk = 128;          // base block / tile edge of every dense kernel
+constexpr int kMaxCoef = 64;       // coefficients per camera staged in shared memory
+constexpr int kMaxDatum = 7;
+constexpr int kRhsRows = 128;      // right-hand-side block: row 0 = n, rows 1..d = datum rows, rest zero
+constexpr double kEps = 1.1102230246251565e-16;  // Constant.EPS = 2^-53 (Constant.java:61-75)
+
+extern long long g_launch_count;   // kernels launched by this library (diagnostic, jaicov_launch_count)
+
+struct CudaError {
+    cudaError_t code;
+    const char *what;
+    const char *file;
+    int line;
+};
+
+#define JCHECK(expr)                                                          \
+    do {                                                                      \
+        cudaError_t e__ = (expr);                                             \
+        if (e__ != cudaSuccess) throw ::jaicov::CudaError{e__, #expr, __FILE__, __LINE__}; \
+    } while (0)
+
+// Flattened problem resident in HBM (structure-of-arrays; all pointers are device pointers).
+struct DevProblem {
+    // cameras
+    int nCam = 0, nCoef = 0;
+    double *io_val = nullptr;       // [3 nCam]
+    int32_t *io_col = nullptr;      // [3 nCam]
+    double *r0 = nullptr;           // [nCam]
+    int32_t *coef_ptr = nullptr;    // [nCam+1]
+    int32_t *coef_type = nullptr, *coef_order = nullptr, *coef_col = nullptr;  // [nCoef]
+    double *coef_val = nullptr;     // [nCoef]
+    int32_t *zern_m = nullptr;      // [nCoef]
+    int32_t *zern_ptr = nullptr;    // [nCoef+1]
+    int32_t *zern_p = nullptr;
+    double *zern_c = nullptr;
+    int32_t *cam_kbase = nullptr;   // [nCam+1] start of camera's raw parameter block (x0,y0,c,coefs) in the camera-parameter list
+    int32_t *campos_col = nullptr;  // [kRaw] column of every raw camera parameter (io then coefs, per camera)
+    int kRaw = 0;                   // sum over cameras of (3 + ncoef)
+    // images
+    int nImg = 0;
+    int32_t *cam_of_img = nullptr;
+    double *eo_val = nullptr;       // [6 nImg]
+    int32_t *eo_col = nullptr;      // [6 nImg]
+    int64_t *pt_ptr = nullptr;      // [nImg+1]
+    double *pose = nullptr;         // [16 nImg]
+    // image points
+    int64_t m = 0;
+    int32_t *obj_idx = nullptr;
+    double *xy = nullptr, *var = nullptr, *rho = nullptr;
+    int32_t *img_of_obs = nullptr;  // [m]
+    int64_t *pt_obs_ptr = nullptr;  // [nPt+1] CSC: observations of every object point
+    int64_t *pt_obs = nullptr;      // [m]
+    // object points
+    int nPt = 0;
+    double *xyz = nullptr;          // [3 nPt]
+    int32_t *pt_col = nullptr;      // [3 nPt]
+    // scale bars
+    int nBar = 0;
+    int32_t *bar_a = nullptr, *bar_b = nullptr;
+    double *bar_len = nullptr, *bar_var = nullptr;
+    // system
+    int d = 0;                      // datum defect (border size)
+    int u = 0;                      // unknowns
+    int64_t np = 0;                 // u padded to a multiple of kBlk (leading dimension of M)
+    double sigma2 = 1.0;
+};
+
+struct WorkItem {
+    int32_t img;
+    int32_t pad;
+    int64_t begin, end;
+};
+
+// ---- assembly.cu ---------------------------------------------------------------------------------------------------
+struct AssemblyScratch {
+    WorkItem *work = nullptr;       // image chunks
+    int nWork = 0;
+    int32_t *img_work_ptr = nullptr;  // [nImg+1] work items of every image
+    int ntImg = 0;                  // 8-column tiles of the by-image Gram
+    int ntPt = 0;                   // 8-column tiles of the by-point Gram
+    double *img_partial = nullptr;  // [nWork][(8 ntImg)^2]
+    double *cam_partial = nullptr;  // [nImg][kc*(kc+1)] camera block + rhs of every image (kc = max raw params per camera)
+    int kcMax = 0;
+    double *pt_partial = nullptr;   // [nPt][3][8 ntPt]
+    double *omega_partial = nullptr;  // [omegaBlocks + 2]
+    int omegaBlocks = 0;
+};
+
+void launch_pose(const DevProblem &P, cudaStream_t s);
+void launch_assemble(const DevProblem &P, const AssemblyScratch &S, double *M, double *rhs, cudaStream_t s);
+void launch_omega(const DevProblem &P, const AssemblyScratch &S, const double *dxref, double *omega_out, cudaStream_t s);
+void launch_eval_k1(const DevProblem &P, int ns_max, double *a, double *w, double *p, cudaStream_t s);
+void launch_scale_bars(const DevProblem &P, double *M, double *rhs, cudaStream_t s);
+void launch_omega_bars(const DevProblem &P, const double *dxref, double *omega_out, cudaStream_t s);
+
+}  // namespace jaicov

@@ -1,0 +1,284 @@
+// dense_kernels.cu -- FP64 tensor-core tile kernels behind dense_driver.hpp (sm_100a).
+//
+//  k_gemm<AL,BL>   C(128x128 tile) = alpha * op(A) op(B) + beta * C on FP64 tensor cores: mma.sync.m8n8k4.f64
+//                  (SASS DMMA.8x8x4 -- the only FP64 tensor instruction of sm_100; tcgen05/TMEM have no f64 kind).
+//                  256 threads = 8 warps (2 x 4), warp tile 64 x 32, 4-stage cp.async (LDGSTS) pipeline of
+//                  128 x 16 operand slabs in padded shared memory (pitch == 4 mod 16 doubles => conflict-free
+//                  LDS.64 fragment loads for both operand orientations).  Triangular operands skip their zero
+//                  k-slabs per output tile; tri_out launches only the lower tiles; tiles are issued longest-first.
+//  k_potrf_diag    one CTA: Cholesky of a 128 x 128 diagonal block in shared memory (left-looking), the factor is
+//                  written back and then inverted in place (dtrti2-style) to give Dinv, which turns every
+//                  triangular solve of the schedule into a GEMM.
+#include <cmath>
+
+#include "common.h"
+#include "dense_driver.hpp"
+
+namespace jaicov {
+
+constexpr int GB = 128;       // tile edge
+constexpr int GK = 16;        // k slab
+constexpr int GSTAGES = 4;
+constexpr int GTHREADS = 256;
+constexpr int PITCH_K = 20;   // [128][16] slab stored with pitch 20 doubles
+constexpr int PITCH_M = 132;  // [16][128] slab stored with pitch 132 doubles
+constexpr int SLAB = 128 * PITCH_K;  // 2560 doubles >= 16 * 132
+constexpr size_t GEMM_SMEM = (size_t)GSTAGES * 2 * SLAB * sizeof(double);
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// load one 128 x 16 operand slab: LAYOUT 0 = rows are the 128 (m or n) index, k contiguous in global memory;
+// LAYOUT 1 = rows are k, the 128 index contiguous in global memory
+template <int LAYOUT>
+__device__ __forceinline__ void load_slab(double *s, const double *g, int64_t ld, int tid) {
+    if (LAYOUT == 0) {
+#pragma unroll
+        for (int c = tid; c < 128 * 8; c += GTHREADS) {
+            const int row = c >> 3, cc = c & 7;
+            cp_async16(s + row * PITCH_K + cc * 2, g + (int64_t)row * ld + cc * 2);
+        }
+    } else {
+#pragma unroll
+        for (int c = tid; c < 16 * 64; c += GTHREADS) {
+            const int kr = c >> 6, cc = c & 63;
+            cp_async16(s + kr * PITCH_M + cc * 2, g + (int64_t)kr * ld + cc * 2);
+        }
+    }
+}
+
+template <int AL, int BL>
+__global__ void __launch_bounds__(GTHREADS, 1) k_gemm(GemmDesc g) {
+    extern __shared__ __align__(16) double gsm[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 1, wn = warp >> 1;   // 2 x 4 warps, warp tile 64 x 32
+    const int grp = lane >> 2, tig = lane & 3;
+
+    // ---- tile decode (longest contraction first) -----------------------------------------------------------------
+    int it, jt;
+    {
+        const int l = blockIdx.x;
+        if (g.tri_out) {
+            it = (int)((sqrt(8.0 * (double)l + 1.0) - 1.0) * 0.5);
+            while ((int64_t)(it + 1) * (it + 2) / 2 <= l) it++;
+            while ((int64_t)it * (it + 1) / 2 > l) it--;
+            jt = l - (int)((int64_t)it * (it + 1) / 2);
+            if (g.kmode != K_MAX_IJ) {  // SYRK: all tiles equal; nothing to reorder
+            }
+        } else {
+            it = l / g.nt;
+            jt = l - it * g.nt;
+            if (g.kmode == K_A_LOWER) it = g.mt - 1 - it;
+        }
+    }
+    int64_t kbeg = 0, kend = g.K;
+    if (g.kmode == K_B_LOWER) kbeg = (int64_t)jt * GB;
+    else if (g.kmode == K_A_LOWER) kend = min(g.K, (int64_t)(it + 1) * GB);
+    else if (g.kmode == K_MAX_IJ) kbeg = (int64_t)max(it, jt) * GB;
+    const int nk = (int)((kend - kbeg) / GK);
+
+    const double *Ag = (AL == 0) ? g.A + (int64_t)it * GB * g.lda + kbeg : g.A + kbeg * g.lda + (int64_t)it * GB;
+    const double *Bg = (BL == 0) ? g.B + (int64_t)jt * GB * g.ldb + kbeg : g.B + kbeg * g.ldb + (int64_t)jt * GB;
+    const int64_t a_step = (AL == 0) ? GK : (int64_t)GK * g.lda;
+    const int64_t b_step = (BL == 0) ? GK : (int64_t)GK * g.ldb;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // ---- pipeline prologue ---------------------------------------------------------------------------------------
+#pragma unroll
+    for (int s = 0; s < GSTAGES - 1; s++) {
+        if (s < nk) {
+            load_slab<AL>(gsm + (size_t)(2 * s) * SLAB, Ag + s * a_step, g.lda, tid);
+            load_slab<BL>(gsm + (size_t)(2 * s + 1) * SLAB, Bg + s * b_step, g.ldb, tid);
+        }
+        cp_async_commit();
+    }
+
+    for (int kt = 0; kt < nk; kt++) {
+        cp_async_wait<GSTAGES - 2>();
+        __syncthreads();
+        {   // prefetch slab kt + STAGES - 1 into the buffer consumed at iteration kt - 1
+            const int kn = kt + GSTAGES - 1;
+            if (kn < nk) {
+                const int sb = kn % GSTAGES;
+                load_slab<AL>(gsm + (size_t)(2 * sb) * SLAB, Ag + kn * a_step, g.lda, tid);
+                load_slab<BL>(gsm + (size_t)(2 * sb + 1) * SLAB, Bg + kn * b_step, g.ldb, tid);
+            }
+            cp_async_commit();
+        }
+        const double *As = gsm + (size_t)(2 * (kt % GSTAGES)) * SLAB;
+        const double *Bs = As + SLAB;
+#pragma unroll
+        for (int kk = 0; kk < GK / 4; kk++) {
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                a[i] = (AL == 0) ? As[(wm * 64 + 8 * i + grp) * PITCH_K + kk * 4 + tig]
+                                 : As[(kk * 4 + tig) * PITCH_M + wm * 64 + 8 * i + grp];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                b[j] = (BL == 0) ? Bs[(wn * 32 + 8 * j + grp) * PITCH_K + kk * 4 + tig]
+                                 : Bs[(kk * 4 + tig) * PITCH_M + wn * 32 + 8 * j + grp];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();   // every load of this CTA has landed before any store: in-place strips (C == A) are safe
+
+    // ---- epilogue ------------------------------------------------------------------------------------------------
+    double *Cg = g.C + ((int64_t)it * GB + wm * 64 + grp) * g.ldc + (int64_t)jt * GB + wn * 32 + 2 * tig;
+    const double alpha = g.alpha, beta = g.beta;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            double2 *p = reinterpret_cast<double2 *>(Cg + (int64_t)(8 * i) * g.ldc + 8 * j);
+            double2 v;
+            if (beta != 0.0) {
+                const double2 c = *p;
+                v.x = alpha * acc[i][j][0] + beta * c.x;
+                v.y = alpha * acc[i][j][1] + beta * c.y;
+            } else {
+                v.x = alpha * acc[i][j][0];
+                v.y = alpha * acc[i][j][1];
+            }
+            *p = v;
+        }
+}
+
+template <int AL, int BL>
+static void launch_gemm_t(const GemmDesc &g, cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) {
+        JCHECK(cudaFuncSetAttribute(k_gemm<AL, BL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+        attr = true;
+    }
+    const int64_t tiles = g.tri_out ? (int64_t)g.mt * (g.mt + 1) / 2 : (int64_t)g.mt * g.nt;
+    if (tiles <= 0) return;
+    g_launch_count++;
+    k_gemm<AL, BL><<<(unsigned)tiles, GTHREADS, GEMM_SMEM, s>>>(g);
+}
+
+void launch_gemm(const GemmDesc &g, cudaStream_t s) {
+    if (g.al == 0 && g.bl == 0) launch_gemm_t<0, 0>(g, s);
+    else if (g.al == 0 && g.bl == 1) launch_gemm_t<0, 1>(g, s);
+    else if (g.al == 1 && g.bl == 1) launch_gemm_t<1, 1>(g, s);
+    else launch_gemm_t<1, 0>(g, s);
+}
+
+// ---- diagonal block: factor + invert ----------------------------------------------------------------------------
+constexpr int DP = 129;  // shared-memory pitch (odd => thread-per-row accesses are conflict-free)
+
+__global__ void __launch_bounds__(128, 1) k_potrf_diag(double *__restrict__ A, int64_t ld, double *__restrict__ dinv,
+                                                        int row0, int *__restrict__ info) {
+    extern __shared__ double a[];   // [128][DP]
+    __shared__ double s_piv;
+    const int i = threadIdx.x;
+    // load the lower triangle (coalesced by rows)
+    for (int r = 0; r < 128; r++) a[r * DP + i] = (i <= r) ? A[(int64_t)r * ld + i] : 0.0;
+    __syncthreads();
+    // left-looking Cholesky: column j <- (a[:,j] - L[:, :j] L[j, :j]') / sqrt(pivot)
+    for (int j = 0; j < 128; j++) {
+        double s = 0.0;
+        if (i >= j) {
+            s = a[i * DP + j];
+            const double *ri = a + i * DP, *rj = a + j * DP;
+            double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
+            int k = 0;
+            for (; k + 4 <= j; k += 4) {
+                s1 += ri[k] * rj[k];
+                s2 += ri[k + 1] * rj[k + 1];
+                s3 += ri[k + 2] * rj[k + 2];
+                s4 += ri[k + 3] * rj[k + 3];
+            }
+            for (; k < j; k++) s1 += ri[k] * rj[k];
+            s -= (s1 + s2) + (s3 + s4);
+        }
+        if (i == j) s_piv = s;
+        __syncthreads();
+        const double piv = s_piv;
+        if (i == j) {
+            if (!(piv > 0.0)) atomicCAS(info, 0, row0 + j + 1);
+            a[i * DP + j] = sqrt(piv);
+        } else if (i > j) {
+            a[i * DP + j] = s / sqrt(piv);
+        }
+        __syncthreads();
+    }
+    // write the factor back (lower triangle only)
+    for (int r = 0; r < 128; r++)
+        if (i <= r) A[(int64_t)r * ld + i] = a[r * DP + i];
+    __syncthreads();
+    // in-place inversion of the lower-triangular factor, last column first (dtrti2, lower):
+    //   inv[j][j] = 1/L[j][j];  inv[i][j] = -(sum_{k=j+1..i} inv[i][k] L[k][j]) * inv[j][j]
+    for (int j = 127; j >= 0; j--) {
+        const double ajj = 1.0 / a[j * DP + j];
+        double s = 0.0;
+        if (i > j) {
+            const double *ri = a + i * DP;
+            double s1 = 0.0, s2 = 0.0;
+            int k = j + 1;
+            for (; k + 2 <= i + 1; k += 2) {
+                s1 += ri[k] * a[k * DP + j];
+                s2 += ri[k + 1] * a[(k + 1) * DP + j];
+            }
+            for (; k <= i; k++) s1 += ri[k] * a[k * DP + j];
+            s = s1 + s2;
+        }
+        __syncthreads();
+        if (i > j) a[i * DP + j] = -s * ajj;
+        else if (i == j) a[j * DP + j] = ajj;
+        __syncthreads();
+    }
+    for (int r = 0; r < 128; r++) dinv[r * 128 + i] = (i <= r) ? a[r * DP + i] : 0.0;
+}
+
+void launch_potrf_diag(double *A, int64_t ld, double *dinv, int row0, int *info, cudaStream_t s) {
+    static bool attr = false;
+    const size_t smem = (size_t)128 * DP * sizeof(double);
+    if (!attr) {
+        JCHECK(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    g_launch_count++;
+    k_potrf_diag<<<1, 128, smem, s>>>(A, ld, dinv, row0, info);
+}
+
+// ---- 2-D copy ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_copy2d(double *__restrict__ dst, int64_t ldd, const double *__restrict__ src,
+                                                int64_t lds, int64_t rows, int64_t cols2) {
+    // cols2 = cols / 2 (everything is 16-byte aligned: cols and leading dimensions are even)
+    const int64_t total = rows * cols2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols2, c = i - r * cols2;
+        reinterpret_cast<double2 *>(dst + r * ldd)[c] = reinterpret_cast<const double2 *>(src + r * lds)[c];
+    }
+}
+
+void launch_copy2d(double *dst, int64_t ldd, const double *src, int64_t lds, int64_t rows, int64_t cols, cudaStream_t s) {
+    const int64_t total = rows * (cols / 2);
+    if (total <= 0) return;
+    const int64_t blocks = (total + 255) / 256;
+    g_launch_count++;
+    k_copy2d<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, s>>>(dst, ldd, src, lds, rows, cols / 2);
+}
+
+}  // namespace jaicov

@@ -1,0 +1,205 @@
+/*
+ * jaicov_b200.h -- C ABI of the B200-native adjustment hot path for JAICOV
+ * (applied-geodesy/bundle-adjustment).
+ *
+ * The library replaces what BundleAdjustment.estimateModel() does between "parameters are indexed"
+ * and "results are exported": the body of the do/while loop at
+ *   JAICOV/src/org/applied_geodesy/adjustment/bundle/BundleAdjustment.java:228-355
+ * i.e. createNormalEquation (:789-834), NormalEquationSystem.applyPrecondition
+ * (adjustment/NormalEquationSystem.java:82-91), MathExtension.solve = dspsv [+ dsptri]
+ * (adjustment/MathExtension.java:338-366), getOmega (:472-491), updateUnknownParameters (:450-462), the
+ * convergence test (:327-350) and the centroid shift (:115-201).
+ *
+ * The Java host keeps prepareUnknownParameters / detectRankDefect (integer bookkeeping, :667-782, :836-1042),
+ * all setters/getters and the result writers; it hands the flattened object graph to this library once per
+ * estimateModel() call (see INTEGRATION.md for the FFM/JNI stub).  All entry points are plain C: pointers and
+ * sizes only, caller owns every buffer it passes and may free it when the call returns.
+ *
+ * Conventions
+ *   - column indices are the reference's UnknownParameter columns AFTER the "+= d" renumbering
+ *     (BundleAdjustment.java:776-781): -1 = unset, INT32_MAX = fixed (parameter/UnknownParameter.java:27),
+ *     otherwise a column in [d, u+d).  Rows/columns [0,d) of N and Qxx are the datum border (:493-635).
+ *   - return value of every function: an EstimationStateType id (adjustment/EstimationStateType.java:24-42)
+ *     or JAICOV_OK (0) for calls that are not an estimation; never throws, never aborts.
+ *   - Qxx is returned in MTJ UpperSymmPackMatrix layout: column-major packed upper,
+ *     element (r,c), r<=c, at r + c(c+1)/2 -- what BundleAdjustment.getCofactorMatrix() (:1177-1179) hands to
+ *     util/io/writer/MatlabResultWriter.java:92-223.
+ *   - one handle = one adjustment = one host thread at a time.  There is no CPU fallback: every function
+ *     that computes fails with JAICOV_NOT_INITIALISED when no sm_100 device is usable.
+ */
+#ifndef JAICOV_B200_H
+#define JAICOV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* EstimationStateType ids (EstimationStateType.java:25-41) */
+#define JAICOV_OK 0
+#define JAICOV_ERROR_FREE_ESTIMATION 1
+#define JAICOV_INTERRUPT (-1)
+#define JAICOV_SINGULAR_MATRIX (-2)
+#define JAICOV_NO_CONVERGENCE (-4)
+#define JAICOV_NOT_INITIALISED (-5)
+#define JAICOV_OUT_OF_MEMORY (-7)
+/* not a reference id: bad argument / unsupported option (the Java side would throw IllegalArgumentException) */
+#define JAICOV_ILLEGAL_ARGUMENT (-100)
+
+/* progress states passed to the callback (names of EstimationStateType) */
+#define JAICOV_STATE_BUSY 100
+#define JAICOV_STATE_ITERATE 101
+#define JAICOV_STATE_CONVERGENCE 102
+#define JAICOV_STATE_INVERT_NORMAL_EQUATION_MATRIX 103
+#define JAICOV_STATE_ESTIMATE_STOCHASTIC_PARAMETERS 104
+
+/* BundleAdjustment.MatrixInversion (BundleAdjustment.java:65-70) */
+#define JAICOV_INVERT_NONE 0
+#define JAICOV_INVERT_FULL 1
+#define JAICOV_INVERT_PRE_ELIMINATION 2 /* not implemented yet: jaicov_estimate returns ILLEGAL_ARGUMENT */
+#define JAICOV_INVERT_REDUCED 3         /* not implemented yet */
+
+/* EstimationType (adjustment/EstimationType.java): only these two are accepted by the reference (:1132-1137) */
+#define JAICOV_L2NORM 0
+#define JAICOV_SIMULATION 1
+
+#define JAICOV_COL_UNSET (-1)
+#define JAICOV_COL_FIXED 2147483647
+
+/* ParameterType ids of distortion coefficients (bundle/parameter/ParameterType.java:27-56) */
+#define JAICOV_PT_RADIAL_A 121
+#define JAICOV_PT_TANGENTIAL_B 131
+#define JAICOV_PT_TANGENTIAL_BX 132
+#define JAICOV_PT_TANGENTIAL_BY 133
+#define JAICOV_PT_AFFINITY_CX 141
+#define JAICOV_PT_AFFINITY_CY 142
+#define JAICOV_PT_DISTANCE_D 151
+#define JAICOV_PT_ZERNIKE_X 161
+#define JAICOV_PT_ZERNIKE_Y 162
+#define JAICOV_PT_ZERNIKE_Z 163
+
+typedef struct jaicov_handle jaicov_handle;
+
+typedef struct {
+    int32_t invert_mode;        /* JAICOV_INVERT_*; setInvertNormalEquation, BundleAdjustment.java:1146 (default FULL, :91) */
+    int32_t estimation_type;    /* JAICOV_L2NORM / JAICOV_SIMULATION; setEstimationType, :1132 */
+    int32_t max_iterations;     /* DefaultValue.getMaximalNumberOfIterations() = 5000 (DefaultValue.java:25) */
+    int32_t use_centroid;       /* useCentroidedCoordinates, :1181 (default 1, :87) */
+    int32_t apply_aposteriori;  /* applyAposterioriVarianceOfUnitWeight, :1185 (default 1, :86) */
+    int32_t device;             /* CUDA device ordinal this handle binds to */
+    double sigma2apriori;       /* min(1, min variance) as accumulated by addObservationGroup, :637-643; <=0 -> 1 (:221) */
+    double damping_value;       /* Levenberg-Marquardt lambda, :1189; must be 0 (LM is a "next" row) */
+} jaicov_options;
+
+typedef struct {
+    int32_t status;             /* last EstimationStateType id */
+    int32_t iterations;         /* number of loop passes executed (incl. the final one) */
+    int32_t iteration_step;     /* the reference's iterationStep = maxIter - runs (:230) at the last pass */
+    int32_t n_unknowns;         /* u */
+    int32_t n_datum;            /* d */
+    int32_t n_observations;     /* 2 m + bars + observed rows */
+    int32_t dof;                /* n_observations - u + d (:1080-1082) */
+    int32_t reserved;
+    double omega;               /* v'Pv of the final pass (:429-430) */
+    double max_abs_dx;          /* of the last pass (:432) */
+    double sigma2apriori;
+    double sigma2aposteriori;   /* getVarianceFactorAposteriori, :1090-1093 */
+    double ms_assembly, ms_factor, ms_solve, ms_inverse, ms_omega, ms_total; /* device time of the LAST pass, CUDA events */
+} jaicov_stats;
+
+/* progress listener: replaces PropertyChangeSupport.firePropertyChange (:72, :205, :232, ...); called on the
+ * calling thread only */
+typedef void (*jaicov_progress_cb)(void *user, int32_t state, double old_value, double new_value);
+
+/* ---- life cycle ------------------------------------------------------------------------------------------------- */
+int32_t jaicov_default_options(jaicov_options *opt);
+int32_t jaicov_create(const jaicov_options *opt, jaicov_handle **out);
+void jaicov_destroy(jaicov_handle *h);
+const char *jaicov_last_error(const jaicov_handle *h);
+/* number of usable sm_100 devices (0 => every compute call fails loudly) */
+int32_t jaicov_device_count(void);
+/* diagnostic: number of CUDA kernels this library has launched in this process so far */
+int64_t jaicov_launch_count(void);
+
+/* ---- problem description (flattened object graph) ---------------------------------------------------------------- */
+/* cameras: io_val/io_col hold x0, y0, c per camera (iterator order camera/orientation/InteriorOrientation.java:70-79);
+ * coefficients of camera k are entries [coef_ptr[k], coef_ptr[k+1]) listed in the reference's evaluation order:
+ * models by enum ordinal AFFINITY, TANGENTIAL, RADIAL, DISTANCE, ZERNIKE_X, ZERNIKE_Y, ZERNIKE_GRADIENT
+ * (camera/Camera.java:50, camera/distortion/DistortionModel.java:29-37); inside TANGENTIAL: Bx, By, then Bi;
+ * inside AFFINITY: Cx, Cy.  Fixed coefficients (col = JAICOV_COL_FIXED) must still be listed: they distort.
+ * coef_order = PolynomialCoefficient.getOrder() (Zernike: the single index j), 0 for Bx/By/Cx/Cy. */
+int32_t jaicov_set_cameras(jaicov_handle *h, int32_t n_cam, const double *io_val, const int32_t *io_col, const double *r0,
+                           const int32_t *coef_ptr, const int32_t *coef_type, const int32_t *coef_order,
+                           const double *coef_val, const int32_t *coef_col);
+/* images in camera->image iteration order; eo = X0,Y0,Z0,omega,phi,kappa
+ * (camera/orientation/ExteriorOrientation.java:39-45); pt_ptr is a CSR over image points */
+int32_t jaicov_set_images(jaicov_handle *h, int32_t n_img, const int32_t *cam_of_img, const double *eo_val,
+                          const int32_t *eo_col, const int64_t *pt_ptr);
+/* image points in the reference's observation order (rows 2j, 2j+1; :670-676); var = sigma_x^2, sigma_y^2
+ * (camera/ImageCoordinate.java:50-51); rho = correlation coefficient (:54) */
+int32_t jaicov_set_image_points(jaicov_handle *h, int64_t m, const int32_t *obj_idx, const double *xy, const double *var,
+                                const double *rho);
+/* object points; is_datum[i] != 0 iff the point is in BundleAdjustment.objectCoordinates and isDatum() (:501-513) */
+int32_t jaicov_set_object_points(jaicov_handle *h, int32_t n_pt, const double *xyz, const int32_t *col,
+                                 const uint8_t *is_datum);
+/* scale bars (ScaleBar.java:34-39): end points, length, variance = sigma^2 */
+int32_t jaicov_set_scale_bars(jaicov_handle *h, int32_t n_bar, const int32_t *a, const int32_t *b, const double *length,
+                              const double *var);
+/* one DirectlyObservedParameterGroup (parameter/DirectlyObservedParameterGroup.java:37-60).  target_kind:
+ * 0 object point (index = point, comp 0..2), 1 interior orientation (index = camera, comp 0..2),
+ * 2 distortion coefficient (index = position in the global coefficient list, comp ignored),
+ * 3 exterior orientation (index = image, comp 0..5).  Either var (diagonal) or sigma_packed_upper
+ * (r(r+1)/2, MTJ packed upper) must be given; with the latter P = sigma0^2 * Sigma^-1 (:80-90). */
+int32_t jaicov_add_observed_group(jaicov_handle *h, int32_t r, const int32_t *target_kind, const int32_t *target_index,
+                                  const int32_t *target_comp, const double *obs, const double *var,
+                                  const double *sigma_packed_upper);
+/* result of detectRankDefect (:836-1042): free_flags in the order tx,ty,tz,rx,ry,rz,scale (1 = FREE);
+ * n_unknowns = numberOfUnknownParameters (:80), n_observations = numberOfObservations (:81) */
+int32_t jaicov_set_datum(jaicov_handle *h, const int32_t free_flags[7], int32_t n_unknowns, int32_t n_observations);
+
+/* ---- the adjustment ------------------------------------------------------------------------------------------------ */
+/* Runs the whole loop on the device and returns the EstimationStateType id. interrupt_flag (may be NULL) is
+ * polled twice per pass like BundleAdjustment.interrupt (:240, :320). */
+int32_t jaicov_estimate(jaicov_handle *h, jaicov_progress_cb cb, void *user, volatile int32_t *interrupt_flag);
+
+/* One pass of the loop body on the CURRENT values (benchmark / stage tests): assembly + datum + precondition,
+ * factor + solve, and if final_pass != 0 also the inversion (if invert_mode FULL) and Omega.  If apply_update
+ * != 0 the unknowns are updated (x += dx) as the reference does. */
+int32_t jaicov_iterate(jaicov_handle *h, int32_t final_pass, int32_t apply_update);
+
+/* ---- results ----------------------------------------------------------------------------------------------------- */
+int32_t jaicov_get_stats(jaicov_handle *h, jaicov_stats *out);
+/* current parameter values (any pointer may be NULL) in the layouts of the set_* calls */
+int32_t jaicov_get_values(jaicov_handle *h, double *xyz, double *io_val, double *coef_val, double *eo_val);
+/* last solution vector dx in reference column order, length u+d (border entries first) */
+int32_t jaicov_get_dx(jaicov_handle *h, double *dx);
+/* Qxx (u+d) in MTJ packed-upper layout, (u+d)(u+d+1)/2 doubles; dst is host memory (pinned or pageable) */
+int32_t jaicov_get_qxx_packed(jaicov_handle *h, double *dst);
+/* rectangular tile rows [r0,r1) x cols [c0,c1) of the full symmetric Qxx, row-major with leading dimension ld */
+int32_t jaicov_get_qxx_block(jaicov_handle *h, int32_t r0, int32_t r1, int32_t c0, int32_t c1, double *dst, int64_t ld);
+/* diagonal of Qxx, length u+d */
+int32_t jaicov_get_qxx_diag(jaicov_handle *h, double *dst);
+
+/* ---- stage access for parity tests and profiling (same kernels the loop uses) ---------------------------------- */
+/* K1: residuals and compact Jacobian of every image point at the current values.  Per point j the 2 x ns
+ * entries are written slot-ordered: slots 0..11 = X,Y,Z,x0,y0,c,X0,Y0,Z0,omega,phi,kappa, slots 12.. = the
+ * coefficients of the point's camera in list order; ns_max = 12 + max coefficients per camera.
+ * a: [m][2][ns_max], w: [m][2], p: [m][3] (P00,P01,P11); host buffers. */
+int32_t jaicov_eval_residual_jacobian(jaicov_handle *h, int32_t ns_max, double *a, double *w, double *p);
+/* Normal equations of the current values BEFORE datum/preconditioning: N (u+d, MTJ packed upper, border rows
+ * as written by addDatumConditionRows) and n (u+d); host buffers; either may be NULL */
+int32_t jaicov_get_normal_equations(jaicov_handle *h, double *n_packed, double *rhs);
+/* Omega = v'Pv for a given dx (reference column order, length u+d) at the current values (getOmega, :472-491) */
+int32_t jaicov_omega(jaicov_handle *h, const double *dx, double *omega);
+
+/* Level-1 seam (the routines BundleAdjustment needs from LAPACK, MathExtension.java:304-366), dense SPD route:
+ * in: a = symmetric positive definite n x n, row-major, host; b = nrhs right-hand sides [nrhs][n] (may be NULL).
+ * out: a <- a^-1 (full symmetric) if invert != 0, b <- solutions.  Returns SINGULAR_MATRIX if not SPD. */
+int32_t jaicov_spd_solve_invert(int32_t device, int64_t n, double *a, int32_t nrhs, double *b, int32_t invert,
+                                double *ms_factor, double *ms_inverse);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JAICOV_B200_H */

@@ -1,0 +1,265 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path through the C ABI against the CPU oracle on the same
+inputs.  Tolerances are the ones BASELINE.json's north_star states: estimated parameters 1e-10 relative, Qxx and
+sigma0^2 1e-8 relative (Qxx correlation-scaled: |dq_ij| <= 1e-8 sqrt(q_ii q_jj)), integer bookkeeping bit-exact.
+"""
+import numpy as np
+import pytest
+
+import bundle_adjustment_b200 as ba
+from oracle.oracle import FlatProblem, Oracle, eval_point, lib as oracle_lib
+from tests.helpers import build_adjustment, flat_problem
+from tests.scenes import example_scene, synthetic_scene
+
+pytestmark = pytest.mark.gpu
+
+TOL_X, TOL_Q, TOL_S2 = 1e-10, 1e-8, 1e-8
+
+
+def session_for(scene, **kw):
+    adj, flat = flat_problem(scene)
+    s = ba.Session(sigma2apriori=adj.getVarianceFactorApriori(), **kw)
+    s.set_problem(flat)
+    return s, flat, adj
+
+
+def zernike_scene():
+    sc, _ = synthetic_scene(2, images=6, targets=60)
+    cam = sc['cameras'][0]
+    cam['coefs'] = cam['coefs'] + [(161, 3, 1e-4, False), (161, 8, -2e-5, False), (162, 4, 3e-5, False), (162, 7, 1e-5, True),
+                                   (163, 5, 2e-5, False), (163, 9, -1e-5, False), (163, 12, 1e-6, False)]
+    return sc
+
+
+def scenes_k1():
+    yield 'example', example_scene()
+    yield 'cfg4_small_Di', synthetic_scene(4, images=10, targets=80)[0]
+    yield 'cfg3_small_rho', synthetic_scene(3, images=6, targets=40)[0]
+    sc = synthetic_scene(4, images=8, targets=50, n_cameras=2)[0]
+    sc['cameras'][1]['coefs'] = sc['cameras'][1]['coefs'][:7] + [(131, 1, 1e-4, False), (131, 2, -1e-6, False)]
+    # Bi must follow Bx, By inside the tangential block (evaluation order)
+    c = sc['cameras'][1]['coefs']
+    sc['cameras'][1]['coefs'] = c[:4] + c[7:] + c[4:7]
+    sc['cameras'][1]['io_fixed'][1] = True
+    sc['points']['fixed'][2] = True
+    yield 'two_cameras_Bi_fixed', sc
+    yield 'zernike', zernike_scene()
+
+
+@pytest.mark.parametrize('name,scene', list(scenes_k1()))
+def test_k1_residual_jacobian_per_entry(built, name, scene):
+    """K1: every Jacobian entry, misclosure and weight of every image point vs the oracle (PDF:285-445)."""
+    s, flat, adj = session_for(scene)
+    a, w, p = s.eval_residual_jacobian()
+    fp = FlatProblem(scene)
+    sigma2 = adj.getVarianceFactorApriori()
+    worst = 0.0
+    for img in range(fp.nImg):
+        for j in range(int(fp.pt_ptr[img]), int(fp.pt_ptr[img + 1])):
+            cols, a0, a1, wo, P3 = eval_point(fp, img, j, sigma2)
+            ns = a0.size
+            scale = max(np.abs(a0).max(), np.abs(a1).max(), 1e-300)
+            worst = max(worst, np.abs(a[j, 0, :ns] - a0).max() / scale, np.abs(a[j, 1, :ns] - a1).max() / scale)
+            np.testing.assert_allclose(a[j, 0, :ns], a0, rtol=1e-11, atol=1e-13 * scale)
+            np.testing.assert_allclose(a[j, 1, :ns], a1, rtol=1e-11, atol=1e-13 * scale)
+            assert not a[j, :, ns:].any()
+            np.testing.assert_allclose(w[j], wo, rtol=0, atol=1e-13 * max(1.0, np.abs(fp.xy[2 * j:2 * j + 2]).max()))
+            np.testing.assert_allclose(p[j], P3, rtol=1e-14)
+    print(name, 'worst scaled Jacobian entry error', worst)
+
+
+def scenes_neq():
+    yield 'example', example_scene()
+    yield 'cfg2_small', synthetic_scene(2, images=10, targets=60)[0]
+    yield 'cfg3_small_dense_sigma', synthetic_scene(3, images=8, targets=50)[0]
+    sc = synthetic_scene(4, images=9, targets=70, visibility=0.6, n_cameras=2)[0]
+    sc['scale_bars'] = [(0, 1, float(np.linalg.norm(sc['points']['xyz'][0] - sc['points']['xyz'][1])) + 0.01, 0.02)]
+    sc['points']['fixed'][4, 1] = True
+    sc['cameras'][0]['images'][1]['eo_fixed'][4] = True
+    yield 'cfg4_small_sparse_two_cameras_bar', sc
+    yield 'zernike', zernike_scene()
+
+
+@pytest.mark.parametrize('name,scene', list(scenes_neq()))
+def test_normal_equations(built, name, scene):
+    """K2/K3: N = A'PA (+ datum border rows) and n = A'Pw vs the oracle's stacking (PDF:475-505, BA:789-799)."""
+    s, flat, adj = session_for(scene)
+    N, n = s.normal_equations()
+    o = Oracle(scene, use_centroid=False)
+    No, no, _ = o.create_normal_equation()
+    nn = o.fp.n
+    idx = np.arange(nn)
+    dg = np.sqrt(np.abs(No[idx + idx * (idx + 1) // 2]))
+    dg[dg == 0] = 1.0
+    iu = np.triu_indices(nn)
+    scale = dg[iu[0]] * dg[iu[1]]
+    k = iu[0] + iu[1] * (iu[1] + 1) // 2
+    err = np.abs(N[k] - No[k]) / scale
+    print(name, 'max scaled N error', err.max(), 'max scaled n error', (np.abs(n - no) / dg).max() / max(1e-300, (np.abs(no) / dg).max()))
+    assert err.max() < 1e-12
+    np.testing.assert_allclose(n / dg, no / dg, rtol=0, atol=1e-11 * (np.abs(no) / dg).max())
+
+
+@pytest.mark.parametrize('name,scene', list(scenes_neq()))
+def test_omega(built, name, scene):
+    """K8: Omega = (A dx - w)'P(A dx - w) for an arbitrary dx vs BundleAdjustment.getOmega (BA:472-491)."""
+    s, flat, adj = session_for(scene)
+    o = Oracle(scene, use_centroid=False)
+    rng = np.random.default_rng(7)
+    dx = rng.normal(0, 1e-4, size=o.fp.n)
+    np.testing.assert_allclose(s.omega(dx), o.get_omega(dx), rtol=1e-11)
+    np.testing.assert_allclose(s.omega(np.zeros(o.fp.n)), o.get_omega(np.zeros(o.fp.n)), rtol=1e-11)
+
+
+@pytest.mark.parametrize('n,nrhs', [(128, 1), (200, 3), (384, 2), (1000, 8), (1817, 1), (2500, 0)])
+def test_spd_solve_invert(built, n, nrhs):
+    """K5/K6 on their own (the level-1 seam, MathExtension.java:304-366): blocked Cholesky, solves and full inverse on
+    FP64 tensor-core tiles vs LAPACK."""
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n))
+    S = A @ A.T + n * np.eye(n)
+    dd = 1 / np.sqrt(np.diag(S))
+    S = S * dd[:, None] * dd[None, :]
+    b = rng.standard_normal((nrhs, n)) if nrhs else None
+    Q, x, ms = ba.spd_solve_invert(S, b, invert=True)
+    Qi = np.linalg.inv(S)
+    sc = np.sqrt(np.diag(Qi))
+    assert (np.abs(Q - Qi) / np.outer(sc, sc)).max() < 1e-11 * np.linalg.cond(S)
+    assert np.abs(Q - Q.T).max() == 0.0
+    if nrhs:
+        np.testing.assert_allclose(x, np.linalg.solve(S, b.T).T, rtol=0, atol=1e-11 * np.abs(b).max() * np.linalg.cond(S) ** 0.5)
+    with pytest.raises(ba.JaicovError) as e:
+        S2 = S.copy()
+        S2[n // 2, n // 2] = -1.0
+        ba.spd_solve_invert(S2, None, invert=False)
+    assert e.value.code == ba._lib.SINGULAR_MATRIX
+
+
+def compare_adjustment(scene, label):
+    adj, pts = build_adjustment(scene)
+    state = adj.estimateModel()
+    o = Oracle(scene)
+    st_o = o.estimate()
+    assert state.getId() == st_o == 1
+    st = adj.stats
+    # integer bookkeeping: bit-exact
+    assert (st.n_unknowns, st.n_datum, st.n_observations, st.dof) == (o.bk.n_unknown, o.bk.d, o.bk.n_obs, o.bk.dof)
+    assert st.iterations == len(o.history)
+    assert st.iteration_step == o.iterations
+    # sigma0^2 and Omega
+    s2g, s2o = adj.getVarianceFactorAposteriori(), o.variance_factor_aposteriori()
+    assert abs(s2g - s2o) <= TOL_S2 * s2o
+    assert abs(st.omega - o.omega) <= TOL_S2 * o.omega
+    # Qxx, correlation-scaled
+    Qo = o.qxx_dense()
+    Qg = adj.getCofactorMatrix().toDense()
+    d = o.fp.d
+    sg = np.sqrt(np.abs(np.diag(Qo)))
+    sg[:d] = 1.0
+    errq = (np.abs(Qg - Qo) / np.outer(sg, sg)).max()
+    # parameters: 1e-10 relative (floor: the parameter's own cofactor standard deviation, for values near zero)
+    s2 = o.variance_factor_aposteriori()
+    xyz_g, io_g, coef_g, eo_g = adj._session.values()
+    errx = 0.0
+    for vg, vo, cols in ((xyz_g, o.fp.xyz, o.fp.pt_col), (io_g, o.fp.io_val, o.fp.io_col), (coef_g, o.fp.coef_val, o.fp.coef_col),
+                         (eo_g, o.fp.eo_val, o.fp.eo_col)):
+        c = cols.astype(np.int64)
+        act = (c >= 0) & (c < 2147483647)
+        np.testing.assert_array_equal(vg[~act], vo[~act])      # fixed / unset parameters are untouched
+        floor = np.sqrt(s2 * np.abs(np.diag(Qo))[c[act]])
+        errx = max(errx, (np.abs(vg[act] - vo[act]) / np.maximum(np.abs(vo[act]), floor)).max())
+    print('%s: passes %d, max|dx| %.3e, sigma0^2 rel err %.2e, scaled Qxx err %.2e, parameter rel err %.2e'
+          % (label, st.iterations, st.max_abs_dx, abs(s2g - s2o) / s2o, errq, errx))
+    assert errq <= TOL_Q
+    assert errx <= TOL_X
+    return adj, o
+
+
+def test_adjustment_example_config1(built):
+    """BASELINE.json configs[0]: the bundled 115-image example, FULL inversion."""
+    adj, o = compare_adjustment(example_scene(), 'config 1')
+    # the external known answer: AICON's S0 = 0.000405 (example.htm:31)
+    s0 = 0.0005 * np.sqrt(adj.getVarianceFactorAposteriori() / adj.getVarianceFactorApriori())
+    assert abs(s0 - 0.000405) < 5e-7
+    # packed getter vs block getter vs diagonal getter
+    Q = adj.getCofactorMatrix().toDense()
+    blk = adj._session.qxx_block(3, 40, 0, 1153)
+    np.testing.assert_array_equal(blk, Q[3:40])
+    np.testing.assert_array_equal(adj._session.qxx_diag(), np.diag(Q))
+
+
+def test_adjustment_config2(built):
+    """BASELINE.json configs[1]: 50 images x 500 targets, in-situ calibration, free network (d = 7)."""
+    compare_adjustment(synthetic_scene(2)[0], 'config 2')
+
+
+def test_adjustment_config3_small(built):
+    """configs[2] scaled down: correlated image xy + fully populated dispersion of observed object points (d = 0)."""
+    compare_adjustment(synthetic_scene(3, images=12, targets=150)[0], 'config 3 (12 x 150)')
+
+
+def test_adjustment_config4_small(built):
+    """configs[3] scaled down: distance-dependent distortion D_i, free network, full Qxx."""
+    compare_adjustment(synthetic_scene(4, images=30, targets=300)[0], 'config 4 (30 x 300)')
+
+
+def test_adjustment_fixed_parameters_scale_bar_two_cameras(built):
+    sc = synthetic_scene(4, images=12, targets=120, visibility=0.7, n_cameras=2)[0]
+    sc['scale_bars'] = [(0, 1, float(np.linalg.norm(sc['points']['xyz'][0] - sc['points']['xyz'][1])), 0.02)]
+    sc['points']['fixed'][4, 1] = True
+    sc['cameras'][0]['images'][1]['eo_fixed'][4] = True
+    sc['cameras'][1]['coefs'][9] = sc['cameras'][1]['coefs'][9][:3] + (True,)
+    compare_adjustment(sc, 'mixed')
+
+
+def test_modes_none_and_simulation(built):
+    sc = synthetic_scene(2, images=10, targets=80)[0]
+    adj, _ = build_adjustment(sc)
+    adj.setInvertNormalEquation(ba.MatrixInversion.NONE)
+    assert adj.estimateModel() == ba.EstimationStateType.ERROR_FREE_ESTIMATION
+    assert adj.getCofactorMatrix() is None
+    o = Oracle(sc, invert='NONE')
+    assert o.estimate() == 1
+    assert abs(adj.getVarianceFactorAposteriori() - o.variance_factor_aposteriori()) <= TOL_S2 * o.variance_factor_aposteriori()
+    adj2, _ = build_adjustment(sc)
+    adj2.setEstimationType(ba.EstimationType.SIMULATION)
+    assert adj2.estimateModel() == ba.EstimationStateType.ERROR_FREE_ESTIMATION
+    assert adj2.stats.iterations == 2 and adj2.stats.max_abs_dx == 0.0
+    assert adj2.getVarianceFactorAposteriori() == adj2.getVarianceFactorApriori()
+
+
+def test_properties_at_config4_size(built):
+    """Size-independent properties at BASELINE.json's config 4 (200 x 5000, n = 16220) where the packed-LAPACK oracle
+    needs tens of minutes: one final pass, then  B dx = 0,  Q N Q = Q on sampled columns,  Omega = w'Pw - n'dx."""
+    sc = synthetic_scene(4)[0]
+    s, flat, adj = session_for(sc)
+    n = s.n
+    N0, n0 = None, None
+    om0 = s.omega(np.zeros(n))                                    # w'Pw at the current values
+    _, rhs = s.L, None
+    Np, nv = s.normal_equations()
+    assert s.iterate(final_pass=True, apply_update=False) == 0
+    dx = s.dx()
+    st = s.stats()
+    d = 7
+    # datum conditions hold: B dx = 0 (rows 0..d-1 of N are the border)
+    idx = np.arange(n)
+    for a in range(d):
+        brow = Np[a + idx[d:] * (idx[d:] + 1) // 2]
+        assert abs(brow @ dx[d:]) < 1e-9 * np.abs(dx).max()
+    # Omega identity of the linearised model
+    assert abs(st.omega - (om0 - nv @ dx)) <= 1e-8 * om0
+    # Q N Q = Q restricted to sampled columns (N symmetric from the packed upper part)
+    cols = np.array([d, d + 17, n // 2, n - 1])
+    Qc = s.qxx_block(0, n, int(cols[0]), int(cols[0]) + 1)[:, 0]
+    iu = np.triu_indices(n)
+    Nd = np.zeros((n, n))
+    Nd[iu] = Np[iu[0] + iu[1] * (iu[1] + 1) // 2]
+    Nd = Nd + np.triu(Nd, 1).T
+    del iu
+    Q_full_cols = np.stack([s.qxx_block(0, n, int(c), int(c) + 1)[:, 0] for c in cols], axis=1)
+    NQ = Nd @ Q_full_cols
+    # K Q = I for the bordered system K = N (with border): columns of the identity
+    for k, c in enumerate(cols):
+        e = np.zeros(n)
+        e[c] = 1.0
+        assert np.abs(NQ[:, k] - e).max() < 1e-7
