@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- adjustment iterations per second (A'PA + Cholesky + full Qxx) on B200, BASELINE.json's metric.
+
+One "step" = one FINAL pass of the adjustment loop on one synthetic network resident in HBM: residual/Jacobian
+evaluation and normal-equation assembly, Jacobi preconditioning + datum reformulation, blocked FP64 Cholesky, solve,
+full inverse Qxx, Omega = v'Pv, max|dx| (jaicov_iterate(final_pass=1)).  The same values are re-used every step
+(apply_update=0), so every step does identical work.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4|5] [--impl reference]
+
+N > 1 (torchrun): every rank runs the same pass on its own GPU as an independent replica (weak scaling); the
+image-sharded assembly / block-cyclic factorisation of SURVEY.md 8(e) is not built yet and this is said in the line.
+`--impl reference` times the CPU oracle (oracle/, the restatement of the Java path; no JVM exists here) on a bounded,
+scaled-down sample of the same workload and extrapolates (assembly ~ image points, factor+inverse ~ n^3).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'adjustment iters/s (A^T P A + Cholesky + full Qxx)'
+UNIT = 'iterations/s'
+
+
+def workload(config, images=None, targets=None):
+    from tests.helpers import flat_problem
+    from tests.scenes import synthetic_scene
+    scene, _ = synthetic_scene(config, images=images, targets=targets)
+    adj, flat = flat_problem(scene)
+    return scene, adj, flat
+
+
+def workload_name(config, flat, adj):
+    n = int(flat['n_unknowns']) + int(np.sum(flat['free_flags']))
+    return ('BASELINE.json configs[%d]: synthetic %d images x %d targets, %d image points, n = u+d = %d'
+            % (config - 1, len(flat['cam_of_img']), flat['xyz'].size // 3, flat['obj_idx'].size, n)), n
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([x.strip() for x in line.split(',')])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm, reasons, smax = [], set(), None
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                smax = float(s[1])
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), s[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': smax, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def fp64_peak_tflops(torch, n=8192, reps=5):
+    """FP64 roofline denominator: MEASURED_PEAKS.json holds no FP64 entry, so cuBLAS DGEMM (torch.matmul, float64,
+    n^3) is measured here, best of `reps` (burst), CUDA events."""
+    a = torch.randn(n, n, dtype=torch.float64, device='cuda')
+    b = torch.randn(n, n, dtype=torch.float64, device='cuda')
+    c = torch.empty_like(a)
+    torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    best = float('inf')
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b, c
+    torch.cuda.empty_cache()
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def cpu_sample(config, n_full, m_full, threads):
+    """Bounded CPU sample: ONE final pass of the oracle (reference-equivalent: per-observation stacking into packed N,
+    dspsv + dsptri, Omega) on a scaled-down network of the same config, extrapolated to the full workload."""
+    from threadpoolctl import threadpool_limits
+    from oracle.oracle import Oracle, lib as olib
+    from tests.scenes import synthetic_scene
+    scene, _ = synthetic_scene(config, images=40, targets=800)
+    with threadpool_limits(limits=threads):
+        o = Oracle(scene)
+        o.history = []
+        if o.use_centroid:
+            o._centroid(False)
+        import ctypes
+        from oracle import lapack_packed as lp
+        t0 = time.perf_counter()
+        N, nv, V = o.create_normal_equation()
+        olib().orc_apply_precondition(o.fp.n, V.ctypes.data, N.ctypes.data, nv.ctypes.data)
+        t1 = time.perf_counter()
+        lp.solve_symm_packed(N, nv, o.fp.n, True)
+        olib().orc_apply_precondition(o.fp.n, V.ctypes.data, N.ctypes.data, nv.ctypes.data)
+        t2 = time.perf_counter()
+        o.get_omega(nv)
+        t3 = time.perf_counter()
+    n_s, m_s = o.fp.n, o.fp.m
+    t_asm, t_dense, t_om = t1 - t0, t2 - t1, t3 - t2
+    t_full = (t_asm + t_om) * (m_full / m_s) + t_dense * (n_full / n_s) ** 3
+    return {'value': 1.0 / t_full, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+            'sample': ('one final pass of the CPU oracle on a scaled-down network of the same config (40 images x 800 targets, '
+                       'n = %d, %d image points): assembly+Omega %.2f s, packed dspsv+dsptri %.2f s; extrapolated to the full '
+                       'workload with assembly ~ image points and factor+inverse ~ n^3 (%.3g s per pass)'
+                       % (n_s, m_s, t_asm + t_om, t_dense, t_full))}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    scene, adj, flat = workload(args.config)
+    name, n = workload_name(args.config, flat, adj)
+    threads = os.cpu_count() or 1
+    vals = []
+    t_all = time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        cb = cpu_sample(args.config, n, flat['obj_idx'].size, threads)
+        if i >= args.warmup:
+            vals.append(cb['value'])
+        if time.perf_counter() - t_all > 240:
+            break
+    v = float(np.mean(vals)) if vals else cb['value']
+    cb['value'] = v
+    print(json.dumps({'metric': METRIC, 'value': v, 'unit': UNIT, 'impl': 'reference', 'n_gpus': args.gpus, 'steps': args.steps,
+                      'warmup': args.warmup, 'ms_per_step': 1000.0 / v, 'higher_is_better': True, 'scaling': 'weak',
+                      'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                      'config': {'workload': name, 'impl_note': 'CPU oracle = reference-equivalent port (no JVM in this image); bounded sample extrapolated'},
+                      'cpu_baseline': cb,
+                      'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--config', type=int, default=int(os.environ.get('JAICOV_BENCH_CONFIG', '4')))
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import bundle_adjustment_b200 as ba
+    L = ba._lib.load()
+    if L.jaicov_device_count() < 1:
+        raise SystemExit('bench.py needs a B200 (sm_100): jaicov_b200 has no CPU path')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    scene, adj, flat = workload(args.config)
+    name, n = workload_name(args.config, flat, adj)
+    sigma2 = adj.getVarianceFactorApriori()
+    sess = ba.Session(sigma2apriori=sigma2, device=local_rank)
+    sess.set_problem(flat)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        rc = sess.iterate(final_pass=True, apply_update=False)
+        assert rc == 0, rc
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.jaicov_launch_count()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, stage = 0.0, np.zeros(5)
+    for _ in range(args.steps):
+        rc = sess.iterate(final_pass=True, apply_update=False)
+        assert rc == 0, rc
+        st = sess.stats()
+        dev_ms += st.ms_total
+        stage += [st.ms_assembly, st.ms_factor, st.ms_solve, st.ms_inverse, st.ms_omega]
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = (L.jaicov_launch_count() - launches0) // args.steps
+    clocks = sampler.finish() if rank == 0 else None
+    # max over ranks of the device time
+    t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_ms_max = float(t[0]), float(t[1])
+    ms_per_step = dev_ms_max / args.steps
+    value = world * args.steps / (dev_ms_max * 1e-3)
+    stage /= args.steps
+
+    # ---- end to end through the C ABI with host buffers -----------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        npk = n * (n + 1) // 2
+        try:
+            qhost = torch.empty(npk, dtype=torch.float64, pin_memory=True).numpy()
+        except Exception:
+            qhost = np.empty(npk)
+        h2d = sum(np.asarray(flat[k]).nbytes for k in ('io_val', 'io_col', 'r0', 'coef_ptr', 'coef_type', 'coef_order', 'coef_val',
+                                                       'coef_col', 'cam_of_img', 'eo_val', 'eo_col', 'pt_ptr', 'xy', 'var', 'rho', 'xyz', 'is_datum'))
+        h2d += flat['obj_idx'].size * 4 + flat['pt_col'].size * 4
+        d2h = npk * 8 + n * 8 + (flat['xyz'].size + flat['io_val'].size + flat['coef_val'].size + flat['eo_val'].size) * 8
+        ksteps = max(1, min(args.steps, 3))
+        sess.close()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            s2 = ba.Session(sigma2apriori=sigma2, device=local_rank)
+            s2.set_problem(flat)                       # host -> device copies of the whole flattened problem
+            rc = s2.iterate(final_pass=True, apply_update=True)
+            assert rc == 0, rc
+            s2.qxx_packed(out=qhost)                   # device -> host: full Qxx in MTJ packed layout
+            dxh = s2.dx()
+            vals = s2.values()
+            s2.close()
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {'value': world * ksteps / float(te[0]), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+               'steps': ksteps, 'includes': 'jaicov_create + set_* (H2D) + one final pass + full packed Qxx, dx and values (D2H) + destroy'}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant stage: factor + inverse on FP64 tensor-core GEMM tiles --------------------------------
+    peak = fp64_peak_tflops(torch)
+    flops = float(n) ** 3                            # n^3/3 (factor) + 2n^3/3 (inverse), SURVEY.md 8(d)
+    t_dense = (stage[1] + stage[3]) * 1e-3
+    achieved = flops / t_dense / 1e12
+    peaks_file = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    hbm = json.load(open(peaks_file)).get('hbm_gbs') if os.path.exists(peaks_file) else 6650.0
+    roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+                'kernel': 'k_gemm<AL,BL> (FP64 DMMA 128x128 tiles); numerator n^3 flop per step, denominator device time of the '
+                          'factor + inverse stages (includes the diagonal-block kernels and copies between GEMM launches)',
+                'peak_source': 'cuBLAS DGEMM 8192^3 via torch.matmul(float64) measured in this run (burst, best of 5); '
+                               'MEASURED_PEAKS.json has no FP64 entry',
+                'assembly_gbs': (flat['obj_idx'].size * 44.0) / (stage[0] * 1e-3) / 1e9, 'hbm_peak_gbs': hbm}
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic',
+            'config': {'workload': name, 'l2': 'inputs larger than L2: the %d x %d FP64 system (%.2f GB) is rewritten every step'
+                       % (n, n, n * n * 8 / 1e9),
+                       'parallelism': 'single GPU' if world == 1 else 'independent replicas (image-sharded assembly / block-cyclic factorisation not built yet)',
+                       'timing': 'CUDA events on the library stream around every pass (jaicov_stats.ms_total), max over ranks',
+                       'stage_ms': {'assembly+precondition': stage[0], 'factor': stage[1], 'solve+datum': stage[2],
+                                    'inverse+Qxx epilogue': stage[3], 'omega': stage[4]},
+                       'wall_ms_per_step': wall_ms_max / args.steps},
+            'roofline': roofline, 'clocks': clocks, 'gpu_launches': int(launches)}
+    if e2e:
+        line['e2e'] = e2e
+    if not args.no_cpu_baseline and world == 1:
+        line['cpu_baseline'] = cpu_sample(args.config, n, flat['obj_idx'].size, 1)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

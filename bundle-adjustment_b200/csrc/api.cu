@@ -23,6 +23,7 @@ long long g_launch_count = 0;
 void launch_gemm(const GemmDesc &g, cudaStream_t s);
 void launch_potrf_diag(double *A, int64_t ld, double *dinv, int row0, int *info, cudaStream_t s);
 void launch_copy2d(double *dst, int64_t ldd, const double *src, int64_t lds, int64_t rows, int64_t cols, cudaStream_t s);
+void launch_solve_rows8(const double *L, int64_t ld, const double *dinv, double *R, double *Y, int64_t np, cudaStream_t s);
 // stage_kernels.cu
 void launch_precond_diag(const double *M, int64_t ld, int u, int64_t np, double *V, cudaStream_t s);
 void launch_datum_rows(const double *xyz, const int32_t *pt_col, const int32_t *datum_pts, int nDatum, int free_mask, int d,
@@ -317,7 +318,7 @@ void prepare(jaicov_handle *h) {
     h->Dinv.alloc(np * kBlk);
     h->rhs.alloc(np); h->V.alloc(np);
     h->Bt.alloc(8 * np); h->Btv.alloc(8 * np); h->H.alloc(8 * np); h->Tq.alloc(8 * np);
-    h->Rt.alloc((size_t)kRhsRows * np);
+    h->Rt.alloc((size_t)kRhsRows * np);   // 8 right-hand-side rows: n, datum rows
     h->small.alloc(128); h->dxref.alloc(np + 8); h->omega_parts.alloc(4 + h->groups.size());
     h->info.alloc(1); h->upd.alloc(2);
     JCHECK(cudaMemset(h->dxref.p, 0, (np + 8) * sizeof(double)));
@@ -415,7 +416,7 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     ds.potrf();
     JCHECK(cudaEventRecord(h->ev[2], s));
     // solve for n and the datum rows, datum correction, dx (K5/K9)
-    ds.solve_rows(h->Rt.p, P.np, 1);
+    launch_solve_rows8(h->M.p, P.np, h->Dinv.p, h->Rt.p, h->Rt.p + 8 * np, P.np, s);
     launch_datum_solve(h->Rt.p, h->Btv.p, P.d, P.np, P.u, h->V.p, h->dxref.p, h->H.p, h->Tq.p, h->small.p, s);
     JCHECK(cudaEventRecord(h->ev[3], s));
     // inverse (K6/K7)
@@ -943,7 +944,8 @@ int32_t jaicov_spd_solve_invert(int32_t device, int64_t n, double *a, int32_t nr
     cudaEventRecord(e0, s);
     ds.potrf();
     cudaEventRecord(e1, s);
-    if (nrhs) ds.solve_rows(Rt.p, np, 1);
+    if (nrhs > 0 && nrhs <= 8) launch_solve_rows8(M.p, np, Dinv.p, Rt.p, Rt.p + 8 * np, np, s);
+    else if (nrhs) ds.solve_rows(Rt.p, np, 1);
     cudaEventRecord(e2, s);
     if (invert) { ds.invert_from_factor(W.p); launch_symmetrize(M.p, np, (int)n, s); }
     cudaEventRecord(e3, s);

@@ -14,7 +14,7 @@ namespace jaicov {
 constexpr int kBlk = 128;          // base block / tile edge of every dense kernel
 constexpr int kMaxCoef = 64;       // coefficients per camera staged in shared memory
 constexpr int kMaxDatum = 7;
-constexpr int kRhsRows = 128;      // right-hand-side block: row 0 = n, rows 1..d = datum rows, rest zero
+constexpr int kRhsRows = 128;      // rows of the right-hand-side buffer (row 0 = n, rows 1..d = datum rows; 8 used by the loop)
 constexpr double kEps = 1.1102230246251565e-16;  // Constant.EPS = 2^-53 (Constant.java:61-75)
 
 extern long long g_launch_count;   // kernels launched by this library (diagnostic, jaicov_launch_count)

@@ -9,6 +9,7 @@
 //  k_potrf_diag    one CTA: Cholesky of a 128 x 128 diagonal block in shared memory (left-looking), the factor is
 //                  written back and then inverted in place (dtrti2-style) to give Dinv, which turns every
 //                  triangular solve of the schedule into a GEMM.
+#include <algorithm>
 #include <cmath>
 
 #include "common.h"
@@ -185,70 +186,86 @@ void launch_gemm(const GemmDesc &g, cudaStream_t s) {
 }
 
 // ---- diagonal block: factor + invert ----------------------------------------------------------------------------
-constexpr int DP = 129;  // shared-memory pitch (odd => thread-per-row accesses are conflict-free)
+// 512 threads: 4 lanes per matrix row split every dot product (k = q mod 4) and combine with two shuffles, so a
+// column step costs <= 32 (2 LDS + FMA) per lane instead of 128.  The shared-memory pitch is == 4 (mod 16) doubles:
+// the 16 lanes of a half-warp (4 rows x 4 k-phases) hit 16 distinct 8-byte banks.  The pivot dot product is
+// recomputed by every row (no broadcast), which leaves ONE barrier per column in the factorisation.
+constexpr int DP = 132;
+constexpr int DTHREADS = 512;
 
-__global__ void __launch_bounds__(128, 1) k_potrf_diag(double *__restrict__ A, int64_t ld, double *__restrict__ dinv,
-                                                        int row0, int *__restrict__ info) {
+__global__ void __launch_bounds__(DTHREADS, 1) k_potrf_diag(double *__restrict__ A, int64_t ld, double *__restrict__ dinv,
+                                                             int row0, int *__restrict__ info) {
     extern __shared__ double a[];   // [128][DP]
-    __shared__ double s_piv;
-    const int i = threadIdx.x;
-    // load the lower triangle (coalesced by rows)
-    for (int r = 0; r < 128; r++) a[r * DP + i] = (i <= r) ? A[(int64_t)r * ld + i] : 0.0;
+    __shared__ double s_diag[128];
+    const int tid = threadIdx.x;
+    const int i = tid >> 2, q = tid & 3;
+    // load the lower triangle, coalesced: 4 rows of 128 per pass
+    {
+        const int c = tid & 127, r0 = tid >> 7;
+#pragma unroll 8
+        for (int r = r0; r < 128; r += 4) a[r * DP + c] = (c <= r) ? A[(int64_t)r * ld + c] : 0.0;
+    }
     __syncthreads();
-    // left-looking Cholesky: column j <- (a[:,j] - L[:, :j] L[j, :j]') / sqrt(pivot)
+    // left-looking Cholesky
+    const double *ri = a + i * DP;
     for (int j = 0; j < 128; j++) {
-        double s = 0.0;
+        const double *rj = a + j * DP;
+        double s = 0.0, p = 0.0;
         if (i >= j) {
-            s = a[i * DP + j];
-            const double *ri = a + i * DP, *rj = a + j * DP;
-            double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
-            int k = 0;
-            for (; k + 4 <= j; k += 4) {
-                s1 += ri[k] * rj[k];
-                s2 += ri[k + 1] * rj[k + 1];
-                s3 += ri[k + 2] * rj[k + 2];
-                s4 += ri[k + 3] * rj[k + 3];
+            for (int k = q; k < j; k += 4) {
+                const double x = rj[k];
+                s += ri[k] * x;
+                p += x * x;
             }
-            for (; k < j; k++) s1 += ri[k] * rj[k];
-            s -= (s1 + s2) + (s3 + s4);
         }
-        if (i == j) s_piv = s;
-        __syncthreads();
-        const double piv = s_piv;
-        if (i == j) {
-            if (!(piv > 0.0)) atomicCAS(info, 0, row0 + j + 1);
-            a[i * DP + j] = sqrt(piv);
-        } else if (i > j) {
-            a[i * DP + j] = s / sqrt(piv);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        p += __shfl_xor_sync(0xffffffffu, p, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        p += __shfl_xor_sync(0xffffffffu, p, 2);
+        // the factored diagonal goes to s_diag so that a[j][j] keeps its input value: nothing read in this step is
+        // overwritten in this step (a[i][j] is read and written by the same thread), hence a single barrier
+        if (i >= j && q == 0) {
+            const double piv = rj[j] - p;
+            if (i == j) {
+                if (!(piv > 0.0)) atomicCAS(info, 0, row0 + j + 1);
+                s_diag[j] = sqrt(piv);
+            } else {
+                a[i * DP + j] = (ri[j] - s) / sqrt(piv);
+            }
         }
         __syncthreads();
     }
-    // write the factor back (lower triangle only)
-    for (int r = 0; r < 128; r++)
-        if (i <= r) A[(int64_t)r * ld + i] = a[r * DP + i];
+    if (tid < 128) a[tid * DP + tid] = s_diag[tid];
     __syncthreads();
+    // write the factor back (lower triangle only)
+    {
+        const int c = tid & 127, r0 = tid >> 7;
+#pragma unroll 8
+        for (int r = r0; r < 128; r += 4)
+            if (c <= r) A[(int64_t)r * ld + c] = a[r * DP + c];
+    }
     // in-place inversion of the lower-triangular factor, last column first (dtrti2, lower):
     //   inv[j][j] = 1/L[j][j];  inv[i][j] = -(sum_{k=j+1..i} inv[i][k] L[k][j]) * inv[j][j]
     for (int j = 127; j >= 0; j--) {
         const double ajj = 1.0 / a[j * DP + j];
         double s = 0.0;
         if (i > j) {
-            const double *ri = a + i * DP;
-            double s1 = 0.0, s2 = 0.0;
-            int k = j + 1;
-            for (; k + 2 <= i + 1; k += 2) {
-                s1 += ri[k] * a[k * DP + j];
-                s2 += ri[k + 1] * a[(k + 1) * DP + j];
-            }
-            for (; k <= i; k++) s1 += ri[k] * a[k * DP + j];
-            s = s1 + s2;
+            for (int k = j + 1 + q; k <= i; k += 4) s += ri[k] * a[k * DP + j];
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        __syncthreads();
+        if (q == 0) {
+            if (i > j) a[i * DP + j] = -s * ajj;
+            else if (i == j) a[j * DP + j] = ajj;
         }
         __syncthreads();
-        if (i > j) a[i * DP + j] = -s * ajj;
-        else if (i == j) a[j * DP + j] = ajj;
-        __syncthreads();
     }
-    for (int r = 0; r < 128; r++) dinv[r * 128 + i] = (i <= r) ? a[r * DP + i] : 0.0;
+    {
+        const int c = tid & 127, r0 = tid >> 7;
+#pragma unroll 8
+        for (int r = r0; r < 128; r += 4) dinv[r * 128 + c] = (c <= r) ? a[r * DP + c] : 0.0;
+    }
 }
 
 void launch_potrf_diag(double *A, int64_t ld, double *dinv, int row0, int *info, cudaStream_t s) {
@@ -259,7 +276,7 @@ void launch_potrf_diag(double *A, int64_t ld, double *dinv, int row0, int *info,
         attr = true;
     }
     g_launch_count++;
-    k_potrf_diag<<<1, 128, smem, s>>>(A, ld, dinv, row0, info);
+    k_potrf_diag<<<1, DTHREADS, smem, s>>>(A, ld, dinv, row0, info);
 }
 
 // ---- 2-D copy ---------------------------------------------------------------------------------------------------
@@ -279,6 +296,145 @@ void launch_copy2d(double *dst, int64_t ldd, const double *src, int64_t lds, int
     const int64_t blocks = (total + 255) / 256;
     g_launch_count++;
     k_copy2d<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, s>>>(dst, ldd, src, lds, rows, cols / 2);
+}
+
+}  // namespace jaicov
+
+namespace jaicov {
+
+// ---- skinny triangular solves: NR = 8 right-hand sides stored as rows R[8][np] ------------------------------------
+// One launch per 128-block step, right-looking, every launch spread over the rows (forward) or columns (backward)
+// still to be updated; the 128 x 128 diagonal solve is the multiplication by Dinv and is recomputed by every CTA
+// (128 KB from L2) instead of being a separate launch.  HBM/L2-bound: L is read exactly once per sweep.
+constexpr int SR = 8;          // right-hand sides
+constexpr int SCHUNK = 512;    // rows (forward) / columns (backward) per CTA
+
+// forward step j: y_j = Dinv_j b_j;  b[i] -= L[i, J] y_j for all rows i below block j
+// (b lives in R and is updated in place below block j; y_j goes to the separate buffer Y so that no CTA can see a
+// half-updated block j)
+__global__ void __launch_bounds__(256) k_solve_fwd_step(const double *__restrict__ L, int64_t ld, const double *__restrict__ dinv,
+                                                        double *__restrict__ R, double *__restrict__ Y, int64_t np, int j) {
+    __shared__ double sb[SR][128];
+    __shared__ double sy[SR][128];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t J = (int64_t)j * 128;
+    for (int i = tid; i < SR * 128; i += 256) sb[i >> 7][i & 127] = R[(int64_t)(i >> 7) * np + J + (i & 127)];
+    __syncthreads();
+    const double *D = dinv + J * 128;
+    // y[t] = sum_k Dinv[t][k] b[k]: one warp per row, lanes over k
+    for (int t = warp; t < 128; t += 8) {
+        double acc[SR];
+#pragma unroll
+        for (int r = 0; r < SR; r++) acc[r] = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+            const int k = lane + 32 * kk;
+            const double dv = D[t * 128 + k];
+#pragma unroll
+            for (int r = 0; r < SR; r++) acc[r] += dv * sb[r][k];
+        }
+#pragma unroll
+        for (int r = 0; r < SR; r++) {
+            double v = acc[r];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) sy[r][t] = v;
+        }
+    }
+    __syncthreads();
+    if (blockIdx.x == 0)
+        for (int i = tid; i < SR * 128; i += 256) Y[(int64_t)(i >> 7) * np + J + (i & 127)] = sy[i >> 7][i & 127];
+    // rows below
+    const int64_t row0 = J + 128 + (int64_t)blockIdx.x * SCHUNK;
+    const int64_t row1 = min(np, row0 + SCHUNK);
+    for (int64_t i = row0 + warp; i < row1; i += 8) {
+        const double *Li = L + i * ld + J;
+        double acc[SR];
+#pragma unroll
+        for (int r = 0; r < SR; r++) acc[r] = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+            const int k = lane + 32 * kk;
+            const double lv = Li[k];
+#pragma unroll
+            for (int r = 0; r < SR; r++) acc[r] += lv * sy[r][k];
+        }
+#pragma unroll
+        for (int r = 0; r < SR; r++) {
+            double v = acc[r];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            acc[r] = v;
+        }
+        if (lane < SR) {
+            double v = acc[0];
+#pragma unroll
+            for (int r = 1; r < SR; r++) v = (lane == r) ? acc[r] : v;
+            R[(int64_t)lane * np + i] -= v;
+        }
+    }
+}
+
+// backward step j: x_j = Dinv_j' y_j;  y[c] -= sum_{i in J} L[i][c] x_j[i] for all columns c left of block j
+// (y lives in Y and is updated in place left of block j; x_j goes to R)
+__global__ void __launch_bounds__(256) k_solve_bwd_step(const double *__restrict__ L, int64_t ld, const double *__restrict__ dinv,
+                                                        double *__restrict__ R, double *__restrict__ Y, int64_t np, int j) {
+    __shared__ double sy[SR][128];
+    __shared__ double sx[SR][128];
+    const int tid = threadIdx.x;
+    const int64_t J = (int64_t)j * 128;
+    for (int i = tid; i < SR * 128; i += 256) sy[i >> 7][i & 127] = Y[(int64_t)(i >> 7) * np + J + (i & 127)];
+    __syncthreads();
+    const double *D = dinv + J * 128;
+    if (tid < 128) {   // x[t] = sum_k Dinv[k][t] y[k]  (coalesced over t)
+        double acc[SR];
+#pragma unroll
+        for (int r = 0; r < SR; r++) acc[r] = 0.0;
+        for (int k = tid; k < 128; k++) {     // Dinv[k][t] = 0 for k < t
+            const double dv = D[k * 128 + tid];
+#pragma unroll
+            for (int r = 0; r < SR; r++) acc[r] += dv * sy[r][k];
+        }
+#pragma unroll
+        for (int r = 0; r < SR; r++) sx[r][tid] = acc[r];
+    }
+    __syncthreads();
+    if (blockIdx.x == 0)
+        for (int i = tid; i < SR * 128; i += 256) R[(int64_t)(i >> 7) * np + J + (i & 127)] = sx[i >> 7][i & 127];
+    if (j == 0) return;
+    const int64_t c0 = (int64_t)blockIdx.x * SCHUNK;
+    for (int64_t c = c0 + tid; c < min(J, c0 + SCHUNK); c += 256) {
+        double acc[SR];
+#pragma unroll
+        for (int r = 0; r < SR; r++) acc[r] = 0.0;
+        const double *Lc = L + J * ld + c;
+#pragma unroll 4
+        for (int i = 0; i < 128; i++) {
+            const double lv = Lc[(int64_t)i * ld];
+#pragma unroll
+            for (int r = 0; r < SR; r++) acc[r] += lv * sx[r][i];
+        }
+#pragma unroll
+        for (int r = 0; r < SR; r++) Y[(int64_t)r * np + c] -= acc[r];
+    }
+}
+
+// R[8][np] <- (L L')^-1 R' (rows are right-hand sides), L = lower factor in M, Dinv = inverted diagonal blocks
+// Y: scratch of the same size as R
+void launch_solve_rows8(const double *L, int64_t ld, const double *dinv, double *R, double *Y, int64_t np, cudaStream_t s) {
+    const int nb = (int)(np / 128);
+    for (int j = 0; j < nb; j++) {
+        const int64_t below = np - (int64_t)(j + 1) * 128;
+        const int grid = (int)std::max<int64_t>(1, (below + SCHUNK - 1) / SCHUNK);
+        g_launch_count++;
+        k_solve_fwd_step<<<grid, 256, 0, s>>>(L, ld, dinv, R, Y, np, j);
+    }
+    for (int j = nb - 1; j >= 0; j--) {
+        const int64_t left = (int64_t)j * 128;
+        const int grid = (int)std::max<int64_t>(1, (left + SCHUNK - 1) / SCHUNK);
+        g_launch_count++;
+        k_solve_bwd_step<<<grid, 256, 0, s>>>(L, ld, dinv, R, Y, np, j);
+    }
 }
 
 }  // namespace jaicov
