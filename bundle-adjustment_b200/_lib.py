@@ -20,7 +20,8 @@ L2NORM, SIMULATION = 0, 1
 COL_UNSET, COL_FIXED = -1, 2147483647
 
 EXPORTS = [
-    'jaicov_default_options', 'jaicov_create', 'jaicov_destroy', 'jaicov_last_error', 'jaicov_device_count', 'jaicov_launch_count',
+    'jaicov_default_options', 'jaicov_create', 'jaicov_destroy', 'jaicov_last_error', 'jaicov_device_count', 'jaicov_launch_count', 'jaicov_nccl_unique_id', 'jaicov_dist_init',
+    'jaicov_get_qxx_local', 'jaicov_shard_images',
     'jaicov_set_cameras', 'jaicov_set_images', 'jaicov_set_image_points', 'jaicov_set_object_points',
     'jaicov_set_scale_bars', 'jaicov_add_observed_group', 'jaicov_set_datum', 'jaicov_estimate', 'jaicov_iterate',
     'jaicov_get_stats', 'jaicov_get_values', 'jaicov_get_dx', 'jaicov_get_qxx_packed', 'jaicov_get_qxx_block',
@@ -68,6 +69,10 @@ def load():
     L.jaicov_last_error.restype = ctypes.c_char_p
     L.jaicov_device_count.argtypes = []
     L.jaicov_launch_count.argtypes = []
+    L.jaicov_nccl_unique_id.argtypes = [vp]
+    L.jaicov_shard_images.argtypes = [i32, vp, i32, i32, ctypes.POINTER(i32), ctypes.POINTER(i32)]
+    L.jaicov_dist_init.argtypes = [vp, i32, i32, vp]
+    L.jaicov_get_qxx_local.argtypes = [vp, vp, vp, i32, vp]
     L.jaicov_set_cameras.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.jaicov_set_images.argtypes = [vp, i32, vp, vp, vp, vp]
     L.jaicov_set_image_points.argtypes = [vp, i64, vp, vp, vp, vp]
@@ -186,6 +191,23 @@ class Session:
         self.shapes = dict(xyz=xyz.size, io=io_val.size, coef=cv.size, eo=ev.size, m=oi.size,
                            ncoef_max=int(np.max(np.diff(cp))) if cp.size > 1 else 0)
 
+    def dist_init(self, rank, world, nccl_id: bytes):
+        """Joins the NCCL communicator of a multi-GPU adjustment (call before set_problem)."""
+        buf = ctypes.create_string_buffer(bytes(nccl_id), 128)
+        self.check(self.L.jaicov_dist_init(self.h, rank, world, buf))
+        self.rank, self.world = rank, world
+
+    def qxx_local(self):
+        """(first reference column of every owned 128-wide tile, np x 128*ntiles array) of a distributed handle."""
+        nt = ctypes.c_int32(0)
+        self.check(self.L.jaicov_get_qxx_local(self.h, ctypes.byref(nt), None, 0, None))
+        cols = np.zeros(max(nt.value, 1), np.int32)
+        u = int(self.flat['n_unknowns'])
+        npad = (max(u, 1) + 127) // 128 * 128
+        out = np.empty((npad, 128 * nt.value))
+        self.check(self.L.jaicov_get_qxx_local(self.h, ctypes.byref(nt), cols.ctypes.data, nt.value, out.ctypes.data if nt.value else None))
+        return cols[:nt.value], out
+
     def estimate(self, progress=None):
         cb = PROGRESS_CB(lambda user, st, a, b: progress(st, a, b)) if progress else None
         rc = self.L.jaicov_estimate(self.h, ctypes.cast(cb, ctypes.c_void_p) if cb else None, None, None)
@@ -248,6 +270,26 @@ class Session:
         out = ctypes.c_double(0.0)
         self.check(self.L.jaicov_omega(self.h, _p(dx), ctypes.byref(out)))
         return out.value
+
+
+def shard_images(pt_ptr, world, rank):
+    """Image range [begin, end) of `rank` (host-only; same rule the library applies internally)."""
+    L = load()
+    pp = np.ascontiguousarray(pt_ptr, dtype=np.int64)
+    b, e = ctypes.c_int32(0), ctypes.c_int32(0)
+    rc = L.jaicov_shard_images(pp.size - 1, pp.ctypes.data, world, rank, ctypes.byref(b), ctypes.byref(e))
+    if rc != OK:
+        raise JaicovError(rc, 'jaicov_shard_images')
+    return b.value, e.value
+
+
+def nccl_unique_id() -> bytes:
+    L = load()
+    buf = ctypes.create_string_buffer(128)
+    rc = L.jaicov_nccl_unique_id(buf)
+    if rc != OK:
+        raise JaicovError(rc, 'jaicov_nccl_unique_id')
+    return buf.raw
 
 
 def spd_solve_invert(a, b=None, invert=True, device=0):

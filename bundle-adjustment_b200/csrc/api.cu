@@ -14,6 +14,7 @@
 
 #include "common.h"
 #include "dense_driver.hpp"
+#include "dist.h"
 
 namespace jaicov {
 
@@ -48,6 +49,11 @@ void launch_group_omega(int r, const int32_t *col, const double *var, const doub
                         const double *dxref, double *out, cudaStream_t s);
 void launch_unpack_scaled(const double *ap, int r, double scale, double *M, int64_t ld, int64_t np, cudaStream_t s);
 void launch_symmetrize(double *M, int64_t ld, int r, cudaStream_t s);
+void launch_identity_columns(double *X, int64_t ldx, int64_t np, const int32_t *ktab, int ntc, cudaStream_t s);
+void launch_qxx_epilogue_cols(double *X, int64_t ldx, int ntc, const int32_t *ktab, int u, const double *V, const double *H,
+                              const double *G, int d, int64_t np, cudaStream_t s);
+void launch_get_block_dist(const double *X, int64_t ldx, const int32_t *col_local, const double *border, int64_t np,
+                           const double *q11, int d, int rank, int r0, int r1, int c0, int c1, double *out, cudaStream_t s);
 
 struct CudaBackend {
     cudaStream_t stream;
@@ -126,6 +132,15 @@ struct jaicov_handle {
     cudaEvent_t ev[8] = {};
     jaicov_stats stats{};
     double centroid[3] = {0, 0, 0};
+    // multi-GPU (one process per GPU)
+    DistContext dist;
+    bool dist_on = false;
+    int panel_tiles = 4;                 // block-column panel width of the distributed Cholesky, in 128-tiles
+    DevBuf<double> Xl;                   // np x (128 * ntc): this rank's column tiles of the inverse
+    DevBuf<int32_t> d_ktab, d_col_local;
+    std::vector<int32_t> ktab;
+    DevBuf<double> d_cam_sum;
+    int64_t strip_row0 = -1;             // first row of the EO strip of N that is all-reduced
 };
 
 namespace {
@@ -238,26 +253,35 @@ void prepare(jaicov_handle *h) {
     if (h->pt_ptr.empty()) h->pt_ptr.assign(1, 0);
     if (h->pt_ptr.back() != P.m) throw std::runtime_error("pt_ptr does not cover the image points");
     P.nPt = (int)(h->xyz.size() / 3);
+    // image shard of this rank: contiguous image ranges balanced by observation count
+    {
+        int32_t i0 = 0, i1 = P.nImg;
+        jaicov_shard_images(P.nImg, h->pt_ptr.data(), h->dist_on ? h->dist.world : 1, h->dist_on ? h->dist.rank : 0, &i0, &i1);
+        P.img0 = i0;
+        P.img1 = i1;
+        P.obs0 = h->pt_ptr[P.img0];
+        P.obs1 = h->pt_ptr[P.img1];
+    }
     std::vector<int32_t> img_of_obs(P.m);
     std::vector<WorkItem> work;
-    std::vector<int32_t> img_work_ptr(P.nImg + 1, 0);
+    std::vector<int32_t> img_work_ptr(P.img1 - P.img0 + 1, 0);
     const int64_t chunk = 1024;
-    for (int i = 0; i < P.nImg; i++) {
-        img_work_ptr[i] = (int32_t)work.size();
+    for (int i = 0; i < P.nImg; i++)
         for (int64_t j = h->pt_ptr[i]; j < h->pt_ptr[i + 1]; j++) img_of_obs[j] = i;
+    for (int i = P.img0; i < P.img1; i++) {
+        img_work_ptr[i - P.img0] = (int32_t)work.size();
         for (int64_t b = h->pt_ptr[i]; b < h->pt_ptr[i + 1]; b += chunk)
             work.push_back(WorkItem{i, 0, b, std::min(b + chunk, h->pt_ptr[i + 1])});
     }
-    img_work_ptr[P.nImg] = (int32_t)work.size();
-    std::vector<int64_t> pt_obs_ptr(P.nPt + 1, 0), pt_obs(P.m);
-    for (int64_t j = 0; j < P.m; j++) {
+    img_work_ptr[P.img1 - P.img0] = (int32_t)work.size();
+    std::vector<int64_t> pt_obs_ptr(P.nPt + 1, 0), pt_obs(std::max<int64_t>(P.obs1 - P.obs0, 1));
+    for (int64_t j = 0; j < P.m; j++)
         if (h->obj_idx[j] < 0 || h->obj_idx[j] >= P.nPt) throw std::runtime_error("object point index out of range");
-        pt_obs_ptr[h->obj_idx[j] + 1]++;
-    }
+    for (int64_t j = P.obs0; j < P.obs1; j++) pt_obs_ptr[h->obj_idx[j] + 1]++;
     for (int p = 0; p < P.nPt; p++) pt_obs_ptr[p + 1] += pt_obs_ptr[p];
     {
         std::vector<int64_t> cur(pt_obs_ptr.begin(), pt_obs_ptr.end() - 1);
-        for (int64_t j = 0; j < P.m; j++) pt_obs[cur[h->obj_idx[j]]++] = j;
+        for (int64_t j = P.obs0; j < P.obs1; j++) pt_obs[cur[h->obj_idx[j]]++] = j;
     }
     // ---- validate columns ----------------------------------------------------------------------------------------
     auto check_cols = [&](const std::vector<int32_t> &c) {
@@ -306,15 +330,39 @@ void prepare(jaicov_handle *h) {
     const int NCi = 8 * S.ntImg, NCp = 8 * S.ntPt;
     h->d_img_partial.alloc((size_t)std::max(S.nWork, 1) * NCi * NCi);
     h->d_cam_partial.alloc((size_t)std::max(P.nImg, 1) * S.kcMax * (S.kcMax + 1));
+    h->d_cam_sum.alloc((size_t)std::max(P.nCam, 1) * S.kcMax * (S.kcMax + 1));
+    S.cam_sum = h->d_cam_sum.p;
     h->d_pt_partial.alloc((size_t)std::max(P.nPt, 1) * 3 * NCp);
-    S.omegaBlocks = (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (P.m + 255) / 256));
+    S.omegaBlocks = (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (P.obs1 - P.obs0 + 255) / 256));
     h->d_omega_partial.alloc(S.omegaBlocks + 2);
     S.img_partial = h->d_img_partial.p; S.cam_partial = h->d_cam_partial.p; S.pt_partial = h->d_pt_partial.p;
     S.omega_partial = h->d_omega_partial.p;
     // ---- system buffers ------------------------------------------------------------------------------------------
     const size_t np = (size_t)P.np;
     h->M.alloc(np * np);
-    if (h->opt.invert_mode == JAICOV_INVERT_FULL) h->W.alloc(np * np);
+    if (h->dist_on) {
+        // column tiles of the inverse owned by this rank: tile c belongs to rank (c / panel_tiles) % world
+        const int nb = (int)(P.np / kBlk);
+        h->ktab.clear();
+        std::vector<int32_t> col_local(nb, -1);
+        for (int c = 0; c < nb; c++)
+            if ((c / h->panel_tiles) % h->dist.world == h->dist.rank) {
+                col_local[c] = (int32_t)h->ktab.size();
+                h->ktab.push_back(c * kBlk);
+            }
+        h->d_col_local.upload(col_local);
+        std::vector<int32_t> kt = h->ktab;
+        if (kt.empty()) kt.push_back(0);
+        h->d_ktab.upload(kt);
+        if (h->opt.invert_mode == JAICOV_INVERT_FULL) h->Xl.alloc(np * (size_t)kBlk * std::max<size_t>(h->ktab.size(), 1));
+        // EO strip of N: every entry the image sweeps write lies in a row >= the smallest EO row
+        int64_t r0 = -1;
+        for (int32_t c : h->eo_col)
+            if (active(c)) r0 = (r0 < 0) ? c - d : std::min<int64_t>(r0, c - d);
+        h->strip_row0 = r0;
+    } else if (h->opt.invert_mode == JAICOV_INVERT_FULL) {
+        h->W.alloc(np * np);
+    }
     h->Dinv.alloc(np * kBlk);
     h->rhs.alloc(np); h->V.alloc(np);
     h->Bt.alloc(8 * np); h->Btv.alloc(8 * np); h->H.alloc(8 * np); h->Tq.alloc(8 * np);
@@ -376,7 +424,17 @@ void assemble(jaicov_handle *h) {
     JCHECK(cudaMemsetAsync(h->rhs.p, 0, np * sizeof(double), s));
     JCHECK(cudaMemsetAsync(h->Bt.p, 0, 8 * np * sizeof(double), s));
     launch_pose(P, s);
-    launch_assemble(P, h->S, h->M.p, h->rhs.p, s);
+    launch_assemble_local(P, h->S, h->M.p, h->rhs.p, s);
+    if (h->dist_on && h->dist.world > 1) {
+        // the only exchange of the assembly: sum the shared pieces over the image shards
+        const AssemblyScratch &S = h->S;
+        h->dist.allreduce_sum(S.pt_partial, (size_t)P.nPt * 3 * 8 * S.ntPt, s);
+        h->dist.allreduce_sum(S.cam_sum, (size_t)P.nCam * S.kcMax * (S.kcMax + 1), s);
+        h->dist.allreduce_sum(h->rhs.p, (size_t)P.np, s);
+        if (h->strip_row0 >= 0)
+            h->dist.allreduce_sum(h->M.p + (size_t)h->strip_row0 * np, ((size_t)P.np - h->strip_row0) * np, s);
+    }
+    launch_assemble_shared(P, h->S, h->M.p, h->rhs.p, s);
     launch_scale_bars(P, h->M.p, h->rhs.p, s);
     for (Group &g : h->groups) {
         launch_group_w(g.r, g.tptr.p, g.d_obs.p, g.w.p, s);
@@ -413,14 +471,35 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     JCHECK(cudaMemsetAsync(h->info.p, 0, sizeof(int), s));
     CudaBackend be{s, h->info.p};
     DenseSchedule<CudaBackend> ds{be, h->M.p, P.np, P.np, h->Dinv.p};
-    ds.potrf();
+    const bool multi = h->dist_on && h->dist.world > 1;
+    if (multi) {
+        PanelComm pc{&h->dist, s, h->M.p, P.np, P.np, h->Dinv.p, h->panel_tiles};
+        pc.ensure_stage((size_t)P.np * h->panel_tiles * kBlk + (size_t)h->panel_tiles * kBlk * kBlk);
+        ds.potrf_distributed(pc, h->dist.rank, h->dist.world, h->panel_tiles);
+        // the last broadcasts this rank rooted are still on the network stream: later stages (and the next pass,
+        // which re-uses the staging buffers) are ordered after them
+        JCHECK(cudaEventRecord(h->dist.ev_tmp, h->dist.net));
+        JCHECK(cudaStreamWaitEvent(s, h->dist.ev_tmp, 0));
+    } else {
+        ds.potrf();
+    }
     JCHECK(cudaEventRecord(h->ev[2], s));
     // solve for n and the datum rows, datum correction, dx (K5/K9)
     launch_solve_rows8(h->M.p, P.np, h->Dinv.p, h->Rt.p, h->Rt.p + 8 * np, P.np, s);
     launch_datum_solve(h->Rt.p, h->Btv.p, P.d, P.np, P.u, h->V.p, h->dxref.p, h->H.p, h->Tq.p, h->small.p, s);
     JCHECK(cudaEventRecord(h->ev[3], s));
     // inverse (K6/K7)
-    if (invert) {
+    if (invert && h->dist_on) {
+        // every rank inverts its own column tiles from the replicated factor: no communication
+        const int ntc = (int)h->ktab.size();
+        if (ntc > 0) {
+            const int64_t ldx = (int64_t)ntc * kBlk;
+            JCHECK(cudaMemsetAsync(h->Xl.p, 0, np * (size_t)ldx * sizeof(double), s));
+            launch_identity_columns(h->Xl.p, ldx, P.np, h->d_ktab.p, ntc, s);
+            ds.inverse_columns(h->Xl.p, ldx, ntc, h->d_ktab.p);
+            launch_qxx_epilogue_cols(h->Xl.p, ldx, ntc, h->d_ktab.p, P.u, h->V.p, h->H.p, h->Rt.p + np, P.d, P.np, s);
+        }
+    } else if (invert) {
         ds.invert_from_factor(h->W.p);
         launch_qxx_epilogue(h->M.p, P.np, P.u, h->V.p, h->H.p, h->Rt.p + np, P.d, P.np, s);
     }
@@ -429,6 +508,7 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     const bool want_omega = final_pass && h->opt.estimation_type != JAICOV_SIMULATION;
     if (want_omega) {
         launch_omega(P, h->S, h->dxref.p, h->omega_parts.p, s);
+        if (multi) h->dist.allreduce_sum(h->omega_parts.p, 1, s);
         if (P.nBar) launch_omega_bars(P, h->dxref.p, h->omega_parts.p + 1, s);
         int gi = 0;
         for (Group &g : h->groups) {
@@ -456,6 +536,14 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     if (P.d > 0) JCHECK(cudaMemcpyAsync(&small99, h->small.p + 98, sizeof(double), cudaMemcpyDeviceToHost, s));
     JCHECK(cudaStreamSynchronize(s));
     if (small99 != 0.0 && r.info == 0) r.info = -1;
+    if (multi) {   // a failed pivot is seen by the panel's owner only: agree on the status
+        double flag = r.info != 0 ? 1.0 : 0.0, *dflag = h->small.p + 120;
+        JCHECK(cudaMemcpyAsync(dflag, &flag, sizeof(double), cudaMemcpyHostToDevice, s));
+        h->dist.allreduce_sum(dflag, 1, s);
+        JCHECK(cudaMemcpyAsync(&flag, dflag, sizeof(double), cudaMemcpyDeviceToHost, s));
+        JCHECK(cudaStreamSynchronize(s));
+        if (flag != 0.0 && r.info == 0) r.info = -2;
+    }
     memcpy(&r.max_abs_dx, &upd[0], sizeof(double));
     r.bad = upd[1] != 0;
     if (want_omega) {
@@ -562,6 +650,7 @@ void jaicov_destroy(jaicov_handle *h) {
     if (h->stream) {
         cudaSetDevice(h->opt.device);
         cudaStreamSynchronize(h->stream);
+        if (h->dist_on) { cudaDeviceSynchronize(); h->dist.destroy(); }
         for (auto &e : h->ev) if (e) cudaEventDestroy(e);
         cudaStreamDestroy(h->stream);
     }
@@ -569,6 +658,46 @@ void jaicov_destroy(jaicov_handle *h) {
 }
 
 const char *jaicov_last_error(const jaicov_handle *h) { return h ? h->err.c_str() : "null handle"; }
+
+int32_t jaicov_shard_images(int32_t n_img, const int64_t *pt_ptr, int32_t world, int32_t rank, int32_t *img_begin, int32_t *img_end) {
+    if (n_img < 0 || !pt_ptr || world < 1 || rank < 0 || rank >= world || !img_begin || !img_end) return JAICOV_ILLEGAL_ARGUMENT;
+    const int64_t m = pt_ptr[n_img];
+    auto bound = [&](int r) -> int32_t {
+        if (r <= 0) return 0;
+        if (r >= world) return n_img;
+        const int64_t target = m * r / world;
+        return (int32_t)(std::lower_bound(pt_ptr, pt_ptr + n_img + 1, target) - pt_ptr);
+    };
+    const int32_t b0 = std::min(bound(rank), n_img);
+    *img_begin = b0;
+    *img_end = std::min(std::max(bound(rank + 1), b0), n_img);
+    return JAICOV_OK;
+}
+
+int32_t jaicov_nccl_unique_id(void *out128) {
+    if (!out128) return JAICOV_ILLEGAL_ARGUMENT;
+    jaicov_handle *h = nullptr;
+    API_GUARD_BEGIN
+    NcclUniqueId id;
+    nccl_unique_id(&id);
+    memcpy(out128, &id, sizeof id);
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+int32_t jaicov_dist_init(jaicov_handle *h, int32_t rank, int32_t world, const void *nccl_id128) {
+    if (!h || world < 1 || rank < 0 || rank >= world || !nccl_id128) return JAICOV_ILLEGAL_ARGUMENT;
+    API_GUARD_BEGIN
+    if (usable_devices() == 0) throw CudaError{cudaErrorNoDevice, "no sm_100 device: jaicov_b200 has no CPU path", __FILE__, __LINE__};
+    JCHECK(cudaSetDevice(h->opt.device));
+    NcclUniqueId id;
+    memcpy(&id, nccl_id128, sizeof id);
+    h->dist.init(rank, world, id);
+    h->dist_on = true;
+    h->prepared = false;
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
 
 int32_t jaicov_set_cameras(jaicov_handle *h, int32_t n_cam, const double *io_val, const int32_t *io_col, const double *r0,
                            const int32_t *coef_ptr, const int32_t *coef_type, const int32_t *coef_order, const double *coef_val,
@@ -799,6 +928,7 @@ static int32_t pack_to_host(jaicov_handle *h, const double *border, const double
 int32_t jaicov_get_qxx_packed(jaicov_handle *h, double *dst) {
     if (!h || !dst) return JAICOV_ILLEGAL_ARGUMENT;
     if (!h->have_qxx) return fail(h, JAICOV_NOT_INITIALISED, "no cofactor matrix: run a final pass with invert_mode FULL");
+    if (h->dist_on) return fail(h, JAICOV_ILLEGAL_ARGUMENT, "distributed handle: Qxx is spread over the ranks, use jaicov_get_qxx_block (partial sums) or jaicov_get_qxx_local");
     API_GUARD_BEGIN
     JCHECK(cudaSetDevice(h->opt.device));
     return pack_to_host(h, h->Tq.p, h->small.p + 49, dst);
@@ -817,7 +947,11 @@ int32_t jaicov_get_qxx_block(jaicov_handle *h, int32_t r0, int32_t r1, int32_t c
     tmp.alloc((size_t)std::min<int64_t>(rows_per, std::max(1, r1 - r0)) * std::max(1, c1 - c0));
     for (int64_t r = r0; r < r1; r += rows_per) {
         const int rr1 = (int)std::min<int64_t>(r1, r + rows_per);
-        launch_get_block(h->M.p, h->P.np, h->Tq.p, h->P.np, h->small.p + 49, h->P.d, (int)r, rr1, c0, c1, tmp.p, h->stream);
+        if (h->dist_on)
+            launch_get_block_dist(h->Xl.p, (int64_t)h->ktab.size() * kBlk, h->d_col_local.p, h->Tq.p, h->P.np, h->small.p + 49, h->P.d,
+                                  h->dist.rank, (int)r, rr1, c0, c1, tmp.p, h->stream);
+        else
+            launch_get_block(h->M.p, h->P.np, h->Tq.p, h->P.np, h->small.p + 49, h->P.d, (int)r, rr1, c0, c1, tmp.p, h->stream);
         JCHECK(cudaMemcpy2DAsync(dst + (r - r0) * ld, ld * sizeof(double), tmp.p, (size_t)(c1 - c0) * sizeof(double),
                                  (size_t)(c1 - c0) * sizeof(double), rr1 - r, cudaMemcpyDeviceToHost, h->stream));
         JCHECK(cudaStreamSynchronize(h->stream));
@@ -829,6 +963,7 @@ int32_t jaicov_get_qxx_block(jaicov_handle *h, int32_t r0, int32_t r1, int32_t c
 int32_t jaicov_get_qxx_diag(jaicov_handle *h, double *dst) {
     if (!h || !dst) return JAICOV_ILLEGAL_ARGUMENT;
     if (!h->have_qxx) return fail(h, JAICOV_NOT_INITIALISED, "no cofactor matrix: run a final pass with invert_mode FULL");
+    if (h->dist_on) return fail(h, JAICOV_ILLEGAL_ARGUMENT, "distributed handle: use jaicov_get_qxx_block");
     API_GUARD_BEGIN
     JCHECK(cudaSetDevice(h->opt.device));
     const DevProblem &P = h->P;
@@ -838,6 +973,23 @@ int32_t jaicov_get_qxx_diag(jaicov_handle *h, double *dst) {
     if (P.u)
         JCHECK(cudaMemcpy2D(dst + P.d, sizeof(double), h->M.p, (size_t)(P.np + 1) * sizeof(double), sizeof(double), P.u,
                             cudaMemcpyDeviceToHost));
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+int32_t jaicov_get_qxx_local(jaicov_handle *h, int32_t *n_tiles, int32_t *tile_first_col, int32_t tile_cap, double *dst) {
+    if (!h || !n_tiles) return JAICOV_ILLEGAL_ARGUMENT;
+    if (!h->dist_on) return fail(h, JAICOV_ILLEGAL_ARGUMENT, "not a distributed handle");
+    API_GUARD_BEGIN
+    *n_tiles = (int32_t)h->ktab.size();
+    if (tile_first_col)
+        for (int i = 0; i < std::min<int>(tile_cap, *n_tiles); i++) tile_first_col[i] = h->ktab[i] + h->P.d;
+    if (dst) {
+        if (!h->have_qxx) return fail(h, JAICOV_NOT_INITIALISED, "no cofactor matrix: run a final pass with invert_mode FULL");
+        JCHECK(cudaSetDevice(h->opt.device));
+        if (!h->ktab.empty())
+            JCHECK(cudaMemcpy(dst, h->Xl.p, (size_t)h->P.np * h->ktab.size() * kBlk * sizeof(double), cudaMemcpyDeviceToHost));
+    }
     return JAICOV_OK;
     API_GUARD_END(h)
 }

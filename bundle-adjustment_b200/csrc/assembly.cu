@@ -262,9 +262,9 @@ __global__ void __launch_bounds__(kImgWarps * 32) k_by_image(DevProblem P, const
 __global__ void __launch_bounds__(256) k_image_finalize(DevProblem P, AssemblyScratch S, double *__restrict__ M,
                                                          double *__restrict__ rhs) {
     extern __shared__ double G[];  // NC*NC
-    const int img = blockIdx.x, tid = threadIdx.x;
+    const int img = P.img0 + blockIdx.x, tid = threadIdx.x;
     const int NC = 8 * S.ntImg;
-    const int w0 = S.img_work_ptr[img], w1 = S.img_work_ptr[img + 1];
+    const int w0 = S.img_work_ptr[blockIdx.x], w1 = S.img_work_ptr[blockIdx.x + 1];   // work items of local image #blockIdx.x
     for (int i = tid; i < NC * NC; i += blockDim.x) {
         double s = 0.0;
         for (int w = w0; w < w1; w++) s += S.img_partial[(size_t)w * NC * NC + i];
@@ -304,12 +304,31 @@ __global__ void __launch_bounds__(256) k_image_finalize(DevProblem P, AssemblySc
     }
 }
 
-// per camera: sum the camera blocks of its images in image order, scatter into N / n
-__global__ void __launch_bounds__(256) k_camera_finalize(DevProblem P, AssemblyScratch S, double *__restrict__ M,
-                                                          double *__restrict__ rhs) {
+// per camera: sum the camera blocks of this rank's images in image order (-> cam_sum, all-reduced across ranks)
+__global__ void __launch_bounds__(256) k_camera_sum(DevProblem P, AssemblyScratch S) {
+    const int cam = blockIdx.x, tid = threadIdx.x;
+    const int kc = 3 + P.coef_ptr[cam + 1] - P.coef_ptr[cam];
+    double *out = S.cam_sum + (size_t)cam * S.kcMax * (S.kcMax + 1);
+    for (int i = tid; i < S.kcMax * (S.kcMax + 1); i += blockDim.x) {
+        const int a = i / (S.kcMax + 1), b = i % (S.kcMax + 1);
+        double s = 0.0;
+        if (a < kc && (b < kc || b == S.kcMax)) {
+            // column kcMax of cam_sum holds the rhs (cam_partial keeps it at column kc)
+            const int bsrc = (b == S.kcMax) ? kc : b;
+            for (int img = P.img0; img < P.img1; img++)
+                if (P.cam_of_img[img] == cam) s += S.cam_partial[(size_t)img * S.kcMax * (S.kcMax + 1) + a * (S.kcMax + 1) + bsrc];
+        }
+        out[i] = s;
+    }
+}
+
+// scatter the camera blocks into N / n
+__global__ void __launch_bounds__(256) k_camera_scatter(DevProblem P, AssemblyScratch S, double *__restrict__ M,
+                                                         double *__restrict__ rhs) {
     const int cam = blockIdx.x, tid = threadIdx.x;
     const int kc = 3 + P.coef_ptr[cam + 1] - P.coef_ptr[cam];
     const int32_t *cc = P.campos_col + P.cam_kbase[cam];
+    const double *in = S.cam_sum + (size_t)cam * S.kcMax * (S.kcMax + 1);
     const int64_t ld = P.np;
     const int d = P.d;
     for (int i = tid; i < kc * (kc + 1); i += blockDim.x) {
@@ -318,11 +337,8 @@ __global__ void __launch_bounds__(256) k_camera_finalize(DevProblem P, AssemblyS
         const int32_t ca = cc[a];
         if (!col_active(ca)) continue;
         if (b < kc && !col_active(cc[b])) continue;
-        double s = 0.0;
-        for (int img = 0; img < P.nImg; img++)
-            if (P.cam_of_img[img] == cam) s += S.cam_partial[(size_t)img * S.kcMax * (S.kcMax + 1) + a * (S.kcMax + 1) + b];
-        if (b < kc) M[lower_idx(ca - d, cc[b] - d, ld)] += s;
-        else rhs[ca - d] += s;
+        if (b < kc) M[lower_idx(ca - d, cc[b] - d, ld)] += in[a * (S.kcMax + 1) + b];
+        else rhs[ca - d] += in[a * (S.kcMax + 1) + S.kcMax];
     }
 }
 
@@ -405,7 +421,6 @@ __global__ void __launch_bounds__(256) k_point_scatter(DevProblem P, AssemblyScr
     if (i >= (int64_t)P.nPt * 3 * NC) return;
     const int pt = (int)(i / (3 * NC));
     const int c = (int)((i / NC) % 3), j = (int)(i % NC);
-    if (P.pt_obs_ptr[pt + 1] == P.pt_obs_ptr[pt]) return;  // no image observation
     const int32_t cp = P.pt_col[3 * (int64_t)pt + c];
     if (!col_active(cp)) return;
     const double v = S.pt_partial[i];
@@ -463,19 +478,27 @@ static void run_by_point(const DevProblem &P, const AssemblyScratch &S, cudaStre
     }
 
 // image points: N (lower, row-major, ld = np) and n.  M and rhs must be zero on entry.
-void launch_assemble(const DevProblem &P, const AssemblyScratch &S, double *M, double *rhs, cudaStream_t s) {
+void launch_assemble_local(const DevProblem &P, const AssemblyScratch &S, double *M, double *rhs, cudaStream_t s) {
     if (P.m == 0) return;
+    if (S.nWork > 0) {
 #define CALL_IMG(NT) run_by_image<NT>(P, S, M, s)
-    JAICOV_DISPATCH_NT(S.ntImg, CALL_IMG)
+        JAICOV_DISPATCH_NT(S.ntImg, CALL_IMG)
 #undef CALL_IMG
-    const int NC = 8 * S.ntImg;
+        const int NC = 8 * S.ntImg;
+        g_launch_count++;
+        k_image_finalize<<<P.img1 - P.img0, 256, NC * NC * sizeof(double), s>>>(P, S, M, rhs);
+    }
     g_launch_count++;
-    k_image_finalize<<<P.nImg, 256, NC * NC * sizeof(double), s>>>(P, S, M, rhs);
-    g_launch_count++;
-    k_camera_finalize<<<P.nCam, 256, 0, s>>>(P, S, M, rhs);
+    k_camera_sum<<<P.nCam, 256, 0, s>>>(P, S);
 #define CALL_PT(NT) run_by_point<NT>(P, S, s)
     JAICOV_DISPATCH_NT(S.ntPt, CALL_PT)
 #undef CALL_PT
+}
+
+void launch_assemble_shared(const DevProblem &P, const AssemblyScratch &S, double *M, double *rhs, cudaStream_t s) {
+    if (P.m == 0) return;
+    g_launch_count++;
+    k_camera_scatter<<<P.nCam, 256, 0, s>>>(P, S, M, rhs);
     const int64_t tot = (int64_t)P.nPt * 3 * 8 * S.ntPt;
     g_launch_count++;
     k_point_scatter<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(P, S, M, rhs);
@@ -543,7 +566,7 @@ __global__ void __launch_bounds__(kOmegaThreads) k_omega(DevProblem P, const dou
                                                          double *__restrict__ partial) {
     __shared__ double s_red[kOmegaThreads / 32];
     double local = 0.0;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < P.m; j += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t j = P.obs0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < P.obs1; j += (int64_t)gridDim.x * blockDim.x) {
         const int img = P.img_of_obs[j], cam = P.cam_of_img[img], pt = P.obj_idx[j];
         const ImgPose q = load_pose(P.pose, img);
         const CamView cv = view_global(P, cam);
@@ -594,7 +617,7 @@ __global__ void k_omega_final(const double *__restrict__ partial, int n, double 
 
 // omega_out[0] = image points part
 void launch_omega(const DevProblem &P, const AssemblyScratch &S, const double *dxref, double *omega_out, cudaStream_t s) {
-    if (P.m == 0) {
+    if (P.obs1 <= P.obs0) {
         cudaMemsetAsync(omega_out, 0, sizeof(double), s);
         return;
     }

@@ -71,6 +71,9 @@ struct DevProblem {
     int nBar = 0;
     int32_t *bar_a = nullptr, *bar_b = nullptr;
     double *bar_len = nullptr, *bar_var = nullptr;
+    // image shard of this rank (multi-GPU: contiguous image range, hence contiguous observation range)
+    int img0 = 0, img1 = 0;
+    int64_t obs0 = 0, obs1 = 0;
     // system
     int d = 0;                      // datum defect (border size)
     int u = 0;                      // unknowns
@@ -93,6 +96,7 @@ struct AssemblyScratch {
     int ntPt = 0;                   // 8-column tiles of the by-point Gram
     double *img_partial = nullptr;  // [nWork][(8 ntImg)^2]
     double *cam_partial = nullptr;  // [nImg][kc*(kc+1)] camera block + rhs of every image (kc = max raw params per camera)
+    double *cam_sum = nullptr;      // [nCam][kc*(kc+1)] sum over this rank's images (all-reduced across ranks)
     int kcMax = 0;
     double *pt_partial = nullptr;   // [nPt][3][8 ntPt]
     double *omega_partial = nullptr;  // [omegaBlocks + 2]
@@ -100,7 +104,14 @@ struct AssemblyScratch {
 };
 
 void launch_pose(const DevProblem &P, cudaStream_t s);
-void launch_assemble(const DevProblem &P, const AssemblyScratch &S, double *M, double *rhs, cudaStream_t s);
+// assembly in two halves: `local` = sweeps over this rank's images (unique EO blocks into M, packed per-point and
+// per-camera partial sums); `shared` = scatter of the (all-reduced) partial sums into M / rhs
+void launch_assemble_local(const DevProblem &P, const AssemblyScratch &S, double *M, double *rhs, cudaStream_t s);
+void launch_assemble_shared(const DevProblem &P, const AssemblyScratch &S, double *M, double *rhs, cudaStream_t s);
+inline void launch_assemble(const DevProblem &P, const AssemblyScratch &S, double *M, double *rhs, cudaStream_t s) {
+    launch_assemble_local(P, S, M, rhs, s);
+    launch_assemble_shared(P, S, M, rhs, s);
+}
 void launch_omega(const DevProblem &P, const AssemblyScratch &S, const double *dxref, double *omega_out, cudaStream_t s);
 void launch_eval_k1(const DevProblem &P, int ns_max, double *a, double *w, double *p, cudaStream_t s);
 void launch_scale_bars(const DevProblem &P, double *M, double *rhs, cudaStream_t s);

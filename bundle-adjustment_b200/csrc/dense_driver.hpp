@@ -18,6 +18,7 @@
 // The schedule is a template over a Backend so that the index logic can be exercised on the host by the unit
 // tests (tests/emul/host_backend.cpp, test-only); the product instantiates it with the CUDA backend only.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 
 namespace jaicov {
@@ -28,7 +29,9 @@ enum KMode : int {
     K_FULL = 0,       // contract over all of [0, K)
     K_B_LOWER = 1,    // B[k][n] lower triangular (k >= n): start at the tile column's diagonal
     K_A_LOWER = 2,    // A[m][k] lower triangular (k <= m): stop after the tile row's diagonal
-    K_MAX_IJ = 3      // A[k][m], B[k][n] both lower triangular: k >= max(m, n)
+    K_MAX_IJ = 3,     // A[k][m], B[k][n] both lower triangular: k >= max(m, n)
+    K_COL_BEG = 4,    // column tile jt of B is zero above global row ktab[jt]: start at ktab[jt] - koff, skip the tile if >= K
+    K_ROW_MASK = 5    // output tile (it, jt) is only wanted if its global row roff + 128 it >= ktab[jt]; full contraction
 };
 
 struct GemmDesc {
@@ -45,6 +48,9 @@ struct GemmDesc {
     int64_t ldc = 0;
     int tri_out = 0;  // only tiles with tile-row >= tile-col (mt == nt, C on the diagonal)
     int kmode = K_FULL;
+    const int32_t *ktab = nullptr;   // K_COL_BEG / K_ROW_MASK: per column tile, first global row of interest
+    int64_t koff = 0;                // K_COL_BEG: global row of k = 0
+    int64_t roff = 0;                // K_ROW_MASK: global row of output tile row 0
 };
 
 template <class BE>
@@ -169,6 +175,112 @@ struct DenseSchedule {
     void invert_from_factor(double *W) {
         trtri(W, 0, nblocks());
         lauum(W);
+    }
+
+    // ---- column-panel inverse: X = (L L')^-1 E for a SUBSET of 128-wide column tiles ------------------------------
+    // X is np x (128 ntc), row-major with leading dimension ldx; column tile jl holds global columns
+    // [ktab[jl], ktab[jl]+128) and starts as the corresponding columns of the identity.  Two wide triangular
+    // sweeps; the zero structure (forward: rows above the column's diagonal are zero; backward: only rows on or
+    // below it are wanted, Qxx is symmetric) is skipped tile by tile, so the work is 2/3 n^3 * (ntc / nblocks).
+    // No communication: with L replicated every GPU inverts its own column tiles (multi-GPU).
+    // X <- L^-1 X
+    void trsm_lln(double *X, int64_t ldx, int ntc, const int32_t *ktab, int64_t r0, int nb) {
+        if (nb == 1) {
+            GemmDesc g;
+            g.al = 0; g.bl = 1; g.mt = 1; g.nt = ntc; g.K = kTile; g.alpha = 1.0; g.beta = 0.0;
+            g.A = Dinv + r0 * kTile; g.lda = kTile;
+            g.B = X + r0 * ldx; g.ldb = ldx;
+            g.C = X + r0 * ldx; g.ldc = ldx;     // in place: tile (0, jt) reads and writes the same 128 x 128 block
+            g.kmode = K_COL_BEG; g.ktab = ktab; g.koff = r0;
+            be.gemm(g);
+            return;
+        }
+        const int hb = nb / 2, rest = nb - hb;
+        const int64_t h = (int64_t)hb * kTile;
+        trsm_lln(X, ldx, ntc, ktab, r0, hb);
+        GemmDesc g;
+        g.al = 0; g.bl = 1; g.mt = rest; g.nt = ntc; g.K = h; g.alpha = -1.0; g.beta = 1.0;
+        g.A = M + (r0 + h) * ld + r0; g.lda = ld;
+        g.B = X + r0 * ldx; g.ldb = ldx;
+        g.C = X + (r0 + h) * ldx; g.ldc = ldx;
+        g.kmode = K_COL_BEG; g.ktab = ktab; g.koff = r0;
+        be.gemm(g);
+        trsm_lln(X, ldx, ntc, ktab, r0 + h, rest);
+    }
+    // X <- L^-T X, rows >= ktab[column tile] only
+    void trsm_llt(double *X, int64_t ldx, int ntc, const int32_t *ktab, int64_t r0, int nb) {
+        if (nb == 1) {
+            GemmDesc g;
+            g.al = 1; g.bl = 1; g.mt = 1; g.nt = ntc; g.K = kTile; g.alpha = 1.0; g.beta = 0.0;
+            g.A = Dinv + r0 * kTile; g.lda = kTile;
+            g.B = X + r0 * ldx; g.ldb = ldx;
+            g.C = X + r0 * ldx; g.ldc = ldx;
+            g.kmode = K_ROW_MASK; g.ktab = ktab; g.roff = r0;
+            be.gemm(g);
+            return;
+        }
+        const int hb = nb / 2, rest = nb - hb;
+        const int64_t h = (int64_t)hb * kTile;
+        trsm_llt(X, ldx, ntc, ktab, r0 + h, rest);
+        GemmDesc g;
+        g.al = 1; g.bl = 1; g.mt = hb; g.nt = ntc; g.K = (int64_t)rest * kTile; g.alpha = -1.0; g.beta = 1.0;
+        g.A = M + (r0 + h) * ld + r0; g.lda = ld;
+        g.B = X + (r0 + h) * ldx; g.ldb = ldx;
+        g.C = X + r0 * ldx; g.ldc = ldx;
+        g.kmode = K_ROW_MASK; g.ktab = ktab; g.roff = r0;
+        be.gemm(g);
+        trsm_llt(X, ldx, ntc, ktab, r0, hb);
+    }
+    void inverse_columns(double *X, int64_t ldx, int ntc, const int32_t *ktab) {
+        trsm_lln(X, ldx, ntc, ktab, 0, nblocks());
+        trsm_llt(X, ldx, ntc, ktab, 0, nblocks());
+    }
+
+    // ---- distributed Cholesky, one rank's share (block-column panels of `pw` tiles, owner = panel mod nranks) ------
+    // Every rank holds the whole matrix; a panel is factored by its owner and broadcast, every rank applies it to
+    // its OWN later panels only.  `comm` supplies bcast_panel(panel index, row0, rows, col0, cols, root): on the
+    // root it ships M[row0.., col0..] (+ the panel's Dinv blocks), elsewhere it receives into the same place.
+    // Look-ahead: the owner of panel k+1 updates and factors it before touching its other panels, so the
+    // broadcast of k+1 overlaps everybody's remaining updates with panel k.
+    template <class Comm>
+    void potrf_distributed(Comm &comm, int rank, int nranks, int pw) {
+        const int nb = nblocks();
+        const int npan = (nb + pw - 1) / pw;
+        auto p0 = [&](int p) { return (int64_t)p * pw * kTile; };
+        auto pbl = [&](int p) { return std::min(pw, nb - p * pw); };
+        auto factor_panel = [&](int p) {
+            const int64_t c0 = p0(p);
+            const int wb = pbl(p);
+            potrf(c0, wb);
+            const int below = nb - (p * pw + wb);
+            if (below > 0) trsm_rlt(M + (c0 + (int64_t)wb * kTile) * ld, ld, below, c0, wb);
+        };
+        auto update_panel = [&](int j, int k) {   // panel j -= L[rows >= j, panel k] * L[panel j rows, panel k]'
+            const int64_t cj = p0(j), ck = p0(k);
+            GemmDesc g;
+            g.al = 0; g.bl = 0; g.mt = nb - j * pw; g.nt = pbl(j); g.K = (int64_t)pbl(k) * kTile; g.alpha = -1.0; g.beta = 1.0;
+            g.A = M + cj * ld + ck; g.lda = ld;
+            g.B = M + cj * ld + ck; g.ldb = ld;
+            g.C = M + cj * ld + cj; g.ldc = ld;
+            be.gemm(g);
+        };
+        if (rank == 0) {
+            factor_panel(0);
+            comm.panel_ready(0);
+        }
+        for (int k = 0; k < npan; k++) {
+            const int64_t c0 = p0(k);
+            comm.bcast_panel(k, c0, np - c0, c0, (int64_t)pbl(k) * kTile, k % nranks);
+            // look-ahead: next panel first
+            if (k + 1 < npan && (k + 1) % nranks == rank) {
+                update_panel(k + 1, k);
+                // panel k+1 has now seen every panel <= k (earlier ones were applied in earlier iterations)
+                factor_panel(k + 1);
+                comm.panel_ready(k + 1);
+            }
+            for (int j = k + 2; j < npan; j++)
+                if (j % nranks == rank) update_panel(j, k);
+        }
     }
 };
 

@@ -87,6 +87,12 @@ __global__ void __launch_bounds__(GTHREADS, 1) k_gemm(GemmDesc g) {
     if (g.kmode == K_B_LOWER) kbeg = (int64_t)jt * GB;
     else if (g.kmode == K_A_LOWER) kend = min(g.K, (int64_t)(it + 1) * GB);
     else if (g.kmode == K_MAX_IJ) kbeg = (int64_t)max(it, jt) * GB;
+    else if (g.kmode == K_COL_BEG) {
+        kbeg = max((int64_t)0, (int64_t)g.ktab[jt] - g.koff);
+        if (kbeg >= g.K) return;            // this column tile is still zero in the whole contraction range
+    } else if (g.kmode == K_ROW_MASK) {
+        if (g.roff + (int64_t)it * GB < (int64_t)g.ktab[jt]) return;   // above the column's diagonal: not wanted
+    }
     const int nk = (int)((kend - kbeg) / GK);
 
     const double *Ag = (AL == 0) ? g.A + (int64_t)it * GB * g.lda + kbeg : g.A + kbeg * g.lda + (int64_t)it * GB;
@@ -307,7 +313,7 @@ namespace jaicov {
 // still to be updated; the 128 x 128 diagonal solve is the multiplication by Dinv and is recomputed by every CTA
 // (128 KB from L2) instead of being a separate launch.  HBM/L2-bound: L is read exactly once per sweep.
 constexpr int SR = 8;          // right-hand sides
-constexpr int SCHUNK = 512;    // rows (forward) / columns (backward) per CTA
+constexpr int SCHUNK = 256;    // rows (forward) / columns (backward) per CTA
 
 // forward step j: y_j = Dinv_j b_j;  b[i] -= L[i, J] y_j for all rows i below block j
 // (b lives in R and is updated in place below block j; y_j goes to the separate buffer Y so that no CTA can see a
@@ -344,33 +350,41 @@ __global__ void __launch_bounds__(256) k_solve_fwd_step(const double *__restrict
     __syncthreads();
     if (blockIdx.x == 0)
         for (int i = tid; i < SR * 128; i += 256) Y[(int64_t)(i >> 7) * np + J + (i & 127)] = sy[i >> 7][i & 127];
-    // rows below
+    // rows below: each warp takes 4 rows per iteration so that 16 independent loads are in flight per lane
     const int64_t row0 = J + 128 + (int64_t)blockIdx.x * SCHUNK;
     const int64_t row1 = min(np, row0 + SCHUNK);
-    for (int64_t i = row0 + warp; i < row1; i += 8) {
-        const double *Li = L + i * ld + J;
-        double acc[SR];
+    for (int64_t i0 = row0 + 4 * warp; i0 < row1; i0 += 32) {
+        double lv[4][4];
 #pragma unroll
-        for (int r = 0; r < SR; r++) acc[r] = 0.0;
+        for (int q = 0; q < 4; q++) {
+            const int64_t i = min(i0 + q, row1 - 1);
+            const double *Li = L + i * ld + J;
 #pragma unroll
-        for (int kk = 0; kk < 4; kk++) {
-            const int k = lane + 32 * kk;
-            const double lv = Li[k];
-#pragma unroll
-            for (int r = 0; r < SR; r++) acc[r] += lv * sy[r][k];
+            for (int kk = 0; kk < 4; kk++) lv[q][kk] = Li[lane + 32 * kk];
         }
 #pragma unroll
-        for (int r = 0; r < SR; r++) {
-            double v = acc[r];
+        for (int q = 0; q < 4; q++) {
+            double acc[SR];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            acc[r] = v;
-        }
-        if (lane < SR) {
-            double v = acc[0];
+            for (int r = 0; r < SR; r++) acc[r] = 0.0;
 #pragma unroll
-            for (int r = 1; r < SR; r++) v = (lane == r) ? acc[r] : v;
-            R[(int64_t)lane * np + i] -= v;
+            for (int kk = 0; kk < 4; kk++) {
+#pragma unroll
+                for (int r = 0; r < SR; r++) acc[r] += lv[q][kk] * sy[r][lane + 32 * kk];
+            }
+#pragma unroll
+            for (int r = 0; r < SR; r++) {
+                double v = acc[r];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                acc[r] = v;
+            }
+            if (lane < SR && i0 + q < row1) {
+                double v = acc[0];
+#pragma unroll
+                for (int r = 1; r < SR; r++) v = (lane == r) ? acc[r] : v;
+                R[(int64_t)lane * np + i0 + q] -= v;
+            }
         }
     }
 }
@@ -408,7 +422,7 @@ __global__ void __launch_bounds__(256) k_solve_bwd_step(const double *__restrict
 #pragma unroll
         for (int r = 0; r < SR; r++) acc[r] = 0.0;
         const double *Lc = L + J * ld + c;
-#pragma unroll 4
+#pragma unroll 16
         for (int i = 0; i < 128; i++) {
             const double lv = Lc[(int64_t)i * ld];
 #pragma unroll

@@ -1,0 +1,38 @@
+// dist.h -- multi-GPU context (NCCL communicator, network stream, panel staging) of one handle.
+#pragma once
+#include "common.h"
+
+namespace jaicov {
+
+struct NcclUniqueId { char internal[128]; };
+
+void nccl_unique_id(NcclUniqueId *out);
+
+struct DistContext {
+    int rank = 0, world = 1;
+    void *comm = nullptr;            // ncclComm_t
+    cudaStream_t net = nullptr;      // high-priority stream of the panel broadcasts
+    double *stage[2] = {nullptr, nullptr};
+    size_t stage_elems = 0;
+    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_bcast[2] = {nullptr, nullptr}, ev_unpacked[2] = {nullptr, nullptr};
+    cudaEvent_t ev_tmp = nullptr;
+    void init(int rank, int world, const NcclUniqueId &id);
+    void destroy();
+    void allreduce_sum(double *buf, size_t count, cudaStream_t s);
+};
+
+// Comm concept of DenseSchedule::potrf_distributed
+struct PanelComm {
+    DistContext *ctx;
+    cudaStream_t compute;
+    double *M;
+    int64_t ld, np;
+    double *Dinv;
+    int pw;                          // panel width in 128-tiles
+    bool used[2] = {false, false};
+    void ensure_stage(size_t elems);
+    void panel_ready(int p);
+    void bcast_panel(int k, int64_t row0, int64_t rows, int64_t col0, int64_t cols, int root);
+};
+
+}  // namespace jaicov

@@ -364,6 +364,75 @@ void launch_get_block(const double *lower, int64_t ld, const double *border, int
     k_get_block<<<(unsigned)(blocks < 4736 ? blocks : 4736), 256, 0, s>>>(lower, ld, border, np, q11, d, r0, r1, c0, c1, out);
 }
 
+// ---- column-tile form of the inverse (multi-GPU: every rank holds np x 128*ntc) -----------------------------------
+__global__ void k_identity_columns(double *__restrict__ X, int64_t ldx, const int32_t *__restrict__ ktab, int ntc) {
+    const int jl = blockIdx.x, i = threadIdx.x;
+    if (jl < ntc) X[(int64_t)(ktab[jl] + i) * ldx + jl * 128 + i] = 1.0;
+}
+
+void launch_identity_columns(double *X, int64_t ldx, int64_t np, const int32_t *ktab, int ntc, cudaStream_t s) {
+    if (ntc) { g_launch_count++; k_identity_columns<<<ntc, 128, 0, s>>>(X, ldx, ktab, ntc); }
+}
+
+// K7 on column tiles: Qxx[r][c] = V[r] V[c] (Minv[r][c] - sum_a H[a][r] G[a][c]) for r >= first row of the tile
+__global__ void __launch_bounds__(256) k_qxx_epilogue_cols(double *__restrict__ X, int64_t ldx, int ntc, const int32_t *__restrict__ ktab,
+                                                           int u, const double *__restrict__ V, const double *__restrict__ H,
+                                                           const double *__restrict__ G, int d, int64_t np) {
+    const int64_t r = blockIdx.x;
+    if (r >= u) return;
+    const double vr = V[r];
+    double hr[kMaxDatum];
+#pragma unroll
+    for (int a = 0; a < kMaxDatum; a++) hr[a] = a < d ? H[a * np + r] : 0.0;
+    double *row = X + r * ldx;
+    for (int64_t cl = threadIdx.x; cl < (int64_t)ntc * 128; cl += blockDim.x) {
+        const int64_t c = ktab[cl >> 7] + (cl & 127);
+        if (c > r || c >= u) continue;
+        double x = row[cl];
+#pragma unroll
+        for (int a = 0; a < kMaxDatum; a++)
+            if (a < d) x -= hr[a] * G[a * np + c];
+        row[cl] = (V[c] * x) * vr;
+    }
+}
+
+void launch_qxx_epilogue_cols(double *X, int64_t ldx, int ntc, const int32_t *ktab, int u, const double *V, const double *H,
+                              const double *G, int d, int64_t np, cudaStream_t s) {
+    if (u == 0 || ntc == 0) return;
+    g_launch_count++;
+    k_qxx_epilogue_cols<<<(unsigned)u, 256, 0, s>>>(X, ldx, ntc, ktab, u, V, H, G, d, np);
+}
+
+// block of the full symmetric matrix from the column-tile form; entries owned by other ranks are 0 (the sum over
+// ranks is the block); the replicated border is contributed by rank 0 only
+__global__ void __launch_bounds__(256) k_get_block_dist(const double *__restrict__ X, int64_t ldx, const int32_t *__restrict__ col_local,
+                                                        const double *__restrict__ border, int64_t np, const double *__restrict__ q11,
+                                                        int d, int rank, int r0, int r1, int c0, int c1, double *__restrict__ out) {
+    const int64_t total = (int64_t)(r1 - r0) * (c1 - c0);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = r0 + (int)(i / (c1 - c0)), c = c0 + (int)(i % (c1 - c0));
+        const int lo = r < c ? r : c, hi = r < c ? c : r;
+        double v = 0.0;
+        if (hi < d) v = rank == 0 ? q11[lo * kMaxDatum + hi] : 0.0;
+        else if (lo < d) v = rank == 0 ? border[(int64_t)lo * np + (hi - d)] : 0.0;
+        else {
+            const int e = lo - d;
+            const int jl = col_local[e >> 7];
+            if (jl >= 0) v = X[(int64_t)(hi - d) * ldx + jl * 128 + (e & 127)];
+        }
+        out[i] = v;
+    }
+}
+
+void launch_get_block_dist(const double *X, int64_t ldx, const int32_t *col_local, const double *border, int64_t np,
+                           const double *q11, int d, int rank, int r0, int r1, int c0, int c1, double *out, cudaStream_t s) {
+    const int64_t total = (int64_t)(r1 - r0) * (c1 - c0);
+    if (total <= 0) return;
+    const int64_t blocks = (total + 255) / 256;
+    g_launch_count++;
+    k_get_block_dist<<<(unsigned)(blocks < 4736 ? blocks : 4736), 256, 0, s>>>(X, ldx, col_local, border, np, q11, d, rank, r0, r1, c0, c1, out);
+}
+
 // ---- directly observed parameter groups (PDF:447-473) -------------------------------------------------------------
 // w_i = obs_i - value(target_i)
 __global__ void k_group_w(int r, const double *const *__restrict__ tptr, const double *__restrict__ obs, double *__restrict__ w) {

@@ -122,6 +122,23 @@ int32_t jaicov_device_count(void);
 /* diagnostic: number of CUDA kernels this library has launched in this process so far */
 int64_t jaicov_launch_count(void);
 
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink ---------------------------------------------------------------
+ * rank 0 calls jaicov_nccl_unique_id and ships the 128 bytes to the other processes (torch.distributed, MPI, a file);
+ * every process then calls jaicov_dist_init on its handle BEFORE the set_* calls take effect.  Every rank passes the
+ * SAME full problem; the library shards the images (contiguous ranges balanced by observation count), all-reduces
+ * the shared normal-equation pieces, factors with a block-column-cyclic Cholesky (panel broadcasts) and inverts its
+ * own column tiles of Qxx.  jaicov_get_qxx_block then returns PARTIAL blocks (zeros for entries owned elsewhere;
+ * the sum over ranks is the block), jaicov_get_qxx_local the rank's column tiles as stored. */
+/* pure host function: the contiguous image range [img_begin, img_end) rank `rank` of `world` works on (boundaries at
+ * the images where the cumulative observation count crosses rank * m / world) */
+int32_t jaicov_shard_images(int32_t n_img, const int64_t *pt_ptr, int32_t world, int32_t rank, int32_t *img_begin, int32_t *img_end);
+int32_t jaicov_nccl_unique_id(void *out128);
+int32_t jaicov_dist_init(jaicov_handle *h, int32_t rank, int32_t world, const void *nccl_id128);
+/* n_tiles <- number of 128-wide column tiles of Qxx this rank owns; tile_first_col[i] <- reference column of tile i;
+ * dst (may be NULL) <- (u padded to 128) x (128 n_tiles) row-major: entry [r][128 i + k] = Qxx[d + r][tile_first_col[i] + k]
+ * for d + r >= tile_first_col[i] + k (lower part; the rest is unspecified) */
+int32_t jaicov_get_qxx_local(jaicov_handle *h, int32_t *n_tiles, int32_t *tile_first_col, int32_t tile_cap, double *dst);
+
 /* ---- problem description (flattened object graph) ---------------------------------------------------------------- */
 /* cameras: io_val/io_col hold x0, y0, c per camera (iterator order camera/orientation/InteriorOrientation.java:70-79);
  * coefficients of camera k are entries [coef_ptr[k], coef_ptr[k+1]) listed in the reference's evaluation order:

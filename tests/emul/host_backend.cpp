@@ -29,6 +29,12 @@ struct HostBackend {
                 if (g.kmode == K_B_LOWER) kbeg = (int64_t)jt * T;
                 else if (g.kmode == K_A_LOWER) kend = std::min<int64_t>(g.K, (int64_t)(it + 1) * T);
                 else if (g.kmode == K_MAX_IJ) kbeg = (int64_t)std::max(it, jt) * T;
+                else if (g.kmode == K_COL_BEG) {
+                    kbeg = std::max<int64_t>(0, (int64_t)g.ktab[jt] - g.koff);
+                    if (kbeg >= g.K) continue;
+                } else if (g.kmode == K_ROW_MASK) {
+                    if (g.roff + (int64_t)it * T < (int64_t)g.ktab[jt]) continue;
+                }
                 // read all inputs of the tile first (the CUDA kernel finishes its loads before it stores)
                 for (int i = 0; i < T; i++)
                     for (int j = 0; j < T; j++) {
@@ -81,7 +87,92 @@ struct HostBackend {
     }
 };
 
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+
+struct Barrier {
+    std::mutex m; std::condition_variable cv; int n, count = 0, gen = 0;
+    explicit Barrier(int n_) : n(n_) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        const int g = gen;
+        if (++count == n) { count = 0; gen++; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g; });
+    }
+};
+
+// virtual ranks in threads: a broadcast copies the root replica's panel (and its Dinv blocks) into every replica
+struct HostComm {
+    int rank, nranks;
+    std::vector<double *> *Ms, *Dinvs;
+    int64_t np;
+    Barrier *bar;
+    void bcast_panel(int, int64_t row0, int64_t rows, int64_t col0, int64_t cols, int root) {
+        bar->wait();
+        if (rank != root) {
+            for (int64_t r = 0; r < rows; r++)
+                std::memcpy((*Ms)[rank] + (row0 + r) * np + col0, (*Ms)[root] + (row0 + r) * np + col0, sizeof(double) * cols);
+            std::memcpy((*Dinvs)[rank] + col0 * kTile, (*Dinvs)[root] + col0 * kTile, sizeof(double) * cols * kTile);
+        }
+        bar->wait();
+    }
+    void panel_ready(int) {}
+};
+
 extern "C" {
+
+// distributed Cholesky with `nranks` virtual ranks (threads), panel width pw tiles; on exit every replica must hold
+// the same factor; replica 0 is returned in M (lower), followed by the column-panel inverse of the column tiles
+// owned by each rank (tile c belongs to rank (c / pw) % nranks), gathered into Q (np x np, lower part valid).
+int emul_distributed(int64_t np, double *M, int nranks, int pw, double *Q, double *maxdiff) {
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    const int nb = (int)(np / kTile);
+    std::vector<std::vector<double>> Mr(nranks, std::vector<double>(M, M + np * np)), Dr(nranks, std::vector<double>((size_t)np * kTile, nan));
+    std::vector<double *> Ms, Ds;
+    for (int r = 0; r < nranks; r++) { Ms.push_back(Mr[r].data()); Ds.push_back(Dr[r].data()); }
+    Barrier bar(nranks);
+    std::vector<int> infos(nranks, 0);
+    std::vector<std::thread> th;
+    for (int r = 0; r < nranks; r++)
+        th.emplace_back([&, r] {
+            HostBackend be;
+            HostComm comm{r, nranks, &Ms, &Ds, np, &bar};
+            DenseSchedule<HostBackend> ds{be, Ms[r], np, np, Ds[r]};
+            ds.potrf_distributed(comm, r, nranks, pw);
+            infos[r] = be.info;
+        });
+    for (auto &t : th) t.join();
+    double md = 0.0;
+    for (int r = 1; r < nranks; r++)
+        for (int64_t i = 0; i < np; i++)
+            for (int64_t j = 0; j <= i; j++) md = std::max(md, std::fabs(Mr[r][i * np + j] - Mr[0][i * np + j]));
+    *maxdiff = md;
+    for (int64_t i = 0; i < np; i++) for (int64_t j = 0; j <= i; j++) M[i * np + j] = Mr[0][i * np + j];
+    // column-panel inverse per rank
+    for (int r = 0; r < nranks; r++) {
+        std::vector<int32_t> ktab;
+        for (int c = 0; c < nb; c++) if ((c / pw) % nranks == r) ktab.push_back(c * kTile);
+        const int ntc = (int)ktab.size();
+        if (!ntc) continue;
+        const int64_t ldx = (int64_t)ntc * kTile;
+        std::vector<double> X((size_t)np * ldx, 0.0);
+        for (int jl = 0; jl < ntc; jl++)
+            for (int i = 0; i < kTile; i++) X[(size_t)(ktab[jl] + i) * ldx + jl * kTile + i] = 1.0;
+        HostBackend be;
+        DenseSchedule<HostBackend> ds{be, Ms[r], np, np, Ds[r]};
+        ds.inverse_columns(X.data(), ldx, ntc, ktab.data());
+        for (int jl = 0; jl < ntc; jl++)
+            for (int64_t row = ktab[jl]; row < np; row++)
+                for (int i = 0; i < kTile; i++) {
+                    const int64_t col = ktab[jl] + i;
+                    if (row >= col) Q[row * np + col] = X[(size_t)row * ldx + jl * kTile + i];
+                }
+    }
+    int info = 0;
+    for (int v : infos) if (v) info = v;
+    return info;
+}
 
 // M: np x np row-major; on entry the LOWER triangle holds an SPD matrix (upper is poisoned here with NaN);
 // R: mt*128 x np right-hand-side rows (solved in place); on exit M lower = inverse.

@@ -1,0 +1,71 @@
+"""Worker of the multi-GPU parity test: run under torchrun, one process per GPU.  Every rank runs the same adjustment
+through the distributed C-ABI path; rank 0 compares with the CPU oracle and prints one JSON line."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bundle_adjustment_b200 as ba  # noqa: E402
+from oracle.oracle import Oracle  # noqa: E402
+from tests.helpers import flat_problem  # noqa: E402
+from tests.scenes import example_scene, synthetic_scene  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    which = sys.argv[1] if len(sys.argv) > 1 else 'cfg2'
+    if which == 'example':
+        scene = example_scene()
+    elif which == 'cfg3':
+        scene = synthetic_scene(3, images=12, targets=150)[0]
+    elif which == 'cfg4':
+        scene = synthetic_scene(4, images=30, targets=300)[0]
+    else:
+        scene = synthetic_scene(2)[0]
+    adj, flat = flat_problem(scene)
+    ids = [ba._lib.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    s = ba.Session(sigma2apriori=adj.getVarianceFactorApriori(), device=local)
+    s.dist_init(rank, world, ids[0])
+    s.set_problem(flat)
+    rc = s.estimate()
+    st = s.stats()
+    n = s.n
+    blk = torch.from_numpy(s.qxx_block(0, n, 0, n)).cuda()
+    dist.all_reduce(blk)            # partial blocks: the sum over ranks is Qxx
+    if rank == 0:
+        o = Oracle(scene)
+        so = o.estimate()
+        Qo = o.qxx_dense()
+        Qg = blk.cpu().numpy()
+        d = o.fp.d
+        sg = np.sqrt(np.abs(np.diag(Qo)))
+        sg[:d] = 1.0
+        errq = float((np.abs(Qg - Qo) / np.outer(sg, sg)).max())
+        s2o = o.variance_factor_aposteriori()
+        xyz, io, coef, eo = s.values()
+        errx = 0.0
+        for vg, vo, cols in ((xyz, o.fp.xyz, o.fp.pt_col), (io, o.fp.io_val, o.fp.io_col), (coef, o.fp.coef_val, o.fp.coef_col),
+                             (eo, o.fp.eo_val, o.fp.eo_col)):
+            c = cols.astype(np.int64)
+            act = (c >= 0) & (c < 2147483647)
+            floor = np.sqrt(s2o * np.abs(np.diag(Qo))[c[act]])
+            errx = max(errx, float((np.abs(vg[act] - vo[act]) / np.maximum(np.abs(vo[act]), floor)).max()))
+        print(json.dumps({'scene': which, 'world': world, 'rc': rc, 'rc_oracle': so, 'iterations': st.iterations,
+                          'iterations_oracle': len(o.history), 'sigma2_rel_err': abs(st.sigma2aposteriori - s2o) / s2o,
+                          'qxx_scaled_err': errq, 'param_rel_err': errx, 'ms_last_pass': st.ms_total,
+                          'ms_factor': st.ms_factor, 'ms_inverse': st.ms_inverse}), flush=True)
+    s.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,38 @@
+"""Multi-GPU parity (needs >= 2 B200s on one box): image-sharded assembly + NCCL all-reduce, block-column-cyclic
+Cholesky with panel broadcasts and the per-rank column-tile inverse, against the CPU oracle."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+import bundle_adjustment_b200 as ba
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason='needs two GPUs')
+@pytest.mark.parametrize('which', ['example', 'cfg2', 'cfg3', 'cfg4'])
+def test_two_gpu_adjustment_matches_oracle(built, which):
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', '29531', os.path.join(ROOT, 'tests', 'multi_worker.py'), which]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith('{')][-1]
+    r = json.loads(line)
+    print(r)
+    assert r['rc'] == r['rc_oracle'] == 1
+    assert r['iterations'] == r['iterations_oracle']
+    assert r['sigma2_rel_err'] <= 1e-8
+    assert r['qxx_scaled_err'] <= 1e-8
+    assert r['param_rel_err'] <= 1e-10
