@@ -8,8 +8,9 @@ full inverse Qxx, Omega = v'Pv, max|dx| (jaicov_iterate(final_pass=1)).  The sam
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4|5] [--impl reference]
 
-N > 1 (torchrun): every rank runs the same pass on its own GPU as an independent replica (weak scaling); the
-image-sharded assembly / block-cyclic factorisation of SURVEY.md 8(e) is not built yet and this is said in the line.
+N > 1 (torchrun): ONE adjustment spread over the N GPUs (strong scaling): image-sharded assembly + NCCL all-reduce of
+the shared blocks, block-column-cyclic Cholesky with panel broadcasts over NVLink, every rank inverts its own column
+tiles of Qxx.
 `--impl reference` times the CPU oracle (oracle/, the restatement of the Java path; no JVM exists here) on a bounded,
 scaled-down sample of the same workload and extrapolates (assembly ~ image points, factor+inverse ~ n^3).
 """
@@ -168,7 +169,7 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--config', type=int, default=int(os.environ.get('JAICOV_BENCH_CONFIG', '4')))
+    ap.add_argument('--config', type=int, default=int(os.environ.get('JAICOV_BENCH_CONFIG', '5')))
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
@@ -194,7 +195,19 @@ def main():
     scene, adj, flat = workload(args.config)
     name, n = workload_name(args.config, flat, adj)
     sigma2 = adj.getVarianceFactorApriori()
-    sess = ba.Session(sigma2apriori=sigma2, device=local_rank)
+    nccl_id = None
+    if world > 1:
+        ids = [ba._lib.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        nccl_id = ids[0]
+
+    def new_session():
+        s_ = ba.Session(sigma2apriori=sigma2, device=local_rank)
+        if world > 1:
+            s_.dist_init(rank, world, nccl_id)
+        return s_
+
+    sess = new_session()
     sess.set_problem(flat)
 
     def barrier():
@@ -229,17 +242,19 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max, wall_ms_max = float(t[0]), float(t[1])
     ms_per_step = dev_ms_max / args.steps
-    value = world * args.steps / (dev_ms_max * 1e-3)
+    value = args.steps / (dev_ms_max * 1e-3)          # one adjustment over all ranks: whole-job iterations/s
     stage /= args.steps
 
     # ---- end to end through the C ABI with host buffers -----------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
         npk = n * (n + 1) // 2
-        try:
-            qhost = torch.empty(npk, dtype=torch.float64, pin_memory=True).numpy()
-        except Exception:
-            qhost = np.empty(npk)
+        qhost = None
+        if world == 1:
+            try:
+                qhost = torch.empty(npk, dtype=torch.float64, pin_memory=True).numpy()
+            except Exception:
+                qhost = np.empty(npk)
         h2d = sum(np.asarray(flat[k]).nbytes for k in ('io_val', 'io_col', 'r0', 'coef_ptr', 'coef_type', 'coef_order', 'coef_val',
                                                        'coef_col', 'cam_of_img', 'eo_val', 'eo_col', 'pt_ptr', 'xy', 'var', 'rho', 'xyz', 'is_datum'))
         h2d += flat['obj_idx'].size * 4 + flat['pt_col'].size * 4
@@ -248,21 +263,34 @@ def main():
         sess.close()
         barrier()
         t0 = time.perf_counter()
+        phase = np.zeros(4)
         for _ in range(ksteps):
-            s2 = ba.Session(sigma2apriori=sigma2, device=local_rank)
+            p0 = time.perf_counter()
+            s2 = new_session()
             s2.set_problem(flat)                       # host -> device copies of the whole flattened problem
+            p1 = time.perf_counter()
             rc = s2.iterate(final_pass=True, apply_update=True)
             assert rc == 0, rc
-            s2.qxx_packed(out=qhost)                   # device -> host: full Qxx in MTJ packed layout
+            p2 = time.perf_counter()
+            if world > 1:
+                cols_l, q_l = s2.qxx_local()           # device -> host: this rank's column tiles of Qxx
+                d2h = q_l.nbytes + n * 8
+            else:
+                s2.qxx_packed(out=qhost)               # device -> host: full Qxx in MTJ packed layout
             dxh = s2.dx()
             vals = s2.values()
+            p3 = time.perf_counter()
             s2.close()
+            p4 = time.perf_counter()
+            phase += [p1 - p0, p2 - p1, p3 - p2, p4 - p3]
         barrier()
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {'value': world * ksteps / float(te[0]), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-               'steps': ksteps, 'includes': 'jaicov_create + set_* (H2D) + one final pass + full packed Qxx, dx and values (D2H) + destroy'}
+        e2e = {'value': ksteps / float(te[0]), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+               'steps': ksteps, 'includes': 'jaicov_create + set_* (H2D) + one final pass + full packed Qxx, dx and values (D2H) + destroy',
+               'phase_ms': dict(zip(('create+set', 'pass (incl. upload, allocation)', 'results D2H', 'destroy'),
+                                    (phase / ksteps * 1e3).round(2).tolist()))}
 
     if rank != 0:
         if world > 1:
@@ -275,18 +303,20 @@ def main():
     achieved = flops / t_dense / 1e12
     peaks_file = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     hbm = json.load(open(peaks_file)).get('hbm_gbs') if os.path.exists(peaks_file) else 6650.0
-    roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+    roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak * world, 'unit': 'TFLOP/s', 'frac': achieved / (peak * world),
+                'traffic': None, 'peak_per_gpu': peak,
                 'kernel': 'k_gemm<AL,BL> (FP64 DMMA 128x128 tiles); numerator n^3 flop per step, denominator device time of the '
                           'factor + inverse stages (includes the diagonal-block kernels and copies between GEMM launches)',
                 'peak_source': 'cuBLAS DGEMM 8192^3 via torch.matmul(float64) measured in this run (burst, best of 5); '
                                'MEASURED_PEAKS.json has no FP64 entry',
                 'assembly_gbs': (flat['obj_idx'].size * 44.0) / (stage[0] * 1e-3) / 1e9, 'hbm_peak_gbs': hbm}
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-            'data': 'synthetic',
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak' if world == 1 else 'strong', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': name, 'l2': 'inputs larger than L2: the %d x %d FP64 system (%.2f GB) is rewritten every step'
                        % (n, n, n * n * 8 / 1e9),
-                       'parallelism': 'single GPU' if world == 1 else 'independent replicas (image-sharded assembly / block-cyclic factorisation not built yet)',
+                       'parallelism': 'single GPU' if world == 1 else ('one adjustment over %d GPUs: image-sharded assembly + NCCL all-reduce, block-column-cyclic '
+                                                                       'Cholesky (panel broadcasts), per-rank column-tile inverse' % world),
                        'timing': 'CUDA events on the library stream around every pass (jaicov_stats.ms_total), max over ranks',
                        'stage_ms': {'assembly+precondition': stage[0], 'factor': stage[1], 'solve+datum': stage[2],
                                     'inverse+Qxx epilogue': stage[3], 'omega': stage[4]},

@@ -6,6 +6,7 @@
 // computing entry point fails with JAICOV_NOT_INITIALISED.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <stdexcept>
@@ -98,6 +99,11 @@ struct Group {
 
 static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// One NCCL communicator per process (one process per GPU): created by the first jaicov_dist_init and re-used by later
+// handles, so that a sequence of adjustments does not pay communicator set-up again.
+static DistContext g_dist;
+static bool g_dist_ready = false;
+
 }  // namespace jaicov
 
 using namespace jaicov;
@@ -132,8 +138,8 @@ struct jaicov_handle {
     cudaEvent_t ev[8] = {};
     jaicov_stats stats{};
     double centroid[3] = {0, 0, 0};
-    // multi-GPU (one process per GPU)
-    DistContext dist;
+    // multi-GPU (one process per GPU); the communicator is process-wide and outlives the handle
+    DistContext &dist = g_dist;
     bool dist_on = false;
     int panel_tiles = 4;                 // block-column panel width of the distributed Cholesky, in 128-tiles
     DevBuf<double> Xl;                   // np x (128 * ntc): this rank's column tiles of the inverse
@@ -475,7 +481,8 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     if (multi) {
         PanelComm pc{&h->dist, s, h->M.p, P.np, P.np, h->Dinv.p, h->panel_tiles};
         pc.ensure_stage((size_t)P.np * h->panel_tiles * kBlk + (size_t)h->panel_tiles * kBlk * kBlk);
-        ds.potrf_distributed(pc, h->dist.rank, h->dist.world, h->panel_tiles);
+        ds.potrf_distributed(pc, h->dist.rank, h->dist.world, h->panel_tiles, h->ktab.empty() ? nullptr : h->d_ktab.p,
+                             (int)h->ktab.size(), h->ktab.data());
         // the last broadcasts this rank rooted are still on the network stream: later stages (and the next pass,
         // which re-uses the staging buffers) are ordered after them
         JCHECK(cudaEventRecord(h->dist.ev_tmp, h->dist.net));
@@ -650,7 +657,7 @@ void jaicov_destroy(jaicov_handle *h) {
     if (h->stream) {
         cudaSetDevice(h->opt.device);
         cudaStreamSynchronize(h->stream);
-        if (h->dist_on) { cudaDeviceSynchronize(); h->dist.destroy(); }
+        if (h->dist_on) cudaDeviceSynchronize();   // the process-wide communicator stays
         for (auto &e : h->ev) if (e) cudaEventDestroy(e);
         cudaStreamDestroy(h->stream);
     }
@@ -690,10 +697,16 @@ int32_t jaicov_dist_init(jaicov_handle *h, int32_t rank, int32_t world, const vo
     API_GUARD_BEGIN
     if (usable_devices() == 0) throw CudaError{cudaErrorNoDevice, "no sm_100 device: jaicov_b200 has no CPU path", __FILE__, __LINE__};
     JCHECK(cudaSetDevice(h->opt.device));
-    NcclUniqueId id;
-    memcpy(&id, nccl_id128, sizeof id);
-    h->dist.init(rank, world, id);
+    if (g_dist_ready && (g_dist.rank != rank || g_dist.world != world))
+        return fail(h, JAICOV_ILLEGAL_ARGUMENT, "this process already joined a communicator with another rank/world");
+    if (!g_dist_ready) {
+        NcclUniqueId id;
+        memcpy(&id, nccl_id128, sizeof id);
+        g_dist.init(rank, world, id);
+        g_dist_ready = true;
+    }
     h->dist_on = true;
+    if (const char *e = getenv("JAICOV_PANEL_TILES")) h->panel_tiles = std::max(1, atoi(e));
     h->prepared = false;
     return JAICOV_OK;
     API_GUARD_END(h)

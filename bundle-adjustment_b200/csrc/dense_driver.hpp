@@ -48,6 +48,8 @@ struct GemmDesc {
     int64_t ldc = 0;
     int tri_out = 0;  // only tiles with tile-row >= tile-col (mt == nt, C on the diagonal)
     int kmode = K_FULL;
+    const int32_t *coltab = nullptr; // if set: 2-D launch, blockIdx.y picks the global column tile coltab[y] / 128, blockIdx.x the
+    int ncoltab = 0;                 //         global row tile; tiles above the diagonal exit (trapezoid update of many panels at once)
     const int32_t *ktab = nullptr;   // K_COL_BEG / K_ROW_MASK: per column tile, first global row of interest
     int64_t koff = 0;                // K_COL_BEG: global row of k = 0
     int64_t roff = 0;                // K_ROW_MASK: global row of output tile row 0
@@ -242,8 +244,11 @@ struct DenseSchedule {
     // root it ships M[row0.., col0..] (+ the panel's Dinv blocks), elsewhere it receives into the same place.
     // Look-ahead: the owner of panel k+1 updates and factors it before touching its other panels, so the
     // broadcast of k+1 overlaps everybody's remaining updates with panel k.
+    // own_cols: first rows (= columns) of the 128-wide column tiles this rank owns, ascending, n_own of them
+    // (device-visible for the CUDA backend); used to apply a received panel to ALL own later tiles in one launch.
     template <class Comm>
-    void potrf_distributed(Comm &comm, int rank, int nranks, int pw) {
+    void potrf_distributed(Comm &comm, int rank, int nranks, int pw, const int32_t *own_cols = nullptr, int n_own = 0,
+                           const int32_t *own_cols_host = nullptr) {
         const int nb = nblocks();
         const int npan = (nb + pw - 1) / pw;
         auto p0 = [&](int p) { return (int64_t)p * pw * kTile; };
@@ -278,8 +283,24 @@ struct DenseSchedule {
                 factor_panel(k + 1);
                 comm.panel_ready(k + 1);
             }
-            for (int j = k + 2; j < npan; j++)
-                if (j % nranks == rank) update_panel(j, k);
+            if (own_cols && own_cols_host) {
+                // one trapezoid launch: every own column tile right of panel k+1, all rows on or below its diagonal
+                const int64_t first = p0(k + 2);
+                int skip = 0;
+                while (skip < n_own && own_cols_host[skip] < first) skip++;
+                if (skip < n_own) {
+                    GemmDesc g;
+                    g.al = 0; g.bl = 0; g.mt = nb; g.nt = n_own - skip; g.K = (int64_t)pbl(k) * kTile; g.alpha = -1.0; g.beta = 1.0;
+                    g.A = M + c0; g.lda = ld;
+                    g.B = M + c0; g.ldb = ld;
+                    g.C = M; g.ldc = ld;
+                    g.coltab = own_cols + skip; g.ncoltab = n_own - skip;
+                    be.gemm(g);
+                }
+            } else {
+                for (int j = k + 2; j < npan; j++)
+                    if (j % nranks == rank) update_panel(j, k);
+            }
         }
     }
 };

@@ -40,43 +40,55 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
-// load one 128 x 16 operand slab: LAYOUT 0 = rows are the 128 (m or n) index, k contiguous in global memory;
-// LAYOUT 1 = rows are k, the 128 index contiguous in global memory
-template <int LAYOUT>
+// load one ROWS x 16 operand slab: LAYOUT 0 = rows are the m (or n) index, k contiguous in global memory;
+// LAYOUT 1 = rows are k, the m (or n) index contiguous in global memory (pitch ROWS + 4)
+template <int LAYOUT, int ROWS>
 __device__ __forceinline__ void load_slab(double *s, const double *g, int64_t ld, int tid) {
     if (LAYOUT == 0) {
 #pragma unroll
-        for (int c = tid; c < 128 * 8; c += GTHREADS) {
+        for (int c = tid; c < ROWS * 8; c += GTHREADS) {
             const int row = c >> 3, cc = c & 7;
             cp_async16(s + row * PITCH_K + cc * 2, g + (int64_t)row * ld + cc * 2);
         }
     } else {
+        constexpr int CPR = ROWS / 2;   // 16-byte chunks per k row
 #pragma unroll
-        for (int c = tid; c < 16 * 64; c += GTHREADS) {
-            const int kr = c >> 6, cc = c & 63;
-            cp_async16(s + kr * PITCH_M + cc * 2, g + (int64_t)kr * ld + cc * 2);
+        for (int c = tid; c < 16 * CPR; c += GTHREADS) {
+            const int kr = c / CPR, cc = c % CPR;
+            cp_async16(s + kr * (ROWS + 4) + cc * 2, g + (int64_t)kr * ld + cc * 2);
         }
     }
 }
 
-template <int AL, int BL>
+// BM = rows of C per CTA (128, 64 or 32; the columns are always 128).  Small BM spreads a 128 x 128 tile over 2 or
+// 4 SMs: a single tile with K = 128 is bound by ONE SM's DMMA rate (~17 us), which is what the many small launches
+// of the recursion's deep levels pay; the host picks BM from the number of tiles of the launch.
+template <int AL, int BL, int BM>
 __global__ void __launch_bounds__(GTHREADS, 1) k_gemm(GemmDesc g) {
+    constexpr int WARPS_M = (BM >= 64) ? 2 : 1;
+    constexpr int WARPS_N = 8 / WARPS_M;
+    constexpr int WT_M = BM / WARPS_M, WT_N = 128 / WARPS_N;
+    constexpr int MI = WT_M / 8, NJ = WT_N / 8;
+    constexpr int SPLIT = 128 / BM;
     extern __shared__ __align__(16) double gsm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp & 1, wn = warp >> 1;   // 2 x 4 warps, warp tile 64 x 32
+    const int wm = warp % WARPS_M, wn = warp / WARPS_M;
     const int grp = lane >> 2, tig = lane & 3;
 
     // ---- tile decode (longest contraction first) -----------------------------------------------------------------
     int it, jt;
-    {
-        const int l = blockIdx.x;
+    const int sub = blockIdx.x % SPLIT;
+    if (g.coltab) {
+        it = blockIdx.x / SPLIT;
+        jt = g.coltab[blockIdx.y] / GB;
+        if (it < jt) return;    // above the diagonal of this column tile
+    } else {
+        const int l = blockIdx.x / SPLIT;
         if (g.tri_out) {
             it = (int)((sqrt(8.0 * (double)l + 1.0) - 1.0) * 0.5);
             while ((int64_t)(it + 1) * (it + 2) / 2 <= l) it++;
             while ((int64_t)it * (it + 1) / 2 > l) it--;
             jt = l - (int)((int64_t)it * (it + 1) / 2);
-            if (g.kmode != K_MAX_IJ) {  // SYRK: all tiles equal; nothing to reorder
-            }
         } else {
             it = l / g.nt;
             jt = l - it * g.nt;
@@ -94,24 +106,25 @@ __global__ void __launch_bounds__(GTHREADS, 1) k_gemm(GemmDesc g) {
         if (g.roff + (int64_t)it * GB < (int64_t)g.ktab[jt]) return;   // above the column's diagonal: not wanted
     }
     const int nk = (int)((kend - kbeg) / GK);
+    const int64_t mrow0 = (int64_t)it * GB + sub * BM;   // first row of C (and of op(A)) of this CTA
 
-    const double *Ag = (AL == 0) ? g.A + (int64_t)it * GB * g.lda + kbeg : g.A + kbeg * g.lda + (int64_t)it * GB;
+    const double *Ag = (AL == 0) ? g.A + mrow0 * g.lda + kbeg : g.A + kbeg * g.lda + mrow0;
     const double *Bg = (BL == 0) ? g.B + (int64_t)jt * GB * g.ldb + kbeg : g.B + kbeg * g.ldb + (int64_t)jt * GB;
     const int64_t a_step = (AL == 0) ? GK : (int64_t)GK * g.lda;
     const int64_t b_step = (BL == 0) ? GK : (int64_t)GK * g.ldb;
 
-    double acc[8][4][2];
+    double acc[MI][NJ][2];
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < MI; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NJ; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     // ---- pipeline prologue ---------------------------------------------------------------------------------------
 #pragma unroll
     for (int s = 0; s < GSTAGES - 1; s++) {
         if (s < nk) {
-            load_slab<AL>(gsm + (size_t)(2 * s) * SLAB, Ag + s * a_step, g.lda, tid);
-            load_slab<BL>(gsm + (size_t)(2 * s + 1) * SLAB, Bg + s * b_step, g.ldb, tid);
+            load_slab<AL, BM>(gsm + (size_t)(2 * s) * SLAB, Ag + s * a_step, g.lda, tid);
+            load_slab<BL, 128>(gsm + (size_t)(2 * s + 1) * SLAB, Bg + s * b_step, g.ldb, tid);
         }
         cp_async_commit();
     }
@@ -123,8 +136,8 @@ __global__ void __launch_bounds__(GTHREADS, 1) k_gemm(GemmDesc g) {
             const int kn = kt + GSTAGES - 1;
             if (kn < nk) {
                 const int sb = kn % GSTAGES;
-                load_slab<AL>(gsm + (size_t)(2 * sb) * SLAB, Ag + kn * a_step, g.lda, tid);
-                load_slab<BL>(gsm + (size_t)(2 * sb + 1) * SLAB, Bg + kn * b_step, g.ldb, tid);
+                load_slab<AL, BM>(gsm + (size_t)(2 * sb) * SLAB, Ag + kn * a_step, g.lda, tid);
+                load_slab<BL, 128>(gsm + (size_t)(2 * sb + 1) * SLAB, Bg + kn * b_step, g.ldb, tid);
             }
             cp_async_commit();
         }
@@ -132,31 +145,31 @@ __global__ void __launch_bounds__(GTHREADS, 1) k_gemm(GemmDesc g) {
         const double *Bs = As + SLAB;
 #pragma unroll
         for (int kk = 0; kk < GK / 4; kk++) {
-            double a[8], b[4];
+            double a[MI], b[NJ];
 #pragma unroll
-            for (int i = 0; i < 8; i++)
-                a[i] = (AL == 0) ? As[(wm * 64 + 8 * i + grp) * PITCH_K + kk * 4 + tig]
-                                 : As[(kk * 4 + tig) * PITCH_M + wm * 64 + 8 * i + grp];
+            for (int i = 0; i < MI; i++)
+                a[i] = (AL == 0) ? As[(wm * WT_M + 8 * i + grp) * PITCH_K + kk * 4 + tig]
+                                 : As[(kk * 4 + tig) * (BM + 4) + wm * WT_M + 8 * i + grp];
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                b[j] = (BL == 0) ? Bs[(wn * 32 + 8 * j + grp) * PITCH_K + kk * 4 + tig]
-                                 : Bs[(kk * 4 + tig) * PITCH_M + wn * 32 + 8 * j + grp];
+            for (int j = 0; j < NJ; j++)
+                b[j] = (BL == 0) ? Bs[(wn * WT_N + 8 * j + grp) * PITCH_K + kk * 4 + tig]
+                                 : Bs[(kk * 4 + tig) * PITCH_M + wn * WT_N + 8 * j + grp];
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int i = 0; i < MI; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < NJ; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
     }
     cp_async_wait<0>();
     __syncthreads();   // every load of this CTA has landed before any store: in-place strips (C == A) are safe
 
     // ---- epilogue ------------------------------------------------------------------------------------------------
-    double *Cg = g.C + ((int64_t)it * GB + wm * 64 + grp) * g.ldc + (int64_t)jt * GB + wn * 32 + 2 * tig;
+    double *Cg = g.C + (mrow0 + wm * WT_M + grp) * g.ldc + (int64_t)jt * GB + wn * WT_N + 2 * tig;
     const double alpha = g.alpha, beta = g.beta;
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < MI; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < NJ; j++) {
             double2 *p = reinterpret_cast<double2 *>(Cg + (int64_t)(8 * i) * g.ldc + 8 * j);
             double2 v;
             if (beta != 0.0) {
@@ -171,24 +184,35 @@ __global__ void __launch_bounds__(GTHREADS, 1) k_gemm(GemmDesc g) {
         }
 }
 
-template <int AL, int BL>
-static void launch_gemm_t(const GemmDesc &g, cudaStream_t s) {
+template <int AL, int BL, int BM>
+static void launch_gemm_t(const GemmDesc &g, int64_t tiles, cudaStream_t s) {
     static bool attr = false;
     if (!attr) {
-        JCHECK(cudaFuncSetAttribute(k_gemm<AL, BL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+        JCHECK(cudaFuncSetAttribute(k_gemm<AL, BL, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
         attr = true;
     }
+    g_launch_count++;
+    if (g.coltab) k_gemm<AL, BL, BM><<<dim3((unsigned)(g.mt * (128 / BM)), (unsigned)g.ncoltab), GTHREADS, GEMM_SMEM, s>>>(g);
+    else k_gemm<AL, BL, BM><<<(unsigned)(tiles * (128 / BM)), GTHREADS, GEMM_SMEM, s>>>(g);
+}
+
+template <int AL, int BL>
+static void launch_gemm_l(const GemmDesc &g, cudaStream_t s) {
     const int64_t tiles = g.tri_out ? (int64_t)g.mt * (g.mt + 1) / 2 : (int64_t)g.mt * g.nt;
     if (tiles <= 0) return;
-    g_launch_count++;
-    k_gemm<AL, BL><<<(unsigned)tiles, GTHREADS, GEMM_SMEM, s>>>(g);
+    // a CTA owns BM full-width rows of C; when C aliases the B operand (left-side base cases) the whole 128 x 128
+    // tile must stay with one CTA
+    const bool alias_b = (const double *)g.C == g.B;
+    if (alias_b || tiles >= 148) launch_gemm_t<AL, BL, 128>(g, tiles, s);
+    else if (tiles >= 74) launch_gemm_t<AL, BL, 64>(g, tiles, s);
+    else launch_gemm_t<AL, BL, 32>(g, tiles, s);
 }
 
 void launch_gemm(const GemmDesc &g, cudaStream_t s) {
-    if (g.al == 0 && g.bl == 0) launch_gemm_t<0, 0>(g, s);
-    else if (g.al == 0 && g.bl == 1) launch_gemm_t<0, 1>(g, s);
-    else if (g.al == 1 && g.bl == 1) launch_gemm_t<1, 1>(g, s);
-    else launch_gemm_t<1, 0>(g, s);
+    if (g.al == 0 && g.bl == 0) launch_gemm_l<0, 0>(g, s);
+    else if (g.al == 0 && g.bl == 1) launch_gemm_l<0, 1>(g, s);
+    else if (g.al == 1 && g.bl == 1) launch_gemm_l<1, 1>(g, s);
+    else launch_gemm_l<1, 0>(g, s);
 }
 
 // ---- diagonal block: factor + invert ----------------------------------------------------------------------------
@@ -202,7 +226,7 @@ constexpr int DTHREADS = 512;
 __global__ void __launch_bounds__(DTHREADS, 1) k_potrf_diag(double *__restrict__ A, int64_t ld, double *__restrict__ dinv,
                                                              int row0, int *__restrict__ info) {
     extern __shared__ double a[];   // [128][DP]
-    __shared__ double s_diag[128];
+    __shared__ double s_diag[128], s_rdiag[128];
     const int tid = threadIdx.x;
     const int i = tid >> 2, q = tid & 3;
     // load the lower triangle, coalesced: 4 rows of 128 per pass
@@ -218,11 +242,24 @@ __global__ void __launch_bounds__(DTHREADS, 1) k_potrf_diag(double *__restrict__
         const double *rj = a + j * DP;
         double s = 0.0, p = 0.0;
         if (i >= j) {
-            for (int k = q; k < j; k += 4) {
+            // 4 independent accumulator pairs, 4 k-values in flight: the LDS latency is paid once per 16 columns
+            double s1 = 0.0, s2 = 0.0, s3 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+            int k = q;
+            for (; k + 12 < j; k += 16) {
+                const double x0 = rj[k], x1 = rj[k + 4], x2 = rj[k + 8], x3 = rj[k + 12];
+                const double y0 = ri[k], y1 = ri[k + 4], y2 = ri[k + 8], y3 = ri[k + 12];
+                s += y0 * x0;  p += x0 * x0;
+                s1 += y1 * x1; p1 += x1 * x1;
+                s2 += y2 * x2; p2 += x2 * x2;
+                s3 += y3 * x3; p3 += x3 * x3;
+            }
+            for (; k < j; k += 4) {
                 const double x = rj[k];
                 s += ri[k] * x;
                 p += x * x;
             }
+            s += (s1 + s2) + s3;
+            p += (p1 + p2) + p3;
         }
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         p += __shfl_xor_sync(0xffffffffu, p, 1);
@@ -230,13 +267,16 @@ __global__ void __launch_bounds__(DTHREADS, 1) k_potrf_diag(double *__restrict__
         p += __shfl_xor_sync(0xffffffffu, p, 2);
         // the factored diagonal goes to s_diag so that a[j][j] keeps its input value: nothing read in this step is
         // overwritten in this step (a[i][j] is read and written by the same thread), hence a single barrier
+        // one reciprocal square root per column instead of sqrt + divide on the critical path
         if (i >= j && q == 0) {
             const double piv = rj[j] - p;
+            const double rinv = rsqrt(piv);
             if (i == j) {
                 if (!(piv > 0.0)) atomicCAS(info, 0, row0 + j + 1);
-                s_diag[j] = sqrt(piv);
+                s_diag[j] = piv * rinv;
+                s_rdiag[j] = rinv;
             } else {
-                a[i * DP + j] = (ri[j] - s) / sqrt(piv);
+                a[i * DP + j] = (ri[j] - s) * rinv;
             }
         }
         __syncthreads();
@@ -252,11 +292,28 @@ __global__ void __launch_bounds__(DTHREADS, 1) k_potrf_diag(double *__restrict__
     }
     // in-place inversion of the lower-triangular factor, last column first (dtrti2, lower):
     //   inv[j][j] = 1/L[j][j];  inv[i][j] = -(sum_{k=j+1..i} inv[i][k] L[k][j]) * inv[j][j]
+    // reciprocal diagonal, one Newton step on the factorisation's rsqrt: 1/L_jj to full precision, computed for all
+    // columns at once instead of one division per column step
+    if (tid < 128) {
+        const double dgg = s_diag[tid];
+        double r = s_rdiag[tid];
+        r = r + r * (1.0 - dgg * r);
+        s_rdiag[tid] = r;
+    }
+    __syncthreads();
     for (int j = 127; j >= 0; j--) {
-        const double ajj = 1.0 / a[j * DP + j];
+        const double ajj = s_rdiag[j];
         double s = 0.0;
         if (i > j) {
-            for (int k = j + 1 + q; k <= i; k += 4) s += ri[k] * a[k * DP + j];
+            double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int k = j + 1 + q;
+            for (; k + 12 <= i; k += 16) {
+                const double x0 = a[k * DP + j], x1 = a[(k + 4) * DP + j], x2 = a[(k + 8) * DP + j], x3 = a[(k + 12) * DP + j];
+                const double y0 = ri[k], y1 = ri[k + 4], y2 = ri[k + 8], y3 = ri[k + 12];
+                s += y0 * x0; s1 += y1 * x1; s2 += y2 * x2; s3 += y3 * x3;
+            }
+            for (; k <= i; k += 4) s += ri[k] * a[k * DP + j];
+            s += (s1 + s2) + s3;
         }
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -327,24 +384,29 @@ __global__ void __launch_bounds__(256) k_solve_fwd_step(const double *__restrict
     for (int i = tid; i < SR * 128; i += 256) sb[i >> 7][i & 127] = R[(int64_t)(i >> 7) * np + J + (i & 127)];
     __syncthreads();
     const double *D = dinv + J * 128;
-    // y[t] = sum_k Dinv[t][k] b[k]: one warp per row, lanes over k
-    for (int t = warp; t < 128; t += 8) {
-        double acc[SR];
+    // y[t] = sum_k Dinv[t][k] b[k]: one warp per row, lanes over k; 4 rows (16 loads) in flight per lane
+    for (int t0 = 4 * warp; t0 < 128; t0 += 32) {
+        double dv[4][4];
 #pragma unroll
-        for (int r = 0; r < SR; r++) acc[r] = 0.0;
+        for (int q = 0; q < 4; q++)
 #pragma unroll
-        for (int kk = 0; kk < 4; kk++) {
-            const int k = lane + 32 * kk;
-            const double dv = D[t * 128 + k];
+            for (int kk = 0; kk < 4; kk++) dv[q][kk] = D[(t0 + q) * 128 + lane + 32 * kk];
 #pragma unroll
-            for (int r = 0; r < SR; r++) acc[r] += dv * sb[r][k];
-        }
+        for (int q = 0; q < 4; q++) {
+            double acc[SR];
 #pragma unroll
-        for (int r = 0; r < SR; r++) {
-            double v = acc[r];
+            for (int r = 0; r < SR; r++) acc[r] = 0.0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) sy[r][t] = v;
+            for (int kk = 0; kk < 4; kk++)
+#pragma unroll
+                for (int r = 0; r < SR; r++) acc[r] += dv[q][kk] * sb[r][lane + 32 * kk];
+#pragma unroll
+            for (int r = 0; r < SR; r++) {
+                double v = acc[r];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) sy[r][t0 + q] = v;
+            }
         }
     }
     __syncthreads();
@@ -400,17 +462,28 @@ __global__ void __launch_bounds__(256) k_solve_bwd_step(const double *__restrict
     for (int i = tid; i < SR * 128; i += 256) sy[i >> 7][i & 127] = Y[(int64_t)(i >> 7) * np + J + (i & 127)];
     __syncthreads();
     const double *D = dinv + J * 128;
-    if (tid < 128) {   // x[t] = sum_k Dinv[k][t] y[k]  (coalesced over t)
+    {   // x[t] = sum_k Dinv[k][t] y[k]  (coalesced over t; Dinv[k][t] = 0 for k < t, so the loop is branch-free and
+        // unrolled: 16 independent loads in flight).  Two threads per t split k into halves.
+        const int t = tid & 127, half = tid >> 7;
         double acc[SR];
 #pragma unroll
         for (int r = 0; r < SR; r++) acc[r] = 0.0;
-        for (int k = tid; k < 128; k++) {     // Dinv[k][t] = 0 for k < t
-            const double dv = D[k * 128 + tid];
+#pragma unroll 16
+        for (int kk = 0; kk < 64; kk++) {
+            const int k = half * 64 + kk;
+            const double dv = D[k * 128 + t];
 #pragma unroll
             for (int r = 0; r < SR; r++) acc[r] += dv * sy[r][k];
         }
+        if (half == 1) {
 #pragma unroll
-        for (int r = 0; r < SR; r++) sx[r][tid] = acc[r];
+            for (int r = 0; r < SR; r++) sx[r][t] = acc[r];
+        }
+        __syncthreads();
+        if (half == 0) {
+#pragma unroll
+            for (int r = 0; r < SR; r++) sx[r][t] += acc[r];
+        }
     }
     __syncthreads();
     if (blockIdx.x == 0)

@@ -23,7 +23,12 @@ struct HostBackend {
         const int T = kTile;
         std::vector<double> acc((size_t)T * T);
         for (int it = 0; it < g.mt; it++)
-            for (int jt = 0; jt < g.nt; jt++) {
+            for (int jl = 0; jl < g.nt; jl++) {
+                int jt = jl;
+                if (g.coltab) {
+                    jt = g.coltab[jl] / T;
+                    if (it < jt) continue;
+                }
                 if (g.tri_out && it < jt) continue;
                 int64_t kbeg = 0, kend = g.K;
                 if (g.kmode == K_B_LOWER) kbeg = (int64_t)jt * T;
@@ -125,7 +130,7 @@ extern "C" {
 // distributed Cholesky with `nranks` virtual ranks (threads), panel width pw tiles; on exit every replica must hold
 // the same factor; replica 0 is returned in M (lower), followed by the column-panel inverse of the column tiles
 // owned by each rank (tile c belongs to rank (c / pw) % nranks), gathered into Q (np x np, lower part valid).
-int emul_distributed(int64_t np, double *M, int nranks, int pw, double *Q, double *maxdiff) {
+int emul_distributed(int64_t np, double *M, int nranks, int pw, double *Q, double *maxdiff, int merged) {
     const double nan = std::numeric_limits<double>::quiet_NaN();
     const int nb = (int)(np / kTile);
     std::vector<std::vector<double>> Mr(nranks, std::vector<double>(M, M + np * np)), Dr(nranks, std::vector<double>((size_t)np * kTile, nan));
@@ -139,7 +144,10 @@ int emul_distributed(int64_t np, double *M, int nranks, int pw, double *Q, doubl
             HostBackend be;
             HostComm comm{r, nranks, &Ms, &Ds, np, &bar};
             DenseSchedule<HostBackend> ds{be, Ms[r], np, np, Ds[r]};
-            ds.potrf_distributed(comm, r, nranks, pw);
+            std::vector<int32_t> own;
+            for (int c = 0; c < (int)(np / kTile); c++) if ((c / pw) % nranks == r) own.push_back(c * kTile);
+            if (merged) ds.potrf_distributed(comm, r, nranks, pw, own.data(), (int)own.size(), own.data());
+            else ds.potrf_distributed(comm, r, nranks, pw);
             infos[r] = be.info;
         });
     for (auto &t : th) t.join();

@@ -46,3 +46,30 @@ def test_not_positive_definite_is_reported(emul):
     M = np.tril(S).copy()
     R = np.zeros((128, n))
     assert emul.emul_spd_solve_invert(n, M.ctypes.data, 0, R.ctypes.data, 0, None) == 201
+
+
+@pytest.mark.parametrize('nb,nranks,pw,merged', [(6, 2, 1, 1), (7, 3, 2, 1), (8, 4, 1, 1), (7, 3, 2, 0), (5, 1, 2, 1)])
+def test_distributed_schedule_with_virtual_ranks(emul, nb, nranks, pw, merged):
+    """Block-column-cyclic Cholesky (panel broadcasts, look-ahead, one trapezoid update launch per panel) on `nranks`
+    virtual ranks (threads, one matrix replica each) followed by every rank's column-tile inverse: all replicas end
+    with the same factor, and the gathered column tiles are the inverse."""
+    emul.emul_distributed.argtypes = [ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_int]
+    rng = np.random.default_rng(100 + nb)
+    n = 128 * nb
+    A = rng.standard_normal((n, n))
+    S = A @ A.T + n * np.eye(n)
+    dd = 1 / np.sqrt(np.diag(S))
+    S = S * dd[:, None] * dd[None, :]
+    M = np.tril(S).copy()
+    M[np.triu_indices(n, 1)] = np.nan
+    for i in range(nb):
+        M[i * 128:(i + 1) * 128, i * 128:(i + 1) * 128] = np.tril(S[i * 128:(i + 1) * 128, i * 128:(i + 1) * 128])
+    Q = np.full((n, n), np.nan)
+    md = ctypes.c_double(0)
+    info = emul.emul_distributed(n, M.ctypes.data, nranks, pw, Q.ctypes.data, ctypes.byref(md), merged)
+    assert info == 0 and md.value == 0.0
+    np.testing.assert_allclose(np.tril(M), np.linalg.cholesky(S), atol=1e-13)
+    Qi = np.linalg.inv(S)
+    assert not np.isnan(np.tril(Q)).any()
+    np.testing.assert_allclose(np.tril(Q), np.tril(Qi), atol=1e-12 * np.abs(Qi).max())
