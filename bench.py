@@ -249,12 +249,12 @@ def main():
     e2e = None
     if not args.no_e2e:
         npk = n * (n + 1) // 2
-        qhost = None
-        if world == 1:
-            try:
-                qhost = torch.empty(npk, dtype=torch.float64, pin_memory=True).numpy()
-            except Exception:
-                qhost = np.empty(npk)
+        npad = (int(flat['n_unknowns']) + 127) // 128 * 128
+        nhost = npk if world == 1 else (npad * npad // world + npad * 128 * 8)     # N > 1: this rank's column tiles, lower part
+        try:
+            qhost = torch.empty(nhost, dtype=torch.float64, pin_memory=True).numpy()
+        except Exception:
+            qhost = np.empty(nhost)
         h2d = sum(np.asarray(flat[k]).nbytes for k in ('io_val', 'io_col', 'r0', 'coef_ptr', 'coef_type', 'coef_order', 'coef_val',
                                                        'coef_col', 'cam_of_img', 'eo_val', 'eo_col', 'pt_ptr', 'xy', 'var', 'rho', 'xyz', 'is_datum'))
         h2d += flat['obj_idx'].size * 4 + flat['pt_col'].size * 4
@@ -273,8 +273,8 @@ def main():
             assert rc == 0, rc
             p2 = time.perf_counter()
             if world > 1:
-                cols_l, q_l = s2.qxx_local()           # device -> host: this rank's column tiles of Qxx
-                d2h = q_l.nbytes + n * 8
+                cols_l, q_l = s2.qxx_local(out=qhost)  # device -> host: this rank's column tiles of Qxx (lower part)
+                d2h = sum(b_.nbytes for b_ in q_l) + n * 8
             else:
                 s2.qxx_packed(out=qhost)               # device -> host: full Qxx in MTJ packed layout
             dxh = s2.dx()

@@ -197,16 +197,26 @@ class Session:
         self.check(self.L.jaicov_dist_init(self.h, rank, world, buf))
         self.rank, self.world = rank, world
 
-    def qxx_local(self):
-        """(first reference column of every owned 128-wide tile, np x 128*ntiles array) of a distributed handle."""
+    def qxx_local(self, out=None):
+        """(first reference column of every owned 128-wide tile, list of (np - e_i) x 128 blocks) of a distributed
+        handle; ``out``: optional (pinned) float64 buffer of at least ``qxx_local_size()`` elements."""
         nt = ctypes.c_int32(0)
         self.check(self.L.jaicov_get_qxx_local(self.h, ctypes.byref(nt), None, 0, None))
         cols = np.zeros(max(nt.value, 1), np.int32)
-        u = int(self.flat['n_unknowns'])
+        self.check(self.L.jaicov_get_qxx_local(self.h, ctypes.byref(nt), cols.ctypes.data, nt.value, None))
+        cols = cols[:nt.value]
+        u, d = int(self.flat['n_unknowns']), self.n - int(self.flat['n_unknowns'])
         npad = (max(u, 1) + 127) // 128 * 128
-        out = np.empty((npad, 128 * nt.value))
-        self.check(self.L.jaicov_get_qxx_local(self.h, ctypes.byref(nt), cols.ctypes.data, nt.value, out.ctypes.data if nt.value else None))
-        return cols[:nt.value], out
+        sizes = [(npad - (int(c) - d)) * 128 for c in cols]
+        total = int(sum(sizes))
+        if out is None:
+            out = np.empty(max(total, 1))
+        self.check(self.L.jaicov_get_qxx_local(self.h, ctypes.byref(nt), None, 0, out.ctypes.data if total else None))
+        blocks, off = [], 0
+        for sz in sizes:
+            blocks.append(out[off:off + sz].reshape(-1, 128))
+            off += sz
+        return cols, blocks
 
     def estimate(self, progress=None):
         cb = PROGRESS_CB(lambda user, st, a, b: progress(st, a, b)) if progress else None

@@ -11,6 +11,7 @@
 //                  triangular solve of the schedule into a GEMM.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.h"
 #include "dense_driver.hpp"
@@ -42,18 +43,18 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // load one ROWS x 16 operand slab: LAYOUT 0 = rows are the m (or n) index, k contiguous in global memory;
 // LAYOUT 1 = rows are k, the m (or n) index contiguous in global memory (pitch ROWS + 4)
-template <int LAYOUT, int ROWS>
+template <int LAYOUT, int ROWS, int NTHREADS>
 __device__ __forceinline__ void load_slab(double *s, const double *g, int64_t ld, int tid) {
     if (LAYOUT == 0) {
 #pragma unroll
-        for (int c = tid; c < ROWS * 8; c += GTHREADS) {
+        for (int c = tid; c < ROWS * 8; c += NTHREADS) {
             const int row = c >> 3, cc = c & 7;
             cp_async16(s + row * PITCH_K + cc * 2, g + (int64_t)row * ld + cc * 2);
         }
     } else {
         constexpr int CPR = ROWS / 2;   // 16-byte chunks per k row
 #pragma unroll
-        for (int c = tid; c < 16 * CPR; c += GTHREADS) {
+        for (int c = tid; c < 16 * CPR; c += NTHREADS) {
             const int kr = c / CPR, cc = c % CPR;
             cp_async16(s + kr * (ROWS + 4) + cc * 2, g + (int64_t)kr * ld + cc * 2);
         }
@@ -63,10 +64,22 @@ __device__ __forceinline__ void load_slab(double *s, const double *g, int64_t ld
 // BM = rows of C per CTA (128, 64 or 32; the columns are always 128).  Small BM spreads a 128 x 128 tile over 2 or
 // 4 SMs: a single tile with K = 128 is bound by ONE SM's DMMA rate (~17 us), which is what the many small launches
 // of the recursion's deep levels pay; the host picks BM from the number of tiles of the launch.
-template <int AL, int BL, int BM>
-__global__ void __launch_bounds__(GTHREADS, 1) k_gemm(GemmDesc g) {
-    constexpr int WARPS_M = (BM >= 64) ? 2 : 1;
-    constexpr int WARPS_N = 8 / WARPS_M;
+// CTA shapes.  BMT = 129: the 128-row tile with 8 warps (2 x 4, warp tile 64 x 32) -- the default; BMT = 128: the same tile
+// with 16 warps (4 x 4, warp tile 32 x 32), tried because "wait" (fixed DMMA issue latency) was the top stall reason with two
+// warps per scheduler, but measured slower (more LDS per DMMA); 64- and 32-row tiles use 8 warps.
+template <int BMT> struct GemmShape {
+    static constexpr int ROWS = (BMT == 129) ? 128 : BMT;
+    static constexpr int WARPS_M = (BMT == 128) ? 4 : ((BMT == 129 || BMT == 64) ? 2 : 1);
+    static constexpr int WARPS_N = (BMT == 128) ? 4 : ((BMT == 129 || BMT == 64) ? 4 : 8);
+    static constexpr int THREADS = 32 * WARPS_M * WARPS_N;
+};
+
+template <int AL, int BL, int BMT>
+__global__ void __launch_bounds__(GemmShape<BMT>::THREADS, 1) k_gemm(GemmDesc g) {
+    constexpr int BM = GemmShape<BMT>::ROWS;
+    constexpr int WARPS_M = GemmShape<BMT>::WARPS_M;
+    constexpr int WARPS_N = GemmShape<BMT>::WARPS_N;
+    constexpr int NTHREADS = GemmShape<BMT>::THREADS;
     constexpr int WT_M = BM / WARPS_M, WT_N = 128 / WARPS_N;
     constexpr int MI = WT_M / 8, NJ = WT_N / 8;
     constexpr int SPLIT = 128 / BM;
@@ -123,8 +136,8 @@ __global__ void __launch_bounds__(GTHREADS, 1) k_gemm(GemmDesc g) {
 #pragma unroll
     for (int s = 0; s < GSTAGES - 1; s++) {
         if (s < nk) {
-            load_slab<AL, BM>(gsm + (size_t)(2 * s) * SLAB, Ag + s * a_step, g.lda, tid);
-            load_slab<BL, 128>(gsm + (size_t)(2 * s + 1) * SLAB, Bg + s * b_step, g.ldb, tid);
+            load_slab<AL, BM, NTHREADS>(gsm + (size_t)(2 * s) * SLAB, Ag + s * a_step, g.lda, tid);
+            load_slab<BL, 128, NTHREADS>(gsm + (size_t)(2 * s + 1) * SLAB, Bg + s * b_step, g.ldb, tid);
         }
         cp_async_commit();
     }
@@ -136,8 +149,8 @@ __global__ void __launch_bounds__(GTHREADS, 1) k_gemm(GemmDesc g) {
             const int kn = kt + GSTAGES - 1;
             if (kn < nk) {
                 const int sb = kn % GSTAGES;
-                load_slab<AL, BM>(gsm + (size_t)(2 * sb) * SLAB, Ag + kn * a_step, g.lda, tid);
-                load_slab<BL, 128>(gsm + (size_t)(2 * sb + 1) * SLAB, Bg + kn * b_step, g.ldb, tid);
+                load_slab<AL, BM, NTHREADS>(gsm + (size_t)(2 * sb) * SLAB, Ag + kn * a_step, g.lda, tid);
+                load_slab<BL, 128, NTHREADS>(gsm + (size_t)(2 * sb + 1) * SLAB, Bg + kn * b_step, g.ldb, tid);
             }
             cp_async_commit();
         }
@@ -184,16 +197,18 @@ __global__ void __launch_bounds__(GTHREADS, 1) k_gemm(GemmDesc g) {
         }
 }
 
-template <int AL, int BL, int BM>
+template <int AL, int BL, int BMT>
 static void launch_gemm_t(const GemmDesc &g, int64_t tiles, cudaStream_t s) {
+    constexpr int BM = GemmShape<BMT>::ROWS;
     static bool attr = false;
     if (!attr) {
-        JCHECK(cudaFuncSetAttribute(k_gemm<AL, BL, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+        JCHECK(cudaFuncSetAttribute(k_gemm<AL, BL, BMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
         attr = true;
     }
     g_launch_count++;
-    if (g.coltab) k_gemm<AL, BL, BM><<<dim3((unsigned)(g.mt * (128 / BM)), (unsigned)g.ncoltab), GTHREADS, GEMM_SMEM, s>>>(g);
-    else k_gemm<AL, BL, BM><<<(unsigned)(tiles * (128 / BM)), GTHREADS, GEMM_SMEM, s>>>(g);
+    constexpr int NT = GemmShape<BMT>::THREADS;
+    if (g.coltab) k_gemm<AL, BL, BMT><<<dim3((unsigned)(g.mt * (128 / BM)), (unsigned)g.ncoltab), NT, GEMM_SMEM, s>>>(g);
+    else k_gemm<AL, BL, BMT><<<(unsigned)(tiles * (128 / BM)), NT, GEMM_SMEM, s>>>(g);
 }
 
 template <int AL, int BL>
@@ -203,7 +218,13 @@ static void launch_gemm_l(const GemmDesc &g, cudaStream_t s) {
     // a CTA owns BM full-width rows of C; when C aliases the B operand (left-side base cases) the whole 128 x 128
     // tile must stay with one CTA
     const bool alias_b = (const double *)g.C == g.B;
-    if (alias_b || tiles >= 148) launch_gemm_t<AL, BL, 128>(g, tiles, s);
+    // A/B measured on B200 (config 5, one final pass): 8 warps 8.06 s, 16 warps 8.31 s -> 8 warps (2 x 4, warp tile 64 x 32)
+    // is the default; JAICOV_GEMM_WARPS=16 selects the 4 x 4 shape
+    static const bool warps16 = [] { const char *e = getenv("JAICOV_GEMM_WARPS"); return e && atoi(e) == 16; }();
+    if (alias_b || tiles >= 148) {
+        if (warps16) launch_gemm_t<AL, BL, 128>(g, tiles, s);
+        else launch_gemm_t<AL, BL, 129>(g, tiles, s);
+    }
     else if (tiles >= 74) launch_gemm_t<AL, BL, 64>(g, tiles, s);
     else launch_gemm_t<AL, BL, 32>(g, tiles, s);
 }

@@ -135,8 +135,10 @@ int32_t jaicov_shard_images(int32_t n_img, const int64_t *pt_ptr, int32_t world,
 int32_t jaicov_nccl_unique_id(void *out128);
 int32_t jaicov_dist_init(jaicov_handle *h, int32_t rank, int32_t world, const void *nccl_id128);
 /* n_tiles <- number of 128-wide column tiles of Qxx this rank owns; tile_first_col[i] <- reference column of tile i;
- * dst (may be NULL) <- (u padded to 128) x (128 n_tiles) row-major: entry [r][128 i + k] = Qxx[d + r][tile_first_col[i] + k]
- * for d + r >= tile_first_col[i] + k (lower part; the rest is unspecified) */
+ * dst (may be NULL, host, pinned preferred) <- the tiles one after the other, tile i as a row-major block of
+ * (np - e_i) rows x 128 columns with e_i = tile_first_col[i] - d and np = u rounded up to 128:
+ * block_i[r][k] = Qxx[tile_first_col[i] + r][tile_first_col[i] + k], i.e. the rows on and below the tile's diagonal
+ * (the part above the diagonal inside the first 128 rows is unspecified; Qxx is symmetric) */
 int32_t jaicov_get_qxx_local(jaicov_handle *h, int32_t *n_tiles, int32_t *tile_first_col, int32_t tile_cap, double *dst);
 
 /* ---- problem description (flattened object graph) ---------------------------------------------------------------- */

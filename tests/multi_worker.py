@@ -40,6 +40,21 @@ def main():
     n = s.n
     blk = torch.from_numpy(s.qxx_block(0, n, 0, n)).cuda()
     dist.all_reduce(blk)            # partial blocks: the sum over ranks is Qxx
+    # the rank's own column tiles as stored (lower part), against the assembled matrix
+    cols_l, blocks = s.qxx_local()
+    Qfull = blk.cpu().numpy()
+    u = int(flat['n_unknowns'])
+    local_err = 0.0
+    for c0, b in zip(cols_l, blocks):
+        c0 = int(c0)
+        w = min(128, n - c0)
+        rows = min(b.shape[0], n - c0)
+        ref = Qfull[c0:c0 + rows, c0:c0 + w]
+        got = b[:rows, :w]
+        mask = np.tril(np.ones((rows, w), bool))        # on and below the tile's diagonal
+        local_err = max(local_err, float(np.abs(np.where(mask, got - ref, 0.0)).max()))
+    le = torch.tensor([local_err], dtype=torch.float64, device='cuda')
+    dist.all_reduce(le, op=dist.ReduceOp.MAX)
     if rank == 0:
         o = Oracle(scene)
         so = o.estimate()
@@ -60,7 +75,7 @@ def main():
             errx = max(errx, float((np.abs(vg[act] - vo[act]) / np.maximum(np.abs(vo[act]), floor)).max()))
         print(json.dumps({'scene': which, 'world': world, 'rc': rc, 'rc_oracle': so, 'iterations': st.iterations,
                           'iterations_oracle': len(o.history), 'sigma2_rel_err': abs(st.sigma2aposteriori - s2o) / s2o,
-                          'qxx_scaled_err': errq, 'param_rel_err': errx, 'ms_last_pass': st.ms_total,
+                          'qxx_scaled_err': errq, 'param_rel_err': errx, 'qxx_local_vs_block_maxabs': float(le[0]), 'ms_last_pass': st.ms_total,
                           'ms_factor': st.ms_factor, 'ms_inverse': st.ms_inverse}), flush=True)
     s.close()
     dist.barrier()

@@ -36,3 +36,4 @@ def test_two_gpu_adjustment_matches_oracle(built, which):
     assert r['sigma2_rel_err'] <= 1e-8
     assert r['qxx_scaled_err'] <= 1e-8
     assert r['param_rel_err'] <= 1e-10
+    assert r['qxx_local_vs_block_maxabs'] == 0.0      # both getters read the same device values
