@@ -16,4 +16,6 @@ from .host import (AffinityShearDistortionModel, BundleAdjustment, Camera, Direc
                    RadialDistanceDistortionModel, RadiallySymmetricDistortionModel, ScaleBar, TangentialDistortionModel,
                    UnknownParameter, UpperSymmPackMatrix, ZernikeDistortionModel)
 
+from .writers import DefaultResultWriter, MatlabResultWriter
+
 __all__ = [n for n in dir() if not n.startswith('_')]

@@ -25,7 +25,7 @@ EXPORTS = [
     'jaicov_set_cameras', 'jaicov_set_images', 'jaicov_set_image_points', 'jaicov_set_object_points',
     'jaicov_set_scale_bars', 'jaicov_add_observed_group', 'jaicov_set_datum', 'jaicov_estimate', 'jaicov_iterate',
     'jaicov_get_stats', 'jaicov_get_values', 'jaicov_get_dx', 'jaicov_get_qxx_packed', 'jaicov_get_qxx_block',
-    'jaicov_get_qxx_diag', 'jaicov_eval_residual_jacobian', 'jaicov_get_normal_equations', 'jaicov_omega',
+    'jaicov_get_qxx_diag', 'jaicov_get_qxx_submatrix', 'jaicov_eval_residual_jacobian', 'jaicov_get_normal_equations', 'jaicov_omega',
     'jaicov_spd_solve_invert',
 ]
 
@@ -88,6 +88,7 @@ def load():
     L.jaicov_get_qxx_packed.argtypes = [vp, vp]
     L.jaicov_get_qxx_block.argtypes = [vp, i32, i32, i32, i32, vp, i64]
     L.jaicov_get_qxx_diag.argtypes = [vp, vp]
+    L.jaicov_get_qxx_submatrix.argtypes = [vp, i32, vp, dbl, vp]
     L.jaicov_eval_residual_jacobian.argtypes = [vp, i32, vp, vp, vp]
     L.jaicov_get_normal_equations.argtypes = [vp, vp, vp]
     L.jaicov_omega.argtypes = [vp, vp, ctypes.POINTER(dbl)]
@@ -256,6 +257,12 @@ class Session:
     def qxx_block(self, r0, r1, c0, c1):
         out = np.empty((r1 - r0, c1 - c0))
         self.check(self.L.jaicov_get_qxx_block(self.h, r0, r1, c0, c1, out.ctypes.data, c1 - c0))
+        return out
+
+    def qxx_submatrix(self, idx, scale=1.0):
+        idx = _i32(idx)
+        out = np.empty((idx.size, idx.size))
+        self.check(self.L.jaicov_get_qxx_submatrix(self.h, idx.size, _p(idx), float(scale), _p(out)))
         return out
 
     def qxx_diag(self):

@@ -53,6 +53,9 @@ void launch_symmetrize(double *M, int64_t ld, int r, cudaStream_t s);
 void launch_identity_columns(double *X, int64_t ldx, int64_t np, const int32_t *ktab, int ntc, cudaStream_t s);
 void launch_qxx_epilogue_cols(double *X, int64_t ldx, int ntc, const int32_t *ktab, int u, const double *V, const double *H,
                               const double *G, int d, int64_t np, cudaStream_t s);
+void launch_get_submatrix(const double *lower, int64_t ld, const double *X, int64_t ldx, const int32_t *col_local, const double *border,
+                          int64_t np, const double *q11, int d, int rank, const int32_t *row_idx, int n_rows, const int32_t *col_idx,
+                          int n_cols, double scale, double *out, cudaStream_t s);
 void launch_get_block_dist(const double *X, int64_t ldx, const int32_t *col_local, const double *border, int64_t np,
                            const double *q11, int d, int rank, int r0, int r1, int c0, int c1, double *out, cudaStream_t s);
 
@@ -187,8 +190,9 @@ struct jaicov_handle {
     int panel_tiles = 8;                 // block-column panel width of the distributed Cholesky, in 128-tiles (1024 columns:
                                          // measured 1628 ms vs 1697 ms for 512 at config 5 on 2 GPUs)
     DevBuf<double> Xl;                   // np x (128 * ntc): this rank's column tiles of the inverse
-    DevBuf<int32_t> d_ktab, d_col_local;
-    std::vector<int32_t> ktab;
+    DevBuf<int32_t> d_ktab, d_col_local, d_ptab;
+    std::vector<int32_t> ktab;           // first columns of the 128-wide tiles of the INVERSE this rank computes
+    std::vector<int32_t> ptab;           // first columns of the tiles of the FACTOR this rank updates (its Cholesky panels)
     DevBuf<double> d_cam_sum;
     int64_t strip_row0 = -1;             // first row of the EO strip of N that is all-reduced
 };
@@ -391,16 +395,28 @@ void prepare(jaicov_handle *h) {
     const size_t np = (size_t)P.np;
     h->M.alloc(np * np);
     if (h->dist_on) {
-        // column tiles of the inverse owned by this rank: tile c belongs to rank (c / panel_tiles) % world
-        const int nb = (int)(P.np / kBlk);
+        // Factor: block-column panels of panel_tiles tiles, owner = panel % world.
+        // Inverse: tile c costs ~ (nb - c)^2, so its tiles are dealt out one by one in snake order
+        // (0..W-1, W-1..0, ...) which balances the quadratic cost to within a fraction of a percent.
+        const int nb = (int)(P.np / kBlk), W = h->dist.world, R = h->dist.rank;
         h->ktab.clear();
+        h->ptab.clear();
         std::vector<int32_t> col_local(nb, -1);
-        for (int c = 0; c < nb; c++)
-            if ((c / h->panel_tiles) % h->dist.world == h->dist.rank) {
+        for (int c = 0; c < nb; c++) {
+            const int q = c % (2 * W);
+            const int owner = q < W ? q : 2 * W - 1 - q;
+            if (owner == R) {
                 col_local[c] = (int32_t)h->ktab.size();
                 h->ktab.push_back(c * kBlk);
             }
+            if ((c / h->panel_tiles) % W == R) h->ptab.push_back(c * kBlk);
+        }
         h->d_col_local.upload(col_local);
+        {
+            std::vector<int32_t> pt = h->ptab;
+            if (pt.empty()) pt.push_back(0);
+            h->d_ptab.upload(pt);
+        }
         std::vector<int32_t> kt = h->ktab;
         if (kt.empty()) kt.push_back(0);
         h->d_ktab.upload(kt);
@@ -525,8 +541,8 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     if (multi) {
         PanelComm pc{&h->dist, s, h->M.p, P.np, P.np, h->Dinv.p, h->panel_tiles};
         pc.ensure_stage((size_t)P.np * h->panel_tiles * kBlk + (size_t)h->panel_tiles * kBlk * kBlk);
-        ds.potrf_distributed(pc, h->dist.rank, h->dist.world, h->panel_tiles, h->ktab.empty() ? nullptr : h->d_ktab.p,
-                             (int)h->ktab.size(), h->ktab.data());
+        ds.potrf_distributed(pc, h->dist.rank, h->dist.world, h->panel_tiles, h->ptab.empty() ? nullptr : h->d_ptab.p,
+                             (int)h->ptab.size(), h->ptab.data());
         // the last broadcasts this rank rooted are still on the network stream: later stages (and the next pass,
         // which re-uses the staging buffers) are ordered after them
         JCHECK(cudaEventRecord(h->dist.ev_tmp, h->dist.net));
@@ -1011,6 +1027,33 @@ int32_t jaicov_get_qxx_block(jaicov_handle *h, int32_t r0, int32_t r1, int32_t c
             launch_get_block(h->M.p, h->P.np, h->Tq.p, h->P.np, h->small.p + 49, h->P.d, (int)r, rr1, c0, c1, tmp.p, h->stream);
         JCHECK(cudaMemcpy2DAsync(dst + (r - r0) * ld, ld * sizeof(double), tmp.p, (size_t)(c1 - c0) * sizeof(double),
                                  (size_t)(c1 - c0) * sizeof(double), rr1 - r, cudaMemcpyDeviceToHost, h->stream));
+        JCHECK(cudaStreamSynchronize(h->stream));
+    }
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+int32_t jaicov_get_qxx_submatrix(jaicov_handle *h, int32_t n_idx, const int32_t *idx, double scale, double *dst) {
+    if (!h || n_idx < 0 || (n_idx > 0 && (!idx || !dst))) return JAICOV_ILLEGAL_ARGUMENT;
+    if (!h->have_qxx) return fail(h, JAICOV_NOT_INITIALISED, "no cofactor matrix: run a final pass with invert_mode FULL");
+    const int n = h->P.u + h->P.d;
+    for (int i = 0; i < n_idx; i++)
+        if (idx[i] < 0 || idx[i] >= n) return fail(h, JAICOV_ILLEGAL_ARGUMENT, "index outside the cofactor matrix");
+    if (n_idx == 0) return JAICOV_OK;
+    API_GUARD_BEGIN
+    JCHECK(cudaSetDevice(h->opt.device));
+    DevBuf<int32_t> didx;
+    didx.upload(std::vector<int32_t>(idx, idx + n_idx));
+    const int64_t rows_per = std::max<int64_t>(1, ((int64_t)1 << 25) / n_idx);
+    DevBuf<double> tmp;
+    tmp.alloc((size_t)std::min<int64_t>(rows_per, n_idx) * n_idx);
+    for (int64_t r = 0; r < n_idx; r += rows_per) {
+        const int nr = (int)std::min<int64_t>(rows_per, n_idx - r);
+        // rows r .. r+nr of the gathered matrix: entry (i, j) = scale * Qxx[idx[r + i], idx[j]]
+        launch_get_submatrix(h->dist_on ? nullptr : h->M.p, h->P.np, h->dist_on ? h->Xl.p : nullptr, (int64_t)h->ktab.size() * kBlk,
+                             h->dist_on ? h->d_col_local.p : nullptr, h->Tq.p, h->P.np, h->small.p + 49, h->P.d,
+                             h->dist_on ? h->dist.rank : 0, didx.p + r, nr, didx.p, n_idx, scale, tmp.p, h->stream);
+        JCHECK(cudaMemcpyAsync(dst + r * n_idx, tmp.p, (size_t)nr * n_idx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         JCHECK(cudaStreamSynchronize(h->stream));
     }
     return JAICOV_OK;

@@ -237,130 +237,192 @@ void launch_gemm(const GemmDesc &g, cudaStream_t s) {
 }
 
 // ---- diagonal block: factor + invert ----------------------------------------------------------------------------
-// 512 threads: 4 lanes per matrix row split every dot product (k = q mod 4) and combine with two shuffles, so a
-// column step costs <= 32 (2 LDS + FMA) per lane instead of 128.  The shared-memory pitch is == 4 (mod 16) doubles:
-// the 16 lanes of a half-warp (4 rows x 4 k-phases) hit 16 distinct 8-byte banks.  The pivot dot product is
-// recomputed by every row (no broadcast), which leaves ONE barrier per column in the factorisation.
-constexpr int DP = 132;
-constexpr int DTHREADS = 512;
+// The 128 x 128 diagonal block is on the critical path of every 128-column step of the factorisation, so this kernel
+// is built for latency, not throughput (one CTA, 256 threads, everything in shared memory / registers):
+//   phase A, four 32-wide panels:  (1) warp 0 factors the 32 x 32 diagonal sub-block IN REGISTERS (lane = row,
+//            register = column; pivots and column entries travel by warp shuffles, no barrier inside) and inverts it
+//            the same way (lane = column of the inverse);  (2) all warps: panel below = B * inv(L_kk)' ;
+//            (3) all warps: trailing update  A22 -= P P'.
+//   phase B: the inverse of the whole 128 x 128 factor from the four 32 x 32 inverses, block column by block column,
+//            in place:  X_IJ = -X_II * sum_{K=J..I-1} L_IK X_KJ.
+// Replaces a column-by-column version (128 + 128 barrier-separated steps, 205 us measured); see profiles/.
+constexpr int DP = 132;        // pitch of the 128 x 128 block in shared memory (== 4 mod 16)
+constexpr int SP = 33;         // pitch of the 32 x 32 scratch blocks
+constexpr int DTHREADS = 256;
+constexpr size_t DIAG_SMEM = ((size_t)128 * DP + 4 * 32 * SP + 96 * SP + 32 * SP) * sizeof(double);
 
 __global__ void __launch_bounds__(DTHREADS, 1) k_potrf_diag(double *__restrict__ A, int64_t ld, double *__restrict__ dinv,
                                                              int row0, int *__restrict__ info) {
-    extern __shared__ double a[];   // [128][DP]
-    __shared__ double s_diag[128], s_rdiag[128];
-    const int tid = threadIdx.x;
-    const int i = tid >> 2, q = tid & 3;
-    // load the lower triangle, coalesced: 4 rows of 128 per pass
+    extern __shared__ double dsm[];
+    double *a = dsm;                       // [128][DP]   the block: A -> L -> (phase B) inverse, lower triangle
+    double *sinv = a + 128 * DP;           // [4][32][SP] inverses of the 32 x 32 diagonal sub-blocks of L
+    double *pan = sinv + 4 * 32 * SP;      // [96][SP]    panel below the current diagonal sub-block
+    double *tmp = pan + 96 * SP;           // [32][SP]    phase B scratch
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned FULL = 0xffffffffu;
+    // load the lower triangle (coalesced rows), zero above the diagonal
     {
         const int c = tid & 127, r0 = tid >> 7;
 #pragma unroll 8
-        for (int r = r0; r < 128; r += 4) a[r * DP + c] = (c <= r) ? A[(int64_t)r * ld + c] : 0.0;
+        for (int r = r0; r < 128; r += 2) a[r * DP + c] = (c <= r) ? A[(int64_t)r * ld + c] : 0.0;
     }
     __syncthreads();
-    // left-looking Cholesky
-    const double *ri = a + i * DP;
-    for (int j = 0; j < 128; j++) {
-        const double *rj = a + j * DP;
-        double s = 0.0, p = 0.0;
-        if (i >= j) {
-            // 4 independent accumulator pairs, 4 k-values in flight: the LDS latency is paid once per 16 columns
-            double s1 = 0.0, s2 = 0.0, s3 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
-            int k = q;
-            for (; k + 12 < j; k += 16) {
-                const double x0 = rj[k], x1 = rj[k + 4], x2 = rj[k + 8], x3 = rj[k + 12];
-                const double y0 = ri[k], y1 = ri[k + 4], y2 = ri[k + 8], y3 = ri[k + 12];
-                s += y0 * x0;  p += x0 * x0;
-                s1 += y1 * x1; p1 += x1 * x1;
-                s2 += y2 * x2; p2 += x2 * x2;
-                s3 += y3 * x3; p3 += x3 * x3;
+
+    // ---------------------------------------------------------------- phase A
+    for (int kb = 0; kb < 4; kb++) {
+        const int base = 32 * kb;
+        const int nr = 96 - base;          // rows below the diagonal sub-block
+        if (warp == 0) {
+            double d[32];
+#pragma unroll
+            for (int c = 0; c < 32; c++) d[c] = a[(base + lane) * DP + base + c];
+            double myr = 0.0;              // 1 / L_ii of this lane's row
+#pragma unroll
+            for (int jj = 0; jj < 32; jj++) {
+                const double pj = __shfl_sync(FULL, d[jj], jj);
+                const double r = rsqrt(pj);
+                if (lane == jj) {
+                    if (!(pj > 0.0)) atomicCAS(info, 0, row0 + base + jj + 1);
+                    myr = r;
+                }
+                const double dj = (lane == jj) ? pj * r : d[jj] * r;
+                d[jj] = dj;
+#pragma unroll
+                for (int c = jj + 1; c < 32; c++) {
+                    const double lc = __shfl_sync(FULL, dj, c);
+                    d[c] -= dj * lc;       // meaningful for lanes >= c; lanes < c only touch their unused upper part
+                }
             }
-            for (; k < j; k += 4) {
-                const double x = rj[k];
-                s += ri[k] * x;
-                p += x * x;
+#pragma unroll
+            for (int c = 0; c < 32; c++)
+                if (c <= lane) a[(base + lane) * DP + base + c] = d[c];
+            // one Newton step: myr = 1/L_ii to full precision (L_ii = d[lane])
+            {
+                double lii = 0.0;
+#pragma unroll
+                for (int c = 0; c < 32; c++) lii = (c == lane) ? d[c] : lii;
+                myr = myr + myr * (1.0 - lii * myr);
             }
-            s += (s1 + s2) + s3;
-            p += (p1 + p2) + p3;
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        p += __shfl_xor_sync(0xffffffffu, p, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        p += __shfl_xor_sync(0xffffffffu, p, 2);
-        // the factored diagonal goes to s_diag so that a[j][j] keeps its input value: nothing read in this step is
-        // overwritten in this step (a[i][j] is read and written by the same thread), hence a single barrier
-        // one reciprocal square root per column instead of sqrt + divide on the critical path
-        if (i >= j && q == 0) {
-            const double piv = rj[j] - p;
-            const double rinv = rsqrt(piv);
-            if (i == j) {
-                if (!(piv > 0.0)) atomicCAS(info, 0, row0 + j + 1);
-                s_diag[j] = piv * rinv;
-                s_rdiag[j] = rinv;
-            } else {
-                a[i * DP + j] = (ri[j] - s) * rinv;
+            // inverse of the 32 x 32 factor: lane c owns column c of X = L^-1; row i of L comes from lane i
+            double xc[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+                const double ri = __shfl_sync(FULL, myr, i);
+                double sacc = (lane == i) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 0; k < i; k++) {
+                    const double lik = __shfl_sync(FULL, d[k], i);
+                    sacc -= lik * xc[k];   // xc[k] = X[k][lane] is zero for k < lane
+                }
+                xc[i] = (lane <= i) ? sacc * ri : 0.0;
             }
+#pragma unroll
+            for (int i = 0; i < 32; i++) sinv[(kb * 32 + i) * SP + lane] = xc[i];
         }
         __syncthreads();
+        if (nr > 0) {
+            // panel: P[r][c] = sum_k B[r][k] X[c][k]   (X lower triangular, zeros stored above its diagonal)
+            const double *X = sinv + kb * 32 * SP;
+            for (int idx = tid; idx < nr * 32; idx += DTHREADS) {
+                const int r = idx >> 5, c = idx & 31;
+                const double *brow = a + (base + 32 + r) * DP + base;
+                const double *xrow = X + c * SP;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 32; k += 4) {
+                    s0 += brow[k] * xrow[k];
+                    s1 += brow[k + 1] * xrow[k + 1];
+                    s2 += brow[k + 2] * xrow[k + 2];
+                    s3 += brow[k + 3] * xrow[k + 3];
+                }
+                pan[r * SP + c] = (s0 + s1) + (s2 + s3);
+            }
+            __syncthreads();
+            // write the panel back as part of L, and update the trailing block (lower part): A22 -= P P'
+            for (int idx = tid; idx < nr * 32; idx += DTHREADS) {
+                const int r = idx >> 5, c = idx & 31;
+                a[(base + 32 + r) * DP + base + c] = pan[r * SP + c];
+            }
+            for (int idx = tid; idx < nr * nr; idx += DTHREADS) {
+                const int r = idx / nr, c = idx - r * nr;
+                if (c > r) continue;
+                const double *pr = pan + r * SP, *pc = pan + c * SP;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 32; k += 4) {
+                    s0 += pr[k] * pc[k];
+                    s1 += pr[k + 1] * pc[k + 1];
+                    s2 += pr[k + 2] * pc[k + 2];
+                    s3 += pr[k + 3] * pc[k + 3];
+                }
+                a[(base + 32 + r) * DP + base + 32 + c] -= (s0 + s1) + (s2 + s3);
+            }
+            __syncthreads();
+        }
     }
-    if (tid < 128) a[tid * DP + tid] = s_diag[tid];
-    __syncthreads();
     // write the factor back (lower triangle only)
     {
         const int c = tid & 127, r0 = tid >> 7;
 #pragma unroll 8
-        for (int r = r0; r < 128; r += 4)
+        for (int r = r0; r < 128; r += 2)
             if (c <= r) A[(int64_t)r * ld + c] = a[r * DP + c];
     }
-    // in-place inversion of the lower-triangular factor, last column first (dtrti2, lower):
-    //   inv[j][j] = 1/L[j][j];  inv[i][j] = -(sum_{k=j+1..i} inv[i][k] L[k][j]) * inv[j][j]
-    // reciprocal diagonal, one Newton step on the factorisation's rsqrt: 1/L_jj to full precision, computed for all
-    // columns at once instead of one division per column step
-    if (tid < 128) {
-        const double dgg = s_diag[tid];
-        double r = s_rdiag[tid];
-        r = r + r * (1.0 - dgg * r);
-        s_rdiag[tid] = r;
-    }
-    __syncthreads();
-    for (int j = 127; j >= 0; j--) {
-        const double ajj = s_rdiag[j];
-        double s = 0.0;
-        if (i > j) {
-            double s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            int k = j + 1 + q;
-            for (; k + 12 <= i; k += 16) {
-                const double x0 = a[k * DP + j], x1 = a[(k + 4) * DP + j], x2 = a[(k + 8) * DP + j], x3 = a[(k + 12) * DP + j];
-                const double y0 = ri[k], y1 = ri[k + 4], y2 = ri[k + 8], y3 = ri[k + 12];
-                s += y0 * x0; s1 += y1 * x1; s2 += y2 * x2; s3 += y3 * x3;
+    // ---------------------------------------------------------------- phase B
+    // block columns J ascending, block rows I ascending, in place: X_IJ overwrites L_IJ once nothing needs L_IJ any more
+    for (int J = 0; J < 3; J++) {
+        for (int I = J + 1; I < 4; I++) {
+            // T = sum_{K=J}^{I-1} L_IK X_KJ   (X_JJ = sinv[J]; X_KJ for K > J already sits in a[K][J])
+            for (int idx = tid; idx < 32 * 32; idx += DTHREADS) {
+                const int r = idx >> 5, c = idx & 31;
+                double s0 = 0.0, s1 = 0.0;
+                for (int K = J; K < I; K++) {
+                    const double *lrow = a + (32 * I + r) * DP + 32 * K;
+                    const double *xcol = (K == J) ? sinv + (J * 32) * SP + c : a + (32 * K) * DP + 32 * J + c;
+                    const int xs = (K == J) ? SP : DP;
+#pragma unroll
+                    for (int k = 0; k < 32; k += 2) {
+                        s0 += lrow[k] * xcol[k * xs];
+                        s1 += lrow[k + 1] * xcol[(k + 1) * xs];
+                    }
+                }
+                tmp[r * SP + c] = s0 + s1;
             }
-            for (; k <= i; k += 4) s += ri[k] * a[k * DP + j];
-            s += (s1 + s2) + s3;
+            __syncthreads();
+            // X_IJ = -X_II T
+            for (int idx = tid; idx < 32 * 32; idx += DTHREADS) {
+                const int r = idx >> 5, c = idx & 31;
+                const double *xr = sinv + (I * 32 + r) * SP;
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 32; k += 2) {
+                    s0 += xr[k] * tmp[k * SP + c];
+                    s1 += xr[k + 1] * tmp[(k + 1) * SP + c];
+                }
+                a[(32 * I + r) * DP + 32 * J + c] = -(s0 + s1);
+            }
+            __syncthreads();
         }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        __syncthreads();
-        if (q == 0) {
-            if (i > j) a[i * DP + j] = -s * ajj;
-            else if (i == j) a[j * DP + j] = ajj;
-        }
-        __syncthreads();
     }
+    // Dinv: off-diagonal blocks from a, diagonal blocks from sinv, zeros above the diagonal
     {
         const int c = tid & 127, r0 = tid >> 7;
 #pragma unroll 8
-        for (int r = r0; r < 128; r += 4) dinv[r * 128 + c] = (c <= r) ? a[r * DP + c] : 0.0;
+        for (int r = r0; r < 128; r += 2) {
+            double v = 0.0;
+            if (c <= r) v = ((c >> 5) == (r >> 5)) ? sinv[((r >> 5) * 32 + (r & 31)) * SP + (c & 31)] : a[r * DP + c];
+            dinv[r * 128 + c] = v;
+        }
     }
 }
 
 void launch_potrf_diag(double *A, int64_t ld, double *dinv, int row0, int *info, cudaStream_t s) {
     static bool attr = false;
-    const size_t smem = (size_t)128 * DP * sizeof(double);
     if (!attr) {
-        JCHECK(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        JCHECK(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
         attr = true;
     }
     g_launch_count++;
-    k_potrf_diag<<<1, DTHREADS, smem, s>>>(A, ld, dinv, row0, info);
+    k_potrf_diag<<<1, DTHREADS, DIAG_SMEM, s>>>(A, ld, dinv, row0, info);
 }
 
 // ---- 2-D copy ---------------------------------------------------------------------------------------------------
@@ -389,86 +451,65 @@ namespace jaicov {
 // ---- skinny triangular solves: NR = 8 right-hand sides stored as rows R[8][np] ------------------------------------
 // One launch per 128-block step, right-looking, every launch spread over the rows (forward) or columns (backward)
 // still to be updated; the 128 x 128 diagonal solve is the multiplication by Dinv and is recomputed by every CTA
-// (128 KB from L2) instead of being a separate launch.  HBM/L2-bound: L is read exactly once per sweep.
+// (128 KB from L2) instead of being a separate launch.  Every product here is (rows x 128) * (128 x 8): exactly one
+// DMMA n-tile wide, so the A fragments are loaded straight from global memory (8 rows x 32-byte sectors per load, all
+// sectors fully used) and the 8 right-hand sides sit in shared memory as the B fragment; no shuffle reductions.
+// HBM/L2-bound: L is read exactly once per sweep.
 constexpr int SR = 8;          // right-hand sides
-constexpr int SCHUNK = 256;    // rows (forward) / columns (backward) per CTA
+constexpr int SCHUNK = 256;    // rows (forward) / columns (backward) per CTA: 8 warps x 32
+constexpr int SPITCH = 132;    // pitch of the right-hand-side tiles in shared memory (== 4 mod 16: conflict-free B fragments)
+
+// acc[mt] += A_tile(mt) * B for NMT 8-row tiles; TRANS = false: A[m][k] at Ap[m * lda + k]; true: A[m][k] at Ap[k * lda + m]
+template <int NMT, bool TRANS>
+__device__ __forceinline__ void skinny_mma(const double *__restrict__ Ap, int64_t lda, const double *sB, double (&acc)[NMT][2],
+                                           int lane) {
+    const int grp = lane >> 2, tig = lane & 3;
+#pragma unroll 8
+    for (int ks = 0; ks < 32; ks++) {
+        const double b = sB[grp * SPITCH + 4 * ks + tig];
+        double a[NMT];
+#pragma unroll
+        for (int mt = 0; mt < NMT; mt++)
+            a[mt] = TRANS ? Ap[(int64_t)(4 * ks + tig) * lda + 8 * mt + grp] : Ap[(int64_t)(8 * mt + grp) * lda + 4 * ks + tig];
+#pragma unroll
+        for (int mt = 0; mt < NMT; mt++) dmma884(acc[mt][0], acc[mt][1], a[mt], b);
+    }
+}
 
 // forward step j: y_j = Dinv_j b_j;  b[i] -= L[i, J] y_j for all rows i below block j
 // (b lives in R and is updated in place below block j; y_j goes to the separate buffer Y so that no CTA can see a
 // half-updated block j)
 __global__ void __launch_bounds__(256) k_solve_fwd_step(const double *__restrict__ L, int64_t ld, const double *__restrict__ dinv,
                                                         double *__restrict__ R, double *__restrict__ Y, int64_t np, int j) {
-    __shared__ double sb[SR][128];
-    __shared__ double sy[SR][128];
+    __shared__ double sb[SR * SPITCH];
+    __shared__ double sy[SR * SPITCH];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = lane >> 2, tig = lane & 3;
     const int64_t J = (int64_t)j * 128;
-    for (int i = tid; i < SR * 128; i += 256) sb[i >> 7][i & 127] = R[(int64_t)(i >> 7) * np + J + (i & 127)];
+    for (int i = tid; i < SR * 128; i += 256) sb[(i >> 7) * SPITCH + (i & 127)] = R[(int64_t)(i >> 7) * np + J + (i & 127)];
     __syncthreads();
-    const double *D = dinv + J * 128;
-    // y[t] = sum_k Dinv[t][k] b[k]: one warp per row, lanes over k; 4 rows (16 loads) in flight per lane
-    for (int t0 = 4 * warp; t0 < 128; t0 += 32) {
-        double dv[4][4];
+    {   // y = Dinv_j b: warp w computes rows 16 w .. 16 w + 15
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        skinny_mma<2, false>(dinv + J * 128 + (int64_t)(16 * warp) * 128, 128, sb, acc, lane);
 #pragma unroll
-        for (int q = 0; q < 4; q++)
-#pragma unroll
-            for (int kk = 0; kk < 4; kk++) dv[q][kk] = D[(t0 + q) * 128 + lane + 32 * kk];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            double acc[SR];
-#pragma unroll
-            for (int r = 0; r < SR; r++) acc[r] = 0.0;
-#pragma unroll
-            for (int kk = 0; kk < 4; kk++)
-#pragma unroll
-                for (int r = 0; r < SR; r++) acc[r] += dv[q][kk] * sb[r][lane + 32 * kk];
-#pragma unroll
-            for (int r = 0; r < SR; r++) {
-                double v = acc[r];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) sy[r][t0 + q] = v;
-            }
+        for (int mt = 0; mt < 2; mt++) {
+            sy[(2 * tig) * SPITCH + 16 * warp + 8 * mt + grp] = acc[mt][0];
+            sy[(2 * tig + 1) * SPITCH + 16 * warp + 8 * mt + grp] = acc[mt][1];
         }
     }
     __syncthreads();
     if (blockIdx.x == 0)
-        for (int i = tid; i < SR * 128; i += 256) Y[(int64_t)(i >> 7) * np + J + (i & 127)] = sy[i >> 7][i & 127];
-    // rows below: each warp takes 4 rows per iteration so that 16 independent loads are in flight per lane
-    const int64_t row0 = J + 128 + (int64_t)blockIdx.x * SCHUNK;
-    const int64_t row1 = min(np, row0 + SCHUNK);
-    for (int64_t i0 = row0 + 4 * warp; i0 < row1; i0 += 32) {
-        double lv[4][4];
+        for (int i = tid; i < SR * 128; i += 256) Y[(int64_t)(i >> 7) * np + J + (i & 127)] = sy[(i >> 7) * SPITCH + (i & 127)];
+    // rows below: warp w takes 32 rows of this CTA's chunk
+    const int64_t row0 = J + 128 + (int64_t)blockIdx.x * SCHUNK + 32 * warp;
+    if (row0 >= np) return;
+    double acc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+    skinny_mma<4, false>(L + row0 * ld + J, ld, sy, acc, lane);
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int64_t i = min(i0 + q, row1 - 1);
-            const double *Li = L + i * ld + J;
-#pragma unroll
-            for (int kk = 0; kk < 4; kk++) lv[q][kk] = Li[lane + 32 * kk];
-        }
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            double acc[SR];
-#pragma unroll
-            for (int r = 0; r < SR; r++) acc[r] = 0.0;
-#pragma unroll
-            for (int kk = 0; kk < 4; kk++) {
-#pragma unroll
-                for (int r = 0; r < SR; r++) acc[r] += lv[q][kk] * sy[r][lane + 32 * kk];
-            }
-#pragma unroll
-            for (int r = 0; r < SR; r++) {
-                double v = acc[r];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                acc[r] = v;
-            }
-            if (lane < SR && i0 + q < row1) {
-                double v = acc[0];
-#pragma unroll
-                for (int r = 1; r < SR; r++) v = (lane == r) ? acc[r] : v;
-                R[(int64_t)lane * np + i0 + q] -= v;
-            }
-        }
+    for (int mt = 0; mt < 4; mt++) {
+        const int64_t row = row0 + 8 * mt + grp;
+        R[(int64_t)(2 * tig) * np + row] -= acc[mt][0];
+        R[(int64_t)(2 * tig + 1) * np + row] -= acc[mt][1];
     }
 }
 
@@ -476,54 +517,36 @@ __global__ void __launch_bounds__(256) k_solve_fwd_step(const double *__restrict
 // (y lives in Y and is updated in place left of block j; x_j goes to R)
 __global__ void __launch_bounds__(256) k_solve_bwd_step(const double *__restrict__ L, int64_t ld, const double *__restrict__ dinv,
                                                         double *__restrict__ R, double *__restrict__ Y, int64_t np, int j) {
-    __shared__ double sy[SR][128];
-    __shared__ double sx[SR][128];
-    const int tid = threadIdx.x;
+    __shared__ double sy[SR * SPITCH];
+    __shared__ double sx[SR * SPITCH];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = lane >> 2, tig = lane & 3;
     const int64_t J = (int64_t)j * 128;
-    for (int i = tid; i < SR * 128; i += 256) sy[i >> 7][i & 127] = Y[(int64_t)(i >> 7) * np + J + (i & 127)];
+    for (int i = tid; i < SR * 128; i += 256) sy[(i >> 7) * SPITCH + (i & 127)] = Y[(int64_t)(i >> 7) * np + J + (i & 127)];
     __syncthreads();
-    const double *D = dinv + J * 128;
-    {   // x[t] = sum_k Dinv[k][t] y[k]  (coalesced over t; Dinv[k][t] = 0 for k < t, so the loop is branch-free and
-        // unrolled: 16 independent loads in flight).  Two threads per t split k into halves.
-        const int t = tid & 127, half = tid >> 7;
-        double acc[SR];
+    {   // x = Dinv_j' y: A[m][k] = Dinv[k][m]
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        skinny_mma<2, true>(dinv + J * 128 + 16 * warp, 128, sy, acc, lane);
 #pragma unroll
-        for (int r = 0; r < SR; r++) acc[r] = 0.0;
-#pragma unroll 16
-        for (int kk = 0; kk < 64; kk++) {
-            const int k = half * 64 + kk;
-            const double dv = D[k * 128 + t];
-#pragma unroll
-            for (int r = 0; r < SR; r++) acc[r] += dv * sy[r][k];
-        }
-        if (half == 1) {
-#pragma unroll
-            for (int r = 0; r < SR; r++) sx[r][t] = acc[r];
-        }
-        __syncthreads();
-        if (half == 0) {
-#pragma unroll
-            for (int r = 0; r < SR; r++) sx[r][t] += acc[r];
+        for (int mt = 0; mt < 2; mt++) {
+            sx[(2 * tig) * SPITCH + 16 * warp + 8 * mt + grp] = acc[mt][0];
+            sx[(2 * tig + 1) * SPITCH + 16 * warp + 8 * mt + grp] = acc[mt][1];
         }
     }
     __syncthreads();
     if (blockIdx.x == 0)
-        for (int i = tid; i < SR * 128; i += 256) R[(int64_t)(i >> 7) * np + J + (i & 127)] = sx[i >> 7][i & 127];
+        for (int i = tid; i < SR * 128; i += 256) R[(int64_t)(i >> 7) * np + J + (i & 127)] = sx[(i >> 7) * SPITCH + (i & 127)];
     if (j == 0) return;
-    const int64_t c0 = (int64_t)blockIdx.x * SCHUNK;
-    for (int64_t c = c0 + tid; c < min(J, c0 + SCHUNK); c += 256) {
-        double acc[SR];
+    // columns left of block j: A[m = column][k = row of block J] = L[J + k][c]
+    const int64_t c0 = (int64_t)blockIdx.x * SCHUNK + 32 * warp;
+    if (c0 >= J) return;
+    double acc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+    skinny_mma<4, true>(L + J * ld + c0, ld, sx, acc, lane);
 #pragma unroll
-        for (int r = 0; r < SR; r++) acc[r] = 0.0;
-        const double *Lc = L + J * ld + c;
-#pragma unroll 16
-        for (int i = 0; i < 128; i++) {
-            const double lv = Lc[(int64_t)i * ld];
-#pragma unroll
-            for (int r = 0; r < SR; r++) acc[r] += lv * sx[r][i];
-        }
-#pragma unroll
-        for (int r = 0; r < SR; r++) Y[(int64_t)r * np + c] -= acc[r];
+    for (int mt = 0; mt < 4; mt++) {
+        const int64_t c = c0 + 8 * mt + grp;
+        Y[(int64_t)(2 * tig) * np + c] -= acc[mt][0];
+        Y[(int64_t)(2 * tig + 1) * np + c] -= acc[mt][1];
     }
 }
 

@@ -433,6 +433,42 @@ void launch_get_block_dist(const double *X, int64_t ldx, const int32_t *col_loca
     k_get_block_dist<<<(unsigned)(blocks < 4736 ? blocks : 4736), 256, 0, s>>>(X, ldx, col_local, border, np, q11, d, rank, r0, r1, c0, c1, out);
 }
 
+// Gather of an arbitrary sub-matrix of Qxx (what util/io/writer/MatlabResultWriter.java:209-223 and
+// DefaultResultWriter.java:126-155 loop over with cofactor.get(row, column)): out[i][j] = scale * Qxx[row_idx[i]][col_idx[j]].
+// Single GPU: lower != nullptr; distributed: X/col_local (entries owned elsewhere are 0, the sum over ranks is the matrix).
+__global__ void __launch_bounds__(256) k_get_submatrix(const double *__restrict__ lower, int64_t ld, const double *__restrict__ X, int64_t ldx,
+                                                       const int32_t *__restrict__ col_local, const double *__restrict__ border, int64_t np,
+                                                       const double *__restrict__ q11, int d, int rank, const int32_t *__restrict__ row_idx,
+                                                       int n_rows, const int32_t *__restrict__ col_idx, int n_cols, double scale,
+                                                       double *__restrict__ out) {
+    const int64_t total = (int64_t)n_rows * n_cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = row_idx[i / n_cols], c = col_idx[i % n_cols];
+        const int lo = r < c ? r : c, hi = r < c ? c : r;
+        double v = 0.0;
+        if (hi < d) v = rank == 0 ? q11[lo * kMaxDatum + hi] : 0.0;
+        else if (lo < d) v = rank == 0 ? border[(int64_t)lo * np + (hi - d)] : 0.0;
+        else if (lower) v = lower[(int64_t)(hi - d) * ld + (lo - d)];
+        else {
+            const int e = lo - d;
+            const int jl = col_local[e >> 7];
+            if (jl >= 0) v = X[(int64_t)(hi - d) * ldx + jl * 128 + (e & 127)];
+        }
+        out[i] = scale * v;
+    }
+}
+
+void launch_get_submatrix(const double *lower, int64_t ld, const double *X, int64_t ldx, const int32_t *col_local, const double *border,
+                          int64_t np, const double *q11, int d, int rank, const int32_t *row_idx, int n_rows, const int32_t *col_idx,
+                          int n_cols, double scale, double *out, cudaStream_t s) {
+    const int64_t total = (int64_t)n_rows * n_cols;
+    if (total <= 0) return;
+    const int64_t blocks = (total + 255) / 256;
+    g_launch_count++;
+    k_get_submatrix<<<(unsigned)(blocks < 4736 ? blocks : 4736), 256, 0, s>>>(lower, ld, X, ldx, col_local, border, np, q11, d, rank, row_idx,
+                                                                            n_rows, col_idx, n_cols, scale, out);
+}
+
 // ---- directly observed parameter groups (PDF:447-473) -------------------------------------------------------------
 // w_i = obs_i - value(target_i)
 __global__ void k_group_w(int r, const double *const *__restrict__ tptr, const double *__restrict__ obs, double *__restrict__ w) {

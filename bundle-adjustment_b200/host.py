@@ -484,6 +484,7 @@ class BundleAdjustment:
         self._omega = 0.0
         self._objectCoordinates = []
         self._status = EstimationStateType.BUSY
+        self._writer = None
         self.stats = None
 
     # :652-665
@@ -497,6 +498,9 @@ class BundleAdjustment:
             else: raise TypeError('unsupported argument %r' % (it,))
 
     def addPropertyChangeListener(self, listener): self._listeners.append(listener)
+
+    def setAdjustmentResultWriter(self, adjustmentResultWriter):     # :1123-1125
+        self._writer = adjustmentResultWriter
 
     def setEstimationType(self, estimationType):       # :1132-1137
         if estimationType in (EstimationType.L2NORM, EstimationType.SIMULATION):
@@ -828,4 +832,9 @@ class BundleAdjustment:
             for p in ep:
                 p.setValue(eo[ke]); ke += 1
         self._status = EstimationStateType(rc) if rc in (1, -1, -2, -4, -7) else EstimationStateType.NOT_INITIALISED
+        if rc in (1, -4) and self._writer is not None:                # exportAdjustmentResults, :360-368, :1164-1171
+            try:
+                self._writer.export(self)
+            except (ValueError, TypeError, OSError):
+                self._status = EstimationStateType.EXPORT_ADJUSTMENT_RESULTS_FAILED
         return self._status

@@ -197,6 +197,11 @@ int32_t jaicov_get_dx(jaicov_handle *h, double *dx);
 int32_t jaicov_get_qxx_packed(jaicov_handle *h, double *dst);
 /* rectangular tile rows [r0,r1) x cols [c0,c1) of the full symmetric Qxx, row-major with leading dimension ld */
 int32_t jaicov_get_qxx_block(jaicov_handle *h, int32_t r0, int32_t r1, int32_t c0, int32_t c1, double *dst, int64_t ld);
+/* dst[i * n_idx + j] = scale * Qxx[idx[i]][idx[j]] (reference column numbers, border included): the sub-matrix the
+ * result writers export -- MatlabResultWriter "dispersion" (scale 1, util/io/writer/MatlabResultWriter.java:209-223) and
+ * DefaultResultWriter ".cxx" (scale sigma0^2 a posteriori, util/io/writer/DefaultResultWriter.java:126-155) -- gathered on
+ * the device so that the full Qxx never has to travel to the host.  Distributed handle: partial (sum over ranks). */
+int32_t jaicov_get_qxx_submatrix(jaicov_handle *h, int32_t n_idx, const int32_t *idx, double scale, double *dst);
 /* diagonal of Qxx, length u+d */
 int32_t jaicov_get_qxx_diag(jaicov_handle *h, double *dst);
 

@@ -281,3 +281,35 @@ def test_properties_at_config4_size(built):
         e[c] = 1.0
         # residual in the Jacobi-scaled system (V K V)(V^-1 Q V^-1) = I, V = diag(K)^-1/2 (1 on the border)
         assert (np.abs(NQ[:, k] - e) * vsc / vsc[c]).max() < 1e-8
+
+
+def test_result_writers_export_from_device(built, tmp_path):
+    """MatlabResultWriter / DefaultResultWriter semantics on the device-resident Qxx -- the exported
+    sub-matrices against the oracle's cofactor matrix (MatlabResultWriter.java:92-223, DefaultResultWriter.java:46-155)."""
+    from scipy.io import loadmat
+    scene = example_scene()
+    adj, pts = build_adjustment(scene)
+    w = ba.MatlabResultWriter(str(tmp_path / 'adjustment_results'))
+    adj.setAdjustmentResultWriter(w)
+    assert adj.estimateModel() == ba.EstimationStateType.ERROR_FREE_ESTIMATION
+    o = Oracle(scene)
+    assert o.estimate() == 1
+    Qo = o.qxx_dense()
+    m = loadmat(str(tmp_path / 'adjustment_results.mat'))
+    idx = np.array(w.indices)
+    # 150 points x 3 + x0,y0,c + Bx,By,A1,A2 (fixed A3, Cx, Cy carry cov = -1)
+    assert idx.size == 450 + 3 + 4 and m['dispersion'].shape == (457, 457)
+    sg = np.sqrt(np.diag(Qo)[idx])
+    assert (np.abs(m['dispersion'] - Qo[np.ix_(idx, idx)]) / np.outer(sg, sg)).max() < TOL_Q
+    assert abs(float(m['variance_of_unit_weight_post']) - o.variance_factor_aposteriori()) <= TOL_S2 * o.variance_factor_aposteriori()
+    assert int(m['degree_of_freedom']) == 18804 and int(m['number_of_unknowns']) == 1147
+    cov = np.array([int(x) for x in m['distortion_parameters']['cov'].ravel()])
+    assert (cov == -1).sum() == 3 and cov.max() == 457
+    d = ba.DefaultResultWriter(str(tmp_path / 'default'))
+    d.export(adj)
+    C = np.loadtxt(str(tmp_path / 'default.cxx'))
+    pidx = np.array(d.indices)
+    ref = o.variance_factor_aposteriori() * Qo[np.ix_(pidx, pidx)]
+    assert C.shape == (450, 450) and np.abs(C - ref).max() < 1e-14 + 1e-8 * np.abs(ref).max()
+    info = open(str(tmp_path / 'default.info')).read().splitlines()
+    assert len(info) == 450 and info[0].split()[1] == 'X' and int(info[2].split()[-1]) == 2

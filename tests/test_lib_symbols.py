@@ -20,7 +20,7 @@ def declared_symbols():
 def test_exports_match_header(built):
     L = ba._lib.load()
     names = declared_symbols()
-    assert len(names) >= 29
+    assert len(names) >= 30
     for n in names:
         assert hasattr(L, n), n
     assert sorted(ba._lib.EXPORTS) == names
