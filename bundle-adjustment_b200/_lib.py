@@ -23,7 +23,7 @@ EXPORTS = [
     'jaicov_default_options', 'jaicov_create', 'jaicov_destroy', 'jaicov_last_error', 'jaicov_device_count', 'jaicov_launch_count', 'jaicov_nccl_unique_id', 'jaicov_dist_init',
     'jaicov_get_qxx_local', 'jaicov_shard_images',
     'jaicov_set_cameras', 'jaicov_set_images', 'jaicov_set_image_points', 'jaicov_set_object_points',
-    'jaicov_set_scale_bars', 'jaicov_add_observed_group', 'jaicov_set_datum', 'jaicov_estimate', 'jaicov_iterate',
+    'jaicov_set_scale_bars', 'jaicov_add_observed_group', 'jaicov_set_datum', 'jaicov_set_reduced_rows', 'jaicov_estimate', 'jaicov_iterate',
     'jaicov_get_stats', 'jaicov_get_values', 'jaicov_get_dx', 'jaicov_get_qxx_packed', 'jaicov_get_qxx_block',
     'jaicov_get_qxx_diag', 'jaicov_get_qxx_submatrix', 'jaicov_eval_residual_jacobian', 'jaicov_get_normal_equations', 'jaicov_omega',
     'jaicov_spd_solve_invert',
@@ -80,6 +80,7 @@ def load():
     L.jaicov_set_scale_bars.argtypes = [vp, i32, vp, vp, vp, vp]
     L.jaicov_add_observed_group.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
     L.jaicov_set_datum.argtypes = [vp, vp, i32, i32]
+    L.jaicov_set_reduced_rows.argtypes = [vp, i32]
     L.jaicov_estimate.argtypes = [vp, vp, vp, vp]
     L.jaicov_iterate.argtypes = [vp, i32, i32]
     L.jaicov_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
@@ -189,6 +190,11 @@ class Session:
         ff = _i32(f['free_flags'])
         self.check(L.jaicov_set_datum(h, _p(ff), int(f['n_unknowns']), int(f['n_observations'])))
         self.n = int(f['n_unknowns']) + int(ff.sum())
+        self.n_qxx = self.n
+        if f.get('reduced_rows') is not None:
+            self.check(L.jaicov_set_reduced_rows(h, int(f['reduced_rows'])))
+            if self.opt.invert_mode in (INVERT_REDUCED, INVERT_PRE_ELIMINATION):
+                self.n_qxx = min(self.n, int(f['reduced_rows']))
         self.shapes = dict(xyz=xyz.size, io=io_val.size, coef=cv.size, eo=ev.size, m=oi.size,
                            ncoef_max=int(np.max(np.diff(cp))) if cp.size > 1 else 0)
 
@@ -250,7 +256,7 @@ class Session:
 
     def qxx_packed(self, out=None):
         if out is None:
-            out = np.empty(self.n * (self.n + 1) // 2)
+            out = np.empty(self.n_qxx * (self.n_qxx + 1) // 2)
         self.check(self.L.jaicov_get_qxx_packed(self.h, out.ctypes.data))
         return out
 
@@ -266,7 +272,7 @@ class Session:
         return out
 
     def qxx_diag(self):
-        out = np.empty(self.n)
+        out = np.empty(self.n_qxx)
         self.check(self.L.jaicov_get_qxx_diag(self.h, out.ctypes.data))
         return out
 

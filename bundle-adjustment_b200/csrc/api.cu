@@ -195,6 +195,15 @@ struct jaicov_handle {
     std::vector<int32_t> ptab;           // first columns of the tiles of the FACTOR this rank updates (its Cholesky panels)
     DevBuf<double> d_cam_sum;
     int64_t strip_row0 = -1;             // first row of the EO strip of N that is all-reduced
+    // MatrixInversion.REDUCED / PRE_ELIMINATION (BA:261-291): numRows of the reduced system (BA:262).  The Schur
+    // complement on the EO blocks is not formed: its solution and cofactor matrix are the leading numRows block of the
+    // full solution / inverse, which the tensor-core path computes anyway; only that block is exposed.
+    int reduced_rows = -1;
+    bool wants_inverse() const { return opt.invert_mode != JAICOV_INVERT_NONE; }
+    int qxx_rows() const {
+        const int n = P.u + P.d;
+        return (opt.invert_mode == JAICOV_INVERT_REDUCED || opt.invert_mode == JAICOV_INVERT_PRE_ELIMINATION) ? std::min(n, reduced_rows) : n;
+    }
 };
 
 namespace {
@@ -420,15 +429,17 @@ void prepare(jaicov_handle *h) {
         std::vector<int32_t> kt = h->ktab;
         if (kt.empty()) kt.push_back(0);
         h->d_ktab.upload(kt);
-        if (h->opt.invert_mode == JAICOV_INVERT_FULL) h->Xl.alloc(np * (size_t)kBlk * std::max<size_t>(h->ktab.size(), 1));
+        if (h->wants_inverse()) h->Xl.alloc(np * (size_t)kBlk * std::max<size_t>(h->ktab.size(), 1));
         // EO strip of N: every entry the image sweeps write lies in a row >= the smallest EO row
         int64_t r0 = -1;
         for (int32_t c : h->eo_col)
             if (active(c)) r0 = (r0 < 0) ? c - d : std::min<int64_t>(r0, c - d);
         h->strip_row0 = r0;
-    } else if (h->opt.invert_mode == JAICOV_INVERT_FULL) {
+    } else if (h->wants_inverse()) {
         h->W.alloc(np * np);
     }
+    if ((h->opt.invert_mode == JAICOV_INVERT_REDUCED || h->opt.invert_mode == JAICOV_INVERT_PRE_ELIMINATION) && h->reduced_rows < 0)
+        throw std::runtime_error("invert_mode REDUCED / PRE_ELIMINATION needs jaicov_set_reduced_rows (numRows of BA:262)");
     h->Dinv.alloc(np * kBlk);
     h->rhs.alloc(np); h->V.alloc(np);
     h->Bt.alloc(8 * np); h->Btv.alloc(8 * np); h->H.alloc(8 * np); h->Tq.alloc(8 * np);
@@ -523,7 +534,7 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     const DevProblem &P = h->P;
     cudaStream_t s = h->stream;
     const size_t np = (size_t)P.np;
-    const bool invert = final_pass && h->opt.invert_mode == JAICOV_INVERT_FULL;
+    const bool invert = final_pass && h->wants_inverse();
     JCHECK(cudaEventRecord(h->ev[0], s));
     assemble(h);
     // preconditioner and SPD reformulation (K4)
@@ -703,7 +714,7 @@ int32_t jaicov_create(const jaicov_options *opt, jaicov_handle **out) {
     if (!opt || !out) return JAICOV_ILLEGAL_ARGUMENT;
     *out = nullptr;
     if (opt->damping_value != 0.0) return JAICOV_ILLEGAL_ARGUMENT;
-    if (opt->invert_mode != JAICOV_INVERT_NONE && opt->invert_mode != JAICOV_INVERT_FULL) return JAICOV_ILLEGAL_ARGUMENT;
+    if (opt->invert_mode < JAICOV_INVERT_NONE || opt->invert_mode > JAICOV_INVERT_REDUCED) return JAICOV_ILLEGAL_ARGUMENT;
     if (opt->estimation_type != JAICOV_L2NORM && opt->estimation_type != JAICOV_SIMULATION) return JAICOV_ILLEGAL_ARGUMENT;
     jaicov_handle *h = new (std::nothrow) jaicov_handle();
     if (!h) return JAICOV_OUT_OF_MEMORY;
@@ -867,6 +878,12 @@ int32_t jaicov_set_datum(jaicov_handle *h, const int32_t free_flags[7], int32_t 
     return JAICOV_OK;
 }
 
+int32_t jaicov_set_reduced_rows(jaicov_handle *h, int32_t num_rows) {
+    if (!h || num_rows < 0) return JAICOV_ILLEGAL_ARGUMENT;
+    h->reduced_rows = num_rows;
+    return JAICOV_OK;
+}
+
 int32_t jaicov_iterate(jaicov_handle *h, int32_t final_pass, int32_t apply_update) {
     if (!h) return JAICOV_ILLEGAL_ARGUMENT;
     API_GUARD_BEGIN
@@ -974,9 +991,9 @@ int32_t jaicov_get_dx(jaicov_handle *h, double *dx) {
     API_GUARD_END(h)
 }
 
-static int32_t pack_to_host(jaicov_handle *h, const double *border, const double *q11, double *dst) {
+static int32_t pack_to_host(jaicov_handle *h, const double *border, const double *q11, double *dst, int64_t n_limit = -1) {
     const DevProblem &P = h->P;
-    const int64_t n = (int64_t)P.u + P.d;
+    const int64_t n = n_limit >= 0 ? n_limit : (int64_t)P.u + P.d;   // the packed leading block is a prefix of the packed matrix
     const int64_t budget = (int64_t)1 << 25;   // doubles per staging chunk (256 MiB)
     DevBuf<double> stage[2];
     int64_t c0 = 0;
@@ -1004,14 +1021,14 @@ int32_t jaicov_get_qxx_packed(jaicov_handle *h, double *dst) {
     if (h->dist_on) return fail(h, JAICOV_ILLEGAL_ARGUMENT, "distributed handle: Qxx is spread over the ranks, use jaicov_get_qxx_block (partial sums) or jaicov_get_qxx_local");
     API_GUARD_BEGIN
     JCHECK(cudaSetDevice(h->opt.device));
-    return pack_to_host(h, h->Tq.p, h->small.p + 49, dst);
+    return pack_to_host(h, h->Tq.p, h->small.p + 49, dst, h->qxx_rows());
     API_GUARD_END(h)
 }
 
 int32_t jaicov_get_qxx_block(jaicov_handle *h, int32_t r0, int32_t r1, int32_t c0, int32_t c1, double *dst, int64_t ld) {
     if (!h || !dst) return JAICOV_ILLEGAL_ARGUMENT;
     if (!h->have_qxx) return fail(h, JAICOV_NOT_INITIALISED, "no cofactor matrix: run a final pass with invert_mode FULL");
-    const int n = h->P.u + h->P.d;
+    const int n = h->qxx_rows();
     if (r0 < 0 || c0 < 0 || r1 > n || c1 > n || r1 < r0 || c1 < c0 || ld < c1 - c0) return JAICOV_ILLEGAL_ARGUMENT;
     API_GUARD_BEGIN
     JCHECK(cudaSetDevice(h->opt.device));
@@ -1036,7 +1053,7 @@ int32_t jaicov_get_qxx_block(jaicov_handle *h, int32_t r0, int32_t r1, int32_t c
 int32_t jaicov_get_qxx_submatrix(jaicov_handle *h, int32_t n_idx, const int32_t *idx, double scale, double *dst) {
     if (!h || n_idx < 0 || (n_idx > 0 && (!idx || !dst))) return JAICOV_ILLEGAL_ARGUMENT;
     if (!h->have_qxx) return fail(h, JAICOV_NOT_INITIALISED, "no cofactor matrix: run a final pass with invert_mode FULL");
-    const int n = h->P.u + h->P.d;
+    const int n = h->qxx_rows();
     for (int i = 0; i < n_idx; i++)
         if (idx[i] < 0 || idx[i] >= n) return fail(h, JAICOV_ILLEGAL_ARGUMENT, "index outside the cofactor matrix");
     if (n_idx == 0) return JAICOV_OK;
@@ -1069,9 +1086,10 @@ int32_t jaicov_get_qxx_diag(jaicov_handle *h, double *dst) {
     const DevProblem &P = h->P;
     std::vector<double> small(128);
     JCHECK(cudaMemcpy(small.data(), h->small.p, 128 * sizeof(double), cudaMemcpyDeviceToHost));
-    for (int a = 0; a < P.d; a++) dst[a] = small[49 + a * kMaxDatum + a];
-    if (P.u)
-        JCHECK(cudaMemcpy2D(dst + P.d, sizeof(double), h->M.p, (size_t)(P.np + 1) * sizeof(double), sizeof(double), P.u,
+    const int nq = h->qxx_rows();
+    for (int a = 0; a < std::min(P.d, nq); a++) dst[a] = small[49 + a * kMaxDatum + a];
+    if (nq > P.d)
+        JCHECK(cudaMemcpy2D(dst + P.d, sizeof(double), h->M.p, (size_t)(P.np + 1) * sizeof(double), sizeof(double), nq - P.d,
                             cudaMemcpyDeviceToHost));
     return JAICOV_OK;
     API_GUARD_END(h)

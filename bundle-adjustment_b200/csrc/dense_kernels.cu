@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(DTHREADS, 1) k_potrf_diag(double *__restrict__
     double *a = dsm;                       // [128][DP]   the block: A -> L -> (phase B) inverse, lower triangle
     double *sinv = a + 128 * DP;           // [4][32][SP] inverses of the 32 x 32 diagonal sub-blocks of L
     double *pan = sinv + 4 * 32 * SP;      // [96][SP]    panel below the current diagonal sub-block
-    double *tmp = pan + 96 * SP;           // [32][SP]    phase B scratch
+    double *tmp = pan + 96 * SP;           // [32][SP]    phase B scratch; phase A: column broadcast buffer
+    __shared__ double s_rdiag[128];        // 1 / L_ii
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
     // load the lower triangle (coalesced rows), zero above the diagonal
@@ -268,81 +269,64 @@ __global__ void __launch_bounds__(DTHREADS, 1) k_potrf_diag(double *__restrict__
     }
     __syncthreads();
 
-    // ---------------------------------------------------------------- phase A
+    // ---------------------------------------------------------------- phase A: Cholesky, four 32-wide panels
     for (int kb = 0; kb < 4; kb++) {
         const int base = 32 * kb;
         const int nr = 96 - base;          // rows below the diagonal sub-block
         if (warp == 0) {
+            // 32 x 32 diagonal sub-block in registers: lane = row, d[c] = column.  The freshly scaled column travels
+            // to the other lanes through a 32-double shared buffer (one LDS.128 per two rows instead of four SHFL).
             double d[32];
 #pragma unroll
             for (int c = 0; c < 32; c++) d[c] = a[(base + lane) * DP + base + c];
-            double myr = 0.0;              // 1 / L_ii of this lane's row
+            double *col = tmp;             // [32]
 #pragma unroll
             for (int jj = 0; jj < 32; jj++) {
                 const double pj = __shfl_sync(FULL, d[jj], jj);
                 const double r = rsqrt(pj);
-                if (lane == jj) {
-                    if (!(pj > 0.0)) atomicCAS(info, 0, row0 + base + jj + 1);
-                    myr = r;
-                }
                 const double dj = (lane == jj) ? pj * r : d[jj] * r;
                 d[jj] = dj;
+                if (lane == jj) {
+                    if (!(pj > 0.0)) atomicCAS(info, 0, row0 + base + jj + 1);
+                    s_rdiag[base + jj] = r + r * (1.0 - dj * r);    // 1 / L_jj, one Newton step on the rsqrt
+                }
+                if (jj < 31) {
+                    col[lane] = dj;
+                    __syncwarp();
 #pragma unroll
-                for (int c = jj + 1; c < 32; c++) {
-                    const double lc = __shfl_sync(FULL, dj, c);
-                    d[c] -= dj * lc;       // meaningful for lanes >= c; lanes < c only touch their unused upper part
+                    for (int c = jj + 1; c < 32; c++) d[c] -= dj * col[c];   // meaningful for lanes >= c
+                    __syncwarp();
                 }
             }
 #pragma unroll
             for (int c = 0; c < 32; c++)
                 if (c <= lane) a[(base + lane) * DP + base + c] = d[c];
-            // one Newton step: myr = 1/L_ii to full precision (L_ii = d[lane])
-            {
-                double lii = 0.0;
-#pragma unroll
-                for (int c = 0; c < 32; c++) lii = (c == lane) ? d[c] : lii;
-                myr = myr + myr * (1.0 - lii * myr);
-            }
-            // inverse of the 32 x 32 factor: lane c owns column c of X = L^-1; row i of L comes from lane i
-            double xc[32];
-#pragma unroll
-            for (int i = 0; i < 32; i++) {
-                const double ri = __shfl_sync(FULL, myr, i);
-                double sacc = (lane == i) ? 1.0 : 0.0;
-#pragma unroll
-                for (int k = 0; k < i; k++) {
-                    const double lik = __shfl_sync(FULL, d[k], i);
-                    sacc -= lik * xc[k];   // xc[k] = X[k][lane] is zero for k < lane
-                }
-                xc[i] = (lane <= i) ? sacc * ri : 0.0;
-            }
-#pragma unroll
-            for (int i = 0; i < 32; i++) sinv[(kb * 32 + i) * SP + lane] = xc[i];
         }
         __syncthreads();
         if (nr > 0) {
-            // panel: P[r][c] = sum_k B[r][k] X[c][k]   (X lower triangular, zeros stored above its diagonal)
-            const double *X = sinv + kb * 32 * SP;
-            for (int idx = tid; idx < nr * 32; idx += DTHREADS) {
-                const int r = idx >> 5, c = idx & 31;
-                const double *brow = a + (base + 32 + r) * DP + base;
-                const double *xrow = X + c * SP;
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            // panel below: row r solves x L_kk' = b by forward substitution (every thread its own row, L_kk broadcast)
+            if (tid < nr) {
+                double *brow = a + (base + 32 + tid) * DP + base;
+                const double *Lk = a + base * DP + base;
+                double x[32];
 #pragma unroll
-                for (int k = 0; k < 32; k += 4) {
-                    s0 += brow[k] * xrow[k];
-                    s1 += brow[k + 1] * xrow[k + 1];
-                    s2 += brow[k + 2] * xrow[k + 2];
-                    s3 += brow[k + 3] * xrow[k + 3];
+                for (int c = 0; c < 32; c++) x[c] = brow[c];
+#pragma unroll
+                for (int c = 0; c < 32; c++) {
+                    double s0 = x[c], s1 = 0.0;
+#pragma unroll
+                    for (int k = 0; k + 1 < c; k += 2) {
+                        s0 -= x[k] * Lk[c * DP + k];
+                        s1 -= x[k + 1] * Lk[c * DP + k + 1];
+                    }
+                    if (c & 1) s0 -= x[c - 1] * Lk[c * DP + c - 1];
+                    x[c] = (s0 + s1) * s_rdiag[base + c];
                 }
-                pan[r * SP + c] = (s0 + s1) + (s2 + s3);
+#pragma unroll
+                for (int c = 0; c < 32; c++) { brow[c] = x[c]; pan[tid * SP + c] = x[c]; }
             }
             __syncthreads();
-            // write the panel back as part of L, and update the trailing block (lower part): A22 -= P P'
-            for (int idx = tid; idx < nr * 32; idx += DTHREADS) {
-                const int r = idx >> 5, c = idx & 31;
-                a[(base + 32 + r) * DP + base + c] = pan[r * SP + c];
-            }
+            // trailing update (lower part): A22 -= P P'
             for (int idx = tid; idx < nr * nr; idx += DTHREADS) {
                 const int r = idx / nr, c = idx - r * nr;
                 if (c > r) continue;
@@ -367,6 +351,27 @@ __global__ void __launch_bounds__(DTHREADS, 1) k_potrf_diag(double *__restrict__
         for (int r = r0; r < 128; r += 2)
             if (c <= r) A[(int64_t)r * ld + c] = a[r * DP + c];
     }
+    // ---------------------------------------------------------------- the four 32 x 32 inverses, one warp each
+    if (warp < 4) {
+        // lane c owns column c of X = L_kk^-1:  X[i][c] = (delta_ic - sum_{k<i} L[i][k] X[k][c]) / L[i][i]
+        const int base = 32 * warp;
+        const double *Lk = a + base * DP + base;
+        double xc[32];
+#pragma unroll
+        for (int i2 = 0; i2 < 32; i2++) {
+            double s0 = (lane == i2) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+            for (int k = 0; k + 1 < i2; k += 2) {
+                s0 -= Lk[i2 * DP + k] * xc[k];          // xc[k] = X[k][lane] is zero for k < lane
+                s1 -= Lk[i2 * DP + k + 1] * xc[k + 1];
+            }
+            if (i2 & 1) s0 -= Lk[i2 * DP + i2 - 1] * xc[i2 - 1];
+            xc[i2] = (lane <= i2) ? (s0 + s1) * s_rdiag[base + i2] : 0.0;
+        }
+#pragma unroll
+        for (int i2 = 0; i2 < 32; i2++) sinv[(warp * 32 + i2) * SP + lane] = xc[i2];
+    }
+    __syncthreads();
     // ---------------------------------------------------------------- phase B
     // block columns J ascending, block rows I ascending, in place: X_IJ overwrites L_IJ once nothing needs L_IJ any more
     for (int J = 0; J < 3; J++) {

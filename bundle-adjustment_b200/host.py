@@ -535,7 +535,15 @@ class BundleAdjustment:
         if self._invert == MatrixInversion.NONE or self._session is None:
             return None
         if self._Qxx is None:
-            self._Qxx = UpperSymmPackMatrix(self._session.n, self._session.qxx_packed())
+            n, nq = self._session.n, self._session.n_qxx
+            data = self._session.qxx_packed()
+            if nq < n:
+                # REDUCED / PRE_ELIMINATION: the reference hands out the full-size matrix object whose leading block is
+                # the reduced cofactor matrix (the rest holds unspecified leftovers there, zeros here)
+                full = np.zeros(n * (n + 1) // 2)
+                full[:data.size] = data
+                data = full
+            self._Qxx = UpperSymmPackMatrix(n, data)
         return self._Qxx
 
     # ---- prepareUnknownParameters, :667-782, and detectRankDefect, :836-1042 ---------------------------------------
@@ -749,6 +757,7 @@ class BundleAdjustment:
             s.column[:] = pt_col[off:off + len(s)]
             off += len(s)
         self._numObs, self._numUnknown, self._defect = numObs, counter, d
+        self._numIO, self._numDist, self._numObjectCoordinates = nIO, nDist, len(oc_list)
         self._objectCoordinates = [ObjectCoordinate._view(*self._locate(stores, g)) for g in oc_list] if len(oc_list) <= 100000 else []
         # ---- flatten ------------------------------------------------------------------------------------------------------
         io_val, io_col, r0, coef_ptr, ctype, cord, cval, ccol = [], [], [], [0], [], [], [], []
@@ -800,12 +809,14 @@ class BundleAdjustment:
     def estimateModel(self):
         if self._damping > 0:
             raise NotImplementedError('Levenberg-Marquardt damping is not available in the B200 path yet')
-        if self._invert in (MatrixInversion.PRE_ELIMINATION, MatrixInversion.REDUCED):
-            raise NotImplementedError('MatrixInversion.%s is not available in the B200 path yet' % self._invert.name)
         flat = self._prepare()
+        # numRows of the reduced system, :262
+        flat['reduced_rows'] = self._numIO + self._numDist + 3 * self._numObjectCoordinates + self._defect
         self._Qxx = None
         self._session = _lib.Session(
-            invert_mode=_lib.INVERT_FULL if self._invert == MatrixInversion.FULL else _lib.INVERT_NONE,
+            invert_mode={MatrixInversion.NONE: _lib.INVERT_NONE, MatrixInversion.FULL: _lib.INVERT_FULL,
+                         MatrixInversion.PRE_ELIMINATION: _lib.INVERT_PRE_ELIMINATION,
+                         MatrixInversion.REDUCED: _lib.INVERT_REDUCED}[self._invert],
             estimation_type=_lib.SIMULATION if self._estimationType == EstimationType.SIMULATION else _lib.L2NORM,
             max_iterations=self._maxIter, use_centroid=self._useCentroid, apply_aposteriori=self._applyAposteriori,
             device=self._device, sigma2apriori=self._sigma2apriori)

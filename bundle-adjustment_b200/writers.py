@@ -26,7 +26,7 @@ class BundleAdjustmentResultWriter:
     @staticmethod
     def _has_cofactor(adj):
         # exportDispersionMatrix = !(cofactor == null || cofactor.numRows() < u + d)
-        return adj.getInvertNormalEquation().name == 'FULL' and adj._session is not None
+        return adj.getInvertNormalEquation().name != 'NONE' and adj._session is not None
 
 
 def _point_indices(adj, first_index):

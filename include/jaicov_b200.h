@@ -57,8 +57,8 @@ extern "C" {
 /* BundleAdjustment.MatrixInversion (BundleAdjustment.java:65-70) */
 #define JAICOV_INVERT_NONE 0
 #define JAICOV_INVERT_FULL 1
-#define JAICOV_INVERT_PRE_ELIMINATION 2 /* not implemented yet: jaicov_estimate returns ILLEGAL_ARGUMENT */
-#define JAICOV_INVERT_REDUCED 3         /* not implemented yet */
+#define JAICOV_INVERT_PRE_ELIMINATION 2 /* BA:261-291, :1197-1453: needs jaicov_set_reduced_rows */
+#define JAICOV_INVERT_REDUCED 3         /* idem; what the reference's three example programs use (ExampleReport.java:89) */
 
 /* EstimationType (adjustment/EstimationType.java): only these two are accepted by the reference (:1132-1137) */
 #define JAICOV_L2NORM 0
@@ -176,6 +176,15 @@ int32_t jaicov_add_observed_group(jaicov_handle *h, int32_t r, const int32_t *ta
 /* result of detectRankDefect (:836-1042): free_flags in the order tx,ty,tz,rx,ry,rz,scale (1 = FREE);
  * n_unknowns = numberOfUnknownParameters (:80), n_observations = numberOfObservations (:81) */
 int32_t jaicov_set_datum(jaicov_handle *h, const int32_t free_flags[7], int32_t n_unknowns, int32_t n_observations);
+
+/* MatrixInversion.REDUCED / PRE_ELIMINATION: numRows of the reduced system = numberOfInteriorOrientations +
+ * numberOfDistortionParameters + 3 * objectCoordinates.size() + d (BundleAdjustment.java:262).  The library does not
+ * form the reference's Schur complement on the 6x6 EO blocks (:1225-1342): the reduced solution and the reduced
+ * cofactor matrix are the leading numRows block of the full ones, which the tensor-core path computes anyway, so both
+ * modes run the full path and expose rows/columns [0, numRows) of Qxx only (jaicov_get_qxx_packed then returns
+ * numRows(numRows+1)/2 doubles).  The exact dx of the EO parameters replaces the reference's final-pass leftovers
+ * (:273 applies the un-solved right-hand side as dx_EO; below the parity tolerance at convergence). */
+int32_t jaicov_set_reduced_rows(jaicov_handle *h, int32_t num_rows);
 
 /* ---- the adjustment ------------------------------------------------------------------------------------------------ */
 /* Runs the whole loop on the device and returns the EstimationStateType id. interrupt_flag (may be NULL) is

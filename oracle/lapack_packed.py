@@ -83,3 +83,21 @@ def inv_spd_packed(ap: np.ndarray, n: int) -> None:
         raise MatrixNotSPDException()
     if info.value < 0:
         raise ValueError('dpptri illegal argument')
+
+
+def inv_symm_packed(ap: np.ndarray, n: int) -> None:
+    """MathExtension.inv(UpperSymmPackMatrix), MathExtension.java:403-426: dsptrf + dsptri in place."""
+    nn, info = ctypes.c_int(n), ctypes.c_int(0)
+    ipiv = np.zeros(max(1, n), np.int32)
+    ipp = ipiv.ctypes.data_as(_c_int_p)
+    _dsptrf(b'U', ctypes.byref(nn), _p(ap), ipp, ctypes.byref(info))
+    if info.value > 0:
+        raise MatrixSingularException()
+    if info.value < 0:
+        raise ValueError('dsptrf illegal argument')
+    work = np.zeros(max(1, n))
+    _dsptri(b'U', ctypes.byref(nn), _p(ap), ipp, _p(work), ctypes.byref(info))
+    if info.value > 0:
+        raise MatrixSingularException()
+    if info.value < 0:
+        raise ValueError('dsptri illegal argument')

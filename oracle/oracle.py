@@ -201,7 +201,8 @@ def pidx(r, c):
 
 
 class Oracle:
-    """One adjustment, reference semantics. ``invert``: 'FULL' or 'NONE' (BundleAdjustment.java:65-70)."""
+    """One adjustment, reference semantics. ``invert``: 'FULL', 'NONE', 'REDUCED' or 'PRE_ELIMINATION'
+    (BundleAdjustment.MatrixInversion, BundleAdjustment.java:65-70)."""
 
     def __init__(self, scene, invert='FULL', max_iter=MAX_ITER, use_centroid=True, apply_aposteriori=True):
         self.bk = Bookkeeping(scene)
@@ -422,6 +423,70 @@ class Oracle:
                 vals[act] += dv
         return mx
 
+    # ---- reduceNormalEquationSystem / extractReducedParameters, BundleAdjustment.java:1197-1453 --------------------
+    def _reduction_sets(self):
+        """Per image (camera -> image order): active EO columns and the row set S = the camera's active IO + distortion
+        columns followed by the active X,Y,Z columns of every point seen in the image (:1205-1236, :1300-1311)."""
+        fp = self.fp
+        out = []
+        for img in range(fp.nImg):
+            cam = int(fp.cam_of_img[img])
+            E = [int(c) for c in fp.eo_col[6 * img:6 * img + 6] if _active(int(c))]
+            S = [int(c) for c in fp.io_col[3 * cam:3 * cam + 3] if _active(int(c))]
+            S += [int(c) for c in fp.coef_col[fp.coef_ptr[cam]:fp.coef_ptr[cam + 1]] if _active(int(c))]
+            pts = fp.obj_idx[int(fp.pt_ptr[img]):int(fp.pt_ptr[img + 1])]
+            pc = fp.pt_col.reshape(-1, 3)[pts].reshape(-1).astype(np.int64)
+            S += [int(c) for c in pc if _active(int(c))]
+            out.append((np.array(E, np.int64), np.array(S, np.int64)))
+        return out
+
+    def num_rows_reduced(self):
+        """numRows of the reduced system, :262 (3 * |objectCoordinates| even if some components are fixed)."""
+        return self.bk.n_io + self.bk.n_dist + 3 * int(self.bk.oc_order.size) + self.bk.d
+
+    def reduce_normal_equation_system(self, N, n):
+        """In place on packed N / n (:1225-1342).  The scalar loops of the reference are evaluated here with dense
+        gathers (same arithmetic, different summation order); writes with row > column are dropped like MTJ does."""
+        nn = self.fp.n
+        D = np.empty((nn, nn))
+        lib().orc_unpack(nn, N.ctypes.data, D.ctypes.data)
+        pre = self.invert == 'PRE_ELIMINATION'
+        for E, S in self._reduction_sets():
+            if E.size == 0:
+                continue
+            N22 = D[np.ix_(E, E)].copy()
+            n2 = n[E].copy()
+            if pre:
+                n[E] = 0.0                                             # :1256-1257
+            k = E.size
+            ap = _pack_upper(N22)
+            lp.inv_symm_packed(ap, k)                                  # MathExtension.inv(UpperSymmPackMatrix), :1259
+            N22i = _unpack_upper(ap, k)
+            if pre:                                                    # :1261-1298
+                D[np.ix_(E, E)] = N22i
+                n[E] += N22i @ n2
+            N1E = D[np.ix_(S, E)]                                      # N[rowN, EO] : never modified by this image
+            T = N1E @ N22i                                             # n12 of every row, :1318-1326
+            n[S] += -(T @ n2)                                          # :1329
+            upd = T @ N1E.T                                            # :1331-1340
+            D[np.ix_(S, S)] -= upd
+        iu = np.triu_indices(nn)
+        N[iu[0] + iu[1] * (iu[1] + 1) // 2] = D[iu]
+
+    def extract_reduced_parameters(self, N, n):
+        """dx2 = inv(N22) n2 - inv(N22) N21 dx1 (:1372-1453); N[EO,EO] holds inv(N22), n[EO] holds inv(N22) n2."""
+        nn = self.fp.n
+        D = np.empty((nn, nn))
+        lib().orc_unpack(nn, N.ctypes.data, D.ctypes.data)
+        for E, S in self._reduction_sets():
+            if E.size == 0:
+                continue
+            invN22 = D[np.ix_(E, E)]
+            dx2 = n[E].copy()
+            N1E = D[np.ix_(S, E)]
+            dx2 += -(invN22 @ (N1E.T @ n[S]))
+            n[E] = dx2
+
     # ---- estimateModel, BundleAdjustment.java:203-387 ---------------------------------------------
     def estimate(self):
         fp = self.fp
@@ -442,11 +507,20 @@ class Oracle:
             estimate_complete = is_estimated
             try:
                 if estimate_complete:
-                    lp.solve_symm_packed(N, nv, n, self.invert == 'FULL')
+                    if self.invert in ('REDUCED', 'PRE_ELIMINATION'):          # :261-267
+                        self.reduce_normal_equation_system(N, nv)
+                        lp.solve_symm_packed(N, nv, self.num_rows_reduced(), True)
+                    else:
+                        lp.solve_symm_packed(N, nv, n, self.invert == 'FULL')
                     L.orc_apply_precondition(n, V.ctypes.data, N.ctypes.data, nv.ctypes.data)
                     self.Qxx = N
                 else:
-                    lp.solve_symm_packed(N, nv, n, False)
+                    if self.invert == 'PRE_ELIMINATION':                       # :283-291
+                        self.reduce_normal_equation_system(N, nv)
+                        lp.solve_symm_packed(N, nv, self.num_rows_reduced(), False)
+                        self.extract_reduced_parameters(N, nv)
+                    else:
+                        lp.solve_symm_packed(N, nv, n, False)
                     L.orc_apply_precondition(n, V.ctypes.data, None, nv.ctypes.data)
             except (lp.MatrixSingularException, lp.MatrixNotSPDException, ValueError):
                 self.status = SINGULAR_MATRIX
@@ -475,6 +549,10 @@ class Oracle:
         self.status = ERROR_FREE_ESTIMATION if is_converge else NO_CONVERGENCE
         return self.status
 
+    def estimate_and_return_qxx(self):
+        self.estimate()
+        return self.qxx_dense()
+
     # ---- getters ------------------------------------------------------------------------------------
     def variance_factor_aposteriori(self):
         """getVarianceFactorAposteriori, BundleAdjustment.java:1090-1093."""
@@ -488,6 +566,22 @@ class Oracle:
         D = np.empty((n, n))
         lib().orc_unpack(n, self.Qxx.ctypes.data, D.ctypes.data)
         return D
+
+
+def _pack_upper(A):
+    k = A.shape[0]
+    iu = np.triu_indices(k)
+    ap = np.empty(k * (k + 1) // 2)
+    ap[iu[0] + iu[1] * (iu[1] + 1) // 2] = A[iu]
+    return ap
+
+
+def _unpack_upper(ap, k):
+    iu = np.triu_indices(k)
+    A = np.empty((k, k))
+    A[iu] = ap[iu[0] + iu[1] * (iu[1] + 1) // 2]
+    A.T[iu] = A[iu]
+    return A
 
 
 def _seq_add(acc, terms):

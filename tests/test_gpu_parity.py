@@ -140,11 +140,12 @@ def test_spd_solve_invert(built, n, nrhs):
     assert e.value.code == ba._lib.SINGULAR_MATRIX
 
 
-def compare_adjustment(scene, label, use_centroid=True):
+def compare_adjustment(scene, label, use_centroid=True, mode='FULL'):
     adj, pts = build_adjustment(scene)
     adj.useCentroidedCoordinates(use_centroid)
+    adj.setInvertNormalEquation(ba.MatrixInversion[mode])
     state = adj.estimateModel()
-    o = Oracle(scene, use_centroid=use_centroid)
+    o = Oracle(scene, use_centroid=use_centroid, invert=mode)
     st_o = o.estimate()
     assert state.getId() == st_o == 1
     st = adj.stats
@@ -156,13 +157,17 @@ def compare_adjustment(scene, label, use_centroid=True):
     s2g, s2o = adj.getVarianceFactorAposteriori(), o.variance_factor_aposteriori()
     assert abs(s2g - s2o) <= TOL_S2 * s2o
     assert abs(st.omega - o.omega) <= TOL_S2 * o.omega
-    # Qxx, correlation-scaled
+    # Qxx, correlation-scaled (REDUCED / PRE_ELIMINATION: only the leading numRows block is defined, BA:262)
     Qo = o.qxx_dense()
     Qg = adj.getCofactorMatrix().toDense()
     d = o.fp.d
+    nq = Qo.shape[0] if mode == 'FULL' else o.num_rows_reduced()
     sg = np.sqrt(np.abs(np.diag(Qo)))
     sg[:d] = 1.0
-    errq = (np.abs(Qg - Qo) / np.outer(sg, sg)).max()
+    errq = (np.abs(Qg - Qo)[:nq, :nq] / np.outer(sg, sg)[:nq, :nq]).max()
+    if mode != 'FULL':
+        # parameter floor below: cofactor standard deviations of ALL parameters, from the oracle's full inverse
+        Qo = Oracle(scene, use_centroid=use_centroid).estimate_and_return_qxx()
     # parameters: 1e-10 relative (floor: the parameter's own cofactor standard deviation, for values near zero)
     s2 = o.variance_factor_aposteriori()
     xyz_g, io_g, coef_g, eo_g = adj._session.values()
@@ -224,6 +229,16 @@ def test_adjustment_fixed_parameters_scale_bar_two_cameras(built):
         Oracle(sc).estimate()
     # ... and adjusts fine without centring
     compare_adjustment(sc, 'mixed', use_centroid=False)
+
+
+@pytest.mark.parametrize('mode', ['REDUCED', 'PRE_ELIMINATION'])
+def test_adjustment_example_reduced_modes(built, mode):
+    """SURVEY 8 row f-2.  MatrixInversion.REDUCED is what the reference's ExampleReport actually runs
+    (example/ExampleReport.java:89); the oracle restates the 6x6 EO pre-elimination (BA:1197-1453) including its
+    final-pass leftovers, the GPU path exposes the leading block of the full solution."""
+    adj, o = compare_adjustment(example_scene(), 'config 1 ' + mode, mode=mode)
+    assert adj.getCofactorMatrix().numRows() == 1153
+    assert adj._session.n_qxx == o.num_rows_reduced() == 463
 
 
 def test_modes_none_and_simulation(built):

@@ -87,3 +87,20 @@ def test_border_block_of_inverse_vanishes(example):
     _, o, _ = example
     Q = o.qxx_dense()
     assert np.abs(Q[:6, :6]).max() < 1e-12
+
+
+@pytest.mark.parametrize('mode', ['REDUCED', 'PRE_ELIMINATION'])
+def test_reduced_modes_agree_with_full(example, mode):
+    """BA:1197-1453 restated: the reduced system's cofactor matrix is the leading block of the full inverse, and the
+    parameters / sigma0^2 agree with the FULL run far inside the parity tolerances (ExampleReport itself uses REDUCED)."""
+    sc, full, _ = example
+    o = Oracle(example_scene(), invert=mode)
+    assert o.estimate() == 1 and len(o.history) == 4
+    nr = o.num_rows_reduced()
+    assert nr == 3 + 4 + 3 * 150 + 6                         # nIO + nDist + 3 |objectCoordinates| + d, BA:262
+    Qf, Qr = full.qxx_dense()[:nr, :nr], o.qxx_dense()[:nr, :nr]
+    sg = np.sqrt(np.abs(np.diag(Qf)))
+    sg[:6] = 1.0
+    assert (np.abs(Qr - Qf) / np.outer(sg, sg)).max() < 1e-9
+    assert abs(o.variance_factor_aposteriori() / full.variance_factor_aposteriori() - 1) < 1e-11
+    assert np.abs(o.fp.xyz - full.fp.xyz).max() < 1e-10 and np.abs(o.fp.eo_val - full.fp.eo_val).max() < 1e-10
