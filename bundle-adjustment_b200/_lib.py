@@ -126,7 +126,7 @@ class Session:
     ``flat`` is a dict of flat arrays in the layout of include/jaicov_b200.h (see ``set_problem``)."""
 
     def __init__(self, invert_mode=INVERT_FULL, estimation_type=L2NORM, max_iterations=5000, use_centroid=True,
-                 apply_aposteriori=True, device=0, sigma2apriori=1.0):
+                 apply_aposteriori=True, device=0, sigma2apriori=1.0, damping_value=0.0):
         self.L = load()
         self.opt = Options()
         self.L.jaicov_default_options(ctypes.byref(self.opt))
@@ -137,6 +137,7 @@ class Session:
         self.opt.apply_aposteriori = int(apply_aposteriori)
         self.opt.device = device
         self.opt.sigma2apriori = sigma2apriori
+        self.opt.damping_value = damping_value
         self.h = ctypes.c_void_p()
         rc = self.L.jaicov_create(ctypes.byref(self.opt), ctypes.byref(self.h))
         if rc != OK:

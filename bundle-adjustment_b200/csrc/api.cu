@@ -50,6 +50,8 @@ void launch_group_omega(int r, const int32_t *col, const double *var, const doub
                         const double *dxref, double *out, cudaStream_t s);
 void launch_unpack_scaled(const double *ap, int r, double scale, double *M, int64_t ld, int64_t np, cudaStream_t s);
 void launch_symmetrize(double *M, int64_t ld, int r, cudaStream_t s);
+void launch_damp_diag(double *M, int64_t ld, int u, double lambda, cudaStream_t s);
+void launch_scale_vector(double *x, int64_t n, double alpha, cudaStream_t s);
 void launch_identity_columns(double *X, int64_t ldx, int64_t np, const int32_t *ktab, int ntc, cudaStream_t s);
 void launch_qxx_epilogue_cols(double *X, int64_t ldx, int ntc, const int32_t *ktab, int u, const double *V, const double *H,
                               const double *G, int d, int64_t np, cudaStream_t s);
@@ -199,6 +201,9 @@ struct jaicov_handle {
     // complement on the EO blocks is not formed: its solution and cofactor matrix are the leading numRows block of the
     // full solution / inverse, which the tensor-core path computes anyway; only that block is exposed.
     int reduced_rows = -1;
+    // Levenberg-Marquardt state of estimateModel (BA:89, :93-97, :207-211)
+    double adapted_damping = 0.0, lm_omega = 0.0, last_valid_max_abs_dx = 0.0;
+    bool derive_first_damping = false;
     bool wants_inverse() const { return opt.invert_mode != JAICOV_INVERT_NONE; }
     int qxx_rows() const {
         const int n = P.u + P.d;
@@ -528,7 +533,30 @@ struct PassResult {
     double max_abs_dx = 0.0;
     bool bad = false;
     double omega = 0.0;
+    bool lm_step = false, lm_accepted = true;
+    double lm_last = 0.0;
 };
+
+// sum of the Omega parts of all observation groups for the dx currently in dxref (device -> host, synchronises)
+double omega_now(jaicov_handle *h, bool multi) {
+    const DevProblem &P = h->P;
+    cudaStream_t s = h->stream;
+    launch_omega(P, h->S, h->dxref.p, h->omega_parts.p, s);
+    if (multi) h->dist.allreduce_sum(h->omega_parts.p, 1, s);
+    if (P.nBar) launch_omega_bars(P, h->dxref.p, h->omega_parts.p + 1, s);
+    int gi = 0;
+    for (Group &g : h->groups) {
+        launch_group_omega(g.r, g.col.p, g.d_var.p, g.Pw.p, g.ldp, P.sigma2, g.w.p, h->dxref.p, h->omega_parts.p + 2 + gi, s);
+        gi++;
+    }
+    std::vector<double> om(2 + h->groups.size(), 0.0);
+    JCHECK(cudaMemcpyAsync(om.data(), h->omega_parts.p, om.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    JCHECK(cudaStreamSynchronize(s));
+    double t = om[0];
+    if (P.nBar) t += om[1];
+    for (size_t g = 0; g < h->groups.size(); g++) t += om[2 + g];
+    return t;
+}
 
 PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     const DevProblem &P = h->P;
@@ -537,6 +565,12 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     const bool invert = final_pass && h->wants_inverse();
     JCHECK(cudaEventRecord(h->ev[0], s));
     assemble(h);
+    // Levenberg-Marquardt: N_cc += lambda N_cc on every unknown column, before the preconditioner (BA:801-822)
+    if (h->derive_first_damping) {
+        h->adapted_damping = h->opt.damping_value;
+        h->derive_first_damping = false;
+    }
+    if (h->adapted_damping > 0) launch_damp_diag(h->M.p, P.np, P.u, h->adapted_damping, s);
     // preconditioner and SPD reformulation (K4)
     launch_precond_diag(h->M.p, P.np, P.u, P.np, h->V.p, s);
     launch_scale_system(h->M.p, P.np, P.u, h->V.p, h->Bt.p, P.d, P.np, s);
@@ -565,6 +599,30 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     // solve for n and the datum rows, datum correction, dx (K5/K9)
     launch_solve_rows8(h->M.p, P.np, h->Dinv.p, h->Rt.p, h->Rt.p + 8 * np, P.np, s);
     launch_datum_solve(h->Rt.p, h->Btv.p, P.d, P.np, P.u, h->V.p, h->dxref.p, h->H.p, h->Tq.p, h->small.p, s);
+    // Levenberg-Marquardt step control (updateModel, BA:390-426): shorten the step, compare Omega, accept or reject
+    PassResult r;
+    bool apply_dx = apply_update;
+    if (h->adapted_damping > 0) {
+        const double SQRT_EPS = std::sqrt(kEps);
+        const double alpha = std::min(0.25 * std::pow(h->adapted_damping, -0.05), 0.75);
+        launch_scale_vector(h->dxref.p, (int64_t)P.u + P.d, alpha, s);
+        double prev = h->lm_omega;
+        const double cur = omega_now(h, h->dist_on && h->dist.world > 1);
+        prev = prev <= 0 ? 1.7976931348623157e308 : prev;
+        const bool converge = prev >= cur;
+        h->lm_omega = cur;
+        r.lm_step = true;
+        r.lm_last = h->adapted_damping;
+        r.lm_accepted = converge;
+        if (converge) {
+            h->adapted_damping *= 0.2;
+        } else {
+            h->adapted_damping *= 5.0;
+            if (h->adapted_damping > 1.0 / SQRT_EPS) { h->adapted_damping = 1.0 / SQRT_EPS; h->lm_omega = 0.0; }
+            JCHECK(cudaMemsetAsync(h->dxref.p, 0, ((size_t)P.u + P.d) * sizeof(double), s));   // dx.zero(), BA:423
+            apply_dx = false;
+        }
+    }
     JCHECK(cudaEventRecord(h->ev[3], s));
     // inverse (K6/K7)
     if (invert && h->dist_on) {
@@ -583,7 +641,7 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     }
     JCHECK(cudaEventRecord(h->ev[4], s));
     // Omega at the pre-update point (K8), BA:429-430
-    const bool want_omega = final_pass && h->opt.estimation_type != JAICOV_SIMULATION;
+    const bool want_omega = final_pass && h->opt.estimation_type != JAICOV_SIMULATION && (!r.lm_step || r.lm_accepted);
     if (want_omega) {
         launch_omega(P, h->S, h->dxref.p, h->omega_parts.p, s);
         if (multi) h->dist.allreduce_sum(h->omega_parts.p, 1, s);
@@ -597,14 +655,13 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     JCHECK(cudaEventRecord(h->ev[5], s));
     // update + max|dx| (K9), BA:450-462
     JCHECK(cudaMemsetAsync(h->upd.p, 0, 2 * sizeof(unsigned long long), s));
-    launch_update(P.xyz, P.pt_col, 3 * (int64_t)P.nPt, h->dxref.p, apply_update, h->upd.p, s);
-    launch_update(P.io_val, P.io_col, 3 * (int64_t)P.nCam, h->dxref.p, apply_update, h->upd.p, s);
-    launch_update(P.coef_val, P.coef_col, P.nCoef, h->dxref.p, apply_update, h->upd.p, s);
-    launch_update(P.eo_val, P.eo_col, 6 * (int64_t)P.nImg, h->dxref.p, apply_update, h->upd.p, s);
+    launch_update(P.xyz, P.pt_col, 3 * (int64_t)P.nPt, h->dxref.p, apply_dx, h->upd.p, s);
+    launch_update(P.io_val, P.io_col, 3 * (int64_t)P.nCam, h->dxref.p, apply_dx, h->upd.p, s);
+    launch_update(P.coef_val, P.coef_col, P.nCoef, h->dxref.p, apply_dx, h->upd.p, s);
+    launch_update(P.eo_val, P.eo_col, 6 * (int64_t)P.nImg, h->dxref.p, apply_dx, h->upd.p, s);
     JCHECK(cudaEventRecord(h->ev[6], s));
     JCHECK(cudaGetLastError());
     // the one host read per pass: status word, max|dx|, Omega
-    PassResult r;
     unsigned long long upd[2];
     std::vector<double> om(2 + h->groups.size(), 0.0);
     double small99 = 0.0;
@@ -624,6 +681,8 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     }
     memcpy(&r.max_abs_dx, &upd[0], sizeof(double));
     r.bad = upd[1] != 0;
+    if (r.lm_step && !r.lm_accepted) r.max_abs_dx = h->last_valid_max_abs_dx;   // BA:420-425
+    else h->last_valid_max_abs_dx = r.max_abs_dx;                               // BA:433
     if (want_omega) {
         r.omega = om[0];
         if (P.nBar) r.omega += om[1];
@@ -713,7 +772,7 @@ int64_t jaicov_launch_count(void) { return (int64_t)g_launch_count; }
 int32_t jaicov_create(const jaicov_options *opt, jaicov_handle **out) {
     if (!opt || !out) return JAICOV_ILLEGAL_ARGUMENT;
     *out = nullptr;
-    if (opt->damping_value != 0.0) return JAICOV_ILLEGAL_ARGUMENT;
+    if (!(opt->damping_value >= 0.0)) return JAICOV_ILLEGAL_ARGUMENT;
     if (opt->invert_mode < JAICOV_INVERT_NONE || opt->invert_mode > JAICOV_INVERT_REDUCED) return JAICOV_ILLEGAL_ARGUMENT;
     if (opt->estimation_type != JAICOV_L2NORM && opt->estimation_type != JAICOV_SIMULATION) return JAICOV_ILLEGAL_ARGUMENT;
     jaicov_handle *h = new (std::nothrow) jaicov_handle();
@@ -909,6 +968,10 @@ int32_t jaicov_estimate(jaicov_handle *h, jaicov_progress_cb cb, void *user, vol
     int runs = maxIter - 1;                                  // BA:213
     bool isEstimated = false, complete = false, isConverge = true;
     if (maxIter == 0) complete = isEstimated = true;         // BA:216-219
+    h->derive_first_damping = h->opt.damping_value > 0;      // BA:207-208
+    h->adapted_damping = 0.0;
+    h->lm_omega = 0.0;
+    h->last_valid_max_abs_dx = 0.0;
     h->prepared = false;                                     // (re)upload the caller's values
     if (h->opt.use_centroid && !centroid_shift(h, false))
         return fail(h, JAICOV_ILLEGAL_ARGUMENT, "numbers of coordinate components are un-equal or zero (BA:151)");
@@ -926,11 +989,15 @@ int32_t jaicov_estimate(jaicov_handle *h, jaicov_progress_cb cb, void *user, vol
         PassResult r = run_pass(h, complete, true);
         h->stats.iterations++;
         if (r.info != 0) { status = JAICOV_SINGULAR_MATRIX; break; }                                        // BA:304-309
-        if (complete) { fire(JAICOV_STATE_ESTIMATE_STOCHASTIC_PARAMETERS, 0, 1); h->stats.omega = r.omega; }
+        if (r.lm_step) fire(JAICOV_STATE_LEVENBERG_MARQUARDT_STEP, r.lm_last, h->adapted_damping);       // BA:417-418
+        if (complete) {
+            fire(JAICOV_STATE_ESTIMATE_STOCHASTIC_PARAMETERS, 0, 1);
+            if (!r.lm_step || r.lm_accepted) { h->stats.omega = r.omega; h->lm_omega = r.omega; }
+        }
         h->stats.max_abs_dx = r.max_abs_dx;
         if (interrupt_flag && *interrupt_flag) { *interrupt_flag = 0; status = JAICOV_INTERRUPT; break; }   // BA:320-325
         if (r.bad || std::isnan(r.max_abs_dx) || std::isinf(r.max_abs_dx)) { status = JAICOV_SINGULAR_MATRIX; break; }  // BA:327-330
-        else if (r.max_abs_dx <= SQRT_EPS && runs > 0) {     // BA:332-337
+        else if (r.max_abs_dx <= SQRT_EPS && runs > 0 && h->adapted_damping == 0) {     // BA:332-337
             isEstimated = true;
             fire(JAICOV_STATE_CONVERGENCE, SQRT_EPS, r.max_abs_dx);
         } else if (runs-- <= 1) {                            // BA:338-345
@@ -939,6 +1006,7 @@ int32_t jaicov_estimate(jaicov_handle *h, jaicov_progress_cb cb, void *user, vol
         } else {
             fire(JAICOV_STATE_CONVERGENCE, SQRT_EPS, r.max_abs_dx);
         }
+        if (isEstimated || h->adapted_damping <= SQRT_EPS || runs < maxIter * 0.5 + 1) h->adapted_damping = 0.0;   // BA:352-353
     } while (!complete);
     download_values(h);
     if (status == JAICOV_OK) {

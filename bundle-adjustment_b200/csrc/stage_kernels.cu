@@ -364,6 +364,22 @@ void launch_get_block(const double *lower, int64_t ld, const double *border, int
     k_get_block<<<(unsigned)(blocks < 4736 ? blocks : 4736), 256, 0, s>>>(lower, ld, border, np, q11, d, r0, r1, c0, c1, out);
 }
 
+// Levenberg-Marquardt: N_cc += lambda * N_cc for every unknown column (BA:814-822)
+__global__ void k_damp_diag(double *__restrict__ M, int64_t ld, int u, double lambda) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < u) { const double v = M[e * ld + e]; M[e * ld + e] = v + lambda * v; }
+}
+void launch_damp_diag(double *M, int64_t ld, int u, double lambda, cudaStream_t s) {
+    if (u) { g_launch_count++; k_damp_diag<<<(u + 255) / 256, 256, 0, s>>>(M, ld, u, lambda); }
+}
+__global__ void k_scale_vector(double *__restrict__ x, int64_t n, double alpha) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] *= alpha;
+}
+void launch_scale_vector(double *x, int64_t n, double alpha, cudaStream_t s) {
+    if (n) { g_launch_count++; k_scale_vector<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, n, alpha); }
+}
+
 // ---- column-tile form of the inverse (multi-GPU: every rank holds np x 128*ntc) -----------------------------------
 __global__ void k_identity_columns(double *__restrict__ X, int64_t ldx, const int32_t *__restrict__ ktab, int ntc) {
     const int jl = blockIdx.x, i = threadIdx.x;

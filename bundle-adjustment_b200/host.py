@@ -807,8 +807,6 @@ class BundleAdjustment:
 
     # ---- estimateModel, :203-387 --------------------------------------------------------------------------------------
     def estimateModel(self):
-        if self._damping > 0:
-            raise NotImplementedError('Levenberg-Marquardt damping is not available in the B200 path yet')
         flat = self._prepare()
         # numRows of the reduced system, :262
         flat['reduced_rows'] = self._numIO + self._numDist + 3 * self._numObjectCoordinates + self._defect
@@ -819,7 +817,7 @@ class BundleAdjustment:
                          MatrixInversion.REDUCED: _lib.INVERT_REDUCED}[self._invert],
             estimation_type=_lib.SIMULATION if self._estimationType == EstimationType.SIMULATION else _lib.L2NORM,
             max_iterations=self._maxIter, use_centroid=self._useCentroid, apply_aposteriori=self._applyAposteriori,
-            device=self._device, sigma2apriori=self._sigma2apriori)
+            device=self._device, sigma2apriori=self._sigma2apriori, damping_value=self._damping)
         self._session.set_problem(flat)
         rc = self._session.estimate(progress=self._fire if self._listeners else None)
         self.stats = self._session.stats()

@@ -53,6 +53,7 @@ extern "C" {
 #define JAICOV_STATE_CONVERGENCE 102
 #define JAICOV_STATE_INVERT_NORMAL_EQUATION_MATRIX 103
 #define JAICOV_STATE_ESTIMATE_STOCHASTIC_PARAMETERS 104
+#define JAICOV_STATE_LEVENBERG_MARQUARDT_STEP 105 /* old = previous, new = adapted damping value (BA:417-418) */
 
 /* BundleAdjustment.MatrixInversion (BundleAdjustment.java:65-70) */
 #define JAICOV_INVERT_NONE 0
@@ -89,7 +90,7 @@ typedef struct {
     int32_t apply_aposteriori;  /* applyAposterioriVarianceOfUnitWeight, :1185 (default 1, :86) */
     int32_t device;             /* CUDA device ordinal this handle binds to */
     double sigma2apriori;       /* min(1, min variance) as accumulated by addObservationGroup, :637-643; <=0 -> 1 (:221) */
-    double damping_value;       /* Levenberg-Marquardt lambda, :1189; must be 0 (LM is a "next" row) */
+    double damping_value;       /* Levenberg-Marquardt lambda >= 0, setLevenbergMarquardtDampingValue :1189; 0 = plain Gauss-Newton (:96) */
 } jaicov_options;
 
 typedef struct {

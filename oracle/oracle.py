@@ -12,7 +12,7 @@ reference (JAICOV/example/example.htm: S0, IO values, IO standard deviations and
 coordinates) through the fixture tests/golden/example_scene.npz.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
-Levenberg-Marquardt damping (:801-822, :390-426) is not restated (dampingValue defaults to 0, :96).
+Levenberg-Marquardt damping (:801-822, :390-426) is restated as well (dampingValue defaults to 0, :96).
 """
 from __future__ import annotations
 
@@ -204,7 +204,7 @@ class Oracle:
     """One adjustment, reference semantics. ``invert``: 'FULL', 'NONE', 'REDUCED' or 'PRE_ELIMINATION'
     (BundleAdjustment.MatrixInversion, BundleAdjustment.java:65-70)."""
 
-    def __init__(self, scene, invert='FULL', max_iter=MAX_ITER, use_centroid=True, apply_aposteriori=True):
+    def __init__(self, scene, invert='FULL', max_iter=MAX_ITER, use_centroid=True, apply_aposteriori=True, damping=0.0):
         self.bk = Bookkeeping(scene)
         self.fp = FlatProblem(scene, self.bk)
         self.invert = invert
@@ -212,6 +212,11 @@ class Oracle:
         self.use_centroid = use_centroid
         self.apply_aposteriori = apply_aposteriori
         self.sigma2apriori = self.bk.sigma2apriori
+        self.damping_value = abs(damping)          # setLevenbergMarquardtDampingValue, BundleAdjustment.java:1189-1191
+        self.adapted_damping = 0.0
+        self.derive_first_damping = False
+        self.last_valid_max_abs_dx = 0.0
+        self.lm_steps = []                         # (lastAdaptedDampingValue, adaptedDampingValue, accepted)
         self.centroid = np.zeros(3)
         self.omega = 0.0
         self.max_abs_dx = 0.0
@@ -394,6 +399,13 @@ class Oracle:
         for k in range(fp.d):                                       # N.set(row, column, value), row < column
             nz = np.nonzero(B[k])[0]
             N[k + nz * (nz + 1) // 2] = B[k, nz]
+        if self.derive_first_damping:                               # :801-812
+            self.adapted_damping = self.damping_value
+            self.derive_first_damping = False
+        if self.adapted_damping > 0:                                # :814-822: N_cc += lambda * N_cc for every unknown column
+            c = np.arange(fp.d, n, dtype=np.int64)
+            dg = c + c * (c + 1) // 2
+            N[dg] = N[dg] + self.adapted_damping * N[dg]
         V = np.empty(n)
         L.orc_preconditioner(n, N.ctypes.data, V.ctypes.data, EPS)
         return N, nv, V
@@ -487,6 +499,34 @@ class Oracle:
             dx2 += -(invN22 @ (N1E.T @ n[S]))
             n[E] = dx2
 
+    # ---- updateModel, BundleAdjustment.java:389-442 (incl. the Levenberg-Marquardt step control) -------------------
+    def _update_model(self, dx, update_complete):
+        if self.adapted_damping > 0:
+            alpha = min(0.25 * self.adapted_damping ** -0.05, 0.75)
+            dx *= alpha
+            prev = self.omega
+            cur = self.get_omega(dx)
+            prev = float('inf') if prev <= 0 else prev
+            converge = prev >= cur
+            self.omega = cur
+            last = self.adapted_damping
+            if converge:
+                self.adapted_damping *= 0.2
+            else:
+                self.adapted_damping *= 5.0
+                if self.adapted_damping > 1.0 / SQRT_EPS:
+                    self.adapted_damping = 1.0 / SQRT_EPS
+                    self.omega = 0.0
+            self.lm_steps.append((last, self.adapted_damping, bool(converge)))
+            if not converge:
+                self.max_abs_dx = self.last_valid_max_abs_dx
+                dx[:] = 0.0
+                return
+        if update_complete:
+            self.omega = self.get_omega(dx)                        # :429-430
+        self.max_abs_dx = self.update_unknowns(dx)                 # :432
+        self.last_valid_max_abs_dx = self.max_abs_dx
+
     # ---- estimateModel, BundleAdjustment.java:203-387 ---------------------------------------------
     def estimate(self):
         fp = self.fp
@@ -494,6 +534,9 @@ class Oracle:
         runs = self.max_iter - 1
         is_estimated = estimate_complete = False
         is_converge = True
+        self.derive_first_damping = self.damping_value > 0         # :207-208
+        self.adapted_damping = 0.0
+        self.last_valid_max_abs_dx = 0.0
         if self.max_iter == 0:
             estimate_complete = is_estimated = True
         if self.use_centroid:
@@ -526,14 +569,12 @@ class Oracle:
                 self.status = SINGULAR_MATRIX
                 return self.status
             dx = nv
-            if estimate_complete:
-                self.omega = self.get_omega(dx)                    # :429-430
-            self.max_abs_dx = self.update_unknowns(dx)             # :432
+            self._update_model(dx, estimate_complete)              # :317, :389-442
             self.history.append(self.max_abs_dx)
             if math.isinf(self.max_abs_dx) or math.isnan(self.max_abs_dx):
                 self.status = SINGULAR_MATRIX
                 return self.status
-            elif self.max_abs_dx <= SQRT_EPS and runs > 0:
+            elif self.max_abs_dx <= SQRT_EPS and runs > 0 and self.adapted_damping == 0:
                 is_estimated = True
             else:
                 r = runs
@@ -542,6 +583,8 @@ class Oracle:
                     if estimate_complete:
                         is_converge = False
                     is_estimated = True
+            if is_estimated or self.adapted_damping <= SQRT_EPS or runs < self.max_iter * 0.5 + 1:   # :352-353
+                self.adapted_damping = 0.0
             if estimate_complete:
                 break
         if self.use_centroid:

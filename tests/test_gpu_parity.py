@@ -140,12 +140,16 @@ def test_spd_solve_invert(built, n, nrhs):
     assert e.value.code == ba._lib.SINGULAR_MATRIX
 
 
-def compare_adjustment(scene, label, use_centroid=True, mode='FULL'):
+def compare_adjustment(scene, label, use_centroid=True, mode='FULL', damping=0.0):
     adj, pts = build_adjustment(scene)
     adj.useCentroidedCoordinates(use_centroid)
     adj.setInvertNormalEquation(ba.MatrixInversion[mode])
+    adj.setLevenbergMarquardtDampingValue(damping)
+    lm_events = []
+    if damping:
+        adj.addPropertyChangeListener(lambda st, old, new: lm_events.append((old, new)) if st == 105 else None)
     state = adj.estimateModel()
-    o = Oracle(scene, use_centroid=use_centroid, invert=mode)
+    o = Oracle(scene, use_centroid=use_centroid, invert=mode, damping=damping)
     st_o = o.estimate()
     assert state.getId() == st_o == 1
     st = adj.stats
@@ -183,6 +187,11 @@ def compare_adjustment(scene, label, use_centroid=True, mode='FULL'):
           % (label, st.iterations, st.max_abs_dx, abs(s2g - s2o) / s2o, errq, errx))
     assert errq <= TOL_Q
     assert errx <= TOL_X
+    if damping:
+        # every Levenberg-Marquardt step: same damping sequence, same accept/reject decisions (BA:390-426)
+        assert len(lm_events) == len(o.lm_steps)
+        for (old, new), (olast, onew, _acc) in zip(lm_events, o.lm_steps):
+            assert old == olast and new == onew
     return adj, o
 
 
@@ -239,6 +248,13 @@ def test_adjustment_example_reduced_modes(built, mode):
     adj, o = compare_adjustment(example_scene(), 'config 1 ' + mode, mode=mode)
     assert adj.getCofactorMatrix().numRows() == 1153
     assert adj._session.n_qxx == o.num_rows_reduced() == 463
+
+
+@pytest.mark.parametrize('damping', [1e-3, 1.0, 100.0])
+def test_adjustment_levenberg_marquardt(built, damping):
+    """Levenberg-Marquardt damping N_cc *= (1 + lambda) (BA:801-822) with the step control of
+    updateModel (BA:390-426): shortened step, Omega comparison, lambda x0.2 / x5."""
+    compare_adjustment(synthetic_scene(2, images=12, targets=80)[0], 'LM lambda=%g' % damping, damping=damping)
 
 
 def test_modes_none_and_simulation(built):

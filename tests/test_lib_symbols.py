@@ -40,8 +40,11 @@ def test_option_validation(built):
     opt.invert_mode = 7                                 # unknown mode -> refused
     assert L.jaicov_create(ctypes.byref(opt), ctypes.byref(h)) == ba._lib.ILLEGAL_ARGUMENT
     opt.invert_mode = ba._lib.INVERT_FULL
-    opt.damping_value = 0.1                             # Levenberg-Marquardt not built yet -> refused, never ignored
+    opt.damping_value = -0.1                            # negative damping -> refused
     assert L.jaicov_create(ctypes.byref(opt), ctypes.byref(h)) == ba._lib.ILLEGAL_ARGUMENT
+    opt.damping_value = 0.1
+    assert L.jaicov_create(ctypes.byref(opt), ctypes.byref(h)) == 0
+    L.jaicov_destroy(h)
 
 
 @pytest.mark.skipif(ba._lib.load().jaicov_device_count() > 0, reason='only meaningful without a GPU')
