@@ -64,19 +64,29 @@ __device__ __forceinline__ void load_slab(double *s, const double *g, int64_t ld
 // BM = rows of C per CTA (128, 64 or 32; the columns are always 128).  Small BM spreads a 128 x 128 tile over 2 or
 // 4 SMs: a single tile with K = 128 is bound by ONE SM's DMMA rate (~17 us), which is what the many small launches
 // of the recursion's deep levels pay; the host picks BM from the number of tiles of the launch.
-// CTA shapes.  BMT = 129: the 128-row tile with 8 warps (2 x 4, warp tile 64 x 32) -- the default; BMT = 128: the same tile
+// CTA shapes.  BMT = 129: the 128-row tile with 8 warps (2 x 4, warp tile 64 x 32); BMT = 128: the same tile
 // with 16 warps (4 x 4, warp tile 32 x 32), tried because "wait" (fixed DMMA issue latency) was the top stall reason with two
 // warps per scheduler, but measured slower (more LDS per DMMA); 64- and 32-row tiles use 8 warps.
+// BMT = 65: 64-row tile, 4 warps (2 x 2, warp tile 32 x 64), 3 stages, TWO CTAs per SM: independent CTAs hide each other's
+// barrier and prologue/epilogue bubbles (the shape class cuBLAS's own d884 kernel uses, 64 x 128 x 16 x 3).  Default for
+// every launch of >= 148 tiles: 96 % of the measured cuBLAS DGEMM rate over a whole config-5 factor + inverse (8 warps: 88 %).
 template <int BMT> struct GemmShape {
-    static constexpr int ROWS = (BMT == 129) ? 128 : BMT;
-    static constexpr int WARPS_M = (BMT == 128) ? 4 : ((BMT == 129 || BMT == 64) ? 2 : 1);
-    static constexpr int WARPS_N = (BMT == 128) ? 4 : ((BMT == 129 || BMT == 64) ? 4 : 8);
+    static constexpr int ROWS = (BMT == 129) ? 128 : (BMT == 65 ? 64 : BMT);
+    static constexpr int WARPS_M = (BMT == 128) ? 4 : ((BMT == 129 || BMT == 64 || BMT == 65) ? 2 : 1);
+    static constexpr int WARPS_N = (BMT == 128) ? 4 : ((BMT == 129 || BMT == 64) ? 4 : (BMT == 65 ? 2 : 8));
     static constexpr int THREADS = 32 * WARPS_M * WARPS_N;
+    static constexpr int STAGES = (BMT == 65) ? 3 : GSTAGES;
+    static constexpr int CTAS_PER_SM = (BMT == 65) ? 2 : 1;
+    static constexpr int A_SLAB = (BMT == 65) ? 64 * PITCH_K : SLAB;      // doubles per A slab
+    static constexpr size_t SMEM = (size_t)STAGES * (A_SLAB + SLAB) * sizeof(double);
 };
 
 template <int AL, int BL, int BMT>
-__global__ void __launch_bounds__(GemmShape<BMT>::THREADS, 1) k_gemm(GemmDesc g) {
+__global__ void __launch_bounds__(GemmShape<BMT>::THREADS, GemmShape<BMT>::CTAS_PER_SM) k_gemm(GemmDesc g) {
     constexpr int BM = GemmShape<BMT>::ROWS;
+    constexpr int NSTAGES = GemmShape<BMT>::STAGES;
+    constexpr int ASLAB = GemmShape<BMT>::A_SLAB;
+    constexpr int STAGE = ASLAB + SLAB;       // doubles per pipeline stage: A slab then B slab
     constexpr int WARPS_M = GemmShape<BMT>::WARPS_M;
     constexpr int WARPS_N = GemmShape<BMT>::WARPS_N;
     constexpr int NTHREADS = GemmShape<BMT>::THREADS;
@@ -134,28 +144,28 @@ __global__ void __launch_bounds__(GemmShape<BMT>::THREADS, 1) k_gemm(GemmDesc g)
 
     // ---- pipeline prologue ---------------------------------------------------------------------------------------
 #pragma unroll
-    for (int s = 0; s < GSTAGES - 1; s++) {
+    for (int s = 0; s < NSTAGES - 1; s++) {
         if (s < nk) {
-            load_slab<AL, BM, NTHREADS>(gsm + (size_t)(2 * s) * SLAB, Ag + s * a_step, g.lda, tid);
-            load_slab<BL, 128, NTHREADS>(gsm + (size_t)(2 * s + 1) * SLAB, Bg + s * b_step, g.ldb, tid);
+            load_slab<AL, BM, NTHREADS>(gsm + (size_t)s * STAGE, Ag + s * a_step, g.lda, tid);
+            load_slab<BL, 128, NTHREADS>(gsm + (size_t)s * STAGE + ASLAB, Bg + s * b_step, g.ldb, tid);
         }
         cp_async_commit();
     }
 
     for (int kt = 0; kt < nk; kt++) {
-        cp_async_wait<GSTAGES - 2>();
+        cp_async_wait<NSTAGES - 2>();
         __syncthreads();
         {   // prefetch slab kt + STAGES - 1 into the buffer consumed at iteration kt - 1
-            const int kn = kt + GSTAGES - 1;
+            const int kn = kt + NSTAGES - 1;
             if (kn < nk) {
-                const int sb = kn % GSTAGES;
-                load_slab<AL, BM, NTHREADS>(gsm + (size_t)(2 * sb) * SLAB, Ag + kn * a_step, g.lda, tid);
-                load_slab<BL, 128, NTHREADS>(gsm + (size_t)(2 * sb + 1) * SLAB, Bg + kn * b_step, g.ldb, tid);
+                const int sb = kn % NSTAGES;
+                load_slab<AL, BM, NTHREADS>(gsm + (size_t)sb * STAGE, Ag + kn * a_step, g.lda, tid);
+                load_slab<BL, 128, NTHREADS>(gsm + (size_t)sb * STAGE + ASLAB, Bg + kn * b_step, g.ldb, tid);
             }
             cp_async_commit();
         }
-        const double *As = gsm + (size_t)(2 * (kt % GSTAGES)) * SLAB;
-        const double *Bs = As + SLAB;
+        const double *As = gsm + (size_t)(kt % NSTAGES) * STAGE;
+        const double *Bs = As + ASLAB;
 #pragma unroll
         for (int kk = 0; kk < GK / 4; kk++) {
             double a[MI], b[NJ];
@@ -202,13 +212,14 @@ static void launch_gemm_t(const GemmDesc &g, int64_t tiles, cudaStream_t s) {
     constexpr int BM = GemmShape<BMT>::ROWS;
     static bool attr = false;
     if (!attr) {
-        JCHECK(cudaFuncSetAttribute(k_gemm<AL, BL, BMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+        JCHECK(cudaFuncSetAttribute(k_gemm<AL, BL, BMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmShape<BMT>::SMEM));
         attr = true;
     }
     g_launch_count++;
     constexpr int NT = GemmShape<BMT>::THREADS;
-    if (g.coltab) k_gemm<AL, BL, BMT><<<dim3((unsigned)(g.mt * (128 / BM)), (unsigned)g.ncoltab), NT, GEMM_SMEM, s>>>(g);
-    else k_gemm<AL, BL, BMT><<<(unsigned)(tiles * (128 / BM)), NT, GEMM_SMEM, s>>>(g);
+    constexpr size_t SM = GemmShape<BMT>::SMEM;
+    if (g.coltab) k_gemm<AL, BL, BMT><<<dim3((unsigned)(g.mt * (128 / BM)), (unsigned)g.ncoltab), NT, SM, s>>>(g);
+    else k_gemm<AL, BL, BMT><<<(unsigned)(tiles * (128 / BM)), NT, SM, s>>>(g);
 }
 
 template <int AL, int BL>
@@ -218,12 +229,15 @@ static void launch_gemm_l(const GemmDesc &g, cudaStream_t s) {
     // a CTA owns BM full-width rows of C; when C aliases the B operand (left-side base cases) the whole 128 x 128
     // tile must stay with one CTA
     const bool alias_b = (const double *)g.C == g.B;
-    // A/B measured on B200 (config 5, one final pass): 8 warps 8.06 s, 16 warps 8.31 s -> 8 warps (2 x 4, warp tile 64 x 32)
-    // is the default; JAICOV_GEMM_WARPS=16 selects the 4 x 4 shape
-    static const bool warps16 = [] { const char *e = getenv("JAICOV_GEMM_WARPS"); return e && atoi(e) == 16; }();
-    if (alias_b || tiles >= 148) {
-        if (warps16) launch_gemm_t<AL, BL, 128>(g, tiles, s);
-        else launch_gemm_t<AL, BL, 129>(g, tiles, s);
+    // A/B measured on B200 (config 5, one final pass; profiles/r01_gemm_shape_ab.txt): 4 warps x 2 CTAs per SM 7.39 s,
+    // 8 warps 8.05 s, 16 warps 8.31 s -> the 64 x 128 / 4-warp shape is the default for launches that fill the machine
+    // twice over; JAICOV_GEMM_WARPS=8 or 16 select the one-CTA-per-SM shapes
+    static const int shape = [] { const char *e = getenv("JAICOV_GEMM_WARPS"); return e ? atoi(e) : 4; }();
+    if (alias_b) launch_gemm_t<AL, BL, 129>(g, tiles, s);
+    else if (tiles >= 148) {
+        if (shape == 16) launch_gemm_t<AL, BL, 128>(g, tiles, s);
+        else if (shape == 8) launch_gemm_t<AL, BL, 129>(g, tiles, s);
+        else launch_gemm_t<AL, BL, 65>(g, tiles, s);      // 64 x 128 tiles, 2 CTAs per SM
     }
     else if (tiles >= 74) launch_gemm_t<AL, BL, 64>(g, tiles, s);
     else launch_gemm_t<AL, BL, 32>(g, tiles, s);
