@@ -45,6 +45,18 @@ def workload_name(config, flat, adj):
             % (config - 1, len(flat['cam_of_img']), flat['xyz'].size // 3, flat['obj_idx'].size, n)), n
 
 
+def structured_flops(flat):
+    """GEMM flop of one final pass of the structured route: with Tp = padded object-coordinate columns and
+    mp = padded (camera + image unknowns + datum rows): K' = K0 - Z'Y (mp^2 Tp), Q'Y' (2 mp^2 Tp), Y(Q'Y') lower (Tp^2 mp),
+    Cholesky + inverse of the reduced system (nc^3)."""
+    pc = np.asarray(flat['pt_col']).astype(np.int64)
+    up = int(((pc >= 0) & (pc < 2147483647)).sum())
+    u, d = int(flat['n_unknowns']), int(np.sum(flat['free_flags']))
+    nc = u - up
+    Tp, mp = (up + 127) // 128 * 128, (nc + d + 127) // 128 * 128
+    return float(mp) ** 2 * Tp * 3 + float(Tp) ** 2 * mp + float(nc) ** 3
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
@@ -173,6 +185,10 @@ def main():
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--solver', choices=('dense', 'structured', 'auto'), default='dense',
+                    help='route of the headline line: dense = the blocked Cholesky + full inverse the metric names (default); '
+                         'the structured (point-block) route is timed next to it and reported under "structured"')
+    ap.add_argument('--no-structured', action='store_true')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -201,8 +217,10 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         nccl_id = ids[0]
 
-    def new_session():
-        s_ = ba.Session(sigma2apriori=sigma2, device=local_rank)
+    SOLVER = {'dense': ba._lib.SOLVER_DENSE, 'structured': ba._lib.SOLVER_STRUCTURED, 'auto': ba._lib.SOLVER_AUTO}
+
+    def new_session(solver=None):
+        s_ = ba.Session(sigma2apriori=sigma2, device=local_rank, solver=SOLVER[solver or args.solver])
         if world > 1:
             s_.dist_init(rank, world, nccl_id)
         return s_
@@ -236,6 +254,7 @@ def main():
     wall = time.perf_counter() - t0
     launches = (L.jaicov_launch_count() - launches0) // args.steps
     clocks = sampler.finish() if rank == 0 else None
+    structured_used = sess.stats().solver_used == ba._lib.SOLVER_STRUCTURED
     # max over ranks of the device time
     t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -244,6 +263,34 @@ def main():
     ms_per_step = dev_ms_max / args.steps
     value = args.steps / (dev_ms_max * 1e-3)          # one adjustment over all ranks: whole-job iterations/s
     stage /= args.steps
+
+    # ---- the structured (point-block) route on the same workload, reported next to the headline ----------------------------
+    structured = None
+    if world == 1 and not structured_used and not args.no_structured and os.environ.get('JAICOV_SOLVER') is None:
+        sess.close()
+        try:
+            sess = new_session('structured')
+            sess.set_problem(flat)
+            for _ in range(args.warmup):
+                assert sess.iterate(final_pass=True, apply_update=False) == 0
+            torch.cuda.synchronize()
+            sdev, sstage = 0.0, np.zeros(5)
+            for _ in range(args.steps):
+                assert sess.iterate(final_pass=True, apply_update=False) == 0
+                st = sess.stats()
+                sdev += st.ms_total
+                sstage += [st.ms_assembly, st.ms_factor, st.ms_solve, st.ms_inverse, st.ms_omega]
+            torch.cuda.synchronize()
+            sstage /= args.steps
+            sfl = structured_flops(flat)
+            structured = {'ms_per_step': sdev / args.steps, 'value': args.steps / (sdev * 1e-3), 'unit': UNIT,
+                          'stage_ms': dict(zip(('assembly+precondition', 'reduced system + its inverse', 'solution', 'Qxx products + placement',
+                                                'omega'), sstage.tolist())),
+                          'gemm_flop': sfl, 'tflops': sfl / ((sstage[1] + sstage[3]) * 1e-3) / 1e12,
+                          'note': 'same inputs and outputs (dx, complete Qxx) as the headline; JAICOV_SOLVER_AUTO picks this route when no '
+                                  'observation couples two object points'}
+        except ba.JaicovError as e:
+            structured = {'unavailable': str(e)}
 
     # ---- end to end through the C ABI with host buffers -----------------------------------------------------------------
     e2e = None
@@ -298,22 +345,24 @@ def main():
         return
     # ---- roofline of the dominant stage: factor + inverse on FP64 tensor-core GEMM tiles --------------------------------
     peak = fp64_peak_tflops(torch)
-    flops = float(n) ** 3                            # n^3/3 (factor) + 2n^3/3 (inverse), SURVEY.md 8(d)
+    flops = structured_flops(flat) if structured_used else float(n) ** 3   # n^3/3 (factor) + 2n^3/3 (inverse), SURVEY.md 8(d)
     t_dense = (stage[1] + stage[3]) * 1e-3
     achieved = flops / t_dense / 1e12
     peaks_file = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     hbm = json.load(open(peaks_file)).get('hbm_gbs') if os.path.exists(peaks_file) else 6650.0
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak * world, 'unit': 'TFLOP/s', 'frac': achieved / (peak * world),
                 'traffic': None, 'peak_per_gpu': peak,
-                'kernel': 'k_gemm<AL,BL> (FP64 DMMA 128x128 tiles); numerator n^3 flop per step, denominator device time of the '
-                          'factor + inverse stages (includes the diagonal-block kernels and copies between GEMM launches)',
+                'kernel': 'k_gemm<AL,BL> (FP64 DMMA 128x128 tiles); numerator %s flop per step, denominator device time of the '
+                          'factor + inverse stages (includes the diagonal-block kernels and copies between GEMM launches)'
+                          % ('the structured route\'s GEMM' if structured_used else 'n^3'),
                 'peak_source': 'cuBLAS DGEMM 8192^3 via torch.matmul(float64) measured in this run (burst, best of 5); '
                                'MEASURED_PEAKS.json has no FP64 entry',
                 'assembly_gbs': (flat['obj_idx'].size * 44.0) / (stage[0] * 1e-3) / 1e9, 'hbm_peak_gbs': hbm}
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak' if world == 1 else 'strong', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': name, 'l2': 'inputs larger than L2: the %d x %d FP64 system (%.2f GB) is rewritten every step'
+            'config': {'workload': name, 'solver': 'structured (point-block)' if structured_used else 'dense (blocked Cholesky + full inverse)',
+                       'l2': 'inputs larger than L2: the %d x %d FP64 system (%.2f GB) is rewritten every step'
                        % (n, n, n * n * 8 / 1e9),
                        'parallelism': 'single GPU' if world == 1 else ('one adjustment over %d GPUs: image-sharded assembly + NCCL all-reduce, block-column-cyclic '
                                                                        'Cholesky (panel broadcasts), per-rank column-tile inverse' % world),
@@ -324,6 +373,10 @@ def main():
             'roofline': roofline, 'clocks': clocks, 'gpu_launches': int(launches)}
     if e2e:
         line['e2e'] = e2e
+    if structured:
+        if 'tflops' in structured:
+            structured['frac_of_fp64_peak'] = structured['tflops'] / peak
+        line['structured'] = structured
     if not args.no_cpu_baseline and world == 1:
         line['cpu_baseline'] = cpu_sample(args.config, n, flat['obj_idx'].size, 1)
     print(json.dumps(line))

@@ -17,6 +17,7 @@ OK, ERROR_FREE_ESTIMATION, INTERRUPT, SINGULAR_MATRIX, NO_CONVERGENCE = 0, 1, -1
 NOT_INITIALISED, OUT_OF_MEMORY, ILLEGAL_ARGUMENT = -5, -7, -100
 INVERT_NONE, INVERT_FULL, INVERT_PRE_ELIMINATION, INVERT_REDUCED = 0, 1, 2, 3
 L2NORM, SIMULATION = 0, 1
+SOLVER_AUTO, SOLVER_DENSE, SOLVER_STRUCTURED = 0, 1, 2
 COL_UNSET, COL_FIXED = -1, 2147483647
 
 EXPORTS = [
@@ -33,13 +34,14 @@ EXPORTS = [
 class Options(ctypes.Structure):
     _fields_ = [('invert_mode', ctypes.c_int32), ('estimation_type', ctypes.c_int32), ('max_iterations', ctypes.c_int32),
                 ('use_centroid', ctypes.c_int32), ('apply_aposteriori', ctypes.c_int32), ('device', ctypes.c_int32),
+                ('solver', ctypes.c_int32), ('reserved0', ctypes.c_int32),
                 ('sigma2apriori', ctypes.c_double), ('damping_value', ctypes.c_double)]
 
 
 class Stats(ctypes.Structure):
     _fields_ = [('status', ctypes.c_int32), ('iterations', ctypes.c_int32), ('iteration_step', ctypes.c_int32),
                 ('n_unknowns', ctypes.c_int32), ('n_datum', ctypes.c_int32), ('n_observations', ctypes.c_int32),
-                ('dof', ctypes.c_int32), ('reserved', ctypes.c_int32),
+                ('dof', ctypes.c_int32), ('solver_used', ctypes.c_int32),
                 ('omega', ctypes.c_double), ('max_abs_dx', ctypes.c_double), ('sigma2apriori', ctypes.c_double),
                 ('sigma2aposteriori', ctypes.c_double),
                 ('ms_assembly', ctypes.c_double), ('ms_factor', ctypes.c_double), ('ms_solve', ctypes.c_double),
@@ -126,7 +128,7 @@ class Session:
     ``flat`` is a dict of flat arrays in the layout of include/jaicov_b200.h (see ``set_problem``)."""
 
     def __init__(self, invert_mode=INVERT_FULL, estimation_type=L2NORM, max_iterations=5000, use_centroid=True,
-                 apply_aposteriori=True, device=0, sigma2apriori=1.0, damping_value=0.0):
+                 apply_aposteriori=True, device=0, sigma2apriori=1.0, damping_value=0.0, solver=SOLVER_AUTO):
         self.L = load()
         self.opt = Options()
         self.L.jaicov_default_options(ctypes.byref(self.opt))
@@ -136,6 +138,7 @@ class Session:
         self.opt.use_centroid = int(use_centroid)
         self.opt.apply_aposteriori = int(apply_aposteriori)
         self.opt.device = device
+        self.opt.solver = solver
         self.opt.sigma2apriori = sigma2apriori
         self.opt.damping_value = damping_value
         self.h = ctypes.c_void_p()

@@ -204,6 +204,14 @@ struct jaicov_handle {
     // Levenberg-Marquardt state of estimateModel (BA:89, :93-97, :207-211)
     double adapted_damping = 0.0, lm_omega = 0.0, last_valid_max_abs_dx = 0.0;
     bool derive_first_damping = false;
+    // structured route (structured.cu): block-diagonal object-point block, reduced camera system
+    struct Structured {
+        bool on = false;
+        StructDims D{};
+        int nBlk = 0;
+        DevBuf<int32_t> blk_start, blk_size, col_blk;
+        DevBuf<double> Pinv, Zt, Yt, T1t, Kp, Sm, Wm, Dinv, Eb, ED, Fb, zp, rp, yr, ys;
+    } st;
     bool wants_inverse() const { return opt.invert_mode != JAICOV_INVERT_NONE; }
     int qxx_rows() const {
         const int n = P.u + P.d;
@@ -262,6 +270,93 @@ void zernike_terms(int order, int &m, std::vector<int32_t> &p, std::vector<doubl
         p.push_back(n - 2 * k);
         c.push_back(length * (double)(((k % 2 == 0) ? 1 : -1) * binomial(n - k, k) * binomial(n - 2 * k, halfnm - k)));
     }
+}
+
+// Decides whether the structured route applies and builds its tables.  It needs the object coordinates to be the
+// leading columns (true whenever no coordinate gets its column late through a scale bar or an observed group,
+// BA:724-771), every point's unknown components in consecutive columns, and no observation that couples two
+// points (scale bars PDF:210-283, observed groups with point targets PDF:447-473) -- then N[p, p] is block diagonal.
+void select_solver(jaicov_handle *h) {
+    jaicov_handle::Structured &st = h->st;
+    st.on = false;
+    int want = h->opt.solver;
+    if (const char *e = getenv("JAICOV_SOLVER")) {
+        if (!strcmp(e, "dense")) want = JAICOV_SOLVER_DENSE;
+        else if (!strcmp(e, "structured")) want = JAICOV_SOLVER_STRUCTURED;
+    }
+    const char *why = nullptr;
+    const DevProblem &P = h->P;
+    const int d = P.d;
+    std::vector<int32_t> blk_start, blk_size, col_blk;
+    int up = 0;
+    if (want == JAICOV_SOLVER_DENSE) why = "dense route requested";
+    else if (h->dist_on) why = "multi-GPU handles use the distributed dense route";
+    else if (!h->bar_a.empty()) why = "scale bars couple object points";
+    if (!why)
+        for (const Group &g : h->groups)
+            for (int k : g.kind)
+                if (k == 0) { why = "a directly observed group targets object coordinates"; break; }
+    if (!why) {
+        const size_t nPt = h->pt_col.size() / 3;
+        int64_t cnt = 0, mx = -1;
+        std::vector<std::pair<int32_t, int32_t>> blocks;   // (start, size)
+        for (size_t p = 0; p < nPt && !why; p++) {
+            int32_t first = -1, prev = -1, sz = 0;
+            for (int c = 0; c < 3; c++) {
+                const int32_t col = h->pt_col[3 * p + c];
+                if (!active(col)) continue;
+                const int32_t e = col - d;
+                if (first < 0) first = e;
+                else if (e != prev + 1) why = "components of an object point are not in consecutive columns";
+                prev = e;
+                sz++;
+                cnt++;
+                mx = std::max<int64_t>(mx, e);
+            }
+            if (sz) blocks.emplace_back(first, sz);
+        }
+        if (!why && (cnt == 0 || mx + 1 != cnt)) why = "object coordinates are not the leading columns";
+        up = (int)cnt;
+        if (!why) {
+            auto below = [&](const std::vector<int32_t> &cols) {
+                for (int32_t c : cols)
+                    if (active(c) && c - d < up) return true;
+                return false;
+            };
+            if (below(h->io_col) || below(h->coef_col) || below(h->eo_col)) why = "a camera or image parameter precedes an object coordinate";
+        }
+        if (!why && P.u - up <= 0) why = "no camera or image unknowns";
+        if (!why && round_up(P.u - up + d, kBlk) > 65535) why = "reduced system too large for one grid dimension";
+        if (!why) {
+            std::sort(blocks.begin(), blocks.end());
+            col_blk.assign(up, -1);
+            for (size_t b = 0; b < blocks.size(); b++) {
+                blk_start.push_back(blocks[b].first);
+                blk_size.push_back(blocks[b].second);
+                for (int k = 0; k < blocks[b].second; k++) col_blk[blocks[b].first + k] = (int32_t)b;
+            }
+            for (int32_t b : col_blk)
+                if (b < 0) { why = "object coordinate columns are not contiguous"; break; }
+        }
+    }
+    if (why) {
+        if (want == JAICOV_SOLVER_STRUCTURED) throw std::runtime_error(std::string("structured solver not applicable: ") + why);
+        return;
+    }
+    st.on = true;
+    StructDims &D = st.D;
+    D.up = up; D.nc = P.u - up; D.d = d; D.u = P.u;
+    D.Tp = round_up(up, kBlk); D.mp = round_up(D.nc + d, kBlk); D.ncp = round_up(D.nc, kBlk); D.np = P.np;
+    st.nBlk = (int)blk_start.size();
+    st.blk_start.upload(blk_start); st.blk_size.upload(blk_size); st.col_blk.upload(col_blk);
+    st.Pinv.alloc((size_t)st.nBlk * 9);
+    const size_t zt = (size_t)D.mp * D.Tp;
+    st.Zt.alloc(zt); st.Yt.alloc(zt);
+    if (h->wants_inverse()) st.T1t.alloc(zt);
+    st.Kp.alloc((size_t)D.mp * D.mp);
+    st.Sm.alloc((size_t)D.ncp * D.ncp); st.Wm.alloc((size_t)D.ncp * D.ncp); st.Dinv.alloc((size_t)D.ncp * kBlk);
+    st.Eb.alloc(8 * (size_t)D.ncp); st.ED.alloc(8 * (size_t)D.ncp); st.Fb.alloc(8 * (size_t)D.ncp);
+    st.zp.alloc((size_t)D.Tp); st.rp.alloc((size_t)D.mp); st.yr.alloc((size_t)D.mp); st.ys.alloc((size_t)P.np);
 }
 
 void prepare(jaicov_handle *h) {
@@ -405,6 +500,8 @@ void prepare(jaicov_handle *h) {
     h->d_omega_partial.alloc(S.omegaBlocks + 2);
     S.img_partial = h->d_img_partial.p; S.cam_partial = h->d_cam_partial.p; S.pt_partial = h->d_pt_partial.p;
     S.omega_partial = h->d_omega_partial.p;
+    // ---- solver route --------------------------------------------------------------------------------------------
+    select_solver(h);
     // ---- system buffers ------------------------------------------------------------------------------------------
     const size_t np = (size_t)P.np;
     h->M.alloc(np * np);
@@ -440,7 +537,7 @@ void prepare(jaicov_handle *h) {
         for (int32_t c : h->eo_col)
             if (active(c)) r0 = (r0 < 0) ? c - d : std::min<int64_t>(r0, c - d);
         h->strip_row0 = r0;
-    } else if (h->wants_inverse()) {
+    } else if (h->wants_inverse() && !h->st.on) {
         h->W.alloc(np * np);
     }
     if ((h->opt.invert_mode == JAICOV_INVERT_REDUCED || h->opt.invert_mode == JAICOV_INVERT_PRE_ELIMINATION) && h->reduced_rows < 0)
@@ -573,7 +670,8 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     if (h->adapted_damping > 0) launch_damp_diag(h->M.p, P.np, P.u, h->adapted_damping, s);
     // preconditioner and SPD reformulation (K4)
     launch_precond_diag(h->M.p, P.np, P.u, P.np, h->V.p, s);
-    launch_scale_system(h->M.p, P.np, P.u, h->V.p, h->Bt.p, P.d, P.np, s);
+    // (the structured route keeps the datum rows as a border of its reduced system instead of folding B'B into N)
+    launch_scale_system(h->M.p, P.np, P.u, h->V.p, h->Bt.p, h->st.on ? 0 : P.d, P.np, s);
     JCHECK(cudaMemsetAsync(h->Rt.p, 0, (size_t)kRhsRows * np * sizeof(double), s));
     launch_build_rhs(h->Rt.p, h->Btv.p, P.np, P.u, h->V.p, h->rhs.p, h->Bt.p, P.d, h->opt.estimation_type == JAICOV_SIMULATION, s);
     h->have_neq = false;
@@ -583,7 +681,28 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     CudaBackend be{s, h->info.p};
     DenseSchedule<CudaBackend> ds{be, h->M.p, P.np, P.np, h->Dinv.p};
     const bool multi = h->dist_on && h->dist.world > 1;
-    if (multi) {
+    jaicov_handle::Structured &st = h->st;
+    if (st.on) {
+        // reduced system K' = [[R, B_r'],[B_r, 0]] - Z'Y and its inverse Q' (structured.cu)
+        const StructDims &D = st.D;
+        launch_point_block_inv(h->M.p, P.np, st.blk_start.p, st.blk_size.p, st.nBlk, st.Pinv.p, h->info.p, s);
+        launch_build_zy(h->M.p, h->Btv.p, D, st.col_blk.p, st.blk_start.p, st.blk_size.p, st.Pinv.p, st.Zt.p, st.Yt.p, s);
+        launch_init_kp(h->M.p, h->Btv.p, D, st.Kp.p, s);
+        {
+            GemmDesc g;
+            g.al = 0; g.bl = 0; g.mt = g.nt = (int)(D.mp / kBlk); g.K = D.Tp; g.alpha = -1.0; g.beta = 1.0;
+            g.A = st.Zt.p; g.lda = D.Tp; g.B = st.Yt.p; g.ldb = D.Tp; g.C = st.Kp.p; g.ldc = D.mp; g.tri_out = 1;
+            be.gemm(g);
+        }
+        if (D.d > 0) launch_border_prep(st.Kp.p, D, st.Eb.p, st.ED.p, h->small.p, s);
+        launch_form_stilde(st.Kp.p, D, st.Eb.p, st.ED.p, st.Sm.p, s);
+        DenseSchedule<CudaBackend> dr{be, st.Sm.p, D.ncp, D.ncp, st.Dinv.p};
+        dr.potrf();
+        dr.invert_from_factor(st.Wm.p);
+        launch_symmetrize(st.Sm.p, D.ncp, D.nc, s);
+        launch_border_f(st.Sm.p, D, st.ED.p, st.Fb.p, h->small.p, s);
+        launch_fill_qprime(st.Sm.p, D, st.Fb.p, h->small.p, st.Kp.p, s);
+    } else if (multi) {
         PanelComm pc{&h->dist, s, h->M.p, P.np, P.np, h->Dinv.p, h->panel_tiles};
         pc.ensure_stage((size_t)P.np * h->panel_tiles * kBlk + (size_t)h->panel_tiles * kBlk * kBlk);
         ds.potrf_distributed(pc, h->dist.rank, h->dist.world, h->panel_tiles, h->ptab.empty() ? nullptr : h->d_ptab.p,
@@ -597,8 +716,14 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     }
     JCHECK(cudaEventRecord(h->ev[2], s));
     // solve for n and the datum rows, datum correction, dx (K5/K9)
-    launch_solve_rows8(h->M.p, P.np, h->Dinv.p, h->Rt.p, h->Rt.p + 8 * np, P.np, s);
-    launch_datum_solve(h->Rt.p, h->Btv.p, P.d, P.np, P.u, h->V.p, h->dxref.p, h->H.p, h->Tq.p, h->small.p, s);
+    if (st.on) {
+        // (H doubles as the d null-space rows K^-1[lambda, x]; small[100..107) holds the datum residual B y)
+        launch_structured_solution(h->Rt.p, st.D, st.col_blk.p, st.blk_start.p, st.blk_size.p, st.Pinv.p, st.Zt.p, st.Yt.p, st.Kp.p,
+                                   h->Btv.p, h->V.p, st.zp.p, st.rp.p, st.yr.p, st.ys.p, h->H.p, h->small.p + 100, h->dxref.p, s);
+    } else {
+        launch_solve_rows8(h->M.p, P.np, h->Dinv.p, h->Rt.p, h->Rt.p + 8 * np, P.np, s);
+        launch_datum_solve(h->Rt.p, h->Btv.p, P.d, P.np, P.u, h->V.p, h->dxref.p, h->H.p, h->Tq.p, h->small.p, s);
+    }
     // Levenberg-Marquardt step control (updateModel, BA:390-426): shorten the step, compare Omega, accept or reject
     PassResult r;
     bool apply_dx = apply_update;
@@ -625,7 +750,20 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     }
     JCHECK(cudaEventRecord(h->ev[3], s));
     // inverse (K6/K7)
-    if (invert && h->dist_on) {
+    if (invert && st.on) {
+        // K^-1[p, r|lambda] = -(Q' Y')', K^-1[p, p] = P^-1 + Y (Q' Y'): two tensor-core products, then placement and V scaling
+        const StructDims &D = st.D;
+        GemmDesc g;
+        g.al = 0; g.bl = 1; g.mt = (int)(D.mp / kBlk); g.nt = (int)(D.Tp / kBlk); g.K = D.mp; g.alpha = 1.0; g.beta = 0.0;
+        g.A = st.Kp.p; g.lda = D.mp; g.B = st.Yt.p; g.ldb = D.Tp; g.C = st.T1t.p; g.ldc = D.Tp;
+        be.gemm(g);
+        GemmDesc q;
+        q.al = 1; q.bl = 1; q.mt = q.nt = (int)(D.Tp / kBlk); q.K = D.mp; q.alpha = 1.0; q.beta = 0.0;
+        q.A = st.Yt.p; q.lda = D.Tp; q.B = st.T1t.p; q.ldb = D.Tp; q.C = h->M.p; q.ldc = P.np; q.tri_out = 1;
+        be.gemm(q);
+        launch_structured_place(h->M.p, D, st.T1t.p, st.Kp.p, st.blk_start.p, st.blk_size.p, st.nBlk, st.Pinv.p, h->V.p, h->Tq.p, s);
+        launch_qxx_epilogue(h->M.p, P.np, P.u, h->V.p, h->H.p, h->Rt.p + np, 0, P.np, s);
+    } else if (invert && h->dist_on) {
         // every rank inverts its own column tiles from the replicated factor: no communication
         const int ntc = (int)h->ktab.size();
         if (ntc > 0) {
@@ -696,6 +834,7 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     cudaEventElapsedTime(&tot, h->ev[0], h->ev[6]);
     h->stats.ms_total = tot;
     h->have_qxx = invert && r.info == 0;
+    h->stats.solver_used = st.on ? JAICOV_SOLVER_STRUCTURED : JAICOV_SOLVER_DENSE;
     return r;
 }
 
@@ -760,6 +899,8 @@ int32_t jaicov_default_options(jaicov_options *opt) {
     opt->use_centroid = 1;
     opt->apply_aposteriori = 1;
     opt->device = 0;
+    opt->solver = JAICOV_SOLVER_AUTO;
+    opt->reserved0 = 0;
     opt->sigma2apriori = 1.0;
     opt->damping_value = 0.0;
     return JAICOV_OK;
@@ -775,6 +916,7 @@ int32_t jaicov_create(const jaicov_options *opt, jaicov_handle **out) {
     if (!(opt->damping_value >= 0.0)) return JAICOV_ILLEGAL_ARGUMENT;
     if (opt->invert_mode < JAICOV_INVERT_NONE || opt->invert_mode > JAICOV_INVERT_REDUCED) return JAICOV_ILLEGAL_ARGUMENT;
     if (opt->estimation_type != JAICOV_L2NORM && opt->estimation_type != JAICOV_SIMULATION) return JAICOV_ILLEGAL_ARGUMENT;
+    if (opt->solver < JAICOV_SOLVER_AUTO || opt->solver > JAICOV_SOLVER_STRUCTURED) return JAICOV_ILLEGAL_ARGUMENT;
     jaicov_handle *h = new (std::nothrow) jaicov_handle();
     if (!h) return JAICOV_OUT_OF_MEMORY;
     h->opt = *opt;

@@ -117,4 +117,31 @@ void launch_eval_k1(const DevProblem &P, int ns_max, double *a, double *w, doubl
 void launch_scale_bars(const DevProblem &P, double *M, double *rhs, cudaStream_t s);
 void launch_omega_bars(const DevProblem &P, const double *dxref, double *omega_out, cudaStream_t s);
 
+// ---- structured.cu: point-block solver (DESIGN.md "structured route") ------------------------------------------------------
+struct StructDims {
+    int up;        // object-coordinate columns (leading, block diagonal)
+    int nc;        // remaining columns (interior orientation, distortion, exterior orientations)
+    int d;         // datum rows
+    int u;         // up + nc
+    int64_t Tp;    // up padded to a multiple of 128 (leading dimension of Zt, Yt, T1t)
+    int64_t mp;    // nc + d padded to a multiple of 128 (leading dimension of Kp)
+    int64_t ncp;   // nc padded to a multiple of 128 (leading dimension of Sm)
+    int64_t np;    // leading dimension of M, Btv, Tq
+};
+void launch_point_block_inv(const double *M, int64_t ld, const int32_t *blk_start, const int32_t *blk_size, int nBlk, double *Pinv,
+                            int *info, cudaStream_t s);
+void launch_build_zy(const double *M, const double *Btv, const StructDims &D, const int32_t *col_blk, const int32_t *blk_start,
+                     const int32_t *blk_size, const double *Pinv, double *Zt, double *Yt, cudaStream_t s);
+void launch_init_kp(const double *M, const double *Btv, const StructDims &D, double *Kp, cudaStream_t s);
+void launch_border_prep(const double *Kp, const StructDims &D, double *Eb, double *ED, double *sb, cudaStream_t s);
+void launch_form_stilde(const double *Kp, const StructDims &D, const double *Eb, const double *ED, double *Sm, cudaStream_t s);
+void launch_border_f(const double *Sm, const StructDims &D, const double *ED, double *Fb, double *sb, cudaStream_t s);
+void launch_fill_qprime(const double *Sm, const StructDims &D, const double *Fb, const double *sb, double *Kp, cudaStream_t s);
+void launch_structured_solution(const double *nrm, const StructDims &D, const int32_t *col_blk, const int32_t *blk_start,
+                                const int32_t *blk_size, const double *Pinv, const double *Zt, const double *Yt, const double *Kp,
+                                const double *Btv, const double *V, double *zp, double *rp, double *yr, double *ys, double *Nt,
+                                double *t, double *dxref, cudaStream_t s);
+void launch_structured_place(double *M, const StructDims &D, const double *T1t, const double *Kp, const int32_t *blk_start,
+                             const int32_t *blk_size, int nBlk, const double *Pinv, const double *V, double *Tq, cudaStream_t s);
+
 }  // namespace jaicov

@@ -21,11 +21,9 @@ namespace jaicov {
 constexpr int GB = 128;       // tile edge
 constexpr int GK = 16;        // k slab
 constexpr int GSTAGES = 4;
-constexpr int GTHREADS = 256;
 constexpr int PITCH_K = 20;   // [128][16] slab stored with pitch 20 doubles
 constexpr int PITCH_M = 132;  // [16][128] slab stored with pitch 132 doubles
 constexpr int SLAB = 128 * PITCH_K;  // 2560 doubles >= 16 * 132
-constexpr size_t GEMM_SMEM = (size_t)GSTAGES * 2 * SLAB * sizeof(double);
 
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"

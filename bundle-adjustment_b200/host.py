@@ -516,6 +516,11 @@ class BundleAdjustment:
     def getLevenbergMarquardtDampingValue(self): return self._damping
     def setMaximalNumberOfIterations(self, n): self._maxIter = int(n)
 
+    def setSolver(self, solver):
+        """Not part of the reference API: _lib.SOLVER_AUTO (default) / SOLVER_DENSE / SOLVER_STRUCTURED, see
+        include/jaicov_b200.h.  Both routes return the reference's results."""
+        self._solver = int(solver)
+
     def getNumberOfObservations(self): return self._numObs
     def getNumberOfUnknownParameters(self): return self._numUnknown
     def getNumberOfDatumConditions(self): return self._defect
@@ -817,7 +822,8 @@ class BundleAdjustment:
                          MatrixInversion.REDUCED: _lib.INVERT_REDUCED}[self._invert],
             estimation_type=_lib.SIMULATION if self._estimationType == EstimationType.SIMULATION else _lib.L2NORM,
             max_iterations=self._maxIter, use_centroid=self._useCentroid, apply_aposteriori=self._applyAposteriori,
-            device=self._device, sigma2apriori=self._sigma2apriori, damping_value=self._damping)
+            device=self._device, sigma2apriori=self._sigma2apriori, damping_value=self._damping,
+            solver=getattr(self, '_solver', _lib.SOLVER_AUTO))
         self._session.set_problem(flat)
         rc = self._session.estimate(progress=self._fire if self._listeners else None)
         self.stats = self._session.stats()

@@ -65,6 +65,14 @@ extern "C" {
 #define JAICOV_L2NORM 0
 #define JAICOV_SIMULATION 1
 
+/* Solver route.  The reference has one (LAPACK on the packed n x n system, MathExtension.java:338-366); both routes here
+ * return its results.  STRUCTURED applies when no observation couples two object points (no scale bars, no directly
+ * observed point groups): the object-coordinate block of N is then block diagonal and dx / Qxx follow from the reduced
+ * camera system.  AUTO takes it when it applies, DENSE never, STRUCTURED fails if it does not. */
+#define JAICOV_SOLVER_AUTO 0
+#define JAICOV_SOLVER_DENSE 1
+#define JAICOV_SOLVER_STRUCTURED 2
+
 #define JAICOV_COL_UNSET (-1)
 #define JAICOV_COL_FIXED 2147483647
 
@@ -89,6 +97,8 @@ typedef struct {
     int32_t use_centroid;       /* useCentroidedCoordinates, :1181 (default 1, :87) */
     int32_t apply_aposteriori;  /* applyAposterioriVarianceOfUnitWeight, :1185 (default 1, :86) */
     int32_t device;             /* CUDA device ordinal this handle binds to */
+    int32_t solver;             /* JAICOV_SOLVER_* (default AUTO); the environment variable JAICOV_SOLVER=dense|structured overrides */
+    int32_t reserved0;
     double sigma2apriori;       /* min(1, min variance) as accumulated by addObservationGroup, :637-643; <=0 -> 1 (:221) */
     double damping_value;       /* Levenberg-Marquardt lambda >= 0, setLevenbergMarquardtDampingValue :1189; 0 = plain Gauss-Newton (:96) */
 } jaicov_options;
@@ -101,7 +111,7 @@ typedef struct {
     int32_t n_datum;            /* d */
     int32_t n_observations;     /* 2 m + bars + observed rows */
     int32_t dof;                /* n_observations - u + d (:1080-1082) */
-    int32_t reserved;
+    int32_t solver_used;        /* JAICOV_SOLVER_DENSE or JAICOV_SOLVER_STRUCTURED: the route the last pass took */
     double omega;               /* v'Pv of the final pass (:429-430) */
     double max_abs_dx;          /* of the last pass (:432) */
     double sigma2apriori;

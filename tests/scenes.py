@@ -165,5 +165,9 @@ def synthetic_scene(config, images=None, targets=None, seed=None, sigma_img=0.00
                        'dispersion': packed})
     scene = {'points': {'xyz': pts0, 'fixed': np.zeros((T, 3), bool), 'datum': np.ones(T, bool)},
              'cameras': cameras, 'scale_bars': [], 'observed_groups': groups}
+    if free_network is False:
+        # datum by three fixed (error-free) object points instead of the free-network conditions
+        scene['points']['fixed'][:3] = True
+        scene['points']['xyz'][:3] = pts_true[:3]
     truth = dict(points=pts_true, io=io_true, coefs=coefs_true, eo=eo_true)
     return scene, truth

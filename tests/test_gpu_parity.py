@@ -140,8 +140,14 @@ def test_spd_solve_invert(built, n, nrhs):
     assert e.value.code == ba._lib.SINGULAR_MATRIX
 
 
-def compare_adjustment(scene, label, use_centroid=True, mode='FULL', damping=0.0):
+SOLVERS = {'dense': ba._lib.SOLVER_DENSE, 'structured': ba._lib.SOLVER_STRUCTURED}
+
+
+def compare_adjustment(scene, label, use_centroid=True, mode='FULL', damping=0.0, solver=None):
     adj, pts = build_adjustment(scene)
+    if solver is not None:
+        adj.setSolver(SOLVERS[solver])
+        label = '%s [%s]' % (label, solver)
     adj.useCentroidedCoordinates(use_centroid)
     adj.setInvertNormalEquation(ba.MatrixInversion[mode])
     adj.setLevenbergMarquardtDampingValue(damping)
@@ -153,6 +159,8 @@ def compare_adjustment(scene, label, use_centroid=True, mode='FULL', damping=0.0
     st_o = o.estimate()
     assert state.getId() == st_o == 1
     st = adj.stats
+    if solver is not None:
+        assert st.solver_used == SOLVERS[solver]
     # integer bookkeeping: bit-exact
     assert (st.n_unknowns, st.n_datum, st.n_observations, st.dof) == (o.bk.n_unknown, o.bk.d, o.bk.n_obs, o.bk.dof)
     assert st.iterations == len(o.history)
@@ -195,9 +203,14 @@ def compare_adjustment(scene, label, use_centroid=True, mode='FULL', damping=0.0
     return adj, o
 
 
+BOTH = pytest.mark.parametrize('solver', ['dense', 'structured'])
+
+
 def test_adjustment_example_config1(built):
-    """BASELINE.json configs[0]: the bundled 115-image example, FULL inversion."""
+    """BASELINE.json configs[0]: the bundled 115-image example, FULL inversion (its scale bars couple object points:
+    JAICOV_SOLVER_AUTO takes the dense route)."""
     adj, o = compare_adjustment(example_scene(), 'config 1')
+    assert adj.stats.solver_used == ba._lib.SOLVER_DENSE
     # the external known answer: AICON's S0 = 0.000405 (example.htm:31)
     s0 = 0.0005 * np.sqrt(adj.getVarianceFactorAposteriori() / adj.getVarianceFactorApriori())
     assert abs(s0 - 0.000405) < 5e-7
@@ -208,19 +221,49 @@ def test_adjustment_example_config1(built):
     np.testing.assert_array_equal(adj._session.qxx_diag(), np.diag(Q))
 
 
-def test_adjustment_config2(built):
+@BOTH
+def test_adjustment_config2(built, solver):
     """BASELINE.json configs[1]: 50 images x 500 targets, in-situ calibration, free network (d = 7)."""
-    compare_adjustment(synthetic_scene(2)[0], 'config 2')
+    compare_adjustment(synthetic_scene(2)[0], 'config 2', solver=solver)
 
 
 def test_adjustment_config3_small(built):
-    """configs[2] scaled down: correlated image xy + fully populated dispersion of observed object points (d = 0)."""
-    compare_adjustment(synthetic_scene(3, images=12, targets=150)[0], 'config 3 (12 x 150)')
+    """configs[2] scaled down: correlated image xy + fully populated dispersion of observed object points (d = 0).
+    The observed group couples the object points: the structured route does not apply and says so."""
+    sc = synthetic_scene(3, images=12, targets=150)[0]
+    adj, _ = compare_adjustment(sc, 'config 3 (12 x 150)')
+    assert adj.stats.solver_used == ba._lib.SOLVER_DENSE
+    adj2, _ = build_adjustment(sc)
+    adj2.setSolver(ba._lib.SOLVER_STRUCTURED)
+    with pytest.raises(ba.JaicovError) as e:
+        adj2.estimateModel()
+    assert e.value.code == ba._lib.ILLEGAL_ARGUMENT and 'structured solver not applicable' in str(e.value)
 
 
-def test_adjustment_config4_small(built):
+def test_adjustment_structured_without_datum_defect(built):
+    """d = 0 with block-diagonal object points: enough fixed coordinates define the datum, no border in the reduced system."""
+    sc = synthetic_scene(2, images=14, targets=120, free_network=False)[0]
+    adj, o = compare_adjustment(sc, 'config 2 (14 x 120), fixed datum', solver='structured')
+    assert o.bk.d == 0
+
+
+@BOTH
+def test_adjustment_config4_small(built, solver):
     """configs[3] scaled down: distance-dependent distortion D_i, free network, full Qxx."""
-    compare_adjustment(synthetic_scene(4, images=30, targets=300)[0], 'config 4 (30 x 300)')
+    compare_adjustment(synthetic_scene(4, images=30, targets=300)[0], 'config 4 (30 x 300)', solver=solver)
+
+
+def test_adjustment_structured_partially_fixed_points_two_cameras(built):
+    """Point blocks of 1, 2 and 3 columns, a fully fixed point, sparse visibility, two cameras, fixed EO / coefficient."""
+    sc = synthetic_scene(4, images=12, targets=120, visibility=0.7, n_cameras=2)[0]
+    sc['points']['fixed'][4, 1] = True
+    sc['points']['fixed'][9, 0] = True
+    sc['points']['fixed'][9, 2] = True
+    sc['points']['fixed'][17] = True
+    sc['cameras'][0]['images'][1]['eo_fixed'][4] = True
+    sc['cameras'][1]['coefs'][9] = sc['cameras'][1]['coefs'][9][:3] + (True,)
+    compare_adjustment(sc, 'mixed blocks', use_centroid=False, solver='structured')
+    compare_adjustment(sc, 'mixed blocks', use_centroid=False, solver='dense')
 
 
 def test_adjustment_fixed_parameters_scale_bar_two_cameras(built):
@@ -250,11 +293,19 @@ def test_adjustment_example_reduced_modes(built, mode):
     assert adj._session.n_qxx == o.num_rows_reduced() == 463
 
 
+@BOTH
+@pytest.mark.parametrize('mode', ['REDUCED', 'PRE_ELIMINATION'])
+def test_adjustment_synthetic_reduced_modes(built, mode, solver):
+    """The reduced modes on a free network without scale bars, through both solver routes."""
+    compare_adjustment(synthetic_scene(2, images=12, targets=80)[0], 'config 2 (12 x 80) ' + mode, mode=mode, solver=solver)
+
+
+@BOTH
 @pytest.mark.parametrize('damping', [1e-3, 1.0, 100.0])
-def test_adjustment_levenberg_marquardt(built, damping):
+def test_adjustment_levenberg_marquardt(built, damping, solver):
     """Levenberg-Marquardt damping N_cc *= (1 + lambda) (BA:801-822) with the step control of
     updateModel (BA:390-426): shortened step, Omega comparison, lambda x0.2 / x5."""
-    compare_adjustment(synthetic_scene(2, images=12, targets=80)[0], 'LM lambda=%g' % damping, damping=damping)
+    compare_adjustment(synthetic_scene(2, images=12, targets=80)[0], 'LM lambda=%g' % damping, damping=damping, solver=solver)
 
 
 def test_modes_none_and_simulation(built):

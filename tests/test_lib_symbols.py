@@ -27,7 +27,7 @@ def test_exports_match_header(built):
 
 
 def test_struct_sizes(built):
-    assert ctypes.sizeof(ba._lib.Options) == 6 * 4 + 2 * 8
+    assert ctypes.sizeof(ba._lib.Options) == 8 * 4 + 2 * 8
     assert ctypes.sizeof(ba._lib.Stats) == 8 * 4 + 10 * 8
 
 
