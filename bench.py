@@ -266,21 +266,25 @@ def main():
 
     # ---- the structured (point-block) route on the same workload, reported next to the headline ----------------------------
     structured = None
-    if world == 1 and not structured_used and not args.no_structured and os.environ.get('JAICOV_SOLVER') is None:
+    if not structured_used and not args.no_structured and os.environ.get('JAICOV_SOLVER') is None:
         sess.close()
         try:
             sess = new_session('structured')
             sess.set_problem(flat)
             for _ in range(args.warmup):
                 assert sess.iterate(final_pass=True, apply_update=False) == 0
-            torch.cuda.synchronize()
+            barrier()
             sdev, sstage = 0.0, np.zeros(5)
             for _ in range(args.steps):
                 assert sess.iterate(final_pass=True, apply_update=False) == 0
                 st = sess.stats()
                 sdev += st.ms_total
                 sstage += [st.ms_assembly, st.ms_factor, st.ms_solve, st.ms_inverse, st.ms_omega]
-            torch.cuda.synchronize()
+            barrier()
+            if world > 1:
+                ts = torch.tensor([sdev] + sstage.tolist(), dtype=torch.float64, device='cuda')
+                dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+                sdev, sstage = float(ts[0]), ts[1:].cpu().numpy()
             sstage /= args.steps
             sfl = structured_flops(flat)
             structured = {'ms_per_step': sdev / args.steps, 'value': args.steps / (sdev * 1e-3), 'unit': UNIT,
@@ -375,7 +379,7 @@ def main():
         line['e2e'] = e2e
     if structured:
         if 'tflops' in structured:
-            structured['frac_of_fp64_peak'] = structured['tflops'] / peak
+            structured['frac_of_fp64_peak'] = structured['tflops'] / (peak * world)
         line['structured'] = structured
     if not args.no_cpu_baseline and world == 1:
         line['cpu_baseline'] = cpu_sample(args.config, n, flat['obj_idx'].size, 1)

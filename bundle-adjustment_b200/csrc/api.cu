@@ -209,6 +209,7 @@ struct jaicov_handle {
         bool on = false;
         StructDims D{};
         int nBlk = 0;
+        int ntp = 0;     // multi-GPU: number of this rank's inverse tiles that hold object-coordinate columns
         DevBuf<int32_t> blk_start, blk_size, col_blk;
         DevBuf<double> Pinv, Zt, Yt, T1t, Kp, Sm, Wm, Dinv, Eb, ED, Fb, zp, rp, yr, ys;
     } st;
@@ -290,7 +291,6 @@ void select_solver(jaicov_handle *h) {
     std::vector<int32_t> blk_start, blk_size, col_blk;
     int up = 0;
     if (want == JAICOV_SOLVER_DENSE) why = "dense route requested";
-    else if (h->dist_on) why = "multi-GPU handles use the distributed dense route";
     else if (!h->bar_a.empty()) why = "scale bars couple object points";
     if (!why)
         for (const Group &g : h->groups)
@@ -352,7 +352,6 @@ void select_solver(jaicov_handle *h) {
     st.Pinv.alloc((size_t)st.nBlk * 9);
     const size_t zt = (size_t)D.mp * D.Tp;
     st.Zt.alloc(zt); st.Yt.alloc(zt);
-    if (h->wants_inverse()) st.T1t.alloc(zt);
     st.Kp.alloc((size_t)D.mp * D.mp);
     st.Sm.alloc((size_t)D.ncp * D.ncp); st.Wm.alloc((size_t)D.ncp * D.ncp); st.Dinv.alloc((size_t)D.ncp * kBlk);
     st.Eb.alloc(8 * (size_t)D.ncp); st.ED.alloc(8 * (size_t)D.ncp); st.Fb.alloc(8 * (size_t)D.ncp);
@@ -540,6 +539,14 @@ void prepare(jaicov_handle *h) {
     } else if (h->wants_inverse() && !h->st.on) {
         h->W.alloc(np * np);
     }
+    if (h->st.on && h->wants_inverse()) {
+        // Q'Y': all object-coordinate columns on one GPU, this rank's object-coordinate tiles (a prefix of ktab) otherwise
+        const StructDims &D = h->st.D;
+        h->st.ntp = 0;
+        for (int32_t c : h->ktab)
+            if (c < D.Tp) h->st.ntp++;
+        h->st.T1t.alloc((size_t)D.mp * (h->dist_on ? (size_t)std::max(h->st.ntp, 1) * kBlk : (size_t)D.Tp));
+    }
     if ((h->opt.invert_mode == JAICOV_INVERT_REDUCED || h->opt.invert_mode == JAICOV_INVERT_PRE_ELIMINATION) && h->reduced_rows < 0)
         throw std::runtime_error("invert_mode REDUCED / PRE_ELIMINATION needs jaicov_set_reduced_rows (numRows of BA:262)");
     h->Dinv.alloc(np * kBlk);
@@ -719,7 +726,7 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     if (st.on) {
         // (H doubles as the d null-space rows K^-1[lambda, x]; small[100..107) holds the datum residual B y)
         launch_structured_solution(h->Rt.p, st.D, st.col_blk.p, st.blk_start.p, st.blk_size.p, st.Pinv.p, st.Zt.p, st.Yt.p, st.Kp.p,
-                                   h->Btv.p, h->V.p, st.zp.p, st.rp.p, st.yr.p, st.ys.p, h->H.p, h->small.p + 100, h->dxref.p, s);
+                                   h->Btv.p, h->V.p, st.zp.p, st.rp.p, st.yr.p, st.ys.p, h->H.p, h->small.p + 100, h->dxref.p, h->Tq.p, s);
     } else {
         launch_solve_rows8(h->M.p, P.np, h->Dinv.p, h->Rt.p, h->Rt.p + 8 * np, P.np, s);
         launch_datum_solve(h->Rt.p, h->Btv.p, P.d, P.np, P.u, h->V.p, h->dxref.p, h->H.p, h->Tq.p, h->small.p, s);
@@ -750,7 +757,31 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     }
     JCHECK(cudaEventRecord(h->ev[3], s));
     // inverse (K6/K7)
-    if (invert && st.on) {
+    if (invert && st.on && h->dist_on) {
+        // the same two products restricted to this rank's column tiles of the inverse (no communication): Q'Y' for its
+        // object-coordinate tiles, then the rows on and below each tile's diagonal of Y (Q'Y')
+        const StructDims &D = st.D;
+        const int ntc = (int)h->ktab.size(), ntp = st.ntp;
+        if (ntc > 0) {
+            const int64_t ldx = (int64_t)ntc * kBlk, ldt = (int64_t)std::max(ntp, 1) * kBlk;
+            JCHECK(cudaMemsetAsync(h->Xl.p, 0, np * (size_t)ldx * sizeof(double), s));
+            if (ntp > 0) {
+                GemmDesc g;
+                g.al = 0; g.bl = 1; g.mt = (int)(D.mp / kBlk); g.nt = ntp; g.K = D.mp; g.alpha = 1.0; g.beta = 0.0;
+                g.A = st.Kp.p; g.lda = D.mp; g.B = st.Yt.p; g.ldb = D.Tp; g.C = st.T1t.p; g.ldc = ldt;
+                g.coltab = h->d_ktab.p; g.ncoltab = ntp; g.coltab_full = 1; g.c_local = 1;
+                be.gemm(g);
+                GemmDesc q;
+                q.al = 1; q.bl = 1; q.mt = (int)(D.Tp / kBlk); q.nt = ntp; q.K = D.mp; q.alpha = 1.0; q.beta = 0.0;
+                q.A = st.Yt.p; q.lda = D.Tp; q.B = st.T1t.p; q.ldb = ldt; q.C = h->Xl.p; q.ldc = ldx;
+                q.kmode = K_ROW_MASK; q.ktab = h->d_ktab.p; q.roff = 0;
+                be.gemm(q);
+            }
+            launch_structured_place_cols(h->Xl.p, ldx, ntc, h->d_ktab.p, h->d_col_local.p, D, st.T1t.p, ldt, st.Kp.p, st.blk_start.p,
+                                         st.blk_size.p, st.nBlk, st.Pinv.p, s);
+            launch_qxx_epilogue_cols(h->Xl.p, ldx, ntc, h->d_ktab.p, P.u, h->V.p, h->H.p, h->Rt.p + np, 0, P.np, s);
+        }
+    } else if (invert && st.on) {
         // K^-1[p, r|lambda] = -(Q' Y')', K^-1[p, p] = P^-1 + Y (Q' Y'): two tensor-core products, then placement and V scaling
         const StructDims &D = st.D;
         GemmDesc g;
@@ -761,7 +792,7 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
         q.al = 1; q.bl = 1; q.mt = q.nt = (int)(D.Tp / kBlk); q.K = D.mp; q.alpha = 1.0; q.beta = 0.0;
         q.A = st.Yt.p; q.lda = D.Tp; q.B = st.T1t.p; q.ldb = D.Tp; q.C = h->M.p; q.ldc = P.np; q.tri_out = 1;
         be.gemm(q);
-        launch_structured_place(h->M.p, D, st.T1t.p, st.Kp.p, st.blk_start.p, st.blk_size.p, st.nBlk, st.Pinv.p, h->V.p, h->Tq.p, s);
+        launch_structured_place(h->M.p, D, st.T1t.p, st.Kp.p, st.blk_start.p, st.blk_size.p, st.nBlk, st.Pinv.p, s);
         launch_qxx_epilogue(h->M.p, P.np, P.u, h->V.p, h->H.p, h->Rt.p + np, 0, P.np, s);
     } else if (invert && h->dist_on) {
         // every rank inverts its own column tiles from the replicated factor: no communication

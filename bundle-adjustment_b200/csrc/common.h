@@ -140,8 +140,11 @@ void launch_fill_qprime(const double *Sm, const StructDims &D, const double *Fb,
 void launch_structured_solution(const double *nrm, const StructDims &D, const int32_t *col_blk, const int32_t *blk_start,
                                 const int32_t *blk_size, const double *Pinv, const double *Zt, const double *Yt, const double *Kp,
                                 const double *Btv, const double *V, double *zp, double *rp, double *yr, double *ys, double *Nt,
-                                double *t, double *dxref, cudaStream_t s);
+                                double *t, double *dxref, double *Tq, cudaStream_t s);
 void launch_structured_place(double *M, const StructDims &D, const double *T1t, const double *Kp, const int32_t *blk_start,
-                             const int32_t *blk_size, int nBlk, const double *Pinv, const double *V, double *Tq, cudaStream_t s);
+                             const int32_t *blk_size, int nBlk, const double *Pinv, cudaStream_t s);
+void launch_structured_place_cols(double *X, int64_t ldx, int ntc, const int32_t *ktab, const int32_t *col_local, const StructDims &D,
+                                  const double *T1l, int64_t ldt, const double *Kp, const int32_t *blk_start, const int32_t *blk_size,
+                                  int nBlk, const double *Pinv, cudaStream_t s);
 
 }  // namespace jaicov

@@ -50,6 +50,8 @@ struct GemmDesc {
     int kmode = K_FULL;
     const int32_t *coltab = nullptr; // if set: 2-D launch, blockIdx.y picks the global column tile coltab[y] / 128, blockIdx.x the
     int ncoltab = 0;                 //         global row tile; tiles above the diagonal exit (trapezoid update of many panels at once)
+    int coltab_full = 0;             // coltab launches: every row tile is wanted (no trapezoid skip)
+    int c_local = 0;                 // coltab launches: C is compact -- column tile blockIdx.y of C holds global tile coltab[y] / 128
     const int32_t *ktab = nullptr;   // K_COL_BEG / K_ROW_MASK: per column tile, first global row of interest
     int64_t koff = 0;                // K_COL_BEG: global row of k = 0
     int64_t roff = 0;                // K_ROW_MASK: global row of output tile row 0

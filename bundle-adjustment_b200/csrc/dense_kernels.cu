@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(GemmShape<BMT>::THREADS, GemmShape<BMT>::CTAS_
     if (g.coltab) {
         it = blockIdx.x / SPLIT;
         jt = g.coltab[blockIdx.y] / GB;
-        if (it < jt) return;    // above the diagonal of this column tile
+        if (!g.coltab_full && it < jt) return;    // above the diagonal of this column tile
     } else {
         const int l = blockIdx.x / SPLIT;
         if (g.tri_out) {
@@ -185,7 +185,8 @@ __global__ void __launch_bounds__(GemmShape<BMT>::THREADS, GemmShape<BMT>::CTAS_
     __syncthreads();   // every load of this CTA has landed before any store: in-place strips (C == A) are safe
 
     // ---- epilogue ------------------------------------------------------------------------------------------------
-    double *Cg = g.C + (mrow0 + wm * WT_M + grp) * g.ldc + (int64_t)jt * GB + wn * WT_N + 2 * tig;
+    const int64_t ctile = (g.coltab && g.c_local) ? (int64_t)blockIdx.y : (int64_t)jt;
+    double *Cg = g.C + (mrow0 + wm * WT_M + grp) * g.ldc + ctile * GB + wn * WT_N + 2 * tig;
     const double alpha = g.alpha, beta = g.beta;
 #pragma unroll
     for (int i = 0; i < MI; i++)

@@ -421,21 +421,26 @@ __global__ void __launch_bounds__(256) k_datum_residual(StructDims D, const doub
     }
 }
 
-// dx = V (ys - Nt' t)
+// dx = V (ys - Nt' t); border rows of the inverse: Tq[a][e] = V[e] K^-1[lambda_a, x_e]
 __global__ void __launch_bounds__(256) k_datum_project(StructDims D, const double *__restrict__ ys, const double *__restrict__ Nt,
                                                        const double *__restrict__ t, const double *__restrict__ V,
-                                                       double *__restrict__ dxref) {
+                                                       double *__restrict__ dxref, double *__restrict__ Tq) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= D.u) return;
     double y = ys[e];
-    for (int a = 0; a < D.d; a++) y -= Nt[a * D.np + e] * t[a];
-    dxref[D.d + e] = V[e] * y;
+    const double v = V[e];
+    for (int a = 0; a < D.d; a++) {
+        const double na = Nt[a * D.np + e];
+        y -= na * t[a];
+        Tq[a * D.np + e] = v * na;
+    }
+    dxref[D.d + e] = v * y;
 }
 
 void launch_structured_solution(const double *nrm, const StructDims &D, const int32_t *col_blk, const int32_t *blk_start,
                                 const int32_t *blk_size, const double *Pinv, const double *Zt, const double *Yt, const double *Kp,
                                 const double *Btv, const double *V, double *zp, double *rp, double *yr, double *ys, double *Nt,
-                                double *t, double *dxref, cudaStream_t s) {
+                                double *t, double *dxref, double *Tq, cudaStream_t s) {
     g_launch_count += 6;
     k_point_rhs<<<(unsigned)((D.Tp + 255) / 256), 256, 0, s>>>(nrm, D, col_blk, blk_start, blk_size, Pinv, zp);
     k_reduced_rhs<<<(unsigned)D.mp, 256, 0, s>>>(Zt, D, zp, nrm, rp);
@@ -443,7 +448,7 @@ void launch_structured_solution(const double *nrm, const StructDims &D, const in
     const int64_t n = D.u > D.d ? D.u : D.d;
     k_back_substitute<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(Yt, D, Kp, yr, zp, ys, Nt, dxref);
     k_datum_residual<<<1, 256, 0, s>>>(D, Btv, ys, t);
-    k_datum_project<<<(unsigned)((D.u + 255) / 256), 256, 0, s>>>(D, ys, Nt, t, V, dxref);
+    k_datum_project<<<(unsigned)((D.u + 255) / 256), 256, 0, s>>>(D, ys, Nt, t, V, dxref, Tq);
 }
 
 // ---- placement of the inverse into M (lower, row-major): rows of the r group, identity padding, P^-1 on the point blocks -------
@@ -472,29 +477,58 @@ __global__ void __launch_bounds__(128) k_add_point_blocks(double *__restrict__ M
         for (int j = 0; j <= i; j++) M[(c0 + i) * ld + c0 + j] += Pinv[(size_t)b * 9 + i * 3 + j];
 }
 
-// border of the inverse: Tq[a][e] = V[e] K^-1[lambda_a, x_e], Q11 = Q'[l,l] (already in sb[49..98))
-__global__ void __launch_bounds__(256) k_border_out(StructDims D, const double *__restrict__ T1t, const double *__restrict__ Kp,
-                                                    const double *__restrict__ V, double *__restrict__ Tq) {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= D.u) return;
-    const double v = V[e];
-    for (int a = 0; a < D.d; a++) {
-        const int64_t i = D.nc + a;
-        Tq[a * D.np + e] = v * (e < D.up ? -T1t[i * D.Tp + e] : Kp[i * D.mp + (e - D.up)]);
-    }
-}
-
 void launch_structured_place(double *M, const StructDims &D, const double *T1t, const double *Kp, const int32_t *blk_start,
-                             const int32_t *blk_size, int nBlk, const double *Pinv, const double *V, double *Tq, cudaStream_t s) {
+                             const int32_t *blk_size, int nBlk, const double *Pinv, cudaStream_t s) {
     int64_t row_end = D.Tp < D.np ? D.Tp : D.np;
     if (row_end < D.u) row_end = D.u;
     g_launch_count += 2;
     k_place_rows<<<(unsigned)(row_end - D.up), 256, 0, s>>>(M, D, T1t, Kp, row_end);
     k_add_point_blocks<<<(unsigned)((nBlk + 127) / 128), 128, 0, s>>>(M, D.np, blk_start, blk_size, nBlk, Pinv);
-    if (D.d > 0) {
-        g_launch_count++;
-        k_border_out<<<(unsigned)((D.u + 255) / 256), 256, 0, s>>>(D, T1t, Kp, V, Tq);
+}
+
+// ---- the same placement on a rank's column tiles (multi-GPU): X is np x (128 ntc), local tile t = global columns ktab[t].. ------
+// T1l holds Q'Y' for this rank's object-coordinate tiles only (the first ntp local tiles), leading dimension ldt
+__global__ void __launch_bounds__(256) k_place_cols(double *__restrict__ X, int64_t ldx, int ntc, const int32_t *__restrict__ ktab,
+                                                    StructDims D, const double *__restrict__ T1l, int64_t ldt,
+                                                    const double *__restrict__ Kp, int64_t row_end) {
+    const int64_t r = D.up + blockIdx.x;
+    if (r >= row_end) return;
+    const int64_t i = blockIdx.x;
+    double *row = X + r * ldx;
+    for (int64_t cl = threadIdx.x; cl < (int64_t)ntc * 128; cl += blockDim.x) {
+        const int64_t c = ktab[cl >> 7] + (cl & 127);
+        if (c > r) continue;
+        double v;
+        if (i < D.nc) v = c < D.up ? -T1l[i * ldt + cl] : Kp[i * D.mp + (c - D.up)];
+        else v = (c == r) ? 1.0 : 0.0;
+        row[cl] = v;
     }
+}
+
+__global__ void __launch_bounds__(128) k_add_point_blocks_cols(double *__restrict__ X, int64_t ldx, const int32_t *__restrict__ col_local,
+                                                               const int32_t *__restrict__ blk_start, const int32_t *__restrict__ blk_size,
+                                                               int nBlk, const double *__restrict__ Pinv) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nBlk) return;
+    const int64_t c0 = blk_start[b];
+    const int sz = blk_size[b];
+    for (int j = 0; j < sz; j++) {
+        const int64_t c = c0 + j;
+        const int t = col_local[c >> 7];
+        if (t < 0) continue;
+        for (int i = j; i < sz; i++) X[(c0 + i) * ldx + (int64_t)t * 128 + (c & 127)] += Pinv[(size_t)b * 9 + i * 3 + j];
+    }
+}
+
+void launch_structured_place_cols(double *X, int64_t ldx, int ntc, const int32_t *ktab, const int32_t *col_local, const StructDims &D,
+                                  const double *T1l, int64_t ldt, const double *Kp, const int32_t *blk_start, const int32_t *blk_size,
+                                  int nBlk, const double *Pinv, cudaStream_t s) {
+    if (ntc == 0) return;
+    int64_t row_end = D.Tp < D.np ? D.Tp : D.np;
+    if (row_end < D.u) row_end = D.u;
+    g_launch_count += 2;
+    k_place_cols<<<(unsigned)(row_end - D.up), 256, 0, s>>>(X, ldx, ntc, ktab, D, T1l, ldt, Kp, row_end);
+    k_add_point_blocks_cols<<<(unsigned)((nBlk + 127) / 128), 128, 0, s>>>(X, ldx, col_local, blk_start, blk_size, nBlk, Pinv);
 }
 
 }  // namespace jaicov

@@ -32,7 +32,9 @@ def main():
     adj, flat = flat_problem(scene)
     ids = [ba._lib.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
-    s = ba.Session(sigma2apriori=adj.getVarianceFactorApriori(), device=local)
+    solver = {'dense': ba._lib.SOLVER_DENSE, 'structured': ba._lib.SOLVER_STRUCTURED, 'auto': ba._lib.SOLVER_AUTO}[
+        sys.argv[2] if len(sys.argv) > 2 else 'auto']
+    s = ba.Session(sigma2apriori=adj.getVarianceFactorApriori(), device=local, solver=solver)
     s.dist_init(rank, world, ids[0])
     s.set_problem(flat)
     rc = s.estimate()
@@ -73,7 +75,7 @@ def main():
             act = (c >= 0) & (c < 2147483647)
             floor = np.sqrt(s2o * np.abs(np.diag(Qo))[c[act]])
             errx = max(errx, float((np.abs(vg[act] - vo[act]) / np.maximum(np.abs(vo[act]), floor)).max()))
-        print(json.dumps({'scene': which, 'world': world, 'rc': rc, 'rc_oracle': so, 'iterations': st.iterations,
+        print(json.dumps({'scene': which, 'world': world, 'solver_used': st.solver_used, 'rc': rc, 'rc_oracle': so, 'iterations': st.iterations,
                           'iterations_oracle': len(o.history), 'sigma2_rel_err': abs(st.sigma2aposteriori - s2o) / s2o,
                           'qxx_scaled_err': errq, 'param_rel_err': errx, 'qxx_local_vs_block_maxabs': float(le[0]), 'ms_last_pass': st.ms_total,
                           'ms_factor': st.ms_factor, 'ms_inverse': st.ms_inverse}), flush=True)

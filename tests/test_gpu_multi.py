@@ -22,16 +22,19 @@ def _ngpu():
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason='needs two GPUs')
-@pytest.mark.parametrize('which', ['example', 'cfg2', 'cfg3', 'cfg4'])
-def test_two_gpu_adjustment_matches_oracle(built, which):
+@pytest.mark.parametrize('which,solver', [('example', 'auto'), ('cfg2', 'dense'), ('cfg2', 'structured'), ('cfg3', 'auto'),
+                                          ('cfg4', 'dense'), ('cfg4', 'structured')])
+def test_two_gpu_adjustment_matches_oracle(built, which, solver):
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
-           '--master-port', '29531', os.path.join(ROOT, 'tests', 'multi_worker.py'), which]
+           '--master-port', '29531', os.path.join(ROOT, 'tests', 'multi_worker.py'), which, solver]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     line = [l for l in out.stdout.splitlines() if l.startswith('{')][-1]
     r = json.loads(line)
     print(r)
     assert r['rc'] == r['rc_oracle'] == 1
+    if solver != 'auto':
+        assert r['solver_used'] == {'dense': 1, 'structured': 2}[solver]
     assert r['iterations'] == r['iterations_oracle']
     assert r['sigma2_rel_err'] <= 1e-8
     assert r['qxx_scaled_err'] <= 1e-8
