@@ -27,7 +27,7 @@ EXPORTS = [
     'jaicov_set_scale_bars', 'jaicov_add_observed_group', 'jaicov_set_datum', 'jaicov_set_reduced_rows', 'jaicov_estimate', 'jaicov_iterate',
     'jaicov_get_stats', 'jaicov_get_values', 'jaicov_get_dx', 'jaicov_get_qxx_packed', 'jaicov_get_qxx_block',
     'jaicov_get_qxx_diag', 'jaicov_get_qxx_submatrix', 'jaicov_eval_residual_jacobian', 'jaicov_get_normal_equations', 'jaicov_omega',
-    'jaicov_spd_solve_invert',
+    'jaicov_spd_solve_invert', 'jaicov_propagate_eo_transform',
 ]
 
 
@@ -93,6 +93,7 @@ def load():
     L.jaicov_get_qxx_diag.argtypes = [vp, vp]
     L.jaicov_get_qxx_submatrix.argtypes = [vp, i32, vp, dbl, vp]
     L.jaicov_eval_residual_jacobian.argtypes = [vp, i32, vp, vp, vp]
+    L.jaicov_propagate_eo_transform.argtypes = [vp, i32, vp, vp, vp, dbl, vp, vp]
     L.jaicov_get_normal_equations.argtypes = [vp, vp, vp]
     L.jaicov_omega.argtypes = [vp, vp, ctypes.POINTER(dbl)]
     L.jaicov_spd_solve_invert.argtypes = [i32, i64, vp, i32, vp, i32, ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
@@ -274,6 +275,17 @@ class Session:
         out = np.empty((idx.size, idx.size))
         self.check(self.L.jaicov_get_qxx_submatrix(self.h, idx.size, _p(idx), float(scale), _p(out)))
         return out
+
+    def propagate_eo_transform(self, point, src_image, trg_image, sigma2, covariance=True):
+        """Transformed coordinates (R, 3) and the packed upper covariance sigma2 * J Qxx J' of the triples
+        (point, source image, target image); see jaicov_propagate_eo_transform."""
+        point, src_image, trg_image = _i32(point), _i32(src_image), _i32(trg_image)
+        n = point.size
+        xyz = np.empty((n, 3))
+        cov = np.empty(3 * n * (3 * n + 1) // 2) if covariance else None
+        self.check(self.L.jaicov_propagate_eo_transform(self.h, n, _p(point), _p(src_image), _p(trg_image), float(sigma2),
+                                                        _p(xyz), _p(cov) if covariance else None))
+        return xyz, cov
 
     def qxx_diag(self):
         out = np.empty(self.n_qxx)

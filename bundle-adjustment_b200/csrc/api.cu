@@ -30,7 +30,7 @@ void launch_solve_rows8(const double *L, int64_t ld, const double *dinv, double 
 void launch_precond_diag(const double *M, int64_t ld, int u, int64_t np, double *V, cudaStream_t s);
 void launch_datum_rows(const double *xyz, const int32_t *pt_col, const int32_t *datum_pts, int nDatum, int free_mask, int d,
                        int64_t np, double *Bt, cudaStream_t s);
-void launch_scale_system(double *M, int64_t ld, int u, const double *V, const double *Bt, int d, int64_t np, cudaStream_t s);
+void launch_scale_system(double *M, int64_t ld, int u, const double *V, const double *Bt, int d, int64_t np, int64_t row0, cudaStream_t s);
 void launch_build_rhs(double *Rt, double *Btv, int64_t np, int u, const double *V, const double *rhs, const double *Bt, int d,
                       int simulation, cudaStream_t s);
 void launch_datum_solve(const double *Xt, const double *Btv, int d, int64_t np, int u, const double *V, double *dxref, double *H,
@@ -60,6 +60,10 @@ void launch_get_submatrix(const double *lower, int64_t ld, const double *X, int6
                           int n_cols, double scale, double *out, cudaStream_t s);
 void launch_get_block_dist(const double *X, int64_t ldx, const int32_t *col_local, const double *border, int64_t np,
                            const double *q11, int d, int rank, int r0, int r1, int c0, int c1, double *out, cudaStream_t s);
+
+void launch_propagate(const double *lower, int64_t ld, const double *X, int64_t ldx, const int32_t *col_local, const double *border,
+                      int64_t np, const double *q11, int d, int rank, int nT, const double *Jv, const int32_t *Jc, double sigma2,
+                      double *out, cudaStream_t s);
 
 struct CudaBackend {
     cudaStream_t stream;
@@ -602,11 +606,18 @@ void prepare(jaicov_handle *h) {
 }
 
 // stages 1-2 of one pass: N, n of the current values in M (lower) / rhs, datum rows in Bt
-void assemble(jaicov_handle *h) {
+// (sparse_clear: the structured route clears only the point blocks and the rows of the camera / image unknowns)
+void assemble(jaicov_handle *h, bool sparse_clear = false) {
     const DevProblem &P = h->P;
     cudaStream_t s = h->stream;
     const size_t np = (size_t)P.np;
-    JCHECK(cudaMemsetAsync(h->M.p, 0, np * np * sizeof(double), s));
+    if (sparse_clear && h->st.on) {
+        const size_t up = (size_t)h->st.D.up;
+        JCHECK(cudaMemsetAsync(h->M.p + up * np, 0, (np - up) * np * sizeof(double), s));
+        launch_zero_point_blocks(h->M.p, P.np, h->st.blk_start.p, h->st.blk_size.p, h->st.nBlk, s);
+    } else {
+        JCHECK(cudaMemsetAsync(h->M.p, 0, np * np * sizeof(double), s));
+    }
     JCHECK(cudaMemsetAsync(h->rhs.p, 0, np * sizeof(double), s));
     JCHECK(cudaMemsetAsync(h->Bt.p, 0, 8 * np * sizeof(double), s));
     launch_pose(P, s);
@@ -668,7 +679,7 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     const size_t np = (size_t)P.np;
     const bool invert = final_pass && h->wants_inverse();
     JCHECK(cudaEventRecord(h->ev[0], s));
-    assemble(h);
+    assemble(h, true);
     // Levenberg-Marquardt: N_cc += lambda N_cc on every unknown column, before the preconditioner (BA:801-822)
     if (h->derive_first_damping) {
         h->adapted_damping = h->opt.damping_value;
@@ -678,7 +689,7 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     // preconditioner and SPD reformulation (K4)
     launch_precond_diag(h->M.p, P.np, P.u, P.np, h->V.p, s);
     // (the structured route keeps the datum rows as a border of its reduced system instead of folding B'B into N)
-    launch_scale_system(h->M.p, P.np, P.u, h->V.p, h->Bt.p, h->st.on ? 0 : P.d, P.np, s);
+    launch_scale_system(h->M.p, P.np, P.u, h->V.p, h->Bt.p, h->st.on ? 0 : P.d, P.np, h->st.on ? h->st.D.up : 0, s);
     JCHECK(cudaMemsetAsync(h->Rt.p, 0, (size_t)kRhsRows * np * sizeof(double), s));
     launch_build_rhs(h->Rt.p, h->Btv.p, P.np, P.u, h->V.p, h->rhs.p, h->Bt.p, P.d, h->opt.estimation_type == JAICOV_SIMULATION, s);
     h->have_neq = false;
@@ -692,14 +703,22 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     if (st.on) {
         // reduced system K' = [[R, B_r'],[B_r, 0]] - Z'Y and its inverse Q' (structured.cu)
         const StructDims &D = st.D;
-        launch_point_block_inv(h->M.p, P.np, st.blk_start.p, st.blk_size.p, st.nBlk, st.Pinv.p, h->info.p, s);
+        launch_point_block_inv(h->M.p, P.np, st.blk_start.p, st.blk_size.p, st.nBlk, h->V.p, st.Pinv.p, h->info.p, s);
         launch_build_zy(h->M.p, h->Btv.p, D, st.col_blk.p, st.blk_start.p, st.blk_size.p, st.Pinv.p, st.Zt.p, st.Yt.p, s);
-        launch_init_kp(h->M.p, h->Btv.p, D, st.Kp.p, s);
         {
-            GemmDesc g;
-            g.al = 0; g.bl = 0; g.mt = g.nt = (int)(D.mp / kBlk); g.K = D.Tp; g.alpha = -1.0; g.beta = 1.0;
-            g.A = st.Zt.p; g.lda = D.Tp; g.B = st.Yt.p; g.ldb = D.Tp; g.C = st.Kp.p; g.ldc = D.mp; g.tri_out = 1;
-            be.gemm(g);
+            // Z'Y contracts over the object coordinates: with several GPUs every rank takes a slice of that range and the
+            // m x m partial products are summed (GEMM -> all-reduce; the result is bitwise the same on every rank)
+            const int64_t nkt = D.Tp / kBlk;
+            const int64_t kt0 = multi ? h->dist.rank * nkt / h->dist.world : 0, kt1 = multi ? (h->dist.rank + 1) * nkt / h->dist.world : nkt;
+            if (!multi || h->dist.rank == 0) launch_init_kp(h->M.p, h->Btv.p, D, st.Kp.p, s);
+            else JCHECK(cudaMemsetAsync(st.Kp.p, 0, (size_t)D.mp * D.mp * sizeof(double), s));
+            if (kt1 > kt0) {
+                GemmDesc g;
+                g.al = 0; g.bl = 0; g.mt = g.nt = (int)(D.mp / kBlk); g.K = (kt1 - kt0) * kBlk; g.alpha = -1.0; g.beta = 1.0;
+                g.A = st.Zt.p + kt0 * kBlk; g.lda = D.Tp; g.B = st.Yt.p + kt0 * kBlk; g.ldb = D.Tp; g.C = st.Kp.p; g.ldc = D.mp; g.tri_out = 1;
+                be.gemm(g);
+            }
+            if (multi) h->dist.allreduce_sum(st.Kp.p, (size_t)D.mp * D.mp, s);
         }
         if (D.d > 0) launch_border_prep(st.Kp.p, D, st.Eb.p, st.ED.p, h->small.p, s);
         launch_form_stilde(st.Kp.p, D, st.Eb.p, st.ED.p, st.Sm.p, s);
@@ -765,6 +784,7 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
         if (ntc > 0) {
             const int64_t ldx = (int64_t)ntc * kBlk, ldt = (int64_t)std::max(ntp, 1) * kBlk;
             JCHECK(cudaMemsetAsync(h->Xl.p, 0, np * (size_t)ldx * sizeof(double), s));
+            launch_scale_yt(st.Yt.p, D, h->V.p, s);
             if (ntp > 0) {
                 GemmDesc g;
                 g.al = 0; g.bl = 1; g.mt = (int)(D.mp / kBlk); g.nt = ntp; g.K = D.mp; g.alpha = 1.0; g.beta = 0.0;
@@ -778,12 +798,13 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
                 be.gemm(q);
             }
             launch_structured_place_cols(h->Xl.p, ldx, ntc, h->d_ktab.p, h->d_col_local.p, D, st.T1t.p, ldt, st.Kp.p, st.blk_start.p,
-                                         st.blk_size.p, st.nBlk, st.Pinv.p, s);
-            launch_qxx_epilogue_cols(h->Xl.p, ldx, ntc, h->d_ktab.p, P.u, h->V.p, h->H.p, h->Rt.p + np, 0, P.np, s);
+                                         st.blk_size.p, st.nBlk, st.Pinv.p, h->V.p, s);
         }
     } else if (invert && st.on) {
         // K^-1[p, r|lambda] = -(Q' Y')', K^-1[p, p] = P^-1 + Y (Q' Y'): two tensor-core products, then placement and V scaling
+        // (Yt is scaled by V first, so both products carry the V (.) V scaling of K7 and no pass over the 16 GB result is needed)
         const StructDims &D = st.D;
+        launch_scale_yt(st.Yt.p, D, h->V.p, s);
         GemmDesc g;
         g.al = 0; g.bl = 1; g.mt = (int)(D.mp / kBlk); g.nt = (int)(D.Tp / kBlk); g.K = D.mp; g.alpha = 1.0; g.beta = 0.0;
         g.A = st.Kp.p; g.lda = D.mp; g.B = st.Yt.p; g.ldb = D.Tp; g.C = st.T1t.p; g.ldc = D.Tp;
@@ -792,8 +813,7 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
         q.al = 1; q.bl = 1; q.mt = q.nt = (int)(D.Tp / kBlk); q.K = D.mp; q.alpha = 1.0; q.beta = 0.0;
         q.A = st.Yt.p; q.lda = D.Tp; q.B = st.T1t.p; q.ldb = D.Tp; q.C = h->M.p; q.ldc = P.np; q.tri_out = 1;
         be.gemm(q);
-        launch_structured_place(h->M.p, D, st.T1t.p, st.Kp.p, st.blk_start.p, st.blk_size.p, st.nBlk, st.Pinv.p, s);
-        launch_qxx_epilogue(h->M.p, P.np, P.u, h->V.p, h->H.p, h->Rt.p + np, 0, P.np, s);
+        launch_structured_place(h->M.p, D, st.T1t.p, st.Kp.p, st.blk_start.p, st.blk_size.p, st.nBlk, st.Pinv.p, h->V.p, s);
     } else if (invert && h->dist_on) {
         // every rank inverts its own column tiles from the replicated factor: no communication
         const int ntc = (int)h->ktab.size();
@@ -1383,6 +1403,107 @@ int32_t jaicov_get_qxx_local(jaicov_handle *h, int32_t *n_tiles, int32_t *tile_f
         JCHECK(cudaStreamSynchronize(s));
         cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
     }
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+// ---- covariance propagation of transformed coordinates ------------------------------------------------------
+namespace {
+
+// R = Rx(omega) Ry(phi) Rz(kappa), the rotation of ExteriorOrientation as written out in
+// CoordinateTransformationExteriorOrientation.java:172-184, and its derivatives with respect to the three angles
+void rotation_with_derivatives(double om, double ph, double ka, double R[3][3], double dR[3][3][3]) {
+    const double so = std::sin(om), co = std::cos(om), sp = std::sin(ph), cp = std::cos(ph), sk = std::sin(ka), ck = std::cos(ka);
+    const double Rx[3][3] = {{1, 0, 0}, {0, co, -so}, {0, so, co}}, dRx[3][3] = {{0, 0, 0}, {0, -so, -co}, {0, co, -so}};
+    const double Ry[3][3] = {{cp, 0, sp}, {0, 1, 0}, {-sp, 0, cp}}, dRy[3][3] = {{-sp, 0, cp}, {0, 0, 0}, {-cp, 0, -sp}};
+    const double Rz[3][3] = {{ck, -sk, 0}, {sk, ck, 0}, {0, 0, 1}}, dRz[3][3] = {{-sk, -ck, 0}, {ck, -sk, 0}, {0, 0, 0}};
+    auto mul3 = [](const double A[3][3], const double B[3][3], const double C[3][3], double out[3][3]) {
+        double T[3][3];
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) T[i][j] = A[i][0] * B[0][j] + A[i][1] * B[1][j] + A[i][2] * B[2][j];
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) out[i][j] = T[i][0] * C[0][j] + T[i][1] * C[1][j] + T[i][2] * C[2][j];
+    };
+    mul3(Rx, Ry, Rz, R);
+    mul3(dRx, Ry, Rz, dR[0]);
+    mul3(Rx, dRy, Rz, dR[1]);
+    mul3(Rx, Ry, dRz, dR[2]);
+}
+
+}  // namespace
+
+int32_t jaicov_propagate_eo_transform(jaicov_handle *h, int32_t n_points, const int32_t *point, const int32_t *src_image,
+                                      const int32_t *trg_image, double sigma2, double *xyz_out, double *cov_packed) {
+    if (!h || n_points < 0 || (n_points > 0 && (!point || !src_image || !trg_image))) return JAICOV_ILLEGAL_ARGUMENT;
+    if (cov_packed && !h->have_qxx) return fail(h, JAICOV_NOT_INITIALISED, "no cofactor matrix: run a final pass with invert_mode FULL");
+    const int nPt = (int)(h->xyz.size() / 3), nImg = (int)(h->eo_val.size() / 6);
+    for (int i = 0; i < n_points; i++)
+        if (point[i] < 0 || point[i] >= nPt || src_image[i] < 0 || src_image[i] >= nImg || trg_image[i] < 0 || trg_image[i] >= nImg)
+            return fail(h, JAICOV_ILLEGAL_ARGUMENT, "point or image index out of range");
+    if (n_points == 0) return JAICOV_OK;
+    API_GUARD_BEGIN
+    JCHECK(cudaSetDevice(h->opt.device));
+    if (h->prepared) download_values(h);       // jaicov_iterate users: the host copies follow the device values
+    const int nq = h->qxx_rows();
+    // X_trg = X0_trg + R_trg R_src' (X - X0_src)  (:209-215) and its Jacobian with respect to
+    // [X0_trg, angles_trg, X0_src, angles_src, X] (:223-279), on the host copies of the adjusted values
+    std::vector<double> Jv((size_t)n_points * 45, 0.0);
+    std::vector<int32_t> Jc((size_t)n_points * 15, -1);
+    auto col_or_skip = [&](int32_t c) { return (active(c) && c < nq) ? c : -1; };
+    for (int i = 0; i < n_points; i++) {
+        const double *X = &h->xyz[3 * (size_t)point[i]];
+        double *J = &Jv[(size_t)i * 45];
+        int32_t *C = &Jc[(size_t)i * 15];
+        for (int k = 0; k < 3; k++) C[12 + k] = col_or_skip(h->pt_col[3 * (size_t)point[i] + k]);
+        if (src_image[i] == trg_image[i]) {     // the reference image itself: identity (:141-149)
+            for (int k = 0; k < 3; k++) {
+                J[k * 15 + 12 + k] = 1.0;
+                if (xyz_out) xyz_out[3 * (size_t)i + k] = X[k];
+            }
+            continue;
+        }
+        const double *eT = &h->eo_val[6 * (size_t)trg_image[i]], *eS = &h->eo_val[6 * (size_t)src_image[i]];
+        for (int k = 0; k < 6; k++) {
+            C[k] = col_or_skip(h->eo_col[6 * (size_t)trg_image[i] + k]);
+            C[6 + k] = col_or_skip(h->eo_col[6 * (size_t)src_image[i] + k]);
+        }
+        double RT[3][3], dRT[3][3][3], RS[3][3], dRS[3][3][3];
+        rotation_with_derivatives(eT[3], eT[4], eT[5], RT, dRT);
+        rotation_with_derivatives(eS[3], eS[4], eS[5], RS, dRS);
+        const double dv[3] = {X[0] - eS[0], X[1] - eS[1], X[2] - eS[2]};
+        double q[3], M3[3][3];
+        for (int a = 0; a < 3; a++) q[a] = RS[0][a] * dv[0] + RS[1][a] * dv[1] + RS[2][a] * dv[2];        // R_src' d
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) M3[r][c] = RT[r][0] * RS[c][0] + RT[r][1] * RS[c][1] + RT[r][2] * RS[c][2];   // R_trg R_src'
+        for (int r = 0; r < 3; r++) {
+            if (xyz_out) xyz_out[3 * (size_t)i + r] = eT[r] + RT[r][0] * q[0] + RT[r][1] * q[1] + RT[r][2] * q[2];
+            J[r * 15 + r] = 1.0;                                                                               // d / d X0_trg
+            for (int a = 0; a < 3; a++) {
+                J[r * 15 + 3 + a] = dRT[a][r][0] * q[0] + dRT[a][r][1] * q[1] + dRT[a][r][2] * q[2];         // d / d angle_trg
+                J[r * 15 + 6 + a] = -M3[r][a];                                                                 // d / d X0_src
+                double s = 0.0;                                                                                // d / d angle_src
+                for (int k = 0; k < 3; k++) {
+                    const double qa = dRS[a][0][k] * dv[0] + dRS[a][1][k] * dv[1] + dRS[a][2][k] * dv[2];    // (dR_src' d)_k
+                    s += RT[r][k] * qa;
+                }
+                J[r * 15 + 9 + a] = s;
+                J[r * 15 + 12 + a] = M3[r][a];                                                                 // d / d X
+            }
+        }
+    }
+    if (!cov_packed) return JAICOV_OK;
+    DevBuf<double> dJ, dout;
+    DevBuf<int32_t> dC;
+    dJ.upload(Jv);
+    dC.upload(Jc);
+    const int64_t n3 = 3 * (int64_t)n_points, npk = n3 * (n3 + 1) / 2;
+    dout.alloc((size_t)npk);
+    launch_propagate(h->dist_on ? nullptr : h->M.p, h->P.np, h->dist_on ? h->Xl.p : nullptr, (int64_t)h->ktab.size() * kBlk,
+                     h->dist_on ? h->d_col_local.p : nullptr, h->Tq.p, h->P.np, h->small.p + 49, h->P.d,
+                     h->dist_on ? h->dist.rank : 0, n_points, dJ.p, dC.p, sigma2, dout.p, h->stream);
+    JCHECK(cudaGetLastError());
+    JCHECK(cudaMemcpyAsync(cov_packed, dout.p, (size_t)npk * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    JCHECK(cudaStreamSynchronize(h->stream));
     return JAICOV_OK;
     API_GUARD_END(h)
 }

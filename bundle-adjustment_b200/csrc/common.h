@@ -128,8 +128,10 @@ struct StructDims {
     int64_t ncp;   // nc padded to a multiple of 128 (leading dimension of Sm)
     int64_t np;    // leading dimension of M, Btv, Tq
 };
-void launch_point_block_inv(const double *M, int64_t ld, const int32_t *blk_start, const int32_t *blk_size, int nBlk, double *Pinv,
-                            int *info, cudaStream_t s);
+void launch_point_block_inv(const double *M, int64_t ld, const int32_t *blk_start, const int32_t *blk_size, int nBlk, const double *V,
+                            double *Pinv, int *info, cudaStream_t s);
+void launch_zero_point_blocks(double *M, int64_t ld, const int32_t *blk_start, const int32_t *blk_size, int nBlk, cudaStream_t s);
+void launch_scale_yt(double *Yt, const StructDims &D, const double *V, cudaStream_t s);
 void launch_build_zy(const double *M, const double *Btv, const StructDims &D, const int32_t *col_blk, const int32_t *blk_start,
                      const int32_t *blk_size, const double *Pinv, double *Zt, double *Yt, cudaStream_t s);
 void launch_init_kp(const double *M, const double *Btv, const StructDims &D, double *Kp, cudaStream_t s);
@@ -142,9 +144,9 @@ void launch_structured_solution(const double *nrm, const StructDims &D, const in
                                 const double *Btv, const double *V, double *zp, double *rp, double *yr, double *ys, double *Nt,
                                 double *t, double *dxref, double *Tq, cudaStream_t s);
 void launch_structured_place(double *M, const StructDims &D, const double *T1t, const double *Kp, const int32_t *blk_start,
-                             const int32_t *blk_size, int nBlk, const double *Pinv, cudaStream_t s);
+                             const int32_t *blk_size, int nBlk, const double *Pinv, const double *V, cudaStream_t s);
 void launch_structured_place_cols(double *X, int64_t ldx, int ntc, const int32_t *ktab, const int32_t *col_local, const StructDims &D,
                                   const double *T1l, int64_t ldt, const double *Kp, const int32_t *blk_start, const int32_t *blk_size,
-                                  int nBlk, const double *Pinv, cudaStream_t s);
+                                  int nBlk, const double *Pinv, const double *V, cudaStream_t s);
 
 }  // namespace jaicov

@@ -101,8 +101,8 @@ void launch_datum_rows(const double *xyz, const int32_t *pt_col, const int32_t *
 
 // K4: M <- V M V + (B V)'(B V) on the lower triangle (NES:82-91 plus the SPD reformulation), identity on the padding
 __global__ void __launch_bounds__(256) k_scale_system(double *__restrict__ M, int64_t ld, int u, const double *__restrict__ V,
-                                                      const double *__restrict__ Bt, int d, int64_t np) {
-    const int64_t r = blockIdx.x;
+                                                      const double *__restrict__ Bt, int d, int64_t np, int64_t row0) {
+    const int64_t r = row0 + blockIdx.x;
     double *row = M + r * ld;
     if (r >= u) {
         for (int64_t c = threadIdx.x; c <= r; c += blockDim.x) row[c] = (c == r) ? 1.0 : 0.0;
@@ -122,9 +122,11 @@ __global__ void __launch_bounds__(256) k_scale_system(double *__restrict__ M, in
     }
 }
 
-void launch_scale_system(double *M, int64_t ld, int u, const double *V, const double *Bt, int d, int64_t np, cudaStream_t s) {
+// rows [row0, np) only (row0 > 0: the structured route scales its point blocks on the fly and never reads the rest of them)
+void launch_scale_system(double *M, int64_t ld, int u, const double *V, const double *Bt, int d, int64_t np, int64_t row0, cudaStream_t s) {
+    if (row0 >= np) return;
     g_launch_count++;
-    k_scale_system<<<(unsigned)np, 256, 0, s>>>(M, ld, u, V, Bt, d, np);
+    k_scale_system<<<(unsigned)(np - row0), 256, 0, s>>>(M, ld, u, V, Bt, d, np, row0);
 }
 
 // right-hand-side block (rows): Rt[0] = V n, Rt[1+a] = B[a] V, everything else zero (Rt is kRhsRows x np, zeroed by caller)

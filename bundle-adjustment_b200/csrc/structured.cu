@@ -26,14 +26,15 @@ namespace jaicov {
 // ---- point blocks: P_b^-1 by Cholesky of the <= 3 x 3 block --------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_point_block_inv(const double *__restrict__ M, int64_t ld, const int32_t *__restrict__ blk_start,
                                                          const int32_t *__restrict__ blk_size, int nBlk,
-                                                         double *__restrict__ Pinv, int *__restrict__ info) {
+                                                         const double *__restrict__ V, double *__restrict__ Pinv,
+                                                         int *__restrict__ info) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nBlk) return;
     const int64_t c0 = blk_start[b];
     const int sz = blk_size[b];
     double a[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-    for (int i = 0; i < sz; i++)
-        for (int j = 0; j <= i; j++) a[i][j] = M[(c0 + i) * ld + c0 + j];
+    for (int i = 0; i < sz; i++)    // the blocks of M hold N unscaled: apply the Jacobi scaling V N V here
+        for (int j = 0; j <= i; j++) a[i][j] = (V[c0 + i] * M[(c0 + i) * ld + c0 + j]) * V[c0 + j];
     // L L' = A
     double l[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     bool bad = false;
@@ -68,11 +69,41 @@ __global__ void __launch_bounds__(128) k_point_block_inv(const double *__restric
         }
 }
 
-void launch_point_block_inv(const double *M, int64_t ld, const int32_t *blk_start, const int32_t *blk_size, int nBlk, double *Pinv,
-                            int *info, cudaStream_t s) {
+void launch_point_block_inv(const double *M, int64_t ld, const int32_t *blk_start, const int32_t *blk_size, int nBlk, const double *V,
+                            double *Pinv, int *info, cudaStream_t s) {
     if (nBlk == 0) return;
     g_launch_count++;
-    k_point_block_inv<<<(unsigned)((nBlk + 127) / 128), 128, 0, s>>>(M, ld, blk_start, blk_size, nBlk, Pinv, info);
+    k_point_block_inv<<<(unsigned)((nBlk + 127) / 128), 128, 0, s>>>(M, ld, blk_start, blk_size, nBlk, V, Pinv, info);
+}
+
+// the structured route clears only what the assembly accumulates into: the point blocks (here) and the rows of the
+// camera / image unknowns (one memset); the rest of the object-point region of M is never read
+__global__ void __launch_bounds__(128) k_zero_point_blocks(double *__restrict__ M, int64_t ld, const int32_t *__restrict__ blk_start,
+                                                           const int32_t *__restrict__ blk_size, int nBlk) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nBlk) return;
+    const int64_t c0 = blk_start[b];
+    const int sz = blk_size[b];
+    for (int i = 0; i < sz; i++)
+        for (int j = 0; j <= i; j++) M[(c0 + i) * ld + c0 + j] = 0.0;
+}
+
+void launch_zero_point_blocks(double *M, int64_t ld, const int32_t *blk_start, const int32_t *blk_size, int nBlk, cudaStream_t s) {
+    if (nBlk == 0) return;
+    g_launch_count++;
+    k_zero_point_blocks<<<(unsigned)((nBlk + 127) / 128), 128, 0, s>>>(M, ld, blk_start, blk_size, nBlk);
+}
+
+// Yt[:, p] *= V[p]: with the scaled operand both products of the inverse come out as V (.) V directly
+__global__ void __launch_bounds__(256) k_scale_yt(double *__restrict__ Yt, StructDims D, const double *__restrict__ V) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= D.up) return;
+    Yt[(int64_t)blockIdx.y * D.Tp + p] *= V[p];
+}
+
+void launch_scale_yt(double *Yt, const StructDims &D, const double *V, cudaStream_t s) {
+    g_launch_count++;
+    k_scale_yt<<<dim3((unsigned)((D.up + 255) / 256), (unsigned)(D.nc + D.d)), 256, 0, s>>>(Yt, D, V);
 }
 
 // ---- Zt (m x Tp) = [C' ; B_p] and Yt = Zt P^-1 (block-wise); rows >= m and columns >= up are zero -----------------------------
@@ -452,15 +483,18 @@ void launch_structured_solution(const double *nrm, const StructDims &D, const in
 }
 
 // ---- placement of the inverse into M (lower, row-major): rows of the r group, identity padding, P^-1 on the point blocks -------
+// (T1t was formed from the V-scaled Yt: its columns carry V already; the row factor and the r-r block are scaled here)
 __global__ void __launch_bounds__(256) k_place_rows(double *__restrict__ M, StructDims D, const double *__restrict__ T1t,
-                                                    const double *__restrict__ Kp, int64_t row_end) {
+                                                    const double *__restrict__ Kp, const double *__restrict__ V, int64_t row_end) {
     const int64_t r = D.up + blockIdx.x;        // row of M
     if (r >= row_end) return;
     double *row = M + r * D.np;
     const int64_t i = blockIdx.x;
     if (i < D.nc) {
         const double *t = T1t + i * D.Tp;
-        for (int64_t c = threadIdx.x; c <= r; c += blockDim.x) row[c] = c < D.up ? -t[c] : Kp[i * D.mp + (c - D.up)];
+        const double vr = V[r];
+        for (int64_t c = threadIdx.x; c <= r; c += blockDim.x)
+            row[c] = c < D.up ? -t[c] * vr : (V[c] * Kp[i * D.mp + (c - D.up)]) * vr;
     } else {
         for (int64_t c = threadIdx.x; c <= r; c += blockDim.x) row[c] = (c == r) ? 1.0 : 0.0;
     }
@@ -468,38 +502,39 @@ __global__ void __launch_bounds__(256) k_place_rows(double *__restrict__ M, Stru
 
 __global__ void __launch_bounds__(128) k_add_point_blocks(double *__restrict__ M, int64_t ld, const int32_t *__restrict__ blk_start,
                                                           const int32_t *__restrict__ blk_size, int nBlk,
-                                                          const double *__restrict__ Pinv) {
+                                                          const double *__restrict__ Pinv, const double *__restrict__ V) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nBlk) return;
     const int64_t c0 = blk_start[b];
     const int sz = blk_size[b];
     for (int i = 0; i < sz; i++)
-        for (int j = 0; j <= i; j++) M[(c0 + i) * ld + c0 + j] += Pinv[(size_t)b * 9 + i * 3 + j];
+        for (int j = 0; j <= i; j++) M[(c0 + i) * ld + c0 + j] += (V[c0 + j] * Pinv[(size_t)b * 9 + i * 3 + j]) * V[c0 + i];
 }
 
 void launch_structured_place(double *M, const StructDims &D, const double *T1t, const double *Kp, const int32_t *blk_start,
-                             const int32_t *blk_size, int nBlk, const double *Pinv, cudaStream_t s) {
+                             const int32_t *blk_size, int nBlk, const double *Pinv, const double *V, cudaStream_t s) {
     int64_t row_end = D.Tp < D.np ? D.Tp : D.np;
     if (row_end < D.u) row_end = D.u;
     g_launch_count += 2;
-    k_place_rows<<<(unsigned)(row_end - D.up), 256, 0, s>>>(M, D, T1t, Kp, row_end);
-    k_add_point_blocks<<<(unsigned)((nBlk + 127) / 128), 128, 0, s>>>(M, D.np, blk_start, blk_size, nBlk, Pinv);
+    k_place_rows<<<(unsigned)(row_end - D.up), 256, 0, s>>>(M, D, T1t, Kp, V, row_end);
+    k_add_point_blocks<<<(unsigned)((nBlk + 127) / 128), 128, 0, s>>>(M, D.np, blk_start, blk_size, nBlk, Pinv, V);
 }
 
 // ---- the same placement on a rank's column tiles (multi-GPU): X is np x (128 ntc), local tile t = global columns ktab[t].. ------
 // T1l holds Q'Y' for this rank's object-coordinate tiles only (the first ntp local tiles), leading dimension ldt
 __global__ void __launch_bounds__(256) k_place_cols(double *__restrict__ X, int64_t ldx, int ntc, const int32_t *__restrict__ ktab,
                                                     StructDims D, const double *__restrict__ T1l, int64_t ldt,
-                                                    const double *__restrict__ Kp, int64_t row_end) {
+                                                    const double *__restrict__ Kp, const double *__restrict__ V, int64_t row_end) {
     const int64_t r = D.up + blockIdx.x;
     if (r >= row_end) return;
     const int64_t i = blockIdx.x;
     double *row = X + r * ldx;
+    const double vr = i < D.nc ? V[r] : 0.0;
     for (int64_t cl = threadIdx.x; cl < (int64_t)ntc * 128; cl += blockDim.x) {
         const int64_t c = ktab[cl >> 7] + (cl & 127);
         if (c > r) continue;
         double v;
-        if (i < D.nc) v = c < D.up ? -T1l[i * ldt + cl] : Kp[i * D.mp + (c - D.up)];
+        if (i < D.nc) v = c < D.up ? -T1l[i * ldt + cl] * vr : (V[c] * Kp[i * D.mp + (c - D.up)]) * vr;
         else v = (c == r) ? 1.0 : 0.0;
         row[cl] = v;
     }
@@ -507,7 +542,8 @@ __global__ void __launch_bounds__(256) k_place_cols(double *__restrict__ X, int6
 
 __global__ void __launch_bounds__(128) k_add_point_blocks_cols(double *__restrict__ X, int64_t ldx, const int32_t *__restrict__ col_local,
                                                                const int32_t *__restrict__ blk_start, const int32_t *__restrict__ blk_size,
-                                                               int nBlk, const double *__restrict__ Pinv) {
+                                                               int nBlk, const double *__restrict__ Pinv,
+                                                               const double *__restrict__ V) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nBlk) return;
     const int64_t c0 = blk_start[b];
@@ -516,19 +552,20 @@ __global__ void __launch_bounds__(128) k_add_point_blocks_cols(double *__restric
         const int64_t c = c0 + j;
         const int t = col_local[c >> 7];
         if (t < 0) continue;
-        for (int i = j; i < sz; i++) X[(c0 + i) * ldx + (int64_t)t * 128 + (c & 127)] += Pinv[(size_t)b * 9 + i * 3 + j];
+        for (int i = j; i < sz; i++)
+            X[(c0 + i) * ldx + (int64_t)t * 128 + (c & 127)] += (V[c] * Pinv[(size_t)b * 9 + i * 3 + j]) * V[c0 + i];
     }
 }
 
 void launch_structured_place_cols(double *X, int64_t ldx, int ntc, const int32_t *ktab, const int32_t *col_local, const StructDims &D,
                                   const double *T1l, int64_t ldt, const double *Kp, const int32_t *blk_start, const int32_t *blk_size,
-                                  int nBlk, const double *Pinv, cudaStream_t s) {
+                                  int nBlk, const double *Pinv, const double *V, cudaStream_t s) {
     if (ntc == 0) return;
     int64_t row_end = D.Tp < D.np ? D.Tp : D.np;
     if (row_end < D.u) row_end = D.u;
     g_launch_count += 2;
-    k_place_cols<<<(unsigned)(row_end - D.up), 256, 0, s>>>(X, ldx, ntc, ktab, D, T1l, ldt, Kp, row_end);
-    k_add_point_blocks_cols<<<(unsigned)((nBlk + 127) / 128), 128, 0, s>>>(X, ldx, col_local, blk_start, blk_size, nBlk, Pinv);
+    k_place_cols<<<(unsigned)(row_end - D.up), 256, 0, s>>>(X, ldx, ntc, ktab, D, T1l, ldt, Kp, V, row_end);
+    k_add_point_blocks_cols<<<(unsigned)((nBlk + 127) / 128), 128, 0, s>>>(X, ldx, col_local, blk_start, blk_size, nBlk, Pinv, V);
 }
 
 }  // namespace jaicov

@@ -358,6 +358,18 @@ class Image:
         else:
             self._chunks.append([objectCoordinate._store, [objectCoordinate._i], [(xp, yp)], [(sigmax, sigmay)], [corrCoefXY]])
 
+    def get(self, objectCoordinate):
+        """camera/Image.java:77-79: the image coordinate of an object point, or None if the point is not observed here."""
+        if getattr(self, '_lookup_n', -1) != len(self._chunks):
+            self._lookup = {}
+            for (store, idx, xy_c, _sg, _rh) in self._chunks:
+                for k, i in enumerate(np.asarray(idx, np.int64).tolist()):
+                    self._lookup.setdefault((id(store), i), tuple(np.asarray(xy_c, float).reshape(-1, 2)[k]))
+            self._lookup_n = len(self._chunks)
+            if self._chunks and isinstance(self._chunks[-1][1], list):
+                self._lookup_n = -1            # an open add() chunk may still grow: rebuild next time
+        return self._lookup.get((id(objectCoordinate._store), objectCoordinate._i))
+
     def addAll(self, objectCoordinates, indices, xy, sigma, rho=None):
         """Bulk form of add(): points ``objectCoordinates[indices[k]]`` (distinct) observed at xy[k] with sigma[k], rho[k]."""
         indices = np.asarray(indices, np.int64)
@@ -442,8 +454,9 @@ class UpperSymmPackMatrix:
     """Read-only stand-in for no.uib.cipr.matrix.UpperSymmPackMatrix holding Qxx: column-major packed upper,
     element (r,c), r<=c, at r + c(c+1)/2."""
 
-    def __init__(self, n, data):
+    def __init__(self, n, data, adjustment=None):
         self._n, self._data = n, data
+        self._adjustment = adjustment      # the BundleAdjustment whose device-resident Qxx this is a host copy of
 
     def numRows(self): return self._n
     def numColumns(self): return self._n
@@ -461,6 +474,49 @@ class UpperSymmPackMatrix:
         D[iu] = self._data[iu[0] + iu[1] * (iu[1] + 1) // 2]
         D.T[iu] = D[iu]
         return D
+
+
+class CoordinateTransformationExteriorOrientation:
+    """tranformation/CoordinateTransformationExteriorOrientation.java: object points carried into the frame of a reference
+    image, X_trg = X0_trg + R_trg R_src' (X - X0_src), with the propagated covariance sigma2 * J Qxx J' (:49-121).
+    The contraction with Qxx runs on the device that holds it (jaicov_propagate_eo_transform); CoVar must be the matrix
+    handed out by BundleAdjustment.getCofactorMatrix()."""
+    _instance = None
+
+    @classmethod
+    def getInstance(cls):
+        if cls._instance is None:
+            cls._instance = cls()
+        return cls._instance
+
+    def __init__(self):
+        self._covariance, self._transformed = None, []
+
+    def transform(self, objectCoordinatesToTransform, imagesToAlign, sigma2, CoVar):
+        adj = getattr(CoVar, '_adjustment', None)
+        if adj is None or adj._session is None:
+            raise _lib.JaicovError(_lib.NOT_INITIALISED, 'CoVar is not the cofactor matrix of a finished adjustment on the device')
+        points, src, trg, names = [], [], [], []
+        for referenceImage, images in imagesToAlign.items():              # :81-105
+            for image in images:
+                for oc in objectCoordinatesToTransform:
+                    if image.get(oc) is None:                            # skip points not visible in the current image, :91-95
+                        continue
+                    points.append(adj._store_base[id(oc._store)] + oc._i)
+                    src.append(adj._image_index[id(image)])
+                    trg.append(adj._image_index[id(referenceImage)])
+                    names.append('%s %s %s' % (oc.getName(), image.getId(), referenceImage.getId()))   # :103
+        xyz, cov = adj._session.propagate_eo_transform(points, src, trg, sigma2)
+        self._transformed = []
+        for k, name in enumerate(names):
+            t = ObjectCoordinate(name, *xyz[k])
+            t.getX().setColumn(3 * k); t.getY().setColumn(3 * k + 1); t.getZ().setColumn(3 * k + 2)   # :146-148, :217-219
+            self._transformed.append(t)
+        self._covariance = UpperSymmPackMatrix(3 * len(names), cov)
+        self._triples = (points, src, trg)
+
+    def getCovarianceMatrix(self): return self._covariance
+    def getTransformedCoordinates(self): return self._transformed
 
 
 # ---- the adjustment ---------------------------------------------------------------------------------------------------
@@ -548,7 +604,7 @@ class BundleAdjustment:
                 full = np.zeros(n * (n + 1) // 2)
                 full[:data.size] = data
                 data = full
-            self._Qxx = UpperSymmPackMatrix(n, data)
+            self._Qxx = UpperSymmPackMatrix(n, data, self)
         return self._Qxx
 
     # ---- prepareUnknownParameters, :667-782, and detectRankDefect, :836-1042 ---------------------------------------
@@ -796,6 +852,7 @@ class BundleAdjustment:
             bar_var=np.array(bar_var, float), groups=groups, free_flags=np.array(free_flags, np.int32),
             n_unknowns=counter, n_observations=numObs)
         self._flat_ctx = (stores, cam_params, eo_params)
+        self._store_base, self._image_index = dict(base), {id(img): k for k, img in enumerate(images)}
         return flat
 
     @staticmethod

@@ -226,6 +226,18 @@ int32_t jaicov_get_qxx_submatrix(jaicov_handle *h, int32_t n_idx, const int32_t 
 int32_t jaicov_get_qxx_diag(jaicov_handle *h, double *dst);
 
 /* ---- stage access for parity tests and profiling (same kernels the loop uses) ---------------------------------- */
+/* Covariance propagation of object points transformed into the frame of a reference image, replacing
+ * CoordinateTransformationExteriorOrientation.transform (tranformation/CoordinateTransformationExteriorOrientation.java:49-121):
+ * for every triple (point, source image, target image)  X_trg = X0_trg + R_trg R_src' (X - X0_src)  (:209-215; source ==
+ * target: identity, :141-149), J = d X_trg / d (EO_trg, EO_src, X)  (:223-279) and
+ *   cov = sigma2 * J Qxx J'   (:110-114), packed upper like MTJ's UpperSymmPackMatrix, (3 n_points)(3 n_points + 1)/2 doubles.
+ * The caller enumerates the triples (the visibility loops of :57-98 stay on the host side); point / image indices are those
+ * of jaicov_set_object_points / jaicov_set_images; fixed parameters contribute nothing.  Qxx is contracted where it lives
+ * (15 x 15 gathers per 3 x 3 block); needs a final pass with a cofactor matrix.  xyz_out (3 n_points) or cov_packed may be
+ * NULL.  Multi-GPU handles return the rank's partial sums (the sum over ranks is cov). */
+int32_t jaicov_propagate_eo_transform(jaicov_handle *h, int32_t n_points, const int32_t *point, const int32_t *src_image,
+                                      const int32_t *trg_image, double sigma2, double *xyz_out, double *cov_packed);
+
 /* K1: residuals and compact Jacobian of every image point at the current values.  Per point j the 2 x ns
  * entries are written slot-ordered: slots 0..11 = X,Y,Z,x0,y0,c,X0,Y0,Z0,omega,phi,kappa, slots 12.. = the
  * coefficients of the point's camera in list order; ns_max = 12 + max coefficients per camera.
