@@ -362,6 +362,10 @@ def main():
     hbm = json.load(open(peaks_file)).get('hbm_gbs') if os.path.exists(peaks_file) else 6650.0
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak * world, 'unit': 'TFLOP/s', 'frac': achieved / (peak * world),
                 'traffic': None, 'peak_per_gpu': peak,
+                'traffic_note': 'k_gemm is launched thousands of times per pass with different tile counts, so there is no single per-launch '
+                                'figure; ncu --set full of its largest launches (profiles/r01_ncu_full_k_gemm_shape65_summary.txt): LAUUM at '
+                                'config 4 moves 21.4 GB of DRAM traffic for 1.43e12 flop (tensor pipe 94.2 % active), the structured '
+                                "route's Y(Q'Y') launch at config 5 353.5 GB for 1.107e13 flop (93.8 %)",
                 'kernel': 'k_gemm<AL,BL> (FP64 DMMA 128x128 tiles); numerator %s flop per step, denominator device time of the '
                           'factor + inverse stages (includes the diagonal-block kernels and copies between GEMM launches)'
                           % ('the structured route\'s GEMM' if structured_used else 'n^3'),
