@@ -11,7 +11,7 @@ There is no CPU compute path: importing works everywhere, computing needs the bu
 from . import _lib
 from ._lib import JaicovError, Session, spd_solve_invert
 from .host import (AffinityShearDistortionModel, BundleAdjustment, Camera, CoordinateTransformationExteriorOrientation,
-                   DirectlyObservedParameterGroup, DistortionModel,
+                   DirectLinearTransformation, DirectlyObservedParameterGroup, DistortionModel, DLTCoefficients,
                    EstimationStateType, EstimationType, ExteriorOrientation, Image, InteriorOrientation, MatrixInversion,
                    ObjectCoordinate, ObjectCoordinateArray, ObservationParameter, ParameterType, PolynomialCoefficient,
                    RadialDistanceDistortionModel, RadiallySymmetricDistortionModel, ScaleBar, TangentialDistortionModel,

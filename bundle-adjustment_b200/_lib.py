@@ -27,7 +27,7 @@ EXPORTS = [
     'jaicov_set_scale_bars', 'jaicov_add_observed_group', 'jaicov_set_datum', 'jaicov_set_reduced_rows', 'jaicov_estimate', 'jaicov_iterate',
     'jaicov_get_stats', 'jaicov_get_values', 'jaicov_get_dx', 'jaicov_get_qxx_packed', 'jaicov_get_qxx_block',
     'jaicov_get_qxx_diag', 'jaicov_get_qxx_submatrix', 'jaicov_eval_residual_jacobian', 'jaicov_get_normal_equations', 'jaicov_omega',
-    'jaicov_spd_solve_invert', 'jaicov_propagate_eo_transform',
+    'jaicov_spd_solve_invert', 'jaicov_propagate_eo_transform', 'jaicov_dlt_batch',
 ]
 
 
@@ -94,6 +94,7 @@ def load():
     L.jaicov_get_qxx_submatrix.argtypes = [vp, i32, vp, dbl, vp]
     L.jaicov_eval_residual_jacobian.argtypes = [vp, i32, vp, vp, vp]
     L.jaicov_propagate_eo_transform.argtypes = [vp, i32, vp, vp, vp, dbl, vp, vp]
+    L.jaicov_dlt_batch.argtypes = [i32, i32, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp]
     L.jaicov_get_normal_equations.argtypes = [vp, vp, vp]
     L.jaicov_omega.argtypes = [vp, vp, ctypes.POINTER(dbl)]
     L.jaicov_spd_solve_invert.argtypes = [i32, i64, vp, i32, vp, i32, ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
@@ -121,6 +122,23 @@ def _f64(a):
 
 def _i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def dlt_batch(pt_ptr, xy, xyz, io, restrictions=(), max_iterations=5000, device=0):
+    """Batched direct linear transformation (jaicov_dlt_batch).  Returns (out (n_img, 20), status (n_img), passes (n_img))."""
+    L = load()
+    pt_ptr = np.ascontiguousarray(pt_ptr, dtype=np.int64)
+    n_img = pt_ptr.size - 1
+    xy, xyz, io = _f64(xy).reshape(-1), _f64(xyz).reshape(-1), _f64(io).reshape(-1)
+    restr = _i32(list(restrictions))
+    out = np.zeros((max(n_img, 0), 20))
+    status = np.zeros(max(n_img, 0), np.int32)
+    passes = np.zeros(max(n_img, 0), np.int32)
+    rc = L.jaicov_dlt_batch(device, n_img, _p(pt_ptr), _p(xy), _p(xyz), _p(io), restr.size, _p(restr), int(max_iterations),
+                            _p(out), _p(status), _p(passes))
+    if rc != OK:
+        raise JaicovError(rc, 'jaicov_dlt_batch failed (no sm_100 device, or illegal argument)')
+    return out, status, passes
 
 
 class Session:

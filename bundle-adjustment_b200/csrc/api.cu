@@ -65,6 +65,9 @@ void launch_propagate(const double *lower, int64_t ld, const double *X, int64_t 
                       int64_t np, const double *q11, int d, int rank, int nT, const double *Jv, const int32_t *Jc, double sigma2,
                       double *out, cudaStream_t s);
 
+void launch_dlt_batch(int n_img, const int64_t *pt_ptr, const double *xy, const double *XYZ, const double *io, int nR,
+                      const int32_t *restr, int max_iterations, double *out, int32_t *status, int32_t *passes, cudaStream_t s);
+
 struct CudaBackend {
     cudaStream_t stream;
     int *info;
@@ -1504,6 +1507,52 @@ int32_t jaicov_propagate_eo_transform(jaicov_handle *h, int32_t n_points, const 
     JCHECK(cudaGetLastError());
     JCHECK(cudaMemcpyAsync(cov_packed, dout.p, (size_t)npk * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     JCHECK(cudaStreamSynchronize(h->stream));
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+// ---- batched direct linear transformation -------------------------------------------------------------------------
+int32_t jaicov_dlt_batch(int32_t device, int32_t n_img, const int64_t *pt_ptr, const double *xy, const double *xyz, const double *io,
+                         int32_t n_restrictions, const int32_t *restrictions, int32_t max_iterations, double *out20,
+                         int32_t *status, int32_t *passes) {
+    if (n_img < 0 || n_restrictions < 0 || max_iterations < 0 || (n_img > 0 && (!pt_ptr || !io || !out20 || !status))) return JAICOV_ILLEGAL_ARGUMENT;
+    if (n_restrictions > 0 && !restrictions) return JAICOV_ILLEGAL_ARGUMENT;
+    if (n_img == 0) return JAICOV_OK;
+    if (pt_ptr[0] != 0) return JAICOV_ILLEGAL_ARGUMENT;
+    for (int i = 0; i < n_img; i++)
+        if (pt_ptr[i + 1] < pt_ptr[i]) return JAICOV_ILLEGAL_ARGUMENT;
+    const int64_t m = pt_ptr[n_img];
+    if (m > 0 && (!xy || !xyz)) return JAICOV_ILLEGAL_ARGUMENT;
+    // validateRestrictions (DLT:268-277): distinct, insertion order; the two fixed principal distances make the identical one redundant
+    std::vector<int32_t> restr;
+    bool has[6] = {false, false, false, false, false, false};
+    for (int i = 0; i < n_restrictions; i++) {
+        const int32_t r = restrictions[i];
+        if (r < 0 || r > 5) return JAICOV_ILLEGAL_ARGUMENT;
+        if (!has[r]) { has[r] = true; restr.push_back(r); }
+    }
+    if (has[JAICOV_DLT_FIXED_PRINCIPLE_DISTANCE_X] && has[JAICOV_DLT_FIXED_PRINCIPLE_DISTANCE_Y] && has[JAICOV_DLT_IDENTICAL_PRINCIPLE_DISTANCE])
+        restr.erase(std::find(restr.begin(), restr.end(), (int32_t)JAICOV_DLT_IDENTICAL_PRINCIPLE_DISTANCE));
+    jaicov_handle *h = nullptr;
+    API_GUARD_BEGIN
+    if (usable_devices() == 0) throw CudaError{cudaErrorNoDevice, "no sm_100 device: jaicov_b200 has no CPU path", __FILE__, __LINE__};
+    JCHECK(cudaSetDevice(device));
+    DevBuf<int64_t> d_ptr;
+    DevBuf<double> d_xy, d_xyz, d_io, d_out;
+    DevBuf<int32_t> d_restr, d_status, d_passes;
+    d_ptr.upload(std::vector<int64_t>(pt_ptr, pt_ptr + n_img + 1));
+    d_xy.upload(std::vector<double>(xy, xy + 2 * m));
+    d_xyz.upload(std::vector<double>(xyz, xyz + 3 * m));
+    d_io.upload(std::vector<double>(io, io + 3 * (size_t)n_img));
+    std::vector<int32_t> rr = restr;
+    if (rr.empty()) rr.push_back(0);
+    d_restr.upload(rr);
+    d_out.alloc(20 * (size_t)n_img); d_status.alloc(n_img); d_passes.alloc(n_img);
+    launch_dlt_batch(n_img, d_ptr.p, d_xy.p, d_xyz.p, d_io.p, (int)restr.size(), d_restr.p, max_iterations, d_out.p, d_status.p, d_passes.p, nullptr);
+    JCHECK(cudaGetLastError());
+    JCHECK(cudaMemcpy(out20, d_out.p, 20 * (size_t)n_img * sizeof(double), cudaMemcpyDeviceToHost));
+    JCHECK(cudaMemcpy(status, d_status.p, (size_t)n_img * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (passes) JCHECK(cudaMemcpy(passes, d_passes.p, (size_t)n_img * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return JAICOV_OK;
     API_GUARD_END(h)
 }

@@ -59,6 +59,17 @@ class ParameterType(enum.IntEnum):
     IMAGE_COORDINATE_X = 411
     IMAGE_COORDINATE_Y = 412
     SCALE_BAR_LENGTH = 511
+    DIRECT_LINEAR_TRANSFORMATION_B11 = 611
+    DIRECT_LINEAR_TRANSFORMATION_B12 = 612
+    DIRECT_LINEAR_TRANSFORMATION_B13 = 613
+    DIRECT_LINEAR_TRANSFORMATION_B14 = 614
+    DIRECT_LINEAR_TRANSFORMATION_B21 = 621
+    DIRECT_LINEAR_TRANSFORMATION_B22 = 622
+    DIRECT_LINEAR_TRANSFORMATION_B23 = 623
+    DIRECT_LINEAR_TRANSFORMATION_B24 = 624
+    DIRECT_LINEAR_TRANSFORMATION_B31 = 631
+    DIRECT_LINEAR_TRANSFORMATION_B32 = 632
+    DIRECT_LINEAR_TRANSFORMATION_B33 = 633
 
     def getId(self):
         return int(self)
@@ -474,6 +485,95 @@ class UpperSymmPackMatrix:
         D[iu] = self._data[iu[0] + iu[1] * (iu[1] + 1) // 2]
         D.T[iu] = D[iu]
         return D
+
+
+class DLTCoefficients:
+    """dlt/DLTCoefficients.java:33-84: the 11 DLT coefficients of an image plus the interior / exterior orientation derived
+    from them, in the reference's insertion order."""
+    _ORDER = tuple(ParameterType(i) for i in (611, 612, 613, 614, 621, 622, 623, 624, 631, 632, 633)) + (
+        ParameterType.PRINCIPAL_POINT_X, ParameterType.PRINCIPAL_POINT_Y, ParameterType.PRINCIPAL_DISTANCE,
+        ParameterType.CAMERA_COORDINATE_X, ParameterType.CAMERA_COORDINATE_Y, ParameterType.CAMERA_COORDINATE_Z,
+        ParameterType.CAMERA_OMEGA, ParameterType.CAMERA_PHI, ParameterType.CAMERA_KAPPA)
+
+    def __init__(self, image):
+        self._image = image
+        self._params = {t: UnknownParameter(t, self) for t in self._ORDER}
+
+    def get(self, parameterType): return self._params[parameterType]
+    def getReference(self): return self._image
+    def __iter__(self): return iter(self._params.values())
+
+
+class DirectLinearTransformation:
+    """dlt/DirectLinearTransformation.java:49-184.  ``adjust`` keeps the reference's per-image signature; ``adjustAll`` is the
+    batched form (one kernel launch for all images, jaicov_dlt_batch)."""
+
+    class RestrictionType(enum.IntEnum):      # ordinal order, :50-57
+        IDENTICAL_PRINCIPLE_DISTANCE = 0
+        ROTATION_WITHOUT_SHEAR = 1
+        FIXED_PRINCIPLE_DISTANCE_X = 2
+        FIXED_PRINCIPLE_DISTANCE_Y = 3
+        FIXED_PRINCIPAL_POINT_X = 4
+        FIXED_PRINCIPAL_POINT_Y = 5
+
+    maximalNumberOfIterations = 5000          # DefaultValue.getMaximalNumberOfIterations(), :63
+
+    @staticmethod
+    def adjust(coefficients, objectCoordinates, *restrictions, device=0):
+        return DirectLinearTransformation.adjustAll([coefficients], objectCoordinates, *restrictions, device=device)[0]
+
+    @staticmethod
+    def adjustAll(coefficientsList, objectCoordinates, *restrictions, device=0):
+        """objectCoordinates: {name: ObjectCoordinate} of the points with known coordinates.  Returns one bool per image."""
+        PT = ParameterType
+        pt_ptr, xy, xyz, io = [0], [], [], []
+        for coef in coefficientsList:
+            # prepareUnknwonParameters, :279-314
+            column = 0
+            for p in coef:
+                p.setValue(0)
+                if 611 <= int(p.getParameterType()) <= 633:
+                    p.setColumn(column)
+                    column += 1
+                else:
+                    p.setColumn(COL_FIXED if p.getColumn() == COL_FIXED else COL_UNSET)
+            image = coef.getReference()
+            inner = image.getReference().getInteriorOrientation()
+            for p in (inner.getPrincipleDistance(), inner.getPrinciplePointX(), inner.getPrinciplePointY()):
+                coef.get(p.getParameterType()).setValue(p.getValue())
+                if p.getColumn() == COL_FIXED:
+                    coef.get(p.getParameterType()).setColumn(COL_FIXED)
+            # homologous points by name, :78-94
+            cnt = 0
+            for (store, idx, xy_c, _sg, _rh) in image._chunks:
+                xy_c = np.asarray(xy_c, float).reshape(-1, 2)
+                for k, i in enumerate(np.asarray(idx, np.int64).tolist()):
+                    oc = objectCoordinates.get(store.names[i])
+                    if oc is None:
+                        continue
+                    xy.append(xy_c[k])
+                    xyz.append((oc.getX().getValue(), oc.getY().getValue(), oc.getZ().getValue()))
+                    cnt += 1
+            pt_ptr.append(pt_ptr[-1] + cnt)
+            io.append((coef.get(PT.PRINCIPAL_DISTANCE).getValue(), coef.get(PT.PRINCIPAL_POINT_X).getValue(),
+                       coef.get(PT.PRINCIPAL_POINT_Y).getValue()))
+        out, status, _passes = _lib.dlt_batch(pt_ptr, np.array(xy).reshape(-1, 2), np.array(xyz).reshape(-1, 3), np.array(io).reshape(-1, 3),
+                                              [int(r) for r in restrictions], DirectLinearTransformation.maximalNumberOfIterations, device)
+        results = []
+        for coef, o, st in zip(coefficientsList, out, status):
+            if st < 0:
+                results.append(False)
+                continue
+            for t, v in zip(DLTCoefficients._ORDER[:11], o[:11]):
+                coef.get(t).setValue(v)
+            # :248-265: fixed interior orientation values are kept
+            for t, v in ((PT.PRINCIPAL_DISTANCE, o[11]), (PT.PRINCIPAL_POINT_X, o[12]), (PT.PRINCIPAL_POINT_Y, o[13])):
+                if coef.get(t).getColumn() != COL_FIXED:
+                    coef.get(t).setValue(v)
+            for t, v in zip(DLTCoefficients._ORDER[14:], o[14:20]):
+                coef.get(t).setValue(v)
+            results.append(bool(st == 1))
+        return results
 
 
 class CoordinateTransformationExteriorOrientation:

@@ -226,6 +226,27 @@ int32_t jaicov_get_qxx_submatrix(jaicov_handle *h, int32_t n_idx, const int32_t 
 int32_t jaicov_get_qxx_diag(jaicov_handle *h, double *dst);
 
 /* ---- stage access for parity tests and profiling (same kernels the loop uses) ---------------------------------- */
+/* DirectLinearTransformation.RestrictionType ordinals (dlt/DirectLinearTransformation.java:50-57) */
+#define JAICOV_DLT_IDENTICAL_PRINCIPLE_DISTANCE 0
+#define JAICOV_DLT_ROTATION_WITHOUT_SHEAR 1
+#define JAICOV_DLT_FIXED_PRINCIPLE_DISTANCE_X 2
+#define JAICOV_DLT_FIXED_PRINCIPLE_DISTANCE_Y 3
+#define JAICOV_DLT_FIXED_PRINCIPAL_POINT_X 4
+#define JAICOV_DLT_FIXED_PRINCIPAL_POINT_Y 5
+
+/* Batched direct linear transformation: initial interior / exterior orientation of n_img images at once,
+ * replacing one DirectLinearTransformation.adjust call per image (dlt/DirectLinearTransformation.java:67-184; normal
+ * equations dlt/DLTPartialDerivativeFactory.java:239-337, restrictions :68-236, expansion DLT:186-266).  The caller
+ * gathers the homologous points (image point + object coordinates matched by name, DLT:78-94): image i owns the
+ * observations [pt_ptr[i], pt_ptr[i+1]) of xy (2 doubles each) and xyz (3 doubles each); io = (c, x0, y0) of the image's
+ * camera (used by the FIXED_* restrictions); the restrictions apply to every image.  out20 per image: b11 b12 b13 b14 b21
+ * b22 b23 b24 b31 b32 b33 (back-scaled), c = (cx + cy)/2, x0, y0, X0, Y0, Z0, omega, phi, kappa.  status per image: 1 =
+ * adjust() returned true, 0 = no convergence, -1 = failed (fewer than 6 points, singular system); passes (may be NULL) =
+ * normal-equation solves.  No handle: like jaicov_spd_solve_invert the call is self-contained. */
+int32_t jaicov_dlt_batch(int32_t device, int32_t n_img, const int64_t *pt_ptr, const double *xy, const double *xyz, const double *io,
+                         int32_t n_restrictions, const int32_t *restrictions, int32_t max_iterations, double *out20,
+                         int32_t *status, int32_t *passes);
+
 /* Covariance propagation of object points transformed into the frame of a reference image, replacing
  * CoordinateTransformationExteriorOrientation.transform (tranformation/CoordinateTransformationExteriorOrientation.java:49-121):
  * for every triple (point, source image, target image)  X_trg = X0_trg + R_trg R_src' (X - X0_src)  (:209-215; source ==
