@@ -5,11 +5,11 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC ${JAICOV_NVCC_EXTRA}"
 mkdir -p _obj
-for f in assembly dense_kernels stage_kernels structured propagate dlt dist api; do
+for f in prep_kernels assembly dense_kernels stage_kernels structured propagate dlt dist api; do
   if [ ! -f _obj/$f.o ] || [ csrc/$f.cu -nt _obj/$f.o ] || [ -n "$(find csrc include ../include -newer _obj/$f.o \( -name '*.h' -o -name '*.hpp' -o -name '*.cuh' \) 2>/dev/null | head -1)" ]; then
     $NVCC $FLAGS -c csrc/$f.cu -o _obj/$f.o &
   fi
 done
 wait
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libjaicov_b200.so _obj/assembly.o _obj/dense_kernels.o _obj/stage_kernels.o _obj/structured.o _obj/propagate.o _obj/dlt.o _obj/dist.o _obj/api.o -ldl -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libjaicov_b200.so _obj/prep_kernels.o _obj/assembly.o _obj/dense_kernels.o _obj/stage_kernels.o _obj/structured.o _obj/propagate.o _obj/dlt.o _obj/dist.o _obj/api.o -ldl -lcudart
 echo built $(pwd)/libjaicov_b200.so

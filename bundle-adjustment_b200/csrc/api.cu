@@ -68,6 +68,11 @@ void launch_propagate(const double *lower, int64_t ld, const double *X, int64_t 
 void launch_dlt_batch(int n_img, const int64_t *pt_ptr, const double *xy, const double *XYZ, const double *io, int nR,
                       const int32_t *restr, int max_iterations, double *out, int32_t *status, int32_t *passes, cudaStream_t s);
 
+void launch_img_of_obs(const int64_t *pt_ptr, int nImg, int32_t *img_of_obs, cudaStream_t s);
+size_t csc_temp_bytes(int64_t n);
+void launch_build_csc(const int32_t *obj, int64_t obs0, int64_t n, int nPt, int32_t *keys_out, int64_t *iota, void *temp,
+                      size_t temp_bytes, int64_t *pt_obs_ptr, int64_t *pt_obs, int32_t minmax_host[2], cudaStream_t s);
+
 struct CudaBackend {
     cudaStream_t stream;
     int *info;
@@ -81,26 +86,31 @@ struct CudaBackend {
 // Process-wide cache of large device allocations: cudaMalloc/cudaFree of tens of GB cost hundreds of milliseconds and
 // every estimateModel() call needs the same buffers again, so big blocks are parked here instead of being freed.
 struct DevCache {
-    static constexpr size_t kMinBytes = (size_t)32 << 20;
-    std::vector<std::pair<size_t, void *>> free_list;
+    static constexpr size_t kMinBytes = 1;     // every buffer: cudaFree / cudaMalloc cost milliseconds each once tens of GB are mapped
+    struct Entry { int device; size_t bytes; void *p; };
+    std::vector<Entry> free_list;
+    static int current_device() { int d = 0; cudaGetDevice(&d); return d; }
     void *take(size_t bytes) {
+        const int dev = current_device();
         for (size_t i = 0; i < free_list.size(); i++)
-            if (free_list[i].first == bytes) {
-                void *p = free_list[i].second;
+            if (free_list[i].bytes == bytes && free_list[i].device == dev) {
+                void *p = free_list[i].p;
                 free_list.erase(free_list.begin() + i);
                 return p;
             }
         return nullptr;
     }
     void give(size_t bytes, void *p) {
-        if (free_list.size() >= 16) {   // bounded: drop the oldest entry
-            cudaFree(free_list.front().second);
+        // bounded by count only (a handle holds ~100 buffers); memory pressure is handled where it shows: a failed
+        // cudaMalloc purges the cache and retries (DevBuf::alloc)
+        if (free_list.size() >= 1024) {   // drop the oldest entry
+            cudaFree(free_list.front().p);
             free_list.erase(free_list.begin());
         }
-        free_list.emplace_back(bytes, p);
+        free_list.push_back(Entry{current_device(), bytes, p});
     }
     void purge() {
-        for (auto &e : free_list) cudaFree(e.second);
+        for (auto &e : free_list) cudaFree(e.p);
         free_list.clear();
     }
 };
@@ -130,6 +140,10 @@ struct DevBuf {
     void upload(const std::vector<T> &h) {
         alloc(h.size());
         if (!h.empty()) JCHECK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    }
+    void upload(const T *src, size_t count) {      // straight from the caller's buffer (no host copy in between)
+        alloc(count);
+        if (count) JCHECK(cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
     }
     void release() {
         if (p) {
@@ -187,6 +201,8 @@ struct jaicov_handle {
     DevBuf<double> M, W, Dinv, rhs, V, Bt, Btv, Rt, H, Tq, small, dxref, omega_parts;
     DevBuf<int> info;
     DevBuf<unsigned long long> upd;
+    int64_t m_obs = 0;                   // image points
+    bool obs_on_device = false;          // jaicov_set_image_points copied the observations straight to the device
     int nDatumPts = 0, free_mask = 0;
     bool prepared = false, have_qxx = false, have_neq = false;
     cudaStream_t stream = nullptr;
@@ -418,7 +434,7 @@ void prepare(jaicov_handle *h) {
     if (h->S.ntPt > 8) throw std::runtime_error("too many camera parameters in total (by-point Gram limited to 64 columns)");
     // ---- images / observations -----------------------------------------------------------------------------------
     P.nImg = (int)h->cam_of_img.size();
-    P.m = (int64_t)h->obj_idx.size();
+    P.m = h->m_obs;
     if (h->pt_ptr.empty()) h->pt_ptr.assign(1, 0);
     if (h->pt_ptr.back() != P.m) throw std::runtime_error("pt_ptr does not cover the image points");
     P.nPt = (int)(h->xyz.size() / 3);
@@ -431,26 +447,40 @@ void prepare(jaicov_handle *h) {
         P.obs0 = h->pt_ptr[P.img0];
         P.obs1 = h->pt_ptr[P.img1];
     }
-    std::vector<int32_t> img_of_obs(P.m);
     std::vector<WorkItem> work;
     std::vector<int32_t> img_work_ptr(P.img1 - P.img0 + 1, 0);
     const int64_t chunk = 1024;
-    for (int i = 0; i < P.nImg; i++)
-        for (int64_t j = h->pt_ptr[i]; j < h->pt_ptr[i + 1]; j++) img_of_obs[j] = i;
     for (int i = P.img0; i < P.img1; i++) {
         img_work_ptr[i - P.img0] = (int32_t)work.size();
         for (int64_t b = h->pt_ptr[i]; b < h->pt_ptr[i + 1]; b += chunk)
             work.push_back(WorkItem{i, 0, b, std::min(b + chunk, h->pt_ptr[i + 1])});
     }
     img_work_ptr[P.img1 - P.img0] = (int32_t)work.size();
-    std::vector<int64_t> pt_obs_ptr(P.nPt + 1, 0), pt_obs(std::max<int64_t>(P.obs1 - P.obs0, 1));
-    for (int64_t j = 0; j < P.m; j++)
-        if (h->obj_idx[j] < 0 || h->obj_idx[j] >= P.nPt) throw std::runtime_error("object point index out of range");
-    for (int64_t j = P.obs0; j < P.obs1; j++) pt_obs_ptr[h->obj_idx[j] + 1]++;
-    for (int p = 0; p < P.nPt; p++) pt_obs_ptr[p + 1] += pt_obs_ptr[p];
+    // observations: already on the device (jaicov_set_image_points), or host copies taken while no device was visible
+    if (!h->obs_on_device) {
+        h->d_obj_idx.upload(h->obj_idx); h->d_xy.upload(h->xy); h->d_var.upload(h->var); h->d_rho.upload(h->rho);
+    }
+    h->d_pt_ptr.upload(h->pt_ptr);
+    // (cudaMemcpy from pageable memory may return while the last staging buffer is still in flight on the legacy stream,
+    // and the handle's stream is non-blocking: order the kernels below after those copies explicitly)
+    JCHECK(cudaStreamSynchronize(0));
+    // index structures on the device: image of every observation, observations of every object point (stable sort)
+    h->d_img_of_obs.alloc((size_t)std::max<int64_t>(P.m, 1));
+    launch_img_of_obs(h->d_pt_ptr.p, P.nImg, h->d_img_of_obs.p, h->stream);
     {
-        std::vector<int64_t> cur(pt_obs_ptr.begin(), pt_obs_ptr.end() - 1);
-        for (int64_t j = P.obs0; j < P.obs1; j++) pt_obs[cur[h->obj_idx[j]]++] = j;
+        const int64_t nloc = P.obs1 - P.obs0;
+        DevBuf<int32_t> keys;
+        DevBuf<int64_t> iota;
+        DevBuf<unsigned char> temp;
+        keys.alloc((size_t)std::max<int64_t>(nloc, 1));
+        iota.alloc((size_t)std::max<int64_t>(nloc, 1));
+        const size_t tb = csc_temp_bytes(std::max<int64_t>(nloc, 1));
+        temp.alloc(std::max<size_t>(tb, 1));
+        h->d_pt_obs_ptr.alloc((size_t)P.nPt + 1);
+        h->d_pt_obs.alloc((size_t)std::max<int64_t>(nloc, 1));
+        int32_t mm[2];
+        launch_build_csc(h->d_obj_idx.p, P.obs0, nloc, P.nPt, keys.p, iota.p, temp.p, tb, h->d_pt_obs_ptr.p, h->d_pt_obs.p, mm, h->stream);
+        if (nloc > 0 && (mm[0] < 0 || mm[1] >= P.nPt)) throw std::runtime_error("object point index out of range");
     }
     // ---- validate columns ----------------------------------------------------------------------------------------
     auto check_cols = [&](const std::vector<int32_t> &c) {
@@ -477,9 +507,7 @@ void prepare(jaicov_handle *h) {
     h->d_zern_m.upload(zm); h->d_zern_ptr.upload(zptr); h->d_zern_p.upload(zp); h->d_zern_c.upload(zc);
     h->d_cam_kbase.upload(kbase); h->d_campos_col.upload(campos);
     h->d_cam_of_img.upload(h->cam_of_img); h->d_eo_val.upload(h->eo_val); h->d_eo_col.upload(h->eo_col);
-    h->d_pt_ptr.upload(h->pt_ptr); h->d_pose.alloc((size_t)std::max(P.nImg, 1) * 16);
-    h->d_obj_idx.upload(h->obj_idx); h->d_xy.upload(h->xy); h->d_var.upload(h->var); h->d_rho.upload(h->rho);
-    h->d_img_of_obs.upload(img_of_obs); h->d_pt_obs_ptr.upload(pt_obs_ptr); h->d_pt_obs.upload(pt_obs);
+    h->d_pose.alloc((size_t)std::max(P.nImg, 1) * 16);
     h->d_xyz.upload(h->xyz); h->d_pt_col.upload(h->pt_col);
     h->d_bar_a.upload(h->bar_a); h->d_bar_b.upload(h->bar_b); h->d_bar_len.upload(h->bar_len); h->d_bar_var.upload(h->bar_var);
     h->d_work.upload(work); h->d_img_work_ptr.upload(img_work_ptr); h->d_datum_pts.upload(datum_pts);
@@ -603,6 +631,7 @@ void prepare(jaicov_handle *h) {
         gi++;
     }
     (void)gi;
+    JCHECK(cudaStreamSynchronize(0));     // every upload of this function has landed before the first pass starts
     h->prepared = true;
     h->have_qxx = false;
     h->have_neq = false;
@@ -1074,10 +1103,26 @@ int32_t jaicov_set_image_points(jaicov_handle *h, int64_t m, const int32_t *obj_
                                 const double *rho) {
     if (!h || m < 0) return JAICOV_ILLEGAL_ARGUMENT;
     API_GUARD_BEGIN
-    h->obj_idx.assign(obj_idx, obj_idx + m);
-    h->xy.assign(xy, xy + 2 * m);
-    h->var.assign(var, var + 2 * m);
-    if (rho) h->rho.assign(rho, rho + m); else h->rho.assign(m, 0.0);
+    if (m > 0 && (!obj_idx || !xy || !var)) return JAICOV_ILLEGAL_ARGUMENT;
+    h->m_obs = m;
+    if (usable_devices() > 0) {
+        // the observations are only ever read by kernels: copy them from the caller's buffers straight to the device
+        JCHECK(cudaSetDevice(h->opt.device));
+        h->d_obj_idx.upload(obj_idx, (size_t)m);
+        h->d_xy.upload(xy, (size_t)(2 * m));
+        h->d_var.upload(var, (size_t)(2 * m));
+        if (rho) h->d_rho.upload(rho, (size_t)m);
+        else { h->d_rho.alloc((size_t)m); if (m) JCHECK(cudaMemset(h->d_rho.p, 0, (size_t)m * sizeof(double))); }
+        h->obs_on_device = true;
+        h->obj_idx.clear(); h->xy.clear(); h->var.clear(); h->rho.clear();
+    } else {
+        // no device visible: keep host copies so that the failure surfaces at the first computing call (no CPU path)
+        h->obj_idx.assign(obj_idx, obj_idx + m);
+        h->xy.assign(xy, xy + 2 * m);
+        h->var.assign(var, var + 2 * m);
+        if (rho) h->rho.assign(rho, rho + m); else h->rho.assign(m, 0.0);
+        h->obs_on_device = false;
+    }
     h->prepared = false;
     return JAICOV_OK;
     API_GUARD_END(h)
