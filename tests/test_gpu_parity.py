@@ -308,6 +308,40 @@ def test_adjustment_levenberg_marquardt(built, damping, solver):
     compare_adjustment(synthetic_scene(2, images=12, targets=80)[0], 'LM lambda=%g' % damping, damping=damping, solver=solver)
 
 
+def _ragged_scene(config, visibility, keep):
+    sc = synthetic_scene(config, images=14, targets=90, visibility=visibility, seed=77)[0]
+    img = sc['cameras'][0]['images'][2]
+    for k in ('obj', 'xy', 'sigma', 'rho'):          # one image keeps only a handful of points
+        img[k] = img[k][:keep]
+    return sc
+
+
+@BOTH
+@pytest.mark.parametrize('config,visibility,keep', [(2, 0.35, 5), (4, 0.5, 10)])
+def test_adjustment_ragged_visibility(built, config, visibility, keep, solver):
+    """Ragged input: sparse visibility (object points with two or three rays), one image with very few points."""
+    sc = _ragged_scene(config, visibility, keep)
+    counts = [len(i['obj']) for i in sc['cameras'][0]['images']]
+    assert min(counts) == keep and max(counts) > 3 * keep
+    compare_adjustment(sc, 'ragged config %d (visibility %.2f, %d points in image 3)' % (config, visibility, keep), solver=solver)
+
+
+@BOTH
+@pytest.mark.parametrize('max_iter', [1, 3, 4])
+def test_iteration_limit_gives_no_convergence(built, max_iter, solver):
+    """BA:327-350: the iteration limit ends the loop with NO_CONVERGENCE after the same number of passes as the reference."""
+    sc = synthetic_scene(2, images=10, targets=60)[0]
+    adj, _ = build_adjustment(sc)
+    adj.setSolver(SOLVERS[solver])
+    adj.setMaximalNumberOfIterations(max_iter)
+    state = adj.estimateModel()
+    o = Oracle(sc, max_iter=max_iter)
+    assert o.estimate() == -4
+    assert state == ba.EstimationStateType.NO_CONVERGENCE
+    assert adj.stats.iterations == len(o.history) and adj.stats.iteration_step == o.iterations
+    assert abs(adj.stats.omega - o.omega) <= 1e-8 * o.omega
+
+
 def test_modes_none_and_simulation(built):
     sc = synthetic_scene(2, images=10, targets=80)[0]
     adj, _ = build_adjustment(sc)
