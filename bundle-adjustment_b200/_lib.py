@@ -21,7 +21,7 @@ SOLVER_AUTO, SOLVER_DENSE, SOLVER_STRUCTURED = 0, 1, 2
 COL_UNSET, COL_FIXED = -1, 2147483647
 
 EXPORTS = [
-    'jaicov_default_options', 'jaicov_create', 'jaicov_destroy', 'jaicov_last_error', 'jaicov_device_count', 'jaicov_launch_count', 'jaicov_nccl_unique_id', 'jaicov_dist_init',
+    'jaicov_default_options', 'jaicov_create', 'jaicov_destroy', 'jaicov_last_error', 'jaicov_device_count', 'jaicov_launch_count', 'jaicov_release_cached_memory', 'jaicov_nccl_unique_id', 'jaicov_dist_init',
     'jaicov_get_qxx_local', 'jaicov_shard_images',
     'jaicov_set_cameras', 'jaicov_set_images', 'jaicov_set_image_points', 'jaicov_set_object_points',
     'jaicov_set_scale_bars', 'jaicov_add_observed_group', 'jaicov_set_datum', 'jaicov_set_reduced_rows', 'jaicov_estimate', 'jaicov_iterate',
@@ -93,6 +93,8 @@ def load():
     L.jaicov_get_qxx_diag.argtypes = [vp, vp]
     L.jaicov_get_qxx_submatrix.argtypes = [vp, i32, vp, dbl, vp]
     L.jaicov_eval_residual_jacobian.argtypes = [vp, i32, vp, vp, vp]
+    L.jaicov_release_cached_memory.restype = ctypes.c_int64
+    L.jaicov_release_cached_memory.argtypes = []
     L.jaicov_propagate_eo_transform.argtypes = [vp, i32, vp, vp, vp, dbl, vp, vp]
     L.jaicov_dlt_batch.argtypes = [i32, i32, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp]
     L.jaicov_get_normal_equations.argtypes = [vp, vp, vp]

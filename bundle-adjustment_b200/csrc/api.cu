@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <stdexcept>
 #include <string>
@@ -89,9 +90,11 @@ struct DevCache {
     static constexpr size_t kMinBytes = 1;     // every buffer: cudaFree / cudaMalloc cost milliseconds each once tens of GB are mapped
     struct Entry { int device; size_t bytes; void *p; };
     std::vector<Entry> free_list;
+    std::mutex mu;                             // handles may live on different host threads
     static int current_device() { int d = 0; cudaGetDevice(&d); return d; }
     void *take(size_t bytes) {
         const int dev = current_device();
+        std::lock_guard<std::mutex> lock(mu);
         for (size_t i = 0; i < free_list.size(); i++)
             if (free_list[i].bytes == bytes && free_list[i].device == dev) {
                 void *p = free_list[i].p;
@@ -103,15 +106,20 @@ struct DevCache {
     void give(size_t bytes, void *p) {
         // bounded by count only (a handle holds ~100 buffers); memory pressure is handled where it shows: a failed
         // cudaMalloc purges the cache and retries (DevBuf::alloc)
+        const int dev = current_device();
+        std::lock_guard<std::mutex> lock(mu);
         if (free_list.size() >= 1024) {   // drop the oldest entry
             cudaFree(free_list.front().p);
             free_list.erase(free_list.begin());
         }
-        free_list.push_back(Entry{current_device(), bytes, p});
+        free_list.push_back(Entry{dev, bytes, p});
     }
-    void purge() {
-        for (auto &e : free_list) cudaFree(e.p);
+    size_t purge() {
+        std::lock_guard<std::mutex> lock(mu);
+        size_t bytes = 0;
+        for (auto &e : free_list) { cudaFree(e.p); bytes += e.bytes; }
         free_list.clear();
+        return bytes;
     }
 };
 static DevCache g_cache;
@@ -990,6 +998,8 @@ int32_t jaicov_default_options(jaicov_options *opt) {
 }
 
 int32_t jaicov_device_count(void) { return usable_devices(); }
+
+int64_t jaicov_release_cached_memory(void) { return (int64_t)g_cache.purge(); }
 
 int64_t jaicov_launch_count(void) { return (int64_t)g_launch_count; }
 

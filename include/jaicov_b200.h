@@ -130,6 +130,10 @@ void jaicov_destroy(jaicov_handle *h);
 const char *jaicov_last_error(const jaicov_handle *h);
 /* number of usable sm_100 devices (0 => every compute call fails loudly) */
 int32_t jaicov_device_count(void);
+/* Device buffers of destroyed handles are kept for the next handle of this process (cudaMalloc / cudaFree of tens of GB
+ * cost hundreds of milliseconds; a failed allocation empties the cache and retries).  This call returns them to the
+ * driver now; result = bytes released. */
+int64_t jaicov_release_cached_memory(void);
 /* diagnostic: number of CUDA kernels this library has launched in this process so far */
 int64_t jaicov_launch_count(void);
 
