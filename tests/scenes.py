@@ -171,3 +171,30 @@ def synthetic_scene(config, images=None, targets=None, seed=None, sigma_img=0.00
         scene['points']['xyz'][:3] = pts_true[:3]
     truth = dict(points=pts_true, io=io_true, coefs=coefs_true, eo=eo_true)
     return scene, truth
+
+
+def random_scene(seed):
+    """Deterministic random network for the randomized parity tests: configuration, number of cameras, size,
+    visibility, fixed point components / points / EO components / coefficients and an optional scale bar all vary
+    with the seed (datum defects from 0 to 7 occur)."""
+    rng = np.random.default_rng(seed)
+    cfg = int(rng.choice([2, 4]))
+    ncam = int(rng.integers(1, 3))
+    images = int(rng.integers(8, 15))
+    targets = int(rng.integers(50, 110))
+    vis = float(rng.uniform(0.55, 1.0))
+    sc = synthetic_scene(cfg, images=images, targets=targets, visibility=vis, seed=1000 + seed, n_cameras=ncam)[0]
+    for _ in range(int(rng.integers(0, 4))):
+        sc['points']['fixed'][int(rng.integers(targets)), int(rng.integers(3))] = True
+    if rng.uniform() < 0.5:
+        sc['points']['fixed'][int(rng.integers(targets))] = True
+    allimgs = [im for c in sc['cameras'] for im in c['images']]
+    if rng.uniform() < 0.7:
+        allimgs[int(rng.integers(len(allimgs)))]['eo_fixed'][int(rng.integers(6))] = True
+    cam = sc['cameras'][int(rng.integers(ncam))]
+    k = int(rng.integers(len(cam['coefs'])))
+    cam['coefs'][k] = cam['coefs'][k][:3] + (True,)
+    if rng.uniform() < 0.3:
+        a, b = 0, 1
+        sc['scale_bars'] = [(a, b, float(np.linalg.norm(sc['points']['xyz'][a] - sc['points']['xyz'][b])) + 0.01, 0.02)]
+    return sc
