@@ -167,6 +167,7 @@ class Session:
         if rc != OK:
             raise JaicovError(rc, 'jaicov_create failed (unsupported option?)')
         self._keep = []
+        self._interrupt = ctypes.c_int32(0)
         self.n = 0
         self.flat = None
 
@@ -250,9 +251,14 @@ class Session:
             off += sz
         return cols, blocks
 
+    def interrupt(self):
+        """Ask a running estimate() to stop at its next check (BundleAdjustment.interrupt, BA:1455-1457); callable from the
+        progress callback or from another thread."""
+        self._interrupt.value = 1
+
     def estimate(self, progress=None):
         cb = PROGRESS_CB(lambda user, st, a, b: progress(st, a, b)) if progress else None
-        rc = self.L.jaicov_estimate(self.h, ctypes.cast(cb, ctypes.c_void_p) if cb else None, None, None)
+        rc = self.L.jaicov_estimate(self.h, ctypes.cast(cb, ctypes.c_void_p) if cb else None, None, ctypes.byref(self._interrupt))
         if rc in (NOT_INITIALISED, OUT_OF_MEMORY, ILLEGAL_ARGUMENT):
             self.check(rc)
         return rc

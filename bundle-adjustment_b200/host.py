@@ -653,7 +653,18 @@ class BundleAdjustment:
                 if it not in self._groups: self._groups.append(it)
             else: raise TypeError('unsupported argument %r' % (it,))
 
-    def addPropertyChangeListener(self, listener): self._listeners.append(listener)
+    def addPropertyChangeListener(self, listener): self._listeners.append(listener)          # :1459-1461
+
+    def removePropertyChangeListener(self, listener):                                         # :1463-1465
+        if listener in self._listeners:
+            self._listeners.remove(listener)
+
+    def interrupt(self):                                                                      # :1455-1457
+        """Stops a running estimateModel() at its next check (:240, :320); a request made while no adjustment runs
+        takes effect in the next one, as in the reference."""
+        self._interrupt_requested = True
+        if self._session is not None:
+            self._session.interrupt()
 
     def setAdjustmentResultWriter(self, adjustmentResultWriter):     # :1123-1125
         self._writer = adjustmentResultWriter
@@ -982,7 +993,11 @@ class BundleAdjustment:
             device=self._device, sigma2apriori=self._sigma2apriori, damping_value=self._damping,
             solver=getattr(self, '_solver', _lib.SOLVER_AUTO))
         self._session.set_problem(flat)
+        if getattr(self, '_interrupt_requested', False):
+            self._session.interrupt()
+        self._interrupt_requested = False
         rc = self._session.estimate(progress=self._fire if self._listeners else None)
+        self._interrupt_requested = False
         self.stats = self._session.stats()
         self._omega = self.stats.omega
         # write the adjusted values back into the object graph

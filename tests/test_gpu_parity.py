@@ -376,6 +376,32 @@ def test_adjustment_randomized(built, seed, solver):
         print('random %d: d = %d, route %s' % (seed, o.bk.d, 'dense' if sc['scale_bars'] else 'structured'))
 
 
+def test_interrupt(built):
+    """BundleAdjustment.interrupt() (BA:1455-1457): the running loop stops at its next check with INTERRUPT (BA:240, :320);
+    a request made before estimateModel() stops the first pass."""
+    sc = synthetic_scene(2, images=10, targets=60)[0]
+    adj, _ = build_adjustment(sc)
+    events = []
+
+    def listener(state, old, new):
+        events.append(state)
+        if len(events) == 3:
+            adj.interrupt()
+
+    adj.addPropertyChangeListener(listener)
+    assert adj.estimateModel() == ba.EstimationStateType.INTERRUPT
+    assert 1 <= adj.stats.iterations <= 2
+    adj.removePropertyChangeListener(listener)
+    assert adj._listeners == []
+    adj2, _ = build_adjustment(sc)
+    adj2.interrupt()
+    assert adj2.estimateModel() == ba.EstimationStateType.INTERRUPT
+    assert adj2.stats.iterations <= 1
+    # the request is consumed: an untouched adjustment of the same network runs to the end
+    adj3, _ = build_adjustment(sc)
+    assert adj3.estimateModel() == ba.EstimationStateType.ERROR_FREE_ESTIMATION
+
+
 def test_modes_none_and_simulation(built):
     sc = synthetic_scene(2, images=10, targets=80)[0]
     adj, _ = build_adjustment(sc)
