@@ -48,6 +48,14 @@ def test_option_validation(built):
 
 
 @pytest.mark.skipif(ba._lib.load().jaicov_device_count() > 0, reason='only meaningful without a GPU')
+def _has_device():
+    try:
+        return ba._lib.load().jaicov_device_count() > 0
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_device(), reason='a B200 is visible: the calls below would compute')
 def test_no_cpu_fallback(built):
     """No B200 -> computing entry points fail with NOT_INITIALISED instead of falling back to the CPU."""
     a = np.eye(4)
@@ -62,3 +70,45 @@ def test_no_cpu_fallback(built):
                            rho=np.zeros(1), xyz=np.zeros(3), pt_col=[0, 1, 2], is_datum=[1], free_flags=[0] * 7,
                            n_unknowns=16, n_observations=2))
         s.iterate(final_pass=True)
+
+
+@pytest.mark.skipif(_has_device(), reason='a B200 is visible: the calls below would compute')
+def test_no_cpu_fallback_for_the_widened_entry_points(built):
+    """jaicov_dlt_batch and the covariance propagation have no CPU route either."""
+    pt_ptr = np.array([0, 6])
+    xy = np.zeros((6, 2))
+    xyz = np.arange(18.0).reshape(6, 3)
+    with pytest.raises(ba.JaicovError) as e:
+        ba._lib.dlt_batch(pt_ptr, xy, xyz, np.array([[30.0, 0.0, 0.0]]))
+    assert e.value.code == ba._lib.NOT_INITIALISED
+    s = ba.Session()
+    with pytest.raises(ba.JaicovError) as e:
+        s.propagate_eo_transform([0], [0], [0], 1.0)          # no problem set, no cofactor matrix
+    assert e.value.code in (ba._lib.NOT_INITIALISED, ba._lib.ILLEGAL_ARGUMENT)
+    # illegal arguments are refused before any device work
+    L = ba._lib.load()
+    assert L.jaicov_dlt_batch(0, 1, None, None, None, None, 0, None, 10, None, None, None) == ba._lib.ILLEGAL_ARGUMENT
+    assert L.jaicov_release_cached_memory() == 0
+
+
+def test_host_mirror_of_the_widened_classes():
+    """Pure host behaviour of the mirrors: Image.get (camera/Image.java:77-79), DLTCoefficients order
+    (dlt/DLTCoefficients.java:38-64), transform() without a device-resident Qxx fails loudly."""
+    pts = ba.ObjectCoordinateArray(['a', 'b', 'c'], np.arange(9.0).reshape(3, 3))
+    cam = ba.Camera(1, 10.0)
+    img = cam.add(7)
+    img.addAll(pts, [0, 2], [[1.0, 2.0], [3.0, 4.0]], [[0.01, 0.01]] * 2)
+    img.add(pts[1], 5.0, 6.0, 0.01, 0.01)
+    assert img.get(pts[0]) == (1.0, 2.0) and img.get(pts[2]) == (3.0, 4.0) and img.get(pts[1]) == (5.0, 6.0)
+    other = ba.ObjectCoordinate('z', 0, 0, 0)
+    assert img.get(other) is None
+    coef = ba.DLTCoefficients(img)
+    ids = [int(p.getParameterType()) for p in coef]
+    assert ids == [611, 612, 613, 614, 621, 622, 623, 624, 631, 632, 633, 111, 112, 113, 251, 252, 253, 261, 262, 263]
+    assert coef.getReference() is img
+    t = ba.CoordinateTransformationExteriorOrientation.getInstance()
+    assert t is ba.CoordinateTransformationExteriorOrientation.getInstance()
+    with pytest.raises(ba.JaicovError):
+        t.transform([pts[0]], {img: [img]}, 1.0, ba.UpperSymmPackMatrix(3, np.zeros(6)))
+    RT = ba.DirectLinearTransformation.RestrictionType
+    assert [r.value for r in RT] == [0, 1, 2, 3, 4, 5] and RT.FIXED_PRINCIPAL_POINT_Y.name == 'FIXED_PRINCIPAL_POINT_Y'
