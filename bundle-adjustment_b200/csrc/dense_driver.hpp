@@ -19,6 +19,7 @@
 // tests (tests/emul/host_backend.cpp, test-only); the product instantiates it with the CUDA backend only.
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 
 namespace jaicov {
@@ -34,6 +35,45 @@ enum KMode : int {
     K_ROW_MASK = 5    // output tile (it, jt) is only wanted if its global row roff + 128 it >= ktab[jt]; full contraction
 };
 
+#if defined(__CUDACC__)
+#define JAICOV_HD __host__ __device__
+#else
+#define JAICOV_HD
+#endif
+
+// Tile (it >= jt) of a lower-triangular launch of mt x mt tiles for the linear CTA index l.
+// band == 0: row by row (row it, columns 0 .. it) -- the order every measured number of round 1 was taken with.
+// band  > 0: bands of `band` tile rows, column by column inside a band, so that the CTAs resident together share the
+//            column operand strip and keep the band's row strips in L2 (experiment for the big symmetric products,
+//            JAICOV_TILE_BAND).  Both orders visit every lower tile exactly once and keep
+//            "smaller max(it, jt) first" up to the band height (K_MAX_IJ launches start their longest contractions first).
+JAICOV_HD inline void tri_tile_decode(int64_t l, int mt, int band, int &it, int &jt) {
+    int row = (int)((sqrt(8.0 * (double)l + 1.0) - 1.0) * 0.5);
+    while ((int64_t)(row + 1) * (row + 2) / 2 <= l) row++;
+    while ((int64_t)row * (row + 1) / 2 > l) row--;
+    if (band <= 0) {
+        it = row;
+        jt = (int)(l - (int64_t)row * (row + 1) / 2);
+        return;
+    }
+    const int r0 = row / band * band;
+    const int h = (mt - r0 < band) ? mt - r0 : band;
+    int64_t idx = l - (int64_t)r0 * (r0 + 1) / 2;
+    const int64_t rect = (int64_t)(r0 + 1) * h;        // columns 0 .. r0 hold all h rows of the band
+    if (idx < rect) {
+        jt = (int)(idx / h);
+        it = r0 + (int)(idx % h);
+        return;
+    }
+    idx -= rect;
+    for (int j = r0 + 1; j < r0 + h; j++) {            // the band's own triangle
+        const int cnt = r0 + h - j;
+        if (idx < cnt) { jt = j; it = j + (int)idx; return; }
+        idx -= cnt;
+    }
+    it = jt = mt - 1;                                  // not reached for l < mt (mt + 1) / 2
+}
+
 struct GemmDesc {
     int al = 0;       // 0: A is [m][k] (k contiguous); 1: A is [k][m] (m contiguous)
     int bl = 0;       // 0: B is [n][k] (k contiguous); 1: B is [k][n] (n contiguous)
@@ -47,6 +87,7 @@ struct GemmDesc {
     double *C = nullptr;
     int64_t ldc = 0;
     int tri_out = 0;  // only tiles with tile-row >= tile-col (mt == nt, C on the diagonal)
+    int tile_band = 0;  // tri_out launches: tile order, see tri_tile_decode (0 = row by row)
     int kmode = K_FULL;
     const int32_t *coltab = nullptr; // if set: 2-D launch, blockIdx.y picks the global column tile coltab[y] / 128, blockIdx.x the
     int ncoltab = 0;                 //         global row tile; tiles above the diagonal exit (trapezoid update of many panels at once)

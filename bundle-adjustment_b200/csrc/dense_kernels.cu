@@ -106,10 +106,7 @@ __global__ void __launch_bounds__(GemmShape<BMT>::THREADS, GemmShape<BMT>::CTAS_
     } else {
         const int l = blockIdx.x / SPLIT;
         if (g.tri_out) {
-            it = (int)((sqrt(8.0 * (double)l + 1.0) - 1.0) * 0.5);
-            while ((int64_t)(it + 1) * (it + 2) / 2 <= l) it++;
-            while ((int64_t)it * (it + 1) / 2 > l) it--;
-            jt = l - (int)((int64_t)it * (it + 1) / 2);
+            tri_tile_decode(l, g.mt, g.tile_band, it, jt);
         } else {
             it = l / g.nt;
             jt = l - it * g.nt;
@@ -242,7 +239,11 @@ static void launch_gemm_l(const GemmDesc &g, cudaStream_t s) {
     else launch_gemm_t<AL, BL, 32>(g, tiles, s);
 }
 
-void launch_gemm(const GemmDesc &g, cudaStream_t s) {
+void launch_gemm(const GemmDesc &g_in, cudaStream_t s) {
+    // experiment switch (default off): band-swizzled tile order of the lower-triangular launches, DESIGN.md section 9
+    static const int band = [] { const char *e = getenv("JAICOV_TILE_BAND"); return e ? atoi(e) : 0; }();
+    GemmDesc g = g_in;
+    if (g.tri_out && band > 0 && g.tile_band == 0) g.tile_band = band;
     if (g.al == 0 && g.bl == 0) launch_gemm_l<0, 0>(g, s);
     else if (g.al == 0 && g.bl == 1) launch_gemm_l<0, 1>(g, s);
     else if (g.al == 1 && g.bl == 1) launch_gemm_l<1, 1>(g, s);

@@ -127,6 +127,9 @@ struct HostComm {
 
 extern "C" {
 
+// tile order of the lower-triangular GEMM launches (dense_driver.hpp: tri_tile_decode), for the bijection test
+void emul_tri_tile_decode(int64_t l, int mt, int band, int *it, int *jt) { jaicov::tri_tile_decode(l, mt, band, *it, *jt); }
+
 // distributed Cholesky with `nranks` virtual ranks (threads), panel width pw tiles; on exit every replica must hold
 // the same factor; replica 0 is returned in M (lower), followed by the column-panel inverse of the column tiles
 // owned by each rank (tile c belongs to rank (c / pw) % nranks), gathered into Q (np x np, lower part valid).

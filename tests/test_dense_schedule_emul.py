@@ -73,3 +73,23 @@ def test_distributed_schedule_with_virtual_ranks(emul, nb, nranks, pw, merged):
     Qi = np.linalg.inv(S)
     assert not np.isnan(np.tril(Q)).any()
     np.testing.assert_allclose(np.tril(Q), np.tril(Qi), atol=1e-12 * np.abs(Qi).max())
+
+
+@pytest.mark.parametrize('mt', [1, 2, 7, 8, 9, 24, 61, 127])
+@pytest.mark.parametrize('band', [0, 1, 3, 8, 16])
+def test_tri_tile_order_is_a_bijection(emul, mt, band):
+    """Every tile order of the lower-triangular launches (row by row, band-swizzled) visits each tile (it >= jt) exactly once,
+    and inside the swizzled order a band's tiles are contiguous."""
+    emul.emul_tri_tile_decode.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+    it, jt = ctypes.c_int(), ctypes.c_int()
+    seen = []
+    for l in range(mt * (mt + 1) // 2):
+        emul.emul_tri_tile_decode(l, mt, band, ctypes.byref(it), ctypes.byref(jt))
+        assert 0 <= jt.value <= it.value < mt
+        seen.append((it.value, jt.value))
+    assert len(set(seen)) == len(seen) == mt * (mt + 1) // 2
+    if band > 0:
+        bands = [i // band for i, _ in seen]
+        assert bands == sorted(bands)
+    else:
+        assert seen == sorted(seen)
