@@ -12,8 +12,11 @@ Restates ``DirectLinearTransformation.adjust`` and its helpers
 
 The gradients of the six restrictions are written here in vector form (r1, r2, r3 = rows of the 3 x 3 part of B);
 they are the same functions the reference spells out entry by entry.  Pin: the reference ships no known answers for
-the DLT; the oracle is checked by re-projection of a synthetic camera (tests/test_dlt.py) -- "parity unpinned" with
-respect to reference outputs.
+the DLT; golden vectors were produced by evaluating the reference's own expressions for the six restriction rows and
+misclosures (DPF:100-236) and for the expansion (DLT:208-246) on seeded random inputs
+(tests/golden/make_formula_fixtures.py -> tests/golden/reference_formulas.npz) and this module matches them to 1e-12
+(tests/test_reference_formulas.py); the loop logic (DLT:108-180) is a restatement, checked by the recovery of a synthetic
+pin-hole camera (tests/test_dlt.py).
 """
 from __future__ import annotations
 

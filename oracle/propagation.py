@@ -8,9 +8,11 @@ every object point seen in an image is carried into the frame of that image's re
 
 and the covariance of all transformed coordinates is ``sigma2 * J Qxx J'`` (:110-114).  The reference writes the 45
 entries of a Jacobian block out as scalar expressions (:223-279); here the same derivatives are stated in matrix form
-(R = Rx(omega) Ry(phi) Rz(kappa), :172-184).  Pin: the reference ships no known answers for this function, so the
-Jacobian is checked against central differences of the transformation formula (tests/test_propagation.py) --
-"parity unpinned" with respect to reference outputs.
+(R = Rx(omega) Ry(phi) Rz(kappa), :172-184).  Pin: the reference ships no known answers for this function; golden vectors
+were produced by evaluating the reference's own 45 scalar expressions and its transformation formula for seeded random
+inputs (tests/golden/make_formula_fixtures.py -> tests/golden/reference_formulas.npz) and this module matches them to
+1e-12 (tests/test_reference_formulas.py); in addition the Jacobian is checked against central differences
+(tests/test_propagation.py).  What stays a plain restatement is the final product sigma2 * J Qxx J' (:110-114).
 """
 from __future__ import annotations
 

@@ -1,0 +1,49 @@
+"""The oracles of the widened rows against golden vectors produced by the REFERENCE's own closed-form expressions
+(tests/golden/make_formula_fixtures.py parses and evaluates the Java right-hand sides; the fixture holds numbers only):
+
+* oracle/propagation.py: 45 Jacobian entries + transformed point, tranformation/CoordinateTransformationExteriorOrientation.java:160-279
+* oracle/dlt.py: restriction gradients / misclosures, dlt/DLTPartialDerivativeFactory.java:100-236, and the expansion of the
+  coefficients, dlt/DirectLinearTransformation.java:208-246
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import dlt as od
+from oracle import propagation as op
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_formulas.npz'))
+
+
+def test_transformation_jacobian_matches_reference_expressions():
+    assert G['transform_jacobian'].shape == (12, 3, 15)
+    for inp, J_ref, xyz_ref in zip(G['transform_inputs'], G['transform_jacobian'], G['transform_xyz']):
+        eT, eS, X = inp[0:6], inp[6:12], inp[12:15]
+        np.testing.assert_allclose(op.transform_point(X, eT, eS), xyz_ref, rtol=1e-13, atol=1e-9)
+        J = op.jacobian_block(X, eT, eS)
+        scale = np.abs(J_ref).max()
+        np.testing.assert_allclose(J, J_ref, rtol=0, atol=1e-12 * scale)
+
+
+def test_dlt_restrictions_match_reference_expressions():
+    assert G['restriction_gradients'].shape == (12, 6, 11)
+    for inp, g_ref, w_ref in zip(G['restriction_inputs'], G['restriction_gradients'], G['restriction_misclosures']):
+        b, (c, x0, y0) = inp[:11], inp[11:]
+        for kind in range(6):
+            g, w = od.restriction_row(kind, b, c, x0, y0)
+            np.testing.assert_allclose(g, g_ref[kind], rtol=1e-12, atol=1e-13 * max(1.0, np.abs(g_ref[kind]).max()))
+            assert w == pytest.approx(w_ref[kind], rel=1e-12, abs=1e-13)
+
+
+def test_dlt_expansion_matches_reference_expressions():
+    """x0, y0, cx, cy, the determinant rule and omega / phi / kappa (DLT:208-246) for random coefficient sets."""
+    flips = 0
+    for b, out in zip(G['expansion_inputs'], G['expansion_outputs']):
+        x0, y0, cx, cy = out[:4]
+        det, omega, phi, kappa = out[13:]
+        flips += det < 0
+        _, d = od.expand(b, 1.0)
+        np.testing.assert_allclose([d['x0'], d['y0'], d['cx'], d['cy']], [x0, y0, cx, cy], rtol=1e-12)
+        np.testing.assert_allclose([d['omega'], d['phi'], d['kappa']], [omega, phi, kappa], rtol=1e-11, atol=1e-13)
+    assert 0 < flips < len(G['expansion_inputs'])          # both branches of the determinant rule occur
