@@ -5,6 +5,10 @@
  * written to follow the reference's evaluation and accumulation ORDER so that it can
  * serve as the parity checker for the CUDA path.  Only tests/, __graft_entry__.smoke()
  * and bench.py's cpu_baseline / --impl reference legs may load this file's library.
+ * Pinned (a) at entry level: every Jacobian entry and misclosure of eval_point equals -- bit for bit -- the value the
+ * reference's own formula bodies give when executed (tests/golden/make_jacobian_fixture.py ->
+ * tests/golden/reference_jacobian.npz, tests/test_reference_formulas.py), for all distortion models incl. Zernike; and
+ * (b) end to end against the known answers of the reference's bundled example (tests/test_oracle_golden.py).
  * Compile with -ffp-contract=off (no FMA contraction: the JVM does not fuse).
  *
  * Reference files restated here (paths relative to

@@ -47,3 +47,35 @@ def test_dlt_expansion_matches_reference_expressions():
         np.testing.assert_allclose([d['x0'], d['y0'], d['cx'], d['cy']], [x0, y0, cx, cy], rtol=1e-12)
         np.testing.assert_allclose([d['omega'], d['phi'], d['kappa']], [omega, phi, kappa], rtol=1e-11, atol=1e-13)
     assert 0 < flips < len(G['expansion_inputs'])          # both branches of the determinant rule occur
+
+
+# ---- main path: per-image-point Jacobian rows and misclosures -------------------------------------------------------------------
+J = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_jacobian.npz'))
+CASES = sorted(k[:-2] for k in J.files if k.endswith('_A'))
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_point_jacobian_matches_reference_formulas(case):
+    """oracle/jaicov_oracle.c (K1: collinearity partials PDF:96-193, chain rule DMF:33-101, all five distortion model
+    factories incl. the three Zernike models) against vectors produced by executing the reference's own formulas
+    (tests/golden/make_jacobian_fixture.py)."""
+    from oracle.oracle import FlatProblem, eval_point
+    coefs = [(int(t), int(o), float(v), False) for t, o, v in J[case + '_coefs']]
+    worst = 0.0
+    for inp, A_ref, w_ref in zip(J[case + '_inputs'], J[case + '_A'], J[case + '_w']):
+        io, X0, ang, X, obs = inp[0:3], inp[3:6], inp[6:9], inp[9:12], inp[12:14]
+        scene = {'points': {'xyz': X.reshape(1, 3).copy(), 'fixed': np.zeros((1, 3), bool), 'datum': np.ones(1, bool)},
+                 'cameras': [{'r0': 10.0, 'io_val': io.copy(), 'io_fixed': np.zeros(3, bool), 'coefs': list(coefs),
+                              'images': [{'eo_val': np.concatenate([X0, ang]), 'eo_fixed': np.zeros(6, bool), 'obj': np.array([0], np.int32),
+                                          'xy': obs.reshape(1, 2).copy(), 'sigma': np.full((1, 2), 0.001), 'rho': np.zeros(1)}]}],
+                 'scale_bars': [], 'observed_groups': []}
+        fp = FlatProblem(scene)
+        cols, a0, a1, w, _ = eval_point(fp, 0, 0, 1e-6)
+        assert a0.size == A_ref.shape[1]
+        scale = max(np.abs(A_ref).max(), 1e-300)
+        # per entry: relative to the entry, with a floor of 1e-13 of the largest entry of the row pair
+        tol = 1e-11 * np.abs(A_ref) + 1e-13 * scale
+        assert (np.abs(np.stack([a0, a1]) - A_ref) <= tol).all(), (case, np.abs(np.stack([a0, a1]) - A_ref).max())
+        np.testing.assert_allclose(w, w_ref, rtol=0, atol=1e-12 * max(1.0, np.abs(obs).max()))
+        worst = max(worst, float((np.abs(np.stack([a0, a1]) - A_ref) / (np.abs(A_ref) + 1e-3 * scale)).max()))
+    print(case, 'worst relative entry difference', worst)
