@@ -38,6 +38,8 @@ def expr(e):
     e = re.sub(r'\bType\.(\w+)', r"'\1'", e)
     e = re.sub(r'\bpj/2\b', '(pj//2)', e)                                                       # long / int
     e = re.sub(r'\bthis\.', 'self.', e)
+    e = e.replace('(double)', 'float').replace('floatcount', 'float(count)')
+    e = e.replace('!', ' not ').replace(' not =', '!=')
     return e
 
 
@@ -70,9 +72,9 @@ def transliterate(lines, header):
             emit('else:')
             ind += 1
             continue
-        m = re.match(r'^for\s*\(.*\s(\w+)\s*:\s*(\w+)\)\s*\{$', line)
+        m = re.match(r'^for\s*\(.*\s(\w+)\s*:\s*([\w\.]+)\)\s*\{$', line)
         if m:
-            emit('for %s in %s:' % (m.group(1), m.group(2)))
+            emit('for %s in %s:' % (m.group(1), expr(m.group(2))))
             ind += 1
             continue
         m = re.match(r'^for\s*\(int\s+(\w+)\s*=\s*0;\s*\1\s*<\s*(\w+);\s*\1\+\+\)\s*\{$', line)
@@ -82,6 +84,27 @@ def transliterate(lines, header):
             continue
         assert line.endswith(';'), line
         line = line[:-1].strip()
+        m = re.match(r'^int\s+(\w+)\s*=\s*(this\.\w+\.\w+\(\))\s*\?\s*(\w+)\+\+\s*:\s*-1$', line)     # x = cond ? counter++ : -1
+        if m:
+            emit('%s = -1' % m.group(1))
+            emit('if %s: %s = %s; %s += 1' % (expr(m.group(2)), m.group(1), m.group(3), m.group(3)))
+            continue
+        m = re.match(r'^double\s+(\w+)\[\]\s*=\s*new\s+double\[(\w+)\]$', line)
+        if m:
+            emit('%s = [0.0] * %s' % (m.group(1), m.group(2)))
+            continue
+        m = re.match(r'^(\w+)\+\+$', line)
+        if m:
+            emit('%s += 1' % m.group(1))
+            continue
+        if line.startswith('throw new '):
+            emit('raise ValueError()')
+            continue
+        m = re.match(r'^double\s+(\w+\s*=\s*[^,]+(?:,\s*\w+\s*=\s*[^,]+)+)$', line)              # double a = 0, b = 0, c = 0
+        if m:
+            for part in m.group(1).split(','):
+                emit(expr(part.strip()))
+            continue
         m = RE_DECL.match(line)
         if m:
             line = '%s = %s' % (m.group(1), m.group(2))
@@ -253,6 +276,66 @@ CASES = {
 }
 
 
+# ---- datum condition rows (BundleAdjustment.addDatumConditionRows, BundleAdjustment.java:493-635) ---------------------------------
+class DatumPoint:
+    def __init__(self, xyz, cols, datum):
+        self.p = [Param('OBJ', v, int(c)) for v, c in zip(xyz, cols)]
+        self.datum = bool(datum)
+
+    def getX(self): return self.p[0]
+    def getY(self): return self.p[1]
+    def getZ(self): return self.p[2]
+    def isDatum(self): return self.datum
+
+
+class RankDefect:
+    def __init__(self, flags): self.f = [bool(x) for x in flags]
+    def getDefect(self): return sum(self.f)
+    def estimateTranslationX(self): return self.f[0]
+    def estimateTranslationY(self): return self.f[1]
+    def estimateTranslationZ(self): return self.f[2]
+    def estimateRotationX(self): return self.f[3]
+    def estimateRotationY(self): return self.f[4]
+    def estimateRotationZ(self): return self.f[5]
+    def estimateScale(self): return self.f[6]
+
+
+class Dense:
+    def __init__(self, r, c): self.v = np.zeros((r, c))
+    def set(self, r, c, x): self.v[r, c] = x
+    def get(self, r, c): return self.v[r, c]
+
+
+class Adjustment:
+    def getClass(self): return 'BundleAdjustment'
+
+
+def datum_vectors():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    from oracle.bookkeeping import Bookkeeping
+    from tests.scenes import random_scene
+    g = {'math': math}
+    body = method_body(os.path.join(REF, 'BundleAdjustment.java'), 'private void addDatumConditionRows(')
+    exec(transliterate(body, 'def add_datum_rows(self, N):'), g)
+    out = {}
+    for seed in range(12):
+        sc = random_scene(seed)
+        bk = Bookkeeping(sc)
+        if bk.d == 0:
+            continue
+        pts = sc['points']
+        n = bk.n_unknown + bk.d
+        adj = Adjustment()
+        adj.rankDefect = RankDefect(bk.defect_free)
+        cols = np.asarray(bk.pt_col if hasattr(bk, 'pt_col') else None)
+        adj.objectCoordinates = [DatumPoint(pts['xyz'][p], cols.reshape(-1, 3)[p], pts['datum'][p]) for p in bk.oc_order.tolist()]
+        N = Dense(bk.d, n)
+        g['add_datum_rows'](adj, N)
+        out['seed%d' % seed] = N.v
+    return out
+
+
 def main():
     g = build_functions()
     rng = np.random.default_rng(20261019)
@@ -280,6 +363,9 @@ def main():
         out[name + '_coefs'] = np.array(coefs, float).reshape(-1, 3)
     np.savez_compressed(OUT, **out)
     print('wrote', OUT, {k: v.shape for k, v in out.items() if k.endswith('_A')})
+    dat = datum_vectors()
+    np.savez_compressed(OUT.replace('reference_jacobian', 'reference_datum_rows'), **dat)
+    print('wrote datum rows', {k: v.shape for k, v in dat.items()})
 
 
 if __name__ == '__main__':

@@ -79,3 +79,65 @@ def test_point_jacobian_matches_reference_formulas(case):
         np.testing.assert_allclose(w, w_ref, rtol=0, atol=1e-12 * max(1.0, np.abs(obs).max()))
         worst = max(worst, float((np.abs(np.stack([a0, a1]) - A_ref) / (np.abs(A_ref) + 1e-3 * scale)).max()))
     print(case, 'worst relative entry difference', worst)
+
+
+# ---- datum condition rows ----------------------------------------------------------------------------------------------------------
+D = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_datum_rows.npz'))
+
+
+@pytest.mark.parametrize('key', sorted(D.files, key=lambda k: int(k[4:])))
+def test_datum_rows_match_reference_method(key):
+    """Oracle.datum_rows against BundleAdjustment.addDatumConditionRows (BA:493-635) executed on the same randomized
+    networks (every combination of free translations / rotations / scale that occurs: d = 2 .. 7)."""
+    from oracle.oracle import Oracle
+    from tests.scenes import random_scene
+    o = Oracle(random_scene(int(key[4:])), use_centroid=False)
+    B = o.datum_rows()
+    assert B.shape == D[key].shape and B.shape[0] == o.bk.d
+    np.testing.assert_array_equal(B, D[key])
+
+
+# ---- integer bookkeeping -------------------------------------------------------------------------------------------------------------
+K = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_bookkeeping.npz'))
+BK_SCENES = sorted({k.split('__')[0] for k in K.files})
+
+
+def _bk_scene(name):
+    from tests.scenes import example_scene, random_scene, synthetic_scene
+    if name.startswith('random'):
+        return random_scene(int(name[6:]))
+    if name == 'example':
+        return example_scene()
+    if name == 'config2_small':
+        return synthetic_scene(2, images=10, targets=60)[0]
+    return synthetic_scene(4, images=9, targets=70, free_network=False)[0]
+
+
+@pytest.mark.parametrize('name', BK_SCENES)
+def test_bookkeeping_matches_executed_reference(name):
+    """Rows, columns, counts, rank-defect flags and sigma2apriori -- bit-exact -- of (a) the oracle's Bookkeeping and (b) the
+    product's host side (bundle-adjustment_b200/host.py: BundleAdjustment._prepare, what fills the C ABI) against the values the
+    reference's own prepareUnknownParameters / detectRankDefect produce when executed (tests/golden/make_bookkeeping_fixture.py)."""
+    from oracle.bookkeeping import Bookkeeping
+    from tests.helpers import flat_problem
+    g = lambda k: K['%s__%s' % (name, k)]
+    n_obs, n_unknown, n_io, n_dist, d, n_oc = (int(v) for v in g('counts'))
+    # (a) oracle
+    bk = Bookkeeping(_bk_scene(name))
+    assert (bk.n_obs, bk.n_unknown, bk.n_io, bk.n_dist, bk.d, len(bk.oc_order)) == (n_obs, n_unknown, n_io, n_dist, d, n_oc)
+    assert [bool(f) for f in bk.defect_free] == g('flags').tolist()
+    np.testing.assert_array_equal(np.asarray(bk.pt_col).reshape(-1, 3), g('pt_col'))
+    np.testing.assert_array_equal(np.concatenate(bk.io_col), g('io_col'))
+    np.testing.assert_array_equal(np.concatenate(bk.coef_col) if g('coef_col').size else np.zeros(0, np.int64), g('coef_col'))
+    np.testing.assert_array_equal(np.concatenate(bk.eo_col), g('eo_col'))
+    assert bk.sigma2apriori == g('sigma2')[0]
+    # (b) host mirror: the flat problem handed to the C ABI
+    adj, flat = flat_problem(_bk_scene(name))
+    assert (int(flat['n_observations']), int(flat['n_unknowns']), int(np.sum(flat['free_flags']))) == (n_obs, n_unknown, d)
+    assert [bool(f) for f in flat['free_flags']] == g('flags').tolist()
+    np.testing.assert_array_equal(np.asarray(flat['pt_col']).reshape(-1, 3), g('pt_col'))
+    np.testing.assert_array_equal(np.asarray(flat['io_col']), g('io_col'))
+    np.testing.assert_array_equal(np.asarray(flat['coef_col']), g('coef_col'))
+    np.testing.assert_array_equal(np.asarray(flat['eo_col']), g('eo_col'))
+    assert adj.getVarianceFactorApriori() == g('sigma2')[0]
+    assert (adj.getNumberOfObservations(), adj.getNumberOfUnknownParameters(), adj.getNumberOfDatumConditions()) == (n_obs, n_unknown, d)
