@@ -47,58 +47,8 @@ def cut_group_loops(lines):
     return out
 
 
-def logical_lines(lines):
-    """Joins the physical lines of a multi-line `if (` condition."""
-    out, buf = [], None
-    for l in lines:
-        s = re.sub(r'//.*$', '', l).strip()
-        if buf is not None:
-            buf += ' ' + s
-            if buf.count('(') == buf.count(')'):
-                out.append(buf)
-                buf = None
-            continue
-        if s.startswith('if (') and s.count('(') != s.count(')'):
-            buf = s
-            continue
-        out.append(l)
-    return out
-
-
 def pre(lines):
-    res = []
-    for l in logical_lines(cut_group_loops(lines)):
-        s = l
-        s = re.sub(r'new LinkedHashSet<[^>]*>\(\)', 'OrderedSet()', s)
-        s = re.sub(r'DefectType\.(\w+)', r"'\1'", s)
-        # x += cond ? 1 : 0;
-        s = re.sub(r'^(\s*[\w\.]+\s*\+=\s*)(.+?)\s*\?\s*1\s*:\s*0\s*;', r'\1(1 if \2 else 0);', s)
-        # f(cond ? a : b)
-        s = re.sub(r"\((\w+)\s*\?\s*('\w+')\s*:\s*('\w+')\)", r'(\2 if \1 else \3)', s)
-        # g( counter++ );  ->  g( counter ); counter += 1;
-        m = re.match(r'^(\s*)(.*\(\s*)(this\.\w+)\+\+(\s*\)\s*;)\s*$', s)
-        if m:
-            res.append('%s%s%s%s' % (m.group(1), m.group(2), m.group(3), m.group(4)))
-            res.append('%s%s += 1;' % (m.group(1), m.group(3)))
-            continue
-        m = re.match(r'^(\s*)(this\.\w+)\+\+;\s*$', s)
-        if m:
-            s = '%s%s += 1;' % (m.group(1), m.group(2))
-        # brace-less for-each: give it braces around the single statement that follows
-        res.append(s)
-    # brace-less `for (...)` followed by one statement -> add braces
-    out, i = [], 0
-    while i < len(res):
-        s = res[i].strip()
-        if re.match(r'^for\s*\(.*\)$', s):
-            out.append(res[i] + ' {')
-            out.append(res[i + 1])
-            out.append('}')
-            i += 2
-            continue
-        out.append(res[i])
-        i += 1
-    return out
+    return cut_group_loops(lines)
 
 
 # ---- stubs -----------------------------------------------------------------------------------------------------------------------

@@ -38,35 +38,86 @@ def expr(e):
     e = re.sub(r'\bType\.(\w+)', r"'\1'", e)
     e = re.sub(r'\bpj/2\b', '(pj//2)', e)                                                       # long / int
     e = re.sub(r'\bthis\.', 'self.', e)
+    e = re.sub(r'\bnew\s+LinkedHashSet<[^>]*>\(\)', 'OrderedSet()', e)
+    e = re.sub(r'\bnew\s+HashSet<[^>]*>\(\)', 'JSet()', e)
+    e = re.sub(r'\bnew\s+ArrayList<[^>]*>\(', 'JList(', e)
+    e = re.sub(r'\bnew\s+', '', e)
+    e = re.sub(r'\bnull\b', 'None', e)
+    e = re.sub(r'\btrue\b', 'True', e)
+    e = re.sub(r'\bfalse\b', 'False', e)
+    e = re.sub(r'\bCollections\.sort\((\w+)\)', r'\1.sort()', e)
+    e = re.sub(r'\bDefectType\.(\w+)', r"'\1'", e)
+    e = re.sub(r"\((\w+)\s*\?\s*('\w+')\s*:\s*('\w+')\)", r'(\2 if \1 else \3)', e)                # f(cond ? 'A' : 'B')
+    e = re.sub(r'\((?:ImageCoordinate|ScaleBar)\)', '', e)
     e = e.replace('(double)', 'float').replace('floatcount', 'float(count)')
     e = e.replace('!', ' not ').replace(' not =', '!=')
     return e
 
 
-def transliterate(lines, header):
-    """Java block (list of source lines, without the enclosing braces) -> Python function source."""
-    out, ind, single = [header], 1, 0
-
-    def emit(text):
-        nonlocal single
-        out.append('    ' * (ind + (1 if single else 0)) + text)
-        single = 0
-
+def clean(lines):
+    """Comments out, blank lines out, multi-line `if (` conditions joined."""
+    out, buf = [], None
     for raw in lines:
         line = re.sub(r'/\*.*?\*/', '', raw)
         line = re.sub(r'//.*$', '', line).strip()
         if not line:
             continue
+        if buf is not None:
+            buf += ' ' + line
+            if buf.count('(') == buf.count(')'):
+                out.append(buf)
+                buf = None
+            continue
+        if re.match(r'^(else\s+)?if\s*\(', line) and line.count('(') != line.count(')'):
+            buf = line
+            continue
+        out.append(line)
+    return out
+
+
+RE_HEAD = re.compile(r'^(?:(?:else\s+)?if\s*\(.*\)|for\s*\(.*\)|else)$')
+
+
+def bracify(lines):
+    """Gives every brace-less if / else / for body its braces (recursively), so that blocks are always explicit."""
+    out = []
+
+    def statement(i):
+        line = lines[i]
+        if RE_HEAD.match(line):
+            out.append(line + ' {')
+            i = statement(i + 1)
+            out.append('}')
+            return i
+        out.append(line)
+        if line.endswith('{'):
+            i += 1
+            while lines[i] != '}':
+                i = statement(i)
+            out.append('}')
+        return i + 1
+
+    i = 0
+    while i < len(lines):
+        i = statement(i)
+    return out
+
+
+def transliterate(lines, header):
+    """Java block (list of source lines, without the enclosing braces) -> Python function source."""
+    out, ind = [header], 1
+
+    def emit(text):
+        out.append('    ' * ind + text)
+
+    for line in bracify(clean(lines)):
         if line == '}':
             ind -= 1
             continue
-        m = re.match(r'^(else\s+)?if\s*\((.*)\)\s*(\{)?$', line)
+        m = re.match(r'^(else\s+)?if\s*\((.*)\)\s*\{$', line)
         if m:
             emit(('elif ' if m.group(1) else 'if ') + expr(m.group(2)) + ':')
-            if m.group(3):
-                ind += 1
-            else:
-                single = 1
+            ind += 1
             continue
         if line == 'else {':
             emit('else:')
@@ -77,9 +128,9 @@ def transliterate(lines, header):
             emit('for %s in %s:' % (m.group(1), expr(m.group(2))))
             ind += 1
             continue
-        m = re.match(r'^for\s*\(int\s+(\w+)\s*=\s*0;\s*\1\s*<\s*(\w+);\s*\1\+\+\)\s*\{$', line)
+        m = re.match(r'^for\s*\(int\s+(\w+)\s*=\s*(\w+);\s*\1\s*<\s*([\w\.\(\)]+);\s*\1\+\+\)\s*\{$', line)
         if m:
-            emit('for %s in range(%s):' % (m.group(1), m.group(2)))
+            emit('for %s in range(%s, %s):' % (m.group(1), m.group(2), expr(m.group(3))))
             ind += 1
             continue
         assert line.endswith(';'), line
@@ -93,9 +144,14 @@ def transliterate(lines, header):
         if m:
             emit('%s = [0.0] * %s' % (m.group(1), m.group(2)))
             continue
-        m = re.match(r'^(\w+)\+\+$', line)
+        m = re.match(r'^([\w\.]+)\+\+$', line)
         if m:
-            emit('%s += 1' % m.group(1))
+            emit('%s += 1' % expr(m.group(1)))
+            continue
+        m = re.match(r'^(.*\(\s*)(this\.\w+)\+\+(\s*\))$', line)                                  # f( this.counter++ )
+        if m:
+            emit(expr(m.group(1) + m.group(2) + m.group(3)))
+            emit('%s += 1' % expr(m.group(2)))
             continue
         if line.startswith('throw new '):
             emit('raise ValueError()')
@@ -104,6 +160,10 @@ def transliterate(lines, header):
         if m:
             for part in m.group(1).split(','):
                 emit(expr(part.strip()))
+            continue
+        m = re.match(r'^(\s*[\w\.]+\s*\+=\s*)(.+?)\s*\?\s*1\s*:\s*0$', line)                        # x += cond ? 1 : 0
+        if m:
+            emit(expr('%s(1 if %s else 0)' % (m.group(1), m.group(2))))
             continue
         m = RE_DECL.match(line)
         if m:
@@ -230,6 +290,26 @@ COEF_TYPES = {121: 'RADIAL_POLYNOMIAL_A', 131: 'TANGENTIAL_POLYNOMIAL_B', 132: '
               151: 'DISTANCE_POLYNOMIAL_D', 161: 'ZERNIKE_POLYNOMIAL_X', 162: 'ZERNIKE_POLYNOMIAL_Y', 163: 'ZERNIKE_POLYNOMIAL_Z'}
 
 
+def apply_models(g, P, r0, ce, cols, A, w):
+    """The switch of PartialDerivativeFactory.java:420-444 over Camera.getDistortionModels(), whose order is the ordinal order
+    of DistortionModel.Type (camera/Camera.java:47, camera/distortion/DistortionModel.java:29-37).  P: {type id: [Param]}."""
+    zero = lambda: Param('none', 0.0, MAXV)
+    if 141 in P or 142 in P:
+        g['affinity'](Model([], r0, Cx=(P.get(141) or [zero()])[0], Cy=(P.get(142) or [zero()])[0]), ce, cols, A, w)
+    if 131 in P or 132 in P or 133 in P:
+        g['tangential'](Model(P.get(131, []), r0, Bx=(P.get(132) or [zero()])[0], By=(P.get(133) or [zero()])[0]), ce, cols, A, w)
+    if 121 in P:
+        g['radial'](Model(P[121], r0), ce, cols, A, w)
+    if 151 in P:
+        g['distance'](Model(P[151], r0), ce, cols, A, w)
+    if 161 in P:
+        g['zernike_xy'](Model(P[161], r0, 'ZERNIKE_X'), ce, cols, A, w, 'ZERNIKE_X')
+    if 162 in P:
+        g['zernike_xy'](Model(P[162], r0, 'ZERNIKE_Y'), ce, cols, A, w, 'ZERNIKE_Y')
+    if 163 in P:
+        g['zernike_gradient'](Model(P[163], r0), ce, cols, A, w)
+
+
 def evaluate(g, io, eo, X, r0, coefs, obs):
     """io = (x0, y0, c); coefs = [(type id, order, value)] in slot order 12...; returns A (2, 12 + ncoef), w (2)."""
     ns = 12 + len(coefs)
@@ -248,22 +328,7 @@ def evaluate(g, io, eo, X, r0, coefs, obs):
     P = {}
     for k, (t, o, v) in enumerate(coefs):
         P.setdefault(t, []).append(Param(COEF_TYPES[t], v, 12 + k, o, ZernikePoly(o) if t in (161, 162, 163) else None))
-    zero = lambda: Param('none', 0.0, MAXV)
-    # model order of Camera.getDistortionModels(): enum ordinal order of DistortionModel.Type
-    if 141 in P or 142 in P:
-        g['affinity'](Model([], r0, Cx=(P.get(141) or [zero()])[0], Cy=(P.get(142) or [zero()])[0]), ce, cols, A, w)
-    if 151 in P:
-        g['distance'](Model(P[151], r0), ce, cols, A, w)
-    if 121 in P:
-        g['radial'](Model(P[121], r0), ce, cols, A, w)
-    if 131 in P or 132 in P or 133 in P:
-        g['tangential'](Model(P.get(131, []), r0, Bx=(P.get(132) or [zero()])[0], By=(P.get(133) or [zero()])[0]), ce, cols, A, w)
-    if 163 in P:
-        g['zernike_gradient'](Model(P[163], r0), ce, cols, A, w)
-    if 161 in P:
-        g['zernike_xy'](Model(P[161], r0, 'ZERNIKE_X'), ce, cols, A, w, 'ZERNIKE_X')
-    if 162 in P:
-        g['zernike_xy'](Model(P[162], r0, 'ZERNIKE_Y'), ce, cols, A, w, 'ZERNIKE_Y')
+    apply_models(g, P, r0, ce, cols, A, w)
     return A.v, w.v
 
 

@@ -141,3 +141,36 @@ def test_bookkeeping_matches_executed_reference(name):
     np.testing.assert_array_equal(np.asarray(flat['eo_col']), g('eo_col'))
     assert adj.getVarianceFactorApriori() == g('sigma2')[0]
     assert (adj.getNumberOfObservations(), adj.getNumberOfUnknownParameters(), adj.getNumberOfDatumConditions()) == (n_obs, n_unknown, d)
+
+
+# ---- normal equations ------------------------------------------------------------------------------------------------------------------
+NE = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_normal_equations.npz'))
+
+
+def _ne_scene(name):
+    from tests.scenes import random_scene, synthetic_scene
+    if name == 'random2_scale_bar':
+        return random_scene(2)
+    if name == 'random0_two_cameras':
+        return random_scene(0)
+    if name == 'config3_rho_no_groups':
+        sc = synthetic_scene(3, images=5, targets=30)[0]
+        sc['observed_groups'] = []
+        return sc
+    sc = synthetic_scene(2, images=5, targets=30)[0]
+    cam = sc['cameras'][0]
+    cam['coefs'] = cam['coefs'][:4] + [(131, 1, 1e-4, False)] + cam['coefs'][4:] + [(161, 3, 1e-4, False), (162, 4, 3e-5, False), (163, 5, 2e-5, False)]
+    return sc
+
+
+@pytest.mark.parametrize('name', sorted({k.split('__')[0] for k in NE.files}))
+def test_normal_equations_match_executed_reference(name):
+    """K2/K3: the oracle's N (packed, datum border included) and n against the reference's own stacking path executed on the
+    same network (tests/golden/make_normal_equation_fixture.py): per-point weights incl. correlated image coordinates
+    (PDF:306-318), stackNormalEquationSystem (PDF:475-505), scale bars (PDF:210-283), datum rows (BA:493-635)."""
+    from oracle.oracle import Oracle
+    o = Oracle(_ne_scene(name), use_centroid=False)
+    N, n, _ = o.create_normal_equation()
+    assert N.shape == NE[name + '__N'].shape
+    np.testing.assert_array_equal(N, NE[name + '__N'])
+    np.testing.assert_array_equal(n, NE[name + '__n'])
