@@ -174,3 +174,29 @@ def test_normal_equations_match_executed_reference(name):
     assert N.shape == NE[name + '__N'].shape
     np.testing.assert_array_equal(N, NE[name + '__N'])
     np.testing.assert_array_equal(n, NE[name + '__n'])
+
+
+# ---- Levenberg-Marquardt step control and parameter update ------------------------------------------------------------------------------
+def test_lm_step_control_matches_executed_reference():
+    """Oracle._update_model / update_unknowns against BundleAdjustment.updateModel / updateUnknownParameters (BA:389-462)
+    executed on 400 scripted situations (tests/golden/make_lm_fixture.py): step length, accept / reject, x0.2 / x5,
+    the 1/sqrt(eps) clamp, max|dx| bookkeeping, the update itself -- all values identical."""
+    import types
+    from oracle.oracle import Oracle
+    L = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_lm_steps.npz'))
+    branches = set()
+    for inp, out in zip(L['inputs'], L['outputs']):
+        lam, prev, cur, complete, last_valid = inp[:5]
+        dx, cols, vals = inp[5:11].copy(), inp[11:17].astype(np.int64), inp[17:23].copy()
+        o = Oracle.__new__(Oracle)
+        o.adapted_damping, o.omega, o.last_valid_max_abs_dx, o.max_abs_dx, o.lm_steps = float(lam), float(prev), float(last_valid), 0.0, []
+        # the six scripted parameters spread over the oracle's four parameter stores
+        o.fp = types.SimpleNamespace(xyz=vals[0:3], pt_col=cols[0:3], io_val=vals[3:4], io_col=cols[3:4], coef_val=vals[4:5], coef_col=cols[4:5],
+                                     eo_val=vals[5:6], eo_col=cols[5:6])
+        o.get_omega = lambda d, cur=cur: float(cur)
+        o._update_model(dx, bool(complete))
+        ev = o.lm_steps[0][:2] if o.lm_steps else (-1.0, -1.0)
+        got = np.concatenate([[o.adapted_damping, o.omega, o.max_abs_dx, o.last_valid_max_abs_dx, ev[0], ev[1]], dx, vals])
+        np.testing.assert_array_equal(got, out)
+        branches.add((lam > 0, bool(o.lm_steps and not o.lm_steps[0][2]), o.adapted_damping == 1.0 / np.sqrt(2.0 ** -53)))
+    assert len(branches) >= 4          # plain Gauss-Newton, accepted step, rejected step, clamped damping value
