@@ -9,9 +9,8 @@ Restates, on a plain "raw scene" dict, what the reference does on its object gra
 * ``RankDefect.getDefect``                         ../defect/RankDefect.java:35-130
 
 Pinned: rows, columns, counts, rank-defect flags and sigma2apriori equal -- bit for bit -- what the reference's own
-methods return when executed on 15 networks (tests/golden/make_bookkeeping_fixture.py ->
-tests/golden/reference_bookkeeping.npz, tests/test_reference_formulas.py); the loops over directly observed groups are
-not part of that fixture.
+methods return when executed on 18 networks incl. directly observed groups (tests/golden/make_bookkeeping_fixture.py ->
+tests/golden/reference_bookkeeping.npz, tests/test_reference_formulas.py).
 
 Raw scene (insertion-ordered, exactly what a user of the reference API would have built)::
 

@@ -12,10 +12,8 @@ Run in the build container only (reads /root/reference):
 
 How: as in make_jacobian_fixture.py the Java method bodies are transliterated to Python text mechanically and exec'ed
 against stub objects standing in for the Java object graph (cameras -> images -> image coordinates -> object coordinates,
-scale bars).  The two loops over DirectlyObservedParameterGroup use `switch` statements the transliterator does not
-handle; they are cut out, and none of the generated networks has such groups -- that part of the bookkeeping stays
-pinned by oracle-vs-host comparison only.  RankDefect (defect/RankDefect.java:25-130) is a bag of seven flags and is
-restated as a stub.  The fixture stores numbers only.
+scale bars, directly observed parameter groups).  RankDefect (defect/RankDefect.java:25-130) is a bag of seven flags and
+is restated as a stub.  The fixture stores numbers only.
 """
 import os
 import re
@@ -48,7 +46,7 @@ def cut_group_loops(lines):
 
 
 def pre(lines):
-    return cut_group_loops(lines)
+    return lines
 
 
 # ---- stubs -----------------------------------------------------------------------------------------------------------------------
@@ -87,7 +85,7 @@ class It:
 class Point:
     def __init__(self, fixed):
         self.p = [UP('OBJECT_COORDINATE_' + 'XYZ'[k], self, bool(fixed[k])) for k in range(3)]
-        self.seen = False
+        self.seen = False          # (the reference's `objectCoordinate.iterator().hasNext()`: seen in at least one image)
 
     def getX(self): return self.p[0]
     def getY(self): return self.p[1]
@@ -137,6 +135,40 @@ class ScaleBar(list):
     def getLength(self): return self[0]
     def getObjectCoordinateA(self): return self.a
     def getObjectCoordinateB(self): return self.b
+
+
+class ObsParam:
+    """ObservationParameter of a directly observed group: reference = the observed UnknownParameter."""
+    def __init__(self, ref, variance, value=0.0): self.ref, self.variance, self.value, self.row = ref, float(variance), float(value), -1
+    def getReference(self): return self.ref
+    def getParameterType(self): return self.ref.getParameterType()
+    def getVariance(self): return self.variance
+    def getValue(self): return self.value
+    def setValue(self, v): self.value = v
+    def setRow(self, r): self.row = r
+
+
+def group_targets(scene, P, cameras):
+    """UnknownParameter objects addressed by the scene's (kind, index, comp) references."""
+    images = [im for c in cameras for im in c]
+
+    def target(kind, index, comp):
+        if kind == 'point':
+            return P[index].p[comp]
+        if kind == 'io':
+            return cameras[index].io[comp]
+        if kind == 'coef':
+            return cameras[index].models[0][comp]
+        return images[index].eo[comp]
+    return target
+
+
+def variances_of(group):
+    r = len(group['refs'])
+    if group.get('dispersion') is not None:
+        ap = np.asarray(group['dispersion'], float)
+        return [ap[k + k * (k + 1) // 2] for k in range(r)]      # DirectlyObservedParameterGroup.java:55-57
+    return list(np.asarray(group['var'], float))
 
 
 class RankDefect:
@@ -198,12 +230,16 @@ def run(scene):
         adj.cameras.append(Camera(images, cam['io_fixed'], [c[3] for c in cam['coefs']]))
     for (a, b, _length, sigma) in scene.get('scale_bars', []):
         adj.scaleBars.add(ScaleBar(P[int(a)], P[int(b)], float(sigma)))
+    target = group_targets(scene, P, adj.cameras)
+    for grp in scene.get('observed_groups', []):
+        adj.observedParameterGroups.append([ObsParam(target(*ref), v) for ref, v in zip(grp['refs'], variances_of(grp))])
     adj.prepareUnknownParameters()
     col = lambda plist: np.array([p.getColumn() for p in plist], np.int64)
     return dict(pt_col=np.array([[p.getColumn() for p in q.p] for q in P], np.int64).reshape(-1, 3),
                 io_col=np.concatenate([col(c.io) for c in adj.cameras]),
                 coef_col=np.concatenate([col(c.models[0]) for c in adj.cameras]) if any(c.models[0] for c in adj.cameras) else np.zeros(0, np.int64),
                 eo_col=np.concatenate([col(im.eo) for c in adj.cameras for im in c]),
+                group_rows=np.array([o.row for g in adj.observedParameterGroups for o in g], np.int64),
                 counts=np.array([adj.numberOfObservations, adj.numberOfUnknownParameters, adj.numberOfInteriorOrientations,
                                  adj.numberOfDistortionParameters, adj.rankDefect.getDefect(), len(adj.objectCoordinates)], np.int64),
                 flags=np.array(adj.rankDefect.flags(), bool), sigma2=np.array([adj.sigma2apriori]))
@@ -216,6 +252,32 @@ def scenes():
     yield 'example', example_scene()
     yield 'config2_small', synthetic_scene(2, images=10, targets=60)[0]
     yield 'config4_fixed_datum', synthetic_scene(4, images=9, targets=70, free_network=False)[0]
+    yield 'config3_observed_points', synthetic_scene(3, images=6, targets=40)[0]
+    yield 'observed_eo_io', observed_eo_io_scene()
+    yield 'observed_omega_only', observed_omega_only_scene()
+
+
+def observed_eo_io_scene():
+    """Free network plus directly observed exterior-orientation and interior-orientation parameters (diagonal weights):
+    exercises the CAMERA_* branches of detectRankDefect and a coordinate that enters only through a group."""
+    from tests.scenes import synthetic_scene
+    sc, truth = synthetic_scene(2, images=7, targets=45)
+    eo = truth['eo']
+    sc['observed_groups'] = [
+        {'refs': [('eo', 1, 0), ('eo', 1, 1), ('eo', 1, 2), ('eo', 1, 3), ('eo', 1, 5)], 'obs': eo[1][[0, 1, 2, 3, 5]] + 0.01,
+         'var': np.array([0.01, 0.01, 0.01, 1e-6, 1e-6]), 'dispersion': None},
+        {'refs': [('eo', 4, 0), ('eo', 4, 4), ('io', 0, 2), ('coef', 0, 4)], 'obs': np.array([eo[4][0], eo[4][4], 28.8, -2e-4]),
+         'var': np.array([0.04, 4e-6, 1e-4, 1e-10]), 'dispersion': None}]
+    return sc
+
+
+def observed_omega_only_scene():
+    """Free network with one directly observed rotation angle and one observed X0: a partial datum (d = 5)."""
+    from tests.scenes import synthetic_scene
+    sc, truth = synthetic_scene(2, images=7, targets=45)
+    sc['observed_groups'] = [{'refs': [('eo', 2, 3), ('eo', 3, 0)], 'obs': np.array([truth['eo'][2][3], truth['eo'][3][0]]),
+                              'var': np.array([1e-6, 0.01]), 'dispersion': None}]
+    return sc
 
 
 def main():

@@ -48,7 +48,7 @@ def expr(e):
     e = re.sub(r'\bCollections\.sort\((\w+)\)', r'\1.sort()', e)
     e = re.sub(r'\bDefectType\.(\w+)', r"'\1'", e)
     e = re.sub(r"\((\w+)\s*\?\s*('\w+')\s*:\s*('\w+')\)", r'(\2 if \1 else \3)', e)                # f(cond ? 'A' : 'B')
-    e = re.sub(r'\((?:ImageCoordinate|ScaleBar)\)', '', e)
+    e = re.sub(r'\((?:ImageCoordinate|ScaleBar|ObjectCoordinate|UpperSPDPackMatrix)\)', '', e)
     e = e.replace('(double)', 'float').replace('floatcount', 'float(count)')
     e = e.replace('!', ' not ').replace(' not =', '!=')
     return e
@@ -72,6 +72,54 @@ def clean(lines):
             buf = line
             continue
         out.append(line)
+    return out
+
+
+def deswitch(lines):
+    """`switch (x) { case A: case B: ...; break; default: ...; }` over ParameterType constants -> if / else-if chain
+    (the reference uses no fall-through with statements in between, only grouped labels)."""
+    out, i = [], 0
+    while i < len(lines):
+        m = re.match(r'^switch\s*\((.*)\)\s*\{$', lines[i])
+        if not m:
+            out.append(lines[i])
+            i += 1
+            continue
+        subject, groups, labels, body, depth = m.group(1).strip(), [], [], [], 1
+        i += 1
+        while depth > 0:
+            l = lines[i]
+            i += 1
+            if l == '}' and depth == 1:
+                depth = 0
+                break
+            c = re.match(r'^case\s+(\w+)\s*:$', l)
+            if depth == 1 and c:
+                labels.append(c.group(1))
+                continue
+            if depth == 1 and l == 'default:':
+                labels.append(None)
+                continue
+            if depth == 1 and l == 'break;':
+                groups.append((labels, body))
+                labels, body = [], []
+                continue
+            depth += l.count('{') - l.count('}')
+            body.append(l)
+        if labels or body:
+            groups.append((labels, body))
+        first = True
+        for labs, stmts in groups:
+            stmts = deswitch(stmts)
+            if None in labs:
+                if not stmts:
+                    continue
+                out.append('else {' if not first else 'if (true) {')
+            else:
+                cond = ' || '.join('%s == ParameterType.%s' % (subject, lab) for lab in labs)
+                out.append(('if (%s) {' if first else 'else if (%s) {') % cond)
+            out += stmts + ['}']
+            first = False
     return out
 
 
@@ -110,7 +158,7 @@ def transliterate(lines, header):
     def emit(text):
         out.append('    ' * ind + text)
 
-    for line in bracify(clean(lines)):
+    for line in bracify(deswitch(clean(lines))):
         if line == '}':
             ind -= 1
             continue
@@ -148,7 +196,7 @@ def transliterate(lines, header):
         if m:
             emit('%s += 1' % expr(m.group(1)))
             continue
-        m = re.match(r'^(.*\(\s*)(this\.\w+)\+\+(\s*\))$', line)                                  # f( this.counter++ )
+        m = re.match(r'^(.*[\(,]\s*)([\w\.]+)\+\+(\s*[\),].*)$', line)                               # f( counter++ ), f(row, row++, x)
         if m:
             emit(expr(m.group(1) + m.group(2) + m.group(3)))
             emit('%s += 1' % expr(m.group(2)))
@@ -156,7 +204,7 @@ def transliterate(lines, header):
         if line.startswith('throw new '):
             emit('raise ValueError()')
             continue
-        m = re.match(r'^double\s+(\w+\s*=\s*[^,]+(?:,\s*\w+\s*=\s*[^,]+)+)$', line)              # double a = 0, b = 0, c = 0
+        m = re.match(r'^(?:double|int)\s+(\w+\s*=\s*[^,]+(?:,\s*\w+\s*=\s*[^,]+)+)$', line)       # double a = 0, b = 0, c = 0
         if m:
             for part in m.group(1).split(','):
                 emit(expr(part.strip()))

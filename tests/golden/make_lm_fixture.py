@@ -60,7 +60,7 @@ def ternaries(lines):
     """`lhs = cond ? a : b;` -> explicit if / else (the only ternary form these two methods use)."""
     out = []
     for l in lines:
-        m = re.match(r'^(\s*)([\w\.]+)\s*=\s*(.+?)\s*\?\s*(.+?)\s*:\s*(.+);\s*$', l)
+        m = re.match(r'^(\s*)(?:double\s+|int\s+)?([\w\.]+)\s*=\s*(.+?)\s*\?\s*(.+?)\s*:\s*(.+);\s*$', l)
         if m and '//' not in l.split('?')[0]:
             ind, lhs, cond, a, b = m.groups()
             # one compound statement (so that a brace-less `if (...)` in front of it keeps governing all of it)

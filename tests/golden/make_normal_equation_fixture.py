@@ -7,8 +7,13 @@ and n of small networks, produced by EXECUTING the reference's own code path
     PartialDerivativeFactory.stackNormalEquationSystem                               :475-505
     BundleAdjustment.addDatumConditionRows                                           BundleAdjustment.java:493-635
 
+    PartialDerivativeFactory.getPartialDerivativeDirectlyObservedParameters          :447-473
+    DirectlyObservedParameterGroup.getWeightMatrix                                   parameter/DirectlyObservedParameterGroup.java:67-91
+    BundleAdjustment.centroidCoordinates                                             BundleAdjustment.java:115-201
+
 in the order of BundleAdjustment.createNormalEquation (:789-799: every observation group in insertion order, then the
-datum rows).  Method bodies are transliterated mechanically (make_jacobian_fixture.transliterate) and exec'ed on stub
+datum rows).  MathExtension.inv(UpperSPDPackMatrix) (dpptrf + dpptri, MathExtension.java:304-324) is third-party LAPACK in
+the reference; here it is the same LAPACK routine pair out of scipy's OpenBLAS (oracle/lapack_packed.py).  Method bodies are transliterated mechanically (make_jacobian_fixture.transliterate) and exec'ed on stub
 objects; the `switch` over the camera's distortion models (:420-444) is replaced by make_jacobian_fixture.apply_models,
 which calls the transliterated model factories in the reference's order.  Numbers only are stored.
 
@@ -26,6 +31,8 @@ sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import make_bookkeeping_fixture as tb  # noqa: E402
 import make_jacobian_fixture as tj  # noqa: E402
+import make_lm_fixture as tl  # noqa: E402
+from oracle.lapack_packed import inv_spd_packed  # noqa: E402
 
 PDF = os.path.join(tj.REF, 'derivation', 'PartialDerivativeFactory.java')
 OUT = os.path.join(HERE, 'reference_normal_equations.npz')
@@ -63,6 +70,41 @@ class UpperSymmPackMatrix:
     def add(self, r, c, x): self.ap[self._k(r, c)] += x
 
 
+class UpperSPDPackMatrix(UpperSymmPackMatrix):
+    def scale(self, a):
+        self.ap *= a
+        return self
+
+
+class MathExtension:
+    @staticmethod
+    def inv(M):
+        inv_spd_packed(M.ap, M.n)
+        return M
+
+
+class Group(list):
+    """DirectlyObservedParameterGroup (parameter/DirectlyObservedParameterGroup.java:36-60): observations, optional dispersion."""
+    def __init__(self, obs, dispersion):
+        super().__init__(obs)
+        self.observedParameters = self
+        self.sigma2apriori = -1
+        self.weightMatrix = None
+        if dispersion is not None:
+            self.weightMatrix = UpperSPDPackMatrix(len(obs))
+            self.weightMatrix.ap[:] = np.asarray(dispersion, float)
+
+    def hasFullyPopulatedWeightMatrix(self): return self.weightMatrix is not None
+    def getNumberOfParameters(self): return len(self)
+
+
+class Centroid:
+    def __init__(self): self.p = [VUP('C', 0.0), VUP('C', 0.0), VUP('C', 0.0)]
+    def getX(self): return self.p[0]
+    def getY(self): return self.p[1]
+    def getZ(self): return self.p[2]
+
+
 class JSet(set):
     pass
 
@@ -84,6 +126,7 @@ class VUP(tb.UP):
         self.value, self.order, self.poly = float(value), order, poly
 
     def getValue(self): return self.value
+    def setValue(self, v): self.value = v
     def getOrder(self): return self.order
     def getZernikePolynomial(self): return self.poly
 
@@ -167,6 +210,7 @@ class ScaleBar(list):
 
 def build(g):
     """Transliterated PartialDerivativeFactory methods + BundleAdjustment.addDatumConditionRows in namespace g."""
+    g.update(UpperSPDPackMatrix=UpperSPDPackMatrix, MathExtension=MathExtension)
     g.update(DenseVector=DenseVector, DenseMatrix=DenseMatrix, UpperSymmBandMatrix=UpperSymmBandMatrix, UpperSymmPackMatrix=UpperSymmPackMatrix,
              JSet=JSet, JList=JList, GaussMarkovEquations=GaussMarkovEquations)
 
@@ -193,12 +237,19 @@ def build(g):
                           'def getPartialDerivativeScaleBar(sigma2apriori, NEQ, neq, scaleBar):'), g)
     exec(tj.transliterate(tj.method_body(PDF, 'private static GaussMarkovEquations stackNormalEquationSystem('),
                           'def stackNormalEquationSystem(NEQ, neq, A, P, w, columns, diagonalWeighting):'), g)
+    exec(tj.transliterate(tj.method_body(PDF, 'private static GaussMarkovEquations getPartialDerivativeDirectlyObservedParameters('),
+                          'def getPartialDerivativeDirectlyObservedParameters(sigma2apriori, NEQ, neq, observedParameterGroup):'), g)
+    dopg = os.path.join(tj.REF, 'parameter', 'DirectlyObservedParameterGroup.java')
+    exec(tj.transliterate(tj.method_body(dopg, 'public Matrix getWeightMatrix('), 'def getWeightMatrix(self, sigma2apriori):'), g)
+    Group.getWeightMatrix = g['getWeightMatrix']
+    exec(tj.transliterate(tl.ternaries(tj.method_body(tb.BA, 'private void centroidCoordinates(')), 'def centroidCoordinates(self, invert):'), g)
+    tb.Adjustment.centroidCoordinates = g['centroidCoordinates']
     exec(tj.transliterate(tj.method_body(tb.BA, 'private void addDatumConditionRows('), 'def addDatumConditionRows(self, N):'), g)
     tb.Adjustment.addDatumConditionRows = g['addDatumConditionRows']
     tb.Adjustment.getClass = lambda self: 'BundleAdjustment'
 
 
-def run(g, scene):
+def graph(scene):
     pts = scene['points']
     P = [Point(pts['xyz'][k], pts['fixed'][k], pts['datum'][k]) for k in range(len(pts['xyz']))]
     adj = tb.Adjustment()
@@ -212,12 +263,42 @@ def run(g, scene):
         adj.cameras.append(camera)
     for (a, b, length, sigma) in scene.get('scale_bars', []):
         adj.scaleBars.add(ScaleBar(P[int(a)], P[int(b)], float(length), float(sigma)))
+    images = [im for c in adj.cameras for im in c]
+
+    def target(kind, index, comp):
+        if kind == 'point':
+            return P[index].p[comp]
+        if kind == 'io':
+            return adj.cameras[index].io[comp]
+        if kind == 'coef':
+            return adj.cameras[index].coefs[comp]
+        return images[index].eo[comp]
+    for grp in scene.get('observed_groups', []):
+        obs = [tb.ObsParam(target(*ref), v, val) for ref, v, val in zip(grp['refs'], tb.variances_of(grp), grp['obs'])]
+        adj.observedParameterGroups.append(Group(obs, grp.get('dispersion')))
+    adj.centroid = Centroid()
     adj.prepareUnknownParameters()
+    return adj, P, images
+
+
+def run_centroid(scene):
+    """centroidCoordinates(false) on the freshly prepared network: the centroid and every shifted value."""
+    adj, P, images = graph(scene)
+    adj.centroidCoordinates(False)
+    return (np.array([p.getValue() for p in adj.centroid.p]), np.array([[q.getValue() for q in pt.p] for pt in P]),
+            np.array([[q.getValue() for q in im.eo] for im in images]),
+            np.array([o.getValue() for grp in adj.observedParameterGroups for o in grp]))
+
+
+def run(g, scene):
+    adj, P, images = graph(scene)
     n = adj.numberOfUnknownParameters + adj.rankDefect.getDefect()
     N, nv = UpperSymmPackMatrix(n), DenseVector(n)
     for grp in adj.observationGroups:                        # createNormalEquation, BundleAdjustment.java:795-797
         if isinstance(grp, ImageCoordinate):
             g['getPartialDerivativeImageCoordinate'](adj.sigma2apriori, N, nv, grp)
+        elif isinstance(grp, Group):
+            g['getPartialDerivativeDirectlyObservedParameters'](adj.sigma2apriori, N, nv, grp)
         else:
             g['getPartialDerivativeScaleBar'](adj.sigma2apriori, N, nv, grp)
     adj.addDatumConditionRows(N)                             # :799
@@ -235,6 +316,8 @@ def scenes():
     cam = sc['cameras'][0]
     cam['coefs'] = cam['coefs'][:4] + [(131, 1, 1e-4, False)] + cam['coefs'][4:] + [(161, 3, 1e-4, False), (162, 4, 3e-5, False), (163, 5, 2e-5, False)]
     yield 'config2_zernike_bi', sc
+    yield 'config3_observed_points_dispersion', synthetic_scene(3, images=5, targets=25)[0]
+    yield 'observed_eo_io', tb.observed_eo_io_scene()
 
 
 def main():
@@ -247,6 +330,14 @@ def main():
         out[name + '__N'] = N
         out[name + '__n'] = n
         print(name, N.size, float(np.abs(N).max()), float(np.abs(n).max()))
+        try:
+            c, xyz, eo, gobs = run_centroid(sc)
+            out[name + '__centroid'] = c
+            out[name + '__centroid_xyz'] = xyz
+            out[name + '__centroid_eo'] = eo
+            out[name + '__centroid_obs'] = gobs
+        except ValueError:                       # UnsupportedOperationException of BundleAdjustment.java:151: unequal counts
+            out[name + '__centroid_refused'] = np.array([1])
     np.savez_compressed(OUT, **out)
     print('wrote', OUT)
 

@@ -110,6 +110,15 @@ def _bk_scene(name):
         return example_scene()
     if name == 'config2_small':
         return synthetic_scene(2, images=10, targets=60)[0]
+    if name == 'config3_observed_points':
+        return synthetic_scene(3, images=6, targets=40)[0]
+    if name.startswith('observed_'):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location('mbf', os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'make_bookkeeping_fixture.py'))
+        # only the two scene builders are used (pure numpy); the module reads /root/reference lazily, not at import
+        mbf = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mbf)
+        return mbf.observed_eo_io_scene() if name == 'observed_eo_io' else mbf.observed_omega_only_scene()
     return synthetic_scene(4, images=9, targets=70, free_network=False)[0]
 
 
@@ -131,6 +140,8 @@ def test_bookkeeping_matches_executed_reference(name):
     np.testing.assert_array_equal(np.concatenate(bk.coef_col) if g('coef_col').size else np.zeros(0, np.int64), g('coef_col'))
     np.testing.assert_array_equal(np.concatenate(bk.eo_col), g('eo_col'))
     assert bk.sigma2apriori == g('sigma2')[0]
+    np.testing.assert_array_equal(np.concatenate([np.asarray(r, np.int64) for r in bk.group_rows]) if len(bk.group_rows) else np.zeros(0, np.int64),
+                                  g('group_rows'))
     # (b) host mirror: the flat problem handed to the C ABI
     adj, flat = flat_problem(_bk_scene(name))
     assert (int(flat['n_observations']), int(flat['n_unknowns']), int(np.sum(flat['free_flags']))) == (n_obs, n_unknown, d)
@@ -157,6 +168,10 @@ def _ne_scene(name):
         sc = synthetic_scene(3, images=5, targets=30)[0]
         sc['observed_groups'] = []
         return sc
+    if name == 'config3_observed_points_dispersion':
+        return synthetic_scene(3, images=5, targets=25)[0]
+    if name == 'observed_eo_io':
+        return _bk_scene('observed_eo_io')
     sc = synthetic_scene(2, images=5, targets=30)[0]
     cam = sc['cameras'][0]
     cam['coefs'] = cam['coefs'][:4] + [(131, 1, 1e-4, False)] + cam['coefs'][4:] + [(161, 3, 1e-4, False), (162, 4, 3e-5, False), (163, 5, 2e-5, False)]
@@ -167,13 +182,32 @@ def _ne_scene(name):
 def test_normal_equations_match_executed_reference(name):
     """K2/K3: the oracle's N (packed, datum border included) and n against the reference's own stacking path executed on the
     same network (tests/golden/make_normal_equation_fixture.py): per-point weights incl. correlated image coordinates
-    (PDF:306-318), stackNormalEquationSystem (PDF:475-505), scale bars (PDF:210-283), datum rows (BA:493-635)."""
+    (PDF:306-318), stackNormalEquationSystem (PDF:475-505), scale bars (PDF:210-283), directly observed groups with diagonal
+    and fully populated dispersion (PDF:447-473, DOPG:67-91), datum rows (BA:493-635)."""
     from oracle.oracle import Oracle
     o = Oracle(_ne_scene(name), use_centroid=False)
     N, n, _ = o.create_normal_equation()
     assert N.shape == NE[name + '__N'].shape
     np.testing.assert_array_equal(N, NE[name + '__N'])
     np.testing.assert_array_equal(n, NE[name + '__n'])
+
+
+@pytest.mark.parametrize('name', sorted({k.split('__')[0] for k in NE.files}))
+def test_centroid_matches_executed_reference(name):
+    """centroidCoordinates(false) (BA:115-201): the centroid, every shifted coordinate of points and projection centres, the
+    shifted observations of directly observed coordinates -- or the refusal when the component counts differ (BA:151)."""
+    from oracle.oracle import Oracle
+    o = Oracle(_ne_scene(name), use_centroid=True)
+    if name + '__centroid_refused' in NE.files:
+        with pytest.raises(RuntimeError):
+            o._centroid(False)
+        return
+    o._centroid(False)
+    np.testing.assert_array_equal(np.asarray(o.centroid, float), NE[name + '__centroid'])
+    np.testing.assert_array_equal(o.fp.xyz.reshape(-1, 3), NE[name + '__centroid_xyz'])
+    np.testing.assert_array_equal(o.fp.eo_val.reshape(-1, 6), NE[name + '__centroid_eo'])
+    gobs = np.concatenate([np.asarray(g['obs'], float) for g in o.fp.groups]) if o.fp.groups else np.zeros(0)
+    np.testing.assert_array_equal(gobs, NE[name + '__centroid_obs'])
 
 
 # ---- Levenberg-Marquardt step control and parameter update ------------------------------------------------------------------------------
