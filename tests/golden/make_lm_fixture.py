@@ -26,10 +26,16 @@ SQRT_EPS = math.sqrt(2.0 ** -53)          # Constant.EPS, Constant.java:61-75; B
 
 
 class JavaMath:
-    pow = staticmethod(math.pow)
+    """java.lang.Math as the transliterated bodies use it: the C library functions plus min / max / abs."""
     min = staticmethod(min)
     max = staticmethod(max)
     abs = staticmethod(abs)
+
+
+for _k in dir(math):
+    if not _k.startswith('_') and not hasattr(JavaMath, _k):
+        _v = getattr(math, _k)
+        setattr(JavaMath, _k, staticmethod(_v) if callable(_v) else _v)
 
 
 class Vec:
@@ -66,8 +72,15 @@ def ternaries(lines):
             # one compound statement (so that a brace-less `if (...)` in front of it keeps governing all of it)
             out += ['%sif (true) {' % ind, '%sif (%s) {' % (ind, cond), '%s%s = %s;' % (ind, lhs, a), '%s}' % ind, '%selse {' % ind,
                     '%s%s = %s;' % (ind, lhs, b), '%s}' % ind, '%s}' % ind]
-        else:
-            out.append(l)
+            continue
+        # f(a, b, cond ? p : q);  ->  if (cond) { f(a, b, p); } else { f(a, b, q); }
+        m = re.match(r'^(\s*)([\w\.]+\(.*,\s*)([^,?]+?)\s*\?\s*(.+?)\s*:\s*(.+?)\);\s*$', l)
+        if m:
+            ind, head, cond, a, b = m.groups()
+            out += ['%sif (true) {' % ind, '%sif (%s) {' % (ind, cond), '%s%s%s);' % (ind, head, a), '%s}' % ind, '%selse {' % ind,
+                    '%s%s%s);' % (ind, head, b), '%s}' % ind, '%s}' % ind]
+            continue
+        out.append(l)
     return out
 
 

@@ -11,8 +11,9 @@ and n of small networks, produced by EXECUTING the reference's own code path
     DirectlyObservedParameterGroup.getWeightMatrix                                   parameter/DirectlyObservedParameterGroup.java:67-91
     BundleAdjustment.centroidCoordinates                                             BundleAdjustment.java:115-201
 
-in the order of BundleAdjustment.createNormalEquation (:789-799: every observation group in insertion order, then the
-datum rows).  MathExtension.inv(UpperSPDPackMatrix) (dpptrf + dpptri, MathExtension.java:304-324) is third-party LAPACK in
+driven by the executed BundleAdjustment.createNormalEquation itself (:789-834: every observation group in insertion
+order, the datum rows, the Levenberg-Marquardt damping of the diagonal, the Jacobi preconditioner V), followed by
+NormalEquationSystem.applyPrecondition (adjustment/NormalEquationSystem.java:82-91).  MathExtension.inv(UpperSPDPackMatrix) (dpptrf + dpptri, MathExtension.java:304-324) is third-party LAPACK in
 the reference; here it is the same LAPACK routine pair out of scipy's OpenBLAS (oracle/lapack_packed.py).  Method bodies are transliterated mechanically (make_jacobian_fixture.transliterate) and exec'ed on stub
 objects; the `switch` over the camera's distortion models (:420-444) is replaced by make_jacobian_fixture.apply_models,
 which calls the transliterated model factories in the reference's order.  Numbers only are stored.
@@ -46,6 +47,11 @@ class DenseVector:
     def get(self, i): return self.v[i]
     def set(self, i, x): self.v[i] = x
     def add(self, i, x): self.v[i] += x
+    def zero(self): self.v[:] = 0.0
+
+
+class NormalEquationSystem:
+    def __init__(self, N, n, V): self.N, self.n, self.V = N, n, V
 
 
 class DenseMatrix:
@@ -56,14 +62,19 @@ class DenseMatrix:
     def add(self, r, c, x): self.v[r, c] += x
 
 
-class UpperSymmBandMatrix(DenseMatrix):
-    def __init__(self, n, kd): super().__init__(n, n)
+class UpperSymmBandMatrix:
+    """Only ever used with zero off-diagonals (kd = 0): a diagonal."""
+    def __init__(self, n, kd): self.d = np.zeros(n)
+    def numRows(self): return self.d.size
+    def get(self, r, c): return self.d[r] if r == c else 0.0
+    def set(self, r, c, x): self.d[r] = x
 
 
 class UpperSymmPackMatrix:
     """no.uib.cipr.matrix.UpperSymmPackMatrix: symmetric, stored column-major packed upper."""
     def __init__(self, n): self.n, self.ap = n, np.zeros(n * (n + 1) // 2)
     def numRows(self): return self.n
+    def numColumns(self): return self.n
     def _k(self, r, c): return (r + c * (c + 1) // 2) if r <= c else (c + r * (r + 1) // 2)
     def get(self, r, c): return self.ap[self._k(r, c)]
     def set(self, r, c, x): self.ap[self._k(r, c)] = x
@@ -246,6 +257,23 @@ def build(g):
     tb.Adjustment.centroidCoordinates = g['centroidCoordinates']
     exec(tj.transliterate(tj.method_body(tb.BA, 'private void addDatumConditionRows('), 'def addDatumConditionRows(self, N):'), g)
     tb.Adjustment.addDatumConditionRows = g['addDatumConditionRows']
+
+    class PDF_:                                             # PartialDerivativeFactory.getPartialDerivative, :199-208 (instanceof chain)
+        @staticmethod
+        def getPartialDerivative(sigma2apriori, NEQ, neq, observations):
+            if isinstance(observations, ImageCoordinate):
+                return g['getPartialDerivativeImageCoordinate'](sigma2apriori, NEQ, neq, observations)
+            if isinstance(observations, ScaleBar):
+                return g['getPartialDerivativeScaleBar'](sigma2apriori, NEQ, neq, observations)
+            return g['getPartialDerivativeDirectlyObservedParameters'](sigma2apriori, NEQ, neq, observations)
+    g.update(PartialDerivativeFactory=PDF_, NormalEquationSystem=NormalEquationSystem)
+    fix = lambda src: src.replace('Constant.EPS', repr(2.0 ** -53)).replace('EstimationType.SIMULATION', "'SIMULATION'")
+    g['math'] = tl.JavaMath
+    exec(fix(tj.transliterate(tl.ternaries(tj.method_body(tb.BA, 'public NormalEquationSystem createNormalEquation(')), 'def createNormalEquation(self):')), g)
+    tb.Adjustment.createNormalEquation = g['createNormalEquation']
+    nes = os.path.join(os.path.dirname(tj.REF), 'NormalEquationSystem.java')
+    exec(tj.transliterate(tl.ternaries(tj.method_body(nes, 'public static void applyPrecondition(UpperSymmBandMatrix V')),
+                          'def applyPrecondition(V, M, m):'), g)
     tb.Adjustment.getClass = lambda self: 'BundleAdjustment'
 
 
@@ -290,19 +318,16 @@ def run_centroid(scene):
             np.array([o.getValue() for grp in adj.observedParameterGroups for o in grp]))
 
 
-def run(g, scene):
+def run(g, scene, damping=0.0):
+    """createNormalEquation() as the first pass of estimateModel() sees it (:207-208: the damping value is taken over in the
+    first pass), then applyPrecondition.  Returns N, n, V and the preconditioned N, n."""
     adj, P, images = graph(scene)
-    n = adj.numberOfUnknownParameters + adj.rankDefect.getDefect()
-    N, nv = UpperSymmPackMatrix(n), DenseVector(n)
-    for grp in adj.observationGroups:                        # createNormalEquation, BundleAdjustment.java:795-797
-        if isinstance(grp, ImageCoordinate):
-            g['getPartialDerivativeImageCoordinate'](adj.sigma2apriori, N, nv, grp)
-        elif isinstance(grp, Group):
-            g['getPartialDerivativeDirectlyObservedParameters'](adj.sigma2apriori, N, nv, grp)
-        else:
-            g['getPartialDerivativeScaleBar'](adj.sigma2apriori, N, nv, grp)
-    adj.addDatumConditionRows(N)                             # :799
-    return N.ap, nv.v
+    adj.estimationType = 'L2NORM'
+    adj.dampingValue, adj.adaptedDampingValue, adj.deriveFirstAdaptedDampingValue = damping, 0.0, damping > 0
+    neq = adj.createNormalEquation()
+    N, nv, V = neq.N.ap.copy(), neq.n.v.copy(), neq.V.d.copy()
+    g['applyPrecondition'](neq.V, neq.N, neq.n)
+    return N, nv, V, neq.N.ap.copy(), neq.n.v.copy()
 
 
 def scenes():
@@ -326,9 +351,15 @@ def main():
     build(g)
     out = {}
     for name, sc in scenes():
-        N, n = run(g, sc)
+        N, n, V, Np, npre = run(g, sc)
         out[name + '__N'] = N
         out[name + '__n'] = n
+        out[name + '__V'] = V
+        out[name + '__N_preconditioned'] = Np
+        out[name + '__n_preconditioned'] = npre
+        Nd, _, Vd, _, _ = run(g, sc, damping=0.7)
+        out[name + '__N_damped'] = Nd
+        out[name + '__V_damped'] = Vd
         print(name, N.size, float(np.abs(N).max()), float(np.abs(n).max()))
         try:
             c, xyz, eo, gobs = run_centroid(sc)

@@ -185,11 +185,26 @@ def test_normal_equations_match_executed_reference(name):
     (PDF:306-318), stackNormalEquationSystem (PDF:475-505), scale bars (PDF:210-283), directly observed groups with diagonal
     and fully populated dispersion (PDF:447-473, DOPG:67-91), datum rows (BA:493-635)."""
     from oracle.oracle import Oracle
+    import ctypes
+    from oracle.oracle import lib
     o = Oracle(_ne_scene(name), use_centroid=False)
-    N, n, _ = o.create_normal_equation()
+    o.derive_first_damping, o.adapted_damping = False, 0.0
+    N, n, V = o.create_normal_equation()
     assert N.shape == NE[name + '__N'].shape
     np.testing.assert_array_equal(N, NE[name + '__N'])
     np.testing.assert_array_equal(n, NE[name + '__n'])
+    # Jacobi preconditioner (BA:824-828) and NormalEquationSystem.applyPrecondition (NES:82-91)
+    np.testing.assert_array_equal(V, NE[name + '__V'])
+    lib().orc_apply_precondition(o.fp.n, V.ctypes.data, N.ctypes.data, n.ctypes.data)
+    np.testing.assert_array_equal(N, NE[name + '__N_preconditioned'])
+    np.testing.assert_array_equal(n, NE[name + '__n_preconditioned'])
+    # Levenberg-Marquardt damping of the diagonal in the first pass (BA:801-822)
+    o2 = Oracle(_ne_scene(name), use_centroid=False, damping=0.7)
+    o2.derive_first_damping, o2.adapted_damping = True, 0.0
+    Nd, _, Vd = o2.create_normal_equation()
+    np.testing.assert_array_equal(Nd, NE[name + '__N_damped'])
+    np.testing.assert_array_equal(Vd, NE[name + '__V_damped'])
+    assert o2.adapted_damping == 0.7 and not o2.derive_first_damping
 
 
 @pytest.mark.parametrize('name', sorted({k.split('__')[0] for k in NE.files}))
