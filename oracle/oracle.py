@@ -7,9 +7,16 @@ Follows ``BundleAdjustment.estimateModel`` (BundleAdjustment.java:203-387) pass 
 (:115-201) and the datum border rows (:493-635).  Per-observation arithmetic is in jaicov_oracle.c
 (same directory), the factorisation is reference LAPACK out of scipy's OpenBLAS (lapack_packed.py).
 
-Parity pin: tests/test_oracle_golden.py checks this oracle against the AICON report bundled with the
-reference (JAICOV/example/example.htm: S0, IO values, IO standard deviations and correlations, object
-coordinates) through the fixture tests/golden/example_scene.npz.
+Parity pins:
+* tests/test_oracle_golden.py checks this oracle against the AICON report bundled with the reference
+  (JAICOV/example/example.htm: S0, IO values, IO standard deviations and correlations, object coordinates) through the
+  fixture tests/golden/example_scene.npz;
+* tests/test_reference_formulas.py checks it against the REFERENCE'S OWN CODE, executed: the Java method bodies are
+  transliterated mechanically and run on stub objects (tests/golden/make_*_fixture.py).  Jacobian rows, bookkeeping,
+  datum rows, normal equations, preconditioner, Levenberg-Marquardt control and centroid are identical bit for bit;
+  complete adjustments (estimateModel end to end: FULL / NONE / SIMULATION, Levenberg-Marquardt, iteration limit, scale
+  bar, observed groups) agree in state, number of passes, every damping value, parameters (1e-13), Omega, sigma0^2 and
+  Qxx (1e-11 correlation-scaled).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
 Levenberg-Marquardt damping (:801-822, :390-426) is restated as well (dampingValue defaults to 0, :96).
@@ -204,7 +211,9 @@ class Oracle:
     """One adjustment, reference semantics. ``invert``: 'FULL', 'NONE', 'REDUCED' or 'PRE_ELIMINATION'
     (BundleAdjustment.MatrixInversion, BundleAdjustment.java:65-70)."""
 
-    def __init__(self, scene, invert='FULL', max_iter=MAX_ITER, use_centroid=True, apply_aposteriori=True, damping=0.0):
+    def __init__(self, scene, invert='FULL', max_iter=MAX_ITER, use_centroid=True, apply_aposteriori=True, damping=0.0,
+                 simulation=False):
+        self.simulation = bool(simulation)         # EstimationType.SIMULATION, BundleAdjustment.java:830-831, :429-430, :1092
         self.bk = Bookkeeping(scene)
         self.fp = FlatProblem(scene, self.bk)
         self.invert = invert
@@ -408,6 +417,8 @@ class Oracle:
             N[dg] = N[dg] + self.adapted_damping * N[dg]
         V = np.empty(n)
         L.orc_preconditioner(n, N.ctypes.data, V.ctypes.data, EPS)
+        if getattr(self, 'simulation', False):                      # :830-831: n.zero()
+            nv[:] = 0.0
         return N, nv, V
 
     def get_omega(self, dx):
@@ -523,7 +534,7 @@ class Oracle:
                 dx[:] = 0.0
                 return
         if update_complete:
-            self.omega = self.get_omega(dx)                        # :429-430
+            self.omega = 0.0 if getattr(self, 'simulation', False) else self.get_omega(dx)      # :429-430
         self.max_abs_dx = self.update_unknowns(dx)                 # :432
         self.last_valid_max_abs_dx = self.max_abs_dx
 
@@ -600,7 +611,7 @@ class Oracle:
     def variance_factor_aposteriori(self):
         """getVarianceFactorAposteriori, BundleAdjustment.java:1090-1093."""
         dof = self.bk.dof
-        if dof > 0 and self.omega > 0 and self.apply_aposteriori:
+        if dof > 0 and self.omega > 0 and not getattr(self, 'simulation', False) and self.apply_aposteriori:
             return abs(self.omega / float(dof))
         return self.sigma2apriori
 

@@ -1,0 +1,225 @@
+"""Generates tests/golden/reference_estimates.npz: complete adjustments -- every pass of BundleAdjustment.estimateModel()
+(BundleAdjustment.java:203-387) with createNormalEquation, the solve, updateModel incl. the Levenberg-Marquardt control,
+getOmega (:472-491), the convergence logic, the final pass with the inversion, the centroid shift back, and
+getVarianceFactorAposteriori (:1090-1093) -- produced by EXECUTING the reference's own method bodies on small networks.
+
+Run in the build container only (reads /root/reference):
+    python tests/golden/make_estimate_fixture.py
+
+The method bodies are transliterated mechanically (make_jacobian_fixture.transliterate) and exec'ed on stub objects, as
+in the other make_*_fixture.py scripts, with two local adaptations that are plain renamings: the loop counter `runs` of
+estimateModel becomes a field (its post-decrement sits inside an `else if` condition), and the reduced-inversion
+branches are never entered (invert modes FULL and NONE only).  Third-party code the reference calls is stood in for by
+the same algorithms: LAPACK dspsv / dsptri out of scipy's OpenBLAS (oracle/lapack_packed.py) for MathExtension.solve, and
+reference-BLAS loop orders for the three MTJ calls of getOmega (DenseMatrix.multAdd = dgemv, UpperSymmPackMatrix.mult =
+dspmv, UpperSymmBandMatrix.mult with kd = 0, DenseVector.dot = ddot).  Numbers only are stored.
+"""
+import math
+import os
+import re
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import make_bookkeeping_fixture as tb  # noqa: E402
+import make_jacobian_fixture as tj  # noqa: E402
+import make_lm_fixture as tl  # noqa: E402
+import make_normal_equation_fixture as tn  # noqa: E402
+from oracle.lapack_packed import MatrixNotSPDException, MatrixSingularException, solve_symm_packed  # noqa: E402
+
+OUT = os.path.join(HERE, 'reference_estimates.npz')
+# EstimationStateType ids (adjustment/EstimationStateType.java:25-41: every progress state has id 0) ...
+STATE_IDS = {'ERROR_FREE_ESTIMATION': 1, 'BUSY': 0, 'ITERATE': 0, 'CONVERGENCE': 0, 'LEVENBERG_MARQUARDT_STEP': 0,
+             'ESTIAMTE_STOCHASTIC_PARAMETERS': 0, 'INVERT_NORMAL_EQUATION_MATRIX': 0, 'INTERRUPT': -1, 'SINGULAR_MATRIX': -2,
+             'NO_CONVERGENCE': -4, 'EXPORT_ADJUSTMENT_RESULTS_FAILED': -6, 'OUT_OF_MEMORY': -7}
+# ... and the codes the fixture (and include/jaicov_b200.h: JAICOV_STATE_*) uses to tell the events apart
+STATES = {'BUSY': 100, 'ITERATE': 101, 'CONVERGENCE': 102, 'INVERT_NORMAL_EQUATION_MATRIX': 103, 'ESTIAMTE_STOCHASTIC_PARAMETERS': 104,
+          'LEVENBERG_MARQUARDT_STEP': 105, 'ERROR_FREE_ESTIMATION': 1, 'INTERRUPT': -1, 'SINGULAR_MATRIX': -2, 'NO_CONVERGENCE': -4,
+          'OUT_OF_MEMORY': -7, 'EXPORT_ADJUSTMENT_RESULTS_FAILED': -6}
+
+
+class State:
+    def __init__(self, name, ident): self._name, self._id = name, ident
+    def name(self): return self._name
+    def getId(self): return self._id
+
+
+class EST:
+    pass
+
+
+for _n, _i in STATE_IDS.items():
+    setattr(EST, _n, State(_n, _i))
+
+
+# ---- MTJ calls of getOmega, reference-BLAS loop orders ----------------------------------------------------------------------------------
+def multAdd(self, alpha, x, y):          # DenseMatrix.multAdd -> dgemv('N'): y += alpha A x, column by column, zero x[j] skipped
+    for j in np.nonzero(np.any(self.v != 0.0, axis=0))[0]:
+        if x.v[j] != 0.0:
+            temp = alpha * x.v[j]
+            for i in range(self.v.shape[0]):
+                y.v[i] += temp * self.v[i, j]
+    return y
+
+
+def band_mult(self, x, y):               # UpperSymmBandMatrix(kd = 0).mult -> dsbmv: y = 0 + 1 * diag * x
+    for j in range(self.d.size):
+        y.v[j] = 0.0
+    for j in range(self.d.size):
+        temp1 = 1.0 * x.v[j]
+        y.v[j] = y.v[j] + temp1 * self.d[j]
+    return y
+
+
+def pack_mult(self, x, y):               # UpperSymmPackMatrix.mult -> dspmv('U'): packed upper, column by column
+    n = self.n
+    for j in range(n):
+        y.v[j] = 0.0
+    kk = 0
+    for j in range(n):
+        temp1 = 1.0 * x.v[j]
+        temp2 = 0.0
+        k = kk
+        for i in range(j):
+            y.v[i] = y.v[i] + temp1 * self.ap[k]
+            temp2 = temp2 + self.ap[k] * x.v[i]
+            k += 1
+        y.v[j] = y.v[j] + temp1 * self.ap[kk + j] + 1.0 * temp2
+        kk += j + 1
+    return y
+
+
+def dot(self, other):                    # DenseVector.dot -> ddot, unit strides (clean-up loop, then steps of five, all left to right)
+    t = 0.0
+    for i in range(self.v.size):
+        t = t + self.v[i] * other.v[i]
+    return t
+
+
+tn.DenseMatrix.multAdd = multAdd
+tn.UpperSymmBandMatrix.mult = band_mult
+tn.UpperSymmPackMatrix.mult = pack_mult
+tn.DenseVector.dot = dot
+tn.DenseVector.scale = lambda self, a: (self.v.__imul__(a), self)[1]
+tn.GaussMarkovEquations.getJacobian = lambda self: self.A
+tn.GaussMarkovEquations.getWeights = lambda self: self.P
+tn.GaussMarkovEquations.getgetMisclosure = lambda self: self.w
+tn.NormalEquationSystem.getMatrix = lambda self: self.N
+tn.NormalEquationSystem.getVector = lambda self: self.n
+tn.NormalEquationSystem.getPreconditioner = lambda self: self.V
+
+
+class MathExtension(tn.MathExtension):
+    @staticmethod
+    def solve(N, n, *args):              # MathExtension.solve(UpperSymmPackMatrix, ...), MathExtension.java:338-366 + overload
+        num_rows, invert = (N.n, args[0]) if len(args) == 1 else args
+        solve_symm_packed(N.ap, n.v, int(num_rows), bool(invert))
+
+
+class NES(tn.NormalEquationSystem):
+    pass
+
+
+def build():
+    g = tj.build_functions()
+    tb.build_methods()
+    tn.build(g)
+    g.update(MathExtension=MathExtension, EstimationStateType=EST, MatrixSingularException=MatrixSingularException,
+             MatrixNotSPDException=MatrixNotSPDException, SQRT_EPS=tl.SQRT_EPS)
+
+    def apply_overloads(*args):          # NormalEquationSystem.applyPrecondition(neq) | (V, M, m), NES:73-80
+        if len(args) == 1:
+            return g['applyPrecondition'](args[0].V, args[0].N, args[0].n)
+        return g['applyPrecondition'](*args)
+    NES.applyPrecondition = staticmethod(apply_overloads)
+    g['NormalEquationSystem'] = NES
+    fix = lambda src: src.replace('Double.MAX_VALUE', '1.7976931348623157e308')
+    A = tb.Adjustment
+    exec(fix(tj.transliterate(tl.ternaries(tj.method_body(tb.BA, 'private void updateModel(')), 'def updateModel(self, dx, updateCompleteModel):')), g)
+    exec(tj.transliterate(tj.method_body(tb.BA, 'private double updateUnknownParameters('), 'def updateUnknownParameters(self, dx):'), g)
+    exec(tj.transliterate(tj.method_body(tb.BA, 'private double getOmega('), 'def getOmega(self, dx):'), g)
+    exec(tj.transliterate(tj.method_body(tb.BA, 'public int getDegreeOfFreedom('), 'def getDegreeOfFreedom(self):'), g)
+    exec(tj.transliterate(tl.ternaries(['double result = ' + l.strip()[len('return '):] if l.strip().startswith('return degreeOfFreedom') else l
+                                        for l in tj.method_body(tb.BA, 'public double getVarianceFactorAposteriori(')] + ['return result;']),
+                          'def getVarianceFactorAposteriori(self):'), g)
+    body = tj.method_body(tb.BA, 'public EstimationStateType estimateModel(')
+    # the loop counter becomes a field: `runs-- <= 1` sits inside an else-if condition
+    body = [re.sub(r'\bint runs\b', 'this.runs', l) for l in body]
+    body = [l.replace('runs-- <= 1', 'this.postDecrementRuns() <= 1') for l in body]
+    body = [re.sub(r'(?<![\w\.])runs\b', 'this.runs', l) for l in body]
+    exec(tj.transliterate(tl.ternaries(body), 'def estimateModel(self):'), g)
+    for name in ('updateModel', 'updateUnknownParameters', 'getOmega', 'getDegreeOfFreedom', 'getVarianceFactorAposteriori', 'estimateModel'):
+        setattr(A, name, g[name])
+
+    def post_decrement(self):
+        self.runs -= 1
+        return self.runs + 1
+    A.postDecrementRuns = post_decrement
+    A.exportAdjustmentResults = lambda self: None
+    A.reduceNormalEquationSystem = lambda self, neq: (_ for _ in ()).throw(RuntimeError('reduced modes are not part of this fixture'))
+    return g
+
+
+class Change:
+    def __init__(self): self.events = []
+    def firePropertyChange(self, name, old, new): self.events.append((name, float(old), float(new)))
+
+
+def run(scene, invert='FULL', damping=0.0, estimation='L2NORM', centroid=True, max_iter=5000):
+    adj, P, images = tn.graph_unprepared(scene)
+    adj.change = Change()
+    adj.dampingValue, adj.maximalNumberOfIterations, adj.estimationType = float(damping), int(max_iter), estimation
+    adj.useCentroidedCoordinates, adj.invertNormalEquationMatrix = bool(centroid), invert
+    adj.interrupt, adj.calculateStochasticParameters, adj.applyAposterioriVarianceOfUnitWeight = False, False, True
+    adj.omega, adj.Qxx, adj.iterationStep = 0.0, None, 0
+    state = adj.estimateModel()
+    cams = adj.cameras
+    return dict(status=np.array([state.getId()]),
+                passes=np.array([sum(1 for e in adj.change.events if e[0] == 'ITERATE')]),
+                events=np.array([STATES[e[0]] for e in adj.change.events]),
+                lm=np.array([[e[1], e[2]] for e in adj.change.events if e[0] == 'LEVENBERG_MARQUARDT_STEP']).reshape(-1, 2),
+                xyz=np.array([[q.getValue() for q in pt.p] for pt in P]),
+                io=np.array([[q.getValue() for q in c.io] for c in cams]),
+                coef=np.array([q.getValue() for c in cams for q in c.coefs]),
+                eo=np.array([[q.getValue() for q in im.eo] for im in images]),
+                omega=np.array([adj.omega]), max_abs_dx=np.array([adj.maxAbsDx]),
+                sigma2=np.array([adj.getVarianceFactorAposteriori()]), dof=np.array([adj.getDegreeOfFreedom()]),
+                qxx=adj.Qxx.ap.copy() if (adj.Qxx is not None and invert == 'FULL') else np.zeros(0))
+
+
+def cases():
+    from tests.scenes import random_scene, synthetic_scene
+    small = lambda: synthetic_scene(2, images=5, targets=30)[0]
+    yield 'config2_full', small(), {}
+    yield 'config2_none', small(), dict(invert='NONE')
+    yield 'config2_simulation', small(), dict(estimation='SIMULATION')
+    yield 'config2_lm_1', small(), dict(damping=1.0)
+    yield 'config2_lm_100', small(), dict(damping=100.0)
+    yield 'config2_max_iter_3', small(), dict(max_iter=3)
+    yield 'config4_small', synthetic_scene(4, images=6, targets=40)[0], {}
+    yield 'config3_dispersion', synthetic_scene(3, images=5, targets=25)[0], {}
+    yield 'observed_eo_io', tb.observed_eo_io_scene(), {}
+    yield 'random2_scale_bar_no_centroid', random_scene(2), dict(centroid=False)
+    yield 'random2_scale_bar_centroid_refused', random_scene(2), dict(centroid=True)
+
+
+def main():
+    build()
+    out = {}
+    for name, scene, kw in cases():
+        try:
+            r = run(scene, **kw)
+        except ValueError:                # UnsupportedOperationException of centroidCoordinates (BA:151) propagates out of estimateModel
+            r = dict(status=np.array([-999]))
+        for k, v in r.items():
+            out['%s__%s' % (name, k)] = v
+        print(name, {k: (v.tolist() if v.size <= 2 else v.shape) for k, v in r.items() if k in ('status', 'passes', 'omega', 'sigma2', 'lm')})
+    np.savez_compressed(OUT, **out)
+    print('wrote', OUT)
+
+
+if __name__ == '__main__':
+    main()

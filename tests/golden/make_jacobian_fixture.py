@@ -43,13 +43,19 @@ def expr(e):
     e = re.sub(r'\bnew\s+ArrayList<[^>]*>\(', 'JList(', e)
     e = re.sub(r'\bnew\s+', '', e)
     e = re.sub(r'\bnull\b', 'None', e)
+    e = re.sub(r'\bBoolean\.TRUE\b', 'True', e)
+    e = re.sub(r'\bBoolean\.FALSE\b', 'False', e)
+    e = re.sub(r'\bDouble\.isInfinite\(', 'math.isinf(', e)
+    e = re.sub(r'\bDouble\.isNaN\(', 'math.isnan(', e)
+    e = re.sub(r'\bMatrixInversion\.(\w+)', r"'\1'", e)
+    e = re.sub(r'\bEstimationType\.(\w+)', r"'\1'", e)
     e = re.sub(r'\btrue\b', 'True', e)
     e = re.sub(r'\bfalse\b', 'False', e)
     e = re.sub(r'\bCollections\.sort\((\w+)\)', r'\1.sort()', e)
     e = re.sub(r'\bDefectType\.(\w+)', r"'\1'", e)
     e = re.sub(r"\((\w+)\s*\?\s*('\w+')\s*:\s*('\w+')\)", r'(\2 if \1 else \3)', e)                # f(cond ? 'A' : 'B')
     e = re.sub(r'\((?:ImageCoordinate|ScaleBar|ObjectCoordinate|UpperSPDPackMatrix)\)', '', e)
-    e = e.replace('(double)', 'float').replace('floatcount', 'float(count)')
+    e = re.sub(r'\(double\)\s*(\w+)', r'float(\1)', e)
     e = e.replace('!', ' not ').replace(' not =', '!=')
     return e
 
@@ -71,8 +77,26 @@ def clean(lines):
         if re.match(r'^(else\s+)?if\s*\(', line) and line.count('(') != line.count(')'):
             buf = line
             continue
+        m = re.match(r'^\}\s*while\s*\((.*)\);$', line)                   # do { ... } while (cond);
+        if m:
+            out += ['__dowhile__(%s);' % m.group(1), '}']
+            continue
+        m = re.match(r'^while\s*\((.*)\);$', line)                          # the same with the `while` on its own line
+        if m and out and out[-1] == '}':
+            out[-1:] = ['__dowhile__(%s);' % m.group(1), '}']
+            continue
+        m = re.match(r'^\}\s*(catch\s*\(.*\)\s*\{|finally\s*\{)$', line)     # } catch (...) {
+        if m:
+            out += ['}', m.group(1)]
+            continue
         out.append(line)
     return out
+
+
+JAVA_EXCEPTIONS = {'MatrixSingularException': 'MatrixSingularException', 'MatrixNotSPDException': 'MatrixNotSPDException',
+                   'IllegalArgumentException': 'ValueError', 'ArrayIndexOutOfBoundsException': 'IndexError', 'Exception': 'Exception',
+                   'OutOfMemoryError': 'MemoryError', 'NullPointerException': 'AttributeError', 'IOException': 'OSError',
+                   'UnsupportedOperationException': 'ValueError'}
 
 
 def deswitch(lines):
@@ -171,6 +195,28 @@ def transliterate(lines, header):
             emit('else:')
             ind += 1
             continue
+        if line == 'do {':
+            emit('while True:')
+            ind += 1
+            continue
+        if line == 'try {':
+            emit('try:')
+            ind += 1
+            continue
+        if line == 'finally {':
+            emit('finally:')
+            ind += 1
+            continue
+        m = re.match(r'^catch\s*\(([\w\s\|]+?)\s+(\w+)\)\s*\{$', line)
+        if m:
+            names = [JAVA_EXCEPTIONS[x.strip()] for x in m.group(1).split('|')]
+            emit('except (%s,) as %s:' % (', '.join(names), m.group(2)))
+            ind += 1
+            continue
+        m = re.match(r'^__dowhile__\((.*)\);$', line)
+        if m:
+            emit('if not (%s): break' % expr(m.group(1)))
+            continue
         m = re.match(r'^for\s*\(.*\s(\w+)\s*:\s*([\w\.]+)\)\s*\{$', line)
         if m:
             emit('for %s in %s:' % (m.group(1), expr(m.group(2))))
@@ -204,7 +250,7 @@ def transliterate(lines, header):
         if line.startswith('throw new '):
             emit('raise ValueError()')
             continue
-        m = re.match(r'^(?:double|int)\s+(\w+\s*=\s*[^,]+(?:,\s*\w+\s*=\s*[^,]+)+)$', line)       # double a = 0, b = 0, c = 0
+        m = re.match(r'^(?:double|int|boolean)\s+(\w+\s*=\s*[^,]+(?:,\s*\w+\s*=\s*[^,]+)+)$', line)   # double a = 0, b = 0, c = 0
         if m:
             for part in m.group(1).split(','):
                 emit(expr(part.strip()))

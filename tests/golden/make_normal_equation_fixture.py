@@ -277,7 +277,12 @@ def build(g):
     tb.Adjustment.getClass = lambda self: 'BundleAdjustment'
 
 
-def graph(scene):
+def graph_unprepared(scene):
+    """The object graph as a user of the reference would have built it (estimateModel calls prepareUnknownParameters itself)."""
+    return graph(scene, prepare=False)
+
+
+def graph(scene, prepare=True):
     pts = scene['points']
     P = [Point(pts['xyz'][k], pts['fixed'][k], pts['datum'][k]) for k in range(len(pts['xyz']))]
     adj = tb.Adjustment()
@@ -305,7 +310,8 @@ def graph(scene):
         obs = [tb.ObsParam(target(*ref), v, val) for ref, v, val in zip(grp['refs'], tb.variances_of(grp), grp['obs'])]
         adj.observedParameterGroups.append(Group(obs, grp.get('dispersion')))
     adj.centroid = Centroid()
-    adj.prepareUnknownParameters()
+    if prepare:
+        adj.prepareUnknownParameters()
     return adj, P, images
 
 

@@ -249,3 +249,61 @@ def test_lm_step_control_matches_executed_reference():
         np.testing.assert_array_equal(got, out)
         branches.add((lam > 0, bool(o.lm_steps and not o.lm_steps[0][2]), o.adapted_damping == 1.0 / np.sqrt(2.0 ** -53)))
     assert len(branches) >= 4          # plain Gauss-Newton, accepted step, rejected step, clamped damping value
+
+
+# ---- complete adjustments -----------------------------------------------------------------------------------------------------------------
+E = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_estimates.npz'))
+
+
+def _estimate_case(name):
+    from tests.scenes import random_scene, synthetic_scene
+    small = lambda: synthetic_scene(2, images=5, targets=30)[0]
+    table = {'config2_full': (small, {}), 'config2_none': (small, dict(invert='NONE')),
+             'config2_simulation': (small, dict(simulation=True)), 'config2_lm_1': (small, dict(damping=1.0)),
+             'config2_lm_100': (small, dict(damping=100.0)), 'config2_max_iter_3': (small, dict(max_iter=3)),
+             'config4_small': (lambda: synthetic_scene(4, images=6, targets=40)[0], {}),
+             'config3_dispersion': (lambda: synthetic_scene(3, images=5, targets=25)[0], {}),
+             'observed_eo_io': (lambda: _bk_scene('observed_eo_io'), {}),
+             'random2_scale_bar_no_centroid': (lambda: random_scene(2), dict(use_centroid=False)),
+             'random2_scale_bar_centroid_refused': (lambda: random_scene(2), dict(use_centroid=True))}
+    make, kw = table[name]
+    return make(), kw
+
+
+@pytest.mark.parametrize('name', sorted({k.split('__')[0] for k in E.files}))
+def test_complete_adjustment_matches_executed_reference(name):
+    """Oracle.estimate() against the reference's estimateModel() executed end to end (tests/golden/make_estimate_fixture.py):
+    final state, number of passes, the sequence of Levenberg-Marquardt steps, every adjusted parameter, Omega, sigma0^2
+    a posteriori and the packed cofactor matrix.  Both sides call the same LAPACK for the solve, so the comparison is tight:
+    identical integers, 1e-13 relative on parameters, 1e-11 on the correlation-scaled Qxx."""
+    from oracle.oracle import Oracle
+    scene, kw = _estimate_case(name)
+    g = lambda k: E['%s__%s' % (name, k)]
+    o = Oracle(scene, **kw)
+    if int(g('status')[0]) == -999:
+        with pytest.raises(RuntimeError):
+            o.estimate()
+        return
+    status = o.estimate()
+    assert status == int(g('status')[0])
+    assert len(o.history) == int(g('passes')[0])
+    lm = g('lm')
+    assert len(o.lm_steps) == lm.shape[0]
+    for (last, new, _acc), ref in zip(o.lm_steps, lm):
+        assert last == ref[0] and new == ref[1]
+    fp = o.fp
+    for got, ref in ((fp.xyz.reshape(-1, 3), g('xyz')), (fp.io_val.reshape(-1, 3), g('io')), (fp.coef_val, g('coef')), (fp.eo_val.reshape(-1, 6), g('eo'))):
+        np.testing.assert_allclose(got, ref, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(o.omega, g('omega')[0], rtol=1e-12)
+    np.testing.assert_allclose(o.variance_factor_aposteriori(), g('sigma2')[0], rtol=1e-12)
+    assert o.bk.dof == int(g('dof')[0])
+    if g('qxx').size:
+        Q, Qr = o.Qxx, g('qxx')
+        n = o.fp.n
+        idx = np.arange(n)
+        sd = np.sqrt(np.abs(Qr[idx + idx * (idx + 1) // 2]))
+        sd[:o.fp.d] = 1.0
+        iu = np.triu_indices(n)
+        scale = sd[iu[0]] * sd[iu[1]]
+        k = iu[0] + iu[1] * (iu[1] + 1) // 2
+        assert (np.abs(Q[k] - Qr[k]) / scale).max() < 1e-11
