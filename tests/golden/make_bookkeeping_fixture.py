@@ -55,6 +55,7 @@ class OrderedSet:
     def add(self, x): self.d.setdefault(id(x), x)
     def contains(self, x): return id(x) in self.d
     def isEmpty(self): return not self.d
+    def size(self): return len(self.d)
     def __iter__(self): return iter(list(self.d.values()))
     def __len__(self): return len(self.d)
 

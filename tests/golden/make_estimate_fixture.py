@@ -8,8 +8,8 @@ Run in the build container only (reads /root/reference):
 
 The method bodies are transliterated mechanically (make_jacobian_fixture.transliterate) and exec'ed on stub objects, as
 in the other make_*_fixture.py scripts, with two local adaptations that are plain renamings: the loop counter `runs` of
-estimateModel becomes a field (its post-decrement sits inside an `else if` condition), and the reduced-inversion
-branches are never entered (invert modes FULL and NONE only).  Third-party code the reference calls is stood in for by
+estimateModel becomes a field (its post-decrement sits inside an `else if` condition), and the three overloads each of
+reduceNormalEquationSystem / extractReducedParameters (:1197-1453) get distinct names behind a dispatcher.  Third-party code the reference calls is stood in for by
 the same algorithms: LAPACK dspsv / dsptri out of scipy's OpenBLAS (oracle/lapack_packed.py) for MathExtension.solve, and
 reference-BLAS loop orders for the three MTJ calls of getOmega (DenseMatrix.multAdd = dgemv, UpperSymmPackMatrix.mult =
 dspmv, UpperSymmBandMatrix.mult with kd = 0, DenseVector.dot = ddot).  Numbers only are stored.
@@ -127,6 +127,10 @@ def build():
     g = tj.build_functions()
     tb.build_methods()
     tn.build(g)
+    def print_stack_trace(e):            # Throwable.printStackTrace(): a harness bug must not pass for a reference state
+        if isinstance(e, (AttributeError, NameError, TypeError, KeyError)):
+            raise e
+    g['printStackTrace'] = print_stack_trace
     g.update(MathExtension=MathExtension, EstimationStateType=EST, MatrixSingularException=MatrixSingularException,
              MatrixNotSPDException=MatrixNotSPDException, SQRT_EPS=tl.SQRT_EPS)
 
@@ -159,7 +163,20 @@ def build():
         return self.runs + 1
     A.postDecrementRuns = post_decrement
     A.exportAdjustmentResults = lambda self: None
-    A.reduceNormalEquationSystem = lambda self, neq: (_ for _ in ()).throw(RuntimeError('reduced modes are not part of this fixture'))
+    # MatrixInversion.REDUCED / PRE_ELIMINATION: three overloads of each method (:1197-1453)
+    for base, sigs in (('reduceNormalEquationSystem', ('private void reduceNormalEquationSystem(NormalEquationSystem neq) ',
+                                                       'private void reduceNormalEquationSystem(NormalEquationSystem neq, Camera camera)',
+                                                       'private void reduceNormalEquationSystem(NormalEquationSystem neq, Image image')),
+                       ('extractReducedParameters', ('private void extractReducedParameters(NormalEquationSystem neq) ',
+                                                     'private void extractReducedParameters(NormalEquationSystem neq, Camera camera)',
+                                                     'public void extractReducedParameters(NormalEquationSystem neq, Image image'))):
+        heads = ('def %s1(self, neq):', 'def %s2(self, neq, camera):', 'def %s3(self, neq, image, unknownInteriorOrientationAndDistortionParameters):')
+        for k, (sig, head) in enumerate(zip(sigs, heads)):
+            exec(tj.transliterate(tj.method_body(tb.BA, sig), head % base), g)
+
+        def dispatch(self, *args, base=base):
+            return g['%s%d' % (base, len(args))](self, *args)
+        setattr(A, base, dispatch)
     return g
 
 
@@ -187,7 +204,9 @@ def run(scene, invert='FULL', damping=0.0, estimation='L2NORM', centroid=True, m
                 eo=np.array([[q.getValue() for q in im.eo] for im in images]),
                 omega=np.array([adj.omega]), max_abs_dx=np.array([adj.maxAbsDx]),
                 sigma2=np.array([adj.getVarianceFactorAposteriori()]), dof=np.array([adj.getDegreeOfFreedom()]),
-                qxx=adj.Qxx.ap.copy() if (adj.Qxx is not None and invert == 'FULL') else np.zeros(0))
+                qxx=adj.Qxx.ap.copy() if (adj.Qxx is not None and invert != 'NONE') else np.zeros(0),
+                num_rows_reduced=np.array([adj.numberOfInteriorOrientations + adj.numberOfDistortionParameters + len(adj.objectCoordinates) * 3
+                                           + adj.rankDefect.getDefect()]))
 
 
 def cases():
@@ -202,6 +221,11 @@ def cases():
     yield 'config4_small', synthetic_scene(4, images=6, targets=40)[0], {}
     yield 'config3_dispersion', synthetic_scene(3, images=5, targets=25)[0], {}
     yield 'observed_eo_io', tb.observed_eo_io_scene(), {}
+    yield 'config2_reduced', small(), dict(invert='REDUCED')
+    yield 'config2_pre_elimination', small(), dict(invert='PRE_ELIMINATION')
+    sc = synthetic_scene(4, images=6, targets=40, n_cameras=2)[0]
+    sc['cameras'][0]['images'][1]['eo_fixed'][4] = True            # an image with five exterior-orientation unknowns
+    yield 'config4_two_cameras_reduced', sc, dict(invert='REDUCED')
     yield 'random2_scale_bar_no_centroid', random_scene(2), dict(centroid=False)
     yield 'random2_scale_bar_centroid_refused', random_scene(2), dict(centroid=True)
 

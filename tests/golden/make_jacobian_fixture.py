@@ -40,8 +40,9 @@ def expr(e):
     e = re.sub(r'\bthis\.', 'self.', e)
     e = re.sub(r'\bnew\s+LinkedHashSet<[^>]*>\(\)', 'OrderedSet()', e)
     e = re.sub(r'\bnew\s+HashSet<[^>]*>\(\)', 'JSet()', e)
-    e = re.sub(r'\bnew\s+ArrayList<[^>]*>\(', 'JList(', e)
+    e = re.sub(r'\bnew\s+ArrayList<(?:[^<>]|<[^<>]*>)*>\(', 'JList(', e)
     e = re.sub(r'\bnew\s+', '', e)
+    e = re.sub(r'\b(\w+)\.printStackTrace\(\)', r'printStackTrace(\1)', e)
     e = re.sub(r'\bnull\b', 'None', e)
     e = re.sub(r'\bBoolean\.TRUE\b', 'True', e)
     e = re.sub(r'\bBoolean\.FALSE\b', 'False', e)
@@ -222,7 +223,7 @@ def transliterate(lines, header):
             emit('for %s in %s:' % (m.group(1), expr(m.group(2))))
             ind += 1
             continue
-        m = re.match(r'^for\s*\(int\s+(\w+)\s*=\s*(\w+);\s*\1\s*<\s*([\w\.\(\)]+);\s*\1\+\+\)\s*\{$', line)
+        m = re.match(r'^for\s*\(int\s+(\w+)\s*=\s*([\w\s\+\-]+?);\s*\1\s*<\s*([\w\.\(\)]+);\s*\1\+\+\)\s*\{$', line)
         if m:
             emit('for %s in range(%s, %s):' % (m.group(1), m.group(2), expr(m.group(3))))
             ind += 1

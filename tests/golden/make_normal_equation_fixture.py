@@ -33,7 +33,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import make_bookkeeping_fixture as tb  # noqa: E402
 import make_jacobian_fixture as tj  # noqa: E402
 import make_lm_fixture as tl  # noqa: E402
-from oracle.lapack_packed import inv_spd_packed  # noqa: E402
+from oracle.lapack_packed import inv_spd_packed, inv_symm_packed  # noqa: E402
 
 PDF = os.path.join(tj.REF, 'derivation', 'PartialDerivativeFactory.java')
 OUT = os.path.join(HERE, 'reference_normal_equations.npz')
@@ -46,7 +46,12 @@ class DenseVector:
     def size(self): return self.v.size
     def get(self, i): return self.v[i]
     def set(self, i, x): self.v[i] = x
-    def add(self, i, x): self.v[i] += x
+    def add(self, *args):
+        if len(args) == 2 and not isinstance(args[1], DenseVector):
+            self.v[args[0]] += args[1]                      # add(index, value)
+        else:
+            self.v += args[0] * args[1].v                   # add(alpha, vector): daxpy
+
     def zero(self): self.v[:] = 0.0
 
 
@@ -71,14 +76,22 @@ class UpperSymmBandMatrix:
 
 
 class UpperSymmPackMatrix:
-    """no.uib.cipr.matrix.UpperSymmPackMatrix: symmetric, stored column-major packed upper."""
+    """no.uib.cipr.matrix.UpperSymmPackMatrix (MTJ 1.0.4): symmetric, stored column-major packed upper.  get() is symmetric;
+    set() and add() act on the stored triangle only -- a write below the diagonal is ignored.  The reference relies on that:
+    reduceNormalEquationSystem (BundleAdjustment.java:1325-1340) loops over all (row, column) pairs and each element is
+    updated once, through its upper-triangle address."""
     def __init__(self, n): self.n, self.ap = n, np.zeros(n * (n + 1) // 2)
     def numRows(self): return self.n
     def numColumns(self): return self.n
-    def _k(self, r, c): return (r + c * (c + 1) // 2) if r <= c else (c + r * (r + 1) // 2)
-    def get(self, r, c): return self.ap[self._k(r, c)]
-    def set(self, r, c, x): self.ap[self._k(r, c)] = x
-    def add(self, r, c, x): self.ap[self._k(r, c)] += x
+    def get(self, r, c): return self.ap[(r + c * (c + 1) // 2) if r <= c else (c + r * (r + 1) // 2)]
+
+    def set(self, r, c, x):
+        if r <= c:
+            self.ap[r + c * (c + 1) // 2] = x
+
+    def add(self, r, c, x):
+        if r <= c:
+            self.ap[r + c * (c + 1) // 2] += x
 
 
 class UpperSPDPackMatrix(UpperSymmPackMatrix):
@@ -90,7 +103,10 @@ class UpperSPDPackMatrix(UpperSymmPackMatrix):
 class MathExtension:
     @staticmethod
     def inv(M):
-        inv_spd_packed(M.ap, M.n)
+        if isinstance(M, UpperSPDPackMatrix):
+            inv_spd_packed(M.ap, M.n)           # MathExtension.inv(UpperSPDPackMatrix): dpptrf + dpptri, MathExtension.java:304-324
+        else:
+            inv_symm_packed(M.ap, M.n)          # MathExtension.inv(UpperSymmPackMatrix): dsptrf + dsptri, :403-426
         return M
 
 
@@ -121,9 +137,13 @@ class JSet(set):
 
 
 class JList(list):
+    def __init__(self, arg=()):
+        super().__init__(() if isinstance(arg, int) else arg)       # new ArrayList<T>(capacity) | new ArrayList<T>(collection)
+
     def get(self, i): return self[i]
     def size(self): return len(self)
     def add(self, x): self.append(x)
+    def addAll(self, other): self.extend(other)
 
 
 class GaussMarkovEquations:

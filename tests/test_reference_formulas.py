@@ -255,12 +255,21 @@ def test_lm_step_control_matches_executed_reference():
 E = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_estimates.npz'))
 
 
+def _two_camera_reduced_scene():
+    from tests.scenes import synthetic_scene
+    sc = synthetic_scene(4, images=6, targets=40, n_cameras=2)[0]
+    sc['cameras'][0]['images'][1]['eo_fixed'][4] = True
+    return sc
+
+
 def _estimate_case(name):
     from tests.scenes import random_scene, synthetic_scene
     small = lambda: synthetic_scene(2, images=5, targets=30)[0]
     table = {'config2_full': (small, {}), 'config2_none': (small, dict(invert='NONE')),
              'config2_simulation': (small, dict(simulation=True)), 'config2_lm_1': (small, dict(damping=1.0)),
              'config2_lm_100': (small, dict(damping=100.0)), 'config2_max_iter_3': (small, dict(max_iter=3)),
+             'config2_reduced': (small, dict(invert='REDUCED')), 'config2_pre_elimination': (small, dict(invert='PRE_ELIMINATION')),
+             'config4_two_cameras_reduced': (_two_camera_reduced_scene, dict(invert='REDUCED')),
              'config4_small': (lambda: synthetic_scene(4, images=6, targets=40)[0], {}),
              'config3_dispersion': (lambda: synthetic_scene(3, images=5, targets=25)[0], {}),
              'observed_eo_io': (lambda: _bk_scene('observed_eo_io'), {}),
@@ -299,11 +308,19 @@ def test_complete_adjustment_matches_executed_reference(name):
     assert o.bk.dof == int(g('dof')[0])
     if g('qxx').size:
         Q, Qr = o.Qxx, g('qxx')
-        n = o.fp.n
+        # REDUCED / PRE_ELIMINATION: the cofactor matrix is the leading numRows block (BA:262); what lies behind it are the
+        # leftovers of the reduction, which the oracle reproduces as well (compared on the block, where they are defined)
+        n = o.fp.n if kw.get('invert', 'FULL') == 'FULL' else int(g('num_rows_reduced')[0])
+        if kw.get('invert', 'FULL') != 'FULL':
+            assert n == o.num_rows_reduced()
         idx = np.arange(n)
         sd = np.sqrt(np.abs(Qr[idx + idx * (idx + 1) // 2]))
         sd[:o.fp.d] = 1.0
         iu = np.triu_indices(n)
         scale = sd[iu[0]] * sd[iu[1]]
         k = iu[0] + iu[1] * (iu[1] + 1) // 2
-        assert (np.abs(Q[k] - Qr[k]) / scale).max() < 1e-11
+        # FULL: same arithmetic up to the Omega sums -> 1e-11.  Reduced modes: the oracle forms the Schur complement with
+        # vectorised sums (another summation order than the reference's scalar loops); on these systems (condition ~1e8) that
+        # shows at the 1e-9 level, inside the 1e-8 bar the Qxx parity uses everywhere
+        tol = 1e-11 if kw.get('invert', 'FULL') == 'FULL' else 1e-8
+        assert (np.abs(Q[k] - Qr[k]) / scale).max() < tol
