@@ -15,8 +15,9 @@ they are the same functions the reference spells out entry by entry.  Pin: the r
 the DLT; golden vectors were produced by evaluating the reference's own expressions for the six restriction rows and
 misclosures (DPF:100-236) and for the expansion (DLT:208-246) on seeded random inputs
 (tests/golden/make_formula_fixtures.py -> tests/golden/reference_formulas.npz) and this module matches them to 1e-12
-(tests/test_reference_formulas.py); the loop logic (DLT:108-180) is a restatement, checked by the recovery of a synthetic
-pin-hole camera (tests/test_dlt.py).
+(tests/test_reference_formulas.py); the complete adjust() -- loop logic, passes, return value, coefficients and derived
+orientation -- matches DirectLinearTransformation.adjust executed end to end (tests/golden/make_dlt_fixture.py ->
+reference_dlt.npz: six images, five restriction sets), and recovers a synthetic pin-hole camera (tests/test_dlt.py).
 """
 from __future__ import annotations
 

@@ -43,6 +43,7 @@ def expr(e):
     e = re.sub(r'\bnew\s+ArrayList<(?:[^<>]|<[^<>]*>)*>\(', 'JList(', e)
     e = re.sub(r'\bnew\s+', '', e)
     e = re.sub(r'\b(\w+)\.printStackTrace\(\)', r'printStackTrace(\1)', e)
+    e = re.sub(r'\b(\w+)\.length\b(?!\()', r'len(\1)', e)
     e = re.sub(r'\bnull\b', 'None', e)
     e = re.sub(r'\bBoolean\.TRUE\b', 'True', e)
     e = re.sub(r'\bBoolean\.FALSE\b', 'False', e)

@@ -74,7 +74,7 @@ def ternaries(lines):
                     '%s%s = %s;' % (ind, lhs, b), '%s}' % ind, '%s}' % ind]
             continue
         # f(a, b, cond ? p : q);  ->  if (cond) { f(a, b, p); } else { f(a, b, q); }
-        m = re.match(r'^(\s*)([\w\.]+\(.*,\s*)([^,?]+?)\s*\?\s*(.+?)\s*:\s*(.+?)\);\s*$', l)
+        m = re.match(r'^(\s*)([\w\.]+\((?:.*,\s*)?)([^,?]+?)\s*\?\s*(.+?)\s*:\s*(.+?)\);\s*$', l)
         if m:
             ind, head, cond, a, b = m.groups()
             out += ['%sif (true) {' % ind, '%sif (%s) {' % (ind, cond), '%s%s%s);' % (ind, head, a), '%s}' % ind, '%selse {' % ind,

@@ -324,3 +324,30 @@ def test_complete_adjustment_matches_executed_reference(name):
         # shows at the 1e-9 level, inside the 1e-8 bar the Qxx parity uses everywhere
         tol = 1e-11 if kw.get('invert', 'FULL') == 'FULL' else 1e-8
         assert (np.abs(Q[k] - Qr[k]) / scale).max() < tol
+
+
+# ---- direct linear transformation, end to end ------------------------------------------------------------------------------------------
+def test_dlt_adjust_matches_executed_reference():
+    """oracle/dlt.py: adjust() against DirectLinearTransformation.adjust executed (tests/golden/make_dlt_fixture.py): the return
+    value, the 11 back-scaled coefficients and the derived interior / exterior orientation of six images (one with too few
+    points) for five restriction sets."""
+    from oracle import dlt as od
+    D = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_dlt.npz'))
+    ptr, xy, xyz, io = D['pt_ptr'], D['xy'], D['xyz'], D['io']
+    worst = 0.0
+    for s in range(5):
+        restr = [int(r) for r in D['set%d_restrictions' % s]]
+        for k in range(ptr.size - 1):
+            sl = slice(int(ptr[k]), int(ptr[k + 1]))
+            ok, b, d, _ = od.adjust(xy[sl], xyz[sl], tuple(io), restr)
+            assert bool(ok) == bool(D['set%d_ok' % s][k])
+            if not ok:
+                continue
+            ref = D['set%d_values' % s][k]          # DLTCoefficients order: b11..b33, x0, y0, c, X0, Y0, Z0, omega, phi, kappa
+            got = np.concatenate([b, [d['x0'], d['y0'], d['c']], d['X0'], [d['omega'], d['phi'], d['kappa']]])
+            scale = np.maximum(np.abs(ref), 1e-3)
+            worst = max(worst, float((np.abs(got - ref) / scale).max()))
+    print('DLT oracle vs executed reference: worst relative difference', worst)
+    # coefficients agree to 1e-14; the derived principal point (0.02 against c = 28.8) and projection centre carry the
+    # cancellation of their formulas: 2e-11 relative to their own small values
+    assert worst < 1e-10
