@@ -489,3 +489,52 @@ def test_result_writers_export_from_device(built, tmp_path):
     assert C.shape == (450, 450) and np.abs(C - ref).max() < 1e-14 + 1e-8 * np.abs(ref).max()
     info = open(str(tmp_path / 'default.info')).read().splitlines()
     assert len(info) == 450 and info[0].split()[1] == 'X' and int(info[2].split()[-1]) == 2
+
+
+# ---- against the committed vectors of the executed reference ------------------------------------------------------------------------
+def _reference_cases():
+    import os
+    E = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_estimates.npz'))
+    return E, sorted({k.split('__')[0] for k in E.files} - {'random2_scale_bar_centroid_refused', 'config2_simulation', 'config2_max_iter_3'})
+
+
+@pytest.mark.parametrize('name', _reference_cases()[1])
+def test_adjustment_matches_executed_reference_vectors(built, name):
+    """The CUDA path against tests/golden/reference_estimates.npz directly: results the reference's own estimateModel() produced when
+    executed (tests/golden/make_estimate_fixture.py) -- final state, passes, Levenberg-Marquardt damping sequence, parameters
+    (1e-10), sigma0^2 and Omega (1e-8), Qxx (1e-8 correlation-scaled; leading block for the reduced modes)."""
+    from tests.test_reference_formulas import _estimate_case
+    E, _ = _reference_cases()
+    g = lambda k: E['%s__%s' % (name, k)]
+    scene, kw = _estimate_case(name)
+    adj, _pts = build_adjustment(scene)
+    adj.useCentroidedCoordinates(kw.get('use_centroid', True))
+    adj.setInvertNormalEquation(ba.MatrixInversion[kw.get('invert', 'FULL')])
+    adj.setLevenbergMarquardtDampingValue(kw.get('damping', 0.0))
+    lm_events = []
+    adj.addPropertyChangeListener(lambda st, old, new: lm_events.append((old, new)) if st == 105 else None)
+    state = adj.estimateModel()
+    assert state.getId() == int(g('status')[0])
+    assert adj.stats.iterations == int(g('passes')[0])
+    assert len(lm_events) == g('lm').shape[0]
+    for (old, new), ref in zip(lm_events, g('lm')):
+        assert old == ref[0] and new == ref[1]
+    assert abs(adj.stats.omega - g('omega')[0]) <= TOL_S2 * g('omega')[0]
+    assert abs(adj.getVarianceFactorAposteriori() - g('sigma2')[0]) <= TOL_S2 * g('sigma2')[0]
+    Qr = g('qxx')
+    xyz, io, coef, eo = adj._session.values()
+    if Qr.size:
+        n = adj._session.n
+        nq = n if kw.get('invert', 'FULL') == 'FULL' else int(g('num_rows_reduced')[0])
+        Qg = adj.getCofactorMatrix().toDense()[:nq, :nq]
+        iu = np.triu_indices(nq)
+        Qd = np.zeros((nq, nq))
+        Qd[iu] = Qr[iu[0] + iu[1] * (iu[1] + 1) // 2]
+        Qd = Qd + np.triu(Qd, 1).T
+        d = adj.getNumberOfDatumConditions()
+        sd = np.sqrt(np.abs(np.diag(Qd)))
+        sd[:d] = 1.0
+        assert (np.abs(Qg - Qd) / np.outer(sd, sd)).max() <= TOL_Q
+    for got, ref in ((xyz.reshape(-1, 3), g('xyz')), (io.reshape(-1, 3), g('io')), (coef, g('coef')), (eo.reshape(-1, 6), g('eo'))):
+        # 1e-10 relative, with the floor the other parity tests use for values near zero: 1e-10 of the largest value of the group
+        assert (np.abs(got - ref) <= TOL_X * np.maximum(np.abs(ref), np.abs(ref).max() * 1e-3 + 1e-12)).all()
