@@ -157,7 +157,9 @@ def run_reference(args, rank):
         return
     scene, adj, flat = workload(args.config)
     name, n = workload_name(args.config, flat, adj)
-    threads = os.cpu_count() or 1
+    # the reference (F2J LAPACK under MTJ) is single-threaded; its stand-in (OpenBLAS dspsv + dsptri: packed, level-2 bound)
+    # gains ~30 % from 4-8 threads and nothing beyond, and oversubscribing a 200-core host only adds spinning: cap at 16
+    threads = min(os.cpu_count() or 1, 16)
     vals = []
     t_all = time.perf_counter()
     for i in range(args.warmup + args.steps):
