@@ -119,13 +119,16 @@ def fp64_peak_tflops(torch, n=8192, reps=5):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
-def cpu_sample(config, n_full, m_full, threads):
+CPU_SAMPLE = (64, 1500)     # images x targets of the bounded CPU sample: n ~ 4900, ~10-20 s of packed dspsv + dsptri on one core
+
+
+def cpu_sample(config, n_full, m_full, threads, size=CPU_SAMPLE):
     """Bounded CPU sample: ONE final pass of the oracle (reference-equivalent: per-observation stacking into packed N,
     dspsv + dsptri, Omega) on a scaled-down network of the same config, extrapolated to the full workload."""
     from threadpoolctl import threadpool_limits
     from oracle.oracle import Oracle, lib as olib
     from tests.scenes import synthetic_scene
-    scene, _ = synthetic_scene(config, images=40, targets=800)
+    scene, _ = synthetic_scene(config, images=size[0], targets=size[1])
     with threadpool_limits(limits=threads):
         o = Oracle(scene)
         o.history = []
@@ -146,10 +149,10 @@ def cpu_sample(config, n_full, m_full, threads):
     t_asm, t_dense, t_om = t1 - t0, t2 - t1, t3 - t2
     t_full = (t_asm + t_om) * (m_full / m_s) + t_dense * (n_full / n_s) ** 3
     return {'value': 1.0 / t_full, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-            'sample': ('one final pass of the CPU oracle on a scaled-down network of the same config (40 images x 800 targets, '
+            'sample': ('one final pass of the CPU oracle on a scaled-down network of the same config (%d images x %d targets, '
                        'n = %d, %d image points): assembly+Omega %.2f s, packed dspsv+dsptri %.2f s; extrapolated to the full '
                        'workload with assembly ~ image points and factor+inverse ~ n^3 (%.3g s per pass)'
-                       % (n_s, m_s, t_asm + t_om, t_dense, t_full))}
+                       % (size[0], size[1], n_s, m_s, t_asm + t_om, t_dense, t_full))}
 
 
 def run_reference(args, rank):
@@ -159,7 +162,13 @@ def run_reference(args, rank):
     name, n = workload_name(args.config, flat, adj)
     # the reference (F2J LAPACK under MTJ) is single-threaded; its stand-in (OpenBLAS dspsv + dsptri: packed, level-2 bound)
     # gains ~30 % from 4-8 threads and nothing beyond, and oversubscribing a 200-core host only adds spinning: cap at 16
-    threads = min(os.cpu_count() or 1, 16)
+    # -- and on small hosts more threads are SLOWER than one (this container, 8 vCPU: 2.97 s vs 1.78 s), so a short calibration
+    # sample picks whichever of {1, cap} is faster on this box before anything is timed
+    cap = min(os.cpu_count() or 1, 16)
+    threads = 1
+    if cap > 1:
+        cal = {t: cpu_sample(args.config, n, flat['obj_idx'].size, t, size=(40, 800))['value'] for t in (1, cap)}
+        threads = max(cal, key=cal.get)
     vals = []
     t_all = time.perf_counter()
     for i in range(args.warmup + args.steps):
@@ -171,7 +180,7 @@ def run_reference(args, rank):
     v = float(np.mean(vals)) if vals else cb['value']
     cb['value'] = v
     print(json.dumps({'metric': METRIC, 'value': v, 'unit': UNIT, 'impl': 'reference', 'n_gpus': args.gpus, 'steps': args.steps,
-                      'warmup': args.warmup, 'ms_per_step': 1000.0 / v, 'higher_is_better': True, 'scaling': 'weak',
+                      'warmup': args.warmup, 'ms_per_step': 1000.0 / v, 'higher_is_better': True, 'scaling': 'strong',
                       'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                       'config': {'workload': name, 'impl_note': 'CPU oracle = reference-equivalent port (no JVM in this image); bounded sample extrapolated'},
                       'cpu_baseline': cb,
@@ -375,7 +384,7 @@ def main():
                                'MEASURED_PEAKS.json has no FP64 entry',
                 'assembly_gbs': (flat['obj_idx'].size * 44.0) / (stage[0] * 1e-3) / 1e9, 'hbm_peak_gbs': hbm}
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak' if world == 1 else 'strong', 'vs_baseline': None,
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': name, 'solver': 'structured (point-block)' if structured_used else 'dense (blocked Cholesky + full inverse)',
                        'l2': 'inputs larger than L2: the %d x %d FP64 system (%.2f GB) is rewritten every step'
