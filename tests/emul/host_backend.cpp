@@ -13,13 +13,105 @@
 
 using namespace jaicov;
 
+// ---- int8-slice ("Ozaki scheme I") emulation of an FP64 GEMM -----------------------------------------------------------
+// Numerics study for DESIGN.md section 9 (FP64 products on the INT8 tcgen05 tensor cores): every operand row is scaled by a
+// power of two to (-1, 1) and cut into `s` signed digits |q| <= 64 (first digit 6 bits, the others 7 bits); digit products
+// are summed EXACTLY in integers per group g = i + j (what an s8 x s8 -> s32 tensor-core accumulator does), groups with
+// i + j > s + 1 are dropped, and the group sums are combined in FP64.  This is the arithmetic the planned kernel would do,
+// bit for bit; it lives in the test-only host backend and nowhere in the product.
+struct OzakiOperand {
+    int64_t rows = 0, K = 0;
+    int s = 0;
+    std::vector<int8_t> q;      // [s][rows][K]
+    std::vector<int> e;         // [rows]: |x| < 2^e on the row's valid range
+    const int8_t *slice(int j, int64_t r) const { return q.data() + ((size_t)j * rows + r) * K; }
+};
+
+// x(r, k) for k in [klo(r), khi(r)); everything outside the valid range becomes zero digits
+template <class Get, class Lo, class Hi>
+static void ozaki_split(OzakiOperand &o, int64_t rows, int64_t K, int s, Get get, Lo klo, Hi khi) {
+    o.rows = rows; o.K = K; o.s = s;
+    o.q.assign((size_t)s * rows * K, 0);
+    o.e.assign(rows, 0);
+    for (int64_t r = 0; r < rows; r++) {
+        const int64_t k0 = klo(r), k1 = khi(r);
+        double amax = 0.0;
+        for (int64_t k = k0; k < k1; k++) amax = std::max(amax, std::fabs(get(r, k)));
+        if (!(amax > 0.0) || !std::isfinite(amax)) continue;
+        const int e = std::ilogb(amax) + 1;
+        o.e[r] = e;
+        for (int64_t k = k0; k < k1; k++) {
+            double t = std::ldexp(get(r, k), 6 - e);           // |t| < 64
+            for (int j = 0; j < s; j++) {
+                const double qd = std::nearbyint(t);
+                o.q[((size_t)j * rows + r) * K + k] = (int8_t)qd;
+                t = (t - qd) * 128.0;                          // exact: |t - qd| <= 0.5
+            }
+        }
+    }
+}
+
 struct HostBackend {
     int info = 0;
     long gemm_calls = 0, diag_calls = 0;
     double flops = 0;
+    int ozaki = 0;              // > 0: number of int8 digits per operand; every eligible launch goes through gemm_ozaki
+    int ozaki_min_tiles = 1;    // launches with fewer output tiles stay on the FP64 path (as the product would do)
+    long ozaki_calls = 0;
+    long long ozaki_max_abs_sum = 0;   // largest |integer group sum| seen (must stay below 2^31)
+
+    void gemm_ozaki(const GemmDesc &g) {
+        const int T = kTile, s = ozaki;
+        const int64_t Mr = (int64_t)g.mt * T, Nr = (int64_t)g.nt * T, K = g.K;
+        OzakiOperand A, B;
+        ozaki_split(A, Mr, K, s,
+                    [&](int64_t m, int64_t k) { return g.al == 0 ? g.A[m * g.lda + k] : g.A[k * g.lda + m]; },
+                    [&](int64_t m) { return g.kmode == K_MAX_IJ ? (m / T) * T : (int64_t)0; },
+                    [&](int64_t m) { return g.kmode == K_A_LOWER ? std::min<int64_t>(K, (m / T + 1) * T) : K; });
+        ozaki_split(B, Nr, K, s,
+                    [&](int64_t n, int64_t k) { return g.bl == 0 ? g.B[n * g.ldb + k] : g.B[k * g.ldb + n]; },
+                    [&](int64_t n) { return (g.kmode == K_MAX_IJ || g.kmode == K_B_LOWER) ? (n / T) * T : (int64_t)0; },
+                    [&](int64_t) { return K; });
+        std::vector<long long> S(2 * s + 1);
+        for (int it = 0; it < g.mt; it++)
+            for (int jt = 0; jt < g.nt; jt++) {
+                if (g.tri_out && it < jt) continue;
+                int64_t kbeg = 0, kend = K;
+                if (g.kmode == K_B_LOWER) kbeg = (int64_t)jt * T;
+                else if (g.kmode == K_A_LOWER) kend = std::min<int64_t>(K, (int64_t)(it + 1) * T);
+                else if (g.kmode == K_MAX_IJ) kbeg = (int64_t)std::max(it, jt) * T;
+                flops += 2.0 * T * T * (double)(kend - kbeg);
+                for (int i = 0; i < T; i++)
+                    for (int j = 0; j < T; j++) {
+                        const int64_t m = (int64_t)it * T + i, n = (int64_t)jt * T + j;
+                        for (auto &v : S) v = 0;
+                        for (int a = 0; a < s; a++) {
+                            const int8_t *qa = A.slice(a, m);
+                            for (int b = 0; a + b + 2 <= s + 1; b++) {
+                                const int8_t *qb = B.slice(b, n);
+                                int32_t acc = 0;                               // one digit pair never overflows: K * 4096 < 2^31
+                                for (int64_t k = kbeg; k < kend; k++) acc += (int32_t)qa[k] * (int32_t)qb[k];
+                                S[a + b + 2] += acc;
+                            }
+                        }
+                        double r = 0.0;
+                        for (int gq = s + 1; gq >= 2; gq--) {                  // Horner, smallest contributions first:
+                            ozaki_max_abs_sum = std::max(ozaki_max_abs_sum, std::llabs(S[gq]));
+                            r = r * 0.0078125 + (double)S[gq];                 // r / 128 + S_g (the kernel's epilogue)
+                        }
+                        r = std::ldexp(r, A.e[m] + B.e[n] - 12);               // digit weights 2^-(7 g - 2), g = 2 last
+                        double *c = g.C + m * g.ldc + n;
+                        *c = g.beta == 0.0 ? g.alpha * r : g.alpha * r + g.beta * *c;
+                    }
+            }
+    }
 
     void gemm(const GemmDesc &g) {
         gemm_calls++;
+        if (ozaki > 0 && !g.coltab && g.kmode <= K_MAX_IJ) {
+            const long tiles = g.tri_out ? (long)g.mt * (g.mt + 1) / 2 : (long)g.mt * g.nt;
+            if (tiles >= ozaki_min_tiles) { ozaki_calls++; gemm_ozaki(g); return; }
+        }
         const int T = kTile;
         std::vector<double> acc((size_t)T * T);
         for (int it = 0; it < g.mt; it++)
@@ -187,13 +279,22 @@ int emul_distributed(int64_t np, double *M, int nranks, int pw, double *Q, doubl
 
 // M: np x np row-major; on entry the LOWER triangle holds an SPD matrix (upper is poisoned here with NaN);
 // R: mt*128 x np right-hand-side rows (solved in place); on exit M lower = inverse.
+int emul_spd_solve_invert_ex(int64_t np, double *M, int mt, double *R, int invert, double *stats, int ozaki, int ozaki_min_tiles);
 int emul_spd_solve_invert(int64_t np, double *M, int mt, double *R, int invert, double *stats) {
+    return emul_spd_solve_invert_ex(np, M, mt, R, invert, stats, 0, 1);
+}
+
+// the same with every GEMM launch of >= ozaki_min_tiles output tiles computed by the int8-slice emulation (ozaki digits);
+// stats (5 doubles): gemm launches, diagonal blocks, flop, launches through the emulation, largest integer group sum
+int emul_spd_solve_invert_ex(int64_t np, double *M, int mt, double *R, int invert, double *stats, int ozaki, int ozaki_min_tiles) {
     const double nan = std::numeric_limits<double>::quiet_NaN();
     for (int64_t r = 0; r < np; r++)
         for (int64_t c = r + 1; c < np; c++)
             if ((r / kTile) != (c / kTile)) M[r * np + c] = nan;   // strictly-upper off-diagonal tiles are never read
     std::vector<double> Dinv((size_t)np * kTile, nan), W;
     HostBackend be;
+    be.ozaki = ozaki;
+    be.ozaki_min_tiles = ozaki_min_tiles;
     DenseSchedule<HostBackend> ds{be, M, np, np, Dinv.data()};
     ds.potrf();
     if (mt > 0) ds.solve_rows(R, np, mt);
@@ -201,7 +302,10 @@ int emul_spd_solve_invert(int64_t np, double *M, int mt, double *R, int invert, 
         W.assign((size_t)np * np, nan);
         ds.invert_from_factor(W.data());
     }
-    if (stats) { stats[0] = (double)be.gemm_calls; stats[1] = (double)be.diag_calls; stats[2] = be.flops; }
+    if (stats) {
+        stats[0] = (double)be.gemm_calls; stats[1] = (double)be.diag_calls; stats[2] = be.flops;
+        if (ozaki > 0) { stats[3] = (double)be.ozaki_calls; stats[4] = (double)be.ozaki_max_abs_sum; }
+    }
     return be.info;
 }
 }

@@ -1,0 +1,58 @@
+"""Numerics of FP64 products built from int8 digit products (experiment JAICOV_GEMM_OZAKI): the
+product's blocked Cholesky + inverse schedule (csrc/dense_driver.hpp) runs on the TEST-ONLY host backend with every GEMM
+launch computed by the integer emulation of tests/emul/host_backend.cpp -- per-row power-of-two scaling, `s` signed digits
+|q| <= 64, exact integer sums per digit-sum group (what an s8 x s8 -> s32 tensor-core accumulator holds), groups beyond
+s + 1 dropped, FP64 Horner combination -- and is compared with the FP64 schedule on the same systems."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'tools'))
+
+import ozaki_study as oz   # noqa: E402
+
+
+@pytest.fixture(scope='module')
+def emul(built):
+    return oz.load_emul()
+
+
+def deviations(emul, S, rhs, digits):
+    Xref = oz.reference_inverse(S)
+    sc = np.sqrt(np.abs(np.diag(Xref))).astype(np.float64)
+    out = {}
+    for s in [0] + list(digits):
+        info, Q, y, st, _ = oz.run(emul, S, rhs, s)
+        assert info == 0
+        out[s] = (float(np.max(np.abs(Q.astype(np.longdouble) - Xref) / np.outer(sc, sc))), st.copy())
+    return out
+
+
+def test_eight_digits_match_the_fp64_schedule_on_a_random_system(emul):
+    rng = np.random.default_rng(5)
+    n = 300                                           # padded to 384 = 3 tiles: recursion, K_B_LOWER / K_A_LOWER / K_MAX_IJ launches
+    A = rng.standard_normal((n, n))
+    S = A @ A.T + 0.05 * n * np.eye(n)
+    dd = 1 / np.sqrt(np.diag(S))
+    S = S * dd[:, None] * dd[None, :]
+    dev = deviations(emul, S, rng.standard_normal(n), (5, 8))
+    e64, e5, e8 = dev[0][0], dev[5][0], dev[8][0]
+    assert dev[8][1][3] > 0                           # launches went through the integer path
+    assert dev[8][1][4] < 2 ** 31                     # every integer group sum fits an s32 accumulator
+    assert e8 <= 8 * e64 + 1e-15, (e8, e64)           # eight digits: FP64-equivalent
+    assert e5 > 100 * e64                             # five digits are visibly short: the test can tell the difference
+
+
+def test_eight_digits_on_a_bundle_network(emul):
+    """M~ = V N V + B~'B~ of a free network (config 2, datum border folded in): the cofactor matrix from int8 digit products
+    stays two orders of magnitude inside the 1e-8 parity bar, like the FP64 schedule."""
+    from tests.scenes import synthetic_scene
+    scene, _ = synthetic_scene(2, images=8, targets=60)
+    S, rhs = oz.scaled_system(scene)
+    dev = deviations(emul, S, rhs, (8,))
+    assert dev[8][0] <= 1e-10 and dev[0][0] <= 1e-10, dev
+    assert dev[8][0] <= 8 * dev[0][0] + 1e-14
