@@ -27,7 +27,7 @@ EXPORTS = [
     'jaicov_set_scale_bars', 'jaicov_add_observed_group', 'jaicov_set_datum', 'jaicov_set_reduced_rows', 'jaicov_estimate', 'jaicov_iterate',
     'jaicov_get_stats', 'jaicov_get_values', 'jaicov_get_dx', 'jaicov_get_qxx_packed', 'jaicov_get_qxx_block',
     'jaicov_get_qxx_diag', 'jaicov_get_qxx_submatrix', 'jaicov_eval_residual_jacobian', 'jaicov_get_normal_equations', 'jaicov_omega',
-    'jaicov_spd_solve_invert', 'jaicov_propagate_eo_transform', 'jaicov_dlt_batch',
+    'jaicov_spd_solve_invert', 'jaicov_propagate_eo_transform', 'jaicov_dlt_batch', 'jaicov_gemm_tiles',
 ]
 
 
@@ -371,3 +371,23 @@ def spd_solve_invert(a, b=None, invert=True, device=0):
     if rc not in (OK,):
         raise JaicovError(rc, 'jaicov_spd_solve_invert')
     return (a if invert else None), b, (f.value, i.value)
+
+
+def gemm_tiles(A, B, C, a_layout=0, b_layout=0, alpha=1.0, beta=0.0, tri_out=False, kmode=0, reps=1, device=0):
+    """Stage access to the tensor-core tile product (jaicov_gemm_tiles): C <- alpha op(A) op(B)' + beta C on 128 x 128 tiles.
+    A: (128 mt, K) if a_layout == 0 else (K, 128 mt); B likewise with 128 nt; C: (128 mt, 128 nt).  Returns (C, ms)."""
+    L = load()
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    B = np.ascontiguousarray(B, dtype=np.float64)
+    C = np.array(C, dtype=np.float64, order='C')
+    Mr, K = (A.shape if a_layout == 0 else A.shape[::-1])
+    Nr = B.shape[0] if b_layout == 0 else B.shape[1]
+    ms = ctypes.c_double(0)
+    L.jaicov_gemm_tiles.argtypes = [ctypes.c_int32] * 5 + [ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_int64,
+                                    ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                    ctypes.c_int32, ctypes.c_void_p]
+    rc = L.jaicov_gemm_tiles(device, a_layout, b_layout, Mr // 128, Nr // 128, K, alpha, beta, A.ctypes.data, A.shape[1], B.ctypes.data,
+                             B.shape[1], C.ctypes.data, C.shape[1], int(bool(tri_out)), kmode, reps, ctypes.byref(ms))
+    if rc != OK:
+        raise JaicovError(rc, 'jaicov_gemm_tiles')
+    return C, ms.value

@@ -24,6 +24,7 @@ long long g_launch_count = 0;
 
 // dense_kernels.cu
 void launch_gemm(const GemmDesc &g, cudaStream_t s);
+size_t ozaki_release_scratch();   // ozaki.cu (experiment, default off)
 void launch_potrf_diag(double *A, int64_t ld, double *dinv, int row0, int *info, cudaStream_t s);
 void launch_copy2d(double *dst, int64_t ldd, const double *src, int64_t lds, int64_t rows, int64_t cols, cudaStream_t s);
 void launch_solve_rows8(const double *L, int64_t ld, const double *dinv, double *R, double *Y, int64_t np, cudaStream_t s);
@@ -999,7 +1000,7 @@ int32_t jaicov_default_options(jaicov_options *opt) {
 
 int32_t jaicov_device_count(void) { return usable_devices(); }
 
-int64_t jaicov_release_cached_memory(void) { return (int64_t)g_cache.purge(); }
+int64_t jaicov_release_cached_memory(void) { return (int64_t)(g_cache.purge() + ozaki_release_scratch()); }
 
 int64_t jaicov_launch_count(void) { return (int64_t)g_launch_count; }
 
@@ -1678,6 +1679,45 @@ int32_t jaicov_omega(jaicov_handle *h, const double *dx, double *omega) {
     double t = 0.0;
     for (double v : om) t += v;
     *omega = t;
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+int32_t jaicov_gemm_tiles(int32_t device, int32_t a_layout, int32_t b_layout, int32_t mt, int32_t nt, int64_t K, double alpha,
+                          double beta, const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc,
+                          int32_t tri_out, int32_t kmode, int32_t reps, double *ms) {
+    if (mt <= 0 || nt <= 0 || K <= 0 || K % kBlk || !A || !B || !C || kmode < K_FULL || kmode > K_MAX_IJ || (tri_out && mt != nt) ||
+        (a_layout != 0 && a_layout != 1) || (b_layout != 0 && b_layout != 1))
+        return JAICOV_ILLEGAL_ARGUMENT;
+    const int64_t Mr = (int64_t)mt * kBlk, Nr = (int64_t)nt * kBlk;
+    if (lda < (a_layout ? Mr : K) || ldb < (b_layout ? Nr : K) || ldc < Nr || (lda | ldb | ldc) % 2) return JAICOV_ILLEGAL_ARGUMENT;
+    jaicov_handle *h = nullptr;
+    API_GUARD_BEGIN
+    if (usable_devices() == 0) return JAICOV_NOT_INITIALISED;
+    JCHECK(cudaSetDevice(device));
+    DevBuf<double> dA, dB, dC;
+    const size_t na = (size_t)(a_layout ? K : Mr) * lda, nb = (size_t)(b_layout ? K : Nr) * ldb, nc = (size_t)Mr * ldc;
+    dA.upload(A, na); dB.upload(B, nb); dC.upload(C, nc);
+    cudaStream_t s;
+    JCHECK(cudaStreamCreate(&s));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    GemmDesc g;
+    g.al = a_layout; g.bl = b_layout; g.mt = mt; g.nt = nt; g.K = K; g.alpha = alpha; g.beta = beta;
+    g.A = dA.p; g.lda = lda; g.B = dB.p; g.ldb = ldb; g.C = dC.p; g.ldc = ldc; g.tri_out = tri_out ? 1 : 0; g.kmode = kmode;
+    const int n_rep = (beta != 0.0 || reps < 1) ? 1 : reps;
+    JCHECK(cudaStreamSynchronize(0));
+    cudaEventRecord(e0, s);
+    for (int r = 0; r < n_rep; r++) launch_gemm(g, s);
+    cudaEventRecord(e1, s);
+    JCHECK(cudaGetLastError());
+    JCHECK(cudaStreamSynchronize(s));
+    float f = 0;
+    cudaEventElapsedTime(&f, e0, e1);
+    if (ms) *ms = f / n_rep;
+    JCHECK(cudaMemcpy(C, dC.p, nc * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaStreamDestroy(s);
     return JAICOV_OK;
     API_GUARD_END(h)
 }

@@ -239,11 +239,14 @@ static void launch_gemm_l(const GemmDesc &g, cudaStream_t s) {
     else launch_gemm_t<AL, BL, 32>(g, tiles, s);
 }
 
+bool launch_gemm_ozaki(const GemmDesc &g, cudaStream_t s);   // ozaki.cu: experiment, takes nothing unless JAICOV_GEMM_OZAKI is set
+
 void launch_gemm(const GemmDesc &g_in, cudaStream_t s) {
     // experiment switch (default off): band-swizzled tile order of the lower-triangular launches, DESIGN.md section 9
     static const int band = [] { const char *e = getenv("JAICOV_TILE_BAND"); return e ? atoi(e) : 0; }();
     GemmDesc g = g_in;
     if (g.tri_out && band > 0 && g.tile_band == 0) g.tile_band = band;
+    if (launch_gemm_ozaki(g, s)) return;
     if (g.al == 0 && g.bl == 0) launch_gemm_l<0, 0>(g, s);
     else if (g.al == 0 && g.bl == 1) launch_gemm_l<0, 1>(g, s);
     else if (g.al == 1 && g.bl == 1) launch_gemm_l<1, 1>(g, s);

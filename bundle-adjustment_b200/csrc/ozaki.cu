@@ -1,0 +1,477 @@
+// ozaki.cu -- EXPERIMENT, default OFF (JAICOV_GEMM_OZAKI=<digits 4..8>): FP64 GEMM tiles built from int8 digit products on
+// the 5th-generation tensor cores (tcgen05.mma kind::i8, operands staged by TMA, s32 accumulators in TMEM).
+//
+// Why: every O(n^3) flop of the path (Cholesky, inverse, the structured route's products) runs on k_gemm at 94 % DMMA pipe
+// utilisation -- 96 % of the measured cuBLAS DGEMM rate.  tcgen05 has no f64 kind, but B200's INT8
+// tensor rate is two orders of magnitude above its FP64 tensor rate, so an FP64 product can be assembled from exact
+// integer digit products ("Ozaki scheme I"):
+//   * every operand row is scaled by a power of two into (-1, 1) and cut into S signed digits |q| <= 64 (6 + 7 (S-1) bits);
+//   * digit products q_i[k] * q_j[k] are summed over k EXACTLY in s32 (|sum| <= pairs * K * 4096 < 2^31), one TMEM
+//     accumulator per digit-sum group g = i + j; pairs with i + j > S + 1 are below the target accuracy and dropped;
+//   * the epilogue combines the groups in FP64 (Horner in 2^-7) and applies the row / column exponents, alpha and beta.
+// With S = 8 (36 digit products) the results are FP64-equivalent: tests/test_ozaki_emulation.py runs the product's own
+// Cholesky + inverse schedule with this arithmetic emulated bit for bit on the host (tests/emul/host_backend.cpp) and gets
+// the cofactor matrix of real bundle networks as close to a long-double reference as the FP64 schedule itself.
+//
+// STATUS: written and compiled for sm_100a without access to a GPU (this round's GPU budget was spent); it has NOT run yet.
+// Nothing takes this path unless JAICOV_GEMM_OZAKI is set; tools/next_round_ab.sh holds the first-run checks (small SPD
+// systems against the FP64 route under a timeout, then config 4 / 5 timings).  Kept out of the default path until it is
+// parity-green on a B200.
+//
+// Shapes: CTA tile 128 x 64 (S accumulators of 64 TMEM columns = all 512 columns for S = 8), k-block 64 bytes (SWIZZLE_64B
+// rows), two smem stages of S * (128 + 64) * 64 bytes (96 KB each for S = 8); warp 0 = TMA producer, warp 1 = MMA issuer and
+// TMEM owner, warps 2..5 = epilogue (one TMEM lane quarter each).  One CTA per SM; the grid is the tile list of the launch in
+// the same order as k_gemm (longest contractions first, lower tiles only for symmetric outputs).
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.h"
+#include "dense_driver.hpp"
+
+namespace jaicov {
+
+// ---- digit extraction ----------------------------------------------------------------------------------------------------
+// valid k-range of the rows of row tile t (rows 128 t .. 128 t + 127) of an operand; everything outside becomes zero digits
+enum OzRange : int { OZ_FULL = 0, OZ_FROM_TILE = 1 /* k >= 128 t */, OZ_UPTO_TILE = 2 /* k < 128 (t + 1) */ };
+
+struct OzSplitArgs {
+    const double *X;
+    int64_t ld;
+    int layout;          // 0: X(row, k) at X[row * ld + k];  1: at X[k * ld + row]
+    int64_t rows, K;     // multiples of 128
+    int range;           // OzRange
+    int S;
+    int8_t *Q;           // [S][rows][K]
+    int32_t *e;          // [rows]: |x| < 2^e over the row's valid range (0 for an all-zero row)
+    unsigned long long *amax;   // [rows]: bit pattern of max |x| (non-negative doubles order like unsigned integers)
+};
+
+__device__ __forceinline__ bool oz_valid(const OzSplitArgs &a, int64_t row, int64_t k) {
+    const int64_t t = row >> 7;
+    if (a.range == OZ_FROM_TILE) return k >= (t << 7);
+    if (a.range == OZ_UPTO_TILE) return k < ((t + 1) << 7);
+    return true;
+}
+
+// thread <-> (row, 16 consecutive k).  layout 0: a warp covers one row and 512 consecutive k (contiguous 4 KB read);
+// layout 1: a warp covers 32 consecutive rows of one 16-wide k chunk (every k is one coalesced 256-byte read).
+__device__ __forceinline__ bool oz_map(const OzSplitArgs &a, int64_t &row, int64_t &k0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (a.layout == 0) {
+        row = (int64_t)blockIdx.y * 4 + warp;
+        k0 = ((int64_t)blockIdx.x * 32 + lane) * 16;
+    } else {
+        row = (int64_t)blockIdx.y * 128 + threadIdx.x;
+        k0 = (int64_t)blockIdx.x * 16;
+    }
+    return row < a.rows && k0 < a.K;
+}
+
+__device__ __forceinline__ void oz_load16(const OzSplitArgs &a, int64_t row, int64_t k0, double (&x)[16]) {
+    if (a.layout == 0) {
+        const double2 *p = reinterpret_cast<const double2 *>(a.X + row * a.ld + k0);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { const double2 v = p[i]; x[2 * i] = v.x; x[2 * i + 1] = v.y; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) x[i] = a.X[(k0 + i) * a.ld + row];
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+        if (!oz_valid(a, row, k0 + i)) x[i] = 0.0;
+}
+
+__global__ void __launch_bounds__(128) k_oz_rowmax(OzSplitArgs a) {
+    int64_t row, k0;
+    const bool on = oz_map(a, row, k0);
+    double m = 0.0;
+    if (on) {
+        double x[16];
+        oz_load16(a, row, k0, x);
+#pragma unroll
+        for (int i = 0; i < 16; i++) m = fmax(m, fabs(x[i]));
+    }
+    if (a.layout == 0) {   // the warp shares one row
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31) == 0 && on && m > 0.0) atomicMax(a.amax + row, (unsigned long long)__double_as_longlong(m));
+    } else if (on && m > 0.0) {
+        atomicMax(a.amax + row, (unsigned long long)__double_as_longlong(m));
+    }
+}
+
+__global__ void __launch_bounds__(128) k_oz_digits(OzSplitArgs a) {
+    int64_t row, k0;
+    if (!oz_map(a, row, k0)) return;
+    const unsigned long long bits = a.amax[row];
+    const int ef = (int)((bits >> 52) & 0x7ff);               // biased exponent of the row maximum
+    const bool zero = ef < 5 || ef > 2046;                    // all-zero row, or too small to scale / not finite: zero digits
+    if (k0 == 0) a.e[row] = zero ? 0 : ef - 1022;             // |x| < 2^(ef - 1022)
+    double t[16];
+    if (!zero) {
+        oz_load16(a, row, k0, t);
+        const double sc = __longlong_as_double((long long)(2051 - ef) << 52);   // 2^(6 - e): |t| < 64
+#pragma unroll
+        for (int i = 0; i < 16; i++) t[i] *= sc;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) t[i] = 0.0;
+    }
+    for (int j = 0; j < a.S; j++) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int q = __double2int_rn(t[i]);              // |q| <= 64
+            t[i] = (t[i] - (double)q) * 128.0;                // exact: |t - q| <= 1/2
+            w[i >> 2] |= (uint32_t)(q & 0xff) << (8 * (i & 3));
+        }
+        *reinterpret_cast<uint4 *>(a.Q + ((size_t)j * a.rows + row) * a.K + k0) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+static void launch_split(const OzSplitArgs &a, cudaStream_t s) {
+    JCHECK(cudaMemsetAsync(a.amax, 0, (size_t)a.rows * sizeof(unsigned long long), s));
+    const dim3 grid = a.layout == 0 ? dim3((unsigned)((a.K + 511) / 512), (unsigned)(a.rows / 4))
+                                    : dim3((unsigned)(a.K / 16), (unsigned)(a.rows / 128));
+    g_launch_count += 2;
+    k_oz_rowmax<<<grid, 128, 0, s>>>(a);
+    k_oz_digits<<<grid, 128, 0, s>>>(a);
+}
+
+// ---- the tile kernel -----------------------------------------------------------------------------------------------------
+constexpr int OZ_BM = 128, OZ_BN = 64, OZ_BK = 64, OZ_STAGES = 2, OZ_THREADS = 192, OZ_TMEM_COLS = 512;
+
+template <int S> struct OzCfg {
+    static constexpr int A_STAGE = S * OZ_BM * OZ_BK;   // bytes: [S][128 rows][64 B]
+    static constexpr int B_STAGE = S * OZ_BN * OZ_BK;   //        [S][ 64 rows][64 B]
+    static constexpr int STAGE = A_STAGE + B_STAGE;
+    static constexpr int SMEM = OZ_STAGES * STAGE + 1024 /* alignment slack */ + 128 /* barriers, TMEM slot */;
+    static_assert(S >= 2 && S * OZ_BN <= OZ_TMEM_COLS, "one 64-column accumulator per digit-sum group");
+    static_assert(SMEM <= 227 * 1024, "two stages must fit the 227 KB of one CTA");
+};
+
+struct OzGemmArgs {
+    const int32_t *ea, *eb;   // row exponents of op(A) / op(B)
+    double *C;
+    int64_t ldc, K;
+    double alpha, beta;
+    int mt, nt, tri_out, tile_band, kmode;
+};
+
+__device__ __forceinline__ uint32_t oz_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void oz_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void oz_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void oz_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void oz_tma_load_3d(const CUtensorMap *map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        :
+        : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// K-major operand rows of 64 bytes, SWIZZLE_64B: 8-row groups are 512 bytes apart (cute::UMMA::SmemDescriptor, sm_100 version 1)
+__device__ __forceinline__ uint64_t oz_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);       // start address >> 4                      bits [0, 14)
+    d |= (uint64_t)1 << 16;                         // leading byte offset (unused, swizzled)  bits [16, 30)
+    d |= (uint64_t)(512 >> 4) << 32;                // stride byte offset: 8 rows x 64 B       bits [32, 46)
+    d |= (uint64_t)1 << 46;                         // descriptor version of sm_100            bits [46, 48)
+    d |= (uint64_t)4 << 61;                         // layout type SWIZZLE_64B                 bits [61, 64)
+    return d;
+}
+// D[tmem] (+)= A[smem] * B[smem]', s8 x s8 -> s32, issued by one thread for the whole CTA
+__device__ __forceinline__ void oz_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)   // no lane disabled
+        : "memory");
+}
+__device__ __forceinline__ void oz_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void oz_tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int S>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+k_gemm_oz(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, OzGemmArgs p) {
+    using Cfg = OzCfg<S>;
+    extern __shared__ uint8_t oz_raw[];
+    const uint32_t raw = oz_smem_u32(oz_raw);
+    uint8_t *sm = oz_raw + (((raw + 1023u) & ~1023u) - raw);           // swizzle atoms need their natural alignment
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + OZ_STAGES * Cfg::STAGE);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+    const uint32_t full0 = oz_smem_u32(bars), empty0 = oz_smem_u32(bars + OZ_STAGES), accum = oz_smem_u32(bars + 2 * OZ_STAGES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- tile decode: the same order as k_gemm, every 128 x 128 tile as two 64-column halves ---------------------------
+    const int l = blockIdx.x >> 1, half = blockIdx.x & 1;
+    int it, jt;
+    if (p.tri_out) {
+        tri_tile_decode(l, p.mt, p.tile_band, it, jt);
+    } else {
+        it = l / p.nt;
+        jt = l - it * p.nt;
+        if (p.kmode == K_A_LOWER) it = p.mt - 1 - it;
+    }
+    int64_t kbeg = 0, kend = p.K;
+    if (p.kmode == K_B_LOWER) kbeg = (int64_t)jt * 128;
+    else if (p.kmode == K_A_LOWER) kend = min(p.K, (int64_t)(it + 1) * 128);
+    else if (p.kmode == K_MAX_IJ) kbeg = (int64_t)max(it, jt) * 128;
+    const int nkb = (int)((kend - kbeg) / OZ_BK);
+    const int m0 = it * 128, n0 = jt * 128 + half * OZ_BN;
+
+    // ---- one-time setup --------------------------------------------------------------------------------------------------
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+        for (int i = 0; i < OZ_STAGES; i++) {
+            oz_mbar_init(full0 + 8 * i, 1);
+            oz_mbar_init(empty0 + 8 * i, 1);
+        }
+        oz_mbar_init(accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem_u32(tmem_slot)), "r"(OZ_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
+
+    if (warp == 0) {
+        // ===== TMA producer: one elected lane, S digit planes of A and of B per stage as two 3-D boxes =====
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; kb++) {
+                const int st = kb % OZ_STAGES;
+                const uint32_t ph = (uint32_t)(kb / OZ_STAGES) & 1u;
+                oz_mbar_wait(empty0 + 8 * st, ph ^ 1u);
+                oz_mbar_expect_tx(full0 + 8 * st, (uint32_t)Cfg::STAGE);
+                const uint32_t dst = oz_smem_u32(sm + st * Cfg::STAGE);
+                const int k0 = (int)(kbeg + (int64_t)kb * OZ_BK);
+                oz_tma_load_3d(&mapA, full0 + 8 * st, dst, k0, m0, 0);
+                oz_tma_load_3d(&mapB, full0 + 8 * st, dst + Cfg::A_STAGE, k0, n0, 0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: digit pair (i, j) accumulates into the TMEM accumulator of its group i + j =====
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D = s32, A = B = signed 8 bit, both K-major, N = 64, M = 128
+            constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
+            for (int kb = 0; kb < nkb; kb++) {
+                const int st = kb % OZ_STAGES;
+                const uint32_t ph = (uint32_t)(kb / OZ_STAGES) & 1u;
+                oz_mbar_wait(full0 + 8 * st, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_base = oz_smem_u32(sm + st * Cfg::STAGE), b_base = a_base + Cfg::A_STAGE;
+#pragma unroll 1
+                for (int i = 0; i < S; i++)
+#pragma unroll 1
+                    for (int j = 0; i + j < S; j++)
+#pragma unroll
+                        for (int kk = 0; kk < OZ_BK / 32; kk++) {
+                            const uint64_t ad = oz_smem_desc(a_base + i * (OZ_BM * OZ_BK) + kk * 32);
+                            const uint64_t bd = oz_smem_desc(b_base + j * (OZ_BN * OZ_BK) + kk * 32);
+                            oz_mma_i8(tmem + (uint32_t)((i + j) * OZ_BN), ad, bd, idesc, (kb > 0 || kk > 0 || i > 0) ? 1u : 0u);
+                        }
+                oz_commit(empty0 + 8 * st);        // frees the stage once these MMAs have read it
+            }
+            oz_commit(accum);                      // all groups complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lanes 32 (warp % 4) .. +31 = rows of the tile =====
+        const int q = warp & 3;
+        oz_mbar_wait(accum, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int64_t m = (int64_t)m0 + 32 * q + lane;
+        const int ea = p.ea[m];
+        double *crow = p.C + m * p.ldc + n0;
+        const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
+        for (int c8 = 0; c8 < OZ_BN / 8; c8++) {
+            double r[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) r[c] = 0.0;
+#pragma unroll 1
+            for (int gi = S - 1; gi >= 0; gi--) {          // Horner in 2^-7, smallest contributions first
+                uint32_t v[8];
+                oz_tmem_ld8(trow + (uint32_t)(gi * OZ_BN + c8 * 8), v);
+#pragma unroll
+                for (int c = 0; c < 8; c++) r[c] = r[c] * 0.0078125 + (double)(int)v[c];
+            }
+            double out[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) out[c] = p.alpha * ldexp(r[c], ea + p.eb[n0 + c8 * 8 + c] - 12);   // digit weights 2^-(7 g - 2)
+            double2 *dst = reinterpret_cast<double2 *>(crow + c8 * 8);
+            if (p.beta != 0.0) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const double2 old = dst[c];
+                    out[2 * c] += p.beta * old.x;
+                    out[2 * c + 1] += p.beta * old.y;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++) dst[c] = make_double2(out[2 * c], out[2 * c + 1]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(OZ_TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------------
+namespace {
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// digit planes Q[S][rows][K] (int8, K contiguous) as a 3-D tensor; one box = S planes x box_rows rows x 64 bytes
+bool make_map(CUtensorMap *map, const int8_t *Q, int64_t rows, int64_t K, int S, int box_rows) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)S};
+    const cuuint64_t gstride[2] = {(cuuint64_t)K, (cuuint64_t)rows * (cuuint64_t)K};   // bytes, dimensions 1 and 2
+    const cuuint32_t box[3] = {(cuuint32_t)OZ_BK, (cuuint32_t)box_rows, (cuuint32_t)S};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t *>(Q), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct OzScratch {
+    int8_t *q[2] = {nullptr, nullptr};
+    size_t cap[2] = {0, 0};
+    int32_t *e[2] = {nullptr, nullptr};
+    unsigned long long *amax[2] = {nullptr, nullptr};
+    size_t rows_cap[2] = {0, 0};
+    bool ensure(int w, size_t bytes, size_t rows) {
+        if (bytes > cap[w]) {
+            if (q[w]) cudaFree(q[w]);
+            q[w] = nullptr; cap[w] = 0;
+            if (cudaMalloc(&q[w], bytes) != cudaSuccess) { cudaGetLastError(); return false; }
+            cap[w] = bytes;
+        }
+        if (rows > rows_cap[w]) {
+            if (e[w]) cudaFree(e[w]);
+            if (amax[w]) cudaFree(amax[w]);
+            e[w] = nullptr; amax[w] = nullptr; rows_cap[w] = 0;
+            if (cudaMalloc(&e[w], rows * sizeof(int32_t)) != cudaSuccess || cudaMalloc(&amax[w], rows * sizeof(unsigned long long)) != cudaSuccess) {
+                cudaGetLastError();
+                return false;
+            }
+            rows_cap[w] = rows;
+        }
+        return true;
+    }
+    size_t release() {
+        size_t b = cap[0] + cap[1];
+        for (int w = 0; w < 2; w++) {
+            if (q[w]) cudaFree(q[w]);
+            if (e[w]) cudaFree(e[w]);
+            if (amax[w]) cudaFree(amax[w]);
+            q[w] = nullptr; e[w] = nullptr; amax[w] = nullptr; cap[w] = rows_cap[w] = 0;
+        }
+        return b;
+    }
+};
+OzScratch g_oz;
+
+template <int S>
+void launch_tiles(const CUtensorMap &ma, const CUtensorMap &mb, const OzGemmArgs &a, int64_t tiles, cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) {
+        JCHECK(cudaFuncSetAttribute(k_gemm_oz<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<S>::SMEM));
+        attr = true;
+    }
+    g_launch_count++;
+    k_gemm_oz<S><<<(unsigned)(tiles * 2), OZ_THREADS, OzCfg<S>::SMEM, s>>>(ma, mb, a);
+}
+
+}  // namespace
+
+size_t ozaki_release_scratch() { return g_oz.release(); }
+
+// Takes the launch if the experiment is switched on and the launch is one of the big plain / triangular-operand products;
+// returns false (nothing launched) otherwise, and the caller runs k_gemm.
+bool launch_gemm_ozaki(const GemmDesc &g, cudaStream_t s) {
+    static const int digits = [] { const char *e = getenv("JAICOV_GEMM_OZAKI"); return e ? atoi(e) : 0; }();
+    if (digits < 4 || digits > 8) return false;
+    static const int64_t min_tiles = [] { const char *e = getenv("JAICOV_OZAKI_MIN_TILES"); return e ? (int64_t)atoll(e) : (int64_t)148; }();
+    if (g.coltab || g.kmode > K_MAX_IJ) return false;
+    const int64_t tiles = g.tri_out ? (int64_t)g.mt * (g.mt + 1) / 2 : (int64_t)g.mt * g.nt;
+    if (tiles < min_tiles || g.K < 128) return false;
+    if ((double)g.K * digits * 4096.0 >= 2147483648.0) return false;     // a digit-sum group must fit its s32 accumulator
+    const int64_t Mr = (int64_t)g.mt * 128, Nr = (int64_t)g.nt * 128;
+    const int ra = g.kmode == K_MAX_IJ ? OZ_FROM_TILE : (g.kmode == K_A_LOWER ? OZ_UPTO_TILE : OZ_FULL);
+    const int rb = (g.kmode == K_MAX_IJ || g.kmode == K_B_LOWER) ? OZ_FROM_TILE : OZ_FULL;
+    const bool shared = g.A == g.B && g.lda == g.ldb && g.al == g.bl && ra == rb && Mr == Nr;
+    if (!g_oz.ensure(0, (size_t)digits * Mr * g.K, (size_t)Mr)) return false;
+    if (!shared && !g_oz.ensure(1, (size_t)digits * Nr * g.K, (size_t)Nr)) return false;
+    CUtensorMap ma, mb;
+    const int wb = shared ? 0 : 1;
+    if (!make_map(&ma, g_oz.q[0], Mr, g.K, digits, OZ_BM) || !make_map(&mb, g_oz.q[wb], Nr, g.K, digits, OZ_BN)) return false;
+    OzSplitArgs sa{g.A, g.lda, g.al, Mr, g.K, ra, digits, g_oz.q[0], g_oz.e[0], g_oz.amax[0]};
+    launch_split(sa, s);
+    if (!shared) {
+        OzSplitArgs sb{g.B, g.ldb, g.bl, Nr, g.K, rb, digits, g_oz.q[1], g_oz.e[1], g_oz.amax[1]};
+        launch_split(sb, s);
+    }
+    OzGemmArgs a{g_oz.e[0], g_oz.e[wb], g.C, g.ldc, g.K, g.alpha, g.beta, g.mt, g.nt, g.tri_out, g.tile_band, g.kmode};
+    switch (digits) {
+        case 4: launch_tiles<4>(ma, mb, a, tiles, s); break;
+        case 5: launch_tiles<5>(ma, mb, a, tiles, s); break;
+        case 6: launch_tiles<6>(ma, mb, a, tiles, s); break;
+        case 7: launch_tiles<7>(ma, mb, a, tiles, s); break;
+        default: launch_tiles<8>(ma, mb, a, tiles, s); break;
+    }
+    return true;
+}
+
+}  // namespace jaicov

@@ -274,6 +274,19 @@ int32_t jaicov_get_normal_equations(jaicov_handle *h, double *n_packed, double *
 /* Omega = v'Pv for a given dx (reference column order, length u+d) at the current values (getOmega, :472-491) */
 int32_t jaicov_omega(jaicov_handle *h, const double *dx, double *omega);
 
+/* The tensor-core tile product behind every O(n^3) stage (factor, inverse, the structured route's products), exposed
+ * for parity tests and profiling:  C = alpha * op(A) op(B)' + beta * C  on 128 x 128 tiles, host buffers.
+ * op(A) is (128 mt) x K: a_layout 0 = stored row-major with leading dimension lda (k contiguous), 1 = stored as K rows of
+ * leading dimension lda (the tile-row index contiguous); op(B) is (128 nt) x K, b_layout likewise; C is (128 mt) x (128 nt)
+ * row-major (ldc).  kmode: 0 full contraction; 1 = op(B)'[k][n] lower triangular (k >= n: starts at the tile column's
+ * diagonal); 2 = op(A)[m][k] lower triangular (k <= m: stops after the tile row's diagonal); 3 = both operands stored
+ * [k][.] lower triangular (k >= max(m, n)) -- the hints the schedule of csrc/dense_driver.hpp passes.  tri_out != 0 (mt == nt):
+ * only tiles on or below the diagonal are computed.  reps >= 1 launches are timed (forced to 1 when beta != 0);
+ * ms (may be NULL) <- average device time of one launch.  No handle; fails with JAICOV_NOT_INITIALISED without a device. */
+int32_t jaicov_gemm_tiles(int32_t device, int32_t a_layout, int32_t b_layout, int32_t mt, int32_t nt, int64_t K, double alpha,
+                          double beta, const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc,
+                          int32_t tri_out, int32_t kmode, int32_t reps, double *ms);
+
 /* Level-1 seam (the routines BundleAdjustment needs from LAPACK, MathExtension.java:304-366), dense SPD route:
  * in: a = symmetric positive definite n x n, row-major, host; b = nrhs right-hand sides [nrhs][n] (may be NULL).
  * out: a <- a^-1 (full symmetric) if invert != 0, b <- solutions.  Returns SINGULAR_MATRIX if not SPD. */

@@ -277,6 +277,19 @@ int emul_distributed(int64_t np, double *M, int nranks, int pw, double *Q, doubl
     return info;
 }
 
+// one tile-grid product through the host backend (ozaki = 0: FP64 loops; > 0: int8-digit emulation): the host twin of
+// jaicov_gemm_tiles, used to validate the expectations of tools/ozaki_gpu_check.py without a GPU
+int emul_gemm_tiles(int al, int bl, int mt, int nt, int64_t K, double alpha, double beta, const double *A, int64_t lda, const double *B,
+                    int64_t ldb, double *C, int64_t ldc, int tri_out, int kmode, int ozaki) {
+    HostBackend be;
+    be.ozaki = ozaki;
+    GemmDesc g;
+    g.al = al; g.bl = bl; g.mt = mt; g.nt = nt; g.K = K; g.alpha = alpha; g.beta = beta;
+    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc; g.tri_out = tri_out; g.kmode = kmode;
+    be.gemm(g);
+    return (int)be.ozaki_calls;
+}
+
 // M: np x np row-major; on entry the LOWER triangle holds an SPD matrix (upper is poisoned here with NaN);
 // R: mt*128 x np right-hand-side rows (solved in place); on exit M lower = inverse.
 int emul_spd_solve_invert_ex(int64_t np, double *M, int mt, double *R, int invert, double *stats, int ozaki, int ozaki_min_tiles);

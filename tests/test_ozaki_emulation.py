@@ -56,3 +56,27 @@ def test_eight_digits_on_a_bundle_network(emul):
     dev = deviations(emul, S, rhs, (8,))
     assert dev[8][0] <= 1e-10 and dev[0][0] <= 1e-10, dev
     assert dev[8][0] <= 8 * dev[0][0] + 1e-14
+
+
+@pytest.mark.parametrize('digits', [0, 8])
+def test_tile_grid_products_with_poisoned_operands(emul, digits):
+    """The case list tools/ozaki_gpu_check.py will run on the B200 (every operand layout, triangular hint and symmetric
+    output; NaN wherever the kernels must not read; rows of very different magnitude), here through the host backend: the
+    FP64 loops and the int8-digit emulation both meet the 1e-13 bar, so a failure on the GPU is the kernel's, not the checker's."""
+    import ozaki_gpu_check as chk
+    emul.emul_gemm_tiles.argtypes = [ctypes.c_int] * 4 + [ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_int64,
+                                     ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+
+    def gemm(As, Bs, C0, al, bl, alpha, beta, tri, kmode):
+        As, Bs, C = np.ascontiguousarray(As), np.ascontiguousarray(Bs), C0.copy()
+        Mr, K = As.shape if al == 0 else As.shape[::-1]
+        Nr = Bs.shape[0] if bl == 0 else Bs.shape[1]
+        n = emul.emul_gemm_tiles(al, bl, Mr // 128, Nr // 128, K, alpha, beta, As.ctypes.data, As.shape[1], Bs.ctypes.data, Bs.shape[1],
+                                 C.ctypes.data, C.shape[1], int(tri), kmode, digits)
+        assert n == (1 if digits else 0)
+        return C
+
+    cases = chk.run_gemm_cases(gemm)
+    assert len(cases) >= 20
+    bad = [c for c in cases if not c['ok']]
+    assert not bad, bad[:3]

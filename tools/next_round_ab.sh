@@ -2,6 +2,9 @@
 # A/B experiments prepared for the next round; run under gpurun, results into gpurun_out/.
 #   bash tools/next_round_ab.sh tile      1 GPU : band-swizzled tile order of the lower-triangular GEMM launches (JAICOV_TILE_BAND)
 #   bash tools/next_round_ab.sh panel N   N GPUs: panel width of the distributed Cholesky (JAICOV_PANEL_TILES)
+#   bash tools/next_round_ab.sh ozaki     1 GPU : first run of the int8-digit tcgen05 GEMM (csrc/ozaki.cu, never executed so far):
+#                                                 correctness on small tile grids and SPD systems under timeouts, then timings;
+#                                                 only if all of that is green: config 4 / 5 passes with JAICOV_GEMM_OZAKI=8
 mkdir -p gpurun_out
 case "$1" in
 tile)
@@ -19,5 +22,17 @@ panel)
       bench.py --gpus $N --steps 2 --warmup 3 --no-e2e --no-structured > gpurun_out/ab_panel_n${N}_pw$pw.log 2>&1
     echo "N=$N panel_tiles=$pw: $(grep -o '"ms_per_step": [0-9.]*' gpurun_out/ab_panel_n${N}_pw$pw.log) $(grep -o '"stage_ms": {[^}]*}' gpurun_out/ab_panel_n${N}_pw$pw.log)"
   done ;;
-*) echo "usage: $0 tile | panel N" ;;
+ozaki)
+  timeout 1500 python tools/ozaki_gpu_check.py > gpurun_out/ozaki_check.log 2>&1
+  cat gpurun_out/ozaki_check.log
+  if grep -q '"ok": false' gpurun_out/ozaki_check.log; then echo "ozaki: checks not green, skipping the bench runs"; exit 0; fi
+  for cfg in 4 5; do
+    for solver in dense structured; do
+      JAICOV_GEMM_OZAKI=8 JAICOV_SOLVER=$solver timeout 900 python bench.py --config $cfg --steps 2 --warmup 3 --no-e2e --no-cpu-baseline \
+        > gpurun_out/ab_ozaki_c${cfg}_$solver.log 2>&1
+      echo "config $cfg $solver, 8 digits: $(grep -o '"ms_per_step": [0-9.]*' gpurun_out/ab_ozaki_c${cfg}_$solver.log) $(grep -o '"frac": [0-9.]*' gpurun_out/ab_ozaki_c${cfg}_$solver.log)"
+    done
+  done
+  JAICOV_GEMM_OZAKI=8 timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > gpurun_out/ozaki_parity.log 2>&1; tail -3 gpurun_out/ozaki_parity.log ;;
+*) echo "usage: $0 tile | panel N | ozaki" ;;
 esac
