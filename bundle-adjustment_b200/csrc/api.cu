@@ -20,7 +20,7 @@
 
 namespace jaicov {
 
-long long g_launch_count = 0;
+std::atomic<long long> g_launch_count{0};
 
 // dense_kernels.cu
 void launch_gemm(const GemmDesc &g, cudaStream_t s);
@@ -1002,7 +1002,7 @@ int32_t jaicov_device_count(void) { return usable_devices(); }
 
 int64_t jaicov_release_cached_memory(void) { return (int64_t)(g_cache.purge() + ozaki_release_scratch()); }
 
-int64_t jaicov_launch_count(void) { return (int64_t)g_launch_count; }
+int64_t jaicov_launch_count(void) { return (int64_t)g_launch_count.load(); }
 
 int32_t jaicov_create(const jaicov_options *opt, jaicov_handle **out) {
     if (!opt || !out) return JAICOV_ILLEGAL_ARGUMENT;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -17,7 +18,7 @@ constexpr int kMaxDatum = 7;
 constexpr int kRhsRows = 128;      // rows of the right-hand-side buffer (row 0 = n, rows 1..d = datum rows; 8 used by the loop)
 constexpr double kEps = 1.1102230246251565e-16;  // Constant.EPS = 2^-53 (Constant.java:61-75)
 
-extern long long g_launch_count;   // kernels launched by this library (diagnostic, jaicov_launch_count)
+extern std::atomic<long long> g_launch_count;   // kernels launched by this library (diagnostic, jaicov_launch_count); handles may live on several host threads
 
 struct CudaError {
     cudaError_t code;
