@@ -190,6 +190,17 @@ __device__ __forceinline__ void oz_tma_load_3d(const CUtensorMap *map, uint32_t 
         : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// the same copy delivered to every CTA of the cluster named in `mask` (same smem offset, same barrier offset in each)
+__device__ __forceinline__ void oz_tma_load_3d_mc(const CUtensorMap *map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5, %6}], [%2], %3;"
+        :
+        : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "h"(mask), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void oz_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // K-major operand rows of 64 bytes, SWIZZLE_64B: 8-row groups are 512 bytes apart (cute::UMMA::SmemDescriptor, sm_100 version 1)
 __device__ __forceinline__ uint64_t oz_smem_desc(uint32_t saddr) {
     uint64_t d = 0;
@@ -215,6 +226,10 @@ __device__ __forceinline__ void oz_mma_i8(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void oz_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void oz_commit_mc(uint32_t bar, uint16_t mask) {   // arrives on the barrier at this offset in every CTA of `mask`
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
+}
 __device__ __forceinline__ void oz_tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
     // load and wait in ONE statement: the registers are only defined once the wait has retired, and nothing can be scheduled between
     asm volatile(
@@ -225,7 +240,11 @@ __device__ __forceinline__ void oz_tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
         : "memory");
 }
 
-template <int S>
+// CL = 1: every CTA loads its own operands.  CL = 2 (JAICOV_OZAKI_CLUSTER=2): the two 64-column halves of one 128 x 128 tile
+// form a thread-block cluster and share op(A): each CTA fetches 64 of the 128 rows of every digit plane and TMA multicasts
+// them into both CTAs' shared memory, which cuts the L2 -> SM traffic per stage from 96 KB to 64 KB (S = 8).  A stage may
+// then only be refilled once BOTH issuers have released it, so the "empty" barriers count two multicast commits.
+template <int S, int CL>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 k_gemm_oz(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, OzGemmArgs p) {
     using Cfg = OzCfg<S>;
@@ -238,7 +257,7 @@ k_gemm_oz(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // ---- tile decode: the same order as k_gemm, every 128 x 128 tile as two 64-column halves ---------------------------
-    const int l = blockIdx.x >> 1, half = blockIdx.x & 1;
+    const int l = blockIdx.x >> 1, half = blockIdx.x & 1;     // CL = 2: half == rank of the CTA in its cluster
     int it, jt;
     if (p.tri_out) {
         tri_tile_decode(l, p.mt, p.tile_band, it, jt);
@@ -260,7 +279,7 @@ k_gemm_oz(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
         for (int i = 0; i < OZ_STAGES; i++) {
             oz_mbar_init(full0 + 8 * i, 1);
-            oz_mbar_init(empty0 + 8 * i, 1);
+            oz_mbar_init(empty0 + 8 * i, CL);
         }
         oz_mbar_init(accum, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -272,6 +291,7 @@ k_gemm_oz(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL > 1) oz_cluster_sync();                 // the peer's barriers exist before anything is multicast at them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
 
@@ -285,7 +305,14 @@ k_gemm_oz(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 oz_mbar_expect_tx(full0 + 8 * st, (uint32_t)Cfg::STAGE);
                 const uint32_t dst = oz_smem_u32(sm + st * Cfg::STAGE);
                 const int k0 = (int)(kbeg + (int64_t)kb * OZ_BK);
-                oz_tma_load_3d(&mapA, full0 + 8 * st, dst, k0, m0, 0);
+                if (CL == 1) {
+                    oz_tma_load_3d(&mapA, full0 + 8 * st, dst, k0, m0, 0);
+                } else {
+                    // this CTA's 64 rows of every digit plane, to both CTAs (mapA's box is 64 bytes x 64 rows x 1 plane here)
+                    for (int pl = 0; pl < S; pl++)
+                        oz_tma_load_3d_mc(&mapA, full0 + 8 * st, dst + pl * (OZ_BM * OZ_BK) + half * (64 * OZ_BK), k0, m0 + 64 * half, pl,
+                                          (uint16_t)3);
+                }
                 oz_tma_load_3d(&mapB, full0 + 8 * st, dst + Cfg::A_STAGE, k0, n0, 0);
             }
         }
@@ -310,7 +337,8 @@ k_gemm_oz(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                             const uint64_t bd = oz_smem_desc(b_base + j * (OZ_BN * OZ_BK) + kk * 32);
                             oz_mma_i8(tmem + (uint32_t)((i + j) * OZ_BN), ad, bd, idesc, (kb > 0 || kk > 0 || i > 0) ? 1u : 0u);
                         }
-                oz_commit(empty0 + 8 * st);        // frees the stage once these MMAs have read it
+                if (CL == 1) oz_commit(empty0 + 8 * st);        // frees the stage once these MMAs have read it
+                else oz_commit_mc(empty0 + 8 * st, (uint16_t)3);   // ... in both CTAs: the peer writes half of our op(A)
             }
             oz_commit(accum);                      // all groups complete
         }
@@ -352,6 +380,7 @@ k_gemm_oz(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
+    if (CL > 1) oz_cluster_sync();                 // no CTA leaves while its peer may still signal its barriers
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(OZ_TMEM_COLS) : "memory");
@@ -376,13 +405,13 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-// digit planes Q[S][rows][K] (int8, K contiguous) as a 3-D tensor; one box = S planes x box_rows rows x 64 bytes
-bool make_map(CUtensorMap *map, const int8_t *Q, int64_t rows, int64_t K, int S, int box_rows) {
+// digit planes Q[S][rows][K] (int8, K contiguous) as a 3-D tensor; one box = box_planes planes x box_rows rows x 64 bytes
+bool make_map(CUtensorMap *map, const int8_t *Q, int64_t rows, int64_t K, int S, int box_rows, int box_planes) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return false;
     const cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)S};
     const cuuint64_t gstride[2] = {(cuuint64_t)K, (cuuint64_t)rows * (cuuint64_t)K};   // bytes, dimensions 1 and 2
-    const cuuint32_t box[3] = {(cuuint32_t)OZ_BK, (cuuint32_t)box_rows, (cuuint32_t)S};
+    const cuuint32_t box[3] = {(cuuint32_t)OZ_BK, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
     const cuuint32_t estr[3] = {1, 1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t *>(Q), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -426,15 +455,38 @@ struct OzScratch {
 };
 OzScratch g_oz;
 
-template <int S>
+template <int S, int CL>
 void launch_tiles(const CUtensorMap &ma, const CUtensorMap &mb, const OzGemmArgs &a, int64_t tiles, cudaStream_t s) {
     static bool attr = false;
     if (!attr) {
-        JCHECK(cudaFuncSetAttribute(k_gemm_oz<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<S>::SMEM));
+        JCHECK(cudaFuncSetAttribute(k_gemm_oz<S, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<S>::SMEM));
         attr = true;
     }
     g_launch_count++;
-    k_gemm_oz<S><<<(unsigned)(tiles * 2), OZ_THREADS, OzCfg<S>::SMEM, s>>>(ma, mb, a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(tiles * 2));
+    cfg.blockDim = dim3(OZ_THREADS);
+    cfg.dynamicSmemBytes = OzCfg<S>::SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    JCHECK(cudaLaunchKernelEx(&cfg, k_gemm_oz<S, CL>, ma, mb, a));
+}
+
+template <int CL>
+void launch_tiles_digits(int digits, const CUtensorMap &ma, const CUtensorMap &mb, const OzGemmArgs &a, int64_t tiles, cudaStream_t s) {
+    switch (digits) {
+        case 4: launch_tiles<4, CL>(ma, mb, a, tiles, s); break;
+        case 5: launch_tiles<5, CL>(ma, mb, a, tiles, s); break;
+        case 6: launch_tiles<6, CL>(ma, mb, a, tiles, s); break;
+        case 7: launch_tiles<7, CL>(ma, mb, a, tiles, s); break;
+        default: launch_tiles<8, CL>(ma, mb, a, tiles, s); break;
+    }
 }
 
 }  // namespace
@@ -459,7 +511,10 @@ bool launch_gemm_ozaki(const GemmDesc &g, cudaStream_t s) {
     if (!shared && !g_oz.ensure(1, (size_t)digits * Nr * g.K, (size_t)Nr)) return false;
     CUtensorMap ma, mb;
     const int wb = shared ? 0 : 1;
-    if (!make_map(&ma, g_oz.q[0], Mr, g.K, digits, OZ_BM) || !make_map(&mb, g_oz.q[wb], Nr, g.K, digits, OZ_BN)) return false;
+    static const int cluster = [] { const char *e = getenv("JAICOV_OZAKI_CLUSTER"); return (e && atoi(e) == 2) ? 2 : 1; }();
+    const bool mapped = cluster == 2 ? make_map(&ma, g_oz.q[0], Mr, g.K, digits, 64, 1)            // half of op(A)'s rows, one plane per copy
+                                     : make_map(&ma, g_oz.q[0], Mr, g.K, digits, OZ_BM, digits);
+    if (!mapped || !make_map(&mb, g_oz.q[wb], Nr, g.K, digits, OZ_BN, digits)) return false;
     OzSplitArgs sa{g.A, g.lda, g.al, Mr, g.K, ra, digits, g_oz.q[0], g_oz.e[0], g_oz.amax[0]};
     launch_split(sa, s);
     if (!shared) {
@@ -467,13 +522,8 @@ bool launch_gemm_ozaki(const GemmDesc &g, cudaStream_t s) {
         launch_split(sb, s);
     }
     OzGemmArgs a{g_oz.e[0], g_oz.e[wb], g.C, g.ldc, g.K, g.alpha, g.beta, g.mt, g.nt, g.tri_out, g.tile_band, g.kmode};
-    switch (digits) {
-        case 4: launch_tiles<4>(ma, mb, a, tiles, s); break;
-        case 5: launch_tiles<5>(ma, mb, a, tiles, s); break;
-        case 6: launch_tiles<6>(ma, mb, a, tiles, s); break;
-        case 7: launch_tiles<7>(ma, mb, a, tiles, s); break;
-        default: launch_tiles<8>(ma, mb, a, tiles, s); break;
-    }
+    if (cluster == 2) launch_tiles_digits<2>(digits, ma, mb, a, tiles, s);
+    else launch_tiles_digits<1>(digits, ma, mb, a, tiles, s);
     return true;
 }
 

@@ -127,7 +127,7 @@ def worker_time():
 
 def run_worker(stage, env_extra, timeout):
     env = dict(os.environ)
-    for k in ('JAICOV_GEMM_OZAKI', 'JAICOV_OZAKI_MIN_TILES'):
+    for k in ('JAICOV_GEMM_OZAKI', 'JAICOV_OZAKI_MIN_TILES', 'JAICOV_OZAKI_CLUSTER'):
         env.pop(k, None)
     env.update(env_extra)
     t0 = time.time()
@@ -156,6 +156,7 @@ def main():
         if not run_worker('gemm', oz, 120):
             print('digit path failed on small tile grids: stop here')
             return
+        run_worker('gemm', dict(oz, JAICOV_OZAKI_CLUSTER='2'), 120)   # cluster of two CTAs sharing op(A) by TMA multicast
     if 'spd' in stages:
         run_worker('spd', {}, 300)
         if not run_worker('spd', oz, 300):
@@ -164,6 +165,7 @@ def main():
         run_worker('time', {}, 600)
         for s in ('6', '7', '8'):
             run_worker('time', {'JAICOV_GEMM_OZAKI': s}, 600)
+        run_worker('time', {'JAICOV_GEMM_OZAKI': '8', 'JAICOV_OZAKI_CLUSTER': '2'}, 600)
 
 
 if __name__ == '__main__':
