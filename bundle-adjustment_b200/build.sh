@@ -15,4 +15,6 @@ for f in prep_kernels assembly dense_kernels ozaki stage_kernels structured prop
 done
 for p in "${pids[@]}"; do wait "$p"; done   # set -e: the first failed compile stops the build
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libjaicov_b200.so _obj/prep_kernels.o _obj/assembly.o _obj/dense_kernels.o _obj/ozaki.o _obj/stage_kernels.o _obj/structured.o _obj/propagate.o _obj/dlt.o _obj/dist.o _obj/api.o -ldl -lcudart
-echo built $(pwd)/libjaicov_b200.so
+# native host mirror of the reference's Java API (header-only jaicov_host.hpp) behind flat C entry points
+g++ -std=c++17 -O2 -Wall -Wextra -fPIC -shared -o libjaicov_host.so host/host_capi.cpp -L. -ljaicov_b200 -Wl,-rpath,'$ORIGIN'
+echo built $(pwd)/libjaicov_b200.so $(pwd)/libjaicov_host.so

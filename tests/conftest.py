@@ -17,7 +17,8 @@ def built():
     """Everything native is built once per session (nvcc cross-compiles without a GPU)."""
     import __graft_entry__ as g
     lib = os.path.join(ROOT, 'bundle-adjustment_b200', 'libjaicov_b200.so')
-    if not os.path.exists(lib) or not os.path.exists(os.path.join(ROOT, 'tests', '_build', 'libemul.so')):
+    if not os.path.exists(lib) or not os.path.exists(os.path.join(ROOT, 'tests', '_build', 'libemul.so')) \
+            or not os.path.exists(os.path.join(ROOT, 'bundle-adjustment_b200', 'libjaicov_host.so')):
         g.build()
     from oracle import oracle
     oracle.build_lib()
