@@ -80,3 +80,14 @@ def test_tile_grid_products_with_poisoned_operands(emul, digits):
     assert len(cases) >= 20
     bad = [c for c in cases if not c['ok']]
     assert not bad, bad[:3]
+
+
+def test_structured_route_products_from_digit_products(emul):
+    """The two big products of the structured route (Q'Y' and Y (Q'Y')) from 8 int8 digits: the point block of the
+    cofactor matrix of a free network stays well inside the 1e-8 parity bar (the operands of these products -- rows of the
+    inverse of the bordered reduced system -- span many orders of magnitude, so the digit path is measurably coarser than FP64
+    here, unlike in the dense schedule; recorded, not hidden)."""
+    from tests.scenes import synthetic_scene
+    dev, up, m = oz.structured_study(emul, synthetic_scene(2, images=8, targets=60)[0], (8,))
+    assert up == 180 and m == 65
+    assert dev[0] <= 1e-11 and dev[8] <= 1e-10, dev

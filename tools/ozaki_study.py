@@ -72,6 +72,50 @@ def run(L, S, rhs, digits, min_tiles=1):
     return info, Q, R[0, :u].copy(), st, dt
 
 
+def structured_study(L, scene, digits):
+    """The two big products of the structured route, T = Q'Y' and K^-1[p, p] = P^-1 + Y T, from int8 digit products:
+    the bordered preconditioned system K = [[P, Z], [Z', Rb]] (object coordinates first, P block diagonal) is assembled by the
+    oracle, the small reduced system is inverted in FP64, and the point block of the inverse is compared with a long-double
+    reference -- FP64 products vs emulated digit products."""
+    from oracle.oracle import Oracle, _unpack_upper
+    o = Oracle(scene)
+    if o.use_centroid:
+        o._centroid(False)
+    N, nv, V = o.create_normal_equation()
+    n, d = o.fp.n, o.fp.d
+    Kb = _unpack_upper(N, n) * V[:, None] * V[None, :]                 # bordered, Jacobi-scaled (V = 1 on the border)
+    pc = np.asarray(o.fp.pt_col).reshape(-1)
+    pcols = np.sort(pc[(pc >= 0) & (pc < 2147483647)])
+    up = pcols.size
+    assert np.array_equal(pcols, np.arange(d, d + up)), 'object coordinates are the leading unknown columns'
+    rest = np.concatenate([np.arange(d + up, n), np.arange(0, d)])     # cameras / images, then the datum multipliers
+    P, Z, Rb = Kb[np.ix_(pcols, pcols)], Kb[np.ix_(pcols, rest)], Kb[np.ix_(rest, rest)]
+    Pinv = np.linalg.inv(P)                                            # block diagonal 3 x 3 (inverted block-wise on the device)
+    Y = Pinv @ Z
+    Qp = np.linalg.inv(Rb - Z.T @ Y)                                   # Q' = K'^-1, m x m, small
+    Kl = Kb.astype(np.longdouble)
+    X = np.linalg.inv(Kb).astype(np.longdouble)
+    for _ in range(2):
+        X = X + X @ (np.eye(n, dtype=np.longdouble) - Kl @ X)
+    ref = X[np.ix_(pcols, pcols)]
+    sc = np.sqrt(np.abs(np.diag(ref))).astype(np.float64)
+    L.emul_gemm_tiles.argtypes = [ctypes.c_int] * 4 + [ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_int64,
+                                  ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    pad = lambda a, r, c: np.pad(a, ((0, r - a.shape[0]), (0, c - a.shape[1])))
+    Tp, mp = (up + 127) // 128 * 128, (rest.size + 127) // 128 * 128
+    Yt = np.ascontiguousarray(pad(Y.T, mp, Tp))                        # stored transposed like the device buffers
+    Qpp = np.ascontiguousarray(pad(Qp, mp, mp))
+    out = {}
+    for s in [0] + list(digits):
+        T1 = np.zeros((mp, Tp))                                        # T = Q' Y'   (A = Q'[m][k], B = Yt[k][n])
+        L.emul_gemm_tiles(0, 1, mp // 128, Tp // 128, mp, 1.0, 0.0, Qpp.ctypes.data, mp, Yt.ctypes.data, Tp, T1.ctypes.data, Tp, 0, 0, s)
+        C = np.zeros((Tp, Tp))                                         # Y T       (A = Yt[k][m], B = T1[k][n]), lower tiles
+        L.emul_gemm_tiles(1, 1, Tp // 128, Tp // 128, mp, 1.0, 0.0, Yt.ctypes.data, Tp, T1.ctypes.data, Tp, C.ctypes.data, Tp, 1, 0, s)
+        Q = np.tril(C[:up, :up]) + np.tril(C[:up, :up], -1).T + Pinv
+        out[s] = float(np.max(np.abs(Q.astype(np.longdouble) - ref) / np.outer(sc, sc)))
+    return out, up, rest.size
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--config', type=int, default=2)
@@ -79,9 +123,16 @@ def main():
     ap.add_argument('--targets', type=int, default=150)
     ap.add_argument('--digits', type=int, nargs='*', default=[6, 7, 8])
     ap.add_argument('--min-tiles', type=int, default=1)
+    ap.add_argument('--structured', action='store_true', help='the structured route\'s two big products instead of the dense schedule')
     args = ap.parse_args()
     from tests.scenes import synthetic_scene
     scene, _ = synthetic_scene(args.config, images=args.images, targets=args.targets)
+    if args.structured:
+        dev, up, m = structured_study(load_emul(), scene, args.digits)
+        print('config %d, %d images x %d targets: %d object-coordinate columns, reduced system %d' % (args.config, args.images, args.targets, up, m))
+        for s, e in dev.items():
+            print('%-22s point block of Qxx, deviation (correlation-scaled) %.2e' % ('FP64 products' if s == 0 else 'int8 slices, s = %d' % s, e))
+        return
     S, rhs = scaled_system(scene)
     u = S.shape[0]
     cond = np.linalg.cond(S)
