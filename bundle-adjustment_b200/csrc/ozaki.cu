@@ -47,6 +47,9 @@ struct OzSplitArgs {
     int8_t *Q;           // [S][rows][K]
     int32_t *e;          // [rows]: |x| < 2^e over the row's valid range (0 for an all-zero row)
     unsigned long long *amax;   // [rows]: bit pattern of max |x| (non-negative doubles order like unsigned integers)
+    const int32_t *fk;   // [K] or null: contraction-index balancing, the operand is read as x * 2^(fsign * fk[k]) (see k_oz_fk)
+    int fsign;
+    unsigned long long *cmax;   // [K]: bit pattern of the column maxima (k_oz_colmax)
 };
 
 __device__ __forceinline__ bool oz_valid(const OzSplitArgs &a, int64_t row, int64_t k) {
@@ -82,6 +85,52 @@ __device__ __forceinline__ void oz_load16(const OzSplitArgs &a, int64_t row, int
 #pragma unroll
     for (int i = 0; i < 16; i++)
         if (!oz_valid(a, row, k0 + i)) x[i] = 0.0;
+    if (a.fk) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) x[i] *= __longlong_as_double((long long)(1023 + a.fsign * a.fk[k0 + i]) << 52);   // exact, |f| <= 1023
+    }
+}
+
+// Contraction-index balancing (tests/emul/host_backend.cpp: gemm_ozaki; tools/ozaki_study.py --structured): column maxima of both
+// operands, then f_k = floor((exponent of max |B[., k]| - exponent of max |A[., k]|) / 2).  op(A)[., k] * 2^f_k and op(B)[., k] * 2^-f_k
+// leave every product unchanged but even out the magnitudes inside the operand rows, which the per-row digit grid resolves.
+__global__ void __launch_bounds__(128) k_oz_colmax(OzSplitArgs a) {
+    double m = 0.0;
+    int64_t k;
+    if (a.layout == 0) {          // thread <-> one k, a slab of 256 rows (every row access is one coalesced 1 KB read of the block)
+        k = (int64_t)blockIdx.x * 128 + threadIdx.x;
+        const int64_t r0 = (int64_t)blockIdx.y * 256, r1 = min(a.rows, r0 + 256);
+        if (k < a.K)
+            for (int64_t r = r0; r < r1; r++)
+                if (oz_valid(a, r, k)) m = fmax(m, fabs(a.X[r * a.ld + k]));
+        if (k < a.K && m > 0.0) atomicMax(a.cmax + k, (unsigned long long)__double_as_longlong(m));
+    } else {                      // warp <-> one k, lanes stride over a slab of 4096 rows (contiguous in memory)
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        k = (int64_t)blockIdx.x * 4 + warp;
+        const int64_t r0 = (int64_t)blockIdx.y * 4096, r1 = min(a.rows, r0 + 4096);
+        if (k < a.K)
+            for (int64_t r = r0 + lane; r < r1; r += 32)
+                if (oz_valid(a, r, k)) m = fmax(m, fabs(a.X[k * a.ld + r]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0 && k < a.K && m > 0.0) atomicMax(a.cmax + k, (unsigned long long)__double_as_longlong(m));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_oz_fk(const unsigned long long *ca, const unsigned long long *cb, int64_t K, int32_t *fk) {
+    const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (k >= K) return;
+    const int ea = (int)((ca[k] >> 52) & 0x7ff), eb = (int)((cb[k] >> 52) & 0x7ff);
+    const int f = (ea == 0 || eb == 0 || ea == 2047 || eb == 2047) ? 0 : ((eb - ea) >> 1);   // zero / subnormal / non-finite column: leave it alone
+    fk[k] = max(-1000, min(1000, f));                                                      // 2^(+-f) stays a normal number
+}
+
+static void launch_colmax(const OzSplitArgs &a, cudaStream_t s) {
+    JCHECK(cudaMemsetAsync(a.cmax, 0, (size_t)a.K * sizeof(unsigned long long), s));
+    const dim3 grid = a.layout == 0 ? dim3((unsigned)((a.K + 127) / 128), (unsigned)((a.rows + 255) / 256))
+                                    : dim3((unsigned)((a.K + 3) / 4), (unsigned)((a.rows + 4095) / 4096));
+    g_launch_count++;
+    k_oz_colmax<<<grid, 128, 0, s>>>(a);
 }
 
 __global__ void __launch_bounds__(128) k_oz_rowmax(OzSplitArgs a) {
@@ -423,6 +472,22 @@ struct OzScratch {
     int32_t *e[2] = {nullptr, nullptr};
     unsigned long long *amax[2] = {nullptr, nullptr};
     size_t rows_cap[2] = {0, 0};
+    unsigned long long *cmax[2] = {nullptr, nullptr};
+    int32_t *fk = nullptr;
+    size_t k_cap = 0;
+    bool ensure_k(size_t K) {
+        if (K <= k_cap) return true;
+        for (int w = 0; w < 2; w++) { if (cmax[w]) cudaFree(cmax[w]); cmax[w] = nullptr; }
+        if (fk) cudaFree(fk);
+        fk = nullptr; k_cap = 0;
+        if (cudaMalloc(&cmax[0], K * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&cmax[1], K * sizeof(unsigned long long)) != cudaSuccess ||
+            cudaMalloc(&fk, K * sizeof(int32_t)) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        k_cap = K;
+        return true;
+    }
     bool ensure(int w, size_t bytes, size_t rows) {
         if (bytes > cap[w]) {
             if (q[w]) cudaFree(q[w]);
@@ -449,7 +514,11 @@ struct OzScratch {
             if (e[w]) cudaFree(e[w]);
             if (amax[w]) cudaFree(amax[w]);
             q[w] = nullptr; e[w] = nullptr; amax[w] = nullptr; cap[w] = rows_cap[w] = 0;
+            if (cmax[w]) cudaFree(cmax[w]);
+            cmax[w] = nullptr;
         }
+        if (fk) cudaFree(fk);
+        fk = nullptr; k_cap = 0;
         return b;
     }
 };
@@ -515,12 +584,21 @@ bool launch_gemm_ozaki(const GemmDesc &g, cudaStream_t s) {
     const bool mapped = cluster == 2 ? make_map(&ma, g_oz.q[0], Mr, g.K, digits, 64, 1)            // half of op(A)'s rows, one plane per copy
                                      : make_map(&ma, g_oz.q[0], Mr, g.K, digits, OZ_BM, digits);
     if (!mapped || !make_map(&mb, g_oz.q[wb], Nr, g.K, digits, OZ_BN, digits)) return false;
-    OzSplitArgs sa{g.A, g.lda, g.al, Mr, g.K, ra, digits, g_oz.q[0], g_oz.e[0], g_oz.amax[0]};
-    launch_split(sa, s);
-    if (!shared) {
-        OzSplitArgs sb{g.B, g.ldb, g.bl, Nr, g.K, rb, digits, g_oz.q[1], g_oz.e[1], g_oz.amax[1]};
-        launch_split(sb, s);
+    // contraction-index balancing is on unless JAICOV_OZAKI_KSCALE=0; it has nothing to do when both operands are one array
+    static const bool kscale = [] { const char *e = getenv("JAICOV_OZAKI_KSCALE"); return !(e && atoi(e) == 0); }();
+    const bool balance = kscale && !shared;
+    if (balance && !g_oz.ensure_k((size_t)g.K)) return false;
+    OzSplitArgs sa{g.A, g.lda, g.al, Mr, g.K, ra, digits, g_oz.q[0], g_oz.e[0], g_oz.amax[0], nullptr, 1, g_oz.cmax[0]};
+    OzSplitArgs sb{g.B, g.ldb, g.bl, Nr, g.K, rb, digits, g_oz.q[1], g_oz.e[1], g_oz.amax[1], nullptr, -1, g_oz.cmax[1]};
+    if (balance) {
+        launch_colmax(sa, s);
+        launch_colmax(sb, s);
+        g_launch_count++;
+        k_oz_fk<<<(unsigned)((g.K + 255) / 256), 256, 0, s>>>(g_oz.cmax[0], g_oz.cmax[1], g.K, g_oz.fk);
+        sa.fk = sb.fk = g_oz.fk;
     }
+    launch_split(sa, s);
+    if (!shared) launch_split(sb, s);
     OzGemmArgs a{g_oz.e[0], g_oz.e[wb], g.C, g.ldc, g.K, g.alpha, g.beta, g.mt, g.nt, g.tri_out, g.tile_band, g.kmode};
     if (cluster == 2) launch_tiles_digits<2>(digits, ma, mb, a, tiles, s);
     else launch_tiles_digits<1>(digits, ma, mb, a, tiles, s);

@@ -57,6 +57,7 @@ struct HostBackend {
     double flops = 0;
     int ozaki = 0;              // > 0: number of int8 digits per operand; every eligible launch goes through gemm_ozaki
     int ozaki_min_tiles = 1;    // launches with fewer output tiles stay on the FP64 path (as the product would do)
+    int ozaki_kscale = 1;       // balance the two operands along the contraction index by exact powers of two first (see gemm_ozaki)
     long ozaki_calls = 0;
     long long ozaki_max_abs_sum = 0;   // largest |integer group sum| seen (must stay below 2^31)
 
@@ -64,14 +65,30 @@ struct HostBackend {
         const int T = kTile, s = ozaki;
         const int64_t Mr = (int64_t)g.mt * T, Nr = (int64_t)g.nt * T, K = g.K;
         OzakiOperand A, B;
-        ozaki_split(A, Mr, K, s,
-                    [&](int64_t m, int64_t k) { return g.al == 0 ? g.A[m * g.lda + k] : g.A[k * g.lda + m]; },
-                    [&](int64_t m) { return g.kmode == K_MAX_IJ ? (m / T) * T : (int64_t)0; },
-                    [&](int64_t m) { return g.kmode == K_A_LOWER ? std::min<int64_t>(K, (m / T + 1) * T) : K; });
-        ozaki_split(B, Nr, K, s,
-                    [&](int64_t n, int64_t k) { return g.bl == 0 ? g.B[n * g.ldb + k] : g.B[k * g.ldb + n]; },
-                    [&](int64_t n) { return (g.kmode == K_MAX_IJ || g.kmode == K_B_LOWER) ? (n / T) * T : (int64_t)0; },
-                    [&](int64_t) { return K; });
+        auto getA = [&](int64_t m, int64_t k) { return g.al == 0 ? g.A[m * g.lda + k] : g.A[k * g.lda + m]; };
+        auto getB = [&](int64_t n, int64_t k) { return g.bl == 0 ? g.B[n * g.ldb + k] : g.B[k * g.ldb + n]; };
+        auto loA = [&](int64_t m) { return g.kmode == K_MAX_IJ ? (m / T) * T : (int64_t)0; };
+        auto hiA = [&](int64_t m) { return g.kmode == K_A_LOWER ? std::min<int64_t>(K, (m / T + 1) * T) : K; };
+        auto loB = [&](int64_t n) { return (g.kmode == K_MAX_IJ || g.kmode == K_B_LOWER) ? (n / T) * T : (int64_t)0; };
+        auto hiB = [&](int64_t) { return K; };
+        // Contraction-index balancing: op(A)[., k] * 2^f_k and op(B)[., k] * 2^-f_k leave every product unchanged (exact powers of
+        // two) but even out the magnitudes inside the operand rows, which is what the per-row digit grid resolves.  f_k = floor of
+        // half the exponent gap of the two column maxima.  Needed where the operands span many orders of magnitude inside a row
+        // (the structured route's Q'Y' and Y (Q'Y'), tools/ozaki_study.py --structured); nothing to do when A and B are the same array.
+        std::vector<int> fk(K, 0);
+        const bool same = (const void *)g.A == (const void *)g.B && g.lda == g.ldb && g.al == g.bl && g.kmode != K_A_LOWER && g.kmode != K_B_LOWER && Mr == Nr;
+        if (ozaki_kscale && !same) {
+            std::vector<double> ca(K, 0.0), cb(K, 0.0);
+            for (int64_t m = 0; m < Mr; m++)
+                for (int64_t k = loA(m); k < hiA(m); k++) ca[k] = std::max(ca[k], std::fabs(getA(m, k)));
+            for (int64_t n = 0; n < Nr; n++)
+                for (int64_t k = loB(n); k < hiB(n); k++) cb[k] = std::max(cb[k], std::fabs(getB(n, k)));
+            for (int64_t k = 0; k < K; k++)
+                if (ca[k] >= 2.3e-308 && cb[k] >= 2.3e-308 && std::isfinite(ca[k]) && std::isfinite(cb[k]))
+                    fk[k] = std::max(-1000, std::min(1000, (std::ilogb(cb[k]) - std::ilogb(ca[k])) >> 1));   // arithmetic shift: floor((eb - ea) / 2)
+        }
+        ozaki_split(A, Mr, K, s, [&](int64_t m, int64_t k) { return std::ldexp(getA(m, k), fk[k]); }, loA, hiA);
+        ozaki_split(B, Nr, K, s, [&](int64_t n, int64_t k) { return std::ldexp(getB(n, k), -fk[k]); }, loB, hiB);
         std::vector<long long> S(2 * s + 1);
         for (int it = 0; it < g.mt; it++)
             for (int jt = 0; jt < g.nt; jt++) {
@@ -282,7 +299,8 @@ int emul_distributed(int64_t np, double *M, int nranks, int pw, double *Q, doubl
 int emul_gemm_tiles(int al, int bl, int mt, int nt, int64_t K, double alpha, double beta, const double *A, int64_t lda, const double *B,
                     int64_t ldb, double *C, int64_t ldc, int tri_out, int kmode, int ozaki) {
     HostBackend be;
-    be.ozaki = ozaki;
+    be.ozaki = ozaki < 0 ? -ozaki : ozaki;        // negative: without the contraction-index balancing
+    be.ozaki_kscale = ozaki < 0 ? 0 : 1;
     GemmDesc g;
     g.al = al; g.bl = bl; g.mt = mt; g.nt = nt; g.K = K; g.alpha = alpha; g.beta = beta;
     g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc; g.tri_out = tri_out; g.kmode = kmode;
@@ -306,7 +324,8 @@ int emul_spd_solve_invert_ex(int64_t np, double *M, int mt, double *R, int inver
             if ((r / kTile) != (c / kTile)) M[r * np + c] = nan;   // strictly-upper off-diagonal tiles are never read
     std::vector<double> Dinv((size_t)np * kTile, nan), W;
     HostBackend be;
-    be.ozaki = ozaki;
+    be.ozaki = ozaki < 0 ? -ozaki : ozaki;        // a negative digit count switches the contraction-index balancing off (studies)
+    be.ozaki_kscale = ozaki < 0 ? 0 : 1;
     be.ozaki_min_tiles = ozaki_min_tiles;
     DenseSchedule<HostBackend> ds{be, M, np, np, Dinv.data()};
     ds.potrf();
@@ -317,7 +336,7 @@ int emul_spd_solve_invert_ex(int64_t np, double *M, int mt, double *R, int inver
     }
     if (stats) {
         stats[0] = (double)be.gemm_calls; stats[1] = (double)be.diag_calls; stats[2] = be.flops;
-        if (ozaki > 0) { stats[3] = (double)be.ozaki_calls; stats[4] = (double)be.ozaki_max_abs_sum; }
+        if (ozaki != 0) { stats[3] = (double)be.ozaki_calls; stats[4] = (double)be.ozaki_max_abs_sum; }
     }
     return be.info;
 }

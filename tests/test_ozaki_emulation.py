@@ -83,11 +83,12 @@ def test_tile_grid_products_with_poisoned_operands(emul, digits):
 
 
 def test_structured_route_products_from_digit_products(emul):
-    """The two big products of the structured route (Q'Y' and Y (Q'Y')) from 8 int8 digits: the point block of the
-    cofactor matrix of a free network stays well inside the 1e-8 parity bar (the operands of these products -- rows of the
-    inverse of the bordered reduced system -- span many orders of magnitude, so the digit path is measurably coarser than FP64
-    here, unlike in the dense schedule; recorded, not hidden)."""
+    """The two big products of the structured route (Q'Y' and Y (Q'Y')) from 8 int8 digits.  Their operands -- rows
+    of the inverse of the bordered reduced system -- span many orders of magnitude inside one row, which a per-row digit grid
+    alone resolves ~10x worse than FP64 (digits = -8: balancing off); with the contraction index balanced by exact powers of two
+    first (the default, also in csrc/ozaki.cu) the point block of the cofactor matrix is as accurate as with FP64 products."""
     from tests.scenes import synthetic_scene
-    dev, up, m = oz.structured_study(emul, synthetic_scene(2, images=8, targets=60)[0], (8,))
+    dev, up, m = oz.structured_study(emul, synthetic_scene(2, images=8, targets=60)[0], (8, -8))
     assert up == 180 and m == 65
-    assert dev[0] <= 1e-11 and dev[8] <= 1e-10, dev
+    assert dev[0] <= 2e-12 and dev[8] <= 2 * dev[0] + 1e-15, dev
+    assert 3 * dev[8] < dev[-8] <= 1e-10, dev          # without the balancing: visibly coarser, still inside the 1e-8 bar
