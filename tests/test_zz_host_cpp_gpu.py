@@ -57,3 +57,18 @@ def test_cpp_host_estimate_matches_python_mirror_and_oracle(H, name):
     s2o = orc.variance_factor_aposteriori()
     assert abs(stats[1] - s2o) <= 1e-8 * s2o
     net.close()
+
+
+def test_tile_product_stage_entry_point(built):
+    """jaicov_gemm_tiles (the FP64 tensor-core tile kernel behind factor / inverse, csrc/dense_kernels.cu: k_gemm) on small tile
+    grids: every operand layout, triangular-operand hint and symmetric output, alpha / beta, against numpy -- with NaN wherever
+    the kernel must not read.  The same case list passes on the CPU against the host emulation (tests/test_ozaki_emulation.py)."""
+    import os
+    import sys
+    import bundle_adjustment_b200 as ba
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools'))
+    import ozaki_gpu_check as chk
+    cases = chk.run_gemm_cases(lambda As, Bs, C0, al, bl, alpha, beta, tri, kmode: ba._lib.gemm_tiles(As, Bs, C0, al, bl, alpha, beta, tri, kmode)[0])
+    assert len(cases) >= 20
+    bad = [c for c in cases if not c['ok']]
+    assert not bad, bad[:3]
