@@ -397,6 +397,9 @@ def main():
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': name, 'solver': 'structured (point-block)' if structured_used else 'dense (blocked Cholesky + full inverse)',
+                       'gemm': ('FP64 DMMA tiles (mma.sync m8n8k4)' if not os.environ.get('JAICOV_GEMM_OZAKI') else
+                                'EXPERIMENT JAICOV_GEMM_OZAKI=%s: big products from int8 digit products on tcgen05 (FP64-equivalent); '
+                                'roofline.peak stays the FP64 tensor pipe, so frac can exceed 1' % os.environ['JAICOV_GEMM_OZAKI']),
                        'l2': 'inputs larger than L2: the %d x %d FP64 system (%.2f GB) is rewritten every step'
                        % (n, n, n * n * 8 / 1e9),
                        'parallelism': 'single GPU' if world == 1 else ('one adjustment over %d GPUs: image-sharded assembly + NCCL all-reduce, block-column-cyclic '
