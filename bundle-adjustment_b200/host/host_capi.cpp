@@ -4,6 +4,7 @@
 // the integer bookkeeping / the adjustment results come back as arrays.  Built into libjaicov_host.so next to
 // libjaicov_b200.so (bundle-adjustment_b200/build.sh); nothing here computes on the CPU.
 #include <cstring>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -268,6 +269,60 @@ int jhost_get_results(void *n, double *stats, double *qxx, int *has_qxx) {
     const UpperSymmPackMatrix *Q = a.getCofactorMatrix();
     if (has_qxx) *has_qxx = Q ? 1 : 0;
     if (Q && qxx) std::memcpy(qxx, Q->getData().data(), Q->getData().size() * sizeof(double));
+    JH_END
+}
+
+// ---- callers either side of the path -----------------------------------------------------------------------------------------
+// DirectLinearTransformation over ALL images of the network with the object points known_idx[n_known] as homologous points.
+// run == 0: only the gathering of DirectLinearTransformation.java:78-94 (pt_ptr[n_img + 1], xy, xyz, io as handed to jaicov_dlt_batch;
+// xy / xyz sized for every observation); run != 0: adjustAll() on the device, out20[20 n_img] = coefficient values in the reference's
+// insertion order, ok[n_img].
+int jhost_dlt(void *n, int n_known, const int32_t *known_idx, int n_restr, const int32_t *restr, int run, int64_t *pt_ptr, double *xy, double *xyz,
+              double *io, double *out20, uint8_t *ok) {
+    JH_BEGIN
+    std::map<std::string, ObjectCoordinate *> known;
+    for (int i = 0; i < n_known; i++) known[N.points.at(known_idx[i])->getName()] = N.points.at(known_idx[i]).get();
+    std::vector<std::unique_ptr<DLTCoefficients>> own;
+    std::vector<DLTCoefficients *> coefs;
+    for (Image *img : N.images) { own.emplace_back(new DLTCoefficients(img)); coefs.push_back(own.back().get()); }
+    if (!run) {
+        DirectLinearTransformation::Gathered g = DirectLinearTransformation::gather(coefs, known);
+        std::memcpy(pt_ptr, g.pt_ptr.data(), g.pt_ptr.size() * sizeof(int64_t));
+        if (!g.xy.empty()) std::memcpy(xy, g.xy.data(), g.xy.size() * sizeof(double));
+        if (!g.xyz.empty()) std::memcpy(xyz, g.xyz.data(), g.xyz.size() * sizeof(double));
+        if (!g.io.empty()) std::memcpy(io, g.io.data(), g.io.size() * sizeof(double));
+    } else {
+        std::vector<DirectLinearTransformation::RestrictionType> r;
+        for (int i = 0; i < n_restr; i++) r.push_back((DirectLinearTransformation::RestrictionType)restr[i]);
+        std::vector<bool> res = DirectLinearTransformation::adjustAll(coefs, known, r, 0);
+        for (size_t i = 0; i < coefs.size(); i++) {
+            ok[i] = res[i] ? 1 : 0;
+            for (int k = 0; k < 20; k++) out20[20 * i + k] = coefs[i]->getValue(k);
+        }
+    }
+    JH_END
+}
+
+// CoordinateTransformationExteriorOrientation.transform after estimateModel(): the object points pts[n_pts] seen in the images
+// imgs[n_imgs] (camera -> image order) are carried into the frame of image `reference`.  *n_out = number of triples; xyz (3 per triple)
+// and cov_packed (may be NULL) are filled when cap >= *n_out.
+int jhost_transform(void *n, int n_pts, const int32_t *pts, int reference, int n_imgs, const int32_t *imgs, double sigma2, int cap, int *n_out,
+                    double *xyz, double *cov_packed) {
+    JH_BEGIN
+    std::vector<ObjectCoordinate *> oc;
+    for (int i = 0; i < n_pts; i++) oc.push_back(N.points.at(pts[i]).get());
+    std::vector<Image *> list;
+    for (int i = 0; i < n_imgs; i++) list.push_back(N.images.at(imgs[i]));
+    CoordinateTransformationExteriorOrientation t;
+    t.transform(oc, {{N.images.at(reference), list}}, sigma2, N.adjustment);
+    const int r = (int)t.getTransformedCoordinates().size();
+    *n_out = r;
+    if (cap >= r) {
+        for (int k = 0; k < r; k++) {
+            xyz[3 * k] = t.getTransformedCoordinates()[k].x; xyz[3 * k + 1] = t.getTransformedCoordinates()[k].y; xyz[3 * k + 2] = t.getTransformedCoordinates()[k].z;
+        }
+        if (cov_packed && r) std::memcpy(cov_packed, t.getCovarianceMatrix()->getData().data(), t.getCovarianceMatrix()->getData().size() * sizeof(double));
+    }
     JH_END
 }
 

@@ -684,6 +684,10 @@ public:
         flatPoints_ = points;
         flatCamParams_ = camParams;
         flatImages_ = images;
+        flatPointPos_.clear();
+        flatImagePos_.clear();
+        for (size_t p = 0; p < points.size(); p++) flatPointPos_[points[p]] = (int)p;
+        for (size_t i = 0; i < images.size(); i++) flatImagePos_[images[i]] = (int)i;
         return f;
     }
 
@@ -703,6 +707,7 @@ public:
         o.solver = solver_;
         o.sigma2apriori = sigma2apriori_;
         o.damping_value = damping_;
+        release();                                     // the previous adjustment's device state, if any
         jaicov_handle *h = nullptr;
         int rc = jaicov_create(&o, &h);
         if (rc != JAICOV_OK) { lastError_ = "jaicov_create failed"; return EstimationStateType::NOT_INITIALISED; }
@@ -755,8 +760,28 @@ public:
             std::vector<double> q((size_t)(n * (n + 1) / 2), 0.0);   // REDUCED modes fill the leading block only
             if (jaicov_get_qxx_packed(h, q.data()) == JAICOV_OK) Qxx_.reset(new UpperSymmPackMatrix((int)n, std::move(q)));
         }
-        jaicov_destroy(h);
+        handle_ = h;                                   // Qxx stays on the device for the consumers next to the path (transform)
         return (EstimationStateType)id;
+    }
+
+    ~BundleAdjustment() { release(); }
+    BundleAdjustment() = default;
+    BundleAdjustment(const BundleAdjustment &) = delete;
+    BundleAdjustment &operator=(const BundleAdjustment &) = delete;
+    // frees the device state of the last estimateModel() (the host copy handed out by getCofactorMatrix() stays valid)
+    void release() {
+        if (handle_) jaicov_destroy(handle_);
+        handle_ = nullptr;
+    }
+    // the library handle of the last estimateModel() and the numbering of its flattened problem (for the callers next to the path)
+    jaicov_handle *handle() const { return handle_; }
+    int flatPointIndex(const ObjectCoordinate *oc) const {
+        auto it = flatPointPos_.find(oc);
+        return it == flatPointPos_.end() ? -1 : it->second;
+    }
+    int flatImageIndex(const Image *img) const {
+        auto it = flatImagePos_.find(img);
+        return it == flatImagePos_.end() ? -1 : it->second;
     }
 
 private:
@@ -783,6 +808,156 @@ private:
     std::vector<ObjectCoordinate *> flatPoints_;
     std::vector<std::vector<UnknownParameter *>> flatCamParams_;
     std::vector<Image *> flatImages_;
+    std::unordered_map<const ObjectCoordinate *, int> flatPointPos_;
+    std::unordered_map<const Image *, int> flatImagePos_;
+    jaicov_handle *handle_ = nullptr;
+};
+
+// ---- callers either side of the path ----------------------------------------------------------------------
+
+// tranformation/CoordinateTransformationExteriorOrientation.java:49-121: object points carried into the frame of a reference image,
+// X_trg = X0_trg + R_trg R_src' (X - X0_src), with the propagated covariance sigma2 * J Qxx J'.  The visibility loops (:57-98) stay
+// here; the contraction with Qxx runs on the device that holds it (jaicov_propagate_eo_transform), so transform() takes the
+// adjustment whose estimateModel() produced the cofactor matrix instead of a host copy of it.
+class CoordinateTransformationExteriorOrientation {
+public:
+    struct TransformedCoordinate {
+        std::string name;           // "<point> <image> <reference image>", :103
+        double x, y, z;
+    };
+    // imagesToAlign: reference image -> images whose object points are carried into its frame (insertion order of the caller)
+    void transform(const std::vector<ObjectCoordinate *> &objectCoordinatesToTransform,
+                   const std::vector<std::pair<Image *, std::vector<Image *>>> &imagesToAlign, double sigma2, BundleAdjustment &adjustment) {
+        if (!adjustment.handle()) throw std::invalid_argument("the adjustment holds no cofactor matrix on the device (run estimateModel() first)");
+        point_.clear(); src_.clear(); trg_.clear(); transformed_.clear();
+        for (auto &entry : imagesToAlign)                                      // :81-105
+            for (Image *image : entry.second)
+                for (ObjectCoordinate *oc : objectCoordinatesToTransform) {
+                    if (!image->get(oc)) continue;                             // not visible in the current image, :91-95
+                    const int p = adjustment.flatPointIndex(oc), si = adjustment.flatImageIndex(image), ti = adjustment.flatImageIndex(entry.first);
+                    if (p < 0 || si < 0 || ti < 0) throw std::invalid_argument("point or image is not part of the adjustment");
+                    point_.push_back(p); src_.push_back(si); trg_.push_back(ti);
+                    transformed_.push_back({oc->getName() + " " + std::to_string(image->getId()) + " " + std::to_string(entry.first->getId()), 0, 0, 0});
+                }
+        const size_t n = point_.size();
+        std::vector<double> xyz(3 * n);
+        std::vector<double> cov(3 * n * (3 * n + 1) / 2);
+        const int rc = jaicov_propagate_eo_transform(adjustment.handle(), (int32_t)n, point_.data(), src_.data(), trg_.data(), sigma2,
+                                                     n ? xyz.data() : nullptr, n ? cov.data() : nullptr);
+        if (rc != JAICOV_OK) throw std::runtime_error(std::string("jaicov_propagate_eo_transform: ") + jaicov_last_error(adjustment.handle()));
+        for (size_t k = 0; k < n; k++) { transformed_[k].x = xyz[3 * k]; transformed_[k].y = xyz[3 * k + 1]; transformed_[k].z = xyz[3 * k + 2]; }
+        covariance_.reset(new UpperSymmPackMatrix((int)(3 * n), std::move(cov)));   // rows 3 k .. 3 k + 2 belong to transformed point k (:146-148)
+    }
+    const UpperSymmPackMatrix *getCovarianceMatrix() const { return covariance_.get(); }
+    const std::vector<TransformedCoordinate> &getTransformedCoordinates() const { return transformed_; }
+    const std::vector<int32_t> &points() const { return point_; }
+    const std::vector<int32_t> &sourceImages() const { return src_; }
+    const std::vector<int32_t> &targetImages() const { return trg_; }
+
+private:
+    std::vector<int32_t> point_, src_, trg_;
+    std::vector<TransformedCoordinate> transformed_;
+    std::unique_ptr<UpperSymmPackMatrix> covariance_;
+};
+
+// dlt/DLTCoefficients.java:33-84 and dlt/DirectLinearTransformation.java:49-184: initial interior / exterior orientation of images
+// from homologous points.  adjust() keeps the reference's per-image meaning; adjustAll() is the batched form (one kernel launch for
+// all images, jaicov_dlt_batch).
+class DLTCoefficients {
+public:
+    explicit DLTCoefficients(Image *image) : image_(image) {
+        static const int order[20] = {611, 612, 613, 614, 621, 622, 623, 624, 631, 632, 633, 111, 112, 113, 251, 252, 253, 261, 262, 263};
+        for (int t : order) { type_.push_back(t); value_.push_back(0.0); fixed_.push_back(false); }
+    }
+    Image *getReference() const { return image_; }
+    int size() const { return 20; }
+    int typeId(int i) const { return type_[i]; }             // ParameterType ids in the reference's insertion order
+    double getValue(int i) const { return value_[i]; }
+    void setValue(int i, double v) { value_[i] = v; }
+    bool isFixed(int i) const { return fixed_[i]; }
+    void setFixed(int i, bool f) { fixed_[i] = f; }
+    int indexOf(int typeId) const {
+        for (int i = 0; i < 20; i++)
+            if (type_[i] == typeId) return i;
+        return -1;
+    }
+
+private:
+    Image *image_;
+    std::vector<int> type_;
+    std::vector<double> value_;
+    std::vector<bool> fixed_;
+};
+
+class DirectLinearTransformation {
+public:
+    enum class RestrictionType : int {   // ordinal order, DirectLinearTransformation.java:50-57
+        IDENTICAL_PRINCIPLE_DISTANCE = 0, ROTATION_WITHOUT_SHEAR = 1, FIXED_PRINCIPLE_DISTANCE_X = 2, FIXED_PRINCIPLE_DISTANCE_Y = 3,
+        FIXED_PRINCIPAL_POINT_X = 4, FIXED_PRINCIPAL_POINT_Y = 5
+    };
+    static constexpr int maximalNumberOfIterations = 5000;   // DefaultValue.getMaximalNumberOfIterations(), :63
+
+    // the homologous points of every image, gathered the way :78-94 does (image point + object coordinates matched by name)
+    struct Gathered {
+        std::vector<int64_t> pt_ptr{0};
+        std::vector<double> xy, xyz, io;
+    };
+    static Gathered gather(std::vector<DLTCoefficients *> &coefficients, const std::map<std::string, ObjectCoordinate *> &objectCoordinates) {
+        Gathered g;
+        for (DLTCoefficients *coef : coefficients) {
+            Image *image = coef->getReference();
+            InteriorOrientation &inner = image->getReference()->getInteriorOrientation();
+            // prepareUnknwonParameters, :279-314: values reset, the camera's interior orientation taken over (fixed stays fixed)
+            for (int i = 0; i < 20; i++) coef->setValue(i, 0.0);
+            UnknownParameter *ioP[3] = {&inner.getPrincipleDistance(), &inner.getPrinciplePointX(), &inner.getPrinciplePointY()};
+            for (UnknownParameter *p : ioP) {
+                const int k = coef->indexOf((int)p->getParameterType());
+                coef->setValue(k, p->getValue());
+                if (p->getColumn() == COL_FIXED) coef->setFixed(k, true);
+            }
+            for (ImageCoordinate &ic : image->coordinates()) {
+                auto it = objectCoordinates.find(ic.getObjectCoordinate()->getName());
+                if (it == objectCoordinates.end()) continue;
+                g.xy.push_back(ic.getX()); g.xy.push_back(ic.getY());
+                g.xyz.push_back(it->second->getX().getValue()); g.xyz.push_back(it->second->getY().getValue()); g.xyz.push_back(it->second->getZ().getValue());
+            }
+            g.pt_ptr.push_back((int64_t)g.xy.size() / 2);
+            g.io.push_back(coef->getValue(coef->indexOf(113))); g.io.push_back(coef->getValue(coef->indexOf(111))); g.io.push_back(coef->getValue(coef->indexOf(112)));
+        }
+        return g;
+    }
+    // one bool per image: what adjust() returns in the reference
+    static std::vector<bool> adjustAll(std::vector<DLTCoefficients *> &coefficients, const std::map<std::string, ObjectCoordinate *> &objectCoordinates,
+                                       const std::vector<RestrictionType> &restrictions = {}, int device = 0) {
+        Gathered g = gather(coefficients, objectCoordinates);
+        const int32_t nImg = (int32_t)coefficients.size();
+        std::vector<int32_t> restr;
+        for (RestrictionType r : restrictions) restr.push_back((int32_t)r);
+        std::vector<double> out((size_t)20 * std::max(nImg, 1));
+        std::vector<int32_t> status(std::max(nImg, 1)), passes(std::max(nImg, 1));
+        const int rc = jaicov_dlt_batch(device, nImg, g.pt_ptr.data(), g.xy.data(), g.xyz.data(), g.io.data(), (int32_t)restr.size(), restr.data(),
+                                        maximalNumberOfIterations, out.data(), status.data(), passes.data());
+        if (rc != JAICOV_OK) throw std::runtime_error("jaicov_dlt_batch failed (no sm_100 device, or illegal argument): " + std::to_string(rc));
+        std::vector<bool> ok;
+        for (int32_t i = 0; i < nImg; i++) {
+            DLTCoefficients &c = *coefficients[i];
+            if (status[i] < 0) { ok.push_back(false); continue; }
+            const double *o = out.data() + (size_t)20 * i;
+            for (int k = 0; k < 11; k++) c.setValue(k, o[k]);
+            // :248-265: fixed interior orientation values are kept; out = ..., c, x0, y0, X0, Y0, Z0, omega, phi, kappa
+            const int ioIdx[3] = {c.indexOf(113), c.indexOf(111), c.indexOf(112)};
+            for (int k = 0; k < 3; k++)
+                if (!c.isFixed(ioIdx[k])) c.setValue(ioIdx[k], o[11 + k]);
+            for (int k = 14; k < 20; k++) c.setValue(k, o[k]);
+            ok.push_back(status[i] == 1);
+        }
+        return ok;
+    }
+    static bool adjust(DLTCoefficients &coefficients, const std::map<std::string, ObjectCoordinate *> &objectCoordinates,
+                       const std::vector<RestrictionType> &restrictions = {}, int device = 0) {
+        std::vector<DLTCoefficients *> one{&coefficients};
+        return adjustAll(one, objectCoordinates, restrictions, device)[0];
+    }
 };
 
 }  // namespace host

@@ -191,3 +191,44 @@ def test_cpp_host_flattens_the_same_problem_as_the_python_mirror(H, name):
         if pg['var'] is not None:
             np.testing.assert_array_equal(var, np.asarray(pg['var'], float))
     net.close()
+
+
+def test_cpp_dlt_gathers_the_same_homologous_points_as_the_python_mirror(H, monkeypatch):
+    """DirectLinearTransformation (dlt/DirectLinearTransformation.java:78-94, :279-314): what the C++ mirror hands to
+    jaicov_dlt_batch -- homologous points matched by name, the camera's interior orientation -- equals what the Python mirror hands
+    over, on a network where only some of the object points are known; and there is no CPU path behind it."""
+    import bundle_adjustment_b200 as ba
+    from tests.helpers import build_adjustment
+    from tests.scenes import synthetic_scene
+    scene = synthetic_scene(2, images=5, targets=40, visibility=0.7)[0]
+    adj, pts = build_adjustment(scene)
+    images = [img for cam in adj.getCameras() for img in cam]
+    known = [i for i in range(40) if i % 3 != 1]
+    captured = {}
+
+    def fake(pt_ptr, xy, xyz, io, restrictions=(), max_iterations=5000, device=0):
+        captured.update(pt_ptr=np.asarray(pt_ptr), xy=np.asarray(xy).reshape(-1), xyz=np.asarray(xyz).reshape(-1), io=np.asarray(io).reshape(-1))
+        n = len(pt_ptr) - 1
+        return np.zeros((n, 20)), -np.ones(n, np.int32), np.zeros(n, np.int32)
+    monkeypatch.setattr(ba._lib, 'dlt_batch', fake)
+    ba.DirectLinearTransformation.adjustAll([ba.DLTCoefficients(img) for img in images], {pts.names[i]: pts[i] for i in known})
+    net = Net(H, scene)
+    kn = np.array(known, np.int32)
+    m = sum(len(im['obj']) for c in scene['cameras'] for im in c['images'])
+    pt_ptr, xy, xyz, io = np.zeros(net.n_img + 1, np.int64), np.zeros(2 * m), np.zeros(3 * m), np.zeros(3 * net.n_img)
+    net.ok(H.jhost_dlt(net.h, len(kn), _p(kn), 0, None, 0, _p(pt_ptr), _p(xy), _p(xyz), _p(io), None, None))
+    np.testing.assert_array_equal(pt_ptr, captured['pt_ptr'])
+    k = int(pt_ptr[-1])
+    assert 0 < k < m
+    np.testing.assert_array_equal(xy[:2 * k], captured['xy'])
+    np.testing.assert_array_equal(xyz[:3 * k], captured['xyz'])
+    np.testing.assert_array_equal(io, captured['io'])
+    if ba._lib.load().jaicov_device_count() == 0:
+        out, ok = np.zeros(20 * net.n_img), np.zeros(net.n_img, np.uint8)
+        assert H.jhost_dlt(net.h, len(kn), _p(kn), 0, None, 1, None, None, None, None, _p(out), _p(ok)) == -1
+        assert b'jaicov_dlt_batch failed' in H.jhost_last_error(net.h)
+        n_out = ctypes.c_int(0)
+        pts_i, imgs_i = np.array([0, 1], np.int32), np.array([0, 1], np.int32)
+        assert H.jhost_transform(net.h, 2, _p(pts_i), 0, 2, _p(imgs_i), ctypes.c_double(1.0), 0, ctypes.byref(n_out), None, None) == -1
+        assert b'no cofactor matrix on the device' in H.jhost_last_error(net.h)
+    net.close()

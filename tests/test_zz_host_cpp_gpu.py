@@ -72,3 +72,43 @@ def test_tile_product_stage_entry_point(built):
     assert len(cases) >= 20
     bad = [c for c in cases if not c['ok']]
     assert not bad, bad[:3]
+
+
+def test_cpp_host_dlt_and_transform_match_python_mirror(H):
+    """The callers either side of the path through the C++ mirror (DirectLinearTransformation.adjustAll -> jaicov_dlt_batch,
+    CoordinateTransformationExteriorOrientation.transform -> jaicov_propagate_eo_transform) give what the Python mirror gives."""
+    import bundle_adjustment_b200 as ba
+    from tests.helpers import build_adjustment
+    from tests.scenes import synthetic_scene
+    scene = synthetic_scene(2, images=6, targets=40)[0]
+    adj, pts = build_adjustment(scene)
+    images = [img for cam in adj.getCameras() for img in cam]
+    # DLT on the initial values, all points known
+    coefs = [ba.DLTCoefficients(img) for img in images]
+    ok_py = ba.DirectLinearTransformation.adjustAll(coefs, {pts.names[i]: pts[i] for i in range(40)})
+    net = Net(H, scene)
+    kn = np.arange(40, dtype=np.int32)
+    out, ok = np.zeros(20 * net.n_img), np.zeros(net.n_img, np.uint8)
+    net.ok(H.jhost_dlt(net.h, 40, _p(kn), 0, None, 1, None, None, None, None, _p(out), _p(ok)))
+    assert [bool(v) for v in ok] == ok_py
+    vals_py = np.array([[p.getValue() for p in c] for c in coefs])
+    np.testing.assert_allclose(out.reshape(-1, 20), vals_py, rtol=1e-12, atol=1e-12)
+    # adjustment, then the transformation of five points seen in images 1..3 into the frame of image 0
+    assert adj.estimateModel().getId() == 1
+    state = ctypes.c_int(0)
+    net.ok(H.jhost_estimate(net.h, ctypes.byref(state)))
+    assert state.value == 1
+    s2 = adj.getVarianceFactorAposteriori()
+    t = ba.CoordinateTransformationExteriorOrientation.getInstance()
+    t.transform([pts[i] for i in range(5)], {images[0]: images[1:4]}, s2, adj.getCofactorMatrix())
+    xyz_py = np.array([[c.getX().getValue(), c.getY().getValue(), c.getZ().getValue()] for c in t.getTransformedCoordinates()])
+    cov_py = t.getCovarianceMatrix().getData()
+    r = xyz_py.shape[0]
+    pts_i, imgs_i = np.arange(5, dtype=np.int32), np.arange(1, 4, dtype=np.int32)
+    n_out = ctypes.c_int(0)
+    xyz, cov = np.zeros(3 * r), np.zeros(3 * r * (3 * r + 1) // 2)
+    net.ok(H.jhost_transform(net.h, 5, _p(pts_i), 0, 3, _p(imgs_i), ctypes.c_double(s2), r, ctypes.byref(n_out), _p(xyz), _p(cov)))
+    assert n_out.value == r == 15
+    np.testing.assert_allclose(xyz.reshape(-1, 3), xyz_py, rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(cov, cov_py, rtol=1e-9, atol=1e-18)
+    net.close()
