@@ -326,4 +326,12 @@ int jhost_transform(void *n, int n_pts, const int32_t *pts, int reference, int n
     JH_END
 }
 
+// DefaultResultWriter on the network as it stands (after jhost_prepare: <base>.info; after jhost_estimate: also <base>.cxx)
+int jhost_export_default(void *n, const char *base) {
+    JH_BEGIN
+    DefaultResultWriter w(base);
+    w.exportResults(N.adjustment);
+    JH_END
+}
+
 }  // extern "C"

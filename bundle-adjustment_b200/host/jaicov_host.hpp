@@ -25,6 +25,7 @@
 #include <array>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <deque>
 #include <functional>
 #include <map>
@@ -424,9 +425,19 @@ struct FlatProblem {
     int32_t n_unknowns = 0, n_observations = 0;
 };
 
+class BundleAdjustment;
+
+// util/io/writer/AdjustmentResultWritable.java:36: export(BundleAdjustment), called by exportAdjustmentResults() (BA:1164-1171)
+class AdjustmentResultWritable {
+public:
+    virtual ~AdjustmentResultWritable() = default;
+    virtual void exportResults(BundleAdjustment &bundleAdjustment) = 0;   // "export" is a C++ keyword
+};
+
 class BundleAdjustment {
 public:
     using PropertyChangeListener = std::function<void(int state, double oldValue, double newValue)>;
+    void setAdjustmentResultWriter(AdjustmentResultWritable *writer) { writer_ = writer; }   // :1123-1125
 
     // ---- BundleAdjustment.java:652-665 ------------------------------------------------------------------------------------
     void add(Camera *camera) { if (std::find(cameras_.begin(), cameras_.end(), camera) == cameras_.end()) cameras_.push_back(camera); }
@@ -760,7 +771,15 @@ public:
             std::vector<double> q((size_t)(n * (n + 1) / 2), 0.0);   // REDUCED modes fill the leading block only
             if (jaicov_get_qxx_packed(h, q.data()) == JAICOV_OK) Qxx_.reset(new UpperSymmPackMatrix((int)n, std::move(q)));
         }
-        handle_ = h;                                   // Qxx stays on the device for the consumers next to the path (transform)
+        handle_ = h;                                   // Qxx stays on the device for the consumers next to the path (transform, writers)
+        if ((id == JAICOV_ERROR_FREE_ESTIMATION || id == JAICOV_NO_CONVERGENCE) && writer_) {   // exportAdjustmentResults, :360-368
+            try {
+                writer_->exportResults(*this);
+            } catch (const std::exception &e) {
+                lastError_ = e.what();
+                return EstimationStateType::EXPORT_ADJUSTMENT_RESULTS_FAILED;
+            }
+        }
         return (EstimationStateType)id;
     }
 
@@ -808,6 +827,7 @@ private:
     std::vector<ObjectCoordinate *> flatPoints_;
     std::vector<std::vector<UnknownParameter *>> flatCamParams_;
     std::vector<Image *> flatImages_;
+    AdjustmentResultWritable *writer_ = nullptr;
     std::unordered_map<const ObjectCoordinate *, int> flatPointPos_;
     std::unordered_map<const Image *, int> flatImagePos_;
     jaicov_handle *handle_ = nullptr;
@@ -858,6 +878,45 @@ private:
     std::vector<int32_t> point_, src_, trg_;
     std::vector<TransformedCoordinate> transformed_;
     std::unique_ptr<UpperSymmPackMatrix> covariance_;
+};
+
+// util/io/writer/DefaultResultWriter.java:46-155: <base>.info (name, component, coordinate, row / column of the exported matrix;
+// format :67) and <base>.cxx (sigma0^2 a posteriori * Qxx of the object coordinates; format :142).  Only the exported sub-matrix
+// leaves the device (jaicov_get_qxx_submatrix); the full cofactor matrix never travels to the host for this.
+class DefaultResultWriter : public AdjustmentResultWritable {
+public:
+    explicit DefaultResultWriter(std::string exportPathAndFileBaseName) : base_(std::move(exportPathAndFileBaseName)) {}
+    const std::string &getExportPathAndFileBaseName() const { return base_; }
+    void exportResults(BundleAdjustment &adj) override {
+        if (base_.empty()) throw std::invalid_argument("Error, export path cannot be null!");
+        std::vector<int32_t> indices;
+        FILE *f = std::fopen((base_ + ".info").c_str(), "w");
+        if (!f) throw std::runtime_error("cannot write " + base_ + ".info");
+        int k = 0;
+        for (ObjectCoordinate *oc : adj.getObjectCoordinates())
+            for (int c = 0; c < 3; c++) {
+                UnknownParameter &p = oc->component(c);
+                int ci = -1;
+                if (p.getColumn() >= 0 && p.getColumn() < COL_FIXED) { indices.push_back(p.getColumn()); ci = k++; }
+                std::fprintf(f, "%25s\t%5s\t%35.15f\t%10d\n", oc->getName().c_str(), c == 0 ? "X" : (c == 1 ? "Y" : "Z"), p.getValue(), ci);
+            }
+        std::fclose(f);
+        if (adj.getInvertNormalEquation() == MatrixInversion::NONE || !adj.handle()) return;   // no cofactor matrix: .info only
+        const size_t n = indices.size();
+        std::vector<double> C(n * n);
+        if (n && jaicov_get_qxx_submatrix(adj.handle(), (int32_t)n, indices.data(), adj.getVarianceFactorAposteriori(), C.data()) != JAICOV_OK)
+            throw std::runtime_error(std::string("jaicov_get_qxx_submatrix: ") + jaicov_last_error(adj.handle()));
+        f = std::fopen((base_ + ".cxx").c_str(), "w");
+        if (!f) throw std::runtime_error("cannot write " + base_ + ".cxx");
+        for (size_t r = 0; r < n; r++) {
+            for (size_t c = 0; c < n; c++) std::fprintf(f, "%+35.15f  ", C[r * n + c]);
+            std::fprintf(f, "\n");
+        }
+        std::fclose(f);
+    }
+
+private:
+    std::string base_;
 };
 
 // dlt/DLTCoefficients.java:33-84 and dlt/DirectLinearTransformation.java:49-184: initial interior / exterior orientation of images

@@ -232,3 +232,23 @@ def test_cpp_dlt_gathers_the_same_homologous_points_as_the_python_mirror(H, monk
         assert H.jhost_transform(net.h, 2, _p(pts_i), 0, 2, _p(imgs_i), ctypes.c_double(1.0), 0, ctypes.byref(n_out), None, None) == -1
         assert b'no cofactor matrix on the device' in H.jhost_last_error(net.h)
     net.close()
+
+
+def test_cpp_default_result_writer_info_file_equals_the_python_writer(H, tmp_path):
+    """DefaultResultWriter (util/io/writer/DefaultResultWriter.java:67): the .info file of the C++ mirror is byte-identical to the
+    Python writer's on a network with fixed components (index -1) -- names, components, values, running indices."""
+    from bundle_adjustment_b200.writers import DefaultResultWriter
+    from tests.helpers import build_adjustment
+    from tests.scenes import random_scene
+    scene = random_scene(5)
+    adj, _pts = build_adjustment(scene)
+    adj._prepare()
+    DefaultResultWriter(str(tmp_path / 'py')).export(adj)
+    net = Net(H, scene)
+    net.prepare()
+    net.ok(H.jhost_export_default(net.h, str(tmp_path / 'cpp').encode()))
+    a, b = (tmp_path / 'py.info').read_bytes(), (tmp_path / 'cpp.info').read_bytes()
+    assert len(a) > 1000 and a == b
+    assert b'-1\n' in a                                              # a fixed component is listed without a row / column
+    assert not (tmp_path / 'cpp.cxx').exists()                        # no adjustment has run: no cofactor matrix to export
+    net.close()

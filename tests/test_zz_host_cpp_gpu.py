@@ -111,4 +111,18 @@ def test_cpp_host_dlt_and_transform_match_python_mirror(H):
     assert n_out.value == r == 15
     np.testing.assert_allclose(xyz.reshape(-1, 3), xyz_py, rtol=1e-12, atol=1e-9)
     np.testing.assert_allclose(cov, cov_py, rtol=1e-9, atol=1e-18)
+    # DefaultResultWriter: <base>.info and <base>.cxx (sigma0^2 * Qxx of the object coordinates, gathered on the device)
+    import os
+    import tempfile
+    from bundle_adjustment_b200.writers import DefaultResultWriter
+    with tempfile.TemporaryDirectory() as tmp:
+        DefaultResultWriter(os.path.join(tmp, 'py')).export(adj)
+        net.ok(H.jhost_export_default(net.h, os.path.join(tmp, 'cpp').encode()))
+        info_py = [l.split('\t') for l in open(os.path.join(tmp, 'py.info'))]
+        info_cpp = [l.split('\t') for l in open(os.path.join(tmp, 'cpp.info'))]
+        assert [(a[0], a[1], a[3]) for a in info_py] == [(a[0], a[1], a[3]) for a in info_cpp]
+        np.testing.assert_allclose([float(a[2]) for a in info_cpp], [float(a[2]) for a in info_py], rtol=1e-12, atol=1e-9)
+        C_py, C_cpp = np.loadtxt(os.path.join(tmp, 'py.cxx')), np.loadtxt(os.path.join(tmp, 'cpp.cxx'))
+        assert C_py.shape == C_cpp.shape == (120, 120)
+        np.testing.assert_allclose(C_cpp, C_py, rtol=1e-9, atol=1e-14)
     net.close()
