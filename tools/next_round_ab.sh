@@ -33,6 +33,7 @@ ozaki)
       echo "config $cfg $solver, 8 digits: $(grep -o '"ms_per_step": [0-9.]*' gpurun_out/ab_ozaki_c${cfg}_$solver.log) $(grep -o '"frac": [0-9.]*' gpurun_out/ab_ozaki_c${cfg}_$solver.log)"
     done
   done
-  JAICOV_GEMM_OZAKI=8 timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > gpurun_out/ozaki_parity.log 2>&1; tail -3 gpurun_out/ozaki_parity.log ;;
+  # the parity networks are small (launches of a few tiles): send EVERY launch through the digit path for this run
+  JAICOV_GEMM_OZAKI=8 JAICOV_OZAKI_MIN_TILES=1 timeout 1200 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > gpurun_out/ozaki_parity.log 2>&1; tail -3 gpurun_out/ozaki_parity.log ;;
 *) echo "usage: $0 tile | panel N | ozaki" ;;
 esac
