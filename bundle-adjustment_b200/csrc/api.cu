@@ -1082,6 +1082,15 @@ int32_t jaicov_set_cameras(jaicov_handle *h, int32_t n_cam, const double *io_val
                            const int32_t *coef_ptr, const int32_t *coef_type, const int32_t *coef_order, const double *coef_val,
                            const int32_t *coef_col) {
     if (!h || n_cam < 0) return JAICOV_ILLEGAL_ARGUMENT;
+    if (n_cam > 0 && (!io_val || !io_col || !r0 || !coef_ptr)) return fail(h, JAICOV_ILLEGAL_ARGUMENT, "jaicov_set_cameras: null array");
+    if (n_cam > 0 && coef_ptr[n_cam] > 0 && (!coef_type || !coef_order || !coef_val || !coef_col))
+        return fail(h, JAICOV_ILLEGAL_ARGUMENT, "jaicov_set_cameras: null coefficient array");
+    if (n_cam == 0) {
+        h->io_val.clear(); h->io_col.clear(); h->r0.clear(); h->coef_ptr.assign(1, 0);
+        h->coef_type.clear(); h->coef_order.clear(); h->coef_val.clear(); h->coef_col.clear();
+        h->prepared = false;
+        return JAICOV_OK;
+    }
     API_GUARD_BEGIN
     h->io_val.assign(io_val, io_val + 3 * (size_t)n_cam);
     h->io_col.assign(io_col, io_col + 3 * (size_t)n_cam);
@@ -1100,6 +1109,7 @@ int32_t jaicov_set_cameras(jaicov_handle *h, int32_t n_cam, const double *io_val
 int32_t jaicov_set_images(jaicov_handle *h, int32_t n_img, const int32_t *cam_of_img, const double *eo_val, const int32_t *eo_col,
                           const int64_t *pt_ptr) {
     if (!h || n_img < 0) return JAICOV_ILLEGAL_ARGUMENT;
+    if (!pt_ptr || (n_img > 0 && (!cam_of_img || !eo_val || !eo_col))) return fail(h, JAICOV_ILLEGAL_ARGUMENT, "jaicov_set_images: null array");
     API_GUARD_BEGIN
     h->cam_of_img.assign(cam_of_img, cam_of_img + n_img);
     h->eo_val.assign(eo_val, eo_val + 6 * (size_t)n_img);
@@ -1141,6 +1151,7 @@ int32_t jaicov_set_image_points(jaicov_handle *h, int64_t m, const int32_t *obj_
 
 int32_t jaicov_set_object_points(jaicov_handle *h, int32_t n_pt, const double *xyz, const int32_t *col, const uint8_t *is_datum) {
     if (!h || n_pt < 0) return JAICOV_ILLEGAL_ARGUMENT;
+    if (n_pt > 0 && (!xyz || !col)) return fail(h, JAICOV_ILLEGAL_ARGUMENT, "jaicov_set_object_points: null array");
     API_GUARD_BEGIN
     h->xyz.assign(xyz, xyz + 3 * (size_t)n_pt);
     h->pt_col.assign(col, col + 3 * (size_t)n_pt);
@@ -1153,6 +1164,7 @@ int32_t jaicov_set_object_points(jaicov_handle *h, int32_t n_pt, const double *x
 int32_t jaicov_set_scale_bars(jaicov_handle *h, int32_t n_bar, const int32_t *a, const int32_t *b, const double *length,
                               const double *var) {
     if (!h || n_bar < 0) return JAICOV_ILLEGAL_ARGUMENT;
+    if (n_bar > 0 && (!a || !b || !length || !var)) return fail(h, JAICOV_ILLEGAL_ARGUMENT, "jaicov_set_scale_bars: null array");
     API_GUARD_BEGIN
     h->bar_a.assign(a, a + n_bar); h->bar_b.assign(b, b + n_bar);
     h->bar_len.assign(length, length + n_bar); h->bar_var.assign(var, var + n_bar);
@@ -1164,6 +1176,7 @@ int32_t jaicov_set_scale_bars(jaicov_handle *h, int32_t n_bar, const int32_t *a,
 int32_t jaicov_add_observed_group(jaicov_handle *h, int32_t r, const int32_t *target_kind, const int32_t *target_index,
                                   const int32_t *target_comp, const double *obs, const double *var, const double *sigma_packed_upper) {
     if (!h || r <= 0 || (!var && !sigma_packed_upper)) return JAICOV_ILLEGAL_ARGUMENT;
+    if (!target_kind || !target_index || !target_comp || !obs) return fail(h, JAICOV_ILLEGAL_ARGUMENT, "jaicov_add_observed_group: null array");
     API_GUARD_BEGIN
     h->groups.emplace_back();
     Group &g = h->groups.back();

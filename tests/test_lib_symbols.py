@@ -111,3 +111,25 @@ def test_host_mirror_of_the_widened_classes():
         t.transform([pts[0]], {img: [img]}, 1.0, ba.UpperSymmPackMatrix(3, np.zeros(6)))
     RT = ba.DirectLinearTransformation.RestrictionType
     assert [r.value for r in RT] == [0, 1, 2, 3, 4, 5] and RT.FIXED_PRINCIPAL_POINT_Y.name == 'FIXED_PRINCIPAL_POINT_Y'
+
+
+def test_null_arrays_are_refused_not_dereferenced(built):
+    """The ABI never aborts: a missing array with a positive count is JAICOV_ILLEGAL_ARGUMENT with a message."""
+    L = ba._lib.load()
+    opt = ba._lib.Options()
+    L.jaicov_default_options(ctypes.byref(opt))
+    h = ctypes.c_void_p()
+    assert L.jaicov_create(ctypes.byref(opt), ctypes.byref(h)) == 0
+    I = ba._lib.ILLEGAL_ARGUMENT
+    assert L.jaicov_set_cameras(h, 1, None, None, None, None, None, None, None, None) == I
+    assert L.jaicov_set_cameras(h, 0, None, None, None, None, None, None, None, None) == 0
+    assert L.jaicov_set_images(h, 1, None, None, None, None) == I
+    assert L.jaicov_set_image_points(h, ctypes.c_int64(3), None, None, None, None) == I
+    assert L.jaicov_set_object_points(h, 2, None, None, None) == I
+    assert L.jaicov_set_scale_bars(h, 1, None, None, None, None) == I
+    one = np.ones(1)
+    assert L.jaicov_add_observed_group(h, 1, None, None, None, None, one.ctypes.data, None) == I
+    assert L.jaicov_set_datum(h, None, 3, 3) == I
+    L.jaicov_last_error.restype = ctypes.c_char_p
+    assert b'null array' in L.jaicov_last_error(h)
+    L.jaicov_destroy(h)
