@@ -13,10 +13,12 @@
 // Cholesky + inverse schedule with this arithmetic emulated bit for bit on the host (tests/emul/host_backend.cpp) and gets
 // the cofactor matrix of real bundle networks as close to a long-double reference as the FP64 schedule itself.
 //
-// STATUS: written and compiled for sm_100a without access to a GPU (this round's GPU budget was spent); it has NOT run yet.
-// Nothing takes this path unless JAICOV_GEMM_OZAKI is set; tools/next_round_ab.sh holds the first-run checks (small SPD
-// systems against the FP64 route under a timeout, then config 4 / 5 timings).  Kept out of the default path until it is
-// parity-green on a B200.
+// STATUS: written and compiled for sm_100a without access to a GPU; the last seconds of the round's GPU budget then went into a
+// first contact (tools/ozaki_quick.py, profiles/r01_ozaki_first_contact.log): three tile-grid products on a B200 -- plain, transposed
+// operand with alpha / beta, symmetric output with triangular operands -- are correct, with exactly the errors the host emulation
+// predicts (4.4e-16, 3.1e-16, 1.2e-14).  NOT yet done: timings, the cluster / multicast variant, the full check
+// (tools/ozaki_gpu_check.py) and the parity suite with the switch on (tools/next_round_ab.sh ozaki).  Nothing takes this path unless
+// JAICOV_GEMM_OZAKI is set; it stays out of the default path until those are green and it is measured faster.
 //
 // Shapes: CTA tile 128 x 64 (S accumulators of 64 TMEM columns = all 512 columns for S = 8), k-block 64 bytes (SWIZZLE_64B
 // rows), two smem stages of S * (128 + 64) * 64 bytes (96 KB each for S = 8); warp 0 = TMA producer, warp 1 = MMA issuer and
