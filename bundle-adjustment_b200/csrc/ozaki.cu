@@ -572,7 +572,9 @@ bool launch_gemm_ozaki(const GemmDesc &g, cudaStream_t s) {
     static const int64_t min_tiles = [] { const char *e = getenv("JAICOV_OZAKI_MIN_TILES"); return e ? (int64_t)atoll(e) : (int64_t)148; }();
     if (g.coltab || g.kmode > K_MAX_IJ) return false;
     const int64_t tiles = g.tri_out ? (int64_t)g.mt * (g.mt + 1) / 2 : (int64_t)g.mt * g.nt;
-    if (tiles < min_tiles || g.K < 128) return false;
+    // short contractions do not pay for the digit pre-pass (six small launches and 8 + S bytes per operand element)
+    static const int64_t min_k = [] { const char *e = getenv("JAICOV_OZAKI_MIN_K"); return e ? (int64_t)atoll(e) : (int64_t)1024; }();
+    if (tiles < min_tiles || g.K < std::max<int64_t>(128, min_k)) return false;
     if ((double)g.K * digits * 4096.0 >= 2147483648.0) return false;     // a digit-sum group must fit its s32 accumulator
     const int64_t Mr = (int64_t)g.mt * 128, Nr = (int64_t)g.nt * 128;
     const int ra = g.kmode == K_MAX_IJ ? OZ_FROM_TILE : (g.kmode == K_A_LOWER ? OZ_UPTO_TILE : OZ_FULL);

@@ -34,6 +34,6 @@ ozaki)
     done
   done
   # the parity networks are small (launches of a few tiles): send EVERY launch through the digit path for this run
-  JAICOV_GEMM_OZAKI=8 JAICOV_OZAKI_MIN_TILES=1 timeout 1200 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > gpurun_out/ozaki_parity.log 2>&1; tail -3 gpurun_out/ozaki_parity.log ;;
+  JAICOV_GEMM_OZAKI=8 JAICOV_OZAKI_MIN_TILES=1 JAICOV_OZAKI_MIN_K=128 timeout 1200 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > gpurun_out/ozaki_parity.log 2>&1; tail -3 gpurun_out/ozaki_parity.log ;;
 *) echo "usage: $0 tile | panel N | ozaki" ;;
 esac

@@ -12,7 +12,7 @@ Stages
   spd   jaicov_spd_solve_invert (blocked Cholesky + inverse) with every launch on the digit path, against numpy.
   time  one 8192^3 product and one 16384^2 x 8192 symmetric product: FP64 DMMA kernel vs 6 / 7 / 8 digits (TFLOP/s FP64-equivalent).
 The environment variables are read once per process, so every setting runs in a subprocess (JAICOV_OZAKI_MIN_TILES=1 sends
-small launches through the experiment as well).  A hang is cut by the timeout and reported, not retried.
+small launches, JAICOV_OZAKI_MIN_K=128 short contractions through the experiment as well).  A hang is cut by the timeout and reported, not retried.
 """
 import json
 import os
@@ -127,7 +127,7 @@ def worker_time():
 
 def run_worker(stage, env_extra, timeout):
     env = dict(os.environ)
-    for k in ('JAICOV_GEMM_OZAKI', 'JAICOV_OZAKI_MIN_TILES', 'JAICOV_OZAKI_CLUSTER'):
+    for k in ('JAICOV_GEMM_OZAKI', 'JAICOV_OZAKI_MIN_TILES', 'JAICOV_OZAKI_MIN_K', 'JAICOV_OZAKI_CLUSTER'):
         env.pop(k, None)
     env.update(env_extra)
     t0 = time.time()
@@ -148,7 +148,7 @@ def main():
         {'gemm': worker_gemm, 'spd': worker_spd, 'time': worker_time}[sys.argv[2]]()
         return
     stages = sys.argv[1:] or ['gemm', 'spd', 'time']
-    oz = {'JAICOV_GEMM_OZAKI': '8', 'JAICOV_OZAKI_MIN_TILES': '1'}
+    oz = {'JAICOV_GEMM_OZAKI': '8', 'JAICOV_OZAKI_MIN_TILES': '1', 'JAICOV_OZAKI_MIN_K': '128'}
     if 'gemm' in stages:
         if not run_worker('gemm', {}, 300):                       # the entry point itself, FP64 tile kernel
             print('FP64 route failed: fix the harness / entry point first')

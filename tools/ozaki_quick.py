@@ -9,6 +9,7 @@ import time
 t0 = time.time()
 os.environ['JAICOV_GEMM_OZAKI'] = os.environ.get('JAICOV_GEMM_OZAKI', '8')
 os.environ['JAICOV_OZAKI_MIN_TILES'] = '1'
+os.environ['JAICOV_OZAKI_MIN_K'] = '128'
 import numpy as np   # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
