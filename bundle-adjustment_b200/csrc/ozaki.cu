@@ -210,6 +210,12 @@ struct OzGemmArgs {
     int64_t ldc, K;
     double alpha, beta;
     int mt, nt, tri_out, tile_band, kmode;
+    // launches of the multi-GPU schedule (dense_driver.hpp): column table (trapezoid update of many panels at once) and the
+    // per-column-tile masks of the column-panel inverse
+    const int32_t *coltab;    // 2-D launch: blockIdx.y picks the global column tile coltab[y] / 128
+    int coltab_full, c_local;
+    const int32_t *ktab;      // K_COL_BEG / K_ROW_MASK: first global row of interest of every column tile
+    int64_t koff, roff;
 };
 
 __device__ __forceinline__ uint32_t oz_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -308,9 +314,14 @@ k_gemm_oz(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // ---- tile decode: the same order as k_gemm, every 128 x 128 tile as two 64-column halves ---------------------------
+    // (tiles that are not wanted leave here, before any barrier or TMEM allocation exists; both CTAs of a cluster share the tile)
     const int l = blockIdx.x >> 1, half = blockIdx.x & 1;     // CL = 2: half == rank of the CTA in its cluster
     int it, jt;
-    if (p.tri_out) {
+    if (p.coltab) {
+        it = l;
+        jt = p.coltab[blockIdx.y] / 128;
+        if (!p.coltab_full && it < jt) return;                // above the diagonal of this column tile
+    } else if (p.tri_out) {
         tri_tile_decode(l, p.mt, p.tile_band, it, jt);
     } else {
         it = l / p.nt;
@@ -321,8 +332,15 @@ k_gemm_oz(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     if (p.kmode == K_B_LOWER) kbeg = (int64_t)jt * 128;
     else if (p.kmode == K_A_LOWER) kend = min(p.K, (int64_t)(it + 1) * 128);
     else if (p.kmode == K_MAX_IJ) kbeg = (int64_t)max(it, jt) * 128;
+    else if (p.kmode == K_COL_BEG) {
+        kbeg = max((int64_t)0, (int64_t)p.ktab[jt] - p.koff);
+        if (kbeg >= p.K) return;                              // this column tile is still zero in the whole contraction range
+    } else if (p.kmode == K_ROW_MASK) {
+        if (p.roff + (int64_t)it * 128 < (int64_t)p.ktab[jt]) return;   // above the column's diagonal: not wanted
+    }
     const int nkb = (int)((kend - kbeg) / OZ_BK);
     const int m0 = it * 128, n0 = jt * 128 + half * OZ_BN;
+    const int64_t c0 = ((p.coltab && p.c_local) ? (int64_t)blockIdx.y : (int64_t)jt) * 128 + half * OZ_BN;   // first column of C
 
     // ---- one-time setup --------------------------------------------------------------------------------------------------
     if (warp == 0 && lane == 0) {
@@ -400,7 +418,7 @@ k_gemm_oz(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int64_t m = (int64_t)m0 + 32 * q + lane;
         const int ea = p.ea[m];
-        double *crow = p.C + m * p.ldc + n0;
+        double *crow = p.C + m * p.ldc + c0;
         const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
         for (int c8 = 0; c8 < OZ_BN / 8; c8++) {
             double r[8];
@@ -527,7 +545,7 @@ struct OzScratch {
 OzScratch g_oz;
 
 template <int S, int CL>
-void launch_tiles(const CUtensorMap &ma, const CUtensorMap &mb, const OzGemmArgs &a, int64_t tiles, cudaStream_t s) {
+void launch_tiles(const CUtensorMap &ma, const CUtensorMap &mb, const OzGemmArgs &a, int64_t tiles, int grid_y, cudaStream_t s) {
     static bool attr = false;
     if (!attr) {
         JCHECK(cudaFuncSetAttribute(k_gemm_oz<S, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<S>::SMEM));
@@ -535,7 +553,7 @@ void launch_tiles(const CUtensorMap &ma, const CUtensorMap &mb, const OzGemmArgs
     }
     g_launch_count++;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(tiles * 2));
+    cfg.gridDim = dim3((unsigned)(tiles * 2), (unsigned)grid_y);   // x: row tile (or tile list) x two 64-column halves; y: column-table slot
     cfg.blockDim = dim3(OZ_THREADS);
     cfg.dynamicSmemBytes = OzCfg<S>::SMEM;
     cfg.stream = s;
@@ -550,13 +568,13 @@ void launch_tiles(const CUtensorMap &ma, const CUtensorMap &mb, const OzGemmArgs
 }
 
 template <int CL>
-void launch_tiles_digits(int digits, const CUtensorMap &ma, const CUtensorMap &mb, const OzGemmArgs &a, int64_t tiles, cudaStream_t s) {
+void launch_tiles_digits(int digits, const CUtensorMap &ma, const CUtensorMap &mb, const OzGemmArgs &a, int64_t tiles, int grid_y, cudaStream_t s) {
     switch (digits) {
-        case 4: launch_tiles<4, CL>(ma, mb, a, tiles, s); break;
-        case 5: launch_tiles<5, CL>(ma, mb, a, tiles, s); break;
-        case 6: launch_tiles<6, CL>(ma, mb, a, tiles, s); break;
-        case 7: launch_tiles<7, CL>(ma, mb, a, tiles, s); break;
-        default: launch_tiles<8, CL>(ma, mb, a, tiles, s); break;
+        case 4: launch_tiles<4, CL>(ma, mb, a, tiles, grid_y, s); break;
+        case 5: launch_tiles<5, CL>(ma, mb, a, tiles, grid_y, s); break;
+        case 6: launch_tiles<6, CL>(ma, mb, a, tiles, grid_y, s); break;
+        case 7: launch_tiles<7, CL>(ma, mb, a, tiles, grid_y, s); break;
+        default: launch_tiles<8, CL>(ma, mb, a, tiles, grid_y, s); break;
     }
 }
 
@@ -570,13 +588,16 @@ bool launch_gemm_ozaki(const GemmDesc &g, cudaStream_t s) {
     static const int digits = [] { const char *e = getenv("JAICOV_GEMM_OZAKI"); return e ? atoi(e) : 0; }();
     if (digits < 4 || digits > 8) return false;
     static const int64_t min_tiles = [] { const char *e = getenv("JAICOV_OZAKI_MIN_TILES"); return e ? (int64_t)atoll(e) : (int64_t)148; }();
-    if (g.coltab || g.kmode > K_MAX_IJ) return false;
-    const int64_t tiles = g.tri_out ? (int64_t)g.mt * (g.mt + 1) / 2 : (int64_t)g.mt * g.nt;
+    // column-table launches: only the trapezoid update of the distributed Cholesky (both operands the same panel, C addressed by
+    // global tiles); the structured route's compact column tables keep the FP64 kernel
+    const bool trapezoid = g.coltab && !g.c_local && g.A == g.B && g.lda == g.ldb && g.al == g.bl && g.kmode == K_FULL;
+    if ((g.coltab && !trapezoid) || g.kmode > K_ROW_MASK) return false;
+    const int64_t tiles = g.coltab ? (int64_t)g.mt * g.ncoltab : (g.tri_out ? (int64_t)g.mt * (g.mt + 1) / 2 : (int64_t)g.mt * g.nt);
     // short contractions do not pay for the digit pre-pass (six small launches and 8 + S bytes per operand element)
     static const int64_t min_k = [] { const char *e = getenv("JAICOV_OZAKI_MIN_K"); return e ? (int64_t)atoll(e) : (int64_t)1024; }();
     if (tiles < min_tiles || g.K < std::max<int64_t>(128, min_k)) return false;
     if ((double)g.K * digits * 4096.0 >= 2147483648.0) return false;     // a digit-sum group must fit its s32 accumulator
-    const int64_t Mr = (int64_t)g.mt * 128, Nr = (int64_t)g.nt * 128;
+    const int64_t Mr = (int64_t)g.mt * 128, Nr = g.coltab ? (int64_t)g.mt * 128 : (int64_t)g.nt * 128;   // column table: op(B) rows by global tile
     const int ra = g.kmode == K_MAX_IJ ? OZ_FROM_TILE : (g.kmode == K_A_LOWER ? OZ_UPTO_TILE : OZ_FULL);
     const int rb = (g.kmode == K_MAX_IJ || g.kmode == K_B_LOWER) ? OZ_FROM_TILE : OZ_FULL;
     const bool shared = g.A == g.B && g.lda == g.ldb && g.al == g.bl && ra == rb && Mr == Nr;
@@ -603,9 +624,12 @@ bool launch_gemm_ozaki(const GemmDesc &g, cudaStream_t s) {
     }
     launch_split(sa, s);
     if (!shared) launch_split(sb, s);
-    OzGemmArgs a{g_oz.e[0], g_oz.e[wb], g.C, g.ldc, g.K, g.alpha, g.beta, g.mt, g.nt, g.tri_out, g.tile_band, g.kmode};
-    if (cluster == 2) launch_tiles_digits<2>(digits, ma, mb, a, tiles, s);
-    else launch_tiles_digits<1>(digits, ma, mb, a, tiles, s);
+    OzGemmArgs a{g_oz.e[0], g_oz.e[wb], g.C, g.ldc, g.K, g.alpha, g.beta, g.mt, g.nt, g.tri_out, g.tile_band, g.kmode,
+                 g.coltab, g.coltab_full, g.c_local, g.ktab, g.koff, g.roff};
+    const int64_t grid_tiles = g.coltab ? (int64_t)g.mt : tiles;     // column table: x runs over the row tiles, y over the table
+    const int grid_y = g.coltab ? g.ncoltab : 1;
+    if (cluster == 2) launch_tiles_digits<2>(digits, ma, mb, a, grid_tiles, grid_y, s);
+    else launch_tiles_digits<1>(digits, ma, mb, a, grid_tiles, grid_y, s);
     return true;
 }
 

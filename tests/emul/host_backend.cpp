@@ -42,6 +42,7 @@ static void ozaki_split(OzakiOperand &o, int64_t rows, int64_t K, int s, Get get
         o.e[r] = e;
         for (int64_t k = k0; k < k1; k++) {
             double t = std::ldexp(get(r, k), 6 - e);           // |t| < 64
+            if (!std::isfinite(t)) t = 0.0;                    // rows nobody reads may hold anything (the device converts NaN to 0 too)
             for (int j = 0; j < s; j++) {
                 const double qd = std::nearbyint(t);
                 o.q[((size_t)j * rows + r) * K + k] = (int8_t)qd;
@@ -63,7 +64,8 @@ struct HostBackend {
 
     void gemm_ozaki(const GemmDesc &g) {
         const int T = kTile, s = ozaki;
-        const int64_t Mr = (int64_t)g.mt * T, Nr = (int64_t)g.nt * T, K = g.K;
+        // column-table launches index op(B) by GLOBAL tile: the operand is the same panel as op(A), all of its g.mt row tiles
+        const int64_t Mr = (int64_t)g.mt * T, Nr = g.coltab ? (int64_t)g.mt * T : (int64_t)g.nt * T, K = g.K;
         OzakiOperand A, B;
         auto getA = [&](int64_t m, int64_t k) { return g.al == 0 ? g.A[m * g.lda + k] : g.A[k * g.lda + m]; };
         auto getB = [&](int64_t n, int64_t k) { return g.bl == 0 ? g.B[n * g.ldb + k] : g.B[k * g.ldb + n]; };
@@ -90,13 +92,25 @@ struct HostBackend {
         ozaki_split(A, Mr, K, s, [&](int64_t m, int64_t k) { return std::ldexp(getA(m, k), fk[k]); }, loA, hiA);
         ozaki_split(B, Nr, K, s, [&](int64_t n, int64_t k) { return std::ldexp(getB(n, k), -fk[k]); }, loB, hiB);
         std::vector<long long> S(2 * s + 1);
+        std::vector<double> cbuf((size_t)T * T);
         for (int it = 0; it < g.mt; it++)
-            for (int jt = 0; jt < g.nt; jt++) {
+            for (int jl = 0; jl < g.nt; jl++) {
+                int jt = jl;
+                if (g.coltab) {
+                    jt = g.coltab[jl] / T;
+                    if (!g.coltab_full && it < jt) continue;
+                }
                 if (g.tri_out && it < jt) continue;
                 int64_t kbeg = 0, kend = K;
                 if (g.kmode == K_B_LOWER) kbeg = (int64_t)jt * T;
                 else if (g.kmode == K_A_LOWER) kend = std::min<int64_t>(K, (int64_t)(it + 1) * T);
                 else if (g.kmode == K_MAX_IJ) kbeg = (int64_t)std::max(it, jt) * T;
+                else if (g.kmode == K_COL_BEG) {
+                    kbeg = std::max<int64_t>(0, (int64_t)g.ktab[jt] - g.koff);
+                    if (kbeg >= K) continue;
+                } else if (g.kmode == K_ROW_MASK) {
+                    if (g.roff + (int64_t)it * T < (int64_t)g.ktab[jt]) continue;
+                }
                 flops += 2.0 * T * T * (double)(kend - kbeg);
                 for (int i = 0; i < T; i++)
                     for (int j = 0; j < T; j++) {
@@ -117,15 +131,24 @@ struct HostBackend {
                             r = r * 0.0078125 + (double)S[gq];                 // r / 128 + S_g (the kernel's epilogue)
                         }
                         r = std::ldexp(r, A.e[m] + B.e[n] - 12);               // digit weights 2^-(7 g - 2), g = 2 last
-                        double *c = g.C + m * g.ldc + n;
-                        *c = g.beta == 0.0 ? g.alpha * r : g.alpha * r + g.beta * *c;
+                        const int64_t ccol = (g.coltab && g.c_local) ? (int64_t)jl * T + j : n;
+                        cbuf[(size_t)i * T + j] = g.alpha * r + (g.beta == 0.0 ? 0.0 : g.beta * g.C[m * g.ldc + ccol]);
+                    }
+                // the tile is stored after all of it has been computed (the digit planes are copies, so in-place launches are safe anyway)
+                for (int i = 0; i < T; i++)
+                    for (int j = 0; j < T; j++) {
+                        const int64_t m = (int64_t)it * T + i, n = (int64_t)jt * T + j;
+                        g.C[m * g.ldc + ((g.coltab && g.c_local) ? (int64_t)jl * T + j : n)] = cbuf[(size_t)i * T + j];
                     }
             }
     }
 
     void gemm(const GemmDesc &g) {
         gemm_calls++;
-        if (ozaki > 0 && !g.coltab && g.kmode <= K_MAX_IJ) {
+        // what csrc/ozaki.cu: launch_gemm_ozaki takes: everything without a column table, and the trapezoid update of the
+        // distributed Cholesky (column table, both operands the same panel of the matrix, C addressed by global tiles)
+        const bool trapezoid = g.coltab && !g.c_local && (const void *)g.A == (const void *)g.B && g.lda == g.ldb && g.al == g.bl && g.kmode == K_FULL;
+        if (ozaki > 0 && (!g.coltab || trapezoid)) {
             const long tiles = g.tri_out ? (long)g.mt * (g.mt + 1) / 2 : (long)g.mt * g.nt;
             if (tiles >= ozaki_min_tiles) { ozaki_calls++; gemm_ozaki(g); return; }
         }
@@ -242,7 +265,12 @@ void emul_tri_tile_decode(int64_t l, int mt, int band, int *it, int *jt) { jaico
 // distributed Cholesky with `nranks` virtual ranks (threads), panel width pw tiles; on exit every replica must hold
 // the same factor; replica 0 is returned in M (lower), followed by the column-panel inverse of the column tiles
 // owned by each rank (tile c belongs to rank (c / pw) % nranks), gathered into Q (np x np, lower part valid).
+int emul_distributed_ex(int64_t np, double *M, int nranks, int pw, double *Q, double *maxdiff, int merged, int ozaki);
 int emul_distributed(int64_t np, double *M, int nranks, int pw, double *Q, double *maxdiff, int merged) {
+    return emul_distributed_ex(np, M, nranks, pw, Q, maxdiff, merged, 0);
+}
+// ozaki > 0: every eligible launch of both stages (panel factor, trapezoid updates, column-tile inverse) through the digit emulation
+int emul_distributed_ex(int64_t np, double *M, int nranks, int pw, double *Q, double *maxdiff, int merged, int ozaki) {
     const double nan = std::numeric_limits<double>::quiet_NaN();
     const int nb = (int)(np / kTile);
     std::vector<std::vector<double>> Mr(nranks, std::vector<double>(M, M + np * np)), Dr(nranks, std::vector<double>((size_t)np * kTile, nan));
@@ -254,6 +282,7 @@ int emul_distributed(int64_t np, double *M, int nranks, int pw, double *Q, doubl
     for (int r = 0; r < nranks; r++)
         th.emplace_back([&, r] {
             HostBackend be;
+            be.ozaki = ozaki;
             HostComm comm{r, nranks, &Ms, &Ds, np, &bar};
             DenseSchedule<HostBackend> ds{be, Ms[r], np, np, Ds[r]};
             std::vector<int32_t> own;
@@ -280,6 +309,7 @@ int emul_distributed(int64_t np, double *M, int nranks, int pw, double *Q, doubl
         for (int jl = 0; jl < ntc; jl++)
             for (int i = 0; i < kTile; i++) X[(size_t)(ktab[jl] + i) * ldx + jl * kTile + i] = 1.0;
         HostBackend be;
+        be.ozaki = ozaki;
         DenseSchedule<HostBackend> ds{be, Ms[r], np, np, Ds[r]};
         ds.inverse_columns(X.data(), ldx, ntc, ktab.data());
         for (int jl = 0; jl < ntc; jl++)

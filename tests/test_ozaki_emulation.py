@@ -92,3 +92,31 @@ def test_structured_route_products_from_digit_products(emul):
     assert up == 180 and m == 65
     assert dev[0] <= 2e-12 and dev[8] <= 2 * dev[0] + 1e-15, dev
     assert 3 * dev[8] < dev[-8] <= 1e-10, dev          # without the balancing: visibly coarser, still inside the 1e-8 bar
+
+
+@pytest.mark.parametrize('nb,nranks,pw,merged', [(6, 2, 1, 1), (7, 3, 2, 1), (7, 3, 2, 0)])
+def test_distributed_schedule_from_digit_products(emul, nb, nranks, pw, merged):
+    """The multi-GPU schedule (block-column-cyclic Cholesky with one trapezoid launch per panel -- column-table launches --, then
+    every rank's column-tile inverse with its per-column-tile masks, csrc/dense_driver.hpp) with every eligible launch computed
+    from 8 int8 digits: all virtual ranks end with the same factor and the gathered column tiles are the inverse.  This is the
+    launch geometry csrc/ozaki.cu accepts beyond the single-GPU one (the kernel itself still has to see a multi-GPU run)."""
+    emul.emul_distributed_ex.argtypes = [ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_int, ctypes.c_int]
+    rng = np.random.default_rng(100 + nb)
+    n = 128 * nb
+    A = rng.standard_normal((n, n))
+    S = A @ A.T + n * np.eye(n)
+    dd = 1 / np.sqrt(np.diag(S))
+    S = S * dd[:, None] * dd[None, :]
+    M = np.tril(S).copy()
+    M[np.triu_indices(n, 1)] = np.nan
+    for i in range(nb):
+        M[i * 128:(i + 1) * 128, i * 128:(i + 1) * 128] = np.tril(S[i * 128:(i + 1) * 128, i * 128:(i + 1) * 128])
+    Q = np.full((n, n), np.nan)
+    md = ctypes.c_double(0)
+    info = emul.emul_distributed_ex(n, M.ctypes.data, nranks, pw, Q.ctypes.data, ctypes.byref(md), merged, 8)
+    assert info == 0 and md.value == 0.0
+    np.testing.assert_allclose(np.tril(M), np.linalg.cholesky(S), atol=1e-13)
+    Qi = np.linalg.inv(S)
+    assert not np.isnan(np.tril(Q)).any()
+    np.testing.assert_allclose(np.tril(Q), np.tril(Qi), atol=1e-12 * np.abs(Qi).max())
