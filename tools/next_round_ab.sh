@@ -5,6 +5,7 @@
 #   bash tools/next_round_ab.sh ozaki     1 GPU : first run of the int8-digit tcgen05 GEMM (csrc/ozaki.cu, never executed so far):
 #                                                 correctness on small tile grids and SPD systems under timeouts, then timings;
 #                                                 only if all of that is green: config 4 / 5 passes with JAICOV_GEMM_OZAKI=8
+#   bash tools/next_round_ab.sh ozaki_multi N  N GPUs: the same switch through the multi-GPU parity tests and the config-5 bench
 mkdir -p gpurun_out
 case "$1" in
 tile)
@@ -35,5 +36,13 @@ ozaki)
   done
   # the parity networks are small (launches of a few tiles): send EVERY launch through the digit path for this run
   JAICOV_GEMM_OZAKI=8 JAICOV_OZAKI_MIN_TILES=1 JAICOV_OZAKI_MIN_K=128 timeout 1200 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > gpurun_out/ozaki_parity.log 2>&1; tail -3 gpurun_out/ozaki_parity.log ;;
-*) echo "usage: $0 tile | panel N | ozaki" ;;
+ozaki_multi)
+  # N GPUs (after `ozaki` is green on one): multi-GPU parity with every launch on the digit path, then the config-5 bench
+  N=${2:-2}
+  JAICOV_GEMM_OZAKI=8 JAICOV_OZAKI_MIN_TILES=1 JAICOV_OZAKI_MIN_K=128 timeout 900 python -m pytest tests/test_gpu_multi.py -x -q -m gpu \
+    > gpurun_out/ozaki_multi_parity_n$N.log 2>&1; tail -3 gpurun_out/ozaki_multi_parity_n$N.log
+  JAICOV_GEMM_OZAKI=8 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29562 \
+    bench.py --gpus $N --steps 2 --warmup 3 --no-e2e > gpurun_out/ab_ozaki_c5_n$N.log 2>&1
+  echo "config 5, $N GPUs, 8 digits: $(grep -o '"ms_per_step": [0-9.]*' gpurun_out/ab_ozaki_c5_n$N.log) $(grep -o '"frac": [0-9.]*' gpurun_out/ab_ozaki_c5_n$N.log)" ;;
+*) echo "usage: $0 tile | panel N | ozaki | ozaki_multi N" ;;
 esac
