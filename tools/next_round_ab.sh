@@ -36,6 +36,15 @@ ozaki)
   done
   # the parity networks are small (launches of a few tiles): send EVERY launch through the digit path for this run
   JAICOV_GEMM_OZAKI=8 JAICOV_OZAKI_MIN_TILES=1 JAICOV_OZAKI_MIN_K=128 timeout 1200 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > gpurun_out/ozaki_parity.log 2>&1; tail -3 gpurun_out/ozaki_parity.log ;;
+ozaki_ncu)
+  # after `ozaki` is green: launch list and one full capture of the digit-product tile kernel on the timing worker
+  # (the plain run directly before, as the profiling recipe asks)
+  JAICOV_GEMM_OZAKI=8 python tools/ozaki_gpu_check.py --worker time > gpurun_out/ozaki_time_plain.log 2>&1 &&
+  JAICOV_GEMM_OZAKI=8 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 200 --csv \
+    --log-file gpurun_out/launches_ozaki_time.csv python tools/ozaki_gpu_check.py --worker time > gpurun_out/ozaki_time_ncu.log 2>&1
+  JAICOV_GEMM_OZAKI=8 ncu --set full --clock-control none --import-source on -k regex:k_gemm_oz -c 1 \
+    -o gpurun_out/ncu_full_k_gemm_oz python tools/ozaki_gpu_check.py --worker time >> gpurun_out/ozaki_time_ncu.log 2>&1
+  tail -5 gpurun_out/ozaki_time_ncu.log ;;
 ozaki_multi)
   # N GPUs (after `ozaki` is green on one): multi-GPU parity with every launch on the digit path, then the config-5 bench
   N=${2:-2}
@@ -44,5 +53,5 @@ ozaki_multi)
   JAICOV_GEMM_OZAKI=8 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29562 \
     bench.py --gpus $N --steps 2 --warmup 3 --no-e2e > gpurun_out/ab_ozaki_c5_n$N.log 2>&1
   echo "config 5, $N GPUs, 8 digits: $(grep -o '"ms_per_step": [0-9.]*' gpurun_out/ab_ozaki_c5_n$N.log) $(grep -o '"frac": [0-9.]*' gpurun_out/ab_ozaki_c5_n$N.log)" ;;
-*) echo "usage: $0 tile | panel N | ozaki | ozaki_multi N" ;;
+*) echo "usage: $0 tile | panel N | ozaki | ozaki_ncu | ozaki_multi N" ;;
 esac
