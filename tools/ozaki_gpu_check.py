@@ -10,7 +10,7 @@ Stages
         first with the FP64 tile kernel (checks the entry point itself), then with 8 digits through the tcgen05 path.
         Everything the kernels must never read is NaN.
   spd   jaicov_spd_solve_invert (blocked Cholesky + inverse) with every launch on the digit path, against numpy.
-  time  one 8192^3 product and one 16384^2 x 8192 symmetric product: FP64 DMMA kernel vs 6 / 7 / 8 digits (TFLOP/s FP64-equivalent).
+  time  one 8192^3 product and one 16384^2 x 8192 symmetric product: FP64 DMMA kernel vs 8 / 7 digits and the cluster variant (TFLOP/s FP64-equivalent).
 The environment variables are read once per process, so every setting runs in a subprocess (JAICOV_OZAKI_MIN_TILES=1 sends
 small launches, JAICOV_OZAKI_MIN_K=128 short contractions through the experiment as well).  A hang is cut by the timeout and reported, not retried.
 """
@@ -163,7 +163,7 @@ def main():
             return
     if 'time' in stages:
         run_worker('time', {}, 600)
-        for s in ('6', '7', '8'):
+        for s in ('8', '7'):
             run_worker('time', {'JAICOV_GEMM_OZAKI': s}, 600)
         run_worker('time', {'JAICOV_GEMM_OZAKI': '8', 'JAICOV_OZAKI_CLUSTER': '2'}, 600)
 
