@@ -252,3 +252,27 @@ def test_cpp_default_result_writer_info_file_equals_the_python_writer(H, tmp_pat
     assert b'-1\n' in a                                              # a fixed component is listed without a row / column
     assert not (tmp_path / 'cpp.cxx').exists()                        # no adjustment has run: no cofactor matrix to export
     net.close()
+
+
+def test_cpp_and_python_mirrors_agree_on_random_networks(H):
+    """Beyond the 18 reference-executed networks: 30 random networks (datum defects 0..7, fixed components, scale bars, two
+    cameras) get the same columns, counts, rank-defect flags and sigma0^2 from both mirrors."""
+    from tests.helpers import flat_problem
+    from tests.scenes import random_scene
+    defects = set()
+    for seed in range(100, 130):
+        scene = random_scene(seed)
+        adj, flat = flat_problem(scene)
+        net = Net(H, scene)
+        counts, flags, s2 = net.prepare()
+        pt, io, cf, eo = net.columns()
+        assert (counts[0], counts[1], counts[4]) == (flat['n_observations'], flat['n_unknowns'], int(np.sum(flat['free_flags']))), seed
+        assert list(flags) == list(flat['free_flags']), seed
+        np.testing.assert_array_equal(pt.reshape(-1), np.asarray(flat['pt_col']), err_msg=str(seed))
+        np.testing.assert_array_equal(io, flat['io_col'])
+        np.testing.assert_array_equal(cf, flat['coef_col'])
+        np.testing.assert_array_equal(eo, flat['eo_col'])
+        assert s2 == adj.getVarianceFactorApriori()
+        defects.add(int(counts[4]))
+        net.close()
+    assert len(defects) >= 3          # the sample really covers different datum situations
