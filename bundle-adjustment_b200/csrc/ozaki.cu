@@ -93,7 +93,7 @@ __device__ __forceinline__ void oz_load16(const OzSplitArgs &a, int64_t row, int
     }
 }
 
-// Contraction-index balancing (tests/emul/host_backend.cpp: gemm_ozaki; tools/ozaki_study.py --structured): column maxima of both
+// Contraction-index balancing (tests/emul/host_backend.cpp: gemm_ozaki; tests/ozaki_study.py --structured): column maxima of both
 // operands, then f_k = floor((exponent of max |B[., k]| - exponent of max |A[., k]|) / 2).  op(A)[., k] * 2^f_k and op(B)[., k] * 2^-f_k
 // leave every product unchanged but even out the magnitudes inside the operand rows, which the per-row digit grid resolves.
 __global__ void __launch_bounds__(128) k_oz_colmax(OzSplitArgs a) {

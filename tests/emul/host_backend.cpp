@@ -76,7 +76,7 @@ struct HostBackend {
         // Contraction-index balancing: op(A)[., k] * 2^f_k and op(B)[., k] * 2^-f_k leave every product unchanged (exact powers of
         // two) but even out the magnitudes inside the operand rows, which is what the per-row digit grid resolves.  f_k = floor of
         // half the exponent gap of the two column maxima.  Needed where the operands span many orders of magnitude inside a row
-        // (the structured route's Q'Y' and Y (Q'Y'), tools/ozaki_study.py --structured); nothing to do when A and B are the same array.
+        // (the structured route's Q'Y' and Y (Q'Y'), tests/ozaki_study.py --structured); nothing to do when A and B are the same array.
         std::vector<int> fk(K, 0);
         const bool same = (const void *)g.A == (const void *)g.B && g.lda == g.ldb && g.al == g.bl && g.kmode != K_A_LOWER && g.kmode != K_B_LOWER && Mr == Nr;
         if (ozaki_kscale && !same) {

@@ -1,10 +1,10 @@
 #!/usr/bin/env python
-"""Numerics study (CPU, test infrastructure): the blocked Cholesky + inverse schedule of csrc/dense_driver.hpp with every
+"""Numerics study (CPU, test infrastructure -- it uses the oracle, hence its place under tests/): the blocked Cholesky + inverse schedule of csrc/dense_driver.hpp with every
 GEMM computed by the int8-slice emulation of tests/emul/host_backend.cpp (what FP64 products on the INT8 tcgen05 tensor
 cores would compute, bit for bit) against the same schedule in FP64, on the preconditioned SPD system M~ = V N V + B~'B~
  of real bundle networks assembled by the oracle.
 
-  python tools/ozaki_study.py [--images 12 --targets 150] [--digits 6 7 8]
+  python tests/ozaki_study.py [--images 12 --targets 150] [--digits 6 7 8]
 
 Prints, per digit count: largest integer group sum (must stay below 2^31), the correlation-scaled deviation of the
 inverse from a long-double reference, next to the deviation of the FP64 schedule itself.

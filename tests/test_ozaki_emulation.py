@@ -11,9 +11,9 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, 'tools'))
+sys.path.insert(0, os.path.join(ROOT, 'tools'))            # ozaki_gpu_check (the case list of the GPU checker)
 
-import ozaki_study as oz   # noqa: E402
+from tests import ozaki_study as oz   # noqa: E402
 
 
 @pytest.fixture(scope='module')
