@@ -133,3 +133,18 @@ def test_null_arrays_are_refused_not_dereferenced(built):
     L.jaicov_last_error.restype = ctypes.c_char_p
     assert b'null array' in L.jaicov_last_error(h)
     L.jaicov_destroy(h)
+
+
+def test_struct_offsets_used_by_the_java_binding(built):
+    """INTEGRATION.md section 3 addresses jaicov_options / jaicov_stats by byte offset from Java (MemorySegment.set/get):
+    those offsets are part of the ABI."""
+    O, S = ba._lib.Options, ba._lib.Stats
+    assert [getattr(O, f).offset for f in ('invert_mode', 'estimation_type', 'max_iterations', 'use_centroid', 'apply_aposteriori',
+                                            'device', 'solver', 'sigma2apriori', 'damping_value')] == [0, 4, 8, 12, 16, 20, 24, 32, 40]
+    assert [getattr(S, f).offset for f in ('status', 'iterations', 'iteration_step', 'n_unknowns', 'n_datum', 'n_observations', 'dof',
+                                            'solver_used', 'omega', 'max_abs_dx', 'sigma2apriori', 'sigma2aposteriori')] == \
+        [0, 4, 8, 12, 16, 20, 24, 28, 32, 40, 48, 56]
+    import re
+    doc = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    assert 'opt.set(JAVA_DOUBLE, 32, sigma2apriori)' in doc and 'opt.set(JAVA_DOUBLE, 40, dampingValue)' in doc
+    assert re.search(r'st\.get\(JAVA_DOUBLE, 32\).*st\.get\(JAVA_DOUBLE, 40\).*st\.get\(JAVA_INT, 8\)', doc)
