@@ -368,6 +368,9 @@ public:
             throw std::invalid_argument("Error, number of observations and number of rows/columns in dispersion matrix are unequal");
         for (size_t i = 0; i < r; i++) obs_[i]->setVariance(packed_[i + i * (i + 1) / 2]);
     }
+    // the reference's argument order (dispersionMatrix first, :49)
+    DirectlyObservedParameterGroup(std::vector<double> dispersionPackedUpper, std::vector<ObservationParameter *> observedParameters)
+        : DirectlyObservedParameterGroup(std::move(observedParameters), std::move(dispersionPackedUpper)) {}
     bool hasFullyPopulatedWeightMatrix() const { return !packed_.empty(); }
     int getNumberOfParameters() const { return (int)obs_.size(); }
     const std::vector<ObservationParameter *> &observations() const { return obs_; }
