@@ -122,6 +122,14 @@ def worker_time():
         _, ms = ba._lib.gemm_tiles(A, B, C, 0, 0, 1.0, 0.0, tri, 0, reps=3)
         flop = 2.0 * (128 * mt) * (128 * nt) * K * (0.5 * (1 + 1 / mt) if tri else 1.0)
         out.append(dict(case=name, ms=ms, tflops=flop / (ms * 1e-3) / 1e12))
+    # the dominant launch of the dense route: M = W'W with W lower triangular, lower output tiles, k >= max(i, j) (LAUUM)
+    nt_ = 96
+    n = 128 * nt_
+    W = np.tril(rng.standard_normal((n, n)))
+    C = np.zeros((n, n))
+    _, ms = ba._lib.gemm_tiles(W, W, C, 1, 1, 1.0, 0.0, 1, 3, reps=2)
+    flop = sum(2.0 * 128 * 128 * (n - 128 * max(i, j)) for i in range(nt_) for j in range(i + 1))
+    out.append(dict(case='lauum %d' % n, ms=ms, tflops=flop / (ms * 1e-3) / 1e12))
     print(json.dumps(dict(stage='time', ok=True, runs=out)))
 
 
