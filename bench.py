@@ -32,8 +32,7 @@ UNIT = 'iterations/s'
 
 
 def workload(config, images=None, targets=None):
-    from tests.helpers import flat_problem
-    from tests.scenes import synthetic_scene
+    from bundle_adjustment_b200.workloads import flat_problem, synthetic_scene
     scene, _ = synthetic_scene(config, images=images, targets=targets)
     adj, flat = flat_problem(scene)
     return scene, adj, flat
@@ -127,7 +126,7 @@ def cpu_sample(config, n_full, m_full, threads, size=CPU_SAMPLE):
     dspsv + dsptri, Omega) on a scaled-down network of the same config, extrapolated to the full workload."""
     from threadpoolctl import threadpool_limits
     from oracle.oracle import Oracle, lib as olib
-    from tests.scenes import synthetic_scene
+    from bundle_adjustment_b200.workloads import synthetic_scene
     scene, _ = synthetic_scene(config, images=size[0], targets=size[1])
     with threadpool_limits(limits=threads):
         o = Oracle(scene)
@@ -148,7 +147,7 @@ def cpu_sample(config, n_full, m_full, threads, size=CPU_SAMPLE):
     n_s, m_s = o.fp.n, o.fp.m
     t_asm, t_dense, t_om = t1 - t0, t2 - t1, t3 - t2
     t_full = (t_asm + t_om) * (m_full / m_s) + t_dense * (n_full / n_s) ** 3
-    return {'value': 1.0 / t_full, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+    return {'value': 1.0 / t_full, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'extrapolated': True,
             'sample': ('one final pass of the CPU oracle on a scaled-down network of the same config (%d images x %d targets, '
                        'n = %d, %d image points): assembly+Omega %.2f s, packed dspsv+dsptri %.2f s; extrapolated to the full '
                        'workload with assembly ~ image points and factor+inverse ~ n^3 (%.3g s per pass)'
@@ -218,6 +217,7 @@ def main():
                     help='route of the headline line: dense = the blocked Cholesky + full inverse the metric names (default); '
                          'the structured (point-block) route is timed next to it and reported under "structured"')
     ap.add_argument('--no-structured', action='store_true')
+    ap.add_argument('--no-check', action='store_true', help='skip the residual / identity verification of the timed pass')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -263,6 +263,26 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def verify_pass(session, omega):
+        """Correctness of what was just timed, at THIS size and on THIS many GPUs (no CPU reference reaches n = 63 020): the defining
+        identities of dx, Qxx and Omega through the matrix-free product K x (bundle_adjustment_b200/verify.py).  Outside the timed region."""
+        from bundle_adjustment_b200 import verify
+
+        def reduce_sum(a):
+            t_ = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+            dist.all_reduce(t_)
+            return t_.cpu().numpy()
+        d_ = n - int(flat['n_unknowns'])
+        cols = verify.sample_columns(n, d_, world=world, panel=1024)
+        chk = verify.check_pass(session, columns=cols, reduce_sum=reduce_sum if world > 1 else None, omega=omega)
+        chk['ok'] = bool(chk['solve_residual'] <= 1e-8 and chk['datum_residual'] <= 1e-8 and chk['cofactor_residual'] <= 1e-8
+                         and chk['omega_rel_diff'] <= 1e-8)
+        chk['what'] = ('scaled residuals of K[lambda;dx]=[0;n], B dx=0, K Qxx e_c=e_c on %d sampled columns (first/last, panel and tile '
+                       'boundaries, one per rank), Omega = w\'Pw - n\'dx; K x matrix-free from the observations (jaicov_normal_product); '
+                       'bound 1e-8' % len(cols))
+        chk.pop('cofactor_residual_per_column', None)
+        return chk
+
     for _ in range(args.warmup):
         rc = sess.iterate(final_pass=True, apply_update=False)
         assert rc == 0, rc
@@ -284,6 +304,7 @@ def main():
     launches = (L.jaicov_launch_count() - launches0) // args.steps
     clocks = sampler.finish() if rank == 0 else None
     structured_used = sess.stats().solver_used == ba._lib.SOLVER_STRUCTURED
+    check = None if args.no_check else verify_pass(sess, sess.stats().omega)
     # max over ranks of the device time
     t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -310,6 +331,7 @@ def main():
                 sdev += st.ms_total
                 sstage += [st.ms_assembly, st.ms_factor, st.ms_solve, st.ms_inverse, st.ms_omega]
             barrier()
+            scheck = None if args.no_check else verify_pass(sess, sess.stats().omega)
             if world > 1:
                 ts = torch.tensor([sdev] + sstage.tolist(), dtype=torch.float64, device='cuda')
                 dist.all_reduce(ts, op=dist.ReduceOp.MAX)
@@ -319,7 +341,7 @@ def main():
             structured = {'ms_per_step': sdev / args.steps, 'value': args.steps / (sdev * 1e-3), 'unit': UNIT,
                           'stage_ms': dict(zip(('assembly+precondition', 'reduced system + its inverse', 'solution', 'Qxx products + placement',
                                                 'omega'), sstage.tolist())),
-                          'gemm_flop': sfl, 'tflops': sfl / ((sstage[1] + sstage[3]) * 1e-3) / 1e12,
+                          'gemm_flop': sfl, 'tflops': sfl / ((sstage[1] + sstage[3]) * 1e-3) / 1e12, 'check': scheck,
                           'note': 'same inputs and outputs (dx, complete Qxx) as the headline; JAICOV_SOLVER_AUTO picks this route when no '
                                   'observation couples two object points'}
         except ba.JaicovError as e:
@@ -426,7 +448,7 @@ def main():
                        'stage_ms': {'assembly+precondition': stage[0], 'factor': stage[1], 'solve+datum': stage[2],
                                     'inverse+Qxx epilogue': stage[3], 'omega': stage[4]},
                        'wall_ms_per_step': wall_ms_max / args.steps},
-            'roofline': roofline, 'clocks': clocks, 'gpu_launches': int(launches)}
+            'roofline': roofline, 'clocks': clocks, 'gpu_launches': int(launches), 'check': check}
     if e2e:
         line['e2e'] = e2e
     if structured:
@@ -442,6 +464,9 @@ def main():
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    bad = [c for c in (check, (structured or {}).get('check')) if c and not c['ok']]
+    if bad:
+        raise SystemExit('bench.py: the timed pass FAILED its verification: %r' % bad)
 
 
 if __name__ == '__main__':

@@ -3,6 +3,8 @@
 
 * ``csrc/``      hand-written CUDA kernels + the C ABI (``include/jaicov_b200.h``) -> ``libjaicov_b200.so``
 * ``_lib``       ctypes binding of the C ABI (``Session``)
+* ``workloads``  synthetic networks of the benchmark configurations + scene -> object graph -> flat arrays
+* ``verify``     size-independent residual checks of a final pass (matrix-free K x on the device)
 * ``host``       host-side mirror of the JAICOV API (Camera, Image, BundleAdjustment, ...): object graph, integer
                  bookkeeping and flattening -- the part that stays in Java in a real integration
 
@@ -18,5 +20,6 @@ from .host import (AffinityShearDistortionModel, BundleAdjustment, Camera, Coord
                    UnknownParameter, UpperSymmPackMatrix, ZernikeDistortionModel)
 
 from .writers import DefaultResultWriter, MatlabResultWriter
+from . import verify, workloads
 
 __all__ = [n for n in dir() if not n.startswith('_')]

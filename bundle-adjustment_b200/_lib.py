@@ -28,6 +28,7 @@ EXPORTS = [
     'jaicov_get_stats', 'jaicov_get_values', 'jaicov_get_dx', 'jaicov_get_qxx_packed', 'jaicov_get_qxx_block',
     'jaicov_get_qxx_diag', 'jaicov_get_qxx_submatrix', 'jaicov_eval_residual_jacobian', 'jaicov_get_normal_equations', 'jaicov_omega',
     'jaicov_spd_solve_invert', 'jaicov_propagate_eo_transform', 'jaicov_dlt_batch', 'jaicov_gemm_tiles',
+    'jaicov_normal_product', 'jaicov_get_preconditioner',
 ]
 
 
@@ -99,6 +100,8 @@ def load():
     L.jaicov_dlt_batch.argtypes = [i32, i32, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp]
     L.jaicov_get_normal_equations.argtypes = [vp, vp, vp]
     L.jaicov_omega.argtypes = [vp, vp, ctypes.POINTER(dbl)]
+    L.jaicov_normal_product.argtypes = [vp, i32, vp, vp, vp, ctypes.POINTER(dbl)]
+    L.jaicov_get_preconditioner.argtypes = [vp, vp]
     L.jaicov_spd_solve_invert.argtypes = [i32, i64, vp, i32, vp, i32, ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
     for name in EXPORTS:
         if name not in ('jaicov_destroy', 'jaicov_last_error', 'jaicov_launch_count'):
@@ -335,6 +338,22 @@ class Session:
         out = ctypes.c_double(0.0)
         self.check(self.L.jaicov_omega(self.h, _p(dx), ctypes.byref(out)))
         return out.value
+
+    def normal_product(self, X=None, want_rhs=True):
+        """(Y, rhs, w'Pw): Y = K X' for the rows of X ([nvec][u+d]) with the bordered normal matrix, matrix-free from the
+        observations (jaicov_normal_product); rhs = [0; A'Pw]."""
+        X = np.zeros((0, self.n)) if X is None else np.ascontiguousarray(np.atleast_2d(np.asarray(X, np.float64)))
+        Y = np.zeros_like(X)
+        rhs = np.zeros(self.n) if want_rhs else None
+        wpw = ctypes.c_double(0.0)
+        self.check(self.L.jaicov_normal_product(self.h, X.shape[0], _p(X) if X.size else None, _p(Y) if Y.size else None,
+                                                _p(rhs) if want_rhs else None, ctypes.byref(wpw) if want_rhs else None))
+        return Y, rhs, wpw.value
+
+    def preconditioner(self):
+        out = np.empty(self.n)
+        self.check(self.L.jaicov_get_preconditioner(self.h, _p(out)))
+        return out
 
 
 def shard_images(pt_ptr, world, rank):

@@ -70,6 +70,13 @@ void launch_propagate(const double *lower, int64_t ld, const double *X, int64_t 
 void launch_dlt_batch(int n_img, const int64_t *pt_ptr, const double *xy, const double *XYZ, const double *io, int nR,
                       const int32_t *restr, int max_iterations, double *out, int32_t *status, int32_t *passes, cudaStream_t s);
 
+void launch_group_product(int r, const int32_t *col, const double *var, const double *Pw, int64_t ldp, double sigma2, const double *w,
+                          int nv, int64_t n, const double *X, double *Y, double *rhs, double *wpw, cudaStream_t s);
+void launch_normal_product_points(const DevProblem &P, int nv, int64_t n, const double *X, double *Y, double *rhs, double *wpw,
+                                  cudaStream_t s);
+void launch_normal_product_rest(const DevProblem &P, int nv, int64_t n, const double *X, double *Y, double *rhs, double *wpw,
+                                const double *Bt, int64_t ldb, cudaStream_t s);
+
 void launch_img_of_obs(const int64_t *pt_ptr, int nImg, int32_t *img_of_obs, cudaStream_t s);
 size_t csc_temp_bytes(int64_t n);
 void launch_build_csc(const int32_t *obj, int64_t obs0, int64_t n, int nPt, int32_t *keys_out, int64_t *iota, void *temp,
@@ -214,6 +221,7 @@ struct jaicov_handle {
     bool obs_on_device = false;          // jaicov_set_image_points copied the observations straight to the device
     int nDatumPts = 0, free_mask = 0;
     bool prepared = false, have_qxx = false, have_neq = false;
+    bool resident = false;               // the device still holds the problem of the last estimate (values centred), although `prepared` was cleared
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
     jaicov_stats stats{};
@@ -1073,7 +1081,7 @@ int32_t jaicov_dist_init(jaicov_handle *h, int32_t rank, int32_t world, const vo
     }
     h->dist_on = true;
     if (const char *e = getenv("JAICOV_PANEL_TILES")) h->panel_tiles = std::max(1, atoi(e));
-    h->prepared = false;
+    h->prepared = false; h->resident = false;
     return JAICOV_OK;
     API_GUARD_END(h)
 }
@@ -1088,7 +1096,7 @@ int32_t jaicov_set_cameras(jaicov_handle *h, int32_t n_cam, const double *io_val
     if (n_cam == 0) {
         h->io_val.clear(); h->io_col.clear(); h->r0.clear(); h->coef_ptr.assign(1, 0);
         h->coef_type.clear(); h->coef_order.clear(); h->coef_val.clear(); h->coef_col.clear();
-        h->prepared = false;
+        h->prepared = false; h->resident = false;
         return JAICOV_OK;
     }
     API_GUARD_BEGIN
@@ -1101,7 +1109,7 @@ int32_t jaicov_set_cameras(jaicov_handle *h, int32_t n_cam, const double *io_val
     h->coef_order.assign(coef_order, coef_order + nc);
     h->coef_val.assign(coef_val, coef_val + nc);
     h->coef_col.assign(coef_col, coef_col + nc);
-    h->prepared = false;
+    h->prepared = false; h->resident = false;
     return JAICOV_OK;
     API_GUARD_END(h)
 }
@@ -1115,7 +1123,7 @@ int32_t jaicov_set_images(jaicov_handle *h, int32_t n_img, const int32_t *cam_of
     h->eo_val.assign(eo_val, eo_val + 6 * (size_t)n_img);
     h->eo_col.assign(eo_col, eo_col + 6 * (size_t)n_img);
     h->pt_ptr.assign(pt_ptr, pt_ptr + n_img + 1);
-    h->prepared = false;
+    h->prepared = false; h->resident = false;
     return JAICOV_OK;
     API_GUARD_END(h)
 }
@@ -1144,7 +1152,7 @@ int32_t jaicov_set_image_points(jaicov_handle *h, int64_t m, const int32_t *obj_
         if (rho) h->rho.assign(rho, rho + m); else h->rho.assign(m, 0.0);
         h->obs_on_device = false;
     }
-    h->prepared = false;
+    h->prepared = false; h->resident = false;
     return JAICOV_OK;
     API_GUARD_END(h)
 }
@@ -1156,7 +1164,7 @@ int32_t jaicov_set_object_points(jaicov_handle *h, int32_t n_pt, const double *x
     h->xyz.assign(xyz, xyz + 3 * (size_t)n_pt);
     h->pt_col.assign(col, col + 3 * (size_t)n_pt);
     if (is_datum) h->is_datum.assign(is_datum, is_datum + n_pt); else h->is_datum.assign(n_pt, 0);
-    h->prepared = false;
+    h->prepared = false; h->resident = false;
     return JAICOV_OK;
     API_GUARD_END(h)
 }
@@ -1168,7 +1176,7 @@ int32_t jaicov_set_scale_bars(jaicov_handle *h, int32_t n_bar, const int32_t *a,
     API_GUARD_BEGIN
     h->bar_a.assign(a, a + n_bar); h->bar_b.assign(b, b + n_bar);
     h->bar_len.assign(length, length + n_bar); h->bar_var.assign(var, var + n_bar);
-    h->prepared = false;
+    h->prepared = false; h->resident = false;
     return JAICOV_OK;
     API_GUARD_END(h)
 }
@@ -1187,7 +1195,7 @@ int32_t jaicov_add_observed_group(jaicov_handle *h, int32_t r, const int32_t *ta
     g.obs.assign(obs, obs + r);
     if (sigma_packed_upper) g.sigma.assign(sigma_packed_upper, sigma_packed_upper + (size_t)r * (r + 1) / 2);
     else g.var.assign(var, var + r);
-    h->prepared = false;
+    h->prepared = false; h->resident = false;
     return JAICOV_OK;
     API_GUARD_END(h)
 }
@@ -1198,7 +1206,7 @@ int32_t jaicov_set_datum(jaicov_handle *h, const int32_t free_flags[7], int32_t 
     h->n_unknowns = n_unknowns;
     h->n_observations = n_observations;
     h->has_datum_call = true;
-    h->prepared = false;
+    h->prepared = false; h->resident = false;
     return JAICOV_OK;
 }
 
@@ -1237,7 +1245,7 @@ int32_t jaicov_estimate(jaicov_handle *h, jaicov_progress_cb cb, void *user, vol
     h->adapted_damping = 0.0;
     h->lm_omega = 0.0;
     h->last_valid_max_abs_dx = 0.0;
-    h->prepared = false;                                     // (re)upload the caller's values
+    h->prepared = false; h->resident = false;                 // (re)upload the caller's values
     if (h->opt.use_centroid && !centroid_shift(h, false))
         return fail(h, JAICOV_ILLEGAL_ARGUMENT, "numbers of coordinate components are un-equal or zero (BA:151)");
     prepare(h);
@@ -1279,6 +1287,7 @@ int32_t jaicov_estimate(jaicov_handle *h, jaicov_progress_cb cb, void *user, vol
         status = isConverge ? JAICOV_ERROR_FREE_ESTIMATION : JAICOV_NO_CONVERGENCE;   // BA:377-384
     }
     h->prepared = false;   // device values are centred; a later call starts from the host copies
+    h->resident = (status == JAICOV_ERROR_FREE_ESTIMATION || status == JAICOV_NO_CONVERGENCE);
     h->stats.status = status;
     return status;
     API_GUARD_END(h)
@@ -1692,6 +1701,56 @@ int32_t jaicov_omega(jaicov_handle *h, const double *dx, double *omega) {
     double t = 0.0;
     for (double v : om) t += v;
     *omega = t;
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+int32_t jaicov_normal_product(jaicov_handle *h, int32_t nvec, const double *x, double *y, double *rhs, double *wpw) {
+    if (!h || nvec < 0 || (nvec > 0 && (!x || !y))) return JAICOV_ILLEGAL_ARGUMENT;
+    API_GUARD_BEGIN
+    if (!h->prepared && !h->resident) prepare(h);
+    JCHECK(cudaSetDevice(h->opt.device));
+    const DevProblem &P = h->P;
+    cudaStream_t s = h->stream;
+    const int64_t n = (int64_t)P.u + P.d;
+    const size_t np = (size_t)P.np;
+    DevBuf<double> dX, dY, dR, dW, dB;
+    dX.alloc(std::max<size_t>(1, (size_t)nvec * n)); dY.alloc(std::max<size_t>(1, (size_t)nvec * n)); dR.alloc((size_t)n); dW.alloc(1);
+    dB.alloc(8 * np);
+    if (nvec) JCHECK(cudaMemcpyAsync(dX.p, x, (size_t)nvec * n * sizeof(double), cudaMemcpyHostToDevice, s));
+    JCHECK(cudaMemsetAsync(dY.p, 0, dY.n * sizeof(double), s));
+    JCHECK(cudaMemsetAsync(dR.p, 0, (size_t)n * sizeof(double), s));
+    JCHECK(cudaMemsetAsync(dW.p, 0, sizeof(double), s));
+    JCHECK(cudaMemsetAsync(dB.p, 0, 8 * np * sizeof(double), s));
+    const bool want_rhs = rhs != nullptr || wpw != nullptr;
+    launch_pose(P, s);
+    launch_normal_product_points(P, nvec, n, dX.p, dY.p, want_rhs ? dR.p : nullptr, want_rhs ? dW.p : nullptr, s);
+    if (h->dist_on && h->dist.world > 1) {      // image shards: sum over the ranks; everything below is replicated
+        if (nvec) h->dist.allreduce_sum(dY.p, (size_t)nvec * n, s);
+        if (want_rhs) { h->dist.allreduce_sum(dR.p, (size_t)n, s); h->dist.allreduce_sum(dW.p, 1, s); }
+    }
+    if (P.d > 0) launch_datum_rows(P.xyz, P.pt_col, h->d_datum_pts.p, h->nDatumPts, h->free_mask, P.d, P.np, dB.p, s);
+    launch_normal_product_rest(P, nvec, n, dX.p, dY.p, want_rhs ? dR.p : nullptr, want_rhs ? dW.p : nullptr, dB.p, P.np, s);
+    for (Group &g : h->groups) {
+        launch_group_w(g.r, g.tptr.p, g.d_obs.p, g.w.p, s);
+        launch_group_product(g.r, g.col.p, g.d_var.p, g.Pw.p, g.ldp, P.sigma2, g.w.p, nvec, n, dX.p, dY.p, want_rhs ? dR.p : nullptr,
+                             want_rhs ? dW.p : nullptr, s);
+    }
+    JCHECK(cudaGetLastError());
+    if (nvec) JCHECK(cudaMemcpyAsync(y, dY.p, (size_t)nvec * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (rhs) JCHECK(cudaMemcpyAsync(rhs, dR.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (wpw) JCHECK(cudaMemcpyAsync(wpw, dW.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+    JCHECK(cudaStreamSynchronize(s));
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+int32_t jaicov_get_preconditioner(jaicov_handle *h, double *v) {
+    if (!h || !v || !h->V.p) return JAICOV_ILLEGAL_ARGUMENT;
+    API_GUARD_BEGIN
+    JCHECK(cudaSetDevice(h->opt.device));
+    for (int a = 0; a < h->P.d; a++) v[a] = 1.0;      // border diagonal is 0 <= EPS (BA:825-828)
+    if (h->P.u) JCHECK(cudaMemcpy(v + h->P.d, h->V.p, (size_t)h->P.u * sizeof(double), cudaMemcpyDeviceToHost));
     return JAICOV_OK;
     API_GUARD_END(h)
 }

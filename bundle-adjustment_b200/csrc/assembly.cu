@@ -15,6 +15,8 @@
 //    (bitwise reproducible); point-level sums (point x point, point x IO, n_point) are produced by a second sweep
 //    with one warp per object point over that point's observations (CSC), again as DMMA tiles;
 //  * the packed per-point / per-camera partial buffers are exactly what an image-sharded multi-GPU run all-reduces.
+#include <algorithm>
+
 #include "common.h"
 #include "model.cuh"
 
@@ -625,6 +627,145 @@ void launch_omega(const DevProblem &P, const AssemblyScratch &S, const double *d
     k_omega<<<S.omegaBlocks, kOmegaThreads, 0, s>>>(P, dxref, S.omega_partial);
     g_launch_count++;
     k_omega_final<<<1, 32, 0, s>>>(S.omega_partial, S.omegaBlocks, omega_out);
+}
+
+// ---- matrix-free product with the bordered normal matrix (verification entry point jaicov_normal_product) -------------
+// Y_v += A' P (A x_v) over this rank's image points, straight from the observations: nothing of the assembled N, its
+// factor or its inverse is read, so  K Qxx e_c = e_c  and  K [lambda; dx] = [0; n]  can be checked at ANY size (the CPU
+// oracle stops at n ~ 2e4) and for any storage layout of the factorisation.  Same model code as the assembly
+// (eval_observation); FP64 atomics (order of summation is free here: the result is only ever compared to a tolerance).
+// X, Y: [nv][n] in reference column numbering (border first); rhs (may be null): += A' P w; wpw (may be null): += w' P w.
+constexpr int kProdThreads = 128;
+
+__global__ void __launch_bounds__(kProdThreads) k_normal_product(DevProblem P, int nv, int64_t n, const double *__restrict__ X,
+                                                                 double *__restrict__ Y, double *__restrict__ rhs,
+                                                                 double *__restrict__ wpw) {
+    __shared__ double s_red[kProdThreads / 32];
+    double local = 0.0;
+    for (int64_t j = P.obs0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < P.obs1; j += (int64_t)gridDim.x * blockDim.x) {
+        const int img = P.img_of_obs[j], cam = P.cam_of_img[img], pt = P.obj_idx[j];
+        const ImgPose q = load_pose(P.pose, img);
+        const CamView cv = view_global(P, cam);
+        const int32_t *ccol = P.coef_col + P.coef_ptr[cam];
+        double a0[12 + kMaxCoef], a1[12 + kMaxCoef];
+        int32_t col[12 + kMaxCoef];
+        BaseRows r;
+        eval_observation(q, cv, P.xyz[3 * (int64_t)pt], P.xyz[3 * (int64_t)pt + 1], P.xyz[3 * (int64_t)pt + 2],
+                         P.xy[2 * j], P.xy[2 * j + 1], r, [&](int k, double v0, double v1) {
+                             a0[12 + k] = v0; a1[12 + k] = v1; col[12 + k] = ccol[k];
+                         });
+        const int ns = 12 + cv.ncoef;
+        const int32_t *pc = P.pt_col + 3 * (int64_t)pt, *ic = P.io_col + 3 * cam, *ec = P.eo_col + 6 * (int64_t)img;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            a0[i] = r.ax[i];  a1[i] = r.ay[i];  col[i] = pc[i];
+            a0[6 + i] = -r.ax[i];  a1[6 + i] = -r.ay[i];  col[6 + i] = ec[i];
+            a0[9 + i] = r.ax[4 + i];  a1[9 + i] = r.ay[4 + i];  col[9 + i] = ec[3 + i];
+            col[3 + i] = ic[i];
+        }
+        a0[3] = 1.0; a1[3] = 0.0; a0[4] = 0.0; a1[4] = 1.0; a0[5] = r.ax[3]; a1[5] = r.ay[3];
+        double p00, p01, p11;
+        point_weight(P.sigma2, P.var[2 * j], P.var[2 * j + 1], P.rho[j], p00, p01, p11);
+        if (rhs) {
+            const double t0 = p00 * r.w0 + p01 * r.w1, t1 = p01 * r.w0 + p11 * r.w1;
+            for (int s = 0; s < ns; s++)
+                if (col_active(col[s])) atomicAdd(rhs + col[s], a0[s] * t0 + a1[s] * t1);
+            local += r.w0 * t0 + r.w1 * t1;
+        }
+        for (int v = 0; v < nv; v++) {
+            const double *x = X + (int64_t)v * n;
+            double s0 = 0.0, s1 = 0.0;
+            for (int s = 0; s < ns; s++)
+                if (col_active(col[s])) { const double xv = x[col[s]]; s0 += a0[s] * xv; s1 += a1[s] * xv; }
+            const double t0 = p00 * s0 + p01 * s1, t1 = p01 * s0 + p11 * s1;
+            double *y = Y + (int64_t)v * n;
+            for (int s = 0; s < ns; s++)
+                if (col_active(col[s])) atomicAdd(y + col[s], a0[s] * t0 + a1[s] * t1);
+        }
+    }
+    if (wpw) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = local;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int i = 0; i < kProdThreads / 32; i++) s += s_red[i];
+            atomicAdd(wpw, s);
+        }
+    }
+}
+
+// scale bars (PDF:210-283) and the datum border rows (BA:493-635): K = [[0, B], [B', N]]
+__global__ void k_product_bars_border(DevProblem P, int nv, int64_t n, const double *__restrict__ X, double *__restrict__ Y,
+                                      double *__restrict__ rhs, double *__restrict__ wpw, const double *__restrict__ Bt, int64_t ldb,
+                                      int with_bars) {
+    const int tid = threadIdx.x;
+    if (with_bars && tid == 0) {
+        double om = 0.0;
+        for (int b = 0; b < P.nBar; b++) {
+            const double *A = P.xyz + 3 * (int64_t)P.bar_a[b], *B = P.xyz + 3 * (int64_t)P.bar_b[b];
+            const double dX = B[0] - A[0], dY = B[1] - A[1], dZ = B[2] - A[2];
+            const double len = sqrt(dX * dX + dY * dY + dZ * dZ);
+            const double a[6] = {-dX / len, -dY / len, -dZ / len, dX / len, dY / len, dZ / len};
+            int32_t col[6];
+            for (int i = 0; i < 3; i++) { col[i] = P.pt_col[3 * (int64_t)P.bar_a[b] + i]; col[3 + i] = P.pt_col[3 * (int64_t)P.bar_b[b] + i]; }
+            const double Pw = P.sigma2 / P.bar_var[b], w = P.bar_len[b] - len;
+            if (rhs) {
+                for (int i = 0; i < 6; i++)
+                    if (col_active(col[i])) rhs[col[i]] += a[i] * Pw * w;
+                om += w * Pw * w;
+            }
+            for (int v = 0; v < nv; v++) {
+                double s = 0.0;
+                for (int i = 0; i < 6; i++)
+                    if (col_active(col[i])) s += a[i] * X[(int64_t)v * n + col[i]];
+                for (int i = 0; i < 6; i++)
+                    if (col_active(col[i])) Y[(int64_t)v * n + col[i]] += a[i] * Pw * s;
+            }
+        }
+        if (wpw) wpw[0] += om;
+    }
+    __syncthreads();
+    // border: Y[a] = sum_c B[a][c] x[d + c];  Y[d + c] += sum_a B[a][c] x[a]   (Bt: d rows of internal columns, ldb apart)
+    const int d = P.d;
+    for (int v = 0; v < nv; v++) {
+        const double *x = X + (int64_t)v * n;
+        double *y = Y + (int64_t)v * n;
+        for (int a = 0; a < d; a++) {
+            __shared__ double red[256];
+            double s = 0.0;
+            for (int c = tid; c < P.u; c += blockDim.x) s += Bt[a * ldb + c] * x[d + c];
+            red[tid] = s;
+            __syncthreads();
+            if (tid == 0) {
+                double t = 0.0;
+                for (int i = 0; i < (int)blockDim.x; i++) t += red[i];
+                y[a] += t;
+            }
+            __syncthreads();
+        }
+        for (int c = tid; c < P.u; c += blockDim.x) {
+            double s = 0.0;
+            for (int a = 0; a < d; a++) s += Bt[a * ldb + c] * x[a];
+            y[d + c] += s;
+        }
+    }
+}
+
+void launch_normal_product_points(const DevProblem &P, int nv, int64_t n, const double *X, double *Y, double *rhs, double *wpw,
+                                  cudaStream_t s) {
+    if (P.obs1 <= P.obs0) return;
+    const int64_t nobs = P.obs1 - P.obs0;
+    const int blocks = (int)std::min<int64_t>(148 * 8, (nobs + kProdThreads - 1) / kProdThreads);
+    g_launch_count++;
+    k_normal_product<<<blocks, kProdThreads, 0, s>>>(P, nv, n, X, Y, rhs, wpw);
+}
+
+void launch_normal_product_rest(const DevProblem &P, int nv, int64_t n, const double *X, double *Y, double *rhs, double *wpw,
+                                const double *Bt, int64_t ldb, cudaStream_t s) {
+    g_launch_count++;
+    k_product_bars_border<<<1, 256, 0, s>>>(P, nv, n, X, Y, rhs, wpw, Bt, ldb, P.nBar > 0);
 }
 
 }  // namespace jaicov

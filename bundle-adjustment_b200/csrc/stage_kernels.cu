@@ -601,4 +601,54 @@ void launch_symmetrize(double *M, int64_t ld, int r, cudaStream_t s) {
     if (r) { g_launch_count++; k_symmetrize<<<r, 256, 0, s>>>(M, ld, r); }
 }
 
+// matrix-free product with a directly observed group's block of N (verification entry point jaicov_normal_product):
+// Y_v[c_i] += sum_j P_ij x_v[c_j], rhs[c_i] += sum_j P_ij w_j, wpw += w'Pw.  One CTA per row i; plain += is safe because the
+// targets of one group are distinct unknowns and the groups run one after the other on the stream.
+__global__ void __launch_bounds__(256) k_group_product(int r, const int32_t *__restrict__ col, const double *__restrict__ var,
+                                                       const double *__restrict__ Pw, int64_t ldp, double sigma2,
+                                                       const double *__restrict__ w, int nv, int64_t n, const double *__restrict__ X,
+                                                       double *__restrict__ Y, double *__restrict__ rhs, double *__restrict__ wpw) {
+    __shared__ double red[8];
+    const int i = blockIdx.x;
+    const bool act = col_active_s(col[i]);
+    auto block_sum = [&](double s) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+        __syncthreads();
+        double t = 0.0;
+        for (int k = 0; k < 8; k++) t += red[k];
+        return t;
+    };
+    for (int v = -1; v < nv; v++) {          // v = -1: the right-hand side and w'Pw
+        if (v < 0 && !rhs) continue;
+        const double *x = v < 0 ? nullptr : X + (int64_t)v * n;
+        double s = 0.0;
+        if (Pw == nullptr) {
+            if (threadIdx.x == 0) s = (sigma2 / var[i]) * (v < 0 ? w[i] : (act ? x[col[i]] : 0.0));
+        } else {
+            const double *Pi = Pw + (int64_t)i * ldp;
+            for (int j = threadIdx.x; j < r; j += blockDim.x)
+                s += Pi[j] * (v < 0 ? w[j] : (col_active_s(col[j]) ? x[col[j]] : 0.0));
+        }
+        const double t = block_sum(s);
+        if (threadIdx.x == 0) {
+            if (v < 0) {
+                if (act) rhs[col[i]] += t;
+                if (wpw) atomicAdd(wpw, w[i] * t);
+            } else if (act) {
+                Y[(int64_t)v * n + col[i]] += t;
+            }
+        }
+    }
+}
+
+void launch_group_product(int r, const int32_t *col, const double *var, const double *Pw, int64_t ldp, double sigma2, const double *w,
+                          int nv, int64_t n, const double *X, double *Y, double *rhs, double *wpw, cudaStream_t s) {
+    if (!r) return;
+    g_launch_count++;
+    k_group_product<<<r, 256, 0, s>>>(r, col, var, Pw, ldp, sigma2, w, nv, n, X, Y, rhs, wpw);
+}
+
 }  // namespace jaicov

@@ -274,6 +274,18 @@ int32_t jaicov_get_normal_equations(jaicov_handle *h, double *n_packed, double *
 /* Omega = v'Pv for a given dx (reference column order, length u+d) at the current values (getOmega, :472-491) */
 int32_t jaicov_omega(jaicov_handle *h, const double *dx, double *omega);
 
+/* Verification at any size: the product with the bordered normal matrix K = [[0, B], [B', N]] of createNormalEquation
+ * (:789-834, N = A'PA over image points PDF:285-445 + scale bars PDF:210-283 + directly observed groups PDF:447-473, B = the
+ * datum rows :493-635; no Levenberg-Marquardt damping), evaluated MATRIX-FREE from the observations at the current values:
+ * y_v = K x_v for nvec vectors x, y = [nvec][u+d] (reference column order, host buffers), rhs (may be NULL, u+d) <- [0; A'Pw],
+ * wpw (may be NULL) <- w'Pw.  Nothing of the assembled matrix, its factor or Qxx is read, so a caller can check
+ *   K [lambda; dx] = [0; n],   K Qxx e_c = e_c (columns from jaicov_get_qxx_block),   Omega = w'Pw - n'dx
+ * on configurations no CPU reference can reach (bench.py does, at every N).  Distributed handles sum their image shards
+ * (NCCL all-reduce); every rank receives the complete product.  Does not disturb Qxx / dx of the last pass. */
+int32_t jaicov_normal_product(jaicov_handle *h, int32_t nvec, const double *x, double *y, double *rhs, double *wpw);
+/* Jacobi preconditioner V of the last pass (:824-828), length u+d (1 on the border) */
+int32_t jaicov_get_preconditioner(jaicov_handle *h, double *v);
+
 /* The tensor-core tile product behind every O(n^3) stage (factor, inverse, the structured route's products), exposed
  * for parity tests and profiling:  C = alpha * op(A) op(B)' + beta * C  on 128 x 128 tiles, host buffers.
  * op(A) is (128 mt) x K: a_layout 0 = stored row-major with leading dimension lda (k contiguous), 1 = stored as K rows of

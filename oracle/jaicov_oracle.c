@@ -547,3 +547,8 @@ void orc_preconditioner(int64_t n, const double *N, double *V, double eps) {
 void orc_unpack(int64_t n, const double *Np, double *D) {
     for (int64_t c = 0; c < n; c++) for (int64_t r = 0; r <= c; r++) { double v = Np[pidx(r, c)]; D[r * n + c] = v; D[c * n + r] = v; }
 }
+
+/* dense symmetric (upper triangle read) -> packed upper, helper of the blocked route (oracle/fast_oracle.py) */
+void orc_pack(int64_t n, const double *D, double *Np) {
+    for (int64_t c = 0; c < n; c++) for (int64_t r = 0; r <= c; r++) Np[pidx(r, c)] = D[r * n + c];
+}

@@ -90,6 +90,8 @@ def lib():
         L.orc_preconditioner.argtypes = [i64, vp, vp, d]
         L.orc_unpack.restype = None
         L.orc_unpack.argtypes = [i64, vp, vp]
+        L.orc_pack.restype = None
+        L.orc_pack.argtypes = [i64, vp, vp]
         _LIB = L
     return _LIB
 
@@ -538,6 +540,11 @@ class Oracle:
         self.max_abs_dx = self.update_unknowns(dx)                 # :432
         self.last_valid_max_abs_dx = self.max_abs_dx
 
+    def _solve_packed(self, ap, b, n, invert):
+        """MathExtension.solve (MathExtension.java:338-366): dspsv [+ dsptri] on the packed bordered system -- the routines the
+        reference calls.  (oracle/fast_oracle.py overrides this one call with a blocked route for sizes these cannot finish.)"""
+        lp.solve_symm_packed(ap, b, n, invert)
+
     # ---- estimateModel, BundleAdjustment.java:203-387 ---------------------------------------------
     def estimate(self):
         fp = self.fp
@@ -563,18 +570,18 @@ class Oracle:
                 if estimate_complete:
                     if self.invert in ('REDUCED', 'PRE_ELIMINATION'):          # :261-267
                         self.reduce_normal_equation_system(N, nv)
-                        lp.solve_symm_packed(N, nv, self.num_rows_reduced(), True)
+                        self._solve_packed(N, nv, self.num_rows_reduced(), True)
                     else:
-                        lp.solve_symm_packed(N, nv, n, self.invert == 'FULL')
+                        self._solve_packed(N, nv, n, self.invert == 'FULL')
                     L.orc_apply_precondition(n, V.ctypes.data, N.ctypes.data, nv.ctypes.data)
                     self.Qxx = N
                 else:
                     if self.invert == 'PRE_ELIMINATION':                       # :283-291
                         self.reduce_normal_equation_system(N, nv)
-                        lp.solve_symm_packed(N, nv, self.num_rows_reduced(), False)
+                        self._solve_packed(N, nv, self.num_rows_reduced(), False)
                         self.extract_reduced_parameters(N, nv)
                     else:
-                        lp.solve_symm_packed(N, nv, n, False)
+                        self._solve_packed(N, nv, n, False)
                     L.orc_apply_precondition(n, V.ctypes.data, None, nv.ctypes.data)
             except (lp.MatrixSingularException, lp.MatrixNotSPDException, ValueError):
                 self.status = SINGULAR_MATRIX
