@@ -278,7 +278,7 @@ def main():
         chk['ok'] = bool(chk['solve_residual'] <= 1e-8 and chk['datum_residual'] <= 1e-8 and chk['cofactor_residual'] <= 1e-8
                          and chk['omega_rel_diff'] <= 1e-8)
         chk['what'] = ('scaled residuals of K[lambda;dx]=[0;n], B dx=0, K Qxx e_c=e_c on %d sampled columns (first/last, panel and tile '
-                       'boundaries, one per rank), Omega = w\'Pw - n\'dx; K x matrix-free from the observations (jaicov_normal_product); '
+                       'boundaries, one per rank), Omega = w\'Pw - 2n\'dx + dx\'N dx; K x matrix-free from the observations (jaicov_normal_product); '
                        'bound 1e-8' % len(cols))
         chk.pop('cofactor_residual_per_column', None)
         return chk

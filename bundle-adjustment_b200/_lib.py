@@ -35,7 +35,7 @@ EXPORTS = [
 class Options(ctypes.Structure):
     _fields_ = [('invert_mode', ctypes.c_int32), ('estimation_type', ctypes.c_int32), ('max_iterations', ctypes.c_int32),
                 ('use_centroid', ctypes.c_int32), ('apply_aposteriori', ctypes.c_int32), ('device', ctypes.c_int32),
-                ('solver', ctypes.c_int32), ('reserved0', ctypes.c_int32),
+                ('solver', ctypes.c_int32), ('n_devices', ctypes.c_int32),
                 ('sigma2apriori', ctypes.c_double), ('damping_value', ctypes.c_double)]
 
 
@@ -152,7 +152,7 @@ class Session:
     ``flat`` is a dict of flat arrays in the layout of include/jaicov_b200.h (see ``set_problem``)."""
 
     def __init__(self, invert_mode=INVERT_FULL, estimation_type=L2NORM, max_iterations=5000, use_centroid=True,
-                 apply_aposteriori=True, device=0, sigma2apriori=1.0, damping_value=0.0, solver=SOLVER_AUTO):
+                 apply_aposteriori=True, device=0, sigma2apriori=1.0, damping_value=0.0, solver=SOLVER_AUTO, n_devices=1):
         self.L = load()
         self.opt = Options()
         self.L.jaicov_default_options(ctypes.byref(self.opt))
@@ -163,6 +163,7 @@ class Session:
         self.opt.apply_aposteriori = int(apply_aposteriori)
         self.opt.device = device
         self.opt.solver = solver
+        self.opt.n_devices = n_devices
         self.opt.sigma2apriori = sigma2apriori
         self.opt.damping_value = damping_value
         self.h = ctypes.c_void_p()

@@ -12,11 +12,13 @@
 #include <new>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.h"
 #include "dense_driver.hpp"
 #include "dist.h"
+#include "model.cuh"
 
 namespace jaicov {
 
@@ -111,10 +113,10 @@ struct DevCache {
             }
         return nullptr;
     }
-    void give(size_t bytes, void *p) {
+    void give(size_t bytes, void *p, int dev) {
         // bounded by count only (a handle holds ~100 buffers); memory pressure is handled where it shows: a failed
-        // cudaMalloc purges the cache and retries (DevBuf::alloc)
-        const int dev = current_device();
+        // cudaMalloc purges the cache and retries (DevBuf::alloc).  `dev` is the device the buffer was allocated on (the
+        // caller's current device may be another one by the time a handle is destroyed).
         std::lock_guard<std::mutex> lock(mu);
         if (free_list.size() >= 1024) {   // drop the oldest entry
             cudaFree(free_list.front().p);
@@ -136,10 +138,12 @@ template <class T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    int dev = -1;                              // device the buffer lives on
     void alloc(size_t count) {
         release();
         n = count;
         if (!count) return;
+        dev = DevCache::current_device();
         const size_t bytes = count * sizeof(T);
         if (bytes >= DevCache::kMinBytes) {
             p = static_cast<T *>(g_cache.take(bytes));
@@ -163,7 +167,7 @@ struct DevBuf {
     }
     void release() {
         if (p) {
-            if (n * sizeof(T) >= DevCache::kMinBytes) g_cache.give(n * sizeof(T), p);
+            if (n * sizeof(T) >= DevCache::kMinBytes) g_cache.give(n * sizeof(T), p, dev);
             else cudaFree(p);
         }
         p = nullptr;
@@ -213,7 +217,9 @@ struct jaicov_handle {
         d_campos_col, d_cam_of_img, d_eo_col, d_obj_idx, d_img_of_obs, d_pt_col, d_bar_a, d_bar_b, d_img_work_ptr, d_datum_pts;
     DevBuf<int64_t> d_pt_ptr, d_pt_obs_ptr, d_pt_obs;
     DevBuf<WorkItem> d_work;
-    DevBuf<double> d_img_partial, d_cam_partial, d_pt_partial, d_omega_partial;
+    DevBuf<double> d_img_partial, d_cam_partial, d_pt_partial, d_omega_partial, d_coef_r0pow, d_rw, d_dxp;
+    std::vector<int32_t> kbase_host;     // start of every camera's raw parameters in the camera-parameter list
+    std::vector<PtGroup> pt_groups;      // camera groups of the by-point sweep (one group unless the cameras have > 68 raw parameters in total)
     DevBuf<double> M, W, Dinv, rhs, V, Bt, Btv, Rt, H, Tq, small, dxref, omega_parts;
     DevBuf<int> info;
     DevBuf<unsigned long long> upd;
@@ -221,14 +227,22 @@ struct jaicov_handle {
     bool obs_on_device = false;          // jaicov_set_image_points copied the observations straight to the device
     int nDatumPts = 0, free_mask = 0;
     bool prepared = false, have_qxx = false, have_neq = false;
+    bool gathered_qxx = false;           // single-process multi-GPU, device 0: M holds the gathered Qxx (lower) instead of the factor
     bool resident = false;               // the device still holds the problem of the last estimate (values centred), although `prepared` was cleared
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
     jaicov_stats stats{};
     double centroid[3] = {0, 0, 0};
     // multi-GPU (one process per GPU); the communicator is process-wide and outlives the handle
-    DistContext &dist = g_dist;
+    DistContext &dist;
     bool dist_on = false;
+    // single-process multi-GPU handle (jaicov_options.n_devices > 1): this handle only fans the calls out to one ordinary
+    // distributed handle per device, each with its own communicator of one ncclCommInitAll clique and its own host thread
+    std::vector<jaicov_handle *> sub;
+    std::vector<DistContext *> sub_ctx;
+    bool group_ready = false;
+    jaicov_handle() : dist(g_dist) {}
+    explicit jaicov_handle(DistContext &d) : dist(d) {}
     int panel_tiles = 8;                 // block-column panel width of the distributed Cholesky, in 128-tiles (1024 columns:
                                          // measured 1628 ms vs 1697 ms for 512 at config 5 on 2 GPUs)
     DevBuf<double> Xl;                   // np x (128 * ntc): this rank's column tiles of the inverse
@@ -420,6 +434,25 @@ void prepare(jaicov_handle *h) {
     P.nCam = (int)h->r0.size();
     P.nCoef = (int)h->coef_val.size();
     if (h->coef_ptr.empty()) h->coef_ptr.assign(1, 0);
+    if ((int)h->coef_ptr.size() != P.nCam + 1 || h->coef_ptr[0] != 0 || h->coef_ptr.back() != P.nCoef)
+        throw std::runtime_error("coef_ptr must have n_cam + 1 entries from 0 to the number of coefficients");
+    for (int c = 0; c < P.nCam; c++)
+        if (h->coef_ptr[c + 1] < h->coef_ptr[c]) throw std::runtime_error("coef_ptr is not monotone");
+    for (int k = 0; k < P.nCoef; k++) {
+        const int t = h->coef_type[k];
+        if (t != JAICOV_PT_RADIAL_A && t != JAICOV_PT_TANGENTIAL_B && t != JAICOV_PT_TANGENTIAL_BX && t != JAICOV_PT_TANGENTIAL_BY &&
+            t != JAICOV_PT_AFFINITY_CX && t != JAICOV_PT_AFFINITY_CY && t != JAICOV_PT_DISTANCE_D && t != JAICOV_PT_ZERNIKE_X &&
+            t != JAICOV_PT_ZERNIKE_Y && t != JAICOV_PT_ZERNIKE_Z)
+            throw std::runtime_error("coef_type: not a distortion ParameterType id");
+        if (h->coef_order[k] < 0 || h->coef_order[k] > 100000) throw std::runtime_error("coef_order out of range");
+        // the evaluation consumes Cx,Cy and Bx,By as pairs (AffinityShear... / Tangential...Factory): each must be followed by its partner
+    }
+    for (int c = 0; c < P.nCam; c++)
+        for (int k = h->coef_ptr[c]; k < h->coef_ptr[c + 1]; k++) {
+            const int t = h->coef_type[k];
+            if ((t == JAICOV_PT_AFFINITY_CX || t == JAICOV_PT_TANGENTIAL_BX) && (k + 1 >= h->coef_ptr[c + 1] || h->coef_type[k + 1] != t + 1))
+                throw std::runtime_error("coef_type: Cx / Bx must be followed by Cy / By of the same camera");
+        }
     std::vector<int32_t> zm(P.nCoef, 0), zptr(P.nCoef + 1, 0), zp;
     std::vector<double> zc;
     int maxcoef = 0;
@@ -446,15 +479,50 @@ void prepare(jaicov_handle *h) {
     P.kRaw = kbase[P.nCam];
     h->S = AssemblyScratch();
     h->S.ntImg = (9 + maxcoef + 1 + 7) / 8;
-    h->S.ntPt = (3 + P.kRaw + 1 + 7) / 8;
     h->S.kcMax = 3 + maxcoef;
-    if (h->S.ntPt > 8) throw std::runtime_error("too many camera parameters in total (by-point Gram limited to 64 columns)");
+    if (h->S.ntImg > 9) throw std::runtime_error("more than 62 distortion coefficients in one camera are not supported (by-image Gram row of 72 columns)");
+    // camera groups of the by-point sweep: consecutive cameras while [X Y Z | raw parameters | w] fits 72 Gram columns
+    h->pt_groups.clear();
+    h->S.ntPt = 1;
+    for (int c = 0; c < P.nCam;) {
+        PtGroup g{c, c, 0, 0};
+        while (g.cam1 < P.nCam && (g.cam1 == g.cam0 || 3 + g.kraw + (kbase[g.cam1 + 1] - kbase[g.cam1]) + 1 <= 72)) {
+            g.kraw += kbase[g.cam1 + 1] - kbase[g.cam1];
+            g.cam1++;
+        }
+        g.nt = (3 + g.kraw + 1 + 7) / 8;
+        h->S.ntPt = std::max(h->S.ntPt, g.nt);
+        h->pt_groups.push_back(g);
+        c = g.cam1;
+    }
+    if (h->pt_groups.empty()) h->pt_groups.push_back(PtGroup{0, 0, 0, 1});
+    // r0^(2 order) of every coefficient (the constant of the radial / distance polynomials; repeated multiplication like the kernels)
+    std::vector<double> r0pow(std::max(P.nCoef, 1), 0.0);
+    for (int c = 0; c < P.nCam; c++)
+        for (int k = h->coef_ptr[c]; k < h->coef_ptr[c + 1]; k++) r0pow[k] = ipow(h->r0[c] * h->r0[c], h->coef_order[k]);
     // ---- images / observations -----------------------------------------------------------------------------------
     P.nImg = (int)h->cam_of_img.size();
     P.m = h->m_obs;
     if (h->pt_ptr.empty()) h->pt_ptr.assign(1, 0);
     if (h->pt_ptr.back() != P.m) throw std::runtime_error("pt_ptr does not cover the image points");
     P.nPt = (int)(h->xyz.size() / 3);
+    // a foreign caller's bad index must come back as JAICOV_ILLEGAL_ARGUMENT, not as an out-of-bounds device read (which is
+    // sticky for the CUDA context): O(nImg + nBar + nCoef) range / monotonicity checks on everything a kernel indexes with
+    if ((int)h->pt_ptr.size() != P.nImg + 1 || h->pt_ptr[0] != 0) throw std::runtime_error("pt_ptr must have n_img + 1 entries starting at 0");
+    for (int i = 0; i < P.nImg; i++) {
+        if (h->pt_ptr[i + 1] < h->pt_ptr[i]) throw std::runtime_error("pt_ptr is not monotone");
+        if (h->cam_of_img[i] < 0 || h->cam_of_img[i] >= P.nCam) throw std::runtime_error("cam_of_img: camera index out of range");
+    }
+    for (size_t b = 0; b < h->bar_a.size(); b++)
+        if (h->bar_a[b] < 0 || h->bar_a[b] >= P.nPt || h->bar_b[b] < 0 || h->bar_b[b] >= P.nPt)
+            throw std::runtime_error("scale bar end point index out of range");
+    for (const Group &g : h->groups)
+        for (int i = 0; i < g.r; i++) {
+            const int k = g.kind[i], ix = g.index[i], cp = g.comp[i];
+            const bool ok = (k == 0 && ix >= 0 && ix < P.nPt && cp >= 0 && cp < 3) || (k == 1 && ix >= 0 && ix < P.nCam && cp >= 0 && cp < 3) ||
+                            (k == 2 && ix >= 0 && ix < P.nCoef) || (k == 3 && ix >= 0 && ix < P.nImg && cp >= 0 && cp < 6);
+            if (!ok) throw std::runtime_error("observed group: target kind / index / component out of range");
+        }
     // image shard of this rank: contiguous image ranges balanced by observation count
     {
         int32_t i0 = 0, i1 = P.nImg;
@@ -520,16 +588,17 @@ void prepare(jaicov_handle *h) {
     // ---- upload --------------------------------------------------------------------------------------------------
     h->d_io_val.upload(h->io_val); h->d_io_col.upload(h->io_col); h->d_r0.upload(h->r0);
     h->d_coef_ptr.upload(h->coef_ptr); h->d_coef_type.upload(h->coef_type); h->d_coef_order.upload(h->coef_order);
-    h->d_coef_val.upload(h->coef_val); h->d_coef_col.upload(h->coef_col);
+    h->d_coef_val.upload(h->coef_val); h->d_coef_col.upload(h->coef_col); h->d_coef_r0pow.upload(r0pow);
     h->d_zern_m.upload(zm); h->d_zern_ptr.upload(zptr); h->d_zern_p.upload(zp); h->d_zern_c.upload(zc);
     h->d_cam_kbase.upload(kbase); h->d_campos_col.upload(campos);
+    h->kbase_host = kbase;
     h->d_cam_of_img.upload(h->cam_of_img); h->d_eo_val.upload(h->eo_val); h->d_eo_col.upload(h->eo_col);
     h->d_pose.alloc((size_t)std::max(P.nImg, 1) * 16);
     h->d_xyz.upload(h->xyz); h->d_pt_col.upload(h->pt_col);
     h->d_bar_a.upload(h->bar_a); h->d_bar_b.upload(h->bar_b); h->d_bar_len.upload(h->bar_len); h->d_bar_var.upload(h->bar_var);
     h->d_work.upload(work); h->d_img_work_ptr.upload(img_work_ptr); h->d_datum_pts.upload(datum_pts);
     P.io_val = h->d_io_val.p; P.io_col = h->d_io_col.p; P.r0 = h->d_r0.p; P.coef_ptr = h->d_coef_ptr.p;
-    P.coef_type = h->d_coef_type.p; P.coef_order = h->d_coef_order.p; P.coef_col = h->d_coef_col.p; P.coef_val = h->d_coef_val.p;
+    P.coef_type = h->d_coef_type.p; P.coef_order = h->d_coef_order.p; P.coef_col = h->d_coef_col.p; P.coef_val = h->d_coef_val.p; P.coef_r0pow = h->d_coef_r0pow.p;
     P.zern_m = h->d_zern_m.p; P.zern_ptr = h->d_zern_ptr.p; P.zern_p = h->d_zern_p.p; P.zern_c = h->d_zern_c.p;
     P.cam_kbase = h->d_cam_kbase.p; P.campos_col = h->d_campos_col.p;
     P.cam_of_img = h->d_cam_of_img.p; P.eo_val = h->d_eo_val.p; P.eo_col = h->d_eo_col.p; P.pt_ptr = h->d_pt_ptr.p;
@@ -547,8 +616,12 @@ void prepare(jaicov_handle *h) {
     h->d_cam_sum.alloc((size_t)std::max(P.nCam, 1) * S.kcMax * (S.kcMax + 1));
     S.cam_sum = h->d_cam_sum.p;
     h->d_pt_partial.alloc((size_t)std::max(P.nPt, 1) * 3 * NCp);
-    S.omegaBlocks = (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (P.obs1 - P.obs0 + 255) / 256));
-    h->d_omega_partial.alloc(S.omegaBlocks + 2);
+    h->d_omega_partial.alloc((size_t)std::max(S.nWork, 1) + 2);
+    h->d_dxp.alloc((size_t)std::max(P.nPt, 1) * 3);
+    S.dxp = h->d_dxp.p;
+    h->d_rw.alloc((size_t)std::max<int64_t>(P.m, 1) * 3);
+    P.rw = h->d_rw.p;
+    launch_obs_weights(P, h->d_rw.p, h->stream);
     S.img_partial = h->d_img_partial.p; S.cam_partial = h->d_cam_partial.p; S.pt_partial = h->d_pt_partial.p;
     S.omega_partial = h->d_omega_partial.p;
     // ---- solver route --------------------------------------------------------------------------------------------
@@ -670,17 +743,25 @@ void assemble(jaicov_handle *h, bool sparse_clear = false) {
     JCHECK(cudaMemsetAsync(h->rhs.p, 0, np * sizeof(double), s));
     JCHECK(cudaMemsetAsync(h->Bt.p, 0, 8 * np * sizeof(double), s));
     launch_pose(P, s);
-    launch_assemble_local(P, h->S, h->M.p, h->rhs.p, s);
-    if (h->dist_on && h->dist.world > 1) {
+    launch_assemble_images(P, h->S, h->M.p, h->rhs.p, s);
+    const bool multi = h->dist_on && h->dist.world > 1;
+    const AssemblyScratch &S = h->S;
+    for (size_t gi = 0; gi < h->pt_groups.size(); gi++) {
+        const PtGroup &g = h->pt_groups[gi];
+        launch_by_point(P, S, g, s);
         // the only exchange of the assembly: sum the shared pieces over the image shards
-        const AssemblyScratch &S = h->S;
-        h->dist.allreduce_sum(S.pt_partial, (size_t)P.nPt * 3 * 8 * S.ntPt, s);
-        h->dist.allreduce_sum(S.cam_sum, (size_t)P.nCam * S.kcMax * (S.kcMax + 1), s);
-        h->dist.allreduce_sum(h->rhs.p, (size_t)P.np, s);
-        if (h->strip_row0 >= 0)
-            h->dist.allreduce_sum(h->M.p + (size_t)h->strip_row0 * np, ((size_t)P.np - h->strip_row0) * np, s);
+        if (multi) h->dist.allreduce_sum(S.pt_partial, (size_t)P.nPt * 3 * 8 * g.nt, s);
+        if (gi == 0) {
+            if (multi) {
+                h->dist.allreduce_sum(S.cam_sum, (size_t)P.nCam * S.kcMax * (S.kcMax + 1), s);
+                h->dist.allreduce_sum(h->rhs.p, (size_t)P.np, s);
+                if (h->strip_row0 >= 0)
+                    h->dist.allreduce_sum(h->M.p + (size_t)h->strip_row0 * np, ((size_t)P.np - h->strip_row0) * np, s);
+            }
+            launch_camera_scatter(P, S, h->M.p, h->rhs.p, s);
+        }
+        launch_point_scatter(P, S, g, h->kbase_host[g.cam0], h->M.p, h->rhs.p, s);
     }
-    launch_assemble_shared(P, h->S, h->M.p, h->rhs.p, s);
     launch_scale_bars(P, h->M.p, h->rhs.p, s);
     for (Group &g : h->groups) {
         launch_group_w(g.r, g.tptr.p, g.d_obs.p, g.w.p, s);
@@ -690,6 +771,7 @@ void assemble(jaicov_handle *h, bool sparse_clear = false) {
     JCHECK(cudaGetLastError());
     h->have_neq = true;
     h->have_qxx = false;
+    h->gathered_qxx = false;
 }
 
 struct PassResult {
@@ -986,6 +1068,75 @@ bool centroid_shift(jaicov_handle *h, bool invert) {
     return true;
 }
 
+// BundleAdjustment.interrupt (:240-245, :320-325): reads and clears the caller's flag.  Several GPUs: the decision must be the same
+// on every rank (a rank that leaves the loop alone would leave the others waiting in a collective), so the ranks agree on it
+// -- one scalar all-reduce; either every rank passes a flag or none does.
+bool interrupted(jaicov_handle *h, volatile int32_t *flag) {
+    if (!flag) return false;
+    int local = 0;
+    if (*flag) { *flag = 0; local = 1; }
+    if (h->dist_on && h->dist.world > 1) {
+        double v = local, *dflag = h->small.p + 121;
+        JCHECK(cudaMemcpyAsync(dflag, &v, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        h->dist.allreduce_sum(dflag, 1, h->stream);
+        JCHECK(cudaMemcpyAsync(&v, dflag, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        JCHECK(cudaStreamSynchronize(h->stream));
+        local = v != 0.0;
+    }
+    return local != 0;
+}
+
+// ---- single-process multi-GPU handle -----------------------------------------------------------------------------------------
+bool is_group(const jaicov_handle *h) { return h && !h->sub.empty(); }
+
+// f(sub handle, index) on every device's handle: index 0 on the CALLING thread (progress callbacks stay on it, as the ABI
+// promises), the others on one host thread each.  Result: the common return code, or the first differing (failing) one with its
+// error text copied to the group handle.
+template <class F>
+int group_run(jaicov_handle *g, F &&f) {
+    const size_t n = g->sub.size();
+    std::vector<int> rc(n, JAICOV_OK);
+    std::vector<std::thread> th;
+    th.reserve(n);
+    for (size_t i = 1; i < n; i++) th.emplace_back([&rc, &f, g, i] { rc[i] = f(g->sub[i], (int)i); });
+    rc[0] = f(g->sub[0], 0);
+    for (auto &t : th) t.join();
+    for (size_t i = 0; i < n; i++)
+        if (rc[i] != rc[0] || (rc[i] < 0 && rc[i] != JAICOV_NO_CONVERGENCE && rc[i] != JAICOV_SINGULAR_MATRIX && rc[i] != JAICOV_INTERRUPT)) {
+            const size_t k = rc[i] != rc[0] ? (rc[i] < rc[0] ? i : 0) : i;
+            g->err = "device " + std::to_string(g->sub[k]->opt.device) + ": " + g->sub[k]->err;
+            return rc[k];
+        }
+    return rc[0];
+}
+
+// communicators of the clique, created by the first computing call (one ncclCommInitAll from the calling thread)
+void group_ensure(jaicov_handle *g) {
+    if (g->group_ready) return;
+    const int n = (int)g->sub.size();
+    if (usable_devices() < g->opt.device + n)
+        throw CudaError{cudaErrorNoDevice, "not enough sm_100 devices for jaicov_options.n_devices (jaicov_b200 has no CPU path)", __FILE__, __LINE__};
+    std::vector<int> devs(n);
+    std::vector<void *> comms(n, nullptr);
+    for (int i = 0; i < n; i++) devs[i] = g->opt.device + i;
+    nccl_comm_init_all(comms.data(), n, devs.data());
+    for (int i = 0; i < n; i++) {
+        JCHECK(cudaSetDevice(devs[i]));
+        g->sub_ctx[i]->adopt(i, n, comms[i]);
+    }
+    JCHECK(cudaSetDevice(devs[0]));
+    g->group_ready = true;
+}
+
+#define GROUP_FORWARD(h, CALL)                                        \
+    if (is_group(h)) {                                                \
+        for (jaicov_handle *s_ : (h)->sub) {                          \
+            const int rc_ = CALL;                                     \
+            if (rc_ != JAICOV_OK) { (h)->err = s_->err; return rc_; } \
+        }                                                             \
+        return JAICOV_OK;                                             \
+    }
+
 }  // namespace
 
 // =====================================================================================================================
@@ -1000,7 +1151,7 @@ int32_t jaicov_default_options(jaicov_options *opt) {
     opt->apply_aposteriori = 1;
     opt->device = 0;
     opt->solver = JAICOV_SOLVER_AUTO;
-    opt->reserved0 = 0;
+    opt->n_devices = 1;
     opt->sigma2apriori = 1.0;
     opt->damping_value = 0.0;
     return JAICOV_OK;
@@ -1019,17 +1170,48 @@ int32_t jaicov_create(const jaicov_options *opt, jaicov_handle **out) {
     if (opt->invert_mode < JAICOV_INVERT_NONE || opt->invert_mode > JAICOV_INVERT_REDUCED) return JAICOV_ILLEGAL_ARGUMENT;
     if (opt->estimation_type != JAICOV_L2NORM && opt->estimation_type != JAICOV_SIMULATION) return JAICOV_ILLEGAL_ARGUMENT;
     if (opt->solver < JAICOV_SOLVER_AUTO || opt->solver > JAICOV_SOLVER_STRUCTURED) return JAICOV_ILLEGAL_ARGUMENT;
+    if (opt->n_devices < 0 || opt->n_devices > 64 || opt->device < 0) return JAICOV_ILLEGAL_ARGUMENT;
     jaicov_handle *h = new (std::nothrow) jaicov_handle();
     if (!h) return JAICOV_OUT_OF_MEMORY;
     h->opt = *opt;
+    if (opt->n_devices > 1) {
+        // single-process multi-GPU: one ordinary distributed handle per device [device, device + n_devices)
+        try {
+            for (int i = 0; i < opt->n_devices; i++) {
+                DistContext *ctx = new DistContext();
+                ctx->rank = i;
+                ctx->world = opt->n_devices;
+                h->sub_ctx.push_back(ctx);
+                jaicov_handle *sh = new jaicov_handle(*ctx);
+                sh->opt = *opt;
+                sh->opt.device = opt->device + i;
+                sh->opt.n_devices = 1;
+                sh->dist_on = true;
+                if (const char *e = getenv("JAICOV_PANEL_TILES")) sh->panel_tiles = std::max(1, atoi(e));
+                h->sub.push_back(sh);
+            }
+        } catch (const std::bad_alloc &) {
+            jaicov_destroy(h);
+            return JAICOV_OUT_OF_MEMORY;
+        }
+    }
     *out = h;
     return JAICOV_OK;
 }
 
 void jaicov_destroy(jaicov_handle *h) {
     if (!h) return;
+    if (is_group(h) || !h->sub_ctx.empty()) {
+        for (jaicov_handle *sh : h->sub) jaicov_destroy(sh);
+        for (DistContext *ctx : h->sub_ctx) {
+            if (ctx->comm && usable_devices() > 0) { cudaSetDevice(h->opt.device + ctx->rank); cudaDeviceSynchronize(); ctx->destroy(); }
+            delete ctx;
+        }
+        delete h;
+        return;
+    }
+    if (usable_devices() > 0) cudaSetDevice(h->opt.device);      // buffers may exist without a stream (set_* before the first pass)
     if (h->stream) {
-        cudaSetDevice(h->opt.device);
         cudaStreamSynchronize(h->stream);
         if (h->dist_on) cudaDeviceSynchronize();   // the process-wide communicator stays
         for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -1068,6 +1250,7 @@ int32_t jaicov_nccl_unique_id(void *out128) {
 
 int32_t jaicov_dist_init(jaicov_handle *h, int32_t rank, int32_t world, const void *nccl_id128) {
     if (!h || world < 1 || rank < 0 || rank >= world || !nccl_id128) return JAICOV_ILLEGAL_ARGUMENT;
+    if (is_group(h) || &h->dist != &g_dist) return fail(h, JAICOV_ILLEGAL_ARGUMENT, "handle already spans several devices of this process (jaicov_options.n_devices)");
     API_GUARD_BEGIN
     if (usable_devices() == 0) throw CudaError{cudaErrorNoDevice, "no sm_100 device: jaicov_b200 has no CPU path", __FILE__, __LINE__};
     JCHECK(cudaSetDevice(h->opt.device));
@@ -1090,6 +1273,7 @@ int32_t jaicov_set_cameras(jaicov_handle *h, int32_t n_cam, const double *io_val
                            const int32_t *coef_ptr, const int32_t *coef_type, const int32_t *coef_order, const double *coef_val,
                            const int32_t *coef_col) {
     if (!h || n_cam < 0) return JAICOV_ILLEGAL_ARGUMENT;
+    GROUP_FORWARD(h, jaicov_set_cameras(s_, n_cam, io_val, io_col, r0, coef_ptr, coef_type, coef_order, coef_val, coef_col))
     if (n_cam > 0 && (!io_val || !io_col || !r0 || !coef_ptr)) return fail(h, JAICOV_ILLEGAL_ARGUMENT, "jaicov_set_cameras: null array");
     if (n_cam > 0 && coef_ptr[n_cam] > 0 && (!coef_type || !coef_order || !coef_val || !coef_col))
         return fail(h, JAICOV_ILLEGAL_ARGUMENT, "jaicov_set_cameras: null coefficient array");
@@ -1117,6 +1301,7 @@ int32_t jaicov_set_cameras(jaicov_handle *h, int32_t n_cam, const double *io_val
 int32_t jaicov_set_images(jaicov_handle *h, int32_t n_img, const int32_t *cam_of_img, const double *eo_val, const int32_t *eo_col,
                           const int64_t *pt_ptr) {
     if (!h || n_img < 0) return JAICOV_ILLEGAL_ARGUMENT;
+    GROUP_FORWARD(h, jaicov_set_images(s_, n_img, cam_of_img, eo_val, eo_col, pt_ptr))
     if (!pt_ptr || (n_img > 0 && (!cam_of_img || !eo_val || !eo_col))) return fail(h, JAICOV_ILLEGAL_ARGUMENT, "jaicov_set_images: null array");
     API_GUARD_BEGIN
     h->cam_of_img.assign(cam_of_img, cam_of_img + n_img);
@@ -1131,6 +1316,8 @@ int32_t jaicov_set_images(jaicov_handle *h, int32_t n_img, const int32_t *cam_of
 int32_t jaicov_set_image_points(jaicov_handle *h, int64_t m, const int32_t *obj_idx, const double *xy, const double *var,
                                 const double *rho) {
     if (!h || m < 0) return JAICOV_ILLEGAL_ARGUMENT;
+    if (is_group(h))   // every device takes its copy over its own PCIe link, in parallel
+        return group_run(h, [&](jaicov_handle *sh, int) { return (int)jaicov_set_image_points(sh, m, obj_idx, xy, var, rho); });
     API_GUARD_BEGIN
     if (m > 0 && (!obj_idx || !xy || !var)) return JAICOV_ILLEGAL_ARGUMENT;
     h->m_obs = m;
@@ -1159,6 +1346,7 @@ int32_t jaicov_set_image_points(jaicov_handle *h, int64_t m, const int32_t *obj_
 
 int32_t jaicov_set_object_points(jaicov_handle *h, int32_t n_pt, const double *xyz, const int32_t *col, const uint8_t *is_datum) {
     if (!h || n_pt < 0) return JAICOV_ILLEGAL_ARGUMENT;
+    GROUP_FORWARD(h, jaicov_set_object_points(s_, n_pt, xyz, col, is_datum))
     if (n_pt > 0 && (!xyz || !col)) return fail(h, JAICOV_ILLEGAL_ARGUMENT, "jaicov_set_object_points: null array");
     API_GUARD_BEGIN
     h->xyz.assign(xyz, xyz + 3 * (size_t)n_pt);
@@ -1172,6 +1360,7 @@ int32_t jaicov_set_object_points(jaicov_handle *h, int32_t n_pt, const double *x
 int32_t jaicov_set_scale_bars(jaicov_handle *h, int32_t n_bar, const int32_t *a, const int32_t *b, const double *length,
                               const double *var) {
     if (!h || n_bar < 0) return JAICOV_ILLEGAL_ARGUMENT;
+    GROUP_FORWARD(h, jaicov_set_scale_bars(s_, n_bar, a, b, length, var))
     if (n_bar > 0 && (!a || !b || !length || !var)) return fail(h, JAICOV_ILLEGAL_ARGUMENT, "jaicov_set_scale_bars: null array");
     API_GUARD_BEGIN
     h->bar_a.assign(a, a + n_bar); h->bar_b.assign(b, b + n_bar);
@@ -1184,6 +1373,7 @@ int32_t jaicov_set_scale_bars(jaicov_handle *h, int32_t n_bar, const int32_t *a,
 int32_t jaicov_add_observed_group(jaicov_handle *h, int32_t r, const int32_t *target_kind, const int32_t *target_index,
                                   const int32_t *target_comp, const double *obs, const double *var, const double *sigma_packed_upper) {
     if (!h || r <= 0 || (!var && !sigma_packed_upper)) return JAICOV_ILLEGAL_ARGUMENT;
+    GROUP_FORWARD(h, jaicov_add_observed_group(s_, r, target_kind, target_index, target_comp, obs, var, sigma_packed_upper))
     if (!target_kind || !target_index || !target_comp || !obs) return fail(h, JAICOV_ILLEGAL_ARGUMENT, "jaicov_add_observed_group: null array");
     API_GUARD_BEGIN
     h->groups.emplace_back();
@@ -1202,6 +1392,7 @@ int32_t jaicov_add_observed_group(jaicov_handle *h, int32_t r, const int32_t *ta
 
 int32_t jaicov_set_datum(jaicov_handle *h, const int32_t free_flags[7], int32_t n_unknowns, int32_t n_observations) {
     if (!h || !free_flags || n_unknowns < 0) return JAICOV_ILLEGAL_ARGUMENT;
+    GROUP_FORWARD(h, jaicov_set_datum(s_, free_flags, n_unknowns, n_observations))
     for (int i = 0; i < 7; i++) h->free_flags[i] = free_flags[i] != 0;
     h->n_unknowns = n_unknowns;
     h->n_observations = n_observations;
@@ -1212,12 +1403,19 @@ int32_t jaicov_set_datum(jaicov_handle *h, const int32_t free_flags[7], int32_t 
 
 int32_t jaicov_set_reduced_rows(jaicov_handle *h, int32_t num_rows) {
     if (!h || num_rows < 0) return JAICOV_ILLEGAL_ARGUMENT;
+    GROUP_FORWARD(h, jaicov_set_reduced_rows(s_, num_rows))
     h->reduced_rows = num_rows;
     return JAICOV_OK;
 }
 
 int32_t jaicov_iterate(jaicov_handle *h, int32_t final_pass, int32_t apply_update) {
     if (!h) return JAICOV_ILLEGAL_ARGUMENT;
+    if (is_group(h)) {
+        API_GUARD_BEGIN
+        group_ensure(h);
+        return group_run(h, [&](jaicov_handle *sh, int) { return (int)jaicov_iterate(sh, final_pass, apply_update); });
+        API_GUARD_END(h)
+    }
     API_GUARD_BEGIN
     prepare(h);
     JCHECK(cudaSetDevice(h->opt.device));
@@ -1233,6 +1431,17 @@ int32_t jaicov_iterate(jaicov_handle *h, int32_t final_pass, int32_t apply_updat
 
 int32_t jaicov_estimate(jaicov_handle *h, jaicov_progress_cb cb, void *user, volatile int32_t *interrupt_flag) {
     if (!h) return JAICOV_ILLEGAL_ARGUMENT;
+    if (is_group(h)) {
+        API_GUARD_BEGIN
+        group_ensure(h);
+        // the listener and the caller's interrupt flag belong to device 0's handle, which runs on the calling thread; the other
+        // devices learn of an interrupt through the agreement step of the loop (agree_interrupt)
+        std::vector<int32_t> dummy(h->sub.size(), 0);
+        return group_run(h, [&](jaicov_handle *sh, int i) {
+            return (int)jaicov_estimate(sh, i == 0 ? cb : nullptr, i == 0 ? user : nullptr, i == 0 || !interrupt_flag ? interrupt_flag : &dummy[i]);
+        });
+        API_GUARD_END(h)
+    }
     API_GUARD_BEGIN
     const double SQRT_EPS = std::sqrt(kEps);                 // BA:77
     auto fire = [&](int st, double a, double b) { if (cb) cb(user, st, a, b); };
@@ -1256,7 +1465,7 @@ int32_t jaicov_estimate(jaicov_handle *h, jaicov_progress_cb cb, void *user, vol
     do {
         h->stats.iteration_step = maxIter - runs;            // BA:230
         fire(JAICOV_STATE_ITERATE, maxIter, h->stats.iteration_step);
-        if (interrupt_flag && *interrupt_flag) { *interrupt_flag = 0; status = JAICOV_INTERRUPT; break; }   // BA:240-245
+        if (interrupted(h, interrupt_flag)) { status = JAICOV_INTERRUPT; break; }   // BA:240-245
         complete = isEstimated;                              // BA:250
         if (complete && h->opt.invert_mode != JAICOV_INVERT_NONE) fire(JAICOV_STATE_INVERT_NORMAL_EQUATION_MATRIX, 0, 1);
         PassResult r = run_pass(h, complete, true);
@@ -1268,7 +1477,7 @@ int32_t jaicov_estimate(jaicov_handle *h, jaicov_progress_cb cb, void *user, vol
             if (!r.lm_step || r.lm_accepted) { h->stats.omega = r.omega; h->lm_omega = r.omega; }
         }
         h->stats.max_abs_dx = r.max_abs_dx;
-        if (interrupt_flag && *interrupt_flag) { *interrupt_flag = 0; status = JAICOV_INTERRUPT; break; }   // BA:320-325
+        if (interrupted(h, interrupt_flag)) { status = JAICOV_INTERRUPT; break; }   // BA:320-325
         if (r.bad || std::isnan(r.max_abs_dx) || std::isinf(r.max_abs_dx)) { status = JAICOV_SINGULAR_MATRIX; break; }  // BA:327-330
         else if (r.max_abs_dx <= SQRT_EPS && runs > 0 && h->adapted_damping == 0) {     // BA:332-337
             isEstimated = true;
@@ -1295,6 +1504,17 @@ int32_t jaicov_estimate(jaicov_handle *h, jaicov_progress_cb cb, void *user, vol
 
 int32_t jaicov_get_stats(jaicov_handle *h, jaicov_stats *out) {
     if (!h || !out) return JAICOV_ILLEGAL_ARGUMENT;
+    if (is_group(h)) {      // device 0's view; stage times: the slowest device
+        int32_t rc = jaicov_get_stats(h->sub[0], out);
+        for (size_t i = 1; i < h->sub.size() && rc == JAICOV_OK; i++) {
+            jaicov_stats t;
+            rc = jaicov_get_stats(h->sub[i], &t);
+            out->ms_assembly = std::max(out->ms_assembly, t.ms_assembly); out->ms_factor = std::max(out->ms_factor, t.ms_factor);
+            out->ms_solve = std::max(out->ms_solve, t.ms_solve); out->ms_inverse = std::max(out->ms_inverse, t.ms_inverse);
+            out->ms_omega = std::max(out->ms_omega, t.ms_omega); out->ms_total = std::max(out->ms_total, t.ms_total);
+        }
+        return rc;
+    }
     int d = 0;
     for (int i = 0; i < 7; i++) d += h->free_flags[i];
     h->stats.n_unknowns = h->n_unknowns;
@@ -1314,6 +1534,7 @@ int32_t jaicov_get_stats(jaicov_handle *h, jaicov_stats *out) {
 
 int32_t jaicov_get_values(jaicov_handle *h, double *xyz, double *io_val, double *coef_val, double *eo_val) {
     if (!h) return JAICOV_ILLEGAL_ARGUMENT;
+    if (is_group(h)) return jaicov_get_values(h->sub[0], xyz, io_val, coef_val, eo_val);     // identical on every device
     API_GUARD_BEGIN
     if (h->prepared) { JCHECK(cudaSetDevice(h->opt.device)); download_values(h); }
     if (xyz && !h->xyz.empty()) memcpy(xyz, h->xyz.data(), h->xyz.size() * sizeof(double));
@@ -1325,6 +1546,7 @@ int32_t jaicov_get_values(jaicov_handle *h, double *xyz, double *io_val, double 
 }
 
 int32_t jaicov_get_dx(jaicov_handle *h, double *dx) {
+    if (is_group(h)) return jaicov_get_dx(h->sub[0], dx);
     if (!h || !dx || !h->dxref.p) return JAICOV_ILLEGAL_ARGUMENT;
     API_GUARD_BEGIN
     JCHECK(cudaSetDevice(h->opt.device));
@@ -1357,8 +1579,53 @@ static int32_t pack_to_host(jaicov_handle *h, const double *border, const double
     return JAICOV_OK;
 }
 
+// Single-process multi-GPU handle: the column tiles of Qxx live on their owners.  They are gathered over NVLink (peer-to-peer 2-D
+// copies, one per tile) into device 0's system buffer -- whose factor is no longer needed once the pass is over -- in the
+// single-GPU layout (row-major lower triangle), and leave through ONE packed DMA stream like on a single GPU.
+static int32_t group_gather_qxx(jaicov_handle *g) {
+    jaicov_handle *h0 = g->sub[0];
+    if (h0->gathered_qxx) return JAICOV_OK;
+    const int64_t np = h0->P.np;
+    JCHECK(cudaSetDevice(h0->opt.device));
+    for (size_t r = 1; r < g->sub.size(); r++) {
+        int can = 0;
+        JCHECK(cudaDeviceCanAccessPeer(&can, h0->opt.device, g->sub[r]->opt.device));
+        if (can) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(g->sub[r]->opt.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) JCHECK(e);
+            cudaGetLastError();
+        }   // without peer access the copies below are staged through the host by the driver: slower, still correct
+    }
+    for (jaicov_handle *sh : g->sub) {          // everybody's pass has finished (group_run joined its threads); drain the streams
+        JCHECK(cudaSetDevice(sh->opt.device));
+        JCHECK(cudaStreamSynchronize(sh->stream));
+    }
+    JCHECK(cudaSetDevice(h0->opt.device));
+    for (jaicov_handle *sh : g->sub) {
+        const int64_t ldx = (int64_t)sh->ktab.size() * kBlk;
+        for (size_t jl = 0; jl < sh->ktab.size(); jl++) {
+            const int64_t e0 = sh->ktab[jl];
+            JCHECK(cudaMemcpy2DAsync(h0->M.p + e0 * np + e0, (size_t)np * sizeof(double), sh->Xl.p + e0 * ldx + (int64_t)jl * kBlk,
+                                     (size_t)ldx * sizeof(double), kBlk * sizeof(double), (size_t)(np - e0), cudaMemcpyDeviceToDevice,
+                                     h0->stream));
+        }
+    }
+    JCHECK(cudaStreamSynchronize(h0->stream));
+    h0->gathered_qxx = true;
+    return JAICOV_OK;
+}
+
 int32_t jaicov_get_qxx_packed(jaicov_handle *h, double *dst) {
     if (!h || !dst) return JAICOV_ILLEGAL_ARGUMENT;
+    if (is_group(h)) {
+        jaicov_handle *h0 = h->sub[0];
+        for (jaicov_handle *sh : h->sub)
+            if (!sh->have_qxx) return fail(h, JAICOV_NOT_INITIALISED, "no cofactor matrix: run a final pass with invert_mode FULL");
+        API_GUARD_BEGIN
+        group_gather_qxx(h);
+        return pack_to_host(h0, h0->Tq.p, h0->small.p + 49, dst, h0->qxx_rows());
+        API_GUARD_END(h)
+    }
     if (!h->have_qxx) return fail(h, JAICOV_NOT_INITIALISED, "no cofactor matrix: run a final pass with invert_mode FULL");
     if (h->dist_on) return fail(h, JAICOV_ILLEGAL_ARGUMENT, "distributed handle: Qxx is spread over the ranks, use jaicov_get_qxx_block (partial sums) or jaicov_get_qxx_local");
     API_GUARD_BEGIN
@@ -1369,6 +1636,21 @@ int32_t jaicov_get_qxx_packed(jaicov_handle *h, double *dst) {
 
 int32_t jaicov_get_qxx_block(jaicov_handle *h, int32_t r0, int32_t r1, int32_t c0, int32_t c1, double *dst, int64_t ld) {
     if (!h || !dst) return JAICOV_ILLEGAL_ARGUMENT;
+    if (is_group(h) && (r1 < r0 || c1 < c0 || ld < c1 - c0)) return JAICOV_ILLEGAL_ARGUMENT;
+    if (is_group(h)) {      // the devices hold disjoint parts: the block is the sum of their partial blocks
+        API_GUARD_BEGIN
+        const int64_t rows = r1 - r0, cols = c1 - c0;
+        std::vector<double> part((size_t)std::max<int64_t>(rows * cols, 1));
+        for (size_t i = 0; i < h->sub.size(); i++) {
+            const int32_t rc = jaicov_get_qxx_block(h->sub[i], r0, r1, c0, c1, i == 0 ? dst : part.data(), i == 0 ? ld : cols);
+            if (rc != JAICOV_OK) { h->err = h->sub[i]->err; return rc; }
+            if (i > 0)
+                for (int64_t r = 0; r < rows; r++)
+                    for (int64_t c = 0; c < cols; c++) dst[r * ld + c] += part[(size_t)(r * cols + c)];
+        }
+        return JAICOV_OK;
+        API_GUARD_END(h)
+    }
     if (!h->have_qxx) return fail(h, JAICOV_NOT_INITIALISED, "no cofactor matrix: run a final pass with invert_mode FULL");
     const int n = h->qxx_rows();
     if (r0 < 0 || c0 < 0 || r1 > n || c1 > n || r1 < r0 || c1 < c0 || ld < c1 - c0) return JAICOV_ILLEGAL_ARGUMENT;
@@ -1394,6 +1676,18 @@ int32_t jaicov_get_qxx_block(jaicov_handle *h, int32_t r0, int32_t r1, int32_t c
 
 int32_t jaicov_get_qxx_submatrix(jaicov_handle *h, int32_t n_idx, const int32_t *idx, double scale, double *dst) {
     if (!h || n_idx < 0 || (n_idx > 0 && (!idx || !dst))) return JAICOV_ILLEGAL_ARGUMENT;
+    if (is_group(h)) {
+        API_GUARD_BEGIN
+        std::vector<double> part((size_t)n_idx * n_idx);
+        for (size_t i = 0; i < h->sub.size(); i++) {
+            const int32_t rc = jaicov_get_qxx_submatrix(h->sub[i], n_idx, idx, scale, i == 0 ? dst : part.data());
+            if (rc != JAICOV_OK) { h->err = h->sub[i]->err; return rc; }
+            if (i > 0)
+                for (size_t k = 0; k < part.size(); k++) dst[k] += part[k];
+        }
+        return JAICOV_OK;
+        API_GUARD_END(h)
+    }
     if (!h->have_qxx) return fail(h, JAICOV_NOT_INITIALISED, "no cofactor matrix: run a final pass with invert_mode FULL");
     const int n = h->qxx_rows();
     for (int i = 0; i < n_idx; i++)
@@ -1421,6 +1715,7 @@ int32_t jaicov_get_qxx_submatrix(jaicov_handle *h, int32_t n_idx, const int32_t 
 
 int32_t jaicov_get_qxx_diag(jaicov_handle *h, double *dst) {
     if (!h || !dst) return JAICOV_ILLEGAL_ARGUMENT;
+    if (is_group(h)) return fail(h, JAICOV_ILLEGAL_ARGUMENT, "several devices: use jaicov_get_qxx_submatrix / jaicov_get_qxx_packed");
     if (!h->have_qxx) return fail(h, JAICOV_NOT_INITIALISED, "no cofactor matrix: run a final pass with invert_mode FULL");
     if (h->dist_on) return fail(h, JAICOV_ILLEGAL_ARGUMENT, "distributed handle: use jaicov_get_qxx_block");
     API_GUARD_BEGIN
@@ -1439,6 +1734,7 @@ int32_t jaicov_get_qxx_diag(jaicov_handle *h, double *dst) {
 
 int32_t jaicov_get_qxx_local(jaicov_handle *h, int32_t *n_tiles, int32_t *tile_first_col, int32_t tile_cap, double *dst) {
     if (!h || !n_tiles) return JAICOV_ILLEGAL_ARGUMENT;
+    if (is_group(h)) return fail(h, JAICOV_ILLEGAL_ARGUMENT, "single-process handle: every getter returns complete results, use jaicov_get_qxx_packed / _block");
     if (!h->dist_on) return fail(h, JAICOV_ILLEGAL_ARGUMENT, "not a distributed handle");
     API_GUARD_BEGIN
     *n_tiles = (int32_t)h->ktab.size();
@@ -1516,6 +1812,21 @@ void rotation_with_derivatives(double om, double ph, double ka, double R[3][3], 
 int32_t jaicov_propagate_eo_transform(jaicov_handle *h, int32_t n_points, const int32_t *point, const int32_t *src_image,
                                       const int32_t *trg_image, double sigma2, double *xyz_out, double *cov_packed) {
     if (!h || n_points < 0 || (n_points > 0 && (!point || !src_image || !trg_image))) return JAICOV_ILLEGAL_ARGUMENT;
+    if (is_group(h)) {
+        API_GUARD_BEGIN
+        const size_t npk = (size_t)(3 * (int64_t)n_points) * (3 * (int64_t)n_points + 1) / 2;
+        std::vector<double> part(cov_packed ? npk : 0);
+        for (size_t i = 0; i < h->sub.size(); i++) {
+            const int32_t rc = jaicov_propagate_eo_transform(h->sub[i], n_points, point, src_image, trg_image, sigma2, i == 0 ? xyz_out : nullptr,
+                                                             cov_packed ? (i == 0 ? cov_packed : part.data()) : nullptr);
+            if (rc != JAICOV_OK) { h->err = h->sub[i]->err; return rc; }
+            if (i > 0 && cov_packed)
+                for (size_t k = 0; k < npk; k++) cov_packed[k] += part[k];
+            if (!cov_packed) break;
+        }
+        return JAICOV_OK;
+        API_GUARD_END(h)
+    }
     if (cov_packed && !h->have_qxx) return fail(h, JAICOV_NOT_INITIALISED, "no cofactor matrix: run a final pass with invert_mode FULL");
     const int nPt = (int)(h->xyz.size() / 3), nImg = (int)(h->eo_val.size() / 6);
     for (int i = 0; i < n_points; i++)
@@ -1637,6 +1948,11 @@ int32_t jaicov_dlt_batch(int32_t device, int32_t n_img, const int64_t *pt_ptr, c
 
 int32_t jaicov_eval_residual_jacobian(jaicov_handle *h, int32_t ns_max, double *a, double *w, double *p) {
     if (!h || !a || !w || !p) return JAICOV_ILLEGAL_ARGUMENT;
+    if (is_group(h)) {      // no collective in this stage: the first device evaluates all image points
+        const int32_t rc = jaicov_eval_residual_jacobian(h->sub[0], ns_max, a, w, p);
+        if (rc != JAICOV_OK) h->err = h->sub[0]->err;
+        return rc;
+    }
     API_GUARD_BEGIN
     prepare(h);
     JCHECK(cudaSetDevice(h->opt.device));
@@ -1661,6 +1977,12 @@ int32_t jaicov_eval_residual_jacobian(jaicov_handle *h, int32_t ns_max, double *
 
 int32_t jaicov_get_normal_equations(jaicov_handle *h, double *n_packed, double *rhs) {
     if (!h) return JAICOV_ILLEGAL_ARGUMENT;
+    if (is_group(h)) {      // the assembly all-reduces: every device takes part, the first one delivers
+        API_GUARD_BEGIN
+        group_ensure(h);
+        return group_run(h, [&](jaicov_handle *sh, int i) { return (int)jaicov_get_normal_equations(sh, i == 0 ? n_packed : nullptr, i == 0 ? rhs : nullptr); });
+        API_GUARD_END(h)
+    }
     API_GUARD_BEGIN
     prepare(h);
     JCHECK(cudaSetDevice(h->opt.device));
@@ -1678,6 +2000,15 @@ int32_t jaicov_get_normal_equations(jaicov_handle *h, double *n_packed, double *
 
 int32_t jaicov_omega(jaicov_handle *h, const double *dx, double *omega) {
     if (!h || !dx || !omega) return JAICOV_ILLEGAL_ARGUMENT;
+    if (is_group(h)) {
+        API_GUARD_BEGIN
+        group_ensure(h);
+        std::vector<double> om(h->sub.size(), 0.0);
+        const int rc = group_run(h, [&](jaicov_handle *sh, int i) { return (int)jaicov_omega(sh, dx, &om[i]); });
+        *omega = om[0];
+        return rc;
+        API_GUARD_END(h)
+    }
     API_GUARD_BEGIN
     prepare(h);
     JCHECK(cudaSetDevice(h->opt.device));
@@ -1707,6 +2038,19 @@ int32_t jaicov_omega(jaicov_handle *h, const double *dx, double *omega) {
 
 int32_t jaicov_normal_product(jaicov_handle *h, int32_t nvec, const double *x, double *y, double *rhs, double *wpw) {
     if (!h || nvec < 0 || (nvec > 0 && (!x || !y))) return JAICOV_ILLEGAL_ARGUMENT;
+    if (is_group(h)) {      // every device computes its image shard and receives the sum; the first one delivers
+        API_GUARD_BEGIN
+        group_ensure(h);
+        const size_t n = h->sub[0]->n_unknowns >= 0 ? (size_t)h->sub[0]->n_unknowns + 7 : 0;
+        std::vector<std::vector<double>> ys(h->sub.size()), rs(h->sub.size());
+        std::vector<double> ws(h->sub.size(), 0.0);
+        for (size_t i = 1; i < h->sub.size(); i++) { ys[i].resize(std::max<size_t>(1, (size_t)nvec * n)); rs[i].resize(std::max<size_t>(1, n)); }
+        return group_run(h, [&](jaicov_handle *sh, int i) {
+            return (int)jaicov_normal_product(sh, nvec, x, i == 0 ? y : ys[i].data(), rhs ? (i == 0 ? rhs : rs[i].data()) : nullptr,
+                                              wpw ? (i == 0 ? wpw : &ws[i]) : nullptr);
+        });
+        API_GUARD_END(h)
+    }
     API_GUARD_BEGIN
     if (!h->prepared && !h->resident) prepare(h);
     JCHECK(cudaSetDevice(h->opt.device));
@@ -1746,6 +2090,7 @@ int32_t jaicov_normal_product(jaicov_handle *h, int32_t nvec, const double *x, d
 }
 
 int32_t jaicov_get_preconditioner(jaicov_handle *h, double *v) {
+    if (is_group(h)) return jaicov_get_preconditioner(h->sub[0], v);
     if (!h || !v || !h->V.p) return JAICOV_ILLEGAL_ARGUMENT;
     API_GUARD_BEGIN
     JCHECK(cudaSetDevice(h->opt.device));

@@ -16,6 +16,7 @@
 //    with one warp per object point over that point's observations (CSC), again as DMMA tiles;
 //  * the packed per-point / per-camera partial buffers are exactly what an image-sharded multi-GPU run all-reduces.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.h"
 #include "model.cuh"
@@ -38,7 +39,7 @@ __device__ __forceinline__ int64_t lower_idx(int64_t a, int64_t b, int64_t ld) {
 struct CamSmem {
     double io[3];
     double r0;
-    double val[kMaxCoef];
+    double val[kMaxCoef], r0pow[kMaxCoef];
     int32_t type[kMaxCoef], order[kMaxCoef], zm[kMaxCoef], zptr[kMaxCoef + 1];
     int32_t ncoef;
 };
@@ -49,6 +50,7 @@ __device__ __forceinline__ void load_camera(const DevProblem &P, int cam, CamSme
     if (tid == 3) { s.r0 = P.r0[cam]; s.ncoef = c1 - c0; }
     for (int k = tid; k < c1 - c0; k += nthreads) {
         s.val[k] = P.coef_val[c0 + k];
+        s.r0pow[k] = P.coef_r0pow[c0 + k];
         s.type[k] = P.coef_type[c0 + k];
         s.order[k] = P.coef_order[c0 + k];
         s.zm[k] = P.zern_m[c0 + k];
@@ -58,7 +60,7 @@ __device__ __forceinline__ void load_camera(const DevProblem &P, int cam, CamSme
 
 __device__ __forceinline__ CamView view_of(const DevProblem &P, const CamSmem &s) {
     CamView v;
-    v.io = s.io; v.r0 = s.r0; v.ncoef = s.ncoef; v.type = s.type; v.order = s.order; v.val = s.val;
+    v.io = s.io; v.r0 = s.r0; v.ncoef = s.ncoef; v.type = s.type; v.order = s.order; v.val = s.val; v.r0pow = s.r0pow;
     v.zern_m = s.zm; v.zern_ptr = s.zptr; v.zern_p = P.zern_p; v.zern_c = P.zern_c;
     return v;
 }
@@ -67,7 +69,7 @@ __device__ __forceinline__ CamView view_global(const DevProblem &P, int cam) {
     const int c0 = P.coef_ptr[cam];
     CamView v;
     v.io = P.io_val + 3 * cam; v.r0 = P.r0[cam]; v.ncoef = P.coef_ptr[cam + 1] - c0;
-    v.type = P.coef_type + c0; v.order = P.coef_order + c0; v.val = P.coef_val + c0;
+    v.type = P.coef_type + c0; v.order = P.coef_order + c0; v.val = P.coef_val + c0; v.r0pow = P.coef_r0pow + c0;
     v.zern_m = P.zern_m + c0; v.zern_ptr = P.zern_ptr + c0; v.zern_p = P.zern_p; v.zern_c = P.zern_c;
     return v;
 }
@@ -144,8 +146,8 @@ void launch_eval_k1(const DevProblem &P, int ns_max, double *a, double *w, doubl
 // tile columns: 0..5 EO (X0,Y0,Z0,omega,phi,kappa), 6..8 IO (x0,y0,c), 9..9+ncoef-1 coefficients, 9+ncoef = w.
 constexpr int kImgWarps = 4;
 
-template <int NT>
-__global__ void __launch_bounds__(kImgWarps * 32) k_by_image(DevProblem P, const WorkItem *__restrict__ work,
+template <int NT, int MINB>
+__global__ void __launch_bounds__(kImgWarps * 32, MINB) k_by_image(DevProblem P, const WorkItem *__restrict__ work,
                                                              double *__restrict__ partial, double *__restrict__ M) {
     constexpr int LDT = 68;  // tile is stored column-major [NC][68]: == 4 (mod 16) -> conflict-free fragment reads,
                              // and lanes write consecutive rows of one column -> conflict-free stores
@@ -153,16 +155,18 @@ __global__ void __launch_bounds__(kImgWarps * 32) k_by_image(DevProblem P, const
     extern __shared__ double smem[];
     __shared__ CamSmem cs;
     __shared__ int32_t s_eocol[6];
+    __shared__ ImgPose s_pose;                 // per-image constants stay in shared memory: 28 registers less per thread
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const WorkItem wi = work[blockIdx.x];
     const int img = wi.img, cam = P.cam_of_img[img];
     load_camera(P, cam, cs, tid, blockDim.x);
     if (tid < 6) s_eocol[tid] = P.eo_col[6 * (int64_t)img + tid];
+    if (tid < 14) reinterpret_cast<double *>(&s_pose)[tid] = P.pose[(int64_t)img * kPoseStride + tid];
     double *tile = smem + (size_t)warp * NC * LDT;
     for (int i = lane; i < NC * LDT; i += 32) tile[i] = 0.0;
     __syncthreads();
     const CamView cv = view_of(P, cs);
-    const ImgPose q = load_pose(P.pose, img);
+    const ImgPose &q = s_pose;
     const int wcol = 9 + cs.ncoef;
     const int64_t ld = P.np;
     const int d = P.d;
@@ -180,13 +184,12 @@ __global__ void __launch_bounds__(kImgWarps * 32) k_by_image(DevProblem P, const
         const int64_t j = base + lane;
         if (j < wi.end) {
             const int pt = P.obj_idx[j];
-            double p00, p01, p11;
-            point_weight(P.sigma2, P.var[2 * j], P.var[2 * j + 1], P.rho[j], p00, p01, p11);
-            // P = R'R, R = [r00 r01; 0 r11]
-            const double r00 = sqrt(p00), r01 = p01 / r00, r11 = sqrt(p11 - r01 * r01);
+            // P = R'R, R = [r00 r01; 0 r11]: constant over the passes, precomputed per observation (k_obs_weights)
+            const double r00 = P.rw[3 * j], r01 = P.rw[3 * j + 1], r11 = P.rw[3 * j + 2];
+            const double2 xyo = reinterpret_cast<const double2 *>(P.xy)[j];
             BaseRows r;
             eval_observation(q, cv, P.xyz[3 * (int64_t)pt], P.xyz[3 * (int64_t)pt + 1], P.xyz[3 * (int64_t)pt + 2],
-                             P.xy[2 * j], P.xy[2 * j + 1], r, [&](int k, double v0, double v1) {
+                             xyo.x, xyo.y, r, [&](int k, double v0, double v1) {
                                  ROW0(9 + k) = r00 * v0 + r01 * v1;
                                  ROW1(9 + k) = r11 * v1;
                              });
@@ -345,53 +348,64 @@ __global__ void __launch_bounds__(256) k_camera_scatter(DevProblem P, AssemblySc
 }
 
 // ---- by-point sweep -----------------------------------------------------------------------------------------------
-// tile columns: 0..2 point X,Y,Z; 3..3+kRaw-1 raw camera parameters of ALL cameras (x0,y0,c,coefs per camera);
-// 3+kRaw = w.  One warp per object point; output rows 0..2 of the skinny Gram: [PP | P x camera | n_P].
+// tile columns: 0..2 point X,Y,Z; 3..3+kraw-1 raw parameters (x0,y0,c,coefs per camera) of the cameras of ONE camera group
+// [cam0, cam1); 3+kraw = w.  One warp per object point; output rows 0..2 of the skinny Gram: [PP | P x camera | n_P].
+// Camera groups: the Gram row is at most 72 columns wide, so a network whose cameras have more than 68 raw parameters in
+// total is swept once per group of consecutive cameras (observations of other cameras contribute nothing to a group's
+// sweep; every observation belongs to exactly one group, so the point block and n_P add up over the groups).  One group --
+// one sweep -- is the common case.  A group of a single camera stages it in shared memory.
 constexpr int kPtWarps = 4;
 
-template <int NT>
-__global__ void __launch_bounds__(kPtWarps * 32) k_by_point(DevProblem P, double *__restrict__ pt_partial) {
+template <int NT, bool ONE_CAM, int MINB>
+__global__ void __launch_bounds__(kPtWarps * 32, MINB) k_by_point(DevProblem P, int cam0, int cam1, int kraw, double *__restrict__ pt_partial) {
     constexpr int LDT = 68;
     constexpr int NC = 8 * NT;
     extern __shared__ double smem[];
+    __shared__ CamSmem cs;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (ONE_CAM) {
+        load_camera(P, cam0, cs, tid, blockDim.x);
+        __syncthreads();
+    }
     const int pt = blockIdx.x * kPtWarps + warp;
     if (pt >= P.nPt) return;  // warp-uniform
     double *tile = smem + (size_t)warp * NC * LDT;
 #define ROW0(c) tile[(c) * LDT + lane]
 #define ROW1(c) tile[(c) * LDT + lane + 32]
-    const int wcol = 3 + P.kRaw;
+    const int wcol = 3 + kraw;
+    const int kbase0 = P.cam_kbase[cam0];
     const double X = P.xyz[3 * (int64_t)pt], Y = P.xyz[3 * (int64_t)pt + 1], Z = P.xyz[3 * (int64_t)pt + 2];
     double acc[NT][2];
 #pragma unroll
     for (int i = 0; i < NT; i++) acc[i][0] = acc[i][1] = 0.0;
     const int64_t o0 = P.pt_obs_ptr[pt], o1 = P.pt_obs_ptr[pt + 1];
     for (int64_t base = o0; base < o1; base += 32) {
-        for (int i = 0; i < NC; i++) { ROW0(i) = 0.0; ROW1(i) = 0.0; }
+        for (int i = 0; i <= wcol; i++) { ROW0(i) = 0.0; ROW1(i) = 0.0; }
         const int64_t oi = base + lane;
         if (oi < o1) {
             const int64_t j = P.pt_obs[oi];
             const int img = P.img_of_obs[j], cam = P.cam_of_img[img];
-            const ImgPose q = load_pose(P.pose, img);
-            const CamView cv = view_global(P, cam);
-            const int kb = 3 + P.cam_kbase[cam];
-            double p00, p01, p11;
-            point_weight(P.sigma2, P.var[2 * j], P.var[2 * j + 1], P.rho[j], p00, p01, p11);
-            const double r00 = sqrt(p00), r01 = p01 / r00, r11 = sqrt(p11 - r01 * r01);
-            BaseRows r;
-            eval_observation(q, cv, X, Y, Z, P.xy[2 * j], P.xy[2 * j + 1], r, [&](int k, double v0, double v1) {
-                ROW0(kb + 3 + k) = r00 * v0 + r01 * v1;
-                ROW1(kb + 3 + k) = r11 * v1;
-            });
+            if (cam >= cam0 && cam < cam1) {
+                const ImgPose q = load_pose(P.pose, img);
+                const CamView cv = ONE_CAM ? view_of(P, cs) : view_global(P, cam);
+                const int kb = 3 + P.cam_kbase[cam] - kbase0;
+                const double r00 = P.rw[3 * j], r01 = P.rw[3 * j + 1], r11 = P.rw[3 * j + 2];
+                const double2 xyo = reinterpret_cast<const double2 *>(P.xy)[j];
+                BaseRows r;
+                eval_observation_t<false>(q, cv, X, Y, Z, xyo.x, xyo.y, r, [&](int k, double v0, double v1) {
+                    ROW0(kb + 3 + k) = r00 * v0 + r01 * v1;
+                    ROW1(kb + 3 + k) = r11 * v1;
+                });
 #pragma unroll
-            for (int i = 0; i < 3; i++) {
-                ROW0(i) = r00 * r.ax[i] + r01 * r.ay[i];
-                ROW1(i) = r11 * r.ay[i];
+                for (int i = 0; i < 3; i++) {
+                    ROW0(i) = r00 * r.ax[i] + r01 * r.ay[i];
+                    ROW1(i) = r11 * r.ay[i];
+                }
+                ROW0(kb) = r00;  ROW1(kb) = 0.0;
+                ROW0(kb + 1) = r01;  ROW1(kb + 1) = r11;
+                ROW0(kb + 2) = r00 * r.ax[3] + r01 * r.ay[3];  ROW1(kb + 2) = r11 * r.ay[3];
+                ROW0(wcol) = r00 * r.w0 + r01 * r.w1;  ROW1(wcol) = r11 * r.w1;
             }
-            ROW0(kb) = r00;  ROW1(kb) = 0.0;
-            ROW0(kb + 1) = r01;  ROW1(kb + 1) = r11;
-            ROW0(kb + 2) = r00 * r.ax[3] + r01 * r.ay[3];  ROW1(kb + 2) = r11 * r.ay[3];
-            ROW0(wcol) = r00 * r.w0 + r01 * r.w1;  ROW1(wcol) = r11 * r.w1;
         }
         __syncwarp();
 #pragma unroll 4
@@ -415,10 +429,9 @@ __global__ void __launch_bounds__(kPtWarps * 32) k_by_point(DevProblem P, double
     }
 }
 
-// scatter the per-point partials into N / n (single owner per entry)
-__global__ void __launch_bounds__(256) k_point_scatter(DevProblem P, AssemblyScratch S, double *__restrict__ M,
-                                                        double *__restrict__ rhs) {
-    const int NC = 8 * S.ntPt;
+// scatter the per-point partials of one camera group into N / n (single owner per entry)
+__global__ void __launch_bounds__(256) k_point_scatter(DevProblem P, AssemblyScratch S, int NC, int kbase0, int kraw,
+                                                        double *__restrict__ M, double *__restrict__ rhs) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)P.nPt * 3 * NC) return;
     const int pt = (int)(i / (3 * NC));
@@ -433,37 +446,47 @@ __global__ void __launch_bounds__(256) k_point_scatter(DevProblem P, AssemblyScr
         const int32_t c2 = P.pt_col[3 * (int64_t)pt + j];
         if (!col_active(c2)) return;
         M[lower_idx(cp - d, c2 - d, ld)] += v;
-    } else if (j < 3 + P.kRaw) {
-        const int32_t c2 = P.campos_col[j - 3];
+    } else if (j < 3 + kraw) {
+        const int32_t c2 = P.campos_col[kbase0 + j - 3];
         if (!col_active(c2)) return;
         M[lower_idx(cp - d, c2 - d, ld)] += v;
-    } else if (j == 3 + P.kRaw) {
+    } else if (j == 3 + kraw) {
         rhs[cp - d] += v;
     }
+}
+
+// resident CTAs per SM the observation sweeps are compiled for (register cap 128 at 4 CTAs of 128 threads): JAICOV_SWEEP_MINB
+static int sweep_min_blocks() {
+    static const int v = [] { const char *e = getenv("JAICOV_SWEEP_MINB"); return e ? atoi(e) : 1; }();
+    return v;
 }
 
 template <int NT>
 static void run_by_image(const DevProblem &P, const AssemblyScratch &S, double *M, cudaStream_t s) {
     const size_t smem = (size_t)kImgWarps * 8 * NT * 68 * sizeof(double);
-    static bool attr = false;
-    if (!attr) {
-        JCHECK(cudaFuncSetAttribute(k_by_image<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    static PerDeviceOnce once3, once4;
     g_launch_count++;
-    k_by_image<NT><<<S.nWork, kImgWarps * 32, smem, s>>>(P, S.work, S.img_partial, M);
+    if (sweep_min_blocks() >= 4 && NT <= 4) {
+        once4.run([&] { JCHECK(cudaFuncSetAttribute(k_by_image<NT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
+        k_by_image<NT, 4><<<S.nWork, kImgWarps * 32, smem, s>>>(P, S.work, S.img_partial, M);
+    } else {
+        once3.run([&] { JCHECK(cudaFuncSetAttribute(k_by_image<NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
+        k_by_image<NT, 1><<<S.nWork, kImgWarps * 32, smem, s>>>(P, S.work, S.img_partial, M);
+    }
 }
 
-template <int NT>
-static void run_by_point(const DevProblem &P, const AssemblyScratch &S, cudaStream_t s) {
+template <int NT, bool ONE_CAM>
+static void run_by_point(const DevProblem &P, const AssemblyScratch &S, const PtGroup &g, cudaStream_t s) {
     const size_t smem = (size_t)kPtWarps * 8 * NT * 68 * sizeof(double);
-    static bool attr = false;
-    if (!attr) {
-        JCHECK(cudaFuncSetAttribute(k_by_point<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    static PerDeviceOnce once3, once4;
     g_launch_count++;
-    k_by_point<NT><<<(P.nPt + kPtWarps - 1) / kPtWarps, kPtWarps * 32, smem, s>>>(P, S.pt_partial);
+    if (sweep_min_blocks() >= 4 && NT <= 4) {
+        once4.run([&] { JCHECK(cudaFuncSetAttribute(k_by_point<NT, ONE_CAM, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
+        k_by_point<NT, ONE_CAM, 4><<<(P.nPt + kPtWarps - 1) / kPtWarps, kPtWarps * 32, smem, s>>>(P, g.cam0, g.cam1, g.kraw, S.pt_partial);
+    } else {
+        once3.run([&] { JCHECK(cudaFuncSetAttribute(k_by_point<NT, ONE_CAM, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
+        k_by_point<NT, ONE_CAM, 1><<<(P.nPt + kPtWarps - 1) / kPtWarps, kPtWarps * 32, smem, s>>>(P, g.cam0, g.cam1, g.kraw, S.pt_partial);
+    }
 }
 
 #define JAICOV_DISPATCH_NT(nt, CALL)                 \
@@ -476,11 +499,13 @@ static void run_by_point(const DevProblem &P, const AssemblyScratch &S, cudaStre
         case 6: CALL(6); break;                      \
         case 7: CALL(7); break;                      \
         case 8: CALL(8); break;                      \
+        case 9: CALL(9); break;                      \
         default: throw CudaError{cudaErrorInvalidValue, "too many camera parameters for one Gram tile row", __FILE__, __LINE__}; \
     }
 
-// image points: N (lower, row-major, ld = np) and n.  M and rhs must be zero on entry.
-void launch_assemble_local(const DevProblem &P, const AssemblyScratch &S, double *M, double *rhs, cudaStream_t s) {
+// image points, first half: sweeps over this rank's images (unique EO blocks straight into N, per-camera sums).
+// M and rhs must be zero on entry.
+void launch_assemble_images(const DevProblem &P, const AssemblyScratch &S, double *M, double *rhs, cudaStream_t s) {
     if (P.m == 0) return;
     if (S.nWork > 0) {
 #define CALL_IMG(NT) run_by_image<NT>(P, S, M, s)
@@ -492,18 +517,51 @@ void launch_assemble_local(const DevProblem &P, const AssemblyScratch &S, double
     }
     g_launch_count++;
     k_camera_sum<<<P.nCam, 256, 0, s>>>(P, S);
-#define CALL_PT(NT) run_by_point<NT>(P, S, s)
-    JAICOV_DISPATCH_NT(S.ntPt, CALL_PT)
-#undef CALL_PT
 }
 
-void launch_assemble_shared(const DevProblem &P, const AssemblyScratch &S, double *M, double *rhs, cudaStream_t s) {
+// per-point partial sums of one camera group over this rank's observations (-> S.pt_partial, all-reduced across ranks)
+void launch_by_point(const DevProblem &P, const AssemblyScratch &S, const PtGroup &g, cudaStream_t s) {
+    if (P.m == 0) return;
+    if (g.cam1 - g.cam0 == 1) {
+#define CALL_PT(NT) run_by_point<NT, true>(P, S, g, s)
+        JAICOV_DISPATCH_NT(g.nt, CALL_PT)
+#undef CALL_PT
+    } else {
+#define CALL_PT(NT) run_by_point<NT, false>(P, S, g, s)
+        JAICOV_DISPATCH_NT(g.nt, CALL_PT)
+#undef CALL_PT
+    }
+}
+
+void launch_camera_scatter(const DevProblem &P, const AssemblyScratch &S, double *M, double *rhs, cudaStream_t s) {
     if (P.m == 0) return;
     g_launch_count++;
     k_camera_scatter<<<P.nCam, 256, 0, s>>>(P, S, M, rhs);
-    const int64_t tot = (int64_t)P.nPt * 3 * 8 * S.ntPt;
+}
+
+void launch_point_scatter(const DevProblem &P, const AssemblyScratch &S, const PtGroup &g, int kbase0, double *M, double *rhs,
+                          cudaStream_t s) {
+    if (P.m == 0) return;
+    const int NC = 8 * g.nt;
+    const int64_t tot = (int64_t)P.nPt * 3 * NC;
     g_launch_count++;
-    k_point_scatter<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(P, S, M, rhs);
+    k_point_scatter<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(P, S, NC, kbase0, g.kraw, M, rhs);
+}
+
+// R with P = R'R of every image point (PDF:296-319): constant over the passes of one adjustment
+__global__ void __launch_bounds__(256) k_obs_weights(DevProblem P, double *__restrict__ rw) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.m) return;
+    double p00, p01, p11;
+    point_weight(P.sigma2, P.var[2 * j], P.var[2 * j + 1], P.rho[j], p00, p01, p11);
+    const double r00 = sqrt(p00), r01 = p01 / r00;
+    rw[3 * j] = r00;  rw[3 * j + 1] = r01;  rw[3 * j + 2] = sqrt(p11 - r01 * r01);
+}
+
+void launch_obs_weights(const DevProblem &P, double *rw, cudaStream_t s) {
+    if (P.m == 0) return;
+    g_launch_count++;
+    k_obs_weights<<<(unsigned)((P.m + 255) / 256), 256, 0, s>>>(P, rw);
 }
 
 // ---- scale bars (PDF:210-283): a handful of observations, one thread, reference order ------------------------
@@ -561,47 +619,71 @@ void launch_omega_bars(const DevProblem &P, const double *dxref, double *omega_o
     k_omega_bars<<<1, 32, 0, s>>>(P, dxref, omega_out);
 }
 
-// ---- K8: Omega = sum v'Pv, v = w - A dx (BA:472-491); warp-shuffle + block reduction, two deterministic stages ----
-constexpr int kOmegaThreads = 256;
+// ---- K8: Omega = sum v'Pv, v = w - A dx (BA:472-491) -----------------------------------------------------------------------
+// One CTA per (image, chunk of <= 1024 points) -- the work items of the by-image sweep -- so that everything an observation
+// shares with its neighbours sits in shared memory: the camera, and the dx of the image's exterior orientation and of the
+// camera parameters (0 where a parameter is fixed: no per-observation column tests).  The dx of the object points is gathered
+// once per pass into a per-point array.  v'Pv = |R v|^2 with the precomputed R.  Block partial sums, then one warp adds them
+// in a fixed order (bitwise reproducible).
+constexpr int kOmegaThreads = 128;
 
-__global__ void __launch_bounds__(kOmegaThreads) k_omega(DevProblem P, const double *__restrict__ dxref,
-                                                         double *__restrict__ partial) {
+__global__ void __launch_bounds__(256) k_gather_point_dx(DevProblem P, const double *__restrict__ dxref, double *__restrict__ dxp) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * (int64_t)P.nPt) return;
+    const int32_t c = P.pt_col[i];
+    dxp[i] = col_active(c) ? dxref[c] : 0.0;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kOmegaThreads, MINB) k_omega(DevProblem P, const WorkItem *__restrict__ work, const double *__restrict__ dxref,
+                                                         const double *__restrict__ dxp, double *__restrict__ partial) {
+    __shared__ CamSmem cs;
+    __shared__ double s_dxe[6], s_dxc[3 + kMaxCoef];
     __shared__ double s_red[kOmegaThreads / 32];
+    __shared__ ImgPose s_pose;
+    const int tid = threadIdx.x;
+    const WorkItem wi = work[blockIdx.x];
+    const int img = wi.img, cam = P.cam_of_img[img];
+    load_camera(P, cam, cs, tid, blockDim.x);
+    if (tid < 14) reinterpret_cast<double *>(&s_pose)[tid] = P.pose[(int64_t)img * kPoseStride + tid];
+    if (tid < 6) {
+        const int32_t c = P.eo_col[6 * (int64_t)img + tid];
+        s_dxe[tid] = col_active(c) ? dxref[c] : 0.0;
+    }
+    {
+        const int nraw = 3 + P.coef_ptr[cam + 1] - P.coef_ptr[cam];
+        const int32_t *cc = P.campos_col + P.cam_kbase[cam];
+        for (int k = tid; k < nraw; k += blockDim.x) s_dxc[k] = col_active(cc[k]) ? dxref[cc[k]] : 0.0;
+    }
+    __syncthreads();
+    const CamView cv = view_of(P, cs);
+    const ImgPose &q = s_pose;
+    const double ex = s_dxe[0], ey = s_dxe[1], ez = s_dxe[2], eo = s_dxe[3], ep = s_dxe[4], ek = s_dxe[5];
+    const double cx0 = s_dxc[0], cy0 = s_dxc[1], cc0 = s_dxc[2];
     double local = 0.0;
-    for (int64_t j = P.obs0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < P.obs1; j += (int64_t)gridDim.x * blockDim.x) {
-        const int img = P.img_of_obs[j], cam = P.cam_of_img[img], pt = P.obj_idx[j];
-        const ImgPose q = load_pose(P.pose, img);
-        const CamView cv = view_global(P, cam);
-        const int32_t *ccol = P.coef_col + P.coef_ptr[cam];
+    for (int64_t j = wi.begin + tid; j < wi.end; j += kOmegaThreads) {
+        const int pt = P.obj_idx[j];
+        const double2 xyo = reinterpret_cast<const double2 *>(P.xy)[j];
+        const double r00 = P.rw[3 * j], r01 = P.rw[3 * j + 1], r11 = P.rw[3 * j + 2];
+        const double *xp = P.xyz + 3 * (int64_t)pt, *dp = dxp + 3 * (int64_t)pt;
         double s0 = 0.0, s1 = 0.0;  // (A dx) rows
         BaseRows r;
-        eval_observation(q, cv, P.xyz[3 * (int64_t)pt], P.xyz[3 * (int64_t)pt + 1], P.xyz[3 * (int64_t)pt + 2],
-                         P.xy[2 * j], P.xy[2 * j + 1], r, [&](int k, double v0, double v1) {
-                             const int32_t c = ccol[k];
-                             if (col_active(c)) { const double dx = dxref[c]; s0 += v0 * dx; s1 += v1 * dx; }
-                         });
-        const int32_t *pc = P.pt_col + 3 * (int64_t)pt, *ic = P.io_col + 3 * cam, *ec = P.eo_col + 6 * (int64_t)img;
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            double dd = 0.0;
-            if (col_active(pc[i])) dd += dxref[pc[i]];
-            if (col_active(ec[i])) dd -= dxref[ec[i]];
-            s0 += r.ax[i] * dd;  s1 += r.ay[i] * dd;
-            if (col_active(ec[3 + i])) { const double dx = dxref[ec[3 + i]]; s0 += r.ax[4 + i] * dx; s1 += r.ay[4 + i] * dx; }
-        }
-        if (col_active(ic[0])) s0 += dxref[ic[0]];
-        if (col_active(ic[1])) s1 += dxref[ic[1]];
-        if (col_active(ic[2])) { const double dx = dxref[ic[2]]; s0 += r.ax[3] * dx; s1 += r.ay[3] * dx; }
+        eval_observation(q, cv, xp[0], xp[1], xp[2], xyo.x, xyo.y, r, [&](int k, double v0, double v1) {
+            const double dx = s_dxc[3 + k];
+            s0 += v0 * dx;  s1 += v1 * dx;
+        });
+        const double d0 = dp[0] - ex, d1 = dp[1] - ey, d2 = dp[2] - ez;      // X0,Y0,Z0 columns = -(X,Y,Z) columns
+        s0 += r.ax[0] * d0 + r.ax[1] * d1 + r.ax[2] * d2 + r.ax[4] * eo + r.ax[5] * ep + r.ax[6] * ek + cx0 + r.ax[3] * cc0;
+        s1 += r.ay[0] * d0 + r.ay[1] * d1 + r.ay[2] * d2 + r.ay[4] * eo + r.ay[5] * ep + r.ay[6] * ek + cy0 + r.ay[3] * cc0;
         const double v0 = r.w0 - s0, v1 = r.w1 - s1;
-        double p00, p01, p11;
-        point_weight(P.sigma2, P.var[2 * j], P.var[2 * j + 1], P.rho[j], p00, p01, p11);
-        local += v0 * (p00 * v0 + p01 * v1) + v1 * (p01 * v0 + p11 * v1);
+        const double t0 = r00 * v0 + r01 * v1, t1 = r11 * v1;
+        local += t0 * t0 + t1 * t1;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = local;
+    if ((tid & 31) == 0) s_red[tid >> 5] = local;
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         double s = 0.0;
         for (int i = 0; i < kOmegaThreads / 32; i++) s += s_red[i];
         partial[blockIdx.x] = s;
@@ -619,14 +701,17 @@ __global__ void k_omega_final(const double *__restrict__ partial, int n, double 
 
 // omega_out[0] = image points part
 void launch_omega(const DevProblem &P, const AssemblyScratch &S, const double *dxref, double *omega_out, cudaStream_t s) {
-    if (P.obs1 <= P.obs0) {
+    if (P.obs1 <= P.obs0 || S.nWork == 0) {
         cudaMemsetAsync(omega_out, 0, sizeof(double), s);
         return;
     }
     g_launch_count++;
-    k_omega<<<S.omegaBlocks, kOmegaThreads, 0, s>>>(P, dxref, S.omega_partial);
+    k_gather_point_dx<<<(unsigned)((3 * (int64_t)P.nPt + 255) / 256), 256, 0, s>>>(P, dxref, S.dxp);
     g_launch_count++;
-    k_omega_final<<<1, 32, 0, s>>>(S.omega_partial, S.omegaBlocks, omega_out);
+    if (sweep_min_blocks() >= 4) k_omega<4><<<S.nWork, kOmegaThreads, 0, s>>>(P, S.work, dxref, S.dxp, S.omega_partial);
+    else k_omega<1><<<S.nWork, kOmegaThreads, 0, s>>>(P, S.work, dxref, S.dxp, S.omega_partial);
+    g_launch_count++;
+    k_omega_final<<<1, 32, 0, s>>>(S.omega_partial, S.nWork, omega_out);
 }
 
 // ---- matrix-free product with the bordered normal matrix (verification entry point jaicov_normal_product) -------------

@@ -33,6 +33,23 @@ struct CudaError {
         if (e__ != cudaSuccess) throw ::jaicov::CudaError{e__, #expr, __FILE__, __LINE__}; \
     } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: one flag per device ordinal, so that handles on several
+// GPUs of one process (and on several host threads) each opt in on their own device
+struct PerDeviceOnce {
+    std::atomic<bool> done[64];
+    PerDeviceOnce() { for (auto &d : done) d.store(false); }
+    template <class F>
+    void run(F &&f) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64) { f(); return; }
+        if (!done[dev].load(std::memory_order_acquire)) {
+            f();            // idempotent: two threads racing here both set the same value
+            done[dev].store(true, std::memory_order_release);
+        }
+    }
+};
+
 // Flattened problem resident in HBM (structure-of-arrays; all pointers are device pointers).
 struct DevProblem {
     // cameras
@@ -43,6 +60,7 @@ struct DevProblem {
     int32_t *coef_ptr = nullptr;    // [nCam+1]
     int32_t *coef_type = nullptr, *coef_order = nullptr, *coef_col = nullptr;  // [nCoef]
     double *coef_val = nullptr;     // [nCoef]
+    double *coef_r0pow = nullptr;   // [nCoef] r0^(2 order) of the coefficient's camera (radial / distance polynomials)
     int32_t *zern_m = nullptr;      // [nCoef]
     int32_t *zern_ptr = nullptr;    // [nCoef+1]
     int32_t *zern_p = nullptr;
@@ -61,6 +79,7 @@ struct DevProblem {
     int64_t m = 0;
     int32_t *obj_idx = nullptr;
     double *xy = nullptr, *var = nullptr, *rho = nullptr;
+    double *rw = nullptr;           // [3 m] r00, r01, r11 with P = R'R (weights are constant over the passes)
     int32_t *img_of_obs = nullptr;  // [m]
     int64_t *pt_obs_ptr = nullptr;  // [nPt+1] CSC: observations of every object point
     int64_t *pt_obs = nullptr;      // [m]
@@ -100,19 +119,23 @@ struct AssemblyScratch {
     double *cam_sum = nullptr;      // [nCam][kc*(kc+1)] sum over this rank's images (all-reduced across ranks)
     int kcMax = 0;
     double *pt_partial = nullptr;   // [nPt][3][8 ntPt]
-    double *omega_partial = nullptr;  // [omegaBlocks + 2]
-    int omegaBlocks = 0;
+    double *omega_partial = nullptr;  // [nWork + 2]
+    double *dxp = nullptr;          // [3 nPt] dx of the object coordinates (0 where fixed), gathered per pass for Omega
 };
 
 void launch_pose(const DevProblem &P, cudaStream_t s);
-// assembly in two halves: `local` = sweeps over this rank's images (unique EO blocks into M, packed per-point and
-// per-camera partial sums); `shared` = scatter of the (all-reduced) partial sums into M / rhs
-void launch_assemble_local(const DevProblem &P, const AssemblyScratch &S, double *M, double *rhs, cudaStream_t s);
-void launch_assemble_shared(const DevProblem &P, const AssemblyScratch &S, double *M, double *rhs, cudaStream_t s);
-inline void launch_assemble(const DevProblem &P, const AssemblyScratch &S, double *M, double *rhs, cudaStream_t s) {
-    launch_assemble_local(P, S, M, rhs, s);
-    launch_assemble_shared(P, S, M, rhs, s);
-}
+void launch_obs_weights(const DevProblem &P, double *rw, cudaStream_t s);
+// Camera group of the by-point sweep: cameras [cam0, cam1) with kraw raw parameters in total, Gram rows of 8 nt columns
+struct PtGroup { int cam0, cam1, kraw, nt; };
+// assembly of the image points in pieces, so that a multi-GPU run can all-reduce in between (api.cu: assemble):
+//   launch_assemble_images: sweeps over this rank's images (unique EO blocks into M, per-camera sums);
+//   launch_by_point:        per-point partial sums of one camera group;
+//   launch_camera_scatter / launch_point_scatter: scatter of the (all-reduced) sums into M / rhs
+void launch_assemble_images(const DevProblem &P, const AssemblyScratch &S, double *M, double *rhs, cudaStream_t s);
+void launch_by_point(const DevProblem &P, const AssemblyScratch &S, const PtGroup &g, cudaStream_t s);
+void launch_camera_scatter(const DevProblem &P, const AssemblyScratch &S, double *M, double *rhs, cudaStream_t s);
+void launch_point_scatter(const DevProblem &P, const AssemblyScratch &S, const PtGroup &g, int kbase0, double *M, double *rhs,
+                          cudaStream_t s);
 void launch_omega(const DevProblem &P, const AssemblyScratch &S, const double *dxref, double *omega_out, cudaStream_t s);
 void launch_eval_k1(const DevProblem &P, int ns_max, double *a, double *w, double *p, cudaStream_t s);
 void launch_scale_bars(const DevProblem &P, double *M, double *rhs, cudaStream_t s);

@@ -206,11 +206,8 @@ __global__ void __launch_bounds__(GemmShape<BMT>::THREADS, GemmShape<BMT>::CTAS_
 template <int AL, int BL, int BMT>
 static void launch_gemm_t(const GemmDesc &g, int64_t tiles, cudaStream_t s) {
     constexpr int BM = GemmShape<BMT>::ROWS;
-    static bool attr = false;
-    if (!attr) {
-        JCHECK(cudaFuncSetAttribute(k_gemm<AL, BL, BMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmShape<BMT>::SMEM));
-        attr = true;
-    }
+    static PerDeviceOnce once;
+    once.run([] { JCHECK(cudaFuncSetAttribute(k_gemm<AL, BL, BMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmShape<BMT>::SMEM)); });
     g_launch_count++;
     constexpr int NT = GemmShape<BMT>::THREADS;
     constexpr size_t SM = GemmShape<BMT>::SMEM;
@@ -438,11 +435,8 @@ __global__ void __launch_bounds__(DTHREADS, 1) k_potrf_diag(double *__restrict__
 }
 
 void launch_potrf_diag(double *A, int64_t ld, double *dinv, int row0, int *info, cudaStream_t s) {
-    static bool attr = false;
-    if (!attr) {
-        JCHECK(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
-        attr = true;
-    }
+    static PerDeviceOnce once;
+    once.run([] { JCHECK(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM)); });
     g_launch_count++;
     k_potrf_diag<<<1, DTHREADS, DIAG_SMEM, s>>>(A, ld, dinv, row0, info);
 }

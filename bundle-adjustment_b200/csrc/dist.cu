@@ -21,6 +21,7 @@ struct NcclApi {
     void *lib = nullptr;
     int (*GetUniqueId)(NcclUniqueId *) = nullptr;
     int (*CommInitRank)(void **, int, NcclUniqueId, int) = nullptr;
+    int (*CommInitAll)(void **, int, const int *) = nullptr;
     int (*Broadcast)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     int (*CommDestroy)(void *) = nullptr;
@@ -44,6 +45,7 @@ void load_nccl() {
     g_nccl.lib = lib;
     bind(g_nccl.GetUniqueId, "ncclGetUniqueId");
     bind(g_nccl.CommInitRank, "ncclCommInitRank");
+    bind(g_nccl.CommInitAll, "ncclCommInitAll");
     bind(g_nccl.Broadcast, "ncclBroadcast");
     bind(g_nccl.AllReduce, "ncclAllReduce");
     bind(g_nccl.CommDestroy, "ncclCommDestroy");
@@ -61,11 +63,24 @@ void nccl_unique_id(NcclUniqueId *out) {
     nccl_check(g_nccl.GetUniqueId(out), "ncclGetUniqueId");
 }
 
+// one communicator per device of ONE process (the single-process multi-GPU handle): comms[i] belongs to devices[i]
+void nccl_comm_init_all(void **comms, int n, const int *devices) {
+    load_nccl();
+    nccl_check(g_nccl.CommInitAll(comms, n, devices), "ncclCommInitAll");
+}
+
 void DistContext::init(int rank_, int world_, const NcclUniqueId &id) {
     load_nccl();
+    void *c = nullptr;
+    nccl_check(g_nccl.CommInitRank(&c, world_, id, rank_), "ncclCommInitRank");
+    adopt(rank_, world_, c);
+}
+
+// streams and events on the CURRENT device (the one the communicator belongs to)
+void DistContext::adopt(int rank_, int world_, void *comm_) {
     rank = rank_;
     world = world_;
-    nccl_check(g_nccl.CommInitRank(&comm, world, id, rank), "ncclCommInitRank");
+    comm = comm_;
     int lo = 0, hi = 0;
     JCHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     JCHECK(cudaStreamCreateWithPriority(&net, cudaStreamNonBlocking, hi));

@@ -7,6 +7,7 @@ namespace jaicov {
 struct NcclUniqueId { char internal[128]; };
 
 void nccl_unique_id(NcclUniqueId *out);
+void nccl_comm_init_all(void **comms, int n, const int *devices);
 
 struct DistContext {
     int rank = 0, world = 1;
@@ -17,6 +18,7 @@ struct DistContext {
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_bcast[2] = {nullptr, nullptr}, ev_unpacked[2] = {nullptr, nullptr};
     cudaEvent_t ev_tmp = nullptr;
     void init(int rank, int world, const NcclUniqueId &id);
+    void adopt(int rank, int world, void *comm);
     void destroy();
     void allreduce_sum(double *buf, size_t count, cudaStream_t s);
 };

@@ -43,6 +43,7 @@ struct CamView {
     const int32_t *type;      // [ncoef] ParameterType id
     const int32_t *order;     // [ncoef]
     const double *val;        // [ncoef]
+    const double *r0pow;      // [ncoef] r0^(2 order): the constant subtracted by the radial / distance polynomials (:58,66)
     // Zernike table (global): per coefficient (global index base k0): m, term range; per term: exponent p, coefficient c
     const int32_t *zern_m;    // indexed by local coefficient position
     const int32_t *zern_ptr;  // [ncoef+1] local positions -> term range
@@ -89,54 +90,68 @@ __host__ __device__ __forceinline__ ImgPose make_pose(const double *eo) {
 
 // Evaluate one observation.  sink(k, v0, v1) receives the own-column entries of coefficient k (local position in
 // the camera's list) exactly once per coefficient.
-template <class Sink>
-__host__ __device__ __forceinline__ void eval_observation(const ImgPose &q, const CamView &cam, double X, double Y, double Z,
-                                                 double xobs, double yobs, BaseRows &r, Sink &&sink) {
+//
+// Arithmetic (round 2; same formulas, fewer FP64 instructions -- the three sweeps that call this are FP64-issue bound, ncu in
+// profiles/r02_*): one reciprocal of N instead of 14 divisions by it; every model's 2 x 2 chain-rule factor d(delta)/d(xs, ys) is
+// SUMMED first and applied to the base partials once at the end -- DistortionModelFactory.apply adds
+// (d delta_x / d xs) px_i + (d delta_x / d ys) py_i with the BASE partials px, py for every model (:33-101), so the sum over models
+// factors out exactly; the explicit N-chain of the distance model (:105-159) factors the same way; r0^(2e) comes from a per-
+// coefficient table (it is a constant of the camera).  Results differ from the term-by-term order by rounding only (~1e-16
+// relative; the per-entry parity test against the oracle holds at 1e-11).  WITH_EO = false skips the omega / phi / kappa partials
+// (the by-point sweep does not use them).
+template <bool WITH_EO, class Sink>
+__host__ __device__ __forceinline__ void eval_observation_t(const ImgPose &q, const CamView &cam, double X, double Y, double Z,
+                                                            double xobs, double yobs, BaseRows &r, Sink &&sink) {
+    constexpr int NB = WITH_EO ? 7 : 4;
     const double x0 = cam.io[0], y0 = cam.io[1], c = cam.io[2];
     const double dX = X - q.X0, dY = Y - q.Y0, dZ = Z - q.Z0;
     const double kx = q.r11 * dX + q.r21 * dY + q.r31 * dZ;
     const double ky = q.r12 * dX + q.r22 * dY + q.r32 * dZ;
     const double N = q.r13 * dX + q.r23 * dY + q.r33 * dZ;
-    const double kxN = kx / N, kyN = ky / N;
+    const double iN = 1.0 / N;
+    const double kxN = kx * iN, kyN = ky * iN;
     const double xs = -c * kxN, ys = -c * kyN;
 
     // base partials, PartialDerivativeFactory.java:157-189
-    double px[7], py[7];
-    px[0] = -(q.r13 * xs + c * q.r11) / N;
-    px[1] = -(q.r23 * xs + c * q.r21) / N;
-    px[2] = -(q.r33 * xs + c * q.r31) / N;
+    double px[NB], py[NB];
+    px[0] = -(q.r13 * xs + c * q.r11) * iN;
+    px[1] = -(q.r23 * xs + c * q.r21) * iN;
+    px[2] = -(q.r33 * xs + c * q.r31) * iN;
     px[3] = -kxN;
-    const double tO = q.r33 * dY - q.r23 * dZ;
-    const double tP = ky * q.sinK - kx * q.cosK;
-    px[4] = (xs * tO + c * (q.r31 * dY - q.r21 * dZ)) / N;
-    px[5] = (xs * tP + c * N * q.cosK) / N;
-    px[6] = ys;
-    py[0] = -(q.r13 * ys + c * q.r12) / N;
-    py[1] = -(q.r23 * ys + c * q.r22) / N;
-    py[2] = -(q.r33 * ys + c * q.r32) / N;
+    py[0] = -(q.r13 * ys + c * q.r12) * iN;
+    py[1] = -(q.r23 * ys + c * q.r22) * iN;
+    py[2] = -(q.r33 * ys + c * q.r32) * iN;
     py[3] = -kyN;
-    py[4] = (ys * tO + c * (q.r32 * dY - q.r22 * dZ)) / N;
-    py[5] = (ys * tP - c * N * q.sinK) / N;
-    py[6] = -xs;
-#pragma unroll
-    for (int i = 0; i < 7; i++) { r.ax[i] = px[i]; r.ay[i] = py[i]; }
-    r.w0 = xobs - (x0 + xs);
-    r.w1 = yobs - (y0 + ys);
-
-    // DistortionModelFactory.apply, :33-101
+    if (WITH_EO) {
+        const double tO = q.r33 * dY - q.r23 * dZ;
+        const double tP = ky * q.sinK - kx * q.cosK;
+        px[NB - 3] = (xs * tO + c * (q.r31 * dY - q.r21 * dZ)) * iN;
+        px[NB - 2] = (xs * tP + c * N * q.cosK) * iN;
+        px[NB - 1] = ys;
+        py[NB - 3] = (ys * tO + c * (q.r32 * dY - q.r22 * dZ)) * iN;
+        py[NB - 2] = (ys * tP - c * N * q.sinK) * iN;
+        py[NB - 1] = -xs;
+    }
+    double w0 = xobs - (x0 + xs), w1 = yobs - (y0 + ys);
+    // accumulated chain-rule factors: [ax; ay] = [[Dxx, Dxy], [Dyx, Dyy]] [px; py] + [gx; gy] dN/dp
+    double Dxx = 1.0, Dxy = 0.0, Dyx = 0.0, Dyy = 1.0, gxs = 0.0, gys = 0.0;
     auto chain = [&](double dlx, double dly, double dXxs, double dXys, double dYxs, double dYys) {
-        r.w0 -= dlx;
-        r.w1 -= dly;
-#pragma unroll
-        for (int i = 0; i < 7; i++) {
-            r.ax[i] += dXxs * px[i] + dXys * py[i];
-            r.ay[i] += dYxs * px[i] + dYys * py[i];
-        }
+        w0 -= dlx;  w1 -= dly;
+        Dxx += dXxs;  Dxy += dXys;  Dyx += dYxs;  Dyy += dYys;
     };
 
     const double r2 = xs * xs + ys * ys;
     const double xxs2 = 2.0 * xs * xs, yys2 = 2.0 * ys * ys, xys2 = 2.0 * xs * ys;
     const double r02 = cam.r0 * cam.r0;
+    // r2^(e) for the polynomial models: the orders of consecutive coefficients usually differ by one, so the last power is
+    // kept and extended by one multiplication instead of a square-and-multiply loop per coefficient
+    int pe = 0;
+    double pv = 1.0;
+    auto r2pow = [&](int e) {
+        if (e == pe + 1) { pv *= r2; pe = e; }
+        else if (e != pe) { pv = ipow(r2, e); pe = e; }
+        return pv;
+    };
     int k = 0;
     const int nc = cam.ncoef;
     while (k < nc) {
@@ -161,7 +176,7 @@ __host__ __device__ __forceinline__ void eval_observation(const ImgPose &q, cons
             while (kb < nc && cam.type[kb] == JAICOV_PT_TANGENTIAL_B) {
                 const double bi = cam.val[kb];
                 const int e = cam.order[kb];
-                const double rim1 = ipow(r2, e - 1);
+                const double rim1 = r2pow(e - 1);
                 const double ri = rim1 * r2;
                 const double dT = bi * ri;
                 sum += dT;
@@ -178,8 +193,8 @@ __host__ __device__ __forceinline__ void eval_observation(const ImgPose &q, cons
         } else if (t == JAICOV_PT_RADIAL_A) {  // RadiallySymmetricDistortionModelFactory.java:39-90
             const double ai = cam.val[k];
             const int e = cam.order[k];
-            const double rim1 = ipow(r2, e - 1);
-            const double dRi = rim1 * r2 - ipow(r02, e);
+            const double rim1 = r2pow(e - 1);
+            const double dRi = rim1 * r2 - cam.r0pow[k];
             const double dRad = ai * dRi;
             const double cR = ai * e * rim1;
             chain(xs * dRad, ys * dRad, xxs2 * cR + dRad, xys2 * cR, xys2 * cR, yys2 * cR + dRad);
@@ -188,21 +203,16 @@ __host__ __device__ __forceinline__ void eval_observation(const ImgPose &q, cons
         } else if (t == JAICOV_PT_DISTANCE_D) {  // RadialDistanceDistortionModelFactory.java:39-161
             const double di = cam.val[k];
             const int e = cam.order[k];
-            const double rim1 = ipow(r2, e - 1);
-            const double dRi = rim1 * r2 - ipow(r02, e);
-            const double dD = (di * dRi) / N;
+            const double rim1 = r2pow(e - 1);
+            const double dRi = rim1 * r2 - cam.r0pow[k];
+            const double dD = (di * dRi) * iN;
             const double dlx = xs * dD, dly = ys * dD;
-            const double cR = (di * e * rim1) / N;
+            const double cR = (di * e * rim1) * iN;
             chain(dlx, dly, xxs2 * cR + dD, xys2 * cR, xys2 * cR, yys2 * cR + dD);
-            sink(k, (xs * dRi) / N, (ys * dRi) / N);
-            // explicit chain through N (:67-77, :105-159); dN/dc = 0, dN/dkappa = 0
-            const double gx = -dlx / N, gy = -dly / N;
-            const double pN[7] = {q.r13, q.r23, q.r33, 0.0, -q.r33 * dY + q.r23 * dZ, kx * q.cosK - ky * q.sinK, 0.0};
-#pragma unroll
-            for (int i = 0; i < 7; i++) {
-                r.ax[i] += pN[i] * gx;
-                r.ay[i] += pN[i] * gy;
-            }
+            sink(k, (xs * dRi) * iN, (ys * dRi) * iN);
+            // explicit chain through N (:67-77, :105-159): coefficient -delta / N of dN/dp, applied after the loop
+            gxs -= dlx * iN;
+            gys -= dly * iN;
             k++;
         } else if (t == JAICOV_PT_ZERNIKE_Z) {  // ZernikeDistortionModelFactory.java:41-137 (gradient model)
             const double xxs = xs * xs, yys = ys * ys, xys = xs * ys;
@@ -274,6 +284,30 @@ __host__ __device__ __forceinline__ void eval_observation(const ImgPose &q, cons
             k++;
         }
     }
+    // apply the accumulated factors once; dN/d(X,Y,Z) = (r13, r23, r33), dN/dc = 0, dN/d omega = -r33 dY + r23 dZ,
+    // dN/d phi = kx cos(kappa) - ky sin(kappa), dN/d kappa = 0   (RadialDistanceDistortionModelFactory.java:67-77)
+    const double pN0 = q.r13, pN1 = q.r23, pN2 = q.r33;
+    r.ax[0] = Dxx * px[0] + Dxy * py[0] + pN0 * gxs;  r.ay[0] = Dyx * px[0] + Dyy * py[0] + pN0 * gys;
+    r.ax[1] = Dxx * px[1] + Dxy * py[1] + pN1 * gxs;  r.ay[1] = Dyx * px[1] + Dyy * py[1] + pN1 * gys;
+    r.ax[2] = Dxx * px[2] + Dxy * py[2] + pN2 * gxs;  r.ay[2] = Dyx * px[2] + Dyy * py[2] + pN2 * gys;
+    r.ax[3] = Dxx * px[3] + Dxy * py[3];              r.ay[3] = Dyx * px[3] + Dyy * py[3];
+    if (WITH_EO) {
+        const double pN4 = -q.r33 * dY + q.r23 * dZ, pN5 = kx * q.cosK - ky * q.sinK;
+        r.ax[4] = Dxx * px[NB - 3] + Dxy * py[NB - 3] + pN4 * gxs;  r.ay[4] = Dyx * px[NB - 3] + Dyy * py[NB - 3] + pN4 * gys;
+        r.ax[5] = Dxx * px[NB - 2] + Dxy * py[NB - 2] + pN5 * gxs;  r.ay[5] = Dyx * px[NB - 2] + Dyy * py[NB - 2] + pN5 * gys;
+        r.ax[6] = Dxx * px[NB - 1] + Dxy * py[NB - 1];              r.ay[6] = Dyx * px[NB - 1] + Dyy * py[NB - 1];
+    } else {
+        r.ax[4] = r.ax[5] = r.ax[6] = 0.0;
+        r.ay[4] = r.ay[5] = r.ay[6] = 0.0;
+    }
+    r.w0 = w0;
+    r.w1 = w1;
+}
+
+template <class Sink>
+__host__ __device__ __forceinline__ void eval_observation(const ImgPose &q, const CamView &cam, double X, double Y, double Z,
+                                                          double xobs, double yobs, BaseRows &r, Sink &&sink) {
+    eval_observation_t<true>(q, cam, X, Y, Z, xobs, yobs, r, sink);
 }
 
 // Weight matrix of an image point, PartialDerivativeFactory.java:296-319: returns P00, P01, P11

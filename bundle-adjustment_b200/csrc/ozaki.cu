@@ -546,11 +546,8 @@ OzScratch g_oz;
 
 template <int S, int CL>
 void launch_tiles(const CUtensorMap &ma, const CUtensorMap &mb, const OzGemmArgs &a, int64_t tiles, int grid_y, cudaStream_t s) {
-    static bool attr = false;
-    if (!attr) {
-        JCHECK(cudaFuncSetAttribute(k_gemm_oz<S, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<S>::SMEM));
-        attr = true;
-    }
+    static PerDeviceOnce once;
+    once.run([] { JCHECK(cudaFuncSetAttribute(k_gemm_oz<S, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzCfg<S>::SMEM)); });
     g_launch_count++;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(tiles * 2), (unsigned)grid_y);   // x: row tile (or tile list) x two 64-column halves; y: column-table slot

@@ -98,7 +98,8 @@ typedef struct {
     int32_t apply_aposteriori;  /* applyAposterioriVarianceOfUnitWeight, :1185 (default 1, :86) */
     int32_t device;             /* CUDA device ordinal this handle binds to */
     int32_t solver;             /* JAICOV_SOLVER_* (default AUTO); the environment variable JAICOV_SOLVER=dense|structured overrides */
-    int32_t reserved0;
+    int32_t n_devices;          /* 0 / 1: one GPU.  k > 1: ONE handle, ONE process, k GPUs [device, device + k) -- what a single JVM thread
+                                 * can drive (BundleAdjustment.estimateModel runs on one thread, :203); see "multi-GPU" below */
     double sigma2apriori;       /* min(1, min variance) as accumulated by addObservationGroup, :637-643; <=0 -> 1 (:221) */
     double damping_value;       /* Levenberg-Marquardt lambda >= 0, setLevenbergMarquardtDampingValue :1189; 0 = plain Gauss-Newton (:96) */
 } jaicov_options;
@@ -137,13 +138,22 @@ int64_t jaicov_release_cached_memory(void);
 /* diagnostic: number of CUDA kernels this library has launched in this process so far */
 int64_t jaicov_launch_count(void);
 
-/* ---- multi-GPU: one process per GPU, NCCL over NVLink ---------------------------------------------------------------
- * rank 0 calls jaicov_nccl_unique_id and ships the 128 bytes to the other processes (torch.distributed, MPI, a file);
- * every process then calls jaicov_dist_init on its handle BEFORE the set_* calls take effect.  Every rank passes the
- * SAME full problem; the library shards the images (contiguous ranges balanced by observation count), all-reduces
- * the shared normal-equation pieces, factors with a block-column-cyclic Cholesky (panel broadcasts) and inverts its
- * own column tiles of Qxx.  jaicov_get_qxx_block then returns PARTIAL blocks (zeros for entries owned elsewhere;
- * the sum over ranks is the block), jaicov_get_qxx_local the rank's column tiles as stored. */
+/* ---- multi-GPU ------------------------------------------------------------------------------------------------------
+ * Two ways to put one adjustment on several GPUs of one box; both run the same device code (image-sharded assembly + NCCL
+ * all-reduce of the shared normal-equation pieces, block-column-cyclic Cholesky with panel broadcasts over NVLink, every GPU
+ * inverts its own column tiles of Qxx):
+ *
+ * (1) jaicov_options.n_devices = k: a SINGLE handle in a SINGLE process -- the form a Java host uses.  Every call is the
+ *     same as on one GPU; internally each GPU gets its own host thread and its own communicator of one ncclCommInitAll clique
+ *     (the progress listener is still only called on the calling thread).  All getters return complete results:
+ *     jaicov_get_qxx_packed gathers the column tiles over NVLink (peer-to-peer) onto the first device and ships the MTJ-packed
+ *     array in one stream; jaicov_get_qxx_block / _submatrix / jaicov_propagate_eo_transform sum the devices' parts.
+ *
+ * (2) one process per GPU (torchrun, MPI): rank 0 calls jaicov_nccl_unique_id and ships the 128 bytes to the other processes;
+ *     every process then calls jaicov_dist_init on its handle BEFORE the set_* calls take effect.  Every rank passes the
+ *     SAME full problem.  jaicov_get_qxx_block then returns PARTIAL blocks (zeros for entries owned elsewhere; the sum over
+ *     ranks is the block), jaicov_get_qxx_local the rank's column tiles as stored.  An interrupt flag must be passed by every
+ *     rank or by none (the ranks agree on the decision with one scalar all-reduce per check). */
 /* pure host function: the contiguous image range [img_begin, img_end) rank `rank` of `world` works on (boundaries at
  * the images where the cumulative observation count crosses rank * m / world) */
 int32_t jaicov_shard_images(int32_t n_img, const int64_t *pt_ptr, int32_t world, int32_t rank, int32_t *img_begin, int32_t *img_end);

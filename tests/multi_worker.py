@@ -1,5 +1,10 @@
 """Worker of the multi-GPU parity test: run under torchrun, one process per GPU.  Every rank runs the same adjustment
-through the distributed C-ABI path; rank 0 compares with the CPU oracle and prints one JSON line."""
+through the distributed C-ABI path; rank 0 compares with the CPU oracle and prints one JSON line.
+
+  torchrun ... tests/multi_worker.py <scene> [dense|structured|auto]
+  scenes: example | cfg2 | cfg3 | cfg4 | cfg4mid (100 images x 2 700 targets, n = 8 720: compared with the blocked fast oracle)
+  JAICOV_PANEL_TILES=1 makes the block-column panels of the distributed Cholesky 128 columns wide, so that even the small
+  scenes run many panels per rank (look-ahead, double-buffered staging, trapezoid updates: cfg2 -> 15 panels, cfg4mid -> 69)."""
 import json
 import os
 import sys
@@ -11,6 +16,8 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bundle_adjustment_b200 as ba  # noqa: E402
+from bundle_adjustment_b200 import verify  # noqa: E402
+from oracle.fast_oracle import FastOracle  # noqa: E402
 from oracle.oracle import Oracle  # noqa: E402
 from tests.helpers import flat_problem  # noqa: E402
 from tests.scenes import example_scene, synthetic_scene  # noqa: E402
@@ -27,6 +34,8 @@ def main():
         scene = synthetic_scene(3, images=12, targets=150)[0]
     elif which == 'cfg4':
         scene = synthetic_scene(4, images=30, targets=300)[0]
+    elif which == 'cfg4mid':
+        scene = synthetic_scene(4, images=100, targets=2700)[0]
     else:
         scene = synthetic_scene(2)[0]
     adj, flat = flat_problem(scene)
@@ -57,8 +66,15 @@ def main():
         local_err = max(local_err, float(np.abs(np.where(mask, got - ref, 0.0)).max()))
     le = torch.tensor([local_err], dtype=torch.float64, device='cuda')
     dist.all_reduce(le, op=dist.ReduceOp.MAX)
+
+    def reduce_sum(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        dist.all_reduce(t)
+        return t.cpu().numpy()
+    chk = verify.check_pass(s, columns=verify.sample_columns(n, n - u, world=world, panel=128 * int(os.environ.get('JAICOV_PANEL_TILES', '8'))),
+                            reduce_sum=reduce_sum, omega=st.omega, values_updated=True)
     if rank == 0:
-        o = Oracle(scene)
+        o = (FastOracle if which == 'cfg4mid' else Oracle)(scene)
         so = o.estimate()
         Qo = o.qxx_dense()
         Qg = blk.cpu().numpy()
@@ -78,7 +94,8 @@ def main():
         print(json.dumps({'scene': which, 'world': world, 'solver_used': st.solver_used, 'rc': rc, 'rc_oracle': so, 'iterations': st.iterations,
                           'iterations_oracle': len(o.history), 'sigma2_rel_err': abs(st.sigma2aposteriori - s2o) / s2o,
                           'qxx_scaled_err': errq, 'param_rel_err': errx, 'qxx_local_vs_block_maxabs': float(le[0]), 'ms_last_pass': st.ms_total,
-                          'ms_factor': st.ms_factor, 'ms_inverse': st.ms_inverse}), flush=True)
+                          'ms_factor': st.ms_factor, 'ms_inverse': st.ms_inverse, 'n': n, 'panel_tiles': int(os.environ.get('JAICOV_PANEL_TILES', '8')),
+                          'verify': {k: chk[k] for k in ('datum_residual', 'cofactor_residual', 'omega_rel_diff')}}), flush=True)
     s.close()
     dist.barrier()
     dist.destroy_process_group()

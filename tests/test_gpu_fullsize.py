@@ -84,9 +84,9 @@ def compare_full(config, solver):
     assert errq <= TOL_Q
     assert errx <= TOL_X
     # the size-independent identities the benchmark relies on at config 5, here next to a direct comparison
-    chk = verify.check_pass(adj._session, columns=verify.sample_columns(n, d), omega=st.omega)
-    print('   verify: solve %.2e, datum %.2e, cofactor columns %.2e, Omega identity %.2e'
-          % (chk['solve_residual'], chk['datum_residual'], chk['cofactor_residual'], chk.get('omega_rel_diff', 0.0)))
+    chk = verify.check_pass(adj._session, columns=verify.sample_columns(n, d), omega=st.omega, values_updated=True)
+    print('   verify: datum %.2e, cofactor columns %.2e, Omega identity %.2e'
+          % (chk['datum_residual'], chk['cofactor_residual'], chk.get('omega_rel_diff', 0.0)))
     verify.assert_ok(chk)
     return adj, o
 

@@ -5,6 +5,7 @@ import os
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 
 import bundle_adjustment_b200 as ba
@@ -22,12 +23,16 @@ def _ngpu():
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason='needs two GPUs')
-@pytest.mark.parametrize('which,solver', [('example', 'auto'), ('cfg2', 'dense'), ('cfg2', 'structured'), ('cfg3', 'auto'),
-                                          ('cfg4', 'dense'), ('cfg4', 'structured')])
-def test_two_gpu_adjustment_matches_oracle(built, which, solver):
-    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+@pytest.mark.parametrize('which,solver,panel_tiles', [('example', 'auto', 8), ('cfg2', 'dense', 8), ('cfg2', 'structured', 8), ('cfg3', 'auto', 8),
+                                                      ('cfg4', 'dense', 8), ('cfg4', 'structured', 8),
+                                                      # many panels per rank: 128-column panels (15 at cfg2, 69 at n = 8 720)
+                                                      ('cfg2', 'dense', 1), ('example', 'auto', 1), ('cfg4mid', 'dense', 1), ('cfg4mid', 'dense', 2),
+                                                      ('cfg4mid', 'structured', 8)])
+def test_two_gpu_adjustment_matches_oracle(built, which, solver, panel_tiles):
+    world = min(_ngpu(), int(os.environ.get('JAICOV_TEST_WORLD', '2')))
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world), '--master-addr', '127.0.0.1',
            '--master-port', '29531', os.path.join(ROOT, 'tests', 'multi_worker.py'), which, solver]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, JAICOV_PANEL_TILES=str(panel_tiles)))
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     line = [l for l in out.stdout.splitlines() if l.startswith('{')][-1]
     r = json.loads(line)
@@ -40,3 +45,75 @@ def test_two_gpu_adjustment_matches_oracle(built, which, solver):
     assert r['qxx_scaled_err'] <= 1e-8
     assert r['param_rel_err'] <= 1e-10
     assert r['qxx_local_vs_block_maxabs'] == 0.0      # both getters read the same device values
+    assert r['panel_tiles'] == panel_tiles and r['world'] == world
+    v = r['verify']                                    # the identities bench.py checks at config 5 (bundle_adjustment_b200/verify.py)
+    assert max(v['datum_residual'], v['cofactor_residual'], v['omega_rel_diff']) <= 1e-8, v
+
+
+def _packed_to_dense(q, n):
+    D = np.empty((n, n))
+    iu = np.triu_indices(n)
+    D[iu] = q[iu[0] + iu[1] * (iu[1] + 1) // 2]
+    D.T[iu] = D[iu]
+    return D
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason='needs two GPUs')
+@pytest.mark.parametrize('which,solver,panel_tiles', [('cfg2', 'dense', 1), ('cfg2', 'structured', 8), ('example', 'auto', 8), ('cfg4', 'dense', 1)])
+def test_single_process_handle_on_several_gpus(built, monkeypatch, which, solver, panel_tiles):
+    """jaicov_options.n_devices: ONE handle in ONE process drives all GPUs (what a single JVM thread can call) and every
+    getter returns complete results -- the MTJ-packed Qxx (column tiles gathered over NVLink onto the first device), blocks,
+    sub-matrices, dx, values -- equal to the oracle's and to what the same library returns on one GPU."""
+    from oracle.oracle import Oracle
+    from tests.helpers import flat_problem
+    from tests.scenes import example_scene, synthetic_scene
+    from bundle_adjustment_b200 import verify
+    monkeypatch.setenv('JAICOV_PANEL_TILES', str(panel_tiles))
+    mk = {'example': example_scene, 'cfg2': lambda: synthetic_scene(2, images=20, targets=200)[0],
+          'cfg4': lambda: synthetic_scene(4, images=30, targets=300)[0]}[which]
+    adj, flat = flat_problem(mk())
+    sv = {'dense': ba._lib.SOLVER_DENSE, 'structured': ba._lib.SOLVER_STRUCTURED, 'auto': ba._lib.SOLVER_AUTO}[solver]
+    world = min(_ngpu(), int(os.environ.get('JAICOV_TEST_WORLD', '2')))
+    events = []
+    s = ba.Session(sigma2apriori=adj.getVarianceFactorApriori(), solver=sv, n_devices=world)
+    s.set_problem(flat)
+    import threading
+    main_thread = threading.get_ident()
+    rc = s.estimate(progress=lambda st, a, b: events.append((st, threading.get_ident())))
+    assert rc == 1
+    assert events and all(t == main_thread for _st, t in events)          # the listener runs on the calling thread only
+    st = s.stats()
+    n = s.n
+    Qm = _packed_to_dense(s.qxx_packed(), n)
+    # one GPU, same library
+    s1 = ba.Session(sigma2apriori=adj.getVarianceFactorApriori(), solver=sv)
+    s1.set_problem(flat)
+    assert s1.estimate() == 1
+    Q1 = _packed_to_dense(s1.qxx_packed(), n)
+    o = Oracle(mk())
+    assert o.estimate() == 1
+    Qo = o.qxx_dense()
+    d = o.fp.d
+    sg = np.sqrt(np.abs(np.diag(Qo)))
+    sg[:d] = 1.0
+    assert st.iterations == s1.stats().iterations == len(o.history)
+    assert np.max(np.abs(Qm - Qo) / np.outer(sg, sg)) <= 1e-8
+    assert np.max(np.abs(Qm - Q1) / np.outer(sg, sg)) <= 1e-9
+    s2o = o.variance_factor_aposteriori()
+    assert abs(st.sigma2aposteriori - s2o) <= 1e-8 * s2o
+    for vg, v1 in zip(s.values(), s1.values()):
+        np.testing.assert_allclose(vg, v1, rtol=1e-11, atol=1e-11)
+    # the other getters agree with the packed matrix
+    np.testing.assert_array_equal(s.qxx_block(3, 40, 0, n), Qm[3:40])
+    idx = np.array([0, d, d + 5, n // 2, n - 1, d + 130], np.int32)
+    np.testing.assert_array_equal(s.qxx_submatrix(idx, 2.0), 2.0 * Qm[np.ix_(idx, idx)])
+    # and the identities of bundle_adjustment_b200.verify hold through the single handle (normal_product runs on every device)
+    chk = verify.check_pass(s, columns=verify.sample_columns(n, d, world=world, panel=128 * panel_tiles), omega=st.omega, values_updated=True)
+    verify.assert_ok(chk)
+    # a second call re-uses the gathered matrix; a new pass invalidates it
+    np.testing.assert_array_equal(_packed_to_dense(s.qxx_packed(), n), Qm)
+    assert s.iterate(final_pass=True, apply_update=False) == 0
+    Qm2 = _packed_to_dense(s.qxx_packed(), n)
+    assert np.max(np.abs(Qm2 - Qm) / np.outer(sg, sg)) <= 1e-9
+    s.close()
+    s1.close()

@@ -538,3 +538,52 @@ def test_adjustment_matches_executed_reference_vectors(built, name):
     for got, ref in ((xyz.reshape(-1, 3), g('xyz')), (io.reshape(-1, 3), g('io')), (coef, g('coef')), (eo.reshape(-1, 6), g('eo'))):
         # 1e-10 relative, with the floor the other parity tests use for values near zero: 1e-10 of the largest value of the group
         assert (np.abs(got - ref) <= TOL_X * np.maximum(np.abs(ref), np.abs(ref).max() * 1e-3 + 1e-12)).all()
+
+
+@BOTH
+def test_many_cameras_by_point_sweep_in_camera_groups(built, solver):
+    """Six cameras with 13 raw parameters each (78 in total): more than one 72-column Gram row of the by-point sweep holds, so the
+    sweep runs once per camera group (round 1 refused such networks: 'too many camera parameters in total'; the reference has no
+    limit on the number of cameras, PDF:285-445)."""
+    sc = synthetic_scene(4, images=24, targets=90, n_cameras=6)[0]
+    adj, o = compare_adjustment(sc, 'six cameras', solver=solver)
+    assert len(sc['cameras']) == 6 and sum(3 + len(c['coefs']) for c in sc['cameras']) == 78
+
+
+def test_bad_indices_are_illegal_arguments_not_device_faults(built):
+    """Out-of-range indices from a foreign caller come back as JAICOV_ILLEGAL_ARGUMENT (the Java side would throw
+    IllegalArgumentException) instead of an out-of-bounds device read, and the process keeps working afterwards."""
+    sc = synthetic_scene(2, images=6, targets=40)[0]
+    sc['scale_bars'] = [(0, 1, 100.0, 0.05)]
+    adj, flat = flat_problem(sc)
+
+    def attempt(**changes):
+        f = dict(flat)
+        for k, v in changes.items():
+            a = np.array(f[k]).copy()
+            v(a)
+            f[k] = a
+        s = ba.Session(sigma2apriori=adj.getVarianceFactorApriori())
+        s.set_problem(f)
+        with pytest.raises(ba.JaicovError) as e:
+            s.iterate(final_pass=False)
+        assert e.value.code == ba._lib.ILLEGAL_ARGUMENT, e.value
+        s.close()
+        return str(e.value)
+
+    def setter(i, v):
+        def f(a):
+            a[i] = v
+        return f
+    assert 'camera index' in attempt(cam_of_img=setter(2, 7))
+    assert 'scale bar' in attempt(bar_a=setter(0, 40))
+    assert 'scale bar' in attempt(bar_b=setter(0, -1))
+    assert 'pt_ptr' in attempt(pt_ptr=setter(2, 1))
+    assert 'coef_type' in attempt(coef_type=setter(1, 999))
+    assert 'object point index' in attempt(obj_idx=setter(5, 40))
+    assert 'column index' in attempt(eo_col=setter(3, 100000))
+    # the context is intact: a correct problem still runs
+    s = ba.Session(sigma2apriori=adj.getVarianceFactorApriori())
+    s.set_problem(flat)
+    assert s.iterate(final_pass=True) == 0
+    s.close()
