@@ -118,6 +118,11 @@ def fp64_peak_tflops(torch, n=8192, reps=5):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
+# DRAM bytes (read + write) per launch of the dominant kernel launch, from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`
+# (profiles/; key = config for the dense route's single M = W^T W launch, -config for the structured route's Y (Q^T Y^T) launch);
+# None where no capture of this round exists
+TRAFFIC = {}
+
 CPU_SAMPLE = (64, 1500)     # images x targets of the bounded CPU sample: n ~ 4900, ~10-20 s of packed dspsv + dsptri on one core
 
 
@@ -217,6 +222,7 @@ def main():
                     help='route of the headline line: dense = the blocked Cholesky + full inverse the metric names (default); '
                          'the structured (point-block) route is timed next to it and reported under "structured"')
     ap.add_argument('--no-structured', action='store_true')
+    ap.add_argument('--no-other-configs', action='store_true', help='skip the short runs of configs 2 and 4 (N = 1 only)')
     ap.add_argument('--no-check', action='store_true', help='skip the residual / identity verification of the timed pass')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -292,13 +298,14 @@ def main():
     launches0 = L.jaicov_launch_count()
     barrier()
     t0 = time.perf_counter()
-    dev_ms, stage = 0.0, np.zeros(5)
+    dev_ms, stage, sweeps = 0.0, np.zeros(5), np.zeros(3)
     for _ in range(args.steps):
         rc = sess.iterate(final_pass=True, apply_update=False)
         assert rc == 0, rc
         st = sess.stats()
         dev_ms += st.ms_total
         stage += [st.ms_assembly, st.ms_factor, st.ms_solve, st.ms_inverse, st.ms_omega]
+        sweeps += sess.sweep_times()
     barrier()
     wall = time.perf_counter() - t0
     launches = (L.jaicov_launch_count() - launches0) // args.steps
@@ -313,6 +320,7 @@ def main():
     ms_per_step = dev_ms_max / args.steps
     value = args.steps / (dev_ms_max * 1e-3)          # one adjustment over all ranks: whole-job iterations/s
     stage /= args.steps
+    sweeps /= args.steps
 
     # ---- the structured (point-block) route on the same workload, reported next to the headline ----------------------------
     structured = None
@@ -346,6 +354,32 @@ def main():
                                   'observation couples two object points'}
         except ba.JaicovError as e:
             structured = {'unavailable': str(e)}
+
+    # ---- the smaller configurations of BASELINE.json (one GPU): latency-bound passes, reported for context ------------------------------
+    other = None
+    if world == 1 and not args.no_other_configs:
+        other = {}
+        sess.close()
+        for cfg_o in (2, 4):
+            _sc, adj_o, flat_o = workload(cfg_o)
+            for sv in ('dense', 'structured'):
+                so = ba.Session(sigma2apriori=adj_o.getVarianceFactorApriori(), device=local_rank, solver=SOLVER[sv])
+                so.set_problem(flat_o)
+                for _ in range(3):
+                    assert so.iterate(final_pass=True, apply_update=False) == 0
+                k_o = 20 if cfg_o == 2 else 5
+                torch.cuda.synchronize()
+                t_o = time.perf_counter()
+                ms_o = 0.0
+                for _ in range(k_o):
+                    assert so.iterate(final_pass=True, apply_update=False) == 0
+                    ms_o += so.stats().ms_total
+                torch.cuda.synchronize()
+                wall_o = (time.perf_counter() - t_o) / k_o * 1e3
+                other['config%d_%s' % (cfg_o, sv)] = {'ms_per_final_pass_device': ms_o / k_o, 'ms_per_final_pass_wall': wall_o,
+                                                      'n': int(flat_o['n_unknowns']) + int(np.sum(flat_o['free_flags'])),
+                                                      'image_points': int(flat_o['obj_idx'].size)}
+                so.close()
 
     # ---- end to end through the C ABI with host buffers -----------------------------------------------------------------
     def run_e2e(solver):
@@ -416,13 +450,28 @@ def main():
         return
     # ---- roofline of the dominant stage: factor + inverse on FP64 tensor-core GEMM tiles --------------------------------
     peak = fp64_peak_tflops(torch)
+    peaks_file = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    hbm = json.load(open(peaks_file)).get('hbm_gbs') if os.path.exists(peaks_file) else 6650.0
     flops = structured_flops(flat) if structured_used else float(n) ** 3   # n^3/3 (factor) + 2n^3/3 (inverse), SURVEY.md 8(d)
     t_dense = (stage[1] + stage[3]) * 1e-3
     achieved = flops / t_dense / 1e12
-    peaks_file = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    hbm = json.load(open(peaks_file)).get('hbm_gbs') if os.path.exists(peaks_file) else 6650.0
+    achieved_stage = achieved
+    achieved = flops / (ms_per_step * 1e-3) / 1e12      # the WHOLE step (assembly, solves, Omega included), not only the two GEMM stages
+    m_pts = float(flat['obj_idx'].size)
+    sweep_gbs = {}
+    for name_, ms_, bytes_ in (('by_image', sweeps[0], 188.0), ('by_point', sweeps[1], 44.0), ('omega', sweeps[2], 44.0)):
+        # algorithmic bytes per image point: 44 B read (obj_idx 4, xy 16, weights 24); the by-image sweep also writes the
+        # unique 6 x 3 EO x point block (144 B).  With N > 1 every rank sweeps its image shard: per-GPU figures of rank 0
+        if ms_ > 0:
+            gbs = m_pts / world * bytes_ / (ms_ * 1e-3) / 1e9
+            sweep_gbs[name_] = {'ms': ms_, 'algorithmic_GBps': gbs, 'frac_of_hbm_peak': gbs / hbm}
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak * world, 'unit': 'TFLOP/s', 'frac': achieved / (peak * world),
-                'traffic': None, 'peak_per_gpu': peak,
+                'traffic': TRAFFIC.get(args.config if not structured_used else -args.config), 'peak_per_gpu': peak,
+                'frac_factor_inverse_stages': achieved_stage / (peak * world),
+                'observation_sweeps': sweep_gbs,
+                'observation_sweeps_note': 'FP64-issue bound, not HBM bound: ~350 FP64 instructions per image point at 13 camera parameters against '
+                                           '44 B (arithmetic intensity 2x the machine balance of FP64 pipe / HBM): a fully busy FP64 pipe caps them at '
+                                           '~36 % of the HBM peak (DESIGN.md section 5, ncu in profiles/r02_ncu_sweeps_*)',
                 'traffic_note': 'k_gemm is launched thousands of times per pass with different tile counts, so there is no single per-launch '
                                 'figure; ncu --set full of its largest launches (profiles/r01_ncu_full_k_gemm_shape65_summary.txt): LAUUM at '
                                 'config 4 moves 21.4 GB of DRAM traffic for 1.43e12 flop (tensor pipe 94.2 % active), the structured '
@@ -432,7 +481,7 @@ def main():
                           % ('the structured route\'s GEMM' if structured_used else 'n^3'),
                 'peak_source': 'cuBLAS DGEMM 8192^3 via torch.matmul(float64) measured in this run (burst, best of 5); '
                                'MEASURED_PEAKS.json has no FP64 entry',
-                'assembly_gbs': (flat['obj_idx'].size * 44.0) / (stage[0] * 1e-3) / 1e9, 'hbm_peak_gbs': hbm}
+                'hbm_peak_gbs': hbm}
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
@@ -451,6 +500,8 @@ def main():
             'roofline': roofline, 'clocks': clocks, 'gpu_launches': int(launches), 'check': check}
     if e2e:
         line['e2e'] = e2e
+    if other:
+        line['other_configs'] = other
     if structured:
         if 'tflops' in structured:
             structured['frac_of_fp64_peak'] = structured['tflops'] / (peak * world)

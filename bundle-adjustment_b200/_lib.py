@@ -28,7 +28,7 @@ EXPORTS = [
     'jaicov_get_stats', 'jaicov_get_values', 'jaicov_get_dx', 'jaicov_get_qxx_packed', 'jaicov_get_qxx_block',
     'jaicov_get_qxx_diag', 'jaicov_get_qxx_submatrix', 'jaicov_eval_residual_jacobian', 'jaicov_get_normal_equations', 'jaicov_omega',
     'jaicov_spd_solve_invert', 'jaicov_propagate_eo_transform', 'jaicov_dlt_batch', 'jaicov_gemm_tiles',
-    'jaicov_normal_product', 'jaicov_get_preconditioner',
+    'jaicov_normal_product', 'jaicov_get_preconditioner', 'jaicov_get_sweep_times',
 ]
 
 
@@ -102,6 +102,7 @@ def load():
     L.jaicov_omega.argtypes = [vp, vp, ctypes.POINTER(dbl)]
     L.jaicov_normal_product.argtypes = [vp, i32, vp, vp, vp, ctypes.POINTER(dbl)]
     L.jaicov_get_preconditioner.argtypes = [vp, vp]
+    L.jaicov_get_sweep_times.argtypes = [vp, ctypes.POINTER(dbl), ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
     L.jaicov_spd_solve_invert.argtypes = [i32, i64, vp, i32, vp, i32, ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
     for name in EXPORTS:
         if name not in ('jaicov_destroy', 'jaicov_last_error', 'jaicov_launch_count'):
@@ -350,6 +351,12 @@ class Session:
         self.check(self.L.jaicov_normal_product(self.h, X.shape[0], _p(X) if X.size else None, _p(Y) if Y.size else None,
                                                 _p(rhs) if want_rhs else None, ctypes.byref(wpw) if want_rhs else None))
         return Y, rhs, wpw.value
+
+    def sweep_times(self):
+        """Device ms of the by-image, by-point and Omega sweeps of the last pass."""
+        a, b, c = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_double(0)
+        self.check(self.L.jaicov_get_sweep_times(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return a.value, b.value, c.value
 
     def preconditioner(self):
         out = np.empty(self.n)

@@ -231,6 +231,8 @@ struct jaicov_handle {
     bool resident = false;               // the device still holds the problem of the last estimate (values centred), although `prepared` was cleared
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
+    cudaEvent_t evk[6] = {};             // around the three observation sweeps (by-image, by-point, Omega) of the last pass
+    bool evk_omega = false;
     jaicov_stats stats{};
     double centroid[3] = {0, 0, 0};
     // multi-GPU (one process per GPU); the communicator is process-wide and outlives the handle
@@ -414,11 +416,13 @@ void select_solver(jaicov_handle *h) {
 
 void prepare(jaicov_handle *h) {
     if (h->prepared) return;
+    NvtxRange nvtx_("jaicov: prepare (upload, index structures, buffers)");
     if (usable_devices() == 0) throw CudaError{cudaErrorNoDevice, "no sm_100 device: jaicov_b200 has no CPU path", __FILE__, __LINE__};
     JCHECK(cudaSetDevice(h->opt.device));
     if (!h->stream) {
         JCHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         for (auto &e : h->ev) JCHECK(cudaEventCreate(&e));
+        for (auto &e : h->evk) JCHECK(cudaEventCreate(&e));
     }
     if (!h->has_datum_call || h->n_unknowns < 0) throw std::runtime_error("jaicov_set_datum has not been called");
     DevProblem &P = h->P;
@@ -730,6 +734,7 @@ void prepare(jaicov_handle *h) {
 // stages 1-2 of one pass: N, n of the current values in M (lower) / rhs, datum rows in Bt
 // (sparse_clear: the structured route clears only the point blocks and the rows of the camera / image unknowns)
 void assemble(jaicov_handle *h, bool sparse_clear = false) {
+    NvtxRange nvtx_("jaicov: assembly N = A'PA, n = A'Pw");
     const DevProblem &P = h->P;
     cudaStream_t s = h->stream;
     const size_t np = (size_t)P.np;
@@ -743,12 +748,16 @@ void assemble(jaicov_handle *h, bool sparse_clear = false) {
     JCHECK(cudaMemsetAsync(h->rhs.p, 0, np * sizeof(double), s));
     JCHECK(cudaMemsetAsync(h->Bt.p, 0, 8 * np * sizeof(double), s));
     launch_pose(P, s);
+    JCHECK(cudaEventRecord(h->evk[0], s));
     launch_assemble_images(P, h->S, h->M.p, h->rhs.p, s);
+    JCHECK(cudaEventRecord(h->evk[1], s));
     const bool multi = h->dist_on && h->dist.world > 1;
     const AssemblyScratch &S = h->S;
     for (size_t gi = 0; gi < h->pt_groups.size(); gi++) {
         const PtGroup &g = h->pt_groups[gi];
+        if (gi == 0) JCHECK(cudaEventRecord(h->evk[2], s));
         launch_by_point(P, S, g, s);
+        if (gi == 0) JCHECK(cudaEventRecord(h->evk[3], s));
         // the only exchange of the assembly: sum the shared pieces over the image shards
         if (multi) h->dist.allreduce_sum(S.pt_partial, (size_t)P.nPt * 3 * 8 * g.nt, s);
         if (gi == 0) {
@@ -809,8 +818,10 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     cudaStream_t s = h->stream;
     const size_t np = (size_t)P.np;
     const bool invert = final_pass && h->wants_inverse();
+    NvtxRange nvtx_pass(final_pass ? "jaicov: final pass" : "jaicov: pass");
     JCHECK(cudaEventRecord(h->ev[0], s));
     assemble(h, true);
+    nvtxRangePushA("jaicov: precondition + datum");
     // Levenberg-Marquardt: N_cc += lambda N_cc on every unknown column, before the preconditioner (BA:801-822)
     if (h->derive_first_damping) {
         h->adapted_damping = h->opt.damping_value;
@@ -825,6 +836,8 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     launch_build_rhs(h->Rt.p, h->Btv.p, P.np, P.u, h->V.p, h->rhs.p, h->Bt.p, P.d, h->opt.estimation_type == JAICOV_SIMULATION, s);
     h->have_neq = false;
     JCHECK(cudaEventRecord(h->ev[1], s));
+    nvtxRangePop();
+    nvtxRangePushA("jaicov: factor");
     // factor (K5)
     JCHECK(cudaMemsetAsync(h->info.p, 0, sizeof(int), s));
     CudaBackend be{s, h->info.p};
@@ -872,6 +885,8 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
         ds.potrf();
     }
     JCHECK(cudaEventRecord(h->ev[2], s));
+    nvtxRangePop();
+    nvtxRangePushA("jaicov: solve + datum correction");
     // solve for n and the datum rows, datum correction, dx (K5/K9)
     if (st.on) {
         // (H doubles as the d null-space rows K^-1[lambda, x]; small[100..107) holds the datum residual B y)
@@ -906,6 +921,8 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
         }
     }
     JCHECK(cudaEventRecord(h->ev[3], s));
+    nvtxRangePop();
+    nvtxRangePushA("jaicov: inverse Qxx");
     // inverse (K6/K7)
     if (invert && st.on && h->dist_on) {
         // the same two products restricted to this rank's column tiles of the inverse (no communication): Q'Y' for its
@@ -960,10 +977,15 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
         launch_qxx_epilogue(h->M.p, P.np, P.u, h->V.p, h->H.p, h->Rt.p + np, P.d, P.np, s);
     }
     JCHECK(cudaEventRecord(h->ev[4], s));
+    nvtxRangePop();
+    nvtxRangePushA("jaicov: omega + update");
     // Omega at the pre-update point (K8), BA:429-430
     const bool want_omega = final_pass && h->opt.estimation_type != JAICOV_SIMULATION && (!r.lm_step || r.lm_accepted);
+    h->evk_omega = want_omega;
     if (want_omega) {
+        JCHECK(cudaEventRecord(h->evk[4], s));
         launch_omega(P, h->S, h->dxref.p, h->omega_parts.p, s);
+        JCHECK(cudaEventRecord(h->evk[5], s));
         if (multi) h->dist.allreduce_sum(h->omega_parts.p, 1, s);
         if (P.nBar) launch_omega_bars(P, h->dxref.p, h->omega_parts.p + 1, s);
         int gi = 0;
@@ -980,6 +1002,7 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     launch_update(P.coef_val, P.coef_col, P.nCoef, h->dxref.p, apply_dx, h->upd.p, s);
     launch_update(P.eo_val, P.eo_col, 6 * (int64_t)P.nImg, h->dxref.p, apply_dx, h->upd.p, s);
     JCHECK(cudaEventRecord(h->ev[6], s));
+    nvtxRangePop();
     JCHECK(cudaGetLastError());
     // the one host read per pass: status word, max|dx|, Omega
     unsigned long long upd[2];
@@ -1215,6 +1238,7 @@ void jaicov_destroy(jaicov_handle *h) {
         cudaStreamSynchronize(h->stream);
         if (h->dist_on) cudaDeviceSynchronize();   // the process-wide communicator stays
         for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+        for (auto &e : h->evk) if (e) cudaEventDestroy(e);
         cudaStreamDestroy(h->stream);
     }
     delete h;
@@ -1556,6 +1580,7 @@ int32_t jaicov_get_dx(jaicov_handle *h, double *dx) {
 }
 
 static int32_t pack_to_host(jaicov_handle *h, const double *border, const double *q11, double *dst, int64_t n_limit = -1) {
+    NvtxRange nvtx_("jaicov: packed Qxx -> host");
     const DevProblem &P = h->P;
     const int64_t n = n_limit >= 0 ? n_limit : (int64_t)P.u + P.d;   // the packed leading block is a prefix of the packed matrix
     const int64_t budget = (int64_t)1 << 25;   // doubles per staging chunk (256 MiB)
@@ -2085,6 +2110,25 @@ int32_t jaicov_normal_product(jaicov_handle *h, int32_t nvec, const double *x, d
     if (rhs) JCHECK(cudaMemcpyAsync(rhs, dR.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (wpw) JCHECK(cudaMemcpyAsync(wpw, dW.p, sizeof(double), cudaMemcpyDeviceToHost, s));
     JCHECK(cudaStreamSynchronize(s));
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+int32_t jaicov_get_sweep_times(jaicov_handle *h, double *ms_by_image, double *ms_by_point, double *ms_omega) {
+    if (!h) return JAICOV_ILLEGAL_ARGUMENT;
+    if (is_group(h)) return jaicov_get_sweep_times(h->sub[0], ms_by_image, ms_by_point, ms_omega);
+    if (!h->stream || !h->have_neq && !h->prepared && !h->resident) return fail(h, JAICOV_NOT_INITIALISED, "no pass has run");
+    API_GUARD_BEGIN
+    JCHECK(cudaSetDevice(h->opt.device));
+    JCHECK(cudaStreamSynchronize(h->stream));
+    float a = 0, b = 0, c = 0;
+    cudaEventElapsedTime(&a, h->evk[0], h->evk[1]);
+    cudaEventElapsedTime(&b, h->evk[2], h->evk[3]);
+    if (h->evk_omega) cudaEventElapsedTime(&c, h->evk[4], h->evk[5]);
+    cudaGetLastError();
+    if (ms_by_image) *ms_by_image = a;
+    if (ms_by_point) *ms_by_point = b;
+    if (ms_omega) *ms_omega = c;
     return JAICOV_OK;
     API_GUARD_END(h)
 }

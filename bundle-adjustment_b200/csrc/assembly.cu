@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(256) k_point_scatter(DevProblem P, AssemblyScr
 
 // resident CTAs per SM the observation sweeps are compiled for (register cap 128 at 4 CTAs of 128 threads): JAICOV_SWEEP_MINB
 static int sweep_min_blocks() {
-    static const int v = [] { const char *e = getenv("JAICOV_SWEEP_MINB"); return e ? atoi(e) : 1; }();
+    static const int v = [] { const char *e = getenv("JAICOV_SWEEP_MINB"); return e ? atoi(e) : 4; }();
     return v;
 }
 

@@ -1,6 +1,7 @@
 // common.h -- shared declarations of the jaicov_b200 CUDA library (host side).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <atomic>
 #include <cstdint>
@@ -48,6 +49,14 @@ struct PerDeviceOnce {
             done[dev].store(true, std::memory_order_release);
         }
     }
+};
+
+// NVTX range of one stage (nsys / ncu --nvtx timelines name the stages of a pass; header-only NVTX3, a no-op without a tool attached)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
 };
 
 // Flattened problem resident in HBM (structure-of-arrays; all pointers are device pointers).

@@ -293,6 +293,10 @@ int32_t jaicov_omega(jaicov_handle *h, const double *dx, double *omega);
  * on configurations no CPU reference can reach (bench.py does, at every N).  Distributed handles sum their image shards
  * (NCCL all-reduce); every rank receives the complete product.  Does not disturb Qxx / dx of the last pass. */
 int32_t jaicov_normal_product(jaicov_handle *h, int32_t nvec, const double *x, double *y, double *rhs, double *wpw);
+/* Device time (CUDA events, ms) of the three observation sweeps of the LAST pass: the by-image sweep (model evaluation + per-image
+ * Gram + the unique EO x point blocks), the by-point sweep (first camera group) and the Omega sweep (0 unless it was a final pass).
+ * These are the kernels whose algorithmic traffic is 44 B per image point; bench.py turns them into GB/s. */
+int32_t jaicov_get_sweep_times(jaicov_handle *h, double *ms_by_image, double *ms_by_point, double *ms_omega);
 /* Jacobi preconditioner V of the last pass (:824-828), length u+d (1 on the border) */
 int32_t jaicov_get_preconditioner(jaicov_handle *h, double *v);
 
