@@ -28,7 +28,7 @@ EXPORTS = [
     'jaicov_get_stats', 'jaicov_get_values', 'jaicov_get_dx', 'jaicov_get_qxx_packed', 'jaicov_get_qxx_block',
     'jaicov_get_qxx_diag', 'jaicov_get_qxx_submatrix', 'jaicov_eval_residual_jacobian', 'jaicov_get_normal_equations', 'jaicov_omega',
     'jaicov_spd_solve_invert', 'jaicov_propagate_eo_transform', 'jaicov_dlt_batch', 'jaicov_gemm_tiles',
-    'jaicov_normal_product', 'jaicov_get_preconditioner', 'jaicov_get_sweep_times',
+    'jaicov_normal_product', 'jaicov_get_preconditioner', 'jaicov_get_sweep_times', 'jaicov_set_image_dispersion', 'jaicov_set_gemm_digits',
 ]
 
 
@@ -102,6 +102,8 @@ def load():
     L.jaicov_omega.argtypes = [vp, vp, ctypes.POINTER(dbl)]
     L.jaicov_normal_product.argtypes = [vp, i32, vp, vp, vp, ctypes.POINTER(dbl)]
     L.jaicov_get_preconditioner.argtypes = [vp, vp]
+    L.jaicov_set_gemm_digits.argtypes = [i32]
+    L.jaicov_set_image_dispersion.argtypes = [vp, i32, i64, vp]
     L.jaicov_get_sweep_times.argtypes = [vp, ctypes.POINTER(dbl), ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
     L.jaicov_spd_solve_invert.argtypes = [i32, i64, vp, i32, vp, i32, ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
     for name in EXPORTS:
@@ -218,6 +220,10 @@ class Session:
             var_g = None if g.get('var') is None else _f64(g['var'])
             sig = None if g.get('sigma') is None else _f64(g['sigma'])
             self.check(L.jaicov_add_observed_group(h, k.size, _p(k), _p(ix), _p(cm), _p(ob), _p(var_g), _p(sig)))
+        for (img_i, sig) in f.get('img_sigma', []):
+            sig = _f64(sig)
+            nr = int(round((-1 + (1 + 8 * sig.size) ** 0.5) / 2))
+            self.check(L.jaicov_set_image_dispersion(h, int(img_i), nr, _p(sig)))
         ff = _i32(f['free_flags'])
         self.check(L.jaicov_set_datum(h, _p(ff), int(f['n_unknowns']), int(f['n_observations'])))
         self.n = int(f['n_unknowns']) + int(ff.sum())
@@ -362,6 +368,11 @@ class Session:
         out = np.empty(self.n)
         self.check(self.L.jaicov_get_preconditioner(self.h, _p(out)))
         return out
+
+
+def set_gemm_digits(digits):
+    """Process-wide arithmetic of the big tile products (jaicov_set_gemm_digits): 0 = FP64 DMMA tiles, 4..8 = int8 digit products."""
+    return load().jaicov_set_gemm_digits(int(digits))
 
 
 def shard_images(pt_ptr, world, rank):

@@ -26,7 +26,8 @@ std::atomic<long long> g_launch_count{0};
 
 // dense_kernels.cu
 void launch_gemm(const GemmDesc &g, cudaStream_t s);
-size_t ozaki_release_scratch();   // ozaki.cu (experiment, default off)
+size_t ozaki_release_scratch();   // ozaki.cu
+int ozaki_set_digits(int digits);
 void launch_potrf_diag(double *A, int64_t ld, double *dinv, int row0, int *info, cudaStream_t s);
 void launch_copy2d(double *dst, int64_t ldd, const double *src, int64_t lds, int64_t rows, int64_t cols, cudaStream_t s);
 void launch_solve_rows8(const double *L, int64_t ld, const double *dinv, double *R, double *Y, int64_t np, cudaStream_t s);
@@ -78,6 +79,16 @@ void launch_normal_product_points(const DevProblem &P, int nv, int64_t n, const 
                                   cudaStream_t s);
 void launch_normal_product_rest(const DevProblem &P, int nv, int64_t n, const double *X, double *Y, double *rhs, double *wpw,
                                 const double *Bt, int64_t ldb, cudaStream_t s);
+
+// dense_sigma.cu: image points of one image with a fully populated dispersion matrix (extension, north_star (2))
+void launch_zero_weights(double *rw, int64_t obs_begin, int64_t obs_end, cudaStream_t s);
+void launch_image_rows(const DevProblem &P, int img, double *Ac, int64_t rp, cudaStream_t s);
+void launch_dense_image_assemble(const DevProblem &P, int img, int64_t m, const double *Pw, int64_t ldp, int64_t rp, double *Ac, double *T,
+                                 double *G, double *M, double *rhs, cudaStream_t s);
+void launch_dense_image_omega(const DevProblem &P, int img, const double *Pw, int64_t ldp, int64_t rp, double *Ac, const double *x, double *v,
+                              double *t, double *out, cudaStream_t s);
+void launch_dense_image_product(const DevProblem &P, int img, const double *Pw, int64_t ldp, int64_t rp, const double *Ac, const double *x,
+                                int mode, double *v, double *t, double *y, double *wpw, cudaStream_t s);
 
 void launch_img_of_obs(const int64_t *pt_ptr, int nImg, int32_t *img_of_obs, cudaStream_t s);
 size_t csc_temp_bytes(int64_t n);
@@ -186,6 +197,14 @@ struct Group {
     int64_t ldp = 0;
 };
 
+// image with a fully populated dispersion of its 2m image coordinates (jaicov_set_image_dispersion)
+struct ImgSigma {
+    int img = -1;
+    std::vector<double> sigma;     // packed upper, (2m)(2m+1)/2
+    DevBuf<double> Pw;             // sigma0^2 Sigma^-1, rp x rp (identity padding)
+    int64_t rp = 0;
+};
+
 static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 // One NCCL communicator per process (one process per GPU): created by the first jaicov_dist_init and re-used by later
@@ -206,6 +225,9 @@ struct jaicov_handle {
     std::vector<int64_t> pt_ptr;
     std::vector<uint8_t> is_datum;
     std::vector<Group> groups;
+    std::vector<ImgSigma> img_sigma;
+    DevBuf<double> ds_Ac, ds_T, ds_G, ds_v, ds_t;   // scratch of the dense-dispersion images (sized for the largest one)
+    DevBuf<uint8_t> d_img_dense;
     int free_flags[7] = {0, 0, 0, 0, 0, 0, 0};
     int n_unknowns = -1, n_observations = 0;
     bool has_datum_call = false;
@@ -348,6 +370,7 @@ void select_solver(jaicov_handle *h) {
     int up = 0;
     if (want == JAICOV_SOLVER_DENSE) why = "dense route requested";
     else if (!h->bar_a.empty()) why = "scale bars couple object points";
+    if (!why && !h->img_sigma.empty()) why = "an image with a fully populated dispersion couples its object points";
     if (!why)
         for (const Group &g : h->groups)
             for (int k : g.kind)
@@ -626,6 +649,46 @@ void prepare(jaicov_handle *h) {
     h->d_rw.alloc((size_t)std::max<int64_t>(P.m, 1) * 3);
     P.rw = h->d_rw.p;
     launch_obs_weights(P, h->d_rw.p, h->stream);
+    // ---- images with a fully populated dispersion (extension): P = (Sigma / sigma0^2)^-1 once, the standard sweeps skip them -----------
+    {
+        std::vector<uint8_t> dense(std::max(P.nImg, 1), 0);
+        int64_t rp_max = 0;
+        if (!h->img_sigma.empty() && h->dist_on) throw std::runtime_error("images with a fully populated dispersion need a single device (their point blocks are not sharded)");
+        for (ImgSigma &is : h->img_sigma) {
+            if (is.img < 0 || is.img >= P.nImg) throw std::runtime_error("jaicov_set_image_dispersion: image index out of range");
+            const int64_t m2 = 2 * (h->pt_ptr[is.img + 1] - h->pt_ptr[is.img]);
+            if ((int64_t)is.sigma.size() != m2 * (m2 + 1) / 2) throw std::runtime_error("jaicov_set_image_dispersion: needs (2m)(2m+1)/2 entries for the image's m points");
+            if (m2 == 0) continue;
+            dense[is.img] = 1;
+            is.rp = round_up(m2, kBlk);
+            rp_max = std::max(rp_max, is.rp);
+            launch_zero_weights(h->d_rw.p, h->pt_ptr[is.img], h->pt_ptr[is.img + 1], h->stream);
+            DevBuf<double> ap, Wg, Dg;
+            DevBuf<int> inf;
+            ap.upload(is.sigma);
+            is.Pw.alloc((size_t)is.rp * is.rp);
+            Wg.alloc((size_t)is.rp * is.rp);
+            Dg.alloc((size_t)is.rp * kBlk);
+            inf.alloc(1);
+            launch_unpack_scaled(ap.p, (int)m2, 1.0 / P.sigma2, is.Pw.p, is.rp, is.rp, h->stream);
+            JCHECK(cudaMemsetAsync(inf.p, 0, sizeof(int), h->stream));
+            CudaBackend be{h->stream, inf.p};
+            DenseSchedule<CudaBackend> ds{be, is.Pw.p, is.rp, is.rp, Dg.p};
+            ds.potrf();
+            ds.invert_from_factor(Wg.p);
+            launch_symmetrize(is.Pw.p, is.rp, (int)m2, h->stream);
+            int info = 0;
+            JCHECK(cudaMemcpyAsync(&info, inf.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            JCHECK(cudaStreamSynchronize(h->stream));
+            if (info != 0) throw std::runtime_error("dispersion matrix of an image is not positive definite");
+        }
+        h->d_img_dense.upload(dense);
+        P.img_dense = h->img_sigma.empty() ? nullptr : h->d_img_dense.p;
+        if (rp_max) {
+            h->ds_Ac.alloc((size_t)rp_max * kBlk); h->ds_T.alloc((size_t)rp_max * kBlk); h->ds_G.alloc((size_t)kBlk * kBlk);
+            h->ds_v.alloc((size_t)rp_max); h->ds_t.alloc((size_t)rp_max);
+        }
+    }
     S.img_partial = h->d_img_partial.p; S.cam_partial = h->d_cam_partial.p; S.pt_partial = h->d_pt_partial.p;
     S.omega_partial = h->d_omega_partial.p;
     // ---- solver route --------------------------------------------------------------------------------------------
@@ -771,6 +834,10 @@ void assemble(jaicov_handle *h, bool sparse_clear = false) {
         }
         launch_point_scatter(P, S, g, h->kbase_host[g.cam0], h->M.p, h->rhs.p, s);
     }
+    for (ImgSigma &is : h->img_sigma)
+        if (is.rp)
+            launch_dense_image_assemble(P, is.img, h->pt_ptr[is.img + 1] - h->pt_ptr[is.img], is.Pw.p, is.rp, is.rp, h->ds_Ac.p, h->ds_T.p,
+                                        h->ds_G.p, h->M.p, h->rhs.p, s);
     launch_scale_bars(P, h->M.p, h->rhs.p, s);
     for (Group &g : h->groups) {
         launch_group_w(g.r, g.tptr.p, g.d_obs.p, g.w.p, s);
@@ -792,12 +859,20 @@ struct PassResult {
     double lm_last = 0.0;
 };
 
+// Omega part of the images with a fully populated dispersion, added to omega_parts[0] (after launch_omega has written it)
+void omega_dense_images(jaicov_handle *h) {
+    for (ImgSigma &is : h->img_sigma)
+        if (is.rp)
+            launch_dense_image_omega(h->P, is.img, is.Pw.p, is.rp, is.rp, h->ds_Ac.p, h->dxref.p, h->ds_v.p, h->ds_t.p, h->omega_parts.p, h->stream);
+}
+
 // sum of the Omega parts of all observation groups for the dx currently in dxref (device -> host, synchronises)
 double omega_now(jaicov_handle *h, bool multi) {
     const DevProblem &P = h->P;
     cudaStream_t s = h->stream;
     launch_omega(P, h->S, h->dxref.p, h->omega_parts.p, s);
     if (multi) h->dist.allreduce_sum(h->omega_parts.p, 1, s);
+    omega_dense_images(h);
     if (P.nBar) launch_omega_bars(P, h->dxref.p, h->omega_parts.p + 1, s);
     int gi = 0;
     for (Group &g : h->groups) {
@@ -987,6 +1062,7 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
         launch_omega(P, h->S, h->dxref.p, h->omega_parts.p, s);
         JCHECK(cudaEventRecord(h->evk[5], s));
         if (multi) h->dist.allreduce_sum(h->omega_parts.p, 1, s);
+        omega_dense_images(h);
         if (P.nBar) launch_omega_bars(P, h->dxref.p, h->omega_parts.p + 1, s);
         int gi = 0;
         for (Group &g : h->groups) {
@@ -1185,6 +1261,8 @@ int32_t jaicov_device_count(void) { return usable_devices(); }
 int64_t jaicov_release_cached_memory(void) { return (int64_t)(g_cache.purge() + ozaki_release_scratch()); }
 
 int64_t jaicov_launch_count(void) { return (int64_t)g_launch_count.load(); }
+
+int32_t jaicov_set_gemm_digits(int32_t digits) { return ozaki_set_digits(digits); }
 
 int32_t jaicov_create(const jaicov_options *opt, jaicov_handle **out) {
     if (!opt || !out) return JAICOV_ILLEGAL_ARGUMENT;
@@ -1409,6 +1487,22 @@ int32_t jaicov_add_observed_group(jaicov_handle *h, int32_t r, const int32_t *ta
     g.obs.assign(obs, obs + r);
     if (sigma_packed_upper) g.sigma.assign(sigma_packed_upper, sigma_packed_upper + (size_t)r * (r + 1) / 2);
     else g.var.assign(var, var + r);
+    h->prepared = false; h->resident = false;
+    return JAICOV_OK;
+    API_GUARD_END(h)
+}
+
+int32_t jaicov_set_image_dispersion(jaicov_handle *h, int32_t image, int64_t n_rows, const double *sigma_packed_upper) {
+    if (!h || image < 0 || n_rows < 0 || (n_rows > 0 && !sigma_packed_upper)) return JAICOV_ILLEGAL_ARGUMENT;
+    GROUP_FORWARD(h, jaicov_set_image_dispersion(s_, image, n_rows, sigma_packed_upper))
+    API_GUARD_BEGIN
+    for (size_t i = 0; i < h->img_sigma.size(); i++)
+        if (h->img_sigma[i].img == image) { h->img_sigma.erase(h->img_sigma.begin() + i); break; }
+    if (n_rows > 0) {
+        h->img_sigma.emplace_back();
+        h->img_sigma.back().img = image;
+        h->img_sigma.back().sigma.assign(sigma_packed_upper, sigma_packed_upper + (size_t)n_rows * (n_rows + 1) / 2);
+    }
     h->prepared = false; h->resident = false;
     return JAICOV_OK;
     API_GUARD_END(h)
@@ -2042,6 +2136,8 @@ int32_t jaicov_omega(jaicov_handle *h, const double *dx, double *omega) {
     JCHECK(cudaMemcpy(h->dxref.p, dx, (size_t)(P.u + P.d) * sizeof(double), cudaMemcpyHostToDevice));
     launch_pose(P, s);
     launch_omega(P, h->S, h->dxref.p, h->omega_parts.p, s);
+    if (h->dist_on && h->dist.world > 1) h->dist.allreduce_sum(h->omega_parts.p, 1, s);
+    omega_dense_images(h);
     JCHECK(cudaMemsetAsync(h->omega_parts.p + 1, 0, sizeof(double), s));
     if (P.nBar) launch_omega_bars(P, h->dxref.p, h->omega_parts.p + 1, s);
     int gi = 0;
@@ -2097,6 +2193,15 @@ int32_t jaicov_normal_product(jaicov_handle *h, int32_t nvec, const double *x, d
     if (h->dist_on && h->dist.world > 1) {      // image shards: sum over the ranks; everything below is replicated
         if (nvec) h->dist.allreduce_sum(dY.p, (size_t)nvec * n, s);
         if (want_rhs) { h->dist.allreduce_sum(dR.p, (size_t)n, s); h->dist.allreduce_sum(dW.p, 1, s); }
+    }
+    for (ImgSigma &is : h->img_sigma) {      // images with a fully populated dispersion (skipped by the kernel above)
+        if (!is.rp) continue;
+        launch_image_rows(P, is.img, h->ds_Ac.p, is.rp, s);
+        for (int v = 0; v < nvec; v++)
+            launch_dense_image_product(P, is.img, is.Pw.p, is.rp, is.rp, h->ds_Ac.p, dX.p + (size_t)v * n, 1, h->ds_v.p, h->ds_t.p,
+                                       dY.p + (size_t)v * n, nullptr, s);
+        if (want_rhs)
+            launch_dense_image_product(P, is.img, is.Pw.p, is.rp, is.rp, h->ds_Ac.p, nullptr, 2, h->ds_v.p, h->ds_t.p, dR.p, dW.p, s);
     }
     if (P.d > 0) launch_datum_rows(P.xyz, P.pt_col, h->d_datum_pts.p, h->nDatumPts, h->free_mask, P.d, P.np, dB.p, s);
     launch_normal_product_rest(P, nvec, n, dX.p, dY.p, want_rhs ? dR.p : nullptr, want_rhs ? dW.p : nullptr, dB.p, P.np, s);

@@ -90,6 +90,7 @@ struct DevProblem {
     double *xy = nullptr, *var = nullptr, *rho = nullptr;
     double *rw = nullptr;           // [3 m] r00, r01, r11 with P = R'R (weights are constant over the passes)
     int32_t *img_of_obs = nullptr;  // [m]
+    const uint8_t *img_dense = nullptr;  // [nImg] or null: image has a fully populated dispersion (dense_sigma.cu), its points carry zero per-point weights
     int64_t *pt_obs_ptr = nullptr;  // [nPt+1] CSC: observations of every object point
     int64_t *pt_obs = nullptr;      // [m]
     // object points

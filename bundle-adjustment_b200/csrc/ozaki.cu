@@ -193,6 +193,8 @@ static void launch_split(const OzSplitArgs &a, cudaStream_t s) {
 }
 
 // ---- the tile kernel -----------------------------------------------------------------------------------------------------
+// digits used when neither jaicov_set_gemm_digits nor JAICOV_GEMM_OZAKI says otherwise (0 = FP64 DMMA tiles everywhere)
+constexpr int kOzakiDefaultDigits = 0;
 constexpr int OZ_BM = 128, OZ_BN = 64, OZ_BK = 64, OZ_STAGES = 2, OZ_THREADS = 192, OZ_TMEM_COLS = 512;
 
 template <int S> struct OzCfg {
@@ -542,7 +544,11 @@ struct OzScratch {
         return b;
     }
 };
-OzScratch g_oz;
+// one scratch set per device ordinal (a handle works on one device; the single-process multi-GPU handle runs one host thread per
+// device).  Launches of ONE stream reuse it safely (stream order); two adjustments running concurrently on the same device would
+// share it -- the library documents one adjustment at a time per device.
+OzScratch g_oz_dev[64];
+std::atomic<int> g_oz_digits{-1};     // -1: not decided yet (JAICOV_GEMM_OZAKI, else the built-in default)
 
 template <int S, int CL>
 void launch_tiles(const CUtensorMap &ma, const CUtensorMap &mb, const OzGemmArgs &a, int64_t tiles, int grid_y, cudaStream_t s) {
@@ -577,13 +583,43 @@ void launch_tiles_digits(int digits, const CUtensorMap &ma, const CUtensorMap &m
 
 }  // namespace
 
-size_t ozaki_release_scratch() { return g_oz.release(); }
+size_t ozaki_release_scratch() {
+    size_t b = 0;
+    int cur = 0, n = 0;
+    cudaGetDevice(&cur);
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    for (int d = 0; d < n && d < 64; d++)
+        if (g_oz_dev[d].cap[0] || g_oz_dev[d].cap[1] || g_oz_dev[d].k_cap || g_oz_dev[d].rows_cap[0]) { cudaSetDevice(d); b += g_oz_dev[d].release(); }
+    cudaSetDevice(cur);
+    return b;
+}
+
+// digits of the int8-digit tile product (0 = FP64 DMMA tiles for every launch); returns the previous setting
+int ozaki_set_digits(int digits) {
+    if (digits < 0) return g_oz_digits.load();
+    return g_oz_digits.exchange((digits >= 4 && digits <= 8) ? digits : 0);
+}
+
+int ozaki_digits() {
+    int d = g_oz_digits.load();
+    if (d < 0) {
+        const char *e = getenv("JAICOV_GEMM_OZAKI");
+        d = e ? atoi(e) : kOzakiDefaultDigits;
+        if (d < 4 || d > 8) d = 0;
+        g_oz_digits.store(d);
+    }
+    return d;
+}
 
 // Takes the launch if the experiment is switched on and the launch is one of the big plain / triangular-operand products;
 // returns false (nothing launched) otherwise, and the caller runs k_gemm.
 bool launch_gemm_ozaki(const GemmDesc &g, cudaStream_t s) {
-    static const int digits = [] { const char *e = getenv("JAICOV_GEMM_OZAKI"); return e ? atoi(e) : 0; }();
+    const int digits = ozaki_digits();
     if (digits < 4 || digits > 8) return false;
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    if (dev_ < 0 || dev_ >= 64) return false;
+    OzScratch &g_oz = g_oz_dev[dev_];
     static const int64_t min_tiles = [] { const char *e = getenv("JAICOV_OZAKI_MIN_TILES"); return e ? (int64_t)atoll(e) : (int64_t)148; }();
     // column-table launches: only the trapezoid update of the distributed Cholesky (both operands the same panel, C addressed by
     // global tiles); the structured route's compact column tables keep the FP64 kernel

@@ -348,6 +348,15 @@ class Image:
         self._eo = ExteriorOrientation(self)
         self._chunks = []
         self._seen = set()
+        self._dispersion = None
+
+    def setDispersion(self, packed_upper):
+        """EXTENSION (not in the reference, whose image-coordinate groups are the two rows of one point, camera/ImageCoordinate.java:
+        102-104): fully populated dispersion of the image's 2m coordinates (x_0, y_0, x_1, y_1, ... in observation order), MTJ packed
+        upper; replaces the per-point sigma / rho.  None removes it."""
+        self._dispersion = None if packed_upper is None else np.ascontiguousarray(packed_upper, np.float64)
+
+    def getDispersion(self): return self._dispersion
 
     def getId(self): return self._id
     def getReference(self): return self._camera
@@ -732,8 +741,17 @@ class BundleAdjustment:
         cam_of_img, eo_params, pt_ptr = [], [], [0]
         obj, xy, var, rho = [], [], [], []
         images = []
+        img_sigma = []
         for ci, cam in enumerate(self._cameras):
             for img in cam:
+                if img.getDispersion() is not None:
+                    sg = img.getDispersion()
+                    m2 = 2 * img.getNumberOfImageCoordinates()
+                    if sg.size != m2 * (m2 + 1) // 2:
+                        raise ValueError('Error, the dispersion of an image needs (2m)(2m+1)/2 entries')
+                    k = np.arange(m2, dtype=np.int64)
+                    sigma2 = min(sigma2, float(sg[k + k * (k + 1) // 2].min()))     # like DirectlyObservedParameterGroup, DOPG:55-57
+                    img_sigma.append((len(images), sg))
                 images.append(img)
                 cam_of_img.append(ci)
                 eo_params.append(list(img.getExteriorOrientation()))
@@ -961,7 +979,7 @@ class BundleAdjustment:
             xyz=xyz.reshape(-1).copy(), pt_col=pt_col.reshape(-1), is_datum=(datum & in_adjustment).astype(np.uint8),
             bar_a=np.array(bar_a, np.int32), bar_b=np.array(bar_b, np.int32), bar_len=np.array(bar_len, float),
             bar_var=np.array(bar_var, float), groups=groups, free_flags=np.array(free_flags, np.int32),
-            n_unknowns=counter, n_observations=numObs)
+            n_unknowns=counter, n_observations=numObs, img_sigma=img_sigma)
         self._flat_ctx = (stores, cam_params, eo_params)
         self._store_base, self._image_index = dict(base), {id(img): k for k, img in enumerate(images)}
         return flat

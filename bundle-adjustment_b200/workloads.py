@@ -215,6 +215,8 @@ def build_adjustment(scene, device=0):
                 p.setValue(v)
                 p.setColumn(FIXED if f else -1)
             img.addAll(pts, im['obj'], im['xy'], im['sigma'], im['rho'])
+            if im.get('dispersion') is not None:         # extension: fully populated dispersion of the image's coordinates
+                img.setDispersion(im['dispersion'])
             imgs.append(img)
         cams.append((cam, cparams))
         adj.add(cam)

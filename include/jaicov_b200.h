@@ -138,6 +138,12 @@ int64_t jaicov_release_cached_memory(void);
 /* diagnostic: number of CUDA kernels this library has launched in this process so far */
 int64_t jaicov_launch_count(void);
 
+/* Arithmetic of the big tile products (process-wide): 0 = FP64 tensor-core tiles (mma.sync DMMA) for every launch; 4..8 = launches of
+ * at least 148 tiles and K >= 1024 are computed from exact int8 digit products on the tcgen05 tensor cores with FP64 recombination
+ * (Ozaki scheme, csrc/ozaki.cu; 8 digits reproduce the FP64 results within the parity tolerances -- DESIGN.md section 9, profiles/).
+ * digits < 0 only queries.  Returns the previous setting (-1: not decided yet = environment variable JAICOV_GEMM_OZAKI or the default). */
+int32_t jaicov_set_gemm_digits(int32_t digits);
+
 /* ---- multi-GPU ------------------------------------------------------------------------------------------------------
  * Two ways to put one adjustment on several GPUs of one box; both run the same device code (image-sharded assembly + NCCL
  * all-reduce of the shared normal-equation pieces, block-column-cyclic Cholesky with panel broadcasts over NVLink, every GPU
@@ -198,6 +204,13 @@ int32_t jaicov_set_scale_bars(jaicov_handle *h, int32_t n_bar, const int32_t *a,
 int32_t jaicov_add_observed_group(jaicov_handle *h, int32_t r, const int32_t *target_kind, const int32_t *target_index,
                                   const int32_t *target_comp, const double *obs, const double *var,
                                   const double *sigma_packed_upper);
+/* EXTENSION (north_star (2), BASELINE.json configs[3] "per-image dense Sigma_ll blocks"; not expressible in the reference, whose
+ * image-coordinate groups are always the two rows of one point, camera/ImageCoordinate.java:102-104 -- parity unpinned beyond the
+ * block-diagonal case): fully populated dispersion of the 2m image coordinates (x_0, y_0, x_1, y_1, ... in observation order) of
+ * image `image`, MTJ packed upper, n_rows = 2m.  The image's points are then weighted with P = sigma0^2 Sigma^-1 as ONE
+ * observation group of 2m rows (the contribution PDF:475-505 would stack for such a group); var / rho of those points are
+ * ignored.  n_rows = 0 removes it.  Couples all points of the image: dense solver route, one device. */
+int32_t jaicov_set_image_dispersion(jaicov_handle *h, int32_t image, int64_t n_rows, const double *sigma_packed_upper);
 /* result of detectRankDefect (:836-1042): free_flags in the order tx,ty,tz,rx,ry,rz,scale (1 = FREE);
  * n_unknowns = numberOfUnknownParameters (:80), n_observations = numberOfObservations (:81) */
 int32_t jaicov_set_datum(jaicov_handle *h, const int32_t free_flags[7], int32_t n_unknowns, int32_t n_observations);
