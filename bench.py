@@ -121,7 +121,7 @@ def fp64_peak_tflops(torch, n=8192, reps=5):
 # DRAM bytes (read + write) per launch of the dominant kernel launch, from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`
 # (profiles/; key = config for the dense route's single M = W^T W launch, -config for the structured route's Y (Q^T Y^T) launch);
 # None where no capture of this round exists
-TRAFFIC = {}
+TRAFFIC = {5: 3.32e12}      # profiles/r02_lauum_c5_dram_traffic.txt: 3.304 TB read + 16.1 GB written by the one M = W^T W launch (2.40 s under ncu)
 
 CPU_SAMPLE = (64, 1500)     # images x targets of the bounded CPU sample: n ~ 4900, ~10-20 s of packed dspsv + dsptri on one core
 
@@ -223,6 +223,7 @@ def main():
                          'the structured (point-block) route is timed next to it and reported under "structured"')
     ap.add_argument('--no-structured', action='store_true')
     ap.add_argument('--no-other-configs', action='store_true', help='skip the short runs of configs 2 and 4 (N = 1 only)')
+    ap.add_argument('--no-dmma', action='store_true', help='skip the comparison run with FP64 DMMA tiles for every launch')
     ap.add_argument('--no-check', action='store_true', help='skip the residual / identity verification of the timed pass')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -312,6 +313,34 @@ def main():
     clocks = sampler.finish() if rank == 0 else None
     structured_used = sess.stats().solver_used == ba._lib.SOLVER_STRUCTURED
     check = None if args.no_check else verify_pass(sess, sess.stats().omega)
+    digits = L.jaicov_set_gemm_digits(-1)
+    if digits < 0:
+        digits = int(os.environ.get('JAICOV_GEMM_OZAKI', '8'))
+
+    # ---- the same passes with FP64 tensor-core (DMMA) tiles for EVERY launch: the arithmetic the metric names literally ------------------
+    dmma = None
+    if digits > 0 and not args.no_dmma:
+        L.jaicov_set_gemm_digits(0)
+        for _ in range(2):
+            assert sess.iterate(final_pass=True, apply_update=False) == 0
+        barrier()
+        ddev, dstage = 0.0, np.zeros(5)
+        for _ in range(args.steps):
+            assert sess.iterate(final_pass=True, apply_update=False) == 0
+            st = sess.stats()
+            ddev += st.ms_total
+            dstage += [st.ms_assembly, st.ms_factor, st.ms_solve, st.ms_inverse, st.ms_omega]
+        barrier()
+        dcheck = None if args.no_check else verify_pass(sess, sess.stats().omega)
+        td = torch.tensor([ddev] + dstage.tolist(), dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        ddev, dstage = float(td[0]), td[1:].cpu().numpy() / args.steps
+        dmma = {'ms_per_step': ddev / args.steps, 'value': args.steps / (ddev * 1e-3), 'unit': UNIT,
+                'stage_ms': dict(zip(('assembly+precondition', 'factor', 'solve+datum', 'inverse+Qxx epilogue', 'omega'), dstage.tolist())),
+                'check': dcheck,
+                'note': 'jaicov_set_gemm_digits(0): every tile product on mma.sync DMMA (k_gemm), same inputs, same outputs'}
+        L.jaicov_set_gemm_digits(digits)
     # max over ranks of the device time
     t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -476,9 +505,14 @@ def main():
                                 'figure; ncu --set full of its largest launches (profiles/r01_ncu_full_k_gemm_shape65_summary.txt): LAUUM at '
                                 'config 4 moves 21.4 GB of DRAM traffic for 1.43e12 flop (tensor pipe 94.2 % active), the structured '
                                 "route's Y(Q'Y') launch at config 5 353.5 GB for 1.107e13 flop (93.8 %)",
-                'kernel': 'k_gemm<AL,BL> (FP64 DMMA 128x128 tiles); numerator %s flop per step, denominator device time of the '
-                          'factor + inverse stages (includes the diagonal-block kernels and copies between GEMM launches)'
-                          % ('the structured route\'s GEMM' if structured_used else 'n^3'),
+                'kernel': ('k_gemm_oz<8,1> (int8 digit products, tcgen05) for the big launches + k_gemm<AL,BL> (FP64 DMMA tiles) for the rest'
+                           if digits else 'k_gemm<AL,BL> (FP64 DMMA 128x128 tiles)') +
+                          '; numerator %s FP64 flop per step, denominator the whole step' % ('the structured route\'s GEMM' if structured_used else 'n^3'),
+                'frac_note': ('peak is the FP64 tensor pipe (cuBLAS DGEMM measured in this run), the roofline north_star names.  frac > 1 '
+                              'means the step beats that pipe: the big products run on the int8 tensor pipe (36 digit products per FP64 product '
+                              'at 8 digits; ncu: tcgen05 pipe 40 % active, L2 -> SM operand traffic 4.8 TB/s is the limiter, '
+                              'profiles/r02_ncu_full_k_gemm_oz_summary.txt).  The all-DMMA step of the same run is fp64_dmma.frac_of_fp64_peak')
+                             if digits else None,
                 'peak_source': 'cuBLAS DGEMM 8192^3 via torch.matmul(float64) measured in this run (burst, best of 5); '
                                'MEASURED_PEAKS.json has no FP64 entry',
                 'hbm_peak_gbs': hbm}
@@ -486,9 +520,11 @@ def main():
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': name, 'solver': 'structured (point-block)' if structured_used else 'dense (blocked Cholesky + full inverse)',
-                       'gemm': ('FP64 DMMA tiles (mma.sync m8n8k4)' if not os.environ.get('JAICOV_GEMM_OZAKI') else
-                                'EXPERIMENT JAICOV_GEMM_OZAKI=%s: big products from int8 digit products on tcgen05 (FP64-equivalent); '
-                                'roofline.peak stays the FP64 tensor pipe, so frac can exceed 1' % os.environ['JAICOV_GEMM_OZAKI']),
+                       'gemm': ('FP64 DMMA tiles (mma.sync m8n8k4) for every launch' if digits == 0 else
+                                'launches of >= 148 tiles and K >= 1024: %d exact int8 digit planes per operand, digit products on tcgen05 '
+                                '(UTCIMMA, TMA, s32 accumulators in TMEM), FP64 recombination -- FP64-equivalent results (parity suite green with '
+                                'every launch on this path; "check" below verifies this very run); everything else FP64 DMMA tiles.  The all-DMMA '
+                                'figures of the same run are under "fp64_dmma"' % digits),
                        'l2': 'inputs larger than L2: the %d x %d FP64 system (%.2f GB) is rewritten every step'
                        % (n, n, n * n * 8 / 1e9),
                        'parallelism': 'single GPU' if world == 1 else ('one adjustment over %d GPUs: image-sharded assembly + NCCL all-reduce, block-column-cyclic '
@@ -500,6 +536,9 @@ def main():
             'roofline': roofline, 'clocks': clocks, 'gpu_launches': int(launches), 'check': check}
     if e2e:
         line['e2e'] = e2e
+    if dmma:
+        dmma['frac_of_fp64_peak'] = flops / (dmma['ms_per_step'] * 1e-3) / 1e12 / (peak * world)
+        line['fp64_dmma'] = dmma
     if other:
         line['other_configs'] = other
     if structured:
@@ -515,7 +554,7 @@ def main():
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-    bad = [c for c in (check, (structured or {}).get('check')) if c and not c['ok']]
+    bad = [c for c in (check, (structured or {}).get('check'), (dmma or {}).get('check')) if c and not c['ok']]
     if bad:
         raise SystemExit('bench.py: the timed pass FAILED its verification: %r' % bad)
 

@@ -74,6 +74,23 @@ JAICOV_HD inline void tri_tile_decode(int64_t l, int mt, int band, int &it, int 
     it = jt = mt - 1;                                  // not reached for l < mt (mt + 1) / 2
 }
 
+// Tile (it, jt) of a full (rectangular) launch of mt x nt tiles for the linear CTA index l: bands of `band` tile rows, column by
+// column inside a band (band <= 0: row by row).  The CTAs resident together then cover a roughly square patch of C and share few
+// operand strips (used by the int8-digit tile kernel, which is L2 / DRAM bound without it; ozaki.cu).
+JAICOV_HD inline void rect_tile_decode(int64_t l, int mt, int nt, int band, int &it, int &jt) {
+    if (band <= 0) {
+        it = (int)(l / nt);
+        jt = (int)(l - (int64_t)it * nt);
+        return;
+    }
+    const int64_t per = (int64_t)band * nt;
+    const int grp = (int)(l / per), first = grp * band;
+    const int gsz = (mt - first < band) ? mt - first : band;
+    const int64_t rem = l - grp * per;
+    it = first + (int)(rem % gsz);
+    jt = (int)(rem / gsz);
+}
+
 struct GemmDesc {
     int al = 0;       // 0: A is [m][k] (k contiguous); 1: A is [k][m] (m contiguous)
     int bl = 0;       // 0: B is [n][k] (k contiguous); 1: B is [k][n] (n contiguous)

@@ -193,8 +193,10 @@ static void launch_split(const OzSplitArgs &a, cudaStream_t s) {
 }
 
 // ---- the tile kernel -----------------------------------------------------------------------------------------------------
-// digits used when neither jaicov_set_gemm_digits nor JAICOV_GEMM_OZAKI says otherwise (0 = FP64 DMMA tiles everywhere)
-constexpr int kOzakiDefaultDigits = 0;
+// digits used when neither jaicov_set_gemm_digits nor JAICOV_GEMM_OZAKI says otherwise (0 = FP64 DMMA tiles everywhere).
+// 8 since round 2: parity-green on every GPU test with ALL launches on this path (1 and 2 GPUs) and 1.39x faster than the DMMA
+// tiles on the dense route at config 5 (profiles/r02_ozaki_*)
+constexpr int kOzakiDefaultDigits = 8;
 constexpr int OZ_BM = 128, OZ_BN = 64, OZ_BK = 64, OZ_STAGES = 2, OZ_THREADS = 192, OZ_TMEM_COLS = 512;
 
 template <int S> struct OzCfg {
@@ -326,8 +328,11 @@ k_gemm_oz(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     } else if (p.tri_out) {
         tri_tile_decode(l, p.mt, p.tile_band, it, jt);
     } else {
-        it = l / p.nt;
-        jt = l - it * p.nt;
+        // bands of tile_band tile rows, column by column inside a band: the CTAs resident together (one per SM, ~74 tiles) then
+        // cover a roughly square patch of C and share ~band + 74 / band operand strips instead of 1 + 64 -- the row-by-row order
+        // re-read op(B) from DRAM once per tile row (ncu: 32 GB of DRAM reads for 1.07 GB of operands at 8192^3, tensor pipe 40 %
+        // active; profiles/r02_ncu_full_k_gemm_oz_summary.txt)
+        rect_tile_decode(l, p.mt, p.nt, p.tile_band, it, jt);
         if (p.kmode == K_A_LOWER) it = p.mt - 1 - it;
     }
     int64_t kbeg = 0, kend = p.K;
@@ -657,7 +662,8 @@ bool launch_gemm_ozaki(const GemmDesc &g, cudaStream_t s) {
     }
     launch_split(sa, s);
     if (!shared) launch_split(sb, s);
-    OzGemmArgs a{g_oz.e[0], g_oz.e[wb], g.C, g.ldc, g.K, g.alpha, g.beta, g.mt, g.nt, g.tri_out, g.tile_band, g.kmode,
+    static const int oz_band = [] { const char *e = getenv("JAICOV_OZAKI_BAND"); return e ? atoi(e) : 8; }();
+    OzGemmArgs a{g_oz.e[0], g_oz.e[wb], g.C, g.ldc, g.K, g.alpha, g.beta, g.mt, g.nt, g.tri_out, g.tile_band > 0 ? g.tile_band : oz_band, g.kmode,
                  g.coltab, g.coltab_full, g.c_local, g.ktab, g.koff, g.roff};
     const int64_t grid_tiles = g.coltab ? (int64_t)g.mt : tiles;     // column table: x runs over the row tiles, y over the table
     const int grid_y = g.coltab ? g.ncoltab : 1;

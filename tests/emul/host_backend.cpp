@@ -260,6 +260,7 @@ struct HostComm {
 extern "C" {
 
 // tile order of the lower-triangular GEMM launches (dense_driver.hpp: tri_tile_decode), for the bijection test
+void emul_rect_tile_decode(int64_t l, int mt, int nt, int band, int *it, int *jt) { jaicov::rect_tile_decode(l, mt, nt, band, *it, *jt); }
 void emul_tri_tile_decode(int64_t l, int mt, int band, int *it, int *jt) { jaicov::tri_tile_decode(l, mt, band, *it, *jt); }
 
 // distributed Cholesky with `nranks` virtual ranks (threads), panel width pw tiles; on exit every replica must hold

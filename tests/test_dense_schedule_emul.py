@@ -93,3 +93,17 @@ def test_tri_tile_order_is_a_bijection(emul, mt, band):
         assert bands == sorted(bands)
     else:
         assert seen == sorted(seen)
+
+
+@pytest.mark.parametrize('mt,nt', [(1, 1), (7, 3), (8, 8), (13, 64), (64, 5)])
+@pytest.mark.parametrize('band', [0, 1, 8, 16])
+def test_rect_tile_order_is_a_bijection(emul, mt, nt, band):
+    """The band-swizzled order of the full (rectangular) launches of the int8-digit tile kernel visits every tile exactly once."""
+    emul.emul_rect_tile_decode.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+    seen = set()
+    it, jt = ctypes.c_int(0), ctypes.c_int(0)
+    for l in range(mt * nt):
+        emul.emul_rect_tile_decode(l, mt, nt, band, ctypes.byref(it), ctypes.byref(jt))
+        assert 0 <= it.value < mt and 0 <= jt.value < nt
+        seen.add((it.value, jt.value))
+    assert len(seen) == mt * nt
