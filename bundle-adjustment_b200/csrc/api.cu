@@ -267,8 +267,10 @@ struct jaicov_handle {
     bool group_ready = false;
     jaicov_handle() : dist(g_dist) {}
     explicit jaicov_handle(DistContext &d) : dist(d) {}
-    int panel_tiles = 8;                 // block-column panel width of the distributed Cholesky, in 128-tiles (1024 columns:
-                                         // measured 1628 ms vs 1697 ms for 512 at config 5 on 2 GPUs)
+    int panel_tiles = 16;                // block-column panel width of the distributed Cholesky, in 128-tiles.  2048 columns since the
+                                         // int8 digit products became the default: their rate grows with the contraction length
+                                         // (36 / 42 / 45 TFLOP/s FP64-equivalent at K = 1024 / 2048 / 4096, profiles/r02_gemm_k_sweep.log);
+                                         // config 5: 3388 -> 3163 ms on 2 GPUs, 1807 -> 1733 ms on 4 (32 tiles: 1790).  JAICOV_PANEL_TILES
     DevBuf<double> Xl;                   // np x (128 * ntc): this rank's column tiles of the inverse
     DevBuf<int32_t> d_ktab, d_col_local, d_ptab;
     std::vector<int32_t> ktab;           // first columns of the 128-wide tiles of the INVERSE this rank computes

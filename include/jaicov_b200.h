@@ -178,7 +178,10 @@ int32_t jaicov_get_qxx_local(jaicov_handle *h, int32_t *n_tiles, int32_t *tile_f
  * models by enum ordinal AFFINITY, TANGENTIAL, RADIAL, DISTANCE, ZERNIKE_X, ZERNIKE_Y, ZERNIKE_GRADIENT
  * (camera/Camera.java:50, camera/distortion/DistortionModel.java:29-37); inside TANGENTIAL: Bx, By, then Bi;
  * inside AFFINITY: Cx, Cy.  Fixed coefficients (col = JAICOV_COL_FIXED) must still be listed: they distort.
- * coef_order = PolynomialCoefficient.getOrder() (Zernike: the single index j), 0 for Bx/By/Cx/Cy. */
+ * coef_order = PolynomialCoefficient.getOrder() (Zernike: the single index j), 0 for Bx/By/Cx/Cy.
+ * Capacity: any number of cameras; at most 62 distortion coefficients in ONE camera (its Gram row [EO | IO | coefficients | w] is held in
+ * nine 8-column tensor-core tiles), else the first computing call returns JAICOV_ILLEGAL_ARGUMENT.  (The reference has no limit; its
+ * cameras carry at most a few dozen coefficients: 2 + 2 + n_A + n_B + n_D + Zernike terms.) */
 int32_t jaicov_set_cameras(jaicov_handle *h, int32_t n_cam, const double *io_val, const int32_t *io_col, const double *r0,
                            const int32_t *coef_ptr, const int32_t *coef_type, const int32_t *coef_order,
                            const double *coef_val, const int32_t *coef_col);

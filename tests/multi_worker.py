@@ -71,7 +71,7 @@ def main():
         t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
         dist.all_reduce(t)
         return t.cpu().numpy()
-    chk = verify.check_pass(s, columns=verify.sample_columns(n, n - u, world=world, panel=128 * int(os.environ.get('JAICOV_PANEL_TILES', '8'))),
+    chk = verify.check_pass(s, columns=verify.sample_columns(n, n - u, world=world, panel=128 * int(os.environ.get('JAICOV_PANEL_TILES', '16'))),
                             reduce_sum=reduce_sum, omega=st.omega, values_updated=True)
     if rank == 0:
         o = (FastOracle if which == 'cfg4mid' else Oracle)(scene)
@@ -94,7 +94,7 @@ def main():
         print(json.dumps({'scene': which, 'world': world, 'solver_used': st.solver_used, 'rc': rc, 'rc_oracle': so, 'iterations': st.iterations,
                           'iterations_oracle': len(o.history), 'sigma2_rel_err': abs(st.sigma2aposteriori - s2o) / s2o,
                           'qxx_scaled_err': errq, 'param_rel_err': errx, 'qxx_local_vs_block_maxabs': float(le[0]), 'ms_last_pass': st.ms_total,
-                          'ms_factor': st.ms_factor, 'ms_inverse': st.ms_inverse, 'n': n, 'panel_tiles': int(os.environ.get('JAICOV_PANEL_TILES', '8')),
+                          'ms_factor': st.ms_factor, 'ms_inverse': st.ms_inverse, 'n': n, 'panel_tiles': int(os.environ.get('JAICOV_PANEL_TILES', '16')),
                           'verify': {k: chk[k] for k in ('datum_residual', 'cofactor_residual', 'omega_rel_diff')}}), flush=True)
     s.close()
     dist.barrier()

@@ -582,6 +582,16 @@ def test_bad_indices_are_illegal_arguments_not_device_faults(built):
     assert 'coef_type' in attempt(coef_type=setter(1, 999))
     assert 'object point index' in attempt(obj_idx=setter(5, 40))
     assert 'column index' in attempt(eo_col=setter(3, 100000))
+    # the one remaining capacity limit (documented in include/jaicov_b200.h): more than 62 distortion coefficients in ONE camera
+    sc63 = synthetic_scene(2, images=4, targets=30)[0]
+    sc63['cameras'][0]['coefs'] = sc63['cameras'][0]['coefs'] + [(163, j, 1e-6, False) for j in range(3, 60)]
+    adj63, flat63 = flat_problem(sc63)
+    s63 = ba.Session(sigma2apriori=adj63.getVarianceFactorApriori())
+    s63.set_problem(flat63)
+    with pytest.raises(ba.JaicovError, match='62 distortion coefficients') as e63:
+        s63.iterate(final_pass=False)
+    assert e63.value.code == ba._lib.ILLEGAL_ARGUMENT
+    s63.close()
     # the context is intact: a correct problem still runs
     s = ba.Session(sigma2apriori=adj.getVarianceFactorApriori())
     s.set_problem(flat)
