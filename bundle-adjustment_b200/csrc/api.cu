@@ -32,10 +32,12 @@ void launch_potrf_diag(double *A, int64_t ld, double *dinv, int row0, int *info,
 void launch_copy2d(double *dst, int64_t ldd, const double *src, int64_t lds, int64_t rows, int64_t cols, cudaStream_t s);
 void launch_solve_rows8(const double *L, int64_t ld, const double *dinv, double *R, double *Y, int64_t np, cudaStream_t s);
 // stage_kernels.cu
-void launch_precond_diag(const double *M, int64_t ld, int u, int64_t np, double *V, cudaStream_t s);
+void launch_precond_diag(const SysView &M, int u, int64_t np, double *V, cudaStream_t s);
 void launch_datum_rows(const double *xyz, const int32_t *pt_col, const int32_t *datum_pts, int nDatum, int free_mask, int d,
                        int64_t np, double *Bt, cudaStream_t s);
 void launch_scale_system(double *M, int64_t ld, int u, const double *V, const double *Bt, int d, int64_t np, int64_t row0, cudaStream_t s);
+void launch_scale_system_own(double *Mo, int64_t ldo, const int32_t *own_cols, int n_own, int u, const double *V, const double *Bt, int d,
+                             int64_t np, cudaStream_t s);
 void launch_build_rhs(double *Rt, double *Btv, int64_t np, int u, const double *V, const double *rhs, const double *Bt, int d,
                       int simulation, cudaStream_t s);
 void launch_datum_solve(const double *Xt, const double *Btv, int d, int64_t np, int u, const double *V, double *dxref, double *H,
@@ -50,12 +52,12 @@ void launch_get_block(const double *lower, int64_t ld, const double *border, int
                       int c0, int c1, double *out, cudaStream_t s);
 void launch_group_w(int r, const double *const *tptr, const double *obs, double *w, cudaStream_t s);
 void launch_group_stack(int r, const int32_t *col, const double *var, const double *Pw, int64_t ldp, double sigma2, const double *w,
-                        int d, int64_t ld, double *M, double *rhs, cudaStream_t s);
+                        int d, const SysView &M, double *rhs, cudaStream_t s);
 void launch_group_omega(int r, const int32_t *col, const double *var, const double *Pw, int64_t ldp, double sigma2, const double *w,
                         const double *dxref, double *out, cudaStream_t s);
 void launch_unpack_scaled(const double *ap, int r, double scale, double *M, int64_t ld, int64_t np, cudaStream_t s);
 void launch_symmetrize(double *M, int64_t ld, int r, cudaStream_t s);
-void launch_damp_diag(double *M, int64_t ld, int u, double lambda, cudaStream_t s);
+void launch_damp_diag(const SysView &M, int u, double lambda, cudaStream_t s);
 void launch_scale_vector(double *x, int64_t n, double alpha, cudaStream_t s);
 void launch_identity_columns(double *X, int64_t ldx, int64_t np, const int32_t *ktab, int ntc, cudaStream_t s);
 void launch_qxx_epilogue_cols(double *X, int64_t ldx, int ntc, const int32_t *ktab, int u, const double *V, const double *H,
@@ -271,6 +273,15 @@ struct jaicov_handle {
                                          // int8 digit products became the default: their rate grows with the contraction length
                                          // (36 / 42 / 45 TFLOP/s FP64-equivalent at K = 1024 / 2048 / 4096, profiles/r02_gemm_k_sweep.log);
                                          // config 5: 3388 -> 3163 ms on 2 GPUs, 1807 -> 1733 ms on 4 (32 tiles: 1790).  JAICOV_PANEL_TILES
+    bool owner_only = false;             // distributed dense route: M holds only this rank's own block-column panels (np x ldo),
+                                         // every rank evaluates all observations and keeps what it owns (no all-reduce of N), the
+                                         // factor is streamed panel by panel (DenseSchedule::factor_solve_invert_streamed)
+    bool obs_sharded = false;            // the observation sweeps run on this rank's image shard only (replicated layout)
+    int64_t ldo = 0;                     // leading dimension of M with owner-only storage (128 * own tiles)
+    SysView sys;                         // where the entries of N live on this rank
+    DevBuf<int32_t> d_tile_lcol;
+    DevBuf<double> gather;               // single-process handle, device 0: the gathered Qxx (np x np lower) when M is owner-only
+    cudaEvent_t ev_phase = nullptr;
     DevBuf<double> Xl;                   // np x (128 * ntc): this rank's column tiles of the inverse
     DevBuf<int32_t> d_ktab, d_col_local, d_ptab;
     std::vector<int32_t> ktab;           // first columns of the 128-wide tiles of the INVERSE this rank computes
@@ -552,10 +563,19 @@ void prepare(jaicov_handle *h) {
                             (k == 2 && ix >= 0 && ix < P.nCoef) || (k == 3 && ix >= 0 && ix < P.nImg && cp >= 0 && cp < 6);
             if (!ok) throw std::runtime_error("observed group: target kind / index / component out of range");
         }
-    // image shard of this rank: contiguous image ranges balanced by observation count
+    // image shard of this rank: contiguous image ranges balanced by observation count.  Owner-only storage (the
+    // distributed dense route): every rank sweeps ALL observations and keeps the entries it owns -- 3.4 ms of replicated sweeps
+    // per pass at config 5 instead of all-reducing 1.5 GB of N.
+    select_solver(h);       // needs only host data; decides the route (and with it the storage layout) before anything is sharded
+    h->owner_only = false;
+    if (h->dist_on && h->dist.world > 1 && !h->st.on) {
+        const char *e = getenv("JAICOV_DIST_STORAGE");
+        h->owner_only = !(e && !strcmp(e, "replica"));
+    }
+    h->obs_sharded = h->dist_on && h->dist.world > 1 && !h->owner_only;
     {
         int32_t i0 = 0, i1 = P.nImg;
-        jaicov_shard_images(P.nImg, h->pt_ptr.data(), h->dist_on ? h->dist.world : 1, h->dist_on ? h->dist.rank : 0, &i0, &i1);
+        jaicov_shard_images(P.nImg, h->pt_ptr.data(), h->obs_sharded ? h->dist.world : 1, h->obs_sharded ? h->dist.rank : 0, &i0, &i1);
         P.img0 = i0;
         P.img1 = i1;
         P.obs0 = h->pt_ptr[P.img0];
@@ -693,11 +713,11 @@ void prepare(jaicov_handle *h) {
     }
     S.img_partial = h->d_img_partial.p; S.cam_partial = h->d_cam_partial.p; S.pt_partial = h->d_pt_partial.p;
     S.omega_partial = h->d_omega_partial.p;
-    // ---- solver route --------------------------------------------------------------------------------------------
-    select_solver(h);
     // ---- system buffers ------------------------------------------------------------------------------------------
     const size_t np = (size_t)P.np;
-    h->M.alloc(np * np);
+    if (h->owner_only && h->st.on) throw std::runtime_error("internal: owner-only storage chosen for the structured route");
+    if (!h->owner_only) h->M.alloc(np * np);
+    h->sys = SysView{h->M.p, P.np, nullptr};
     if (h->dist_on) {
         // Factor: block-column panels of panel_tiles tiles, owner = panel % world.
         // Inverse: tile c costs ~ (nb - c)^2, so its tiles are dealt out one by one in snake order
@@ -721,6 +741,16 @@ void prepare(jaicov_handle *h) {
             if (pt.empty()) pt.push_back(0);
             h->d_ptab.upload(pt);
         }
+        if (h->owner_only) {
+            // own tiles side by side in ascending order: local tile index = position in ptab
+            std::vector<int32_t> lcol(nb, -1);
+            for (size_t lt = 0; lt < h->ptab.size(); lt++) lcol[h->ptab[lt] / kBlk] = (int32_t)(lt * kBlk);
+            h->d_tile_lcol.upload(lcol);
+            h->ldo = (int64_t)std::max<size_t>(h->ptab.size(), 1) * kBlk;
+            h->M.alloc(np * (size_t)h->ldo);
+            h->sys = SysView{h->M.p, h->ldo, h->d_tile_lcol.p};
+            if (!h->ev_phase) JCHECK(cudaEventCreate(&h->ev_phase));
+        }
         std::vector<int32_t> kt = h->ktab;
         if (kt.empty()) kt.push_back(0);
         h->d_ktab.upload(kt);
@@ -729,7 +759,7 @@ void prepare(jaicov_handle *h) {
         int64_t r0 = -1;
         for (int32_t c : h->eo_col)
             if (active(c)) r0 = (r0 < 0) ? c - d : std::min<int64_t>(r0, c - d);
-        h->strip_row0 = r0;
+        h->strip_row0 = h->owner_only ? -1 : r0;
     } else if (h->wants_inverse() && !h->st.on) {
         h->W.alloc(np * np);
     }
@@ -808,15 +838,15 @@ void assemble(jaicov_handle *h, bool sparse_clear = false) {
         JCHECK(cudaMemsetAsync(h->M.p + up * np, 0, (np - up) * np * sizeof(double), s));
         launch_zero_point_blocks(h->M.p, P.np, h->st.blk_start.p, h->st.blk_size.p, h->st.nBlk, s);
     } else {
-        JCHECK(cudaMemsetAsync(h->M.p, 0, np * np * sizeof(double), s));
+        JCHECK(cudaMemsetAsync(h->M.p, 0, np * (h->owner_only ? (size_t)h->ldo : np) * sizeof(double), s));
     }
     JCHECK(cudaMemsetAsync(h->rhs.p, 0, np * sizeof(double), s));
     JCHECK(cudaMemsetAsync(h->Bt.p, 0, 8 * np * sizeof(double), s));
     launch_pose(P, s);
     JCHECK(cudaEventRecord(h->evk[0], s));
-    launch_assemble_images(P, h->S, h->M.p, h->rhs.p, s);
+    launch_assemble_images(P, h->S, h->sys, h->rhs.p, s);
     JCHECK(cudaEventRecord(h->evk[1], s));
-    const bool multi = h->dist_on && h->dist.world > 1;
+    const bool multi = h->obs_sharded;      // image shards: the shared pieces are summed over the ranks
     const AssemblyScratch &S = h->S;
     for (size_t gi = 0; gi < h->pt_groups.size(); gi++) {
         const PtGroup &g = h->pt_groups[gi];
@@ -832,18 +862,18 @@ void assemble(jaicov_handle *h, bool sparse_clear = false) {
                 if (h->strip_row0 >= 0)
                     h->dist.allreduce_sum(h->M.p + (size_t)h->strip_row0 * np, ((size_t)P.np - h->strip_row0) * np, s);
             }
-            launch_camera_scatter(P, S, h->M.p, h->rhs.p, s);
+            launch_camera_scatter(P, S, h->sys, h->rhs.p, s);
         }
-        launch_point_scatter(P, S, g, h->kbase_host[g.cam0], h->M.p, h->rhs.p, s);
+        launch_point_scatter(P, S, g, h->kbase_host[g.cam0], h->sys, h->rhs.p, s);
     }
     for (ImgSigma &is : h->img_sigma)
         if (is.rp)
             launch_dense_image_assemble(P, is.img, h->pt_ptr[is.img + 1] - h->pt_ptr[is.img], is.Pw.p, is.rp, is.rp, h->ds_Ac.p, h->ds_T.p,
                                         h->ds_G.p, h->M.p, h->rhs.p, s);
-    launch_scale_bars(P, h->M.p, h->rhs.p, s);
+    launch_scale_bars(P, h->sys, h->rhs.p, s);
     for (Group &g : h->groups) {
         launch_group_w(g.r, g.tptr.p, g.d_obs.p, g.w.p, s);
-        launch_group_stack(g.r, g.col.p, g.d_var.p, g.Pw.p, g.ldp, P.sigma2, g.w.p, P.d, P.np, h->M.p, h->rhs.p, s);
+        launch_group_stack(g.r, g.col.p, g.d_var.p, g.Pw.p, g.ldp, P.sigma2, g.w.p, P.d, h->sys, h->rhs.p, s);
     }
     if (P.d > 0) launch_datum_rows(P.xyz, P.pt_col, h->d_datum_pts.p, h->nDatumPts, h->free_mask, P.d, P.np, h->Bt.p, s);
     JCHECK(cudaGetLastError());
@@ -904,11 +934,15 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
         h->adapted_damping = h->opt.damping_value;
         h->derive_first_damping = false;
     }
-    if (h->adapted_damping > 0) launch_damp_diag(h->M.p, P.np, P.u, h->adapted_damping, s);
+    if (h->adapted_damping > 0) launch_damp_diag(h->sys, P.u, h->adapted_damping, s);
     // preconditioner and SPD reformulation (K4)
-    launch_precond_diag(h->M.p, P.np, P.u, P.np, h->V.p, s);
+    launch_precond_diag(h->sys, P.u, P.np, h->V.p, s);
+    if (h->owner_only) h->dist.allreduce_sum(h->V.p, (size_t)P.np, s);      // every rank contributed the entries of its own diagonal
     // (the structured route keeps the datum rows as a border of its reduced system instead of folding B'B into N)
-    launch_scale_system(h->M.p, P.np, P.u, h->V.p, h->Bt.p, h->st.on ? 0 : P.d, P.np, h->st.on ? h->st.D.up : 0, s);
+    if (h->owner_only)
+        launch_scale_system_own(h->M.p, h->ldo, h->d_ptab.p, (int)h->ptab.size(), P.u, h->V.p, h->Bt.p, P.d, P.np, s);
+    else
+        launch_scale_system(h->M.p, P.np, P.u, h->V.p, h->Bt.p, h->st.on ? 0 : P.d, P.np, h->st.on ? h->st.D.up : 0, s);
     JCHECK(cudaMemsetAsync(h->Rt.p, 0, (size_t)kRhsRows * np * sizeof(double), s));
     launch_build_rhs(h->Rt.p, h->Btv.p, P.np, P.u, h->V.p, h->rhs.p, h->Bt.p, P.d, h->opt.estimation_type == JAICOV_SIMULATION, s);
     h->have_neq = false;
@@ -949,6 +983,22 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
         launch_symmetrize(st.Sm.p, D.ncp, D.nc, s);
         launch_border_f(st.Sm.p, D, st.ED.p, st.Fb.p, h->small.p, s);
         launch_fill_qprime(st.Sm.p, D, st.Fb.p, h->small.p, st.Kp.p, s);
+    } else if (multi && h->owner_only) {
+        // owner-only storage: factorisation, the solves for n and the datum rows, and (final pass) both triangular sweeps of this
+        // rank's columns of the inverse in ONE schedule that consumes every panel where the broadcast lands it
+        const int ntc = invert ? (int)h->ktab.size() : 0;
+        const int64_t ldx = (int64_t)std::max(ntc, 1) * kBlk;
+        if (ntc > 0) {
+            JCHECK(cudaMemsetAsync(h->Xl.p, 0, np * (size_t)ldx * sizeof(double), s));
+            launch_identity_columns(h->Xl.p, ldx, P.np, h->d_ktab.p, ntc, s);
+        }
+        StreamPanelComm sc{&h->dist, s, h->M.p, h->ldo, P.np, h->Dinv.p, h->panel_tiles, h->ev_phase};
+        sc.ensure_stage((size_t)P.np * h->panel_tiles * kBlk + (size_t)h->panel_tiles * kBlk * kBlk);
+        DenseSchedule<CudaBackend> dso{be, h->M.p, h->ldo, P.np, h->Dinv.p};
+        dso.factor_solve_invert_streamed(sc, h->dist.rank, h->dist.world, h->panel_tiles, h->d_ptab.p, (int)h->ptab.size(), h->ptab.data(),
+                                         h->Rt.p, P.np, 1, ntc > 0 ? h->Xl.p : nullptr, ldx, ntc, h->d_ktab.p, true);
+        JCHECK(cudaEventRecord(h->dist.ev_tmp, h->dist.net));
+        JCHECK(cudaStreamWaitEvent(s, h->dist.ev_tmp, 0));
     } else if (multi) {
         PanelComm pc{&h->dist, s, h->M.p, P.np, P.np, h->Dinv.p, h->panel_tiles};
         pc.ensure_stage((size_t)P.np * h->panel_tiles * kBlk + (size_t)h->panel_tiles * kBlk * kBlk);
@@ -970,7 +1020,7 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
         launch_structured_solution(h->Rt.p, st.D, st.col_blk.p, st.blk_start.p, st.blk_size.p, st.Pinv.p, st.Zt.p, st.Yt.p, st.Kp.p,
                                    h->Btv.p, h->V.p, st.zp.p, st.rp.p, st.yr.p, st.ys.p, h->H.p, h->small.p + 100, h->dxref.p, h->Tq.p, s);
     } else {
-        launch_solve_rows8(h->M.p, P.np, h->Dinv.p, h->Rt.p, h->Rt.p + 8 * np, P.np, s);
+        if (!h->owner_only) launch_solve_rows8(h->M.p, P.np, h->Dinv.p, h->Rt.p, h->Rt.p + 8 * np, P.np, s);
         launch_datum_solve(h->Rt.p, h->Btv.p, P.d, P.np, P.u, h->V.p, h->dxref.p, h->H.p, h->Tq.p, h->small.p, s);
     }
     // Levenberg-Marquardt step control (updateModel, BA:390-426): shorten the step, compare Omega, accept or reject
@@ -981,7 +1031,7 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
         const double alpha = std::min(0.25 * std::pow(h->adapted_damping, -0.05), 0.75);
         launch_scale_vector(h->dxref.p, (int64_t)P.u + P.d, alpha, s);
         double prev = h->lm_omega;
-        const double cur = omega_now(h, h->dist_on && h->dist.world > 1);
+        const double cur = omega_now(h, h->obs_sharded);
         prev = prev <= 0 ? 1.7976931348623157e308 : prev;
         const bool converge = prev >= cur;
         h->lm_omega = cur;
@@ -1044,9 +1094,11 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
         const int ntc = (int)h->ktab.size();
         if (ntc > 0) {
             const int64_t ldx = (int64_t)ntc * kBlk;
-            JCHECK(cudaMemsetAsync(h->Xl.p, 0, np * (size_t)ldx * sizeof(double), s));
-            launch_identity_columns(h->Xl.p, ldx, P.np, h->d_ktab.p, ntc, s);
-            ds.inverse_columns(h->Xl.p, ldx, ntc, h->d_ktab.p);
+            if (!h->owner_only) {          // (owner-only storage: both sweeps already ran inside the streamed schedule)
+                JCHECK(cudaMemsetAsync(h->Xl.p, 0, np * (size_t)ldx * sizeof(double), s));
+                launch_identity_columns(h->Xl.p, ldx, P.np, h->d_ktab.p, ntc, s);
+                ds.inverse_columns(h->Xl.p, ldx, ntc, h->d_ktab.p);
+            }
             launch_qxx_epilogue_cols(h->Xl.p, ldx, ntc, h->d_ktab.p, P.u, h->V.p, h->H.p, h->Rt.p + np, P.d, P.np, s);
         }
     } else if (invert) {
@@ -1063,7 +1115,7 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
         JCHECK(cudaEventRecord(h->evk[4], s));
         launch_omega(P, h->S, h->dxref.p, h->omega_parts.p, s);
         JCHECK(cudaEventRecord(h->evk[5], s));
-        if (multi) h->dist.allreduce_sum(h->omega_parts.p, 1, s);
+        if (h->obs_sharded) h->dist.allreduce_sum(h->omega_parts.p, 1, s);
         omega_dense_images(h);
         if (P.nBar) launch_omega_bars(P, h->dxref.p, h->omega_parts.p + 1, s);
         int gi = 0;
@@ -1111,6 +1163,13 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
     }
     float ms[6];
     for (int i = 0; i < 6; i++) cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]);
+    if (h->owner_only && multi) {   // one fused schedule: forward phase = factor (+ forward substitutions), backward phase counts as inverse
+        float fwd = 0, bwd = 0;
+        cudaEventElapsedTime(&fwd, h->ev[1], h->ev_phase);
+        cudaEventElapsedTime(&bwd, h->ev_phase, h->ev[2]);
+        ms[1] = fwd;
+        ms[3] += bwd;
+    }
     h->stats.ms_assembly = ms[0]; h->stats.ms_factor = ms[1]; h->stats.ms_solve = ms[2]; h->stats.ms_inverse = ms[3];
     h->stats.ms_omega = ms[4];
     float tot;
@@ -1319,6 +1378,7 @@ void jaicov_destroy(jaicov_handle *h) {
         if (h->dist_on) cudaDeviceSynchronize();   // the process-wide communicator stays
         for (auto &e : h->ev) if (e) cudaEventDestroy(e);
         for (auto &e : h->evk) if (e) cudaEventDestroy(e);
+        if (h->ev_phase) cudaEventDestroy(h->ev_phase);
         cudaStreamDestroy(h->stream);
     }
     delete h;
@@ -1675,7 +1735,9 @@ int32_t jaicov_get_dx(jaicov_handle *h, double *dx) {
     API_GUARD_END(h)
 }
 
-static int32_t pack_to_host(jaicov_handle *h, const double *border, const double *q11, double *dst, int64_t n_limit = -1) {
+static int32_t pack_to_host(jaicov_handle *h, const double *border, const double *q11, double *dst, int64_t n_limit = -1,
+                            const double *lower = nullptr) {
+    if (!lower) lower = h->M.p;
     NvtxRange nvtx_("jaicov: packed Qxx -> host");
     const DevProblem &P = h->P;
     const int64_t n = n_limit >= 0 ? n_limit : (int64_t)P.u + P.d;   // the packed leading block is a prefix of the packed matrix
@@ -1690,7 +1752,7 @@ static int32_t pack_to_host(jaicov_handle *h, const double *border, const double
         int64_t c1 = c0;
         int64_t cnt = 0;
         while (c1 < n && (cnt == 0 || cnt + c1 + 1 <= (int64_t)stage[0].n)) { cnt += c1 + 1; c1++; }
-        launch_pack_columns(h->M.p, P.np, border, P.np, q11, P.d, c0, c1, stage[which].p, s);
+        launch_pack_columns(lower, P.np, border, P.np, q11, P.d, c0, c1, stage[which].p, s);
         JCHECK(cudaMemcpyAsync(dst + c0 * (c0 + 1) / 2, stage[which].p, cnt * sizeof(double), cudaMemcpyDeviceToHost, s));
         which ^= 1;
         c0 = c1;
@@ -1708,6 +1770,11 @@ static int32_t group_gather_qxx(jaicov_handle *g) {
     if (h0->gathered_qxx) return JAICOV_OK;
     const int64_t np = h0->P.np;
     JCHECK(cudaSetDevice(h0->opt.device));
+    double *dstM = h0->M.p;
+    if (h0->owner_only) {            // device 0 holds only its own panels: the gathered matrix gets a buffer of its own
+        if (h0->gather.n < (size_t)np * np) h0->gather.alloc((size_t)np * np);
+        dstM = h0->gather.p;
+    }
     for (size_t r = 1; r < g->sub.size(); r++) {
         int can = 0;
         JCHECK(cudaDeviceCanAccessPeer(&can, h0->opt.device, g->sub[r]->opt.device));
@@ -1726,7 +1793,7 @@ static int32_t group_gather_qxx(jaicov_handle *g) {
         const int64_t ldx = (int64_t)sh->ktab.size() * kBlk;
         for (size_t jl = 0; jl < sh->ktab.size(); jl++) {
             const int64_t e0 = sh->ktab[jl];
-            JCHECK(cudaMemcpy2DAsync(h0->M.p + e0 * np + e0, (size_t)np * sizeof(double), sh->Xl.p + e0 * ldx + (int64_t)jl * kBlk,
+            JCHECK(cudaMemcpy2DAsync(dstM + e0 * np + e0, (size_t)np * sizeof(double), sh->Xl.p + e0 * ldx + (int64_t)jl * kBlk,
                                      (size_t)ldx * sizeof(double), kBlk * sizeof(double), (size_t)(np - e0), cudaMemcpyDeviceToDevice,
                                      h0->stream));
         }
@@ -1744,7 +1811,7 @@ int32_t jaicov_get_qxx_packed(jaicov_handle *h, double *dst) {
             if (!sh->have_qxx) return fail(h, JAICOV_NOT_INITIALISED, "no cofactor matrix: run a final pass with invert_mode FULL");
         API_GUARD_BEGIN
         group_gather_qxx(h);
-        return pack_to_host(h0, h0->Tq.p, h0->small.p + 49, dst, h0->qxx_rows());
+        return pack_to_host(h0, h0->Tq.p, h0->small.p + 49, dst, h0->qxx_rows(), h0->owner_only ? h0->gather.p : h0->M.p);
         API_GUARD_END(h)
     }
     if (!h->have_qxx) return fail(h, JAICOV_NOT_INITIALISED, "no cofactor matrix: run a final pass with invert_mode FULL");
@@ -2107,6 +2174,8 @@ int32_t jaicov_get_normal_equations(jaicov_handle *h, double *n_packed, double *
     API_GUARD_BEGIN
     prepare(h);
     JCHECK(cudaSetDevice(h->opt.device));
+    if (h->owner_only && n_packed)
+        return fail(h, JAICOV_ILLEGAL_ARGUMENT, "the distributed dense route stores only this rank's panels of N (JAICOV_DIST_STORAGE=replica keeps a whole copy per rank)");
     assemble(h);
     JCHECK(cudaStreamSynchronize(h->stream));
     const DevProblem &P = h->P;
@@ -2138,7 +2207,7 @@ int32_t jaicov_omega(jaicov_handle *h, const double *dx, double *omega) {
     JCHECK(cudaMemcpy(h->dxref.p, dx, (size_t)(P.u + P.d) * sizeof(double), cudaMemcpyHostToDevice));
     launch_pose(P, s);
     launch_omega(P, h->S, h->dxref.p, h->omega_parts.p, s);
-    if (h->dist_on && h->dist.world > 1) h->dist.allreduce_sum(h->omega_parts.p, 1, s);
+    if (h->obs_sharded) h->dist.allreduce_sum(h->omega_parts.p, 1, s);
     omega_dense_images(h);
     JCHECK(cudaMemsetAsync(h->omega_parts.p + 1, 0, sizeof(double), s));
     if (P.nBar) launch_omega_bars(P, h->dxref.p, h->omega_parts.p + 1, s);
@@ -2192,7 +2261,7 @@ int32_t jaicov_normal_product(jaicov_handle *h, int32_t nvec, const double *x, d
     const bool want_rhs = rhs != nullptr || wpw != nullptr;
     launch_pose(P, s);
     launch_normal_product_points(P, nvec, n, dX.p, dY.p, want_rhs ? dR.p : nullptr, want_rhs ? dW.p : nullptr, s);
-    if (h->dist_on && h->dist.world > 1) {      // image shards: sum over the ranks; everything below is replicated
+    if (h->obs_sharded) {      // image shards: sum over the ranks; everything below is replicated
         if (nvec) h->dist.allreduce_sum(dY.p, (size_t)nvec * n, s);
         if (want_rhs) { h->dist.allreduce_sum(dR.p, (size_t)n, s); h->dist.allreduce_sum(dW.p, 1, s); }
     }

@@ -90,7 +90,7 @@ constexpr int kImgWarps = 4;
 
 template <int NT, int MINB>
 __global__ void __launch_bounds__(kImgWarps * 32, MINB) k_by_image(DevProblem P, const WorkItem *__restrict__ work,
-                                                             double *__restrict__ partial, double *__restrict__ M) {
+                                                                   double *__restrict__ partial, SysView M) {
     constexpr int LDT = 68;  // tile is stored column-major [NC][68]: == 4 (mod 16) -> conflict-free fragment reads,
                              // and lanes write consecutive rows of one column -> conflict-free stores
     constexpr int NC = 8 * NT;
@@ -110,7 +110,6 @@ __global__ void __launch_bounds__(kImgWarps * 32, MINB) k_by_image(DevProblem P,
     const CamView cv = view_of(P, cs);
     const ImgPose &q = s_pose;
     const int wcol = 9 + cs.ncoef;
-    const int64_t ld = P.np;
     const int d = P.d;
 
     double acc[NT][NT][2];
@@ -161,7 +160,7 @@ __global__ void __launch_bounds__(kImgWarps * 32, MINB) k_by_image(DevProblem P,
                 for (int c = 0; c < 3; c++) {
                     const int32_t cp = pc[c];
                     if (!col_active(cp)) continue;
-                    M[lower_idx(ce - d, cp - d, ld)] = tex[e] * tpx[c] + tey[e] * tpy[c];
+                    sys_set(M, ce - d, cp - d, tex[e] * tpx[c] + tey[e] * tpy[c]);
                 }
             }
         } else {
@@ -206,8 +205,7 @@ __global__ void __launch_bounds__(kImgWarps * 32, MINB) k_by_image(DevProblem P,
 }
 
 // per image: sum work-item partials (fixed order), scatter EO blocks, hand the camera block to cam_partial
-__global__ void __launch_bounds__(256) k_image_finalize(DevProblem P, AssemblyScratch S, double *__restrict__ M,
-                                                         double *__restrict__ rhs) {
+__global__ void __launch_bounds__(256) k_image_finalize(DevProblem P, AssemblyScratch S, SysView M, double *__restrict__ rhs) {
     extern __shared__ double G[];  // NC*NC
     const int img = P.img0 + blockIdx.x, tid = threadIdx.x;
     const int NC = 8 * S.ntImg;
@@ -223,7 +221,6 @@ __global__ void __launch_bounds__(256) k_image_finalize(DevProblem P, AssemblySc
     const int kc = 3 + ncoef, wcol = 9 + ncoef;
     const int32_t *ec = P.eo_col + 6 * (int64_t)img;
     const int32_t *cc = P.campos_col + P.cam_kbase[cam];
-    const int64_t ld = P.np;
     const int d = P.d;
     // EO x EO (lower incl. diagonal), EO x camera parameters, rhs of EO
     for (int i = tid; i < 6 * (6 + kc + 1); i += blockDim.x) {
@@ -234,11 +231,11 @@ __global__ void __launch_bounds__(256) k_image_finalize(DevProblem P, AssemblySc
             if (c > e) continue;
             const int32_t c2 = ec[c];
             if (!col_active(c2)) continue;
-            M[lower_idx(ce - d, c2 - d, ld)] += G[e * NC + c];
+            sys_add(M, ce - d, c2 - d, G[e * NC + c]);
         } else if (c < 6 + kc) {
             const int32_t c2 = cc[c - 6];
             if (!col_active(c2)) continue;
-            M[lower_idx(ce - d, c2 - d, ld)] += G[e * NC + c];
+            sys_add(M, ce - d, c2 - d, G[e * NC + c]);
         } else {
             rhs[ce - d] += G[e * NC + wcol];
         }
@@ -270,13 +267,11 @@ __global__ void __launch_bounds__(256) k_camera_sum(DevProblem P, AssemblyScratc
 }
 
 // scatter the camera blocks into N / n
-__global__ void __launch_bounds__(256) k_camera_scatter(DevProblem P, AssemblyScratch S, double *__restrict__ M,
-                                                         double *__restrict__ rhs) {
+__global__ void __launch_bounds__(256) k_camera_scatter(DevProblem P, AssemblyScratch S, SysView M, double *__restrict__ rhs) {
     const int cam = blockIdx.x, tid = threadIdx.x;
     const int kc = 3 + P.coef_ptr[cam + 1] - P.coef_ptr[cam];
     const int32_t *cc = P.campos_col + P.cam_kbase[cam];
     const double *in = S.cam_sum + (size_t)cam * S.kcMax * (S.kcMax + 1);
-    const int64_t ld = P.np;
     const int d = P.d;
     for (int i = tid; i < kc * (kc + 1); i += blockDim.x) {
         const int a = i / (kc + 1), b = i % (kc + 1);
@@ -284,7 +279,7 @@ __global__ void __launch_bounds__(256) k_camera_scatter(DevProblem P, AssemblySc
         const int32_t ca = cc[a];
         if (!col_active(ca)) continue;
         if (b < kc && !col_active(cc[b])) continue;
-        if (b < kc) M[lower_idx(ca - d, cc[b] - d, ld)] += in[a * (S.kcMax + 1) + b];
+        if (b < kc) sys_add(M, ca - d, cc[b] - d, in[a * (S.kcMax + 1) + b]);
         else rhs[ca - d] += in[a * (S.kcMax + 1) + S.kcMax];
     }
 }
@@ -372,8 +367,8 @@ __global__ void __launch_bounds__(kPtWarps * 32, MINB) k_by_point(DevProblem P, 
 }
 
 // scatter the per-point partials of one camera group into N / n (single owner per entry)
-__global__ void __launch_bounds__(256) k_point_scatter(DevProblem P, AssemblyScratch S, int NC, int kbase0, int kraw,
-                                                        double *__restrict__ M, double *__restrict__ rhs) {
+__global__ void __launch_bounds__(256) k_point_scatter(DevProblem P, AssemblyScratch S, int NC, int kbase0, int kraw, SysView M,
+                                                        double *__restrict__ rhs) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)P.nPt * 3 * NC) return;
     const int pt = (int)(i / (3 * NC));
@@ -381,17 +376,16 @@ __global__ void __launch_bounds__(256) k_point_scatter(DevProblem P, AssemblyScr
     const int32_t cp = P.pt_col[3 * (int64_t)pt + c];
     if (!col_active(cp)) return;
     const double v = S.pt_partial[i];
-    const int64_t ld = P.np;
     const int d = P.d;
     if (j < 3) {
         if (j > c) return;
         const int32_t c2 = P.pt_col[3 * (int64_t)pt + j];
         if (!col_active(c2)) return;
-        M[lower_idx(cp - d, c2 - d, ld)] += v;
+        sys_add(M, cp - d, c2 - d, v);
     } else if (j < 3 + kraw) {
         const int32_t c2 = P.campos_col[kbase0 + j - 3];
         if (!col_active(c2)) return;
-        M[lower_idx(cp - d, c2 - d, ld)] += v;
+        sys_add(M, cp - d, c2 - d, v);
     } else if (j == 3 + kraw) {
         rhs[cp - d] += v;
     }
@@ -404,7 +398,7 @@ static int sweep_min_blocks() {
 }
 
 template <int NT>
-static void run_by_image(const DevProblem &P, const AssemblyScratch &S, double *M, cudaStream_t s) {
+static void run_by_image(const DevProblem &P, const AssemblyScratch &S, const SysView &M, cudaStream_t s) {
     const size_t smem = (size_t)kImgWarps * 8 * NT * 68 * sizeof(double);
     static PerDeviceOnce once3, once4;
     g_launch_count++;
@@ -447,7 +441,7 @@ static void run_by_point(const DevProblem &P, const AssemblyScratch &S, const Pt
 
 // image points, first half: sweeps over this rank's images (unique EO blocks straight into N, per-camera sums).
 // M and rhs must be zero on entry.
-void launch_assemble_images(const DevProblem &P, const AssemblyScratch &S, double *M, double *rhs, cudaStream_t s) {
+void launch_assemble_images(const DevProblem &P, const AssemblyScratch &S, const SysView &M, double *rhs, cudaStream_t s) {
     if (P.m == 0) return;
     if (S.nWork > 0) {
 #define CALL_IMG(NT) run_by_image<NT>(P, S, M, s)
@@ -475,13 +469,13 @@ void launch_by_point(const DevProblem &P, const AssemblyScratch &S, const PtGrou
     }
 }
 
-void launch_camera_scatter(const DevProblem &P, const AssemblyScratch &S, double *M, double *rhs, cudaStream_t s) {
+void launch_camera_scatter(const DevProblem &P, const AssemblyScratch &S, const SysView &M, double *rhs, cudaStream_t s) {
     if (P.m == 0) return;
     g_launch_count++;
     k_camera_scatter<<<P.nCam, 256, 0, s>>>(P, S, M, rhs);
 }
 
-void launch_point_scatter(const DevProblem &P, const AssemblyScratch &S, const PtGroup &g, int kbase0, double *M, double *rhs,
+void launch_point_scatter(const DevProblem &P, const AssemblyScratch &S, const PtGroup &g, int kbase0, const SysView &M, double *rhs,
                           cudaStream_t s) {
     if (P.m == 0) return;
     const int NC = 8 * g.nt;
@@ -507,9 +501,8 @@ void launch_obs_weights(const DevProblem &P, double *rw, cudaStream_t s) {
 }
 
 // ---- scale bars (PDF:210-283): a handful of observations, one thread, reference order ------------------------
-__global__ void k_scale_bars(DevProblem P, double *__restrict__ M, double *__restrict__ rhs) {
+__global__ void k_scale_bars(DevProblem P, SysView M, double *__restrict__ rhs) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    const int64_t ld = P.np;
     const int d = P.d;
     for (int b = 0; b < P.nBar; b++) {
         const double *A = P.xyz + 3 * (int64_t)P.bar_a[b], *B = P.xyz + 3 * (int64_t)P.bar_b[b];
@@ -525,13 +518,13 @@ __global__ void k_scale_bars(DevProblem P, double *__restrict__ M, double *__res
             rhs[col[i] - d] += a[i] * Pw * w;
             for (int j = 0; j <= i; j++) {
                 if (!col_active(col[j])) continue;
-                M[lower_idx(col[i] - d, col[j] - d, ld)] += a[i] * Pw * a[j];
+                sys_add(M, col[i] - d, col[j] - d, a[i] * Pw * a[j]);
             }
         }
     }
 }
 
-void launch_scale_bars(const DevProblem &P, double *M, double *rhs, cudaStream_t s) {
+void launch_scale_bars(const DevProblem &P, const SysView &M, double *rhs, cudaStream_t s) {
     if (P.nBar == 0) return;
     g_launch_count++;
     k_scale_bars<<<1, 32, 0, s>>>(P, M, rhs);

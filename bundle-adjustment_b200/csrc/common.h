@@ -59,6 +59,33 @@ struct NvtxRange {
     NvtxRange &operator=(const NvtxRange &) = delete;
 };
 
+// Where the entries of the symmetric system matrix live on this rank.  tile_lcol == nullptr: the whole lower triangle, row-major,
+// ld = np (one GPU, or the replicated layout).  Otherwise owner-only storage (distributed dense route): only the 128-column tiles
+// this rank owns, side by side, full height; tile_lcol[t] = first LOCAL column of global tile t, -1 for tiles stored elsewhere
+// (writes to those are dropped -- every rank evaluates all observations and keeps what it owns, no all-reduce of N).
+struct SysView {
+    double *p = nullptr;
+    int64_t ld = 0;
+    const int32_t *tile_lcol = nullptr;
+};
+#if defined(__CUDACC__)
+// address of entry (a, b) / (b, a) of the lower triangle (internal indices), or nullptr if this rank does not store it
+__device__ __forceinline__ double *sys_at(const SysView &v, int64_t a, int64_t b) {
+    const int64_t r = a >= b ? a : b, c = a >= b ? b : a;
+    if (!v.tile_lcol) return v.p + r * v.ld + c;
+    const int32_t lc = v.tile_lcol[c >> 7];
+    return lc < 0 ? nullptr : v.p + r * v.ld + lc + (c & 127);
+}
+__device__ __forceinline__ void sys_add(const SysView &v, int64_t a, int64_t b, double x) {
+    double *q = sys_at(v, a, b);
+    if (q) *q += x;
+}
+__device__ __forceinline__ void sys_set(const SysView &v, int64_t a, int64_t b, double x) {
+    double *q = sys_at(v, a, b);
+    if (q) *q = x;
+}
+#endif
+
 // Flattened problem resident in HBM (structure-of-arrays; all pointers are device pointers).
 struct DevProblem {
     // cameras
@@ -141,14 +168,14 @@ struct PtGroup { int cam0, cam1, kraw, nt; };
 //   launch_assemble_images: sweeps over this rank's images (unique EO blocks into M, per-camera sums);
 //   launch_by_point:        per-point partial sums of one camera group;
 //   launch_camera_scatter / launch_point_scatter: scatter of the (all-reduced) sums into M / rhs
-void launch_assemble_images(const DevProblem &P, const AssemblyScratch &S, double *M, double *rhs, cudaStream_t s);
+void launch_assemble_images(const DevProblem &P, const AssemblyScratch &S, const SysView &M, double *rhs, cudaStream_t s);
 void launch_by_point(const DevProblem &P, const AssemblyScratch &S, const PtGroup &g, cudaStream_t s);
-void launch_camera_scatter(const DevProblem &P, const AssemblyScratch &S, double *M, double *rhs, cudaStream_t s);
-void launch_point_scatter(const DevProblem &P, const AssemblyScratch &S, const PtGroup &g, int kbase0, double *M, double *rhs,
+void launch_camera_scatter(const DevProblem &P, const AssemblyScratch &S, const SysView &M, double *rhs, cudaStream_t s);
+void launch_point_scatter(const DevProblem &P, const AssemblyScratch &S, const PtGroup &g, int kbase0, const SysView &M, double *rhs,
                           cudaStream_t s);
 void launch_omega(const DevProblem &P, const AssemblyScratch &S, const double *dxref, double *omega_out, cudaStream_t s);
 void launch_eval_k1(const DevProblem &P, int ns_max, double *a, double *w, double *p, cudaStream_t s);
-void launch_scale_bars(const DevProblem &P, double *M, double *rhs, cudaStream_t s);
+void launch_scale_bars(const DevProblem &P, const SysView &M, double *rhs, cudaStream_t s);
 void launch_omega_bars(const DevProblem &P, const double *dxref, double *omega_out, cudaStream_t s);
 
 // ---- structured.cu: point-block solver (DESIGN.md "structured route") ------------------------------------------------------

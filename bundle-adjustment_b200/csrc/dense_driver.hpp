@@ -363,6 +363,144 @@ struct DenseSchedule {
             }
         }
     }
+
+    // ---- owner-only storage: factor, solve and column-tile inverse with the factor STREAMED panel by panel -----------------------
+    // Every rank keeps only its OWN block-column panels of the system (`this->M` = Mo: full height, the own 128-tiles side by side
+    // in ascending global order, `this->ld` = 128 * number of own tiles) -- 1/P of the matrix instead of all of it.  A factored
+    // panel reaches the other ranks through `comm` and lives there only in a bounded receive window; everything that needs the
+    // factor consumes it panel by panel, in the order the panels become available:
+    //   forward  (k = 0 .. npan-1, fused with the factorisation):  right-hand-side rows  R[:, k] <- R[:, k] L_kk^-T,
+    //            R[:, >k] -= R[:, k] L_>k,k';   inverse columns  X[k, :] <- L_kk^-1 X[k, :],  X[>k, :] -= L_>k,k X[k, :]
+    //   backward (k = npan-1 .. 0, the owners publish their panels a second time):  R[:, k] -= R[:, >k] L_>k,k,
+    //            R[:, k] <- R[:, k] L_kk^-1;   X[k, :] -= L_>k,k' X[>k, :],  X[k, :] <- L_kk^-T X[k, :]
+    // -- the same operations, in the same order per entry, as potrf_distributed + solve_rows + inverse_columns on a replicated
+    // factor (the panel is the first split of their recursions).  A panel is addressed through a VIRTUAL base: L(r, c) =
+    // ref.base[r * ref.ld + c] for global r >= c0 and c inside the panel, wherever it lives (own storage or the receive window).
+    struct PanelRef { double *base; int64_t ld; };
+    // Comm concept:  publish_panel(p)            owner: panel p is final in Mo -> make it available to the other ranks
+    //                PanelRef get_panel(k, c0, cols, root, own_ref)   panel k is readable through the returned reference
+    //                done_panel(k)               everything that reads panel k has been enqueued
+    //                phase_boundary()            between the forward and the backward phase (stage timing)
+    template <class Comm>
+    void factor_solve_invert_streamed(Comm &comm, int rank, int nranks, int pw, const int32_t *own_cols, int n_own,
+                                      const int32_t *own_cols_host, double *R, int64_t ldr, int r_tiles, double *X, int64_t ldx, int ntc,
+                                      const int32_t *ktab, bool backward) {
+        const int nb = nblocks();
+        const int npan = (nb + pw - 1) / pw;
+        const int64_t pwc = (int64_t)pw * kTile;
+        auto p0 = [&](int p) { return (int64_t)p * pwc; };
+        auto pbl = [&](int p) { return std::min(pw, nb - p * pw); };
+        auto own_ref = [&](int p) {      // own panel p: local panel p / nranks starts at local column (p / nranks) * pwc
+            return PanelRef{M + (int64_t)(p / nranks) * pwc - p0(p), ld};
+        };
+        auto view = [&](const PanelRef &r) { return DenseSchedule<BE>{be, r.base, r.ld, np, Dinv}; };
+        auto factor_panel = [&](int p) {
+            DenseSchedule<BE> v = view(own_ref(p));
+            const int64_t c0 = p0(p);
+            const int wb = pbl(p);
+            v.potrf(c0, wb);
+            const int below = nb - (p * pw + wb);
+            if (below > 0) v.trsm_rlt(v.M + (c0 + (int64_t)wb * kTile) * v.ld, v.ld, below, c0, wb);
+        };
+        auto substitute_forward = [&](int k, const PanelRef &L) {
+            DenseSchedule<BE> v = view(L);
+            const int64_t c0 = p0(k);
+            const int wb = pbl(k), below = nb - (k * pw + wb);
+            const int64_t c1 = c0 + (int64_t)wb * kTile;
+            if (R) {
+                v.trsm_rlt(R, ldr, r_tiles, c0, wb);
+                if (below > 0) {
+                    GemmDesc g;
+                    g.al = 0; g.bl = 0; g.mt = r_tiles; g.nt = below; g.K = (int64_t)wb * kTile; g.alpha = -1.0; g.beta = 1.0;
+                    g.A = R + c0; g.lda = ldr; g.B = L.base + c1 * L.ld + c0; g.ldb = L.ld; g.C = R + c1; g.ldc = ldr;
+                    be.gemm(g);
+                }
+            }
+            if (X && ntc > 0) {
+                v.trsm_lln(X, ldx, ntc, ktab, c0, wb);
+                if (below > 0) {
+                    GemmDesc g;
+                    g.al = 0; g.bl = 1; g.mt = below; g.nt = ntc; g.K = (int64_t)wb * kTile; g.alpha = -1.0; g.beta = 1.0;
+                    g.A = L.base + c1 * L.ld + c0; g.lda = L.ld; g.B = X + c0 * ldx; g.ldb = ldx; g.C = X + c1 * ldx; g.ldc = ldx;
+                    g.kmode = K_COL_BEG; g.ktab = ktab; g.koff = c0;
+                    be.gemm(g);
+                }
+            }
+        };
+        auto substitute_backward = [&](int k, const PanelRef &L) {
+            DenseSchedule<BE> v = view(L);
+            const int64_t c0 = p0(k);
+            const int wb = pbl(k), below = nb - (k * pw + wb);
+            const int64_t c1 = c0 + (int64_t)wb * kTile;
+            if (R) {
+                if (below > 0) {
+                    GemmDesc g;
+                    g.al = 0; g.bl = 1; g.mt = r_tiles; g.nt = wb; g.K = (int64_t)below * kTile; g.alpha = -1.0; g.beta = 1.0;
+                    g.A = R + c1; g.lda = ldr; g.B = L.base + c1 * L.ld + c0; g.ldb = L.ld; g.C = R + c0; g.ldc = ldr;
+                    be.gemm(g);
+                }
+                v.trsm_rln(R, ldr, r_tiles, c0, wb);
+            }
+            if (X && ntc > 0) {
+                if (below > 0) {
+                    GemmDesc g;
+                    g.al = 1; g.bl = 1; g.mt = wb; g.nt = ntc; g.K = (int64_t)below * kTile; g.alpha = -1.0; g.beta = 1.0;
+                    g.A = L.base + c1 * L.ld + c0; g.lda = L.ld; g.B = X + c1 * ldx; g.ldb = ldx; g.C = X + c0 * ldx; g.ldc = ldx;
+                    g.kmode = K_ROW_MASK; g.ktab = ktab; g.roff = c0;
+                    be.gemm(g);
+                }
+                v.trsm_llt(X, ldx, ntc, ktab, c0, wb);
+            }
+        };
+        // ---- factorisation with look-ahead, forward substitution on the fly -------------------------------------------------------
+        if (rank == 0) {
+            factor_panel(0);
+            comm.publish_panel(0);
+        }
+        for (int k = 0; k < npan; k++) {
+            const int64_t c0 = p0(k);
+            const int root = k % nranks;
+            const PanelRef L = comm.get_panel(k, c0, (int64_t)pbl(k) * kTile, root, own_ref(k));
+            if (k + 1 < npan && (k + 1) % nranks == rank) {      // look-ahead: the next panel first
+                const PanelRef own = own_ref(k + 1);
+                const int64_t cj = p0(k + 1);
+                GemmDesc g;
+                g.al = 0; g.bl = 0; g.mt = nb - (k + 1) * pw; g.nt = pbl(k + 1); g.K = (int64_t)pbl(k) * kTile; g.alpha = -1.0; g.beta = 1.0;
+                g.A = L.base + cj * L.ld + c0; g.lda = L.ld;
+                g.B = g.A; g.ldb = L.ld;
+                g.C = own.base + cj * own.ld + cj; g.ldc = own.ld;
+                be.gemm(g);
+                factor_panel(k + 1);
+                comm.publish_panel(k + 1);
+            }
+            {   // one trapezoid launch: every own tile right of panel k+1, all rows on or below its diagonal (C compact)
+                const int64_t first = p0(k + 2);
+                int skip = 0;
+                while (skip < n_own && own_cols_host[skip] < first) skip++;
+                if (skip < n_own) {
+                    GemmDesc g;
+                    g.al = 0; g.bl = 0; g.mt = nb; g.nt = n_own - skip; g.K = (int64_t)pbl(k) * kTile; g.alpha = -1.0; g.beta = 1.0;
+                    g.A = L.base + c0; g.lda = L.ld;
+                    g.B = g.A; g.ldb = L.ld;
+                    g.C = M + (int64_t)skip * kTile; g.ldc = ld;
+                    g.coltab = own_cols + skip; g.ncoltab = n_own - skip; g.c_local = 1;
+                    be.gemm(g);
+                }
+            }
+            substitute_forward(k, L);
+            comm.done_panel(k);
+        }
+        comm.phase_boundary();
+        if (!backward) return;
+        // ---- backward substitution: the owners publish their panels once more, last panel first -----------------------------------
+        for (int k = npan - 1; k >= 0; k--) {
+            const int root = k % nranks;
+            if (root == rank) comm.publish_panel(k);
+            const PanelRef L = comm.get_panel(k, p0(k), (int64_t)pbl(k) * kTile, root, own_ref(k));
+            substitute_backward(k, L);
+            comm.done_panel(k);
+        }
+    }
 };
 
 }  // namespace jaicov

@@ -8,6 +8,7 @@
 //   * nothing for the inverse: with the factor replicated every GPU inverts its own column tiles.
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cstring>
 #include <stdexcept>
 
@@ -152,6 +153,59 @@ void PanelComm::bcast_panel(int k, int64_t row0, int64_t rows, int64_t col0, int
         JCHECK(cudaEventRecord(ctx->ev_unpacked[b], compute));
     }
     used[b] = true;
+}
+
+// ---- owner-only storage: panels are consumed in the staging slots -------------------------------------------------------------------
+void StreamPanelComm::ensure_stage(size_t elems) {
+    if (ctx->stage_elems >= elems) { used[0] = used[1] = false; return; }
+    for (int b = 0; b < 2; b++) {
+        if (ctx->stage[b]) cudaFree(ctx->stage[b]);
+        JCHECK(cudaMalloc(&ctx->stage[b], elems * sizeof(double)));
+    }
+    ctx->stage_elems = elems;
+    used[0] = used[1] = false;
+}
+
+// owner: panel p of Mo is final -> pack rows >= c0 (and the panel's Dinv blocks) into slot p & 1
+void StreamPanelComm::publish_panel(int p) {
+    const int b = p & 1;
+    const int64_t c0 = (int64_t)p * pw * kBlk;
+    const int64_t cols = std::min<int64_t>((int64_t)pw * kBlk, np - c0), rows = np - c0;
+    const int64_t lcol = (int64_t)(p / ctx->world) * pw * kBlk;        // first local column of own panel p
+    if (used[b]) JCHECK(cudaStreamWaitEvent(compute, ctx->ev_bcast[b], 0));   // the previous transfer through this slot is done
+    launch_copy2d(ctx->stage[b], cols, Mo + c0 * ldo + lcol, ldo, rows, cols, compute);
+    launch_copy2d(ctx->stage[b] + rows * cols, kBlk, Dinv + c0 * kBlk, kBlk, cols, kBlk, compute);
+    JCHECK(cudaEventRecord(ctx->ev_ready[b], compute));
+}
+
+StreamPanelComm::Ref StreamPanelComm::get_panel_impl(int k, int64_t c0, int64_t cols, int root) {
+    const int b = k & 1;
+    const int64_t rows = np - c0;
+    const size_t count = (size_t)rows * cols + (size_t)cols * kBlk;
+    if (ctx->rank == root) {
+        JCHECK(cudaStreamWaitEvent(ctx->net, ctx->ev_ready[b], 0));
+        nccl_check(g_nccl.Broadcast(ctx->stage[b], ctx->stage[b], count, kNcclFloat64, root, ctx->comm, ctx->net), "ncclBroadcast");
+        JCHECK(cudaEventRecord(ctx->ev_bcast[b], ctx->net));
+    } else {
+        if (used[b]) JCHECK(cudaStreamWaitEvent(ctx->net, ctx->ev_unpacked[b], 0));   // the slot's previous panel has been consumed
+        nccl_check(g_nccl.Broadcast(ctx->stage[b], ctx->stage[b], count, kNcclFloat64, root, ctx->comm, ctx->net), "ncclBroadcast");
+        JCHECK(cudaEventRecord(ctx->ev_bcast[b], ctx->net));
+        JCHECK(cudaStreamWaitEvent(compute, ctx->ev_bcast[b], 0));
+        launch_copy2d(Dinv + c0 * kBlk, kBlk, ctx->stage[b] + rows * cols, kBlk, cols, kBlk, compute);
+    }
+    used[b] = true;
+    root_of[b] = root;
+    // virtual base: L(r, c) = base[r * ld + c] for global r >= c0, c in [c0, c0 + cols)
+    return Ref{ctx->stage[b] - c0 * cols - c0, cols};
+}
+
+void StreamPanelComm::done_panel(int k) {
+    const int b = k & 1;
+    if (root_of[b] != ctx->rank) JCHECK(cudaEventRecord(ctx->ev_unpacked[b], compute));
+}
+
+void StreamPanelComm::phase_boundary() {
+    if (ev_phase) JCHECK(cudaEventRecord(ev_phase, compute));
 }
 
 }  // namespace jaicov

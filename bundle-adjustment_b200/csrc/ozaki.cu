@@ -627,8 +627,8 @@ bool launch_gemm_ozaki(const GemmDesc &g, cudaStream_t s) {
     OzScratch &g_oz = g_oz_dev[dev_];
     static const int64_t min_tiles = [] { const char *e = getenv("JAICOV_OZAKI_MIN_TILES"); return e ? (int64_t)atoll(e) : (int64_t)148; }();
     // column-table launches: only the trapezoid update of the distributed Cholesky (both operands the same panel, C addressed by
-    // global tiles); the structured route's compact column tables keep the FP64 kernel
-    const bool trapezoid = g.coltab && !g.c_local && g.A == g.B && g.lda == g.ldb && g.al == g.bl && g.kmode == K_FULL;
+    // global tiles, or by compact own tiles with owner-only storage); the structured route's column tables keep the FP64 kernel
+    const bool trapezoid = g.coltab && !g.coltab_full && g.A == g.B && g.lda == g.ldb && g.al == g.bl && g.kmode == K_FULL;
     if ((g.coltab && !trapezoid) || g.kmode > K_ROW_MASK) return false;
     const int64_t tiles = g.coltab ? (int64_t)g.mt * g.ncoltab : (g.tri_out ? (int64_t)g.mt * (g.mt + 1) / 2 : (int64_t)g.mt * g.nt);
     // short contractions do not pay for the digit pre-pass (six small launches and 8 + S bytes per operand element)

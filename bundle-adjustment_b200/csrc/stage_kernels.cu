@@ -10,20 +10,23 @@ __device__ __forceinline__ bool col_active_s(int32_t c) { return c >= 0 && c != 
 __device__ __forceinline__ int64_t lower_idx_s(int64_t a, int64_t b, int64_t ld) { return a >= b ? a * ld + b : b * ld + a; }
 
 // V = diag(N)^-1/2 (1 where diag <= EPS), BA:824-828; padding rows get 1
-__global__ void k_precond_diag(const double *__restrict__ M, int64_t ld, int u, int64_t np, double *__restrict__ V) {
+// (owner-only storage: a rank sees only its own diagonal entries; the others get 0 here and the ranks' vectors are summed --
+//  api.cu all-reduces V right after this launch)
+__global__ void k_precond_diag(SysView M, int u, int64_t np, double *__restrict__ V) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= np) return;
-    double v = 1.0;
-    if (e < u) {
-        const double x = M[e * ld + e];
+    const double *q = sys_at(M, e, e);
+    double v = q ? 1.0 : 0.0;
+    if (e < u && q) {
+        const double x = *q;
         v = x > kEps ? 1.0 / sqrt(x) : 1.0;
     }
     V[e] = v;
 }
 
-void launch_precond_diag(const double *M, int64_t ld, int u, int64_t np, double *V, cudaStream_t s) {
+void launch_precond_diag(const SysView &M, int u, int64_t np, double *V, cudaStream_t s) {
     g_launch_count++;
-    k_precond_diag<<<(unsigned)((np + 255) / 256), 256, 0, s>>>(M, ld, u, np, V);
+    k_precond_diag<<<(unsigned)((np + 255) / 256), 256, 0, s>>>(M, u, np, V);
 }
 
 // Datum rows (addDatumConditionRows, BA:493-635): Bt[a][e], a = condition, e = internal unknown index; Bt must be
@@ -127,6 +130,35 @@ void launch_scale_system(double *M, int64_t ld, int u, const double *V, const do
     if (row0 >= np) return;
     g_launch_count++;
     k_scale_system<<<(unsigned)(np - row0), 256, 0, s>>>(M, ld, u, V, Bt, d, np, row0);
+}
+
+// the same on owner-only storage: row r of the own tiles (own_cols[lt] = first global column of local tile lt), columns <= r
+__global__ void __launch_bounds__(256) k_scale_system_own(double *__restrict__ Mo, int64_t ldo, const int32_t *__restrict__ own_cols, int n_own,
+                                                          int u, const double *__restrict__ V, const double *__restrict__ Bt, int d, int64_t np) {
+    const int64_t r = blockIdx.x;
+    double *row = Mo + r * ldo;
+    const double vr = r < u ? V[r] : 0.0;
+    double br[kMaxDatum];
+#pragma unroll
+    for (int a = 0; a < kMaxDatum; a++) br[a] = (a < d && r < u) ? Bt[a * np + r] * vr : 0.0;
+    for (int64_t lc = threadIdx.x; lc < (int64_t)n_own * 128; lc += blockDim.x) {
+        const int64_t c = own_cols[lc >> 7] + (lc & 127);
+        if (c > r) continue;
+        if (r >= u) { row[lc] = (c == r) ? 1.0 : 0.0; continue; }
+        const double vc = V[c];
+        double x = (vr * row[lc]) * vc;
+#pragma unroll
+        for (int a = 0; a < kMaxDatum; a++)
+            if (a < d) x += br[a] * (Bt[a * np + c] * vc);
+        row[lc] = x;
+    }
+}
+
+void launch_scale_system_own(double *Mo, int64_t ldo, const int32_t *own_cols, int n_own, int u, const double *V, const double *Bt, int d,
+                             int64_t np, cudaStream_t s) {
+    if (n_own == 0) return;
+    g_launch_count++;
+    k_scale_system_own<<<(unsigned)np, 256, 0, s>>>(Mo, ldo, own_cols, n_own, u, V, Bt, d, np);
 }
 
 // right-hand-side block (rows): Rt[0] = V n, Rt[1+a] = B[a] V, everything else zero (Rt is kRhsRows x np, zeroed by caller)
@@ -367,12 +399,14 @@ void launch_get_block(const double *lower, int64_t ld, const double *border, int
 }
 
 // Levenberg-Marquardt: N_cc += lambda * N_cc for every unknown column (BA:814-822)
-__global__ void k_damp_diag(double *__restrict__ M, int64_t ld, int u, double lambda) {
+__global__ void k_damp_diag(SysView M, int u, double lambda) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < u) { const double v = M[e * ld + e]; M[e * ld + e] = v + lambda * v; }
+    if (e >= u) return;
+    double *q = sys_at(M, e, e);
+    if (q) { const double v = *q; *q = v + lambda * v; }
 }
-void launch_damp_diag(double *M, int64_t ld, int u, double lambda, cudaStream_t s) {
-    if (u) { g_launch_count++; k_damp_diag<<<(u + 255) / 256, 256, 0, s>>>(M, ld, u, lambda); }
+void launch_damp_diag(const SysView &M, int u, double lambda, cudaStream_t s) {
+    if (u) { g_launch_count++; k_damp_diag<<<(u + 255) / 256, 256, 0, s>>>(M, u, lambda); }
 }
 __global__ void k_scale_vector(double *__restrict__ x, int64_t n, double alpha) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -496,20 +530,19 @@ __global__ void k_group_w(int r, const double *const *__restrict__ tptr, const d
 
 // diagonal weights: N[c,c] += sigma0^2/var, n[c] += P w
 __global__ void k_group_stack_diag(int r, const int32_t *__restrict__ col, const double *__restrict__ var, double sigma2,
-                                   const double *__restrict__ w, int d, int64_t ld, double *__restrict__ M,
-                                   double *__restrict__ rhs) {
+                                   const double *__restrict__ w, int d, SysView M, double *__restrict__ rhs) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= r || !col_active_s(col[i])) return;
     const double P = sigma2 / var[i];
     const int64_t e = col[i] - d;
-    M[e * ld + e] += P;
+    sys_add(M, e, e, P);
     rhs[e] += P * w[i];
 }
 
 // full weights (Pw = symmetric r x r, row-major, leading dimension ldp): n[c_i] += sum_j P_ij w_j; N[c_i,c_j] += P_ij
 __global__ void __launch_bounds__(256) k_group_stack_full(int r, const int32_t *__restrict__ col, const double *__restrict__ Pw,
-                                                          int64_t ldp, const double *__restrict__ w, int d, int64_t ld,
-                                                          double *__restrict__ M, double *__restrict__ rhs) {
+                                                          int64_t ldp, const double *__restrict__ w, int d, SysView M,
+                                                          double *__restrict__ rhs) {
     __shared__ double red[8];
     const int i = blockIdx.x;
     if (!col_active_s(col[i])) return;
@@ -519,7 +552,7 @@ __global__ void __launch_bounds__(256) k_group_stack_full(int r, const int32_t *
     for (int j = threadIdx.x; j < r; j += blockDim.x) {
         const double p = Pi[j];
         s += p * w[j];
-        if (j <= i && col_active_s(col[j])) M[lower_idx_s(ei, col[j] - d, ld)] += p;
+        if (j <= i && col_active_s(col[j])) sys_add(M, ei, col[j] - d, p);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -567,10 +600,10 @@ void launch_group_w(int r, const double *const *tptr, const double *obs, double 
     if (r) { g_launch_count++; k_group_w<<<(r + 255) / 256, 256, 0, s>>>(r, tptr, obs, w); }
 }
 void launch_group_stack(int r, const int32_t *col, const double *var, const double *Pw, int64_t ldp, double sigma2, const double *w,
-                        int d, int64_t ld, double *M, double *rhs, cudaStream_t s) {
+                        int d, const SysView &M, double *rhs, cudaStream_t s) {
     if (!r) return;
-    if (Pw == nullptr) { g_launch_count++; k_group_stack_diag<<<(r + 255) / 256, 256, 0, s>>>(r, col, var, sigma2, w, d, ld, M, rhs); }
-    else { g_launch_count++; k_group_stack_full<<<r, 256, 0, s>>>(r, col, Pw, ldp, w, d, ld, M, rhs); }
+    if (Pw == nullptr) { g_launch_count++; k_group_stack_diag<<<(r + 255) / 256, 256, 0, s>>>(r, col, var, sigma2, w, d, M, rhs); }
+    else { g_launch_count++; k_group_stack_full<<<r, 256, 0, s>>>(r, col, Pw, ldp, w, d, M, rhs); }
 }
 void launch_group_omega(int r, const int32_t *col, const double *var, const double *Pw, int64_t ldp, double sigma2, const double *w,
                         const double *dxref, double *out, cudaStream_t s) {

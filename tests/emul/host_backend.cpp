@@ -147,7 +147,7 @@ struct HostBackend {
         gemm_calls++;
         // what csrc/ozaki.cu: launch_gemm_ozaki takes: everything without a column table, and the trapezoid update of the
         // distributed Cholesky (column table, both operands the same panel of the matrix, C addressed by global tiles)
-        const bool trapezoid = g.coltab && !g.c_local && (const void *)g.A == (const void *)g.B && g.lda == g.ldb && g.al == g.bl && g.kmode == K_FULL;
+        const bool trapezoid = g.coltab && !g.coltab_full && (const void *)g.A == (const void *)g.B && g.lda == g.ldb && g.al == g.bl && g.kmode == K_FULL;
         if (ozaki > 0 && (!g.coltab || trapezoid)) {
             const long tiles = g.tri_out ? (long)g.mt * (g.mt + 1) / 2 : (long)g.mt * g.nt;
             if (tiles >= ozaki_min_tiles) { ozaki_calls++; gemm_ozaki(g); return; }
@@ -186,7 +186,7 @@ struct HostBackend {
                 flops += 2.0 * T * T * (double)(kend - kbeg);
                 for (int i = 0; i < T; i++)
                     for (int j = 0; j < T; j++) {
-                        double *c = g.C + ((int64_t)it * T + i) * g.ldc + (int64_t)jt * T + j;
+                        double *c = g.C + ((int64_t)it * T + i) * g.ldc + ((g.coltab && g.c_local) ? (int64_t)jl : (int64_t)jt) * T + j;
                         *c = g.beta == 0.0 ? g.alpha * acc[(size_t)i * T + j] : g.alpha * acc[(size_t)i * T + j] + g.beta * *c;
                     }
             }
@@ -257,7 +257,109 @@ struct HostComm {
     void panel_ready(int) {}
 };
 
+// Comm of DenseSchedule::factor_solve_invert_streamed for virtual ranks in threads: the root's panel (own storage, compact columns)
+// is copied into the receiver's two-slot window; nobody but the owner ever holds a panel for longer than it is in the window
+struct HostStreamComm {
+    int rank, nranks, pw;
+    std::vector<double *> *Mos;          // own-panel storage of every rank
+    std::vector<int64_t> *ldos;
+    std::vector<double *> *Dinvs;
+    std::vector<double> window[2];
+    int64_t np;
+    Barrier *bar;
+    long received = 0;
+    void publish_panel(int) {}
+    DenseSchedule<HostBackend>::PanelRef get_panel(int k, int64_t c0, int64_t cols, int root, DenseSchedule<HostBackend>::PanelRef own) {
+        bar->wait();                     // the root has finished writing the panel
+        DenseSchedule<HostBackend>::PanelRef ref = own;
+        if (rank != root) {
+            std::vector<double> &w = window[k & 1];
+            w.assign((size_t)(np - c0) * cols, std::numeric_limits<double>::quiet_NaN());
+            const double *src = (*Mos)[root] + (int64_t)(k / nranks) * pw * kTile;      // root's local panel, row 0
+            const int64_t lds = (*ldos)[root];
+            for (int64_t r = c0; r < np; r++) std::memcpy(w.data() + (r - c0) * cols, src + r * lds, sizeof(double) * cols);
+            std::memcpy((*Dinvs)[rank] + c0 * kTile, (*Dinvs)[root] + c0 * kTile, sizeof(double) * cols * kTile);
+            ref.base = w.data() - c0 * cols - c0;
+            ref.ld = cols;
+            received++;
+        }
+        bar->wait();                     // everybody has its copy: the root may go on (it never overwrites a published panel)
+        return ref;
+    }
+    void done_panel(int) {}
+    void phase_boundary() {}
+};
+
 extern "C" {
+
+// Owner-only storage (DenseSchedule::factor_solve_invert_streamed) with `nranks` virtual ranks: every rank gets ONLY its own
+// block-column panels of M (everything else it holds is NaN), the right-hand sides R (nrhs rows, replicated) and the identity
+// columns of its inverse tiles (tile c belongs to rank c % nranks).  Out: R <- solutions, Q (np x np, lower part) <- the inverse
+// gathered from the ranks' tiles, maxdiff <- largest difference between the ranks' copies of the solutions.
+int emul_streamed(int64_t np, const double *M, int nranks, int pw, int nrhs, double *R, double *Q, double *maxdiff, int ozaki, long *received) {
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    const int nb = (int)(np / kTile);
+    const int64_t pwc = (int64_t)pw * kTile;
+    std::vector<std::vector<double>> Mo(nranks), Dr(nranks, std::vector<double>((size_t)np * kTile, nan)), Rr(nranks), Xr(nranks);
+    std::vector<std::vector<int32_t>> own(nranks), ktab(nranks);
+    std::vector<double *> Mos, Ds;
+    std::vector<int64_t> ldos;
+    for (int r = 0; r < nranks; r++) {
+        for (int c = 0; c < nb; c++) {
+            if ((c / pw) % nranks == r) own[r].push_back(c * kTile);
+            if (c % nranks == r) ktab[r].push_back(c * kTile);
+        }
+        const int64_t ldo = std::max<int64_t>(1, (int64_t)own[r].size()) * kTile;
+        Mo[r].assign((size_t)np * ldo, nan);
+        for (size_t lt = 0; lt < own[r].size(); lt++)
+            for (int64_t row = own[r][lt]; row < np; row++)        // lower part of the own tiles only
+                for (int j = 0; j < kTile; j++)
+                    if (own[r][lt] + j <= row) Mo[r][(size_t)row * ldo + lt * kTile + j] = M[row * np + own[r][lt] + j];
+        Rr[r].assign((size_t)kTile * np, 0.0);
+        for (int i = 0; i < nrhs; i++) std::memcpy(Rr[r].data() + (size_t)i * np, R + (size_t)i * np, sizeof(double) * np);
+        const int64_t ldx = std::max<int64_t>(1, (int64_t)ktab[r].size()) * kTile;
+        Xr[r].assign((size_t)np * ldx, 0.0);
+        for (size_t jl = 0; jl < ktab[r].size(); jl++)
+            for (int i = 0; i < kTile; i++) Xr[r][(size_t)(ktab[r][jl] + i) * ldx + jl * kTile + i] = 1.0;
+        Mos.push_back(Mo[r].data()); Ds.push_back(Dr[r].data()); ldos.push_back(ldo);
+    }
+    Barrier bar(nranks);
+    std::vector<int> infos(nranks, 0);
+    std::vector<long> recv(nranks, 0);
+    std::vector<std::thread> th;
+    for (int r = 0; r < nranks; r++)
+        th.emplace_back([&, r] {
+            HostBackend be;
+            be.ozaki = ozaki;
+            HostStreamComm comm{r, nranks, pw, &Mos, &ldos, &Ds, {}, np, &bar};
+            DenseSchedule<HostBackend> ds{be, Mos[r], ldos[r], np, Ds[r]};
+            ds.factor_solve_invert_streamed(comm, r, nranks, pw, own[r].data(), (int)own[r].size(), own[r].data(), Rr[r].data(), np, 1,
+                                            Xr[r].data(), (int64_t)std::max<size_t>(1, ktab[r].size()) * kTile, (int)ktab[r].size(), ktab[r].data(), true);
+            infos[r] = be.info;
+            recv[r] = comm.received;
+        });
+    for (auto &t : th) t.join();
+    (void)pwc;
+    double md = 0.0;
+    for (int r = 1; r < nranks; r++)
+        for (int i = 0; i < nrhs; i++)
+            for (int64_t e = 0; e < np; e++) md = std::max(md, std::fabs(Rr[r][(size_t)i * np + e] - Rr[0][(size_t)i * np + e]));
+    *maxdiff = md;
+    for (int i = 0; i < nrhs; i++) std::memcpy(R + (size_t)i * np, Rr[0].data() + (size_t)i * np, sizeof(double) * np);
+    for (int r = 0; r < nranks; r++) {
+        const int64_t ldx = std::max<int64_t>(1, (int64_t)ktab[r].size()) * kTile;
+        for (size_t jl = 0; jl < ktab[r].size(); jl++)
+            for (int64_t row = ktab[r][jl]; row < np; row++)
+                for (int i = 0; i < kTile; i++) {
+                    const int64_t col = ktab[r][jl] + i;
+                    if (row >= col) Q[row * np + col] = Xr[r][(size_t)row * ldx + jl * kTile + i];
+                }
+    }
+    if (received) *received = recv[nranks > 1 ? 1 : 0];
+    int info = 0;
+    for (int v : infos) if (v) info = v;
+    return info;
+}
 
 // tile order of the lower-triangular GEMM launches (dense_driver.hpp: tri_tile_decode), for the bijection test
 void emul_rect_tile_decode(int64_t l, int mt, int nt, int band, int *it, int *jt) { jaicov::rect_tile_decode(l, mt, nt, band, *it, *jt); }

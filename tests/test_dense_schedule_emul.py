@@ -107,3 +107,35 @@ def test_rect_tile_order_is_a_bijection(emul, mt, nt, band):
         assert 0 <= it.value < mt and 0 <= jt.value < nt
         seen.add((it.value, jt.value))
     assert len(seen) == mt * nt
+
+
+@pytest.mark.parametrize('nb,nranks,pw,ozaki', [(1, 1, 1, 0), (3, 2, 1, 0), (5, 2, 2, 0), (7, 3, 2, 0), (6, 4, 1, 0), (9, 2, 3, 0), (4, 8, 1, 0), (3, 2, 1, 8)])
+def test_streamed_owner_only_schedule_with_virtual_ranks(emul, nb, nranks, pw, ozaki):
+    """Owner-only storage (DenseSchedule::factor_solve_invert_streamed): every virtual rank holds ONLY its own block-column panels
+    (the rest of its matrix is NaN), receives the others through a two-slot window, and still produces the solutions of the
+    right-hand sides (identical on every rank) and its column tiles of the inverse -- against numpy."""
+    n = 128 * nb
+    rng = np.random.default_rng(100 + nb + 7 * nranks + pw)
+    G = rng.standard_normal((n, n))
+    S = G @ G.T + 0.1 * n * np.eye(n)
+    dsc = 1 / np.sqrt(np.diag(S))
+    S = S * dsc[:, None] * dsc[None, :]
+    R = rng.standard_normal((3, n))
+    M = np.ascontiguousarray(S)
+    Rio = np.ascontiguousarray(R.copy())
+    Q = np.full((n, n), np.nan)
+    md, recv = ctypes.c_double(0), ctypes.c_long(0)
+    emul.emul_streamed.argtypes = [ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                   ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.POINTER(ctypes.c_long)]
+    info = emul.emul_streamed(n, M.ctypes.data, nranks, pw, 3, Rio.ctypes.data, Q.ctypes.data, ctypes.byref(md), ozaki, ctypes.byref(recv))   # ozaki: every launch through the int8-digit emulation
+    assert info == 0
+    assert md.value == 0.0                                   # every rank computes the same solutions, bit for bit
+    Sinv = np.linalg.inv(S)
+    np.testing.assert_allclose(Rio, np.linalg.solve(S, R.T).T, rtol=0, atol=1e-10)
+    il = np.tril_indices(n)
+    assert np.isfinite(Q[il]).all()
+    sc = np.sqrt(np.diag(Sinv))
+    assert np.max(np.abs(Q[il] - Sinv[il]) / (sc[il[0]] * sc[il[1]])) < 1e-11
+    npan = (nb + pw - 1) // pw
+    if nranks > 1:
+        assert recv.value <= 2 * npan                        # a non-owner sees every panel at most twice (forward, backward)
