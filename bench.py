@@ -492,7 +492,9 @@ def main():
         # algorithmic bytes per image point: 44 B read (obj_idx 4, xy 16, weights 24); the by-image sweep also writes the
         # unique 6 x 3 EO x point block (144 B).  With N > 1 every rank sweeps its image shard: per-GPU figures of rank 0
         if ms_ > 0:
-            gbs = m_pts / world * bytes_ / (ms_ * 1e-3) / 1e9
+            # (dense route on several GPUs = owner-only storage: every rank sweeps ALL image points and keeps the entries it owns)
+            sharded = world > 1 and (structured_used or os.environ.get('JAICOV_DIST_STORAGE') == 'replica')
+            gbs = (m_pts / world if sharded else m_pts) * bytes_ / (ms_ * 1e-3) / 1e9
             sweep_gbs[name_] = {'ms': ms_, 'algorithmic_GBps': gbs, 'frac_of_hbm_peak': gbs / hbm}
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak * world, 'unit': 'TFLOP/s', 'frac': achieved / (peak * world),
                 'traffic': TRAFFIC.get(args.config if not structured_used else -args.config), 'peak_per_gpu': peak,

@@ -28,7 +28,7 @@ EXPORTS = [
     'jaicov_get_stats', 'jaicov_get_values', 'jaicov_get_dx', 'jaicov_get_qxx_packed', 'jaicov_get_qxx_block',
     'jaicov_get_qxx_diag', 'jaicov_get_qxx_submatrix', 'jaicov_eval_residual_jacobian', 'jaicov_get_normal_equations', 'jaicov_omega',
     'jaicov_spd_solve_invert', 'jaicov_propagate_eo_transform', 'jaicov_dlt_batch', 'jaicov_gemm_tiles',
-    'jaicov_normal_product', 'jaicov_get_preconditioner', 'jaicov_get_sweep_times', 'jaicov_set_image_dispersion', 'jaicov_set_gemm_digits',
+    'jaicov_normal_product', 'jaicov_get_preconditioner', 'jaicov_get_sweep_times', 'jaicov_set_image_dispersion', 'jaicov_set_gemm_digits', 'jaicov_get_device_bytes',
 ]
 
 
@@ -103,6 +103,7 @@ def load():
     L.jaicov_normal_product.argtypes = [vp, i32, vp, vp, vp, ctypes.POINTER(dbl)]
     L.jaicov_get_preconditioner.argtypes = [vp, vp]
     L.jaicov_set_gemm_digits.argtypes = [i32]
+    L.jaicov_get_device_bytes.argtypes = [vp, vp]
     L.jaicov_set_image_dispersion.argtypes = [vp, i32, i64, vp]
     L.jaicov_get_sweep_times.argtypes = [vp, ctypes.POINTER(dbl), ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
     L.jaicov_spd_solve_invert.argtypes = [i32, i64, vp, i32, vp, i32, ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
@@ -363,6 +364,12 @@ class Session:
         a, b, c = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_double(0)
         self.check(self.L.jaicov_get_sweep_times(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         return a.value, b.value, c.value
+
+    def device_bytes(self):
+        """Bytes of (system matrix, second square, inverse column tiles, panel staging) on the device (jaicov_get_device_bytes)."""
+        out = np.zeros(4, np.int64)
+        self.check(self.L.jaicov_get_device_bytes(self.h, _p(out)))
+        return [int(v) for v in out]
 
     def preconditioner(self):
         out = np.empty(self.n)

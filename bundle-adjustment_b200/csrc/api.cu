@@ -2309,6 +2309,25 @@ int32_t jaicov_get_sweep_times(jaicov_handle *h, double *ms_by_image, double *ms
     API_GUARD_END(h)
 }
 
+int32_t jaicov_get_device_bytes(jaicov_handle *h, int64_t out[4]) {
+    if (!h || !out) return JAICOV_ILLEGAL_ARGUMENT;
+    if (is_group(h)) {      // the largest device's figures
+        out[0] = out[1] = out[2] = out[3] = 0;
+        for (jaicov_handle *sh : h->sub) {
+            int64_t t[4];
+            const int32_t rc = jaicov_get_device_bytes(sh, t);
+            if (rc != JAICOV_OK) return rc;
+            for (int i = 0; i < 4; i++) out[i] = std::max(out[i], t[i]);
+        }
+        return JAICOV_OK;
+    }
+    out[0] = (int64_t)(h->M.n * sizeof(double));
+    out[1] = (int64_t)(h->W.n * sizeof(double));
+    out[2] = (int64_t)(h->Xl.n * sizeof(double));
+    out[3] = h->dist_on ? (int64_t)(2 * h->dist.stage_elems * sizeof(double)) : 0;
+    return JAICOV_OK;
+}
+
 int32_t jaicov_get_preconditioner(jaicov_handle *h, double *v) {
     if (is_group(h)) return jaicov_get_preconditioner(h->sub[0], v);
     if (!h || !v || !h->V.p) return JAICOV_ILLEGAL_ARGUMENT;

@@ -113,6 +113,8 @@ struct GemmDesc {
     const int32_t *ktab = nullptr;   // K_COL_BEG / K_ROW_MASK: per column tile, first global row of interest
     int64_t koff = 0;                // K_COL_BEG: global row of k = 0
     int64_t roff = 0;                // K_ROW_MASK: global row of output tile row 0
+    int64_t row_min = 0;             // column-table launches: no wanted tile lies above this global row (host-known): operand rows above it
+                                     // are never read -- with owner-only storage they do not exist (virtual panel base)
 };
 
 template <class BE>
@@ -354,7 +356,7 @@ struct DenseSchedule {
                     g.A = M + c0; g.lda = ld;
                     g.B = M + c0; g.ldb = ld;
                     g.C = M; g.ldc = ld;
-                    g.coltab = own_cols + skip; g.ncoltab = n_own - skip;
+                    g.coltab = own_cols + skip; g.ncoltab = n_own - skip; g.row_min = own_cols_host[skip];
                     be.gemm(g);
                 }
             } else {
@@ -483,7 +485,7 @@ struct DenseSchedule {
                     g.A = L.base + c0; g.lda = L.ld;
                     g.B = g.A; g.ldb = L.ld;
                     g.C = M + (int64_t)skip * kTile; g.ldc = ld;
-                    g.coltab = own_cols + skip; g.ncoltab = n_own - skip; g.c_local = 1;
+                    g.coltab = own_cols + skip; g.ncoltab = n_own - skip; g.c_local = 1; g.row_min = own_cols_host[skip];
                     be.gemm(g);
                 }
             }

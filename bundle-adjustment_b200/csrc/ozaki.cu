@@ -44,6 +44,7 @@ struct OzSplitArgs {
     int64_t ld;
     int layout;          // 0: X(row, k) at X[row * ld + k];  1: at X[k * ld + row]
     int64_t rows, K;     // multiples of 128
+    int64_t row_min;     // rows below this one are not wanted by any tile of the launch: neither read nor split
     int range;           // OzRange
     int S;
     int8_t *Q;           // [S][rows][K]
@@ -72,7 +73,7 @@ __device__ __forceinline__ bool oz_map(const OzSplitArgs &a, int64_t &row, int64
         row = (int64_t)blockIdx.y * 128 + threadIdx.x;
         k0 = (int64_t)blockIdx.x * 16;
     }
-    return row < a.rows && k0 < a.K;
+    return row >= a.row_min && row < a.rows && k0 < a.K;
 }
 
 __device__ __forceinline__ void oz_load16(const OzSplitArgs &a, int64_t row, int64_t k0, double (&x)[16]) {
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(128) k_oz_colmax(OzSplitArgs a) {
     int64_t k;
     if (a.layout == 0) {          // thread <-> one k, a slab of 256 rows (every row access is one coalesced 1 KB read of the block)
         k = (int64_t)blockIdx.x * 128 + threadIdx.x;
-        const int64_t r0 = (int64_t)blockIdx.y * 256, r1 = min(a.rows, r0 + 256);
+        const int64_t r0 = max(a.row_min, (int64_t)blockIdx.y * 256), r1 = min(a.rows, (int64_t)blockIdx.y * 256 + 256);
         if (k < a.K)
             for (int64_t r = r0; r < r1; r++)
                 if (oz_valid(a, r, k)) m = fmax(m, fabs(a.X[r * a.ld + k]));
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(128) k_oz_colmax(OzSplitArgs a) {
     } else {                      // warp <-> one k, lanes stride over a slab of 4096 rows (contiguous in memory)
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         k = (int64_t)blockIdx.x * 4 + warp;
-        const int64_t r0 = (int64_t)blockIdx.y * 4096, r1 = min(a.rows, r0 + 4096);
+        const int64_t r0 = max(a.row_min, (int64_t)blockIdx.y * 4096), r1 = min(a.rows, (int64_t)blockIdx.y * 4096 + 4096);
         if (k < a.K)
             for (int64_t r = r0 + lane; r < r1; r += 32)
                 if (oz_valid(a, r, k)) m = fmax(m, fabs(a.X[k * a.ld + r]));
@@ -651,8 +652,9 @@ bool launch_gemm_ozaki(const GemmDesc &g, cudaStream_t s) {
     static const bool kscale = [] { const char *e = getenv("JAICOV_OZAKI_KSCALE"); return !(e && atoi(e) == 0); }();
     const bool balance = kscale && !shared;
     if (balance && !g_oz.ensure_k((size_t)g.K)) return false;
-    OzSplitArgs sa{g.A, g.lda, g.al, Mr, g.K, ra, digits, g_oz.q[0], g_oz.e[0], g_oz.amax[0], nullptr, 1, g_oz.cmax[0]};
-    OzSplitArgs sb{g.B, g.ldb, g.bl, Nr, g.K, rb, digits, g_oz.q[1], g_oz.e[1], g_oz.amax[1], nullptr, -1, g_oz.cmax[1]};
+    const int64_t rmin = g.coltab ? (g.row_min / 128) * 128 : 0;
+    OzSplitArgs sa{g.A, g.lda, g.al, Mr, g.K, rmin, ra, digits, g_oz.q[0], g_oz.e[0], g_oz.amax[0], nullptr, 1, g_oz.cmax[0]};
+    OzSplitArgs sb{g.B, g.ldb, g.bl, Nr, g.K, rmin, rb, digits, g_oz.q[1], g_oz.e[1], g_oz.amax[1], nullptr, -1, g_oz.cmax[1]};
     if (balance) {
         launch_colmax(sa, s);
         launch_colmax(sb, s);

@@ -313,6 +313,11 @@ int32_t jaicov_normal_product(jaicov_handle *h, int32_t nvec, const double *x, d
  * Gram + the unique EO x point blocks), the by-point sweep (first camera group) and the Omega sweep (0 unless it was a final pass).
  * These are the kernels whose algorithmic traffic is 44 B per image point; bench.py turns them into GB/s. */
 int32_t jaicov_get_sweep_times(jaicov_handle *h, double *ms_by_image, double *ms_by_point, double *ms_omega);
+/* Device memory of the big buffers of this handle, in bytes: out[0] the system matrix N -> L (whole lower-triangular square on one GPU;
+ * ONLY THE RANK'S OWN block-column panels -- about 1/P of it -- on the distributed dense route), out[1] the second square of the
+ * single-GPU inverse (0 otherwise), out[2] the rank's column tiles of Qxx (distributed), out[3] the two panel staging slots.
+ * Single-process multi-GPU handle: the largest device's figures. */
+int32_t jaicov_get_device_bytes(jaicov_handle *h, int64_t out[4]);
 /* Jacobi preconditioner V of the last pass (:824-828), length u+d (1 on the border) */
 int32_t jaicov_get_preconditioner(jaicov_handle *h, double *v);
 

@@ -70,9 +70,10 @@ struct HostBackend {
         auto getA = [&](int64_t m, int64_t k) { return g.al == 0 ? g.A[m * g.lda + k] : g.A[k * g.lda + m]; };
         auto getB = [&](int64_t n, int64_t k) { return g.bl == 0 ? g.B[n * g.ldb + k] : g.B[k * g.ldb + n]; };
         auto loA = [&](int64_t m) { return g.kmode == K_MAX_IJ ? (m / T) * T : (int64_t)0; };
-        auto hiA = [&](int64_t m) { return g.kmode == K_A_LOWER ? std::min<int64_t>(K, (m / T + 1) * T) : K; };
+        const int64_t rmin = g.coltab ? (g.row_min / T) * T : 0;      // rows above it belong to no wanted tile: never read (csrc/ozaki.cu: row_min)
+        auto hiA = [&](int64_t m) { return m < rmin ? (int64_t)0 : (g.kmode == K_A_LOWER ? std::min<int64_t>(K, (m / T + 1) * T) : K); };
         auto loB = [&](int64_t n) { return (g.kmode == K_MAX_IJ || g.kmode == K_B_LOWER) ? (n / T) * T : (int64_t)0; };
-        auto hiB = [&](int64_t) { return K; };
+        auto hiB = [&](int64_t n) { return n < rmin ? (int64_t)0 : K; };
         // Contraction-index balancing: op(A)[., k] * 2^f_k and op(B)[., k] * 2^-f_k leave every product unchanged (exact powers of
         // two) but even out the magnitudes inside the operand rows, which is what the per-row digit grid resolves.  f_k = floor of
         // half the exponent gap of the two column maxima.  Needed where the operands span many orders of magnitude inside a row

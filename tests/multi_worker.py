@@ -71,6 +71,8 @@ def main():
         t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
         dist.all_reduce(t)
         return t.cpu().numpy()
+    mem = torch.tensor(s.device_bytes(), dtype=torch.float64, device='cuda')
+    dist.all_reduce(mem, op=dist.ReduceOp.MAX)          # the largest rank's buffers
     chk = verify.check_pass(s, columns=verify.sample_columns(n, n - u, world=world, panel=128 * int(os.environ.get('JAICOV_PANEL_TILES', '16'))),
                             reduce_sum=reduce_sum, omega=st.omega, values_updated=True)
     if rank == 0:
@@ -94,8 +96,8 @@ def main():
         print(json.dumps({'scene': which, 'world': world, 'solver_used': st.solver_used, 'rc': rc, 'rc_oracle': so, 'iterations': st.iterations,
                           'iterations_oracle': len(o.history), 'sigma2_rel_err': abs(st.sigma2aposteriori - s2o) / s2o,
                           'qxx_scaled_err': errq, 'param_rel_err': errx, 'qxx_local_vs_block_maxabs': float(le[0]), 'ms_last_pass': st.ms_total,
-                          'ms_factor': st.ms_factor, 'ms_inverse': st.ms_inverse, 'n': n, 'panel_tiles': int(os.environ.get('JAICOV_PANEL_TILES', '16')),
-                          'verify': {k: chk[k] for k in ('datum_residual', 'cofactor_residual', 'omega_rel_diff')}}), flush=True)
+                          'ms_factor': st.ms_factor, 'ms_inverse': st.ms_inverse, 'n': n, 'd': n - u, 'panel_tiles': int(os.environ.get('JAICOV_PANEL_TILES', '16')),
+                          'device_bytes_max': [int(v) for v in mem.cpu().tolist()], 'verify': {k: chk[k] for k in ('datum_residual', 'cofactor_residual', 'omega_rel_diff')}}), flush=True)
     s.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -46,6 +46,16 @@ def test_two_gpu_adjustment_matches_oracle(built, which, solver, panel_tiles):
     assert r['param_rel_err'] <= 1e-10
     assert r['qxx_local_vs_block_maxabs'] == 0.0      # both getters read the same device values
     assert r['panel_tiles'] == panel_tiles and r['world'] == world
+    if r['solver_used'] == 1 and os.environ.get('JAICOV_DIST_STORAGE') != 'replica':
+        # owner-only storage of the dense route: the largest rank holds its own block-column panels of the system matrix, not all of
+        # it -- ceil(panels / world) panels of 128 * panel_tiles columns (the whole square was np^2 * 8 bytes per rank in round 1)
+        npad = (r['n'] - r.get('d', 0) + 127) // 128 * 128
+        cnt = [0] * world
+        for c in range(npad // 128):
+            cnt[(c // panel_tiles) % world] += 1               # tile c belongs to panel c // panel_tiles, owned cyclically
+        assert r['device_bytes_max'][0] == npad * max(max(cnt), 1) * 128 * 8, (r['device_bytes_max'], npad, cnt)
+        assert r['device_bytes_max'][0] <= npad * npad * 8 * (1.0 / world + panel_tiles * 128.0 / npad)
+        assert r['device_bytes_max'][1] == 0
     v = r['verify']                                    # the identities bench.py checks at config 5 (bundle_adjustment_b200/verify.py)
     assert max(v['datum_residual'], v['cofactor_residual'], v['omega_rel_diff']) <= 1e-8, v
 
