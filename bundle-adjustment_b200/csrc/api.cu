@@ -31,6 +31,9 @@ int ozaki_set_digits(int digits);
 void launch_potrf_diag(double *A, int64_t ld, double *dinv, int row0, int *info, cudaStream_t s);
 void launch_copy2d(double *dst, int64_t ldd, const double *src, int64_t lds, int64_t rows, int64_t cols, cudaStream_t s);
 void launch_solve_rows8(const double *L, int64_t ld, const double *dinv, double *R, double *Y, int64_t np, cudaStream_t s);
+void launch_solve_fwd_block(const double *L, int64_t ld, const double *dinv, double *R, double *Y, int64_t np, int j, cudaStream_t s);
+void launch_solve_bwd_block_col(const double *L, int64_t ld, const double *dinv, double *R, const double *Y, int64_t np, int j, double *partial,
+                                cudaStream_t s);
 // stage_kernels.cu
 void launch_precond_diag(const SysView &M, int u, int64_t np, double *V, cudaStream_t s);
 void launch_datum_rows(const double *xyz, const int32_t *pt_col, const int32_t *datum_pts, int nDatum, int free_mask, int d,
@@ -100,6 +103,13 @@ void launch_build_csc(const int32_t *obj, int64_t obs0, int64_t n, int nPt, int3
 struct CudaBackend {
     cudaStream_t stream;
     int *info;
+    double *solve_partial = nullptr;   // scratch of the column-oriented skinny backward solve (owner-only storage)
+    void solve_fwd_block(const double *L, int64_t ld, const double *dinv, double *R, double *Y, int64_t np, int j) {
+        launch_solve_fwd_block(L, ld, dinv, R, Y, np, j, stream);
+    }
+    void solve_bwd_block_col(const double *L, int64_t ld, const double *dinv, double *R, const double *Y, int64_t np, int j) {
+        launch_solve_bwd_block_col(L, ld, dinv, R, Y, np, j, solve_partial, stream);
+    }
     void gemm(const GemmDesc &g) { launch_gemm(g, stream); }
     void potrf_diag(double *a, int64_t ld, double *dinv, int row0) { launch_potrf_diag(a, ld, dinv, row0, info, stream); }
     void copy2d(double *dst, int64_t ldd, const double *src, int64_t lds, int64_t rows, int64_t cols) {
@@ -280,6 +290,7 @@ struct jaicov_handle {
     int64_t ldo = 0;                     // leading dimension of M with owner-only storage (128 * own tiles)
     SysView sys;                         // where the entries of N live on this rank
     DevBuf<int32_t> d_tile_lcol;
+    DevBuf<double> solve_partial;        // owner-only storage: partial sums of the column-oriented skinny backward solve
     DevBuf<double> gather;               // single-process handle, device 0: the gathered Qxx (np x np lower) when M is owner-only
     cudaEvent_t ev_phase = nullptr;
     DevBuf<double> Xl;                   // np x (128 * ntc): this rank's column tiles of the inverse
@@ -750,6 +761,7 @@ void prepare(jaicov_handle *h) {
             h->M.alloc(np * (size_t)h->ldo);
             h->sys = SysView{h->M.p, h->ldo, h->d_tile_lcol.p};
             if (!h->ev_phase) JCHECK(cudaEventCreate(&h->ev_phase));
+            h->solve_partial.alloc(((size_t)P.np / 256 + 2) * 8 * 128);
         }
         std::vector<int32_t> kt = h->ktab;
         if (kt.empty()) kt.push_back(0);
@@ -994,9 +1006,10 @@ PassResult run_pass(jaicov_handle *h, bool final_pass, bool apply_update) {
         }
         StreamPanelComm sc{&h->dist, s, h->M.p, h->ldo, P.np, h->Dinv.p, h->panel_tiles, h->ev_phase};
         sc.ensure_stage((size_t)P.np * h->panel_tiles * kBlk + (size_t)h->panel_tiles * kBlk * kBlk);
+        be.solve_partial = h->solve_partial.p;
         DenseSchedule<CudaBackend> dso{be, h->M.p, h->ldo, P.np, h->Dinv.p};
         dso.factor_solve_invert_streamed(sc, h->dist.rank, h->dist.world, h->panel_tiles, h->d_ptab.p, (int)h->ptab.size(), h->ptab.data(),
-                                         h->Rt.p, P.np, 1, ntc > 0 ? h->Xl.p : nullptr, ldx, ntc, h->d_ktab.p, true);
+                                         h->Rt.p, h->Rt.p + 8 * np, ntc > 0 ? h->Xl.p : nullptr, ldx, ntc, h->d_ktab.p, true);
         JCHECK(cudaEventRecord(h->dist.ev_tmp, h->dist.net));
         JCHECK(cudaStreamWaitEvent(s, h->dist.ev_tmp, 0));
     } else if (multi) {

@@ -371,10 +371,10 @@ struct DenseSchedule {
     // in ascending global order, `this->ld` = 128 * number of own tiles) -- 1/P of the matrix instead of all of it.  A factored
     // panel reaches the other ranks through `comm` and lives there only in a bounded receive window; everything that needs the
     // factor consumes it panel by panel, in the order the panels become available:
-    //   forward  (k = 0 .. npan-1, fused with the factorisation):  right-hand-side rows  R[:, k] <- R[:, k] L_kk^-T,
-    //            R[:, >k] -= R[:, k] L_>k,k';   inverse columns  X[k, :] <- L_kk^-1 X[k, :],  X[>k, :] -= L_>k,k X[k, :]
-    //   backward (k = npan-1 .. 0, the owners publish their panels a second time):  R[:, k] -= R[:, >k] L_>k,k,
-    //            R[:, k] <- R[:, k] L_kk^-1;   X[k, :] -= L_>k,k' X[>k, :],  X[k, :] <- L_kk^-T X[k, :]
+    //   forward  (k = 0 .. npan-1, fused with the factorisation):  right-hand-side rows  y_k = L_kk^-1 b_k,
+    //            b_>k -= L_>k,k y_k (skinny kernels);   inverse columns  X[k, :] <- L_kk^-1 X[k, :],  X[>k, :] -= L_>k,k X[k, :]
+    //   backward (k = npan-1 .. 0, the owners publish their panels a second time):  x_k = L_kk^-T (y_k - L_>k,k' x_>k)
+    //            (column-oriented skinny kernels);   X[k, :] -= L_>k,k' X[>k, :],  X[k, :] <- L_kk^-T X[k, :]
     // -- the same operations, in the same order per entry, as potrf_distributed + solve_rows + inverse_columns on a replicated
     // factor (the panel is the first split of their recursions).  A panel is addressed through a VIRTUAL base: L(r, c) =
     // ref.base[r * ref.ld + c] for global r >= c0 and c inside the panel, wherever it lives (own storage or the receive window).
@@ -385,7 +385,7 @@ struct DenseSchedule {
     //                phase_boundary()            between the forward and the backward phase (stage timing)
     template <class Comm>
     void factor_solve_invert_streamed(Comm &comm, int rank, int nranks, int pw, const int32_t *own_cols, int n_own,
-                                      const int32_t *own_cols_host, double *R, int64_t ldr, int r_tiles, double *X, int64_t ldx, int ntc,
+                                      const int32_t *own_cols_host, double *R, double *Y, double *X, int64_t ldx, int ntc,
                                       const int32_t *ktab, bool backward) {
         const int nb = nblocks();
         const int npan = (nb + pw - 1) / pw;
@@ -409,15 +409,8 @@ struct DenseSchedule {
             const int64_t c0 = p0(k);
             const int wb = pbl(k), below = nb - (k * pw + wb);
             const int64_t c1 = c0 + (int64_t)wb * kTile;
-            if (R) {
-                v.trsm_rlt(R, ldr, r_tiles, c0, wb);
-                if (below > 0) {
-                    GemmDesc g;
-                    g.al = 0; g.bl = 0; g.mt = r_tiles; g.nt = below; g.K = (int64_t)wb * kTile; g.alpha = -1.0; g.beta = 1.0;
-                    g.A = R + c0; g.lda = ldr; g.B = L.base + c1 * L.ld + c0; g.ldb = L.ld; g.C = R + c1; g.ldc = ldr;
-                    be.gemm(g);
-                }
-            }
+            if (R)      // the <= 8 right-hand sides (rows of R, np apart; Y = scratch of the same size): one skinny launch per 128-block
+                for (int j = k * pw; j < k * pw + wb; j++) be.solve_fwd_block(L.base, L.ld, Dinv, R, Y, np, j);
             if (X && ntc > 0) {
                 v.trsm_lln(X, ldx, ntc, ktab, c0, wb);
                 if (below > 0) {
@@ -434,15 +427,8 @@ struct DenseSchedule {
             const int64_t c0 = p0(k);
             const int wb = pbl(k), below = nb - (k * pw + wb);
             const int64_t c1 = c0 + (int64_t)wb * kTile;
-            if (R) {
-                if (below > 0) {
-                    GemmDesc g;
-                    g.al = 0; g.bl = 1; g.mt = r_tiles; g.nt = wb; g.K = (int64_t)below * kTile; g.alpha = -1.0; g.beta = 1.0;
-                    g.A = R + c1; g.lda = ldr; g.B = L.base + c1 * L.ld + c0; g.ldb = L.ld; g.C = R + c0; g.ldc = ldr;
-                    be.gemm(g);
-                }
-                v.trsm_rln(R, ldr, r_tiles, c0, wb);
-            }
+            if (R)
+                for (int j = k * pw + wb - 1; j >= k * pw; j--) be.solve_bwd_block_col(L.base, L.ld, Dinv, R, Y, np, j);
             if (X && ntc > 0) {
                 if (below > 0) {
                     GemmDesc g;
@@ -495,10 +481,12 @@ struct DenseSchedule {
         comm.phase_boundary();
         if (!backward) return;
         // ---- backward substitution: the owners publish their panels once more, last panel first -----------------------------------
+        // (a panel is published one step ahead, before the work of the current step is enqueued: its broadcast overlaps that work)
+        if ((npan - 1) % nranks == rank) comm.publish_panel(npan - 1);
         for (int k = npan - 1; k >= 0; k--) {
             const int root = k % nranks;
-            if (root == rank) comm.publish_panel(k);
             const PanelRef L = comm.get_panel(k, p0(k), (int64_t)pbl(k) * kTile, root, own_ref(k));
+            if (k > 0 && (k - 1) % nranks == rank) comm.publish_panel(k - 1);
             substitute_backward(k, L);
             comm.done_panel(k);
         }

@@ -584,4 +584,80 @@ void launch_solve_rows8(const double *L, int64_t ld, const double *dinv, double 
     }
 }
 
+// ---- the same skinny solves, one 128-block at a time and COLUMN-oriented on the way back (owner-only storage) ------------------
+// With the factor streamed panel by panel only the block COLUMN j of L is at hand when block j is processed (a virtual panel base:
+// L(r, c) = L[r * ld + c] for c inside the panel).  Forward is right-looking already (k_solve_fwd_step reads column block j).  The
+// backward step of launch_solve_rows8 reads the block ROW j of L, which spans every earlier panel; here it is left-looking instead:
+//   x_j = Dinv_j' (y_j - sum_{r below block j} L[r, J]' x[r])
+// -- partial sums per 256-row chunk (one CTA each), then one CTA adds them in chunk order (bitwise reproducible: every rank solves
+// the same right-hand sides and must take the same decisions from them) and applies Dinv_j'.
+__global__ void __launch_bounds__(256) k_solve_bwd_col_partial(const double *__restrict__ L, int64_t ld, const double *__restrict__ R,
+                                                               int64_t np, int j, double *__restrict__ partial) {
+    __shared__ double sx[SR * SPITCH];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = lane >> 2, tig = lane & 3;
+    const int64_t J = (int64_t)j * 128;
+    const int64_t row0 = J + 128 + (int64_t)blockIdx.x * SCHUNK;
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    for (int slab = 0; slab < SCHUNK / 128; slab++) {
+        const int64_t r0 = row0 + (int64_t)slab * 128;
+        if (r0 >= np) break;                                   // block-uniform
+        __syncthreads();
+        for (int i = tid; i < SR * 128; i += 256) sx[(i >> 7) * SPITCH + (i & 127)] = R[(int64_t)(i >> 7) * np + r0 + (i & 127)];
+        __syncthreads();
+        // A[m = column of block j][k = row r0 + k] = L[r0 + k][J + m]; warp w: columns 16 w .. 16 w + 15
+        skinny_mma<2, true>(L + r0 * ld + J + 16 * warp, ld, sx, acc, lane);
+    }
+    double *out = partial + (size_t)blockIdx.x * SR * 128;
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++) {
+        out[(2 * tig) * 128 + 16 * warp + 8 * mt + grp] = acc[mt][0];
+        out[(2 * tig + 1) * 128 + 16 * warp + 8 * mt + grp] = acc[mt][1];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_solve_bwd_col_finish(const double *__restrict__ dinv, double *__restrict__ R, const double *__restrict__ Y,
+                                                              int64_t np, int j, const double *__restrict__ partial, int nchunk) {
+    __shared__ double sy[SR * SPITCH];
+    __shared__ double sxx[SR * SPITCH];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = lane >> 2, tig = lane & 3;
+    const int64_t J = (int64_t)j * 128;
+    for (int i = tid; i < SR * 128; i += 256) {
+        double s = 0.0;
+        for (int c = 0; c < nchunk; c++) s += partial[(size_t)c * SR * 128 + i];      // fixed order
+        sy[(i >> 7) * SPITCH + (i & 127)] = Y[(int64_t)(i >> 7) * np + J + (i & 127)] - s;
+    }
+    __syncthreads();
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    skinny_mma<2, true>(dinv + J * 128 + 16 * warp, 128, sy, acc, lane);      // x = Dinv_j' t
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++) {
+        sxx[(2 * tig) * SPITCH + 16 * warp + 8 * mt + grp] = acc[mt][0];
+        sxx[(2 * tig + 1) * SPITCH + 16 * warp + 8 * mt + grp] = acc[mt][1];
+    }
+    __syncthreads();
+    for (int i = tid; i < SR * 128; i += 256) R[(int64_t)(i >> 7) * np + J + (i & 127)] = sxx[(i >> 7) * SPITCH + (i & 127)];
+}
+
+void launch_solve_fwd_block(const double *L, int64_t ld, const double *dinv, double *R, double *Y, int64_t np, int j, cudaStream_t s) {
+    const int64_t below = np - (int64_t)(j + 1) * 128;
+    const int grid = (int)std::max<int64_t>(1, (below + SCHUNK - 1) / SCHUNK);
+    g_launch_count++;
+    k_solve_fwd_step<<<grid, 256, 0, s>>>(L, ld, dinv, R, Y, np, j);
+}
+
+// partial: scratch of at least (np / 256 + 1) * 8 * 128 doubles
+void launch_solve_bwd_block_col(const double *L, int64_t ld, const double *dinv, double *R, const double *Y, int64_t np, int j, double *partial,
+                                cudaStream_t s) {
+    const int64_t below = np - (int64_t)(j + 1) * 128;
+    const int nchunk = (int)((below + SCHUNK - 1) / SCHUNK);
+    if (nchunk > 0) {
+        g_launch_count++;
+        k_solve_bwd_col_partial<<<nchunk, 256, 0, s>>>(L, ld, R, np, j, partial);
+    }
+    g_launch_count++;
+    k_solve_bwd_col_finish<<<1, 256, 0, s>>>(dinv, R, Y, np, j, partial, nchunk);
+}
+
 }  // namespace jaicov

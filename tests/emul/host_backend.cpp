@@ -220,6 +220,43 @@ struct HostBackend {
         }
     }
 
+    // skinny solves of 8 right-hand sides stored as rows R[8][np] (csrc/dense_kernels.cu: k_solve_fwd_step, k_solve_bwd_col_*)
+    void solve_fwd_block(const double *L, int64_t ld, const double *dinv, double *R, double *Y, int64_t np, int j) {
+        const int T = kTile;
+        const int64_t J = (int64_t)j * T;
+        for (int q = 0; q < 8; q++) {
+            double y[kTile];
+            for (int i = 0; i < T; i++) {
+                double s = 0.0;
+                for (int k = 0; k < T; k++) s += dinv[(J + i) * T + k] * R[(int64_t)q * np + J + k];
+                y[i] = s;
+            }
+            for (int i = 0; i < T; i++) Y[(int64_t)q * np + J + i] = y[i];
+            for (int64_t r = J + T; r < np; r++) {
+                double s = 0.0;
+                for (int k = 0; k < T; k++) s += L[r * ld + J + k] * y[k];
+                R[(int64_t)q * np + r] -= s;
+            }
+        }
+    }
+    void solve_bwd_block_col(const double *L, int64_t ld, const double *dinv, double *R, const double *Y, int64_t np, int j) {
+        const int T = kTile;
+        const int64_t J = (int64_t)j * T;
+        for (int q = 0; q < 8; q++) {
+            double t[kTile];
+            for (int c = 0; c < T; c++) {
+                double s = 0.0;
+                for (int64_t r = J + T; r < np; r++) s += L[r * ld + J + c] * R[(int64_t)q * np + r];
+                t[c] = Y[(int64_t)q * np + J + c] - s;
+            }
+            for (int i = 0; i < T; i++) {
+                double s = 0.0;
+                for (int k = 0; k < T; k++) s += dinv[(J + k) * T + i] * t[k];      // Dinv' t
+                R[(int64_t)q * np + J + i] = s;
+            }
+        }
+    }
+
     void copy2d(double *dst, int64_t ldd, const double *src, int64_t lds, int64_t rows, int64_t cols) {
         for (int64_t r = 0; r < rows; r++) std::memcpy(dst + r * ldd, src + r * lds, sizeof(double) * cols);
     }
@@ -316,7 +353,7 @@ int emul_streamed(int64_t np, const double *M, int nranks, int pw, int nrhs, dou
             for (int64_t row = own[r][lt]; row < np; row++)        // lower part of the own tiles only
                 for (int j = 0; j < kTile; j++)
                     if (own[r][lt] + j <= row) Mo[r][(size_t)row * ldo + lt * kTile + j] = M[row * np + own[r][lt] + j];
-        Rr[r].assign((size_t)kTile * np, 0.0);
+        Rr[r].assign((size_t)16 * np, 0.0);       // rows 0..7 right-hand sides, rows 8..15 the scratch Y
         for (int i = 0; i < nrhs; i++) std::memcpy(Rr[r].data() + (size_t)i * np, R + (size_t)i * np, sizeof(double) * np);
         const int64_t ldx = std::max<int64_t>(1, (int64_t)ktab[r].size()) * kTile;
         Xr[r].assign((size_t)np * ldx, 0.0);
@@ -334,7 +371,7 @@ int emul_streamed(int64_t np, const double *M, int nranks, int pw, int nrhs, dou
             be.ozaki = ozaki;
             HostStreamComm comm{r, nranks, pw, &Mos, &ldos, &Ds, {}, np, &bar};
             DenseSchedule<HostBackend> ds{be, Mos[r], ldos[r], np, Ds[r]};
-            ds.factor_solve_invert_streamed(comm, r, nranks, pw, own[r].data(), (int)own[r].size(), own[r].data(), Rr[r].data(), np, 1,
+            ds.factor_solve_invert_streamed(comm, r, nranks, pw, own[r].data(), (int)own[r].size(), own[r].data(), Rr[r].data(), Rr[r].data() + 8 * np,
                                             Xr[r].data(), (int64_t)std::max<size_t>(1, ktab[r].size()) * kTile, (int)ktab[r].size(), ktab[r].data(), true);
             infos[r] = be.info;
             recv[r] = comm.received;
