@@ -145,9 +145,11 @@ int64_t jaicov_launch_count(void);
 int32_t jaicov_set_gemm_digits(int32_t digits);
 
 /* ---- multi-GPU ------------------------------------------------------------------------------------------------------
- * Two ways to put one adjustment on several GPUs of one box; both run the same device code (image-sharded assembly + NCCL
- * all-reduce of the shared normal-equation pieces, block-column-cyclic Cholesky with panel broadcasts over NVLink, every GPU
- * inverts its own column tiles of Qxx):
+ * Two ways to put one adjustment on several GPUs of one box; both run the same device code.  Dense route: every GPU stores only
+ * its own block-column panels of the system (about 1/P of it, jaicov_get_device_bytes), evaluates all observations and keeps what it
+ * owns, and the block-column-cyclic Cholesky streams every factored panel over NVLink (NCCL broadcast) to where the trailing
+ * updates, the solves and the GPU's own column tiles of Qxx consume it (JAICOV_DIST_STORAGE=replica: round 1's whole copy per
+ * GPU).  Structured route: image-sharded assembly + all-reduce of the shared pieces, per-GPU column tiles of the Qxx products:
  *
  * (1) jaicov_options.n_devices = k: a SINGLE handle in a SINGLE process -- the form a Java host uses.  Every call is the
  *     same as on one GPU; internally each GPU gets its own host thread and its own communicator of one ncclCommInitAll clique
