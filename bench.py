@@ -500,9 +500,9 @@ def main():
                 'traffic': TRAFFIC.get(args.config if not structured_used else -args.config), 'peak_per_gpu': peak,
                 'frac_factor_inverse_stages': achieved_stage / (peak * world),
                 'observation_sweeps': sweep_gbs,
-                'observation_sweeps_note': 'FP64-issue bound, not HBM bound: ~350 FP64 instructions per image point at 13 camera parameters against '
+                'observation_sweeps_note': 'FP64-issue bound, not HBM bound: ~340 FP64 instructions per image point at 13 camera parameters against '
                                            '44 B (arithmetic intensity 2x the machine balance of FP64 pipe / HBM): a fully busy FP64 pipe caps them at '
-                                           '~36 % of the HBM peak (DESIGN.md section 5, ncu in profiles/r02_ncu_sweeps_*)',
+                                           '~36 % of the HBM peak; ncu: FP64 pipe 52 % active in the Omega sweep (DESIGN.md section 5, profiles/r02_ncu_sweeps_final_summary.txt)',
                 'traffic_note': 'k_gemm is launched thousands of times per pass with different tile counts, so there is no single per-launch '
                                 'figure; ncu --set full of its largest launches (profiles/r01_ncu_full_k_gemm_shape65_summary.txt): LAUUM at '
                                 'config 4 moves 21.4 GB of DRAM traffic for 1.43e12 flop (tensor pipe 94.2 % active), the structured '

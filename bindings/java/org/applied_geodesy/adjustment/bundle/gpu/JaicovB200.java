@@ -29,6 +29,8 @@ public final class JaicovB200 {
 
 	/** sizeof(jaicov_options), sizeof(jaicov_stats) */
 	public static final long OPTIONS_BYTES = 48, STATS_BYTES = 112;
+	/** byte offset of jaicov_options.n_devices: 1 = one GPU; k > 1 = this ONE handle (and the one JVM thread calling it) drives k GPUs */
+	public static final long OPTIONS_N_DEVICES = 28;
 
 	private static final Linker LINKER = Linker.nativeLinker();
 	private static final SymbolLookup LIB = SymbolLookup.libraryLookup("libjaicov_b200.so", Arena.global());
@@ -54,6 +56,10 @@ public final class JaicovB200 {
 	public static final MethodHandle GET_VALUES = h("jaicov_get_values", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
 	public static final MethodHandle GET_QXX_PACKED = h("jaicov_get_qxx_packed", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
 	public static final MethodHandle GET_QXX_BLOCK = h("jaicov_get_qxx_block", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS, JAVA_LONG));
+	/** optional self-check after estimateModel(): y = K x matrix-free from the observations (K Qxx e_c = e_c on a few columns) */
+	public static final MethodHandle NORMAL_PRODUCT = h("jaicov_normal_product", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+	/** extension: fully populated dispersion of the image coordinates of one image (not in the reference) */
+	public static final MethodHandle SET_IMAGE_DISPERSION = h("jaicov_set_image_dispersion", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_LONG, ADDRESS));
 	public static final MethodHandle GET_QXX_SUBMATRIX = h("jaicov_get_qxx_submatrix", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, JAVA_DOUBLE, ADDRESS));
 
 	/** progress callback: void (*)(void *user, int32_t state, double old_value, double new_value) -> PropertyChangeSupport.firePropertyChange */

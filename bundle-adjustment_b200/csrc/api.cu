@@ -251,6 +251,7 @@ struct jaicov_handle {
         d_campos_col, d_cam_of_img, d_eo_col, d_obj_idx, d_img_of_obs, d_pt_col, d_bar_a, d_bar_b, d_img_work_ptr, d_datum_pts;
     DevBuf<int64_t> d_pt_ptr, d_pt_obs_ptr, d_pt_obs;
     DevBuf<WorkItem> d_work;
+    DevBuf<int32_t> d_cam_std;
     DevBuf<double> d_img_partial, d_cam_partial, d_pt_partial, d_omega_partial, d_coef_r0pow, d_rw, d_dxp;
     std::vector<int32_t> kbase_host;     // start of every camera's raw parameters in the camera-parameter list
     std::vector<PtGroup> pt_groups;      // camera groups of the by-point sweep (one group unless the cameras have > 68 raw parameters in total)
@@ -547,6 +548,24 @@ void prepare(jaicov_handle *h) {
         c = g.cam1;
     }
     if (h->pt_groups.empty()) h->pt_groups.push_back(PtGroup{0, 0, 0, 1});
+    // canonical coefficient lists ([Cx Cy]? [Bx By B1..]? [A1..] [D1..], orders consecutive from 1 -- what the reference's readers
+    // build, AICONReportFileReader.java:308): the sweeps then evaluate them straight-line (model.cuh, STD) instead of interpreting
+    std::vector<int32_t> cam_std((size_t)std::max(P.nCam, 1) * 5, 0);
+    bool all_std = P.nCam > 0 && getenv("JAICOV_SWEEP_GENERIC") == nullptr;
+    for (int c = 0; c < P.nCam; c++) {
+        int k = h->coef_ptr[c];
+        const int k1 = h->coef_ptr[c + 1];
+        int32_t *t = &cam_std[5 * (size_t)c];
+        auto type_at = [&](int i) { return i < k1 ? h->coef_type[i] : -1; };
+        if (type_at(k) == JAICOV_PT_AFFINITY_CX && type_at(k + 1) == JAICOV_PT_AFFINITY_CY) { t[0] = 1; k += 2; }
+        if (type_at(k) == JAICOV_PT_TANGENTIAL_BX && type_at(k + 1) == JAICOV_PT_TANGENTIAL_BY) {
+            t[1] = 1; k += 2;
+            while (type_at(k) == JAICOV_PT_TANGENTIAL_B && h->coef_order[k] == t[2] + 1) { t[2]++; k++; }
+        }
+        while (type_at(k) == JAICOV_PT_RADIAL_A && h->coef_order[k] == t[3] + 1) { t[3]++; k++; }
+        while (type_at(k) == JAICOV_PT_DISTANCE_D && h->coef_order[k] == t[4] + 1) { t[4]++; k++; }
+        if (k != k1) { t[0] = -1; all_std = false; }
+    }
     // r0^(2 order) of every coefficient (the constant of the radial / distance polynomials; repeated multiplication like the kernels)
     std::vector<double> r0pow(std::max(P.nCoef, 1), 0.0);
     for (int c = 0; c < P.nCam; c++)
@@ -649,6 +668,8 @@ void prepare(jaicov_handle *h) {
     h->d_io_val.upload(h->io_val); h->d_io_col.upload(h->io_col); h->d_r0.upload(h->r0);
     h->d_coef_ptr.upload(h->coef_ptr); h->d_coef_type.upload(h->coef_type); h->d_coef_order.upload(h->coef_order);
     h->d_coef_val.upload(h->coef_val); h->d_coef_col.upload(h->coef_col); h->d_coef_r0pow.upload(r0pow);
+    h->d_cam_std.upload(cam_std);
+    P.cam_std = h->d_cam_std.p;
     h->d_zern_m.upload(zm); h->d_zern_ptr.upload(zptr); h->d_zern_p.upload(zp); h->d_zern_c.upload(zc);
     h->d_cam_kbase.upload(kbase); h->d_campos_col.upload(campos);
     h->kbase_host = kbase;
@@ -668,6 +689,7 @@ void prepare(jaicov_handle *h) {
     P.nBar = (int)h->bar_a.size();
     P.bar_a = h->d_bar_a.p; P.bar_b = h->d_bar_b.p; P.bar_len = h->d_bar_len.p; P.bar_var = h->d_bar_var.p;
     AssemblyScratch &S = h->S;
+    S.std_eval = all_std ? 1 : 0;
     S.nWork = (int)work.size();
     S.work = h->d_work.p; S.img_work_ptr = h->d_img_work_ptr.p;
     const int NCi = 8 * S.ntImg, NCp = 8 * S.ntPt;

@@ -88,7 +88,7 @@ void launch_eval_k1(const DevProblem &P, int ns_max, double *a, double *w, doubl
 // tile columns: 0..5 EO (X0,Y0,Z0,omega,phi,kappa), 6..8 IO (x0,y0,c), 9..9+ncoef-1 coefficients, 9+ncoef = w.
 constexpr int kImgWarps = 4;
 
-template <int NT, int MINB>
+template <int NT, int MINB, bool STD>
 __global__ void __launch_bounds__(kImgWarps * 32, MINB) k_by_image(DevProblem P, const WorkItem *__restrict__ work,
                                                                    double *__restrict__ partial, SysView M) {
     constexpr int LDT = 68;  // tile is stored column-major [NC][68]: == 4 (mod 16) -> conflict-free fragment reads,
@@ -129,11 +129,11 @@ __global__ void __launch_bounds__(kImgWarps * 32, MINB) k_by_image(DevProblem P,
             const double r00 = P.rw[3 * j], r01 = P.rw[3 * j + 1], r11 = P.rw[3 * j + 2];
             const double2 xyo = reinterpret_cast<const double2 *>(P.xy)[j];
             BaseRows r;
-            eval_observation(q, cv, P.xyz[3 * (int64_t)pt], P.xyz[3 * (int64_t)pt + 1], P.xyz[3 * (int64_t)pt + 2],
-                             xyo.x, xyo.y, r, [&](int k, double v0, double v1) {
-                                 ROW0(9 + k) = r00 * v0 + r01 * v1;
-                                 ROW1(9 + k) = r11 * v1;
-                             });
+            eval_observation_t<true, STD>(q, cv, P.xyz[3 * (int64_t)pt], P.xyz[3 * (int64_t)pt + 1], P.xyz[3 * (int64_t)pt + 2],
+                                          xyo.x, xyo.y, r, [&](int k, double v0, double v1) {
+                                              ROW0(9 + k) = r00 * v0 + r01 * v1;
+                                              ROW1(9 + k) = r11 * v1;
+                                          });
             // weighted base rows
             double tpx[3], tpy[3], tex[6], tey[6];
 #pragma unroll
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256) k_camera_scatter(DevProblem P, AssemblySc
 // one sweep -- is the common case.  A group of a single camera stages it in shared memory.
 constexpr int kPtWarps = 4;
 
-template <int NT, bool ONE_CAM, int MINB>
+template <int NT, bool ONE_CAM, int MINB, bool STD>
 __global__ void __launch_bounds__(kPtWarps * 32, MINB) k_by_point(DevProblem P, int cam0, int cam1, int kraw, double *__restrict__ pt_partial) {
     constexpr int LDT = 68;
     constexpr int NC = 8 * NT;
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(kPtWarps * 32, MINB) k_by_point(DevProblem P, 
                 const double r00 = P.rw[3 * j], r01 = P.rw[3 * j + 1], r11 = P.rw[3 * j + 2];
                 const double2 xyo = reinterpret_cast<const double2 *>(P.xy)[j];
                 BaseRows r;
-                eval_observation_t<false>(q, cv, X, Y, Z, xyo.x, xyo.y, r, [&](int k, double v0, double v1) {
+                eval_observation_t<false, STD>(q, cv, X, Y, Z, xyo.x, xyo.y, r, [&](int k, double v0, double v1) {
                     ROW0(kb + 3 + k) = r00 * v0 + r01 * v1;
                     ROW1(kb + 3 + k) = r11 * v1;
                 });
@@ -400,28 +400,34 @@ static int sweep_min_blocks() {
 template <int NT>
 static void run_by_image(const DevProblem &P, const AssemblyScratch &S, const SysView &M, cudaStream_t s) {
     const size_t smem = (size_t)kImgWarps * 8 * NT * 68 * sizeof(double);
-    static PerDeviceOnce once3, once4;
+    static PerDeviceOnce once3, once4, once4s;
     g_launch_count++;
-    if (sweep_min_blocks() >= 4 && NT <= 4) {
-        once4.run([&] { JCHECK(cudaFuncSetAttribute(k_by_image<NT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
-        k_by_image<NT, 4><<<S.nWork, kImgWarps * 32, smem, s>>>(P, S.work, S.img_partial, M);
+    if (sweep_min_blocks() >= 4 && NT <= 4 && S.std_eval) {
+        once4s.run([&] { JCHECK(cudaFuncSetAttribute(k_by_image<NT, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
+        k_by_image<NT, 4, true><<<S.nWork, kImgWarps * 32, smem, s>>>(P, S.work, S.img_partial, M);
+    } else if (sweep_min_blocks() >= 4 && NT <= 4) {
+        once4.run([&] { JCHECK(cudaFuncSetAttribute(k_by_image<NT, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
+        k_by_image<NT, 4, false><<<S.nWork, kImgWarps * 32, smem, s>>>(P, S.work, S.img_partial, M);
     } else {
-        once3.run([&] { JCHECK(cudaFuncSetAttribute(k_by_image<NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
-        k_by_image<NT, 1><<<S.nWork, kImgWarps * 32, smem, s>>>(P, S.work, S.img_partial, M);
+        once3.run([&] { JCHECK(cudaFuncSetAttribute(k_by_image<NT, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
+        k_by_image<NT, 1, false><<<S.nWork, kImgWarps * 32, smem, s>>>(P, S.work, S.img_partial, M);
     }
 }
 
 template <int NT, bool ONE_CAM>
 static void run_by_point(const DevProblem &P, const AssemblyScratch &S, const PtGroup &g, cudaStream_t s) {
     const size_t smem = (size_t)kPtWarps * 8 * NT * 68 * sizeof(double);
-    static PerDeviceOnce once3, once4;
+    static PerDeviceOnce once3, once4, once4s;
     g_launch_count++;
-    if (sweep_min_blocks() >= 4 && NT <= 4) {
-        once4.run([&] { JCHECK(cudaFuncSetAttribute(k_by_point<NT, ONE_CAM, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
-        k_by_point<NT, ONE_CAM, 4><<<(P.nPt + kPtWarps - 1) / kPtWarps, kPtWarps * 32, smem, s>>>(P, g.cam0, g.cam1, g.kraw, S.pt_partial);
+    if (sweep_min_blocks() >= 4 && NT <= 4 && ONE_CAM && S.std_eval) {
+        once4s.run([&] { JCHECK(cudaFuncSetAttribute(k_by_point<NT, ONE_CAM, 4, ONE_CAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
+        k_by_point<NT, ONE_CAM, 4, ONE_CAM><<<(P.nPt + kPtWarps - 1) / kPtWarps, kPtWarps * 32, smem, s>>>(P, g.cam0, g.cam1, g.kraw, S.pt_partial);
+    } else if (sweep_min_blocks() >= 4 && NT <= 4) {
+        once4.run([&] { JCHECK(cudaFuncSetAttribute(k_by_point<NT, ONE_CAM, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
+        k_by_point<NT, ONE_CAM, 4, false><<<(P.nPt + kPtWarps - 1) / kPtWarps, kPtWarps * 32, smem, s>>>(P, g.cam0, g.cam1, g.kraw, S.pt_partial);
     } else {
-        once3.run([&] { JCHECK(cudaFuncSetAttribute(k_by_point<NT, ONE_CAM, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
-        k_by_point<NT, ONE_CAM, 1><<<(P.nPt + kPtWarps - 1) / kPtWarps, kPtWarps * 32, smem, s>>>(P, g.cam0, g.cam1, g.kraw, S.pt_partial);
+        once3.run([&] { JCHECK(cudaFuncSetAttribute(k_by_point<NT, ONE_CAM, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
+        k_by_point<NT, ONE_CAM, 1, false><<<(P.nPt + kPtWarps - 1) / kPtWarps, kPtWarps * 32, smem, s>>>(P, g.cam0, g.cam1, g.kraw, S.pt_partial);
     }
 }
 
@@ -569,7 +575,7 @@ __global__ void __launch_bounds__(256) k_gather_point_dx(DevProblem P, const dou
     dxp[i] = col_active(c) ? dxref[c] : 0.0;
 }
 
-template <int MINB>
+template <int MINB, bool STD>
 __global__ void __launch_bounds__(kOmegaThreads, MINB) k_omega(DevProblem P, const WorkItem *__restrict__ work, const double *__restrict__ dxref,
                                                          const double *__restrict__ dxp, double *__restrict__ partial) {
     __shared__ CamSmem cs;
@@ -603,7 +609,7 @@ __global__ void __launch_bounds__(kOmegaThreads, MINB) k_omega(DevProblem P, con
         const double *xp = P.xyz + 3 * (int64_t)pt, *dp = dxp + 3 * (int64_t)pt;
         double s0 = 0.0, s1 = 0.0;  // (A dx) rows
         BaseRows r;
-        eval_observation(q, cv, xp[0], xp[1], xp[2], xyo.x, xyo.y, r, [&](int k, double v0, double v1) {
+        eval_observation_t<true, STD>(q, cv, xp[0], xp[1], xp[2], xyo.x, xyo.y, r, [&](int k, double v0, double v1) {
             const double dx = s_dxc[3 + k];
             s0 += v0 * dx;  s1 += v1 * dx;
         });
@@ -643,8 +649,9 @@ void launch_omega(const DevProblem &P, const AssemblyScratch &S, const double *d
     g_launch_count++;
     k_gather_point_dx<<<(unsigned)((3 * (int64_t)P.nPt + 255) / 256), 256, 0, s>>>(P, dxref, S.dxp);
     g_launch_count++;
-    if (sweep_min_blocks() >= 4) k_omega<4><<<S.nWork, kOmegaThreads, 0, s>>>(P, S.work, dxref, S.dxp, S.omega_partial);
-    else k_omega<1><<<S.nWork, kOmegaThreads, 0, s>>>(P, S.work, dxref, S.dxp, S.omega_partial);
+    if (sweep_min_blocks() >= 4 && S.std_eval) k_omega<4, true><<<S.nWork, kOmegaThreads, 0, s>>>(P, S.work, dxref, S.dxp, S.omega_partial);
+    else if (sweep_min_blocks() >= 4) k_omega<4, false><<<S.nWork, kOmegaThreads, 0, s>>>(P, S.work, dxref, S.dxp, S.omega_partial);
+    else k_omega<1, false><<<S.nWork, kOmegaThreads, 0, s>>>(P, S.work, dxref, S.dxp, S.omega_partial);
     g_launch_count++;
     k_omega_final<<<1, 32, 0, s>>>(S.omega_partial, S.nWork, omega_out);
 }

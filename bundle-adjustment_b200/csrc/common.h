@@ -96,6 +96,7 @@ struct DevProblem {
     int32_t *coef_ptr = nullptr;    // [nCam+1]
     int32_t *coef_type = nullptr, *coef_order = nullptr, *coef_col = nullptr;  // [nCoef]
     double *coef_val = nullptr;     // [nCoef]
+    const int32_t *cam_std = nullptr;  // [5 nCam] hasC, hasB, nB, nA, nD of a canonical coefficient list (hasC = -1: not canonical)
     double *coef_r0pow = nullptr;   // [nCoef] r0^(2 order) of the coefficient's camera (radial / distance polynomials)
     int32_t *zern_m = nullptr;      // [nCoef]
     int32_t *zern_ptr = nullptr;    // [nCoef+1]
@@ -155,6 +156,7 @@ struct AssemblyScratch {
     double *cam_partial = nullptr;  // [nImg][kc*(kc+1)] camera block + rhs of every image (kc = max raw params per camera)
     double *cam_sum = nullptr;      // [nCam][kc*(kc+1)] sum over this rank's images (all-reduced across ranks)
     int kcMax = 0;
+    int std_eval = 0;               // every camera has a canonical coefficient list: the sweeps use the straight-line evaluation
     double *pt_partial = nullptr;   // [nPt][3][8 ntPt]
     double *omega_partial = nullptr;  // [nWork + 2]
     double *dxp = nullptr;          // [3 nPt] dx of the object coordinates (0 where fixed), gathered per pass for Omega

@@ -44,6 +44,8 @@ struct CamView {
     const int32_t *order;     // [ncoef]
     const double *val;        // [ncoef]
     const double *r0pow;      // [ncoef] r0^(2 order): the constant subtracted by the radial / distance polynomials (:58,66)
+    // canonical coefficient list (STD evaluation): [Cx Cy]? [Bx By B1..BnB]? [A1..AnA] [D1..DnD], orders consecutive from 1, no Zernike
+    int hasC = 0, hasB = 0, nB = 0, nA = 0, nD = 0;
     // Zernike table (global): per coefficient (global index base k0): m, term range; per term: exponent p, coefficient c
     const int32_t *zern_m;    // indexed by local coefficient position
     const int32_t *zern_ptr;  // [ncoef+1] local positions -> term range
@@ -99,7 +101,7 @@ __host__ __device__ __forceinline__ ImgPose make_pose(const double *eo) {
 // coefficient table (it is a constant of the camera).  Results differ from the term-by-term order by rounding only (~1e-16
 // relative; the per-entry parity test against the oracle holds at 1e-11).  WITH_EO = false skips the omega / phi / kappa partials
 // (the by-point sweep does not use them).
-template <bool WITH_EO, class Sink>
+template <bool WITH_EO, bool STD, class Sink>
 __host__ __device__ __forceinline__ void eval_observation_t(const ImgPose &q, const CamView &cam, double X, double Y, double Z,
                                                             double xobs, double yobs, BaseRows &r, Sink &&sink) {
     constexpr int NB = WITH_EO ? 7 : 4;
@@ -152,17 +154,19 @@ __host__ __device__ __forceinline__ void eval_observation_t(const ImgPose &q, co
         else if (e != pe) { pv = ipow(r2, e); pe = e; }
         return pv;
     };
-    int k = 0;
-    const int nc = cam.ncoef;
-    while (k < nc) {
-        const int t = cam.type[k];
-        if (t == JAICOV_PT_AFFINITY_CX) {  // AffinityShearDistortionModelFactory.java:37-81
-            const double cx = cam.val[k], cy = cam.val[k + 1];
+    if (STD) {
+        // Straight-line evaluation of the canonical coefficient list (what AICONReportFileReader builds, :308): the same formulas and
+        // the same order of operations as the interpreter below, without its per-coefficient type dispatch, power look-ups and
+        // int -> double conversions.  The loop counts are per camera, i.e. uniform over the CTA.
+        int k = 0;
+        if (cam.hasC) {  // AffinityShearDistortionModelFactory.java:37-81
+            const double cx = cam.val[0], cy = cam.val[1];
             chain(cx * xs + cy * ys, 0.0, cx, cy, 0.0, 0.0);
-            sink(k, xs, 0.0);
-            sink(k + 1, ys, 0.0);
-            k += 2;
-        } else if (t == JAICOV_PT_TANGENTIAL_BX) {  // TangentialDistortionModelFactory.java:39-134
+            sink(0, xs, 0.0);
+            sink(1, ys, 0.0);
+            k = 2;
+        }
+        if (cam.hasB) {  // TangentialDistortionModelFactory.java:39-134
             const double bx = cam.val[k], by = cam.val[k + 1];
             double sum = 1.0;
             const double dlx = bx * (r2 + xxs2) + by * xys2;
@@ -172,116 +176,186 @@ __host__ __device__ __forceinline__ void eval_observation_t(const ImgPose &q, co
             const double dYxs = dXys;
             const double dYys = 2.0 * (bx * xs + 3.0 * by * ys);
             chain(dlx, dly, dXxs, dXys, dYxs, dYys);
-            int kb = k + 2;
-            while (kb < nc && cam.type[kb] == JAICOV_PT_TANGENTIAL_B) {
-                const double bi = cam.val[kb];
-                const int e = cam.order[kb];
-                const double rim1 = r2pow(e - 1);
+            double rim1 = 1.0, ef = 1.0;
+            for (int i = 0; i < cam.nB; i++) {
+                const double bi = cam.val[k + 2 + i];
                 const double ri = rim1 * r2;
                 const double dT = bi * ri;
                 sum += dT;
-                const double cT = 2.0 * bi * e * rim1;
+                const double cT = 2.0 * bi * ef * rim1;
                 const double cTx = dlx * cT, cTy = dly * cT;
-                chain(dlx * dT, dly * dT, dT * dXxs + xs * cTx, dT * dXys + ys * cTx, dT * dYxs + xs * cTy,
-                      dT * dYys + ys * cTy);
-                sink(kb, dlx * ri, dly * ri);
-                kb++;
+                chain(dlx * dT, dly * dT, dT * dXxs + xs * cTx, dT * dXys + ys * cTx, dT * dYxs + xs * cTy, dT * dYys + ys * cTy);
+                sink(k + 2 + i, dlx * ri, dly * ri);
+                rim1 = ri;
+                ef += 1.0;
             }
             sink(k, sum * (r2 + xxs2), sum * xys2);
             sink(k + 1, sum * xys2, sum * (r2 + yys2));
-            k = kb;
-        } else if (t == JAICOV_PT_RADIAL_A) {  // RadiallySymmetricDistortionModelFactory.java:39-90
-            const double ai = cam.val[k];
-            const int e = cam.order[k];
-            const double rim1 = r2pow(e - 1);
-            const double dRi = rim1 * r2 - cam.r0pow[k];
-            const double dRad = ai * dRi;
-            const double cR = ai * e * rim1;
-            chain(xs * dRad, ys * dRad, xxs2 * cR + dRad, xys2 * cR, xys2 * cR, yys2 * cR + dRad);
-            sink(k, xs * dRi, ys * dRi);
-            k++;
-        } else if (t == JAICOV_PT_DISTANCE_D) {  // RadialDistanceDistortionModelFactory.java:39-161
-            const double di = cam.val[k];
-            const int e = cam.order[k];
-            const double rim1 = r2pow(e - 1);
-            const double dRi = rim1 * r2 - cam.r0pow[k];
-            const double dD = (di * dRi) * iN;
-            const double dlx = xs * dD, dly = ys * dD;
-            const double cR = (di * e * rim1) * iN;
-            chain(dlx, dly, xxs2 * cR + dD, xys2 * cR, xys2 * cR, yys2 * cR + dD);
-            sink(k, (xs * dRi) * iN, (ys * dRi) * iN);
-            // explicit chain through N (:67-77, :105-159): coefficient -delta / N of dN/dp, applied after the loop
-            gxs -= dlx * iN;
-            gys -= dly * iN;
-            k++;
-        } else if (t == JAICOV_PT_ZERNIKE_Z) {  // ZernikeDistortionModelFactory.java:41-137 (gradient model)
-            const double xxs = xs * xs, yys = ys * ys, xys = xs * ys;
-            const double phi = atan2(ys, xs);
-            const double rn2 = r2 / r02, c2 = 2.0 / rn2 / r02;
-            const double zi = cam.val[k], m = (double)cam.zern_m[k];
-            const double sm = sin(m * phi), cm = cos(m * phi);
-            double pxZ = 0.0, pyZ = 0.0;
-            for (int jt = cam.zern_ptr[k]; jt < cam.zern_ptr[k + 1]; jt++) {
-                const int pji = cam.zern_p[jt];
-                const double pj = (double)pji;
-                const int cei = pji / 2 - 1;
-                const double ce = (double)cei;
-                const double cC = cam.zern_c[jt] / r02 * ipow(rn2, cei);
-                double cX, cY, a, b, c_, d;
-                if (m < 0) {
-                    cX = (-pj * xs * sm + m * ys * cm);
-                    cY = (-pj * ys * sm - m * xs * cm);
-                    a = zi * cC * (ce * xs * c2 * cX - pj * sm + m / r2 * (pj * xys * cm + m * yys * sm));
-                    b = zi * cC * (ce * ys * c2 * cX + m * cm - m / r2 * (pj * xxs * cm + m * xys * sm));
-                    c_ = zi * cC * (ce * xs * c2 * cY - m * cm + m / r2 * (pj * yys * cm - m * xys * sm));
-                    d = zi * cC * (ce * ys * c2 * cY - pj * sm - m / r2 * (pj * xys * cm - m * xxs * sm));
-                } else {
-                    cX = (pj * xs * cm + m * ys * sm);
-                    cY = (pj * ys * cm - m * xs * sm);
-                    a = zi * cC * (ce * xs * c2 * cX + pj * cm + m / r2 * (pj * xys * sm - m * yys * cm));
-                    b = zi * cC * (ce * ys * c2 * cX + m * sm - m / r2 * (pj * xxs * sm - m * xys * cm));
-                    c_ = zi * cC * (ce * xs * c2 * cY - m * sm + m / r2 * (pj * yys * sm + m * xys * cm));
-                    d = zi * cC * (ce * ys * c2 * cY + pj * cm - m / r2 * (pj * xys * sm + m * xxs * cm));
-                }
-                chain(zi * cC * cX, zi * cC * cY, a, b, c_, d);
-                pxZ += cC * cX;
-                pyZ += cC * cY;
+            k += 2 + cam.nB;
+        }
+        {   // RadiallySymmetricDistortionModelFactory.java:39-90
+            double rim1 = 1.0, ef = 1.0;
+            for (int i = 0; i < cam.nA; i++, k++) {
+                const double ai = cam.val[k];
+                const double ri = rim1 * r2;
+                const double dRi = ri - cam.r0pow[k];
+                const double dRad = ai * dRi;
+                const double cR = ai * ef * rim1;
+                chain(xs * dRad, ys * dRad, xxs2 * cR + dRad, xys2 * cR, xys2 * cR, yys2 * cR + dRad);
+                sink(k, xs * dRi, ys * dRi);
+                rim1 = ri;
+                ef += 1.0;
             }
-            sink(k, pxZ, pyZ);
-            k++;
-        } else if (t == JAICOV_PT_ZERNIKE_X || t == JAICOV_PT_ZERNIKE_Y) {  // :147-227 scalar models, verbatim
-            const double phi = atan2(ys, xs);
-            const double rn2 = r2 / r02;
-            const double zi = cam.val[k], m = (double)cam.zern_m[k];
-            const double sm = sin(m * phi), cm = cos(m * phi);
-            double pZ = 0.0;
-            for (int jt = cam.zern_ptr[k]; jt < cam.zern_ptr[k + 1]; jt++) {
-                const int pji = cam.zern_p[jt];
-                const double pj = (double)pji;
-                const double cj = cam.zern_c[jt];
-                const double rp = ipow(rn2, pji / 2 - 1);
-                const double cC = cj * ipow(rn2, pji / 2);
-                const double cZ = zi * cj / r02 * rp;
-                double delta, pdx, pdy;
-                if (m < 0) {
-                    pdx = cZ * (-pj * xs * sm + m * ys * cm);
-                    pdy = cZ * (-pj * ys * sm - m * xs * cm);
-                    delta = -zi * cC * sm;
-                    pZ += -cC * sm;
-                } else {
-                    pdx = cZ * (pj * xs * cm + m * ys * sm);
-                    pdy = cZ * (pj * ys * cm - m * xs * sm);
-                    delta = zi * cC * cm;
-                    pZ += cC * cm;
-                }
-                if (t == JAICOV_PT_ZERNIKE_X) chain(delta, 0.0, pdx, pdy, 0.0, 0.0);
-                else chain(0.0, delta, 0.0, 0.0, pdx, pdy);
+        }
+        {   // RadialDistanceDistortionModelFactory.java:39-161
+            double rim1 = 1.0, ef = 1.0;
+            for (int i = 0; i < cam.nD; i++, k++) {
+                const double di = cam.val[k];
+                const double ri = rim1 * r2;
+                const double dRi = ri - cam.r0pow[k];
+                const double dD = (di * dRi) * iN;
+                const double dlx = xs * dD, dly = ys * dD;
+                const double cR = (di * ef * rim1) * iN;
+                chain(dlx, dly, xxs2 * cR + dD, xys2 * cR, xys2 * cR, yys2 * cR + dD);
+                sink(k, (xs * dRi) * iN, (ys * dRi) * iN);
+                gxs -= dlx * iN;
+                gys -= dly * iN;
+                rim1 = ri;
+                ef += 1.0;
             }
-            if (t == JAICOV_PT_ZERNIKE_X) sink(k, pZ, 0.0);
-            else sink(k, 0.0, pZ);
-            k++;
-        } else {
-            k++;
+        }
+    } else {
+        int k = 0;
+        const int nc = cam.ncoef;
+        while (k < nc) {
+            const int t = cam.type[k];
+            if (t == JAICOV_PT_AFFINITY_CX) {  // AffinityShearDistortionModelFactory.java:37-81
+                const double cx = cam.val[k], cy = cam.val[k + 1];
+                chain(cx * xs + cy * ys, 0.0, cx, cy, 0.0, 0.0);
+                sink(k, xs, 0.0);
+                sink(k + 1, ys, 0.0);
+                k += 2;
+            } else if (t == JAICOV_PT_TANGENTIAL_BX) {  // TangentialDistortionModelFactory.java:39-134
+                const double bx = cam.val[k], by = cam.val[k + 1];
+                double sum = 1.0;
+                const double dlx = bx * (r2 + xxs2) + by * xys2;
+                const double dly = by * (r2 + yys2) + bx * xys2;
+                const double dXxs = 2.0 * (3.0 * bx * xs + by * ys);
+                const double dXys = 2.0 * (by * xs + bx * ys);
+                const double dYxs = dXys;
+                const double dYys = 2.0 * (bx * xs + 3.0 * by * ys);
+                chain(dlx, dly, dXxs, dXys, dYxs, dYys);
+                int kb = k + 2;
+                while (kb < nc && cam.type[kb] == JAICOV_PT_TANGENTIAL_B) {
+                    const double bi = cam.val[kb];
+                    const int e = cam.order[kb];
+                    const double rim1 = r2pow(e - 1);
+                    const double ri = rim1 * r2;
+                    const double dT = bi * ri;
+                    sum += dT;
+                    const double cT = 2.0 * bi * e * rim1;
+                    const double cTx = dlx * cT, cTy = dly * cT;
+                    chain(dlx * dT, dly * dT, dT * dXxs + xs * cTx, dT * dXys + ys * cTx, dT * dYxs + xs * cTy,
+                          dT * dYys + ys * cTy);
+                    sink(kb, dlx * ri, dly * ri);
+                    kb++;
+                }
+                sink(k, sum * (r2 + xxs2), sum * xys2);
+                sink(k + 1, sum * xys2, sum * (r2 + yys2));
+                k = kb;
+            } else if (t == JAICOV_PT_RADIAL_A) {  // RadiallySymmetricDistortionModelFactory.java:39-90
+                const double ai = cam.val[k];
+                const int e = cam.order[k];
+                const double rim1 = r2pow(e - 1);
+                const double dRi = rim1 * r2 - cam.r0pow[k];
+                const double dRad = ai * dRi;
+                const double cR = ai * e * rim1;
+                chain(xs * dRad, ys * dRad, xxs2 * cR + dRad, xys2 * cR, xys2 * cR, yys2 * cR + dRad);
+                sink(k, xs * dRi, ys * dRi);
+                k++;
+            } else if (t == JAICOV_PT_DISTANCE_D) {  // RadialDistanceDistortionModelFactory.java:39-161
+                const double di = cam.val[k];
+                const int e = cam.order[k];
+                const double rim1 = r2pow(e - 1);
+                const double dRi = rim1 * r2 - cam.r0pow[k];
+                const double dD = (di * dRi) * iN;
+                const double dlx = xs * dD, dly = ys * dD;
+                const double cR = (di * e * rim1) * iN;
+                chain(dlx, dly, xxs2 * cR + dD, xys2 * cR, xys2 * cR, yys2 * cR + dD);
+                sink(k, (xs * dRi) * iN, (ys * dRi) * iN);
+                // explicit chain through N (:67-77, :105-159): coefficient -delta / N of dN/dp, applied after the loop
+                gxs -= dlx * iN;
+                gys -= dly * iN;
+                k++;
+            } else if (t == JAICOV_PT_ZERNIKE_Z) {  // ZernikeDistortionModelFactory.java:41-137 (gradient model)
+                const double xxs = xs * xs, yys = ys * ys, xys = xs * ys;
+                const double phi = atan2(ys, xs);
+                const double rn2 = r2 / r02, c2 = 2.0 / rn2 / r02;
+                const double zi = cam.val[k], m = (double)cam.zern_m[k];
+                const double sm = sin(m * phi), cm = cos(m * phi);
+                double pxZ = 0.0, pyZ = 0.0;
+                for (int jt = cam.zern_ptr[k]; jt < cam.zern_ptr[k + 1]; jt++) {
+                    const int pji = cam.zern_p[jt];
+                    const double pj = (double)pji;
+                    const int cei = pji / 2 - 1;
+                    const double ce = (double)cei;
+                    const double cC = cam.zern_c[jt] / r02 * ipow(rn2, cei);
+                    double cX, cY, a, b, c_, d;
+                    if (m < 0) {
+                        cX = (-pj * xs * sm + m * ys * cm);
+                        cY = (-pj * ys * sm - m * xs * cm);
+                        a = zi * cC * (ce * xs * c2 * cX - pj * sm + m / r2 * (pj * xys * cm + m * yys * sm));
+                        b = zi * cC * (ce * ys * c2 * cX + m * cm - m / r2 * (pj * xxs * cm + m * xys * sm));
+                        c_ = zi * cC * (ce * xs * c2 * cY - m * cm + m / r2 * (pj * yys * cm - m * xys * sm));
+                        d = zi * cC * (ce * ys * c2 * cY - pj * sm - m / r2 * (pj * xys * cm - m * xxs * sm));
+                    } else {
+                        cX = (pj * xs * cm + m * ys * sm);
+                        cY = (pj * ys * cm - m * xs * sm);
+                        a = zi * cC * (ce * xs * c2 * cX + pj * cm + m / r2 * (pj * xys * sm - m * yys * cm));
+                        b = zi * cC * (ce * ys * c2 * cX + m * sm - m / r2 * (pj * xxs * sm - m * xys * cm));
+                        c_ = zi * cC * (ce * xs * c2 * cY - m * sm + m / r2 * (pj * yys * sm + m * xys * cm));
+                        d = zi * cC * (ce * ys * c2 * cY + pj * cm - m / r2 * (pj * xys * sm + m * xxs * cm));
+                    }
+                    chain(zi * cC * cX, zi * cC * cY, a, b, c_, d);
+                    pxZ += cC * cX;
+                    pyZ += cC * cY;
+                }
+                sink(k, pxZ, pyZ);
+                k++;
+            } else if (t == JAICOV_PT_ZERNIKE_X || t == JAICOV_PT_ZERNIKE_Y) {  // :147-227 scalar models, verbatim
+                const double phi = atan2(ys, xs);
+                const double rn2 = r2 / r02;
+                const double zi = cam.val[k], m = (double)cam.zern_m[k];
+                const double sm = sin(m * phi), cm = cos(m * phi);
+                double pZ = 0.0;
+                for (int jt = cam.zern_ptr[k]; jt < cam.zern_ptr[k + 1]; jt++) {
+                    const int pji = cam.zern_p[jt];
+                    const double pj = (double)pji;
+                    const double cj = cam.zern_c[jt];
+                    const double rp = ipow(rn2, pji / 2 - 1);
+                    const double cC = cj * ipow(rn2, pji / 2);
+                    const double cZ = zi * cj / r02 * rp;
+                    double delta, pdx, pdy;
+                    if (m < 0) {
+                        pdx = cZ * (-pj * xs * sm + m * ys * cm);
+                        pdy = cZ * (-pj * ys * sm - m * xs * cm);
+                        delta = -zi * cC * sm;
+                        pZ += -cC * sm;
+                    } else {
+                        pdx = cZ * (pj * xs * cm + m * ys * sm);
+                        pdy = cZ * (pj * ys * cm - m * xs * sm);
+                        delta = zi * cC * cm;
+                        pZ += cC * cm;
+                    }
+                    if (t == JAICOV_PT_ZERNIKE_X) chain(delta, 0.0, pdx, pdy, 0.0, 0.0);
+                    else chain(0.0, delta, 0.0, 0.0, pdx, pdy);
+                }
+                if (t == JAICOV_PT_ZERNIKE_X) sink(k, pZ, 0.0);
+                else sink(k, 0.0, pZ);
+                k++;
+            } else {
+                k++;
+            }
         }
     }
     // apply the accumulated factors once; dN/d(X,Y,Z) = (r13, r23, r33), dN/dc = 0, dN/d omega = -r33 dY + r23 dZ,
@@ -307,7 +381,7 @@ __host__ __device__ __forceinline__ void eval_observation_t(const ImgPose &q, co
 template <class Sink>
 __host__ __device__ __forceinline__ void eval_observation(const ImgPose &q, const CamView &cam, double X, double Y, double Z,
                                                           double xobs, double yobs, BaseRows &r, Sink &&sink) {
-    eval_observation_t<true>(q, cam, X, Y, Z, xobs, yobs, r, sink);
+    eval_observation_t<true, false>(q, cam, X, Y, Z, xobs, yobs, r, sink);
 }
 
 // Weight matrix of an image point, PartialDerivativeFactory.java:296-319: returns P00, P01, P11

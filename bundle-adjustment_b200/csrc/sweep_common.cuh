@@ -25,12 +25,14 @@ struct CamSmem {
     double val[kMaxCoef], r0pow[kMaxCoef];
     int32_t type[kMaxCoef], order[kMaxCoef], zm[kMaxCoef], zptr[kMaxCoef + 1];
     int32_t ncoef;
+    int32_t std5[5];     // hasC, hasB, nB, nA, nD of a canonical coefficient list (model.cuh: STD evaluation); hasC < 0: not canonical
 };
 
 __device__ __forceinline__ void load_camera(const DevProblem &P, int cam, CamSmem &s, int tid, int nthreads) {
     const int c0 = P.coef_ptr[cam], c1 = P.coef_ptr[cam + 1];
     if (tid < 3) s.io[tid] = P.io_val[3 * cam + tid];
     if (tid == 3) { s.r0 = P.r0[cam]; s.ncoef = c1 - c0; }
+    if (tid >= 4 && tid < 9) s.std5[tid - 4] = P.cam_std[5 * cam + tid - 4];
     for (int k = tid; k < c1 - c0; k += nthreads) {
         s.val[k] = P.coef_val[c0 + k];
         s.r0pow[k] = P.coef_r0pow[c0 + k];
@@ -45,6 +47,7 @@ __device__ __forceinline__ CamView view_of(const DevProblem &P, const CamSmem &s
     CamView v;
     v.io = s.io; v.r0 = s.r0; v.ncoef = s.ncoef; v.type = s.type; v.order = s.order; v.val = s.val; v.r0pow = s.r0pow;
     v.zern_m = s.zm; v.zern_ptr = s.zptr; v.zern_p = P.zern_p; v.zern_c = P.zern_c;
+    v.hasC = s.std5[0]; v.hasB = s.std5[1]; v.nB = s.std5[2]; v.nA = s.std5[3]; v.nD = s.std5[4];
     return v;
 }
 

@@ -22,7 +22,7 @@ def main(path, top=25):
         byop[op] += n
         samp[op] += int(r[iSm] or 0)
     print('total executed warp instructions %d, static %d' % (tot, len(rows) - h - 1))
-    for k, v in byop.most_common(top):
+    for k, v in byop.most_common(top):  # noqa
         print('%-10s %12d %5.1f%%  stall samples %d' % (k, v, 100.0 * v / tot, samp[k]))
 
 
