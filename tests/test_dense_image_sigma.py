@@ -19,12 +19,12 @@ def _pack(S):
     return out
 
 
-def scene_with_dispersions(images_dense, common_mode, seed=3):
+def scene_with_dispersions(images_dense, common_mode, seed=3, images=8, targets=40):
     """config-2 style network with correlated image coordinates; the listed images get their dispersion as a dense matrix:
     blockdiag(2 x 2 from sigma, rho) + common_mode * sigma^2 * (u u' + v v') with u / v = indicator of the x / y rows
     (a common-mode error of all coordinates of the image; 0 gives the block-diagonal case)."""
     rng = np.random.default_rng(seed)
-    sc = synthetic_scene(2, images=8, targets=40, seed=77)[0]
+    sc = synthetic_scene(2, images=images, targets=targets, seed=77)[0]
     k = 0
     for cam in sc['cameras']:
         for im in cam['images']:
@@ -126,3 +126,28 @@ def test_gpu_dense_image_dispersion(built, common_mode):
     assert s.iterate(final_pass=True, apply_update=False) == 0
     verify.assert_ok(verify.check_pass(s, omega=s.stats().omega))
     s.close()
+
+
+@pytest.mark.gpu
+def test_gpu_dense_dispersion_on_every_image_midsize(built):
+    """Every image of a 12 x 300 network carries a fully populated 600 x 600 dispersion (block diagonal + common mode): the point block
+    of N is then dense (every pair of points is coupled through every image), 12 device Cholesky + inverse of the dispersions, the
+    tensor-core products T = P Ac at 640 rows.  Against the oracle extension and the matrix-free identities."""
+    import bundle_adjustment_b200 as ba
+    from bundle_adjustment_b200 import verify
+    from tests.helpers import build_adjustment
+    dense = set(range(12))
+    mk = lambda: scene_with_dispersions(dense, 0.3, images=12, targets=300)
+    adj, _pts = build_adjustment(mk())
+    assert adj.estimateModel() == ba.EstimationStateType.ERROR_FREE_ESTIMATION
+    o = DenseImageSigmaOracle(mk())
+    assert o.estimate() == 1 and adj.stats.iterations == len(o.history)
+    Qg, Qo = adj.getCofactorMatrix().toDense(), o.qxx_dense()
+    sg = np.sqrt(np.abs(np.diag(Qo)))
+    sg[:o.fp.d] = 1.0
+    errq = np.max(np.abs(Qg - Qo) / np.outer(sg, sg))
+    s2g, s2o = adj.getVarianceFactorAposteriori(), o.variance_factor_aposteriori()
+    print('dense dispersion on all 12 images (n = %d): scaled Qxx err %.2e, sigma0^2 rel err %.2e, last pass %.2f ms'
+          % (o.fp.n, errq, abs(s2g - s2o) / s2o, adj.stats.ms_total))
+    assert errq <= 1e-8 and abs(s2g - s2o) <= 1e-8 * s2o
+    verify.assert_ok(verify.check_pass(adj._session, omega=adj.stats.omega, values_updated=True))

@@ -72,6 +72,34 @@ def test_no_cpu_fallback(built):
 
 
 @pytest.mark.skipif(_has_device(), reason='a B200 is visible: the calls below would compute')
+def test_no_cpu_fallback_for_the_round2_entry_points(built):
+    """The single-process multi-GPU handle, the matrix-free product, the dense image dispersion and the device queries fail loudly
+    (NOT_INITIALISED) without devices -- and the handle still closes cleanly."""
+    from bundle_adjustment_b200.workloads import flat_problem, synthetic_scene
+    sc = synthetic_scene(2, images=4, targets=20)[0]
+    m2 = 2 * len(sc['cameras'][0]['images'][1]['obj'])
+    sc['cameras'][0]['images'][1]['dispersion'] = np.full(m2 * (m2 + 1) // 2, 0.0)      # content irrelevant here
+    adj, flat = flat_problem(sc)
+    assert [i for i, _s in flat['img_sigma']] == [1]
+    for nd in (1, 2):
+        s = ba.Session(sigma2apriori=adj.getVarianceFactorApriori(), n_devices=nd)
+        s.set_problem(flat)
+        with pytest.raises(ba.JaicovError) as e:
+            s.estimate()
+        assert e.value.code == ba._lib.NOT_INITIALISED and 'no CPU path' in str(e.value)
+        with pytest.raises(ba.JaicovError) as e:
+            s.normal_product(np.zeros((1, s.n)))
+        assert e.value.code == ba._lib.NOT_INITIALISED
+        with pytest.raises(ba.JaicovError):
+            s.qxx_packed()
+        assert s.device_bytes() == [0, 0, 0, 0]
+        s.close()
+    assert ba._lib.set_gemm_digits(-1) in (-1, 0, 8)             # query only: nothing decided without a device
+    with pytest.raises(ba.JaicovError):
+        ba.Session(n_devices=-1)
+
+
+@pytest.mark.skipif(_has_device(), reason='a B200 is visible: the calls below would compute')
 def test_no_cpu_fallback_for_the_widened_entry_points(built):
     """jaicov_dlt_batch and the covariance propagation have no CPU route either."""
     pt_ptr = np.array([0, 6])
