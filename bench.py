@@ -8,9 +8,12 @@ full inverse Qxx, Omega = v'Pv, max|dx| (jaicov_iterate(final_pass=1)).  The sam
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4|5] [--impl reference]
 
-N > 1 (torchrun): ONE adjustment spread over the N GPUs (strong scaling): image-sharded assembly + NCCL all-reduce of
-the shared blocks, block-column-cyclic Cholesky with panel broadcasts over NVLink, every rank inverts its own column
-tiles of Qxx.
+N > 1 (torchrun): ONE adjustment spread over the N GPUs (strong scaling).  Every rank runs the observation sweeps and keeps
+only the tile columns of the system it owns (block-column-cyclic, no all-reduce of N); the Cholesky panels, the fused
+forward substitution and the panels of the inverse sweep are broadcast over NVLink/NCCL; every rank inverts its own column
+tiles of Qxx.  After the timed region every arm is checked with the matrix-free identities of
+bundle-adjustment_b200/verify.py (K [lambda; dx] = [0; n], K Qxx e_c = e_c on sampled columns, the Omega identity); a
+failed check makes bench.py exit non-zero.
 `--impl reference` times the CPU oracle (oracle/, the restatement of the Java path; no JVM exists here) on a bounded,
 scaled-down sample of the same workload and extrapolates (assembly ~ image points, factor+inverse ~ n^3).
 """
