@@ -26,6 +26,13 @@ def test_exports_match_header(built):
     assert sorted(ba._lib.EXPORTS) == names
 
 
+def test_every_entry_point_is_documented_for_the_integrator():
+    """INTEGRATION.md section 2 maps every C entry point to the reference interface it replaces (or says it has none)."""
+    doc = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    missing = [n for n in declared_symbols() if n not in doc]
+    assert not missing, missing
+
+
 def test_struct_sizes(built):
     assert ctypes.sizeof(ba._lib.Options) == 8 * 4 + 2 * 8
     assert ctypes.sizeof(ba._lib.Stats) == 8 * 4 + 10 * 8
