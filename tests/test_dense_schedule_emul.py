@@ -109,7 +109,8 @@ def test_rect_tile_order_is_a_bijection(emul, mt, nt, band):
     assert len(seen) == mt * nt
 
 
-@pytest.mark.parametrize('nb,nranks,pw,ozaki', [(1, 1, 1, 0), (3, 2, 1, 0), (5, 2, 2, 0), (7, 3, 2, 0), (6, 4, 1, 0), (9, 2, 3, 0), (4, 8, 1, 0), (3, 2, 1, 8)])
+@pytest.mark.parametrize('nb,nranks,pw,ozaki', [(1, 1, 1, 0), (3, 2, 1, 0), (5, 2, 2, 0), (7, 3, 2, 0), (6, 4, 1, 0), (9, 2, 3, 0), (4, 8, 1, 0), (3, 2, 1, 8),
+                                                (17, 8, 2, 0), (13, 4, 3, 0), (11, 8, 1, 0), (10, 3, 16, 0), (5, 3, 2, 8)])   # shapes of config 5 scaled down: more panels than ranks, narrow last panel, one panel wider than the matrix
 def test_streamed_owner_only_schedule_with_virtual_ranks(emul, nb, nranks, pw, ozaki):
     """Owner-only storage (DenseSchedule::factor_solve_invert_streamed): every virtual rank holds ONLY its own block-column panels
     (the rest of its matrix is NaN), receives the others through a two-slot window, and still produces the solutions of the
