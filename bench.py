@@ -500,13 +500,22 @@ def main():
             gbs = (m_pts / world if sharded else m_pts) * bytes_ / (ms_ * 1e-3) / 1e9
             sweep_gbs[name_] = {'ms': ms_, 'algorithmic_GBps': gbs, 'frac_of_hbm_peak': gbs / hbm}
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak * world, 'unit': 'TFLOP/s', 'frac': achieved / (peak * world),
-                'traffic': TRAFFIC.get(args.config if not structured_used else -args.config), 'peak_per_gpu': peak,
+                # the measured figure belongs to the all-DMMA step on one GPU (its single M = W^T W launch); the digit path's launches
+                # were captured at 8192^3 and in the first part of a config-5 factorisation only (traffic_note)
+                'traffic': (TRAFFIC.get(args.config if not structured_used else -args.config) if digits == 0 and world == 1 else None),
+                'traffic_fp64_dmma_lauum_launch': TRAFFIC.get(args.config) if (world == 1 and not structured_used) else None,
+                'peak_per_gpu': peak,
                 'frac_factor_inverse_stages': achieved_stage / (peak * world),
                 'observation_sweeps': sweep_gbs,
                 'observation_sweeps_note': 'FP64-issue bound, not HBM bound: ~340 FP64 instructions per image point at 13 camera parameters against '
                                            '44 B (arithmetic intensity 2x the machine balance of FP64 pipe / HBM): a fully busy FP64 pipe caps them at '
                                            '~36 % of the HBM peak; ncu: FP64 pipe 52 % active in the Omega sweep (DESIGN.md section 5, profiles/r02_ncu_sweeps_final_summary.txt)',
-                'traffic_note': 'k_gemm is launched thousands of times per pass with different tile counts, so there is no single per-launch '
+                'traffic_note': 'digit path (k_gemm_oz<8,1>): ncu --set full at 8192^3 (profiles/r02_ncu_full_k_gemm_oz_summary.txt): 9.2 GB of DRAM traffic '
+                                'for 1.07 GB of FP64 operands (band-swizzled tile order; 32 GB before), not the limiter (L2 -> SM operand traffic is); '
+                                'launch list of a config-5 pass (profiles/r02_launches_c5_dense_partial.txt, first 2 196 launches): 2.74 GB per '
+                                'k_gemm_oz launch on average.  All-DMMA step: the single M = W^T W launch of config 5 moves 3.32 TB '
+                                '(profiles/r02_lauum_c5_dram_traffic.txt) for 16 GB of operands at 94 % DMMA pipe activity.  '
+                                'k_gemm is launched thousands of times per pass with different tile counts, so there is no single per-launch '
                                 'figure; ncu --set full of its largest launches (profiles/r01_ncu_full_k_gemm_shape65_summary.txt): LAUUM at '
                                 'config 4 moves 21.4 GB of DRAM traffic for 1.43e12 flop (tensor pipe 94.2 % active), the structured '
                                 "route's Y(Q'Y') launch at config 5 353.5 GB for 1.107e13 flop (93.8 %)",
