@@ -236,10 +236,10 @@ static void launch_gemm_l(const GemmDesc &g, cudaStream_t s) {
     else launch_gemm_t<AL, BL, 32>(g, tiles, s);
 }
 
-bool launch_gemm_ozaki(const GemmDesc &g, cudaStream_t s);   // ozaki.cu: experiment, takes nothing unless JAICOV_GEMM_OZAKI is set
+bool launch_gemm_ozaki(const GemmDesc &g, cudaStream_t s);   // ozaki.cu: int8 digit products on tcgen05, takes the big launches (>= 148 tiles, K >= 1024) unless switched off
 
 void launch_gemm(const GemmDesc &g_in, cudaStream_t s) {
-    // experiment switch (default off): band-swizzled tile order of the lower-triangular launches, DESIGN.md section 9
+    // switch (default off, measured: no gain on the DMMA-bound launches): band-swizzled tile order of the lower-triangular launches, DESIGN.md section 9.4
     static const int band = [] { const char *e = getenv("JAICOV_TILE_BAND"); return e ? atoi(e) : 0; }();
     GemmDesc g = g_in;
     if (g.tri_out && band > 0 && g.tile_band == 0) g.tile_band = band;

@@ -1,4 +1,5 @@
-// ozaki.cu -- EXPERIMENT, default OFF (JAICOV_GEMM_OZAKI=<digits 4..8>): FP64 GEMM tiles built from int8 digit products on
+// ozaki.cu -- the big tile products of the path (DEFAULT since round 2, 8 digits; JAICOV_GEMM_OZAKI=0 or jaicov_set_gemm_digits(0)
+// switch back to the FP64 DMMA tiles of dense_kernels.cu): FP64 GEMM tiles built from int8 digit products on
 // the 5th-generation tensor cores (tcgen05.mma kind::i8, operands staged by TMA, s32 accumulators in TMEM).
 //
 // Why: every O(n^3) flop of the path (Cholesky, inverse, the structured route's products) runs on k_gemm at 94 % DMMA pipe
@@ -13,12 +14,13 @@
 // Cholesky + inverse schedule with this arithmetic emulated bit for bit on the host (tests/emul/host_backend.cpp) and gets
 // the cofactor matrix of real bundle networks as close to a long-double reference as the FP64 schedule itself.
 //
-// STATUS: written and compiled for sm_100a without access to a GPU; the last seconds of the round's GPU budget then went into a
-// first contact (tools/ozaki_quick.py, profiles/r01_ozaki_first_contact.log): three tile-grid products on a B200 -- plain, transposed
-// operand with alpha / beta, symmetric output with triangular operands -- are correct, with exactly the errors the host emulation
-// predicts (4.4e-16, 3.1e-16, 1.2e-14).  NOT yet done: timings, the cluster / multicast variant, the full check
-// (tools/ozaki_gpu_check.py) and the parity suite with the switch on (tools/next_round_ab.sh ozaki).  Nothing takes this path unless
-// JAICOV_GEMM_OZAKI is set; it stays out of the default path until those are green and it is measured faster.
+// STATUS (round 2): validated and measured on B200 -- tools/ozaki_gpu_check.py complete (every operand layout /
+// triangular hint / symmetric output with NaN-poisoned operands, SPD solve + inverse: errors exactly the host emulation's), the whole
+// parity suite incl. the full-size configs 3 / 4 and the multi-GPU cases with EVERY launch forced onto this path
+// (JAICOV_OZAKI_MIN_TILES=1 JAICOV_OZAKI_MIN_K=128), 29 / 36 / 42 / 45 TFLOP/s FP64-equivalent at K = 512 / 1024 / 2048 / 4096 against 33-35
+// for the DMMA tiles (hence the thresholds below: launches of >= 148 tiles with K >= 1024), config 5 dense 7.40 s -> 5.39 s per final
+// pass.  ncu: tcgen05 pipe 40 % active, bound by L2 -> shared-memory operand traffic (4.8 TB/s) of the 128 x 64 tile; the two-CTA
+// cluster variant with TMA multicast of op(A) measures the same on whole passes and stays off (JAICOV_OZAKI_CLUSTER).
 //
 // Shapes: CTA tile 128 x 64 (S accumulators of 64 TMEM columns = all 512 columns for S = 8), k-block 64 bytes (SWIZZLE_64B
 // rows), two smem stages of S * (128 + 64) * 64 bytes (96 KB each for S = 8); warp 0 = TMA producer, warp 1 = MMA issuer and
@@ -617,7 +619,7 @@ int ozaki_digits() {
     return d;
 }
 
-// Takes the launch if the experiment is switched on and the launch is one of the big plain / triangular-operand products;
+// Takes the launch if the digit path is on (default) and the launch is one of the big plain / triangular-operand products;
 // returns false (nothing launched) otherwise, and the caller runs k_gemm.
 bool launch_gemm_ozaki(const GemmDesc &g, cudaStream_t s) {
     const int digits = ozaki_digits();

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""First-run checks of the int8-digit GEMM experiment (csrc/ozaki.cu, JAICOV_GEMM_OZAKI) on a B200 -- NOT part of tests/:
-the kernel was written without a GPU and must pass here before anything depends on it.
+"""Stand-alone checks of the int8-digit tile products (csrc/ozaki.cu, JAICOV_GEMM_OZAKI) on a B200 -- NOT part of tests/ (the parity
+suite covers the path through the adjustment); this is the kernel-level check it had to pass before it became the default
+(profiles/r02_ozaki_check.log).
 
   python tools/ozaki_gpu_check.py            # all stages, every worker in its own process under a timeout
   python tools/ozaki_gpu_check.py gemm|spd|time
@@ -12,7 +13,7 @@ Stages
   spd   jaicov_spd_solve_invert (blocked Cholesky + inverse) with every launch on the digit path, against numpy.
   time  one 8192^3 product and one 16384^2 x 8192 symmetric product: FP64 DMMA kernel vs 8 / 7 digits and the cluster variant (TFLOP/s FP64-equivalent).
 The environment variables are read once per process, so every setting runs in a subprocess (JAICOV_OZAKI_MIN_TILES=1 sends
-small launches, JAICOV_OZAKI_MIN_K=128 short contractions through the experiment as well).  A hang is cut by the timeout and reported, not retried.
+small launches, JAICOV_OZAKI_MIN_K=128 short contractions through the digit path as well).  A hang is cut by the timeout and reported, not retried.
 """
 import json
 import os
