@@ -307,7 +307,7 @@ int32_t jaicov_omega(jaicov_handle *h, const double *dx, double *omega);
  * datum rows :493-635; no Levenberg-Marquardt damping), evaluated MATRIX-FREE from the observations at the current values:
  * y_v = K x_v for nvec vectors x, y = [nvec][u+d] (reference column order, host buffers), rhs (may be NULL, u+d) <- [0; A'Pw],
  * wpw (may be NULL) <- w'Pw.  Nothing of the assembled matrix, its factor or Qxx is read, so a caller can check
- *   K [lambda; dx] = [0; n],   K Qxx e_c = e_c (columns from jaicov_get_qxx_block),   Omega = w'Pw - n'dx
+ *   K [lambda; dx] = [0; n],   K Qxx e_c = e_c (columns from jaicov_get_qxx_block),   Omega = w'Pw - 2 n'dx + dx'N dx
  * on configurations no CPU reference can reach (bench.py does, at every N).  Distributed handles sum their image shards
  * (NCCL all-reduce); every rank receives the complete product.  Does not disturb Qxx / dx of the last pass. */
 int32_t jaicov_normal_product(jaicov_handle *h, int32_t nvec, const double *x, double *y, double *rhs, double *wpw);
