@@ -161,7 +161,12 @@ int32_t jaicov_set_gemm_digits(int32_t digits);
  *     every process then calls jaicov_dist_init on its handle BEFORE the set_* calls take effect.  Every rank passes the
  *     SAME full problem.  jaicov_get_qxx_block then returns PARTIAL blocks (zeros for entries owned elsewhere; the sum over
  *     ranks is the block), jaicov_get_qxx_local the rank's column tiles as stored.  An interrupt flag must be passed by every
- *     rank or by none (the ranks agree on the decision with one scalar all-reduce per check). */
+ *     rank or by none (the ranks agree on the decision with one scalar all-reduce per check).
+ *
+ * Failure semantics (both forms): errors that follow from the problem (illegal arguments, a matrix that is not positive definite, the
+ * iteration limit, an interrupt) are detected identically or agreed upon by all devices, and every device returns the same id.  An
+ * error that strikes ONE device only (out of memory because another process holds that GPU, a device fault) is not agreed upon: the
+ * other devices wait in their next collective, as in any NCCL program -- give every device of the handle the same free memory. */
 /* pure host function: the contiguous image range [img_begin, img_end) rank `rank` of `world` works on (boundaries at
  * the images where the cumulative observation count crosses rank * m / world) */
 int32_t jaicov_shard_images(int32_t n_img, const int64_t *pt_ptr, int32_t world, int32_t rank, int32_t *img_begin, int32_t *img_end);
