@@ -107,10 +107,12 @@ def load():
     L.jaicov_set_image_dispersion.argtypes = [vp, i32, i64, vp]
     L.jaicov_get_sweep_times.argtypes = [vp, ctypes.POINTER(dbl), ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
     L.jaicov_spd_solve_invert.argtypes = [i32, i64, vp, i32, vp, i32, ctypes.POINTER(dbl), ctypes.POINTER(dbl)]
+    L.jaicov_gemm_tiles.argtypes = [i32] * 5 + [i64, dbl, dbl, vp, i64, vp, i64, vp, i64, i32, i32, i32, vp]
     for name in EXPORTS:
-        if name not in ('jaicov_destroy', 'jaicov_last_error', 'jaicov_launch_count'):
+        if name not in ('jaicov_destroy', 'jaicov_last_error', 'jaicov_launch_count', 'jaicov_release_cached_memory'):
             getattr(L, name).restype = ctypes.c_int32
     L.jaicov_launch_count.restype = ctypes.c_int64
+    L.jaicov_release_cached_memory.restype = ctypes.c_int64       # bytes: tens of GB
     _lib = L
     return L
 
@@ -428,9 +430,6 @@ def gemm_tiles(A, B, C, a_layout=0, b_layout=0, alpha=1.0, beta=0.0, tri_out=Fal
     Mr, K = (A.shape if a_layout == 0 else A.shape[::-1])
     Nr = B.shape[0] if b_layout == 0 else B.shape[1]
     ms = ctypes.c_double(0)
-    L.jaicov_gemm_tiles.argtypes = [ctypes.c_int32] * 5 + [ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_int64,
-                                    ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
-                                    ctypes.c_int32, ctypes.c_void_p]
     rc = L.jaicov_gemm_tiles(device, a_layout, b_layout, Mr // 128, Nr // 128, K, alpha, beta, A.ctypes.data, A.shape[1], B.ctypes.data,
                              B.shape[1], C.ctypes.data, C.shape[1], int(bool(tri_out)), kmode, reps, ctypes.byref(ms))
     if rc != OK:

@@ -67,3 +67,30 @@ def test_binding_covers_the_call_sequence_of_estimate_model():
                  'jaicov_get_values', 'jaicov_get_stats', 'jaicov_get_qxx_packed', 'jaicov_get_qxx_block', 'jaicov_get_qxx_submatrix',
                  'jaicov_last_error', 'jaicov_destroy'):
         assert name in desc, name
+
+
+def test_ctypes_binding_matches_the_header(built):
+    """Same check for the ctypes binding the parity tests and bench.py go through (bundle-adjustment_b200/_lib.py): a c_int where the
+    header says int64_t would pass small tests and corrupt large ones."""
+    import ctypes
+
+    import bundle_adjustment_b200 as ba
+    L = ba._lib.load()
+    protos = header_prototypes()
+
+    def layout(t):
+        if t is None:
+            return 'VOID'
+        if t in (ctypes.c_int32, ctypes.c_int):
+            return 'JAVA_INT'
+        if t in (ctypes.c_int64, ctypes.c_longlong, ctypes.c_long):
+            return 'JAVA_LONG' if ctypes.sizeof(t) == 8 else 'JAVA_INT'
+        if t is ctypes.c_double:
+            return 'JAVA_DOUBLE'
+        return 'ADDRESS'                                     # c_void_p, c_char_p, POINTER(...), CFUNCTYPE
+
+    for name, (ret, args) in protos.items():
+        f = getattr(L, name)
+        assert f.argtypes is not None, '%s: argtypes not declared' % name
+        assert [layout(t) for t in f.argtypes] == args, (name, f.argtypes, args)
+        assert layout(f.restype) == ret, (name, f.restype, ret)
