@@ -334,4 +334,12 @@ int jhost_export_default(void *n, const char *base) {
     JH_END
 }
 
+// test hook: java_format_f of jaicov_host.hpp (the number format of the result writers); returns the length written
+int jhost_java_format_f(double v, int width, int precision, int plus, char *out, int cap) {
+    const std::string s = java_format_f(v, width, precision, plus != 0);
+    if (!out || cap <= (int)s.size()) return -1;
+    std::memcpy(out, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+
 }  // extern "C"

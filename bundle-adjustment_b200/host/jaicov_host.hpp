@@ -23,6 +23,7 @@
 #pragma once
 #include <algorithm>
 #include <array>
+#include <charconv>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -883,6 +884,49 @@ private:
     std::unique_ptr<UpperSymmPackMatrix> covariance_;
 };
 
+// String.format(Locale.ENGLISH, "%[+]<width>.<precision>f", double) as java.util.Formatter prints it (the reference needs JDK 25): the
+// digits of Double.toString -- the SHORTEST decimal that round-trips -- rounded HALF_UP to the precision and padded with zeros beyond
+// them.  printf expands the exact binary value and rounds half-even instead ("%.20f" of 0.1: 0.10000000000000000000 in Java,
+// 0.10000000000000000555 in C; "%.1f" of 0.15: 0.2 vs 0.1); the writer's "%35.15f" carries up to 18 significant digits, so the last
+// digits of the .info / .cxx files depend on it.  Same function as writers.py: java_format_f (compared on random doubles in the tests).
+inline std::string java_format_f(double v, int width, int precision, bool plus) {
+    std::string s;
+    if (std::isnan(v)) s = "NaN";
+    else if (std::isinf(v)) s = std::string(v < 0 ? "-" : (plus ? "+" : "")) + "Infinity";
+    else {
+        char buf[64];
+        const auto r = std::to_chars(buf, buf + sizeof buf - 1, std::fabs(v), std::chars_format::scientific);   // shortest round-trip digits
+        *r.ptr = 0;
+        std::string digs;
+        const char *p = buf;
+        for (; *p && *p != 'e'; ++p)
+            if (*p != '.') digs.push_back(*p);
+        const long point = (*p ? std::atol(p + 1) : 0) + 1;       // |v| = 0.d1d2d3... x 10^point
+        const long keep = point + precision;                      // digits in front of the rounding position
+        std::string kept;                                         // round(|v| 10^precision) as a digit string
+        if (keep >= 0) {
+            kept = digs.substr(0, (size_t)std::min<long>(keep, (long)digs.size()));
+            const bool up = keep < (long)digs.size() && digs[(size_t)keep] >= '5';
+            if (keep > (long)digs.size()) kept.append((size_t)(keep - (long)digs.size()), '0');
+            if (up) {
+                long i = (long)kept.size() - 1;
+                for (; i >= 0; i--) {
+                    if (kept[(size_t)i] == '9') kept[(size_t)i] = '0';
+                    else { kept[(size_t)i]++; break; }
+                }
+                if (i < 0) kept.insert(kept.begin(), '1');
+            }
+        }
+        if ((long)kept.size() < precision + 1) kept.insert(0, (size_t)(precision + 1 - (long)kept.size()), '0');
+        if (std::signbit(v)) s = "-";
+        else if (plus) s = "+";
+        s += kept.substr(0, kept.size() - (size_t)precision);
+        if (precision > 0) { s += '.'; s += kept.substr(kept.size() - (size_t)precision); }
+    }
+    if ((long)s.size() < width) s.insert(0, (size_t)(width - (long)s.size()), ' ');
+    return s;
+}
+
 // util/io/writer/DefaultResultWriter.java:46-155: <base>.info (name, component, coordinate, row / column of the exported matrix;
 // format :67) and <base>.cxx (sigma0^2 a posteriori * Qxx of the object coordinates; format :142).  Only the exported sub-matrix
 // leaves the device (jaicov_get_qxx_submatrix); the full cofactor matrix never travels to the host for this.
@@ -901,7 +945,7 @@ public:
                 UnknownParameter &p = oc->component(c);
                 int ci = -1;
                 if (p.getColumn() >= 0 && p.getColumn() < COL_FIXED) { indices.push_back(p.getColumn()); ci = k++; }
-                std::fprintf(f, "%25s\t%5s\t%35.15f\t%10d\n", oc->getName().c_str(), c == 0 ? "X" : (c == 1 ? "Y" : "Z"), p.getValue(), ci);
+                std::fprintf(f, "%25s\t%5s\t%s\t%10d\n", oc->getName().c_str(), c == 0 ? "X" : (c == 1 ? "Y" : "Z"), java_format_f(p.getValue(), 35, 15, false).c_str(), ci);
             }
         std::fclose(f);
         if (adj.getInvertNormalEquation() == MatrixInversion::NONE || !adj.handle()) return;   // no cofactor matrix: .info only
@@ -912,7 +956,7 @@ public:
         f = std::fopen((base_ + ".cxx").c_str(), "w");
         if (!f) throw std::runtime_error("cannot write " + base_ + ".cxx");
         for (size_t r = 0; r < n; r++) {
-            for (size_t c = 0; c < n; c++) std::fprintf(f, "%+35.15f  ", C[r * n + c]);
+            for (size_t c = 0; c < n; c++) { std::fputs(java_format_f(C[r * n + c], 35, 15, true).c_str(), f); std::fputs("  ", f); }
             std::fprintf(f, "\n");
         }
         std::fclose(f);

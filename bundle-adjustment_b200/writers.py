@@ -8,9 +8,34 @@ cofactor matrix (16 GB packed at config 5, not representable in MTJ beyond n = 4
 """
 from __future__ import annotations
 
+import decimal
+
 import numpy as np
 
 from .host import COL_FIXED, PolynomialCoefficient
+
+
+_CTX = decimal.Context(prec=800, rounding=decimal.ROUND_HALF_UP)
+
+
+def java_format_f(value, width, precision, plus=False):
+    """``String.format(Locale.ENGLISH, "%[+]<width>.<precision>f", double)`` as java.util.Formatter prints it (the reference needs
+    JDK 25): the digits are those of ``Double.toString`` -- the SHORTEST decimal that round-trips -- rounded HALF_UP to the precision
+    and padded with zeros beyond them.  C's printf (and Python's ``%``) expand the exact binary value instead and round it half-even:
+    ``%.20f`` of 0.1 is ``0.10000000000000000000`` in Java but ``0.10000000000000000555`` in C, ``%.1f`` of 0.15 is ``0.2`` vs ``0.1``.
+    The .info / .cxx files of DefaultResultWriter (formats ``%35.15f`` and ``%+35.15f``, DefaultResultWriter.java:67,142) carry up
+    to 18 significant digits, so the difference shows in their last digits."""
+    v = float(value)
+    if v != v:
+        s = 'NaN'
+    elif v in (float('inf'), float('-inf')):
+        s = ('-' if v < 0 else ('+' if plus else '')) + 'Infinity'
+    else:
+        q = _CTX.quantize(decimal.Decimal(repr(v)), decimal.Decimal(1).scaleb(-precision))
+        s = format(q, 'f')
+        if plus and not s.startswith('-'):
+            s = '+' + s
+    return s.rjust(width)
 
 
 class BundleAdjustmentResultWriter:
@@ -116,11 +141,11 @@ class DefaultResultWriter(BundleAdjustmentResultWriter):
         with open(self._base + '.info', 'w') as f:
             for oc, c in zip(adj.getObjectCoordinates(), cov):
                 for comp, p, ci in zip('XYZ', (oc.getX(), oc.getY(), oc.getZ()), c):
-                    f.write('%25s\t%5s\t%35.15f\t%10d\n' % (oc.getName(), comp, p.getValue(), ci))
+                    f.write('%25s\t%5s\t%s\t%10d\n' % (oc.getName(), comp, java_format_f(p.getValue(), 35, 15), ci))
         if self._has_cofactor(adj):
             C = adj._session.qxx_submatrix(np.array(indices, np.int32), adj.getVarianceFactorAposteriori())
             with open(self._base + '.cxx', 'w') as f:
                 for row in C:
-                    f.write(''.join('%+35.15f  ' % v for v in row) + '\n')
+                    f.write(''.join(java_format_f(v, 35, 15, plus=True) + '  ' for v in row) + '\n')
         self.indices = indices
         return self._base + '.info', self._base + '.cxx'
