@@ -109,8 +109,12 @@ class MatlabResultWriter(BundleAdjustmentResultWriter):
                     else:
                         c = -1
                     dist_rows.append((cam.getId(), p.getParameterType().name.lower(), p.getValue(), order, c))
-        io = np.array(io_rows, dtype=[('cam_id', 'i8'), ('name', 'O'), ('value', 'f8'), ('cov', 'i4')])
-        dist = np.array(dist_rows, dtype=[('cam_id', 'i8'), ('name', 'O'), ('value', 'f8'), ('order', 'i4'), ('cov', 'i4')])
+        # the reference sets the "cov" field of these two structs only when a dispersion matrix is exported (:150-160, :175-187)
+        cov_field = [('cov', 'i4')] if export_disp else []
+        if not export_disp:
+            io_rows, dist_rows = [r[:-1] for r in io_rows], [r[:-1] for r in dist_rows]
+        io = np.array(io_rows, dtype=[('cam_id', 'i8'), ('name', 'O'), ('value', 'f8')] + cov_field)
+        dist = np.array(dist_rows, dtype=[('cam_id', 'i8'), ('name', 'O'), ('value', 'f8'), ('order', 'i4')] + cov_field)
         out = {
             'variance_of_unit_weight_prio': adj.getVarianceFactorApriori(),
             'variance_of_unit_weight_post': adj.getVarianceFactorAposteriori(),

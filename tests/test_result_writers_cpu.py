@@ -101,3 +101,20 @@ def test_matlab_result_writer_variables(tmp_path):
     assert used == list(range(1, idx.size + 1))
     assert int(m['number_of_unknowns'].ravel()[0]) == adj.getNumberOfUnknownParameters()
     assert float(m['variance_of_unit_weight_post'].ravel()[0]) == adj.getVarianceFactorAposteriori()
+
+
+def test_matlab_result_writer_without_cofactor_matrix(tmp_path):
+    """MatrixInversion.NONE: no "dispersion" variable, and -- as in the reference (:150-160, :175-187) -- the interior-orientation and
+    distortion structs carry no "cov" field at all, while the coordinates keep their running covx / covy / covz (:107-135)."""
+    from scipy.io import loadmat
+    adj, _Q = _prepared(11)
+    adj.setInvertNormalEquation(ba.MatrixInversion.NONE)
+    base = str(tmp_path / 'r')
+    ba.MatlabResultWriter(base).export(adj)
+    m = loadmat(base + '.mat')
+    assert 'dispersion' not in m and adj._session.calls == []
+    assert 'cov' not in m['interior_orientations'].dtype.names and 'cov' not in m['distortion_parameters'].dtype.names
+    assert {'cam_id', 'name', 'value'} <= set(m['interior_orientations'].dtype.names)
+    assert {'cam_id', 'name', 'value', 'order'} <= set(m['distortion_parameters'].dtype.names)
+    assert {'name', 'X', 'Y', 'Z', 'covx', 'covy', 'covz'} <= set(m['coordinates'].dtype.names)
+    assert m['coordinates'].shape[0] == 1 and m['interior_orientations'].shape == (1, 3 * len(adj.getCameras()))
