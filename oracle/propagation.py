@@ -12,7 +12,10 @@ entries of a Jacobian block out as scalar expressions (:223-279); here the same 
 were produced by evaluating the reference's own 45 scalar expressions and its transformation formula for seeded random
 inputs (tests/golden/make_formula_fixtures.py -> tests/golden/reference_formulas.npz) and this module matches them to
 1e-12 (tests/test_reference_formulas.py); in addition the Jacobian is checked against central differences
-(tests/test_propagation.py).  What stays a plain restatement is the final product sigma2 * J Qxx J' (:110-114).
+(tests/test_propagation.py).  The function as a whole -- visibility loops, order and names of the transformed points, column
+placement, the final product sigma2 * J Qxx J' (:110-114) in packed upper layout -- is pinned by EXECUTING the reference's transform()
+and setPartialDerivations() (tests/golden/make_transform_fixture.py -> reference_transform.npz; tests/test_reference_transform.py:
+coordinates 1e-13, covariance 1e-12 correlation-scaled).
 """
 from __future__ import annotations
 
