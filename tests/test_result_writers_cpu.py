@@ -118,3 +118,82 @@ def test_matlab_result_writer_without_cofactor_matrix(tmp_path):
     assert {'cam_id', 'name', 'value', 'order'} <= set(m['distortion_parameters'].dtype.names)
     assert {'name', 'X', 'Y', 'Z', 'covx', 'covy', 'covz'} <= set(m['coordinates'].dtype.names)
     assert m['coordinates'].shape[0] == 1 and m['interior_orientations'].shape == (1, 3 * len(adj.getCameras()))
+
+
+# ---- against what the reference's own writer code produced when executed (tests/golden/make_writer_fixture.py) -----------------------------
+def _fixture_network():
+    """The network of make_writer_fixture.network()."""
+    from bundle_adjustment_b200.workloads import synthetic_scene
+    scene = synthetic_scene(2, images=4, targets=14, seed=77, n_cameras=2)[0]
+    fixed = np.array(scene['points']['fixed'], bool).reshape(-1, 3)
+    fixed[2, 1] = fixed[5, 2] = True
+    fixed[9, :] = True
+    scene['points']['fixed'] = fixed
+    scene['cameras'][1]['io_fixed'] = [True, False, False]
+    c0 = scene['cameras'][0]['coefs']
+    scene['cameras'][0]['coefs'] = [(t, o, v, f or (t == 121 and o == 3) or t == 141) for (t, o, v, f) in c0]
+    adj, _pts = build_adjustment(scene)
+    adj._prepare()
+    return adj
+
+
+@pytest.mark.parametrize('tag', ['full', 'none'])
+def test_writers_match_the_executed_reference(tmp_path, tag):
+    """Row f-1 against tests/golden/reference_writers.npz: the arguments the reference's DefaultResultWriter passes to printf (format
+    strings, names, components, values, running indices; every cell of the .cxx matrix) and the variables, struct fields and the
+    dispersion matrix its MatlabResultWriter hands to the MAT-file library -- with and without a cofactor matrix."""
+    import json
+    import os
+
+    from scipy.io import loadmat
+    E = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_writers.npz'))
+    g = lambda k: E['%s__%s' % (tag, k)]
+    adj = _fixture_network()
+    Q = E['Q']
+    assert Q.shape[0] == adj.getNumberOfUnknownParameters() + adj.getNumberOfDatumConditions()
+    adj._session = StubSession(Q)
+    if tag == 'none':
+        adj.setInvertNormalEquation(ba.MatrixInversion.NONE)
+    s2post = 1.25 * adj.getVarianceFactorApriori()                     # what the fixture's stub adjustment reports
+    adj.getVarianceFactorAposteriori = lambda: s2post
+    # DefaultResultWriter
+    base = str(tmp_path / 'd')
+    w = ba.DefaultResultWriter(base)
+    w.export(adj)
+    assert list(w.indices) == list(g('default_indices'))
+    assert list(g('info_format')) == ['%25s\t%5s\t%35.15f\t%10d%n']
+    want = ['%25s\t%5s\t%s\t%10d' % (n, c, java_format_f(v, 35, 15), i)
+            for n, c, v, i in zip(g('info_names'), g('info_comp'), g('info_value'), g('info_index'))]
+    assert open(base + '.info').read().splitlines() == want
+    assert os.path.exists(base + '.cxx') == bool(g('cxx_written'))
+    if bool(g('cxx_written')):
+        assert list(g('cxx_format')) == ['%+35.15f  ', '%n']
+        ref = g('cxx_values')
+        lines = open(base + '.cxx').read().split('\n')
+        assert lines[-1] == '' and len(lines) == ref.shape[0] + 1
+        for line, row in zip(lines, ref):
+            assert line == ''.join(java_format_f(v, 35, 15, plus=True) + '  ' for v in row)
+    # MatlabResultWriter
+    mbase = str(tmp_path / 'm')
+    ba.MatlabResultWriter(mbase).export(adj)
+    assert str(E['%s__mat_path' % tag]).endswith('.mat')
+    m = loadmat(mbase + '.mat')
+    desc = json.loads(str(g('mat_json')))
+    assert [k for k in m if not k.startswith('__')] == list(g('mat_variables'))         # the same variables in the same order
+    scalar = lambda v: np.asarray(v).ravel()[0]
+    for name in ('variance_of_unit_weight_prio', 'variance_of_unit_weight_post', 'degree_of_freedom', 'number_of_observations', 'number_of_unknowns'):
+        kind, val = desc[name]
+        assert scalar(m[name]) == val and str(m[name].dtype) == {'double': 'float64', 'int32': 'int32'}[kind], name
+    for name in ('coordinates', 'interior_orientations', 'distortion_parameters'):
+        d = desc[name]
+        assert list(m[name].shape) == d['shape'], name                                # 1 x N struct arrays
+        assert set(m[name].dtype.names) == set(d['fields']), name                     # "cov" only with a dispersion matrix
+        for f, vals in d['fields'].items():
+            got = [scalar(x) for x in m[name][f].ravel()]
+            assert len(got) == len(vals), (name, f)
+            for a, (kind, b) in zip(got, vals):
+                assert (str(a) == b) if kind == 'string' else (a == b), (name, f, a, b)
+                if kind in ('int32', 'int64'):
+                    assert str(np.asarray(a).dtype) == kind, (name, f)
+    if 'dispersion' in desc:
+        np.testing.assert_array_equal(m['dispersion'], g('mat_dispersion'))
