@@ -94,3 +94,16 @@ def test_ctypes_binding_matches_the_header(built):
         assert f.argtypes is not None, '%s: argtypes not declared' % name
         assert [layout(t) for t in f.argtypes] == args, (name, f.argtypes, args)
         assert layout(f.restype) == ret, (name, f.restype, ret)
+
+
+def test_integration_excerpt_uses_the_names_of_the_shipped_java_sources():
+    """INTEGRATION.md section 3 patches estimateModel() with JaicovB200.<HANDLE> and FlatProblem fields: they exist in bindings/java."""
+    doc = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    java = open(JAVA).read()
+    flat = open(os.path.join(os.path.dirname(JAVA), 'FlatProblem.java')).read()
+    handles = set(re.findall(r'\bJaicovB200\.([A-Z_]+)\b', doc))
+    assert len(handles) >= 12
+    assert not [h for h in handles if not re.search(r'MethodHandle\s+%s\b' % h, java)]
+    fields = set(re.findall(r'\bf\.(\w+)', doc))
+    assert len(fields) >= 25
+    assert not [f for f in fields if not re.search(r'\b%s\b' % f, flat)]
