@@ -59,3 +59,33 @@ def test_bench_line_carries_the_contract_keys():
                 'sample', 'e2e', 'h2d_bytes_per_step', 'd2h_bytes_per_step', 'clocks', 'sm_mhz', 'sm_max_mhz', 'reasons', 'gpu_launches',
                 'impl', 'check'):
         assert "'%s'" % key in src, key
+
+
+def test_oracle_and_reference_stay_out_of_the_product():
+    """oracle/ is test infrastructure: the package, the tools and the C / C++ / CUDA sources never import, link or read it; bench.py only
+    inside its CPU-baseline / reference-arm functions; and nothing that runs on the GPU box reads /root/reference (only the
+    fixture generators under tests/golden/ do, in the build container)."""
+    import glob
+    import re
+    pkg = glob.glob(os.path.join(ROOT, 'bundle-adjustment_b200', '**', '*'), recursive=True)
+    for path in pkg + glob.glob(os.path.join(ROOT, 'tools', '*')) + glob.glob(os.path.join(ROOT, 'include', '*')):
+        if os.path.isfile(path) and path.endswith(('.py', '.cu', '.cuh', '.h', '.hpp', '.cpp', '.sh')):
+            src = open(path).read()
+            assert not re.search(r'^\s*(from|import)\s+oracle\b', src, re.M), path
+            assert 'libjaicov_oracle' not in src and 'jaicov_oracle.c' not in src, path
+            assert not re.search(r'(open|listdir|exists|join|load|glob|walk)\([^\n]*/root/reference', src), path      # citations in comments are fine
+    tree = ast.parse(open(os.path.join(ROOT, 'bench.py')).read())
+    importers = set()
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        for n in ast.walk(fn):
+            if isinstance(n, ast.ImportFrom) and (n.module or '').split('.')[0] == 'oracle':
+                importers.add(fn.name)
+    assert importers and importers <= {'cpu_sample', 'best_effort_cpu', 'reference_arm'}, importers
+    for n in tree.body:                                   # no module-level import of the oracle
+        assert not (isinstance(n, (ast.Import, ast.ImportFrom)) and 'oracle' in ast.dump(n))
+    for path in [os.path.join(ROOT, 'bench.py'), os.path.join(ROOT, '__graft_entry__.py')] + glob.glob(os.path.join(ROOT, 'tests', '*.py')):
+        if os.path.basename(path) == 'test_bench_static.py':
+            continue
+        src = open(path).read()
+        uses = [l for l in src.splitlines() if re.search(r'(open|listdir|exists|join|load|glob|walk)\([^\n]*/root/reference', l)]
+        assert not uses, (path, uses)
